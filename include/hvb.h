@@ -1,0 +1,317 @@
+/*
+ * hvb.h -- batched C-ABI of the B200-native Turing-codec pixel hot path.
+ *
+ * This is the drop-in boundary underneath the reference encoder's havoc function tables
+ * (turing/StateFunctionTables.h:37-102).  The reference calls one primitive on one <=64x64 block
+ * through a C function pointer (havoc/sad.h:56-120, ssd.h:32-52, hadamard.h:31-53,
+ * pred_inter.h:33-106, pred_intra.h:29-60, transform.h:33-146, quantize.h:40-99); this ABI takes a
+ * BATCH of such calls against device-resident pictures, so that a CTU's (or a wavefront's) worth of
+ * PU/TU candidates is one kernel launch.  The literal per-block tables are provided on top of it by
+ * include/havoc_b200.h.
+ *
+ * Conventions
+ *  - extern "C", opaque handle, plain pointers and sizes; no CUDA or torch types.
+ *  - every function returns 0 on success or a negative hvb_status; hvb_last_error() has the text.
+ *  - a context owns one CUDA stream (replaceable with hvb_set_stream) and is used by ONE host
+ *    thread at a time; the reference's pool threads (turing/ThreadPool.cpp:87-103) each own one.
+ *  - `mem` says where the task / result arrays live: HVB_HOST (pageable or pinned host memory, the
+ *    call stages them through pinned buffers and returns after the results have landed) or
+ *    HVB_DEVICE (device pointers; the call only enqueues work on the context's stream).
+ *  - a "picture" is a device-resident planar 4:2:0 picture (Y, Cb, Cr) whose planes are padded on
+ *    all sides like the reference's (turing/StatePictures.h:154-156), so motion vectors may point
+ *    outside the picture exactly as far as the reference allows.
+ *  - all results are bit-exact with the reference's C path (`--asm 0`), including its quirks:
+ *    16-bit SAD >> 2, SSD >> 4 (mod 2^32), SATD >> 2, forward-transform wrap to int16.
+ */
+#ifndef HVB_H
+#define HVB_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hvb_context hvb_context;
+
+typedef enum
+{
+    HVB_OK = 0,
+    HVB_ERR_INVALID = -1,  /* bad argument */
+    HVB_ERR_CUDA = -2,     /* CUDA runtime error (see hvb_last_error) */
+    HVB_ERR_NOMEM = -3,
+    HVB_ERR_NO_DEVICE = -4 /* no usable sm_100 device: there is NO CPU fallback */
+} hvb_status;
+
+typedef enum
+{
+    HVB_HOST = 0,
+    HVB_DEVICE = 1
+} hvb_mem;
+
+/* ---- context ------------------------------------------------------------------------ */
+
+/* bytes_per_sample: 1 (uint8_t pictures, bit_depth 8) or 2 (uint16_t pictures, bit_depth 8..10);
+ * replaces havoc_new_code()/havoc_delete_code() (havoc/havoc.h:143-149). */
+int hvb_create(int device, int bytes_per_sample, int bit_depth, hvb_context **out);
+void hvb_destroy(hvb_context *ctx);
+const char *hvb_last_error(hvb_context *ctx);
+/* use an existing cudaStream_t (passed as void*) for all subsequent work; NULL = own stream */
+int hvb_set_stream(hvb_context *ctx, void *cuda_stream);
+int hvb_sync(hvb_context *ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int64_t hvb_launch_count(hvb_context *ctx);
+/* 1 when the device is present and kernels for it are in this binary */
+int hvb_device_ok(int device);
+
+/* ---- pictures ------------------------------------------------------------------------ */
+
+/* luma width x height; chroma planes are (w/2) x (h/2).  pad = luma padding in samples on every
+ * side (chroma gets pad/2); the reference uses 96 (StatePictures.h:154-156).  */
+int hvb_picture_create(hvb_context *ctx, int width, int height, int pad, int *pic);
+int hvb_picture_destroy(hvb_context *ctx, int pic);
+/* copy rows [y0, y0+rows) of plane cIdx from host (stride in samples) */
+int hvb_picture_upload(hvb_context *ctx, int pic, int cIdx, const void *host, intptr_t stride,
+                       int y0, int rows);
+int hvb_picture_download(hvb_context *ctx, int pic, int cIdx, void *host, intptr_t stride,
+                         int y0, int rows);
+/* replicate edge samples into the padding of all three planes (turing/Padding.h) */
+int hvb_picture_pad(hvb_context *ctx, int pic);
+/* raw device view of a plane: pointer to sample (0,0) and stride in samples (for zero-copy fills) */
+int hvb_picture_plane(hvb_context *ctx, int pic, int cIdx, void **dev_ptr, intptr_t *stride);
+
+/* ---- block metrics (hot loops A, B, C) ------------------------------------------------ */
+
+/* A block of a picture plane.  x,y in samples of that plane; may lie in the padding. */
+typedef struct
+{
+    int16_t pic;
+    int16_t cIdx;
+    int16_t x, y;
+} hvb_block;
+
+/* one candidate of havoc_sad / havoc_ssd / measureSatd: metric(a, b) over w x h */
+typedef struct
+{
+    hvb_block a, b;
+    int16_t w, h;
+    int32_t reserved;
+} hvb_metric_task; /* 24 bytes */
+
+/* havoc_sad<Sample> (havoc/sad.h:58): out[i] = int32 SAD; 16-bit samples: >> 2 */
+int hvb_sad_batch(hvb_context *ctx, const hvb_metric_task *tasks, int n, int32_t *out, hvb_mem mem);
+/* havoc_ssd<Sample> (havoc/ssd.h:33), any w x h: out[i] = uint32 SSD (mod 2^32; 16-bit >> 4) */
+int hvb_ssd_batch(hvb_context *ctx, const hvb_metric_task *tasks, int n, uint32_t *out, hvb_mem mem);
+/* measureSatd (turing/Measure.h:96-135) over havoc_hadamard_satd tiles (havoc/hadamard.h:32) */
+int hvb_satd_batch(hvb_context *ctx, const hvb_metric_task *tasks, int n, int32_t *out, hvb_mem mem);
+
+/* havoc_sad_multiref<Sample> (havoc/sad.h:100): four references, one source block */
+typedef struct
+{
+    hvb_block src;
+    int16_t ref_pic, ref_cIdx;
+    int16_t w, h;
+    int16_t rx[4], ry[4]; /* top-left of each reference block in the reference plane */
+} hvb_sad4_task; /* 32 bytes */
+int hvb_sad4_batch(hvb_context *ctx, const hvb_sad4_task *tasks, int n, int32_t *out /* [n][4] */,
+                   hvb_mem mem);
+
+/* ---- inter prediction (hot loop B) ----------------------------------------------------- */
+
+/* HavocPredUni (havoc/pred_inter.h:35) / HavocPredBi (:63).  Luma (cIdx 0): 8-tap, mv in
+ * quarter-samples; chroma: 4-tap, mv in eighth-samples of the chroma plane (the caller passes
+ * the luma mv unchanged, as turing/Dsp.h:789-812 does).  dst receives w x h samples. */
+typedef struct
+{
+    hvb_block dst;
+    int16_t ref_pic[2]; /* ref_pic[1] < 0 -> uni-prediction */
+    int16_t x, y;       /* block position in the reference plane(s) before displacement */
+    int16_t w, h;
+    int16_t mvx[2], mvy[2];
+    int32_t reserved;
+} hvb_pred_task; /* 32 bytes */
+int hvb_pred_batch(hvb_context *ctx, const hvb_pred_task *tasks, int n, hvb_mem mem);
+
+/* havoc::SubtractBi (havoc/pred_inter.h:87): dst = clip(2*src - pred) */
+typedef struct
+{
+    hvb_block dst, pred, src;
+    int16_t w, h;
+    int32_t reserved;
+} hvb_subtract_bi_task; /* 32 bytes */
+int hvb_subtract_bi_batch(hvb_context *ctx, const hvb_subtract_bi_task *tasks, int n, hvb_mem mem);
+
+/* costDistortionMv (turing/Search.hpp:1965-2000) without the lambda product: interpolate the luma
+ * block at quarter-pel mv and return measureSatd(src, prediction).  Nothing is written back. */
+typedef struct
+{
+    hvb_block src;
+    int16_t ref_pic, reserved0;
+    int16_t w, h;
+    int16_t mvx, mvy; /* quarter-pel */
+} hvb_interp_satd_task; /* 20 bytes */
+int hvb_interp_satd_batch(hvb_context *ctx, const hvb_interp_satd_task *tasks, int n, int32_t *out,
+                          hvb_mem mem);
+
+/* ---- intra prediction (hot loop D) ------------------------------------------------------ */
+
+/* havoc::intra::Function (havoc/pred_intra.h:32).  Neighbours live in a device-resident sample
+ * pool (hvb_pool_upload); `nb` is the index of the sample holding p(-1,-1) so that
+ * p(x,-1) = pool[nb + 1 + x] and p(-1,y) = pool[nb - 1 - y]  (4n+1 samples). */
+int hvb_pool_upload(hvb_context *ctx, const void *samples, size_t count, size_t offset);
+
+typedef struct
+{
+    hvb_block dst;
+    int32_t nb;
+    int8_t log2n, mode, edge_flag, reserved;
+} hvb_intra_task; /* 16 bytes */
+int hvb_intra_pred_batch(hvb_context *ctx, const hvb_intra_task *tasks, int n, hvb_mem mem);
+
+/* 35-mode SATD sweep of searchIntraPartition (turing/Search.hpp:39-267 via
+ * Reconstruct.cpp:630-712): out[i][m] = SATD(src, intra(m)), m = 0..34.  nb_unfiltered /
+ * nb_filtered select the reference array per mode by the filterFlag rule
+ * (turing/IntraReferenceSamples.h filterFlag). */
+typedef struct
+{
+    hvb_block src;
+    int32_t nb_unfiltered, nb_filtered;
+    int8_t log2n, cIdx, reserved[6];
+} hvb_intra_sweep_task; /* 24 bytes */
+int hvb_intra_satd35_batch(hvb_context *ctx, const hvb_intra_sweep_task *tasks, int n,
+                           int32_t *out /* [n][35] */, hvb_mem mem);
+
+/* ---- transform / quantisation (hot loop C) ------------------------------------------------ */
+
+/* raw coefficient-domain primitives over a device-resident int16 pool (hvb_coeff_upload /
+ * hvb_coeff_download); offsets are in int16 elements, blocks are n x n contiguous. */
+int hvb_coeff_upload(hvb_context *ctx, const int16_t *data, size_t count, size_t offset);
+int hvb_coeff_download(hvb_context *ctx, int16_t *data, size_t count, size_t offset);
+
+typedef struct
+{
+    int32_t src, dst;     /* pool offsets */
+    int32_t src_stride;   /* forward transform only: residual stride in elements */
+    int8_t log2n, trType; /* trType 1 = 4x4 DST */
+    int16_t reserved;
+} hvb_transform_task; /* 16 bytes */
+/* havoc::Transform (havoc/transform.h:117) */
+int hvb_transform_fwd_batch(hvb_context *ctx, const hvb_transform_task *tasks, int n, hvb_mem mem);
+/* havoc::inverse_transform (havoc/transform.h:33): residual only */
+int hvb_transform_inv_batch(hvb_context *ctx, const hvb_transform_task *tasks, int n, hvb_mem mem);
+
+typedef struct
+{
+    int32_t src, dst;
+    int32_t n;
+    int32_t scale, shift, offset;
+} hvb_quant_task; /* 24 bytes */
+/* havoc_quantize (havoc/quantize.h:63): cbf[i] = 1 when any output is non-zero, else 0 */
+int hvb_quantize_batch(hvb_context *ctx, const hvb_quant_task *tasks, int n, int32_t *cbf, hvb_mem mem);
+/* havoc_quantize_inverse (havoc/quantize.h:42) */
+int hvb_quantize_inverse_batch(hvb_context *ctx, const hvb_quant_task *tasks, int n, hvb_mem mem);
+
+/* havoc::inverse_transform_add (havoc/transform.h:61): rec = clip(pred + IT(coeffs)) */
+typedef struct
+{
+    hvb_block dst, pred;
+    int32_t coeffs; /* pool offset */
+    int8_t log2n, trType;
+    int16_t reserved;
+} hvb_ita_task; /* 24 bytes */
+int hvb_inverse_transform_add_batch(hvb_context *ctx, const hvb_ita_task *tasks, int n, hvb_mem mem);
+
+/* The whole TU pipeline of ReconstructInterBlock / the intra flavour
+ * (turing/Reconstruct.cpp:180-356, :731-857) for one transform block:
+ *   residual = src - pred; coeffs = T(residual); levels = Q(coeffs) [plain or RDOQ];
+ *   if cbf: rec = clip(pred + IT(IQ(levels))) else rec = pred;  ssd = SSD(src, rec)
+ * levels are written to the coefficient pool at `levels` (n*n int16). */
+typedef struct
+{
+    hvb_block src, pred, rec;
+    int32_t levels;
+    int8_t log2n, trType, cIdx, flags; /* flags bit0: use RDOQ, bit1: isIntra, bit2: SDH */
+    int32_t qscale, qshift, qoffset;   /* forward quantiser (QpState.h) */
+    int32_t iqscale, iqshift;          /* inverse quantiser */
+    int8_t scanIdx, reserved[3];
+    int32_t rdoq_ctx;                  /* index of the RDOQ context snapshot (hvb_rdoq_contexts_upload) */
+} hvb_tu_task; /* 56 bytes */
+
+typedef struct
+{
+    uint32_t ssd;
+    int32_t cbf;
+} hvb_tu_result;
+int hvb_tu_chain_batch(hvb_context *ctx, const hvb_tu_task *tasks, int n, hvb_tu_result *out, hvb_mem mem);
+
+/* RDOQ inputs that are not pixels: a snapshot of the CABAC context states the reference's
+ * Rdoq reads through estimateBits (turing/Rdoq.cpp:26-31) plus lambda.  One snapshot serves many
+ * TUs (the reference snapshots per CU).  Layout: see hvb_rdoq_ctx below. */
+typedef struct
+{
+    uint8_t sig_coeff_flag[44];
+    uint8_t greater1_flag[24];
+    uint8_t greater2_flag[6];
+    uint8_t coded_sub_block_flag[4];
+    uint8_t last_x_prefix[18];
+    uint8_t last_y_prefix[18];
+    uint8_t cbf_luma[2];
+    uint8_t cbf_cbcr[5];
+    uint8_t rqt_root_cbf[1];
+    uint8_t reserved[6];
+    double lambda; /* as passed to Rdoq::Rdoq (turing/Rdoq.h:170) */
+} hvb_rdoq_ctx; /* 136 bytes */
+int hvb_rdoq_contexts_upload(hvb_context *ctx, const hvb_rdoq_ctx *snapshots, int count, int first);
+
+/* Rdoq::runQuantisation alone (turing/Rdoq.cpp:35-450) on pool coefficients */
+typedef struct
+{
+    int32_t src, dst;
+    int32_t qscale, qshift;
+    int32_t iqscale;
+    int8_t log2n, cIdx, scanIdx, flags; /* flags bit1: isIntra, bit2: SDH */
+    int32_t rdoq_ctx;
+} hvb_rdoq_task; /* 28 bytes */
+int hvb_rdoq_batch(hvb_context *ctx, const hvb_rdoq_task *tasks, int n, int32_t *cbf, hvb_mem mem);
+
+/* ---- motion search (hot loops A + B with their control flow) ------------------------------ */
+
+typedef struct
+{
+    int16_t x, y;
+} hvb_mv;
+
+/* One uni-directional PU search: fullPelMotionEstimation (turing/Search.hpp:2064-2336) followed
+ * by subPelRefinement (:2339-2357), as chained by searchMotionUni (:1315-1352).  Everything the
+ * reference reads from encoder state is an explicit input. */
+typedef struct
+{
+    int16_t src_pic, ref_pic;
+    int16_t x0, y0, w, h;        /* PU in luma samples */
+    hvb_mv mvp[2];               /* AMVP predictors, quarter-pel */
+    int64_t rateMvpFlag[2];      /* Cost (Q16) of mvp_lX_flag = 0 / 1 */
+    int32_t lambda;              /* Lambda (Q16): FixedPoint<int32,16>::set(reciprocal sqrt lambda) */
+    hvb_mv limitMin, limitMax;   /* LimitFullPelMv (Search.hpp:1366-1407), full-pel, inclusive */
+    hvb_mv prev2Nx2N;            /* mvPreviousInteger2Nx2N[refList], quarter-pel units */
+    uint8_t smallSearchWindow, met, log2CbSize, usePrev2Nx2N;
+    uint8_t halfPel, quarterPel, reserved[2];
+} hvb_me_task; /* 64 bytes */
+
+typedef struct
+{
+    hvb_mv mv, mvd;              /* after sub-pel refinement when enabled */
+    hvb_mv mvInteger;            /* best integer vector (mvPreviousInteger2Nx2N update) */
+    int32_t mvpFlag;
+    int64_t cost;                /* best integer-search cost (Q16) */
+    int64_t costMvdZero[2];
+    int64_t subpelCost;
+    int32_t nSad, reserved;
+} hvb_me_result; /* 56 bytes */
+int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, int n, hvb_me_result *out, hvb_mem mem);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

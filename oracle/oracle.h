@@ -1,0 +1,155 @@
+/*
+ * oracle/oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C CPU restatement of the Turing codec's pixel hot path (the havoc primitive
+ * library plus the turing/Search + Rdoq loops that drive it).  It exists so that the
+ * CUDA path can be checked bit-for-bit.  Nothing in the product (turingcodec_b200/,
+ * include/) may include, link or call this; only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs do.
+ *
+ * Parity status: PINNED.  Every function below is checked in tests/test_oracle_pin.py
+ * against oracle/_ref/libhavoc_ref.so (the unmodified reference havoc library built by
+ * oracle/Makefile from /root/reference/havoc) on the reference self-test's own input
+ * recipes, and against committed golden vectors in tests/golden/
+ * that were generated from that reference build (tests/golden/make_golden.py).
+ *
+ * Conventions: strides are in SAMPLES (as in the reference), `bps` is bytes per sample
+ * (1 -> uint8_t planes, 2 -> uint16_t planes).  Each function cites the reference body
+ * it restates.
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- distortion metrics ------------------------------------------------------------ */
+
+/* havoc/sad.cpp:432-449 (havoc_sad_c_ref): sum |src-ref| over w x h; 16-bit result >>= 2. */
+int orc_sad(const void *src, intptr_t stride_src, const void *ref, intptr_t stride_ref,
+            int w, int h, int bps);
+
+/* havoc/sad.cpp:513-542 (havoc_sad_multiref_4_c_ref): four SADs sharing one source block. */
+void orc_sad_multiref4(const void *src, intptr_t stride_src, const void *const ref[4],
+                       intptr_t stride_ref, int sad[4], int w, int h, int bps);
+
+/* havoc/ssd.cpp:28-43 (havoc_ssd_c_ref): sum (a-b)^2 mod 2^32; 16-bit result >>= 4. */
+uint32_t orc_ssd(const void *a, intptr_t stride_a, const void *b, intptr_t stride_b,
+                 int w, int h, int bps);
+
+/* havoc/diff.cpp:29-38 (havoc_ssd_linear_c_ref). */
+int orc_ssd_linear(const uint8_t *a, const uint8_t *b, int n);
+
+/* havoc/hadamard.cpp:58-98 (compute_satd_c_ref<n>): n = 1<<log2n in {2,4,8}. */
+int orc_hadamard_satd(const void *a, intptr_t stride_a, const void *b, intptr_t stride_b,
+                      int log2n, int bps);
+
+/* turing/Measure.h:96-135 (measureSatd): tiles a w x h block with 8x8, 4x4 or 2x2 SATDs. */
+int32_t orc_measure_satd(const void *a, intptr_t stride_a, const void *b, intptr_t stride_b,
+                         int w, int h, int bps);
+
+/* ---- inter prediction --------------------------------------------------------------- */
+
+/* havoc/pred_inter.cpp:39-69 (havoc_pred_coefficient). */
+int orc_pred_coefficient(int taps, int frac, int k);
+
+/* havoc/pred_inter.cpp:76-202: copy / h / v / hv uni-prediction, taps = 8 (luma) or 4 (chroma). */
+void orc_pred_uni(void *dst, intptr_t stride_dst, const void *ref, intptr_t stride_ref,
+                  int w, int h, int xFrac, int yFrac, int bitDepth, int taps, int bps);
+
+/* havoc/pred_inter.cpp:1207-1252 (havocPredBi_c_ref). */
+void orc_pred_bi(void *dst, intptr_t stride_dst, const void *ref0, const void *ref1,
+                 intptr_t stride_ref, int w, int h, int xFrac0, int yFrac0, int xFrac1, int yFrac1,
+                 int bitDepth, int taps, int bps);
+
+/* havoc/pred_inter.cpp:2063-2080 (subtractBi_c_ref): dst = clip(2*src - pred). */
+void orc_subtract_bi(void *dst, intptr_t stride_dst, const void *pred, intptr_t stride_pred,
+                     const void *src, intptr_t stride_src, int w, int h, int bitDepth, int bps);
+
+/* ---- intra prediction ---------------------------------------------------------------- */
+
+/* havoc/pred_intra.cpp:43-51,76-98,20282-20401: planar(0) / DC(1) / angular(2..34).
+ * `neighbours` points at the sample above-left+1, i.e. p(x,y) = neighbours[x - y - 1].
+ * edge_flag selects the cIdx==0 && log2<5 filtered variants (pred_intra.h:41-49). */
+void orc_pred_intra(void *dst, intptr_t stride_dst, const void *neighbours, int mode,
+                    int log2n, int bitDepth, int edge_flag, int bps);
+
+/* ---- transform / quantisation -------------------------------------------------------- */
+
+/* havoc/transform.cpp:3071-3397: forward DCT-II (trType 0, log2n 2..5) or DST-VII (trType 1, 4x4).
+ * Each pass result is truncated to int16 with wrap-around (shiftRight, :3071-3084). */
+void orc_transform_fwd(int16_t *coeffs, const int16_t *src, intptr_t stride_src,
+                       int trType, int log2n, int bitDepth);
+
+/* havoc/transform.cpp:50-401 + transform.h:104-114: inverse transform, add to pred, clip. */
+void orc_inverse_transform_add(void *dst, intptr_t stride_dst, const void *pred, intptr_t stride_pred,
+                               const int16_t *coeffs, int trType, int log2n, int bitDepth, int bps);
+
+/* residual-only inverse (havoc::inverse_transform, transform.cpp:2861-2868 table) */
+void orc_inverse_transform(int16_t *res, const int16_t *coeffs, int trType, int log2n, int bitDepth);
+
+/* havoc/quantize.cpp:278-304 (havoc_quantize_c_ref); returns OR of outputs (only ==0 is meaningful). */
+int orc_quantize(int16_t *dst, const int16_t *src, int scale, int shift, int offset, int n);
+
+/* havoc/quantize.cpp:37-46 (havoc_quantize_inverse_c_ref). */
+void orc_quantize_inverse(int16_t *dst, const int16_t *src, int scale, int shift, int n);
+
+/* havoc/quantize.cpp:538-548 (havoc_quantize_reconstruct_c_ref). */
+void orc_quantize_reconstruct(uint8_t *rec, intptr_t stride_rec, const uint8_t *pred,
+                              intptr_t stride_pred, const int16_t *res, int n);
+
+/* ---- motion search (turing/Search.hpp) ------------------------------------------------ */
+
+typedef struct
+{
+    int16_t x, y;
+} orc_mv;
+
+typedef struct
+{
+    /* block, in luma samples relative to the plane origin */
+    int x0, y0, w, h;
+    /* AMVP predictors (quarter-pel) and the rate of mvp_lX_flag = 0 / 1 as Cost (Q16, int64) */
+    orc_mv mvp[2];
+    int64_t rateMvpFlag[2];
+    /* Lambda (Q16 int32) = FixedPoint<int32,16>::set(getReciprocalSqrtLambda) */
+    int32_t lambda;
+    /* LimitFullPelMv (Search.hpp:1366-1407): inclusive full-pel limits */
+    orc_mv limitMin, limitMax;
+    /* switches (Search.hpp:2088-2094, :2116-2126) */
+    int smallSearchWindow; /* speed->useSmallSearchWindow() */
+    int met;               /* stateEncode->met */
+    int log2CbSize;
+    int usePrev2Nx2N;      /* PartMode != 2Nx2N || cqtDepth != 0 */
+    orc_mv prev2Nx2N;      /* mvPreviousInteger2Nx2N[refList] */
+    int halfPel, quarterPel; /* Speed::doHalfPelRefinement / doQuarterPelRefinement */
+    int bitDepth;
+} orc_me_task;
+
+typedef struct
+{
+    orc_mv mv, mvd;
+    int64_t cost;        /* best integer candidate cost (Q16) */
+    int mvpFlag;
+    int64_t costMvdZero[2];
+    int64_t subpelCost;  /* bestCost after subPelRefinement (valid when halfPel) */
+    int nSad;            /* number of SAD evaluations performed (statistics only) */
+} orc_me_result;
+
+/* turing/Search.hpp:2064-2336 (fullPelMotionEstimation) followed by :2339-2357 (subPelRefinement)
+ * as chained in searchMotionUni (:1315-1352).  src/ref are plane origins (sample (0,0)). */
+void orc_me_search(const void *srcPlane, intptr_t stride_src, const void *refPlane, intptr_t stride_ref,
+                   const orc_me_task *task, orc_me_result *out, int bps);
+
+/* turing/Measure.h:177-220: rateOf(mvd) as a Q16 Cost. */
+int64_t orc_rate_of_mvd(int dx, int dy);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

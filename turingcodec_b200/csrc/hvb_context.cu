@@ -1,0 +1,409 @@
+// hvb_context.cu -- context, device-resident pictures, pools and host<->device staging.
+//
+// Replaces the reference's havoc_code life cycle (havoc/havoc.h:138-149, havoc.cpp:144-155) and gives
+// the batched kernels what the reference gets from plain CPU pointers: source pictures
+// (turing/encode.cpp:363-451 copies planes into PictureWrap) and padded reconstructed pictures
+// (turing/StatePictures.h:154-156, Padding.h) living in HBM.
+#include "hvb_internal.cuh"
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+static_assert(sizeof(hvb_block) == 8, "abi");
+static_assert(sizeof(hvb_metric_task) == 24, "abi");
+static_assert(sizeof(hvb_sad4_task) == 32, "abi");
+static_assert(sizeof(hvb_pred_task) == 32, "abi");
+static_assert(sizeof(hvb_subtract_bi_task) == 32, "abi");
+static_assert(sizeof(hvb_interp_satd_task) == 20, "abi");
+static_assert(sizeof(hvb_intra_task) == 16, "abi");
+static_assert(sizeof(hvb_intra_sweep_task) == 24, "abi");
+static_assert(sizeof(hvb_transform_task) == 16, "abi");
+static_assert(sizeof(hvb_quant_task) == 24, "abi");
+static_assert(sizeof(hvb_ita_task) == 24, "abi");
+static_assert(sizeof(hvb_tu_task) == 60, "abi");
+static_assert(sizeof(hvb_tu_result) == 8, "abi");
+static_assert(sizeof(hvb_rdoq_ctx) == 136, "abi");
+static_assert(sizeof(hvb_rdoq_task) == 28, "abi");
+static_assert(sizeof(hvb_me_task) == 64, "abi");
+static_assert(sizeof(hvb_me_result) == 56, "abi");
+
+int hvbFail(hvb_context *ctx, int status, const char *what)
+{
+    if (ctx) ctx->lastError = what;
+    return status;
+}
+
+int hvbCuda(hvb_context *ctx, cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return HVB_OK;
+    if (ctx)
+    {
+        ctx->lastError = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    }
+    return e == cudaErrorMemoryAllocation ? HVB_ERR_NOMEM : HVB_ERR_CUDA;
+}
+
+extern "C" int hvb_device_ok(int device)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return 0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 0;
+    return prop.major == 10 ? 1 : 0; // kernels are compiled for sm_100a only
+}
+
+extern "C" int hvb_create(int device, int bytes_per_sample, int bit_depth, hvb_context **out)
+{
+    if (!out) return HVB_ERR_INVALID;
+    *out = nullptr;
+    if (bytes_per_sample != 1 && bytes_per_sample != 2) return HVB_ERR_INVALID;
+    if (bit_depth < 8 || bit_depth > (bytes_per_sample == 1 ? 8 : 10)) return HVB_ERR_INVALID;
+    // No CPU fallback: without a Blackwell device the product path fails loudly.
+    if (!hvb_device_ok(device)) return HVB_ERR_NO_DEVICE;
+
+    hvb_context *ctx = new (std::nothrow) hvb_context;
+    if (!ctx) return HVB_ERR_NOMEM;
+    ctx->device = device;
+    ctx->bps = bytes_per_sample;
+    ctx->bitDepth = bit_depth;
+
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->dPlanes, sizeof(HvbPlane) * HVB_MAX_PICTURES * 3);
+    if (e == cudaSuccess) e = cudaMemset(ctx->dPlanes, 0, sizeof(HvbPlane) * HVB_MAX_PICTURES * 3);
+    int sms = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess)
+    {
+        hvb_destroy(ctx);
+        return HVB_ERR_CUDA;
+    }
+    ctx->smCount = sms;
+    ctx->stream = ctx->ownStream;
+    *out = ctx;
+    return HVB_OK;
+}
+
+extern "C" void hvb_destroy(hvb_context *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &p : ctx->pictures)
+        for (int c = 0; c < 3; ++c)
+            if (p.alloc[c]) cudaFree(p.alloc[c]);
+    if (ctx->dPlanes) cudaFree(ctx->dPlanes);
+    if (ctx->hostStage) cudaFreeHost(ctx->hostStage);
+    if (ctx->devStage) cudaFree(ctx->devStage);
+    if (ctx->samplePool) cudaFree(ctx->samplePool);
+    if (ctx->coeffPool) cudaFree(ctx->coeffPool);
+    if (ctx->rdoqCtx) cudaFree(ctx->rdoqCtx);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+    delete ctx;
+}
+
+extern "C" const char *hvb_last_error(hvb_context *ctx) { return ctx ? ctx->lastError.c_str() : "null context"; }
+
+extern "C" int hvb_set_stream(hvb_context *ctx, void *cuda_stream)
+{
+    if (!ctx) return HVB_ERR_INVALID;
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->ownStream;
+    return HVB_OK;
+}
+
+extern "C" int hvb_sync(hvb_context *ctx)
+{
+    if (!ctx) return HVB_ERR_INVALID;
+    return hvbCuda(ctx, cudaStreamSynchronize(ctx->stream), "hvb_sync");
+}
+
+extern "C" int64_t hvb_launch_count(hvb_context *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// Pictures
+// ---------------------------------------------------------------------------------------------
+
+extern "C" int hvb_picture_create(hvb_context *ctx, int width, int height, int pad, int *pic)
+{
+    HVB_CHECK_ARGS(ctx, pic && width > 0 && height > 0 && pad >= 0 && !(width & 1) && !(height & 1) && !(pad & 1));
+    int id = -1;
+    for (int i = 0; i < HVB_MAX_PICTURES; ++i)
+        if (!ctx->pictures[i].live)
+        {
+            id = i;
+            break;
+        }
+    if (id < 0) return hvbFail(ctx, HVB_ERR_NOMEM, "picture table full");
+    cudaSetDevice(ctx->device);
+    HvbPicture &p = ctx->pictures[id];
+    p.width = width;
+    p.height = height;
+    p.pad = pad;
+    for (int c = 0; c < 3; ++c)
+    {
+        const int w = c ? width / 2 : width, h = c ? height / 2 : height, pd = c ? pad / 2 : pad;
+        // row pitch: multiple of 256 bytes; left padding rounded up so that sample (0,0) of each row is
+        // 256-byte aligned (source rows are then always 128-bit loadable).
+        const size_t padLeft = ((size_t)pd * ctx->bps + 255) / 256 * 256 / ctx->bps;
+        const size_t strideSamples = (padLeft + w + pd + 16 + (256 / ctx->bps - 1)) / (256 / ctx->bps) * (256 / ctx->bps);
+        const size_t rows = (size_t)h + 2 * pd + 2; // +2 slack rows: vector loads may run a few bytes past a block
+        const size_t bytes = strideSamples * rows * ctx->bps;
+        cudaError_t e = cudaMalloc(&p.alloc[c], bytes);
+        if (e != cudaSuccess)
+        {
+            for (int k = 0; k < c; ++k)
+            {
+                cudaFree(p.alloc[k]);
+                p.alloc[k] = nullptr;
+            }
+            return hvbCuda(ctx, e, "hvb_picture_create");
+        }
+        cudaMemsetAsync(p.alloc[c], 0, bytes, ctx->stream);
+        p.allocBytes[c] = bytes;
+        p.plane[c].base = static_cast<char *>(p.alloc[c]) + ((size_t)pd * strideSamples + padLeft) * ctx->bps;
+        p.plane[c].stride = (int32_t)strideSamples;
+        p.plane[c].width = w;
+        p.plane[c].height = h;
+        p.plane[c].pad = pd;
+        p.plane[c].reserved = 0;
+    }
+    p.live = true;
+    ctx->planesDirty = true;
+    *pic = id;
+    return HVB_OK;
+}
+
+extern "C" int hvb_picture_destroy(hvb_context *ctx, int pic)
+{
+    HVB_CHECK_ARGS(ctx, pic >= 0 && pic < HVB_MAX_PICTURES && ctx->pictures[pic].live);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    HvbPicture &p = ctx->pictures[pic];
+    for (int c = 0; c < 3; ++c)
+    {
+        cudaFree(p.alloc[c]);
+        p.alloc[c] = nullptr;
+    }
+    p.live = false;
+    ctx->planesDirty = true;
+    return HVB_OK;
+}
+
+int hvbSyncPlanes(hvb_context *ctx)
+{
+    if (!ctx->planesDirty) return HVB_OK;
+    std::vector<HvbPlane> host(HVB_MAX_PICTURES * 3);
+    memset(host.data(), 0, host.size() * sizeof(HvbPlane));
+    for (int i = 0; i < HVB_MAX_PICTURES; ++i)
+        if (ctx->pictures[i].live)
+            for (int c = 0; c < 3; ++c) host[i * 3 + c] = ctx->pictures[i].plane[c];
+    // synchronous small copy: the table changes only when pictures are created or destroyed
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(ctx->dPlanes, host.data(), host.size() * sizeof(HvbPlane), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return hvbCuda(ctx, e, "hvbSyncPlanes");
+    ctx->planesDirty = false;
+    return HVB_OK;
+}
+
+static int planeCopy(hvb_context *ctx, int pic, int cIdx, void *host, intptr_t stride, int y0, int rows, bool upload)
+{
+    HVB_CHECK_ARGS(ctx, pic >= 0 && pic < HVB_MAX_PICTURES && ctx->pictures[pic].live && cIdx >= 0 && cIdx < 3 && host);
+    const HvbPlane &pl = ctx->pictures[pic].plane[cIdx];
+    HVB_CHECK_ARGS(ctx, y0 >= 0 && rows >= 0 && y0 + rows <= pl.height && stride >= pl.width);
+    if (!rows) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    char *dev = static_cast<char *>(pl.base) + (size_t)y0 * pl.stride * ctx->bps;
+    char *h = static_cast<char *>(host) + (size_t)y0 * stride * ctx->bps;
+    cudaError_t e;
+    if (upload)
+        e = cudaMemcpy2DAsync(dev, (size_t)pl.stride * ctx->bps, h, (size_t)stride * ctx->bps,
+                              (size_t)pl.width * ctx->bps, rows, cudaMemcpyHostToDevice, ctx->stream);
+    else
+        e = cudaMemcpy2DAsync(h, (size_t)stride * ctx->bps, dev, (size_t)pl.stride * ctx->bps,
+                              (size_t)pl.width * ctx->bps, rows, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // host buffer may be pageable
+    return hvbCuda(ctx, e, upload ? "hvb_picture_upload" : "hvb_picture_download");
+}
+
+extern "C" int hvb_picture_upload(hvb_context *ctx, int pic, int cIdx, const void *host, intptr_t stride, int y0, int rows)
+{
+    return planeCopy(ctx, pic, cIdx, const_cast<void *>(host), stride, y0, rows, true);
+}
+
+extern "C" int hvb_picture_download(hvb_context *ctx, int pic, int cIdx, void *host, intptr_t stride, int y0, int rows)
+{
+    return planeCopy(ctx, pic, cIdx, host, stride, y0, rows, false);
+}
+
+extern "C" int hvb_picture_plane(hvb_context *ctx, int pic, int cIdx, void **dev_ptr, intptr_t *stride)
+{
+    HVB_CHECK_ARGS(ctx, pic >= 0 && pic < HVB_MAX_PICTURES && ctx->pictures[pic].live && cIdx >= 0 && cIdx < 3);
+    if (dev_ptr) *dev_ptr = ctx->pictures[pic].plane[cIdx].base;
+    if (stride) *stride = ctx->pictures[pic].plane[cIdx].stride;
+    return HVB_OK;
+}
+
+// Edge replication (turing/Padding.h): every padding sample takes the value of the nearest picture sample.
+template <typename Sample>
+__global__ void padKernel(HvbPlane pl)
+{
+    const int W = pl.width + 2 * pl.pad, H = pl.height + 2 * pl.pad;
+    Sample *base = reinterpret_cast<Sample *>(pl.base);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < W * H; idx += gridDim.x * blockDim.x)
+    {
+        const int x = idx % W - pl.pad, y = idx / W - pl.pad;
+        if (x >= 0 && x < pl.width && y >= 0 && y < pl.height) continue;
+        const int sx = min(max(x, 0), pl.width - 1), sy = min(max(y, 0), pl.height - 1);
+        base[(intptr_t)y * pl.stride + x] = base[(intptr_t)sy * pl.stride + sx];
+    }
+}
+
+extern "C" int hvb_picture_pad(hvb_context *ctx, int pic)
+{
+    HVB_CHECK_ARGS(ctx, pic >= 0 && pic < HVB_MAX_PICTURES && ctx->pictures[pic].live);
+    cudaSetDevice(ctx->device);
+    for (int c = 0; c < 3; ++c)
+    {
+        const HvbPlane &pl = ctx->pictures[pic].plane[c];
+        if (!pl.pad) continue;
+        const int blocks = ctx->smCount * 4;
+        if (ctx->bps == 1)
+            padKernel<uint8_t><<<blocks, 256, 0, ctx->stream>>>(pl);
+        else
+            padKernel<uint16_t><<<blocks, 256, 0, ctx->stream>>>(pl);
+        HVB_LAUNCH_CHECK(ctx, "padKernel");
+    }
+    return HVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pools and staging
+// ---------------------------------------------------------------------------------------------
+
+template <typename T>
+static int growDevice(hvb_context *ctx, T **ptr, size_t *have, size_t want, size_t elemBytes, const char *what)
+{
+    if (*have >= want) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    size_t cap = *have ? *have : 1024;
+    while (cap < want) cap *= 2;
+    void *fresh = nullptr;
+    cudaError_t e = cudaMalloc(&fresh, cap * elemBytes);
+    if (e != cudaSuccess) return hvbCuda(ctx, e, what);
+    cudaStreamSynchronize(ctx->stream);
+    if (*ptr)
+    {
+        cudaMemcpy(fresh, *ptr, *have * elemBytes, cudaMemcpyDeviceToDevice);
+        cudaFree(*ptr);
+    }
+    cudaMemset(static_cast<char *>(fresh) + *have * elemBytes, 0, (cap - *have) * elemBytes);
+    *ptr = static_cast<T *>(fresh);
+    *have = cap;
+    return HVB_OK;
+}
+
+int hvbEnsureScratch(hvb_context *ctx, size_t bytes)
+{
+    return growDevice(ctx, reinterpret_cast<char **>(&ctx->scratch), &ctx->scratchBytes, bytes, 1, "scratch");
+}
+
+int hvbEnsureCoeffPool(hvb_context *ctx, size_t count)
+{
+    return growDevice(ctx, &ctx->coeffPool, &ctx->coeffPoolCount, count, sizeof(int16_t), "coeff pool");
+}
+
+int hvbEnsureSamplePool(hvb_context *ctx, size_t count)
+{
+    return growDevice(ctx, reinterpret_cast<char **>(&ctx->samplePool), &ctx->samplePoolCount, count, (size_t)ctx->bps,
+                      "sample pool");
+}
+
+extern "C" int hvb_pool_upload(hvb_context *ctx, const void *samples, size_t count, size_t offset)
+{
+    HVB_CHECK_ARGS(ctx, samples || !count);
+    int rc = hvbEnsureSamplePool(ctx, offset + count + 64);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(static_cast<char *>(ctx->samplePool) + offset * ctx->bps, samples, count * ctx->bps,
+                                    cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    return hvbCuda(ctx, e, "hvb_pool_upload");
+}
+
+extern "C" int hvb_coeff_upload(hvb_context *ctx, const int16_t *data, size_t count, size_t offset)
+{
+    HVB_CHECK_ARGS(ctx, data || !count);
+    int rc = hvbEnsureCoeffPool(ctx, offset + count);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(ctx->coeffPool + offset, data, count * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    return hvbCuda(ctx, e, "hvb_coeff_upload");
+}
+
+extern "C" int hvb_coeff_download(hvb_context *ctx, int16_t *data, size_t count, size_t offset)
+{
+    HVB_CHECK_ARGS(ctx, (data || !count) && offset + count <= ctx->coeffPoolCount);
+    cudaError_t e = cudaMemcpyAsync(data, ctx->coeffPool + offset, count * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    return hvbCuda(ctx, e, "hvb_coeff_download");
+}
+
+extern "C" int hvb_rdoq_contexts_upload(hvb_context *ctx, const hvb_rdoq_ctx *snapshots, int count, int first)
+{
+    HVB_CHECK_ARGS(ctx, snapshots && count > 0 && first >= 0);
+    size_t have = (size_t)ctx->rdoqCtxCount;
+    int rc = growDevice(ctx, &ctx->rdoqCtx, &have, (size_t)first + count, sizeof(hvb_rdoq_ctx), "rdoq contexts");
+    if (rc) return rc;
+    ctx->rdoqCtxCount = (int)have;
+    cudaError_t e = cudaMemcpyAsync(ctx->rdoqCtx + first, snapshots, sizeof(hvb_rdoq_ctx) * count, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    return hvbCuda(ctx, e, "hvb_rdoq_contexts_upload");
+}
+
+int hvbStageIn(hvb_context *ctx, const void *tasks, size_t inBytes, void *out, size_t outBytes, hvb_mem mem, HvbStaged *st)
+{
+    int rc = hvbSyncPlanes(ctx);
+    if (rc) return rc;
+    if (mem == HVB_DEVICE)
+    {
+        st->dTasks = tasks;
+        st->dOut = out;
+        return HVB_OK;
+    }
+    cudaSetDevice(ctx->device);
+    const size_t inPad = (inBytes + 255) & ~size_t(255);
+    const size_t total = inPad + ((outBytes + 255) & ~size_t(255));
+    if (ctx->hostStageBytes < total)
+    {
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->hostStage) cudaFreeHost(ctx->hostStage);
+        if (ctx->devStage) cudaFree(ctx->devStage);
+        ctx->hostStage = ctx->devStage = nullptr;
+        ctx->hostStageBytes = ctx->devStageBytes = 0;
+        size_t cap = 1 << 20;
+        while (cap < total) cap *= 2;
+        cudaError_t e = cudaMallocHost(&ctx->hostStage, cap);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->devStage, cap);
+        if (e != cudaSuccess) return hvbCuda(ctx, e, "staging buffers");
+        ctx->hostStageBytes = ctx->devStageBytes = cap;
+    }
+    memcpy(ctx->hostStage, tasks, inBytes);
+    cudaError_t e = cudaMemcpyAsync(ctx->devStage, ctx->hostStage, inBytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return hvbCuda(ctx, e, "stage in");
+    st->dTasks = ctx->devStage;
+    st->dOut = static_cast<char *>(ctx->devStage) + inPad;
+    st->hOutPinned = static_cast<char *>(ctx->hostStage) + inPad;
+    return HVB_OK;
+}
+
+int hvbStageOut(hvb_context *ctx, void *out, size_t outBytes, hvb_mem mem, const HvbStaged &st)
+{
+    if (mem == HVB_DEVICE) return HVB_OK;
+    cudaError_t e = cudaSuccess;
+    if (outBytes) e = cudaMemcpyAsync(st.hOutPinned, st.dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return hvbCuda(ctx, e, "stage out");
+    if (outBytes) memcpy(out, st.hOutPinned, outBytes);
+    return HVB_OK;
+}

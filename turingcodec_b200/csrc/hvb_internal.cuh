@@ -1,0 +1,152 @@
+// hvb_internal.cuh -- shared host/device definitions of libhvb (not part of the public ABI).
+#pragma once
+
+#include "../../include/hvb.h"
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+// ---------------------------------------------------------------------------------------------
+// Device-side view of a picture plane.  `base` points at sample (0,0); samples at negative
+// coordinates down to -pad and beyond width/height up to +pad are valid memory (edge padding).
+// Rows are `stride` samples apart; stride*bps is a multiple of 256 bytes and base-pad*bps is
+// 256-byte aligned, so TMA descriptors and 128-bit loads on row starts are legal.
+// ---------------------------------------------------------------------------------------------
+struct HvbPlane
+{
+    void *base;
+    int32_t stride; // in samples
+    int32_t width, height;
+    int32_t pad;
+    int32_t reserved;
+};
+
+static const int HVB_MAX_PICTURES = 256;
+
+struct HvbPicture
+{
+    bool live = false;
+    int width = 0, height = 0, pad = 0;
+    void *alloc[3] = {nullptr, nullptr, nullptr};
+    size_t allocBytes[3] = {0, 0, 0};
+    HvbPlane plane[3];
+};
+
+struct hvb_context
+{
+    int device = 0;
+    int bps = 1;
+    int bitDepth = 8;
+    int smCount = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t ownStream = nullptr;
+    int64_t launches = 0;
+    std::string lastError;
+
+    HvbPicture pictures[HVB_MAX_PICTURES];
+    HvbPlane *dPlanes = nullptr; // [HVB_MAX_PICTURES*3] mirrored on device
+    bool planesDirty = true;
+
+    // staging for HVB_HOST calls
+    void *hostStage = nullptr;  // pinned
+    size_t hostStageBytes = 0;
+    void *devStage = nullptr;
+    size_t devStageBytes = 0;
+
+    // pools
+    void *samplePool = nullptr; // neighbour samples (bps each)
+    size_t samplePoolCount = 0;
+    int16_t *coeffPool = nullptr;
+    size_t coeffPoolCount = 0;
+    hvb_rdoq_ctx *rdoqCtx = nullptr;
+    int rdoqCtxCount = 0;
+    void *scratch = nullptr; // kernel workspace (RDOQ per-TU state, ...)
+    size_t scratchBytes = 0;
+};
+
+// --- host helpers (hvb_context.cu) -----------------------------------------------------------
+int hvbFail(hvb_context *ctx, int status, const char *what);
+int hvbCuda(hvb_context *ctx, cudaError_t e, const char *what);
+int hvbSyncPlanes(hvb_context *ctx);
+int hvbEnsureScratch(hvb_context *ctx, size_t bytes);
+int hvbEnsureCoeffPool(hvb_context *ctx, size_t count);
+int hvbEnsureSamplePool(hvb_context *ctx, size_t count);
+
+// Stage `inBytes` of tasks to the device when mem == HVB_HOST and reserve `outBytes` of device
+// result space behind them.  Returns device pointers for both.
+struct HvbStaged
+{
+    const void *dTasks = nullptr;
+    void *dOut = nullptr;
+    void *hOutPinned = nullptr;
+};
+int hvbStageIn(hvb_context *ctx, const void *tasks, size_t inBytes, void *out, size_t outBytes,
+               hvb_mem mem, HvbStaged *st);
+int hvbStageOut(hvb_context *ctx, void *out, size_t outBytes, hvb_mem mem, const HvbStaged &st);
+
+#define HVB_CHECK_ARGS(ctx, cond)                                                   \
+    do                                                                              \
+    {                                                                               \
+        if (!(ctx)) return HVB_ERR_INVALID;                                         \
+        if (!(cond)) return hvbFail((ctx), HVB_ERR_INVALID, "invalid argument: " #cond); \
+    } while (0)
+
+#define HVB_LAUNCH_CHECK(ctx, name)                                 \
+    do                                                              \
+    {                                                               \
+        (ctx)->launches++;                                          \
+        cudaError_t e__ = cudaGetLastError();                       \
+        if (e__ != cudaSuccess) return hvbCuda((ctx), e__, name);   \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+template <typename Sample>
+__device__ __forceinline__ const Sample *hvbBlockPtr(const HvbPlane *planes, const hvb_block &b, int &stride)
+{
+    const HvbPlane &p = planes[b.pic * 3 + b.cIdx];
+    stride = p.stride;
+    return reinterpret_cast<const Sample *>(p.base) + (intptr_t)b.y * p.stride + b.x;
+}
+
+template <typename Sample>
+__device__ __forceinline__ Sample *hvbBlockPtrW(const HvbPlane *planes, const hvb_block &b, int &stride)
+{
+    const HvbPlane &p = planes[b.pic * 3 + b.cIdx];
+    stride = p.stride;
+    return reinterpret_cast<Sample *>(p.base) + (intptr_t)b.y * p.stride + b.x;
+}
+
+__device__ __forceinline__ int hvbWarpSum(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ unsigned hvbWarpSumU(unsigned v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int hvbClip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Unaligned 4 x u8 load: two aligned 32-bit loads and a byte funnel.
+__device__ __forceinline__ uint32_t hvbLoad4u8(const uint8_t *p)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+    const unsigned sh = (unsigned)(a & 3);
+    const uint32_t lo = __ldg(q);
+    if (sh == 0) return lo;
+    const uint32_t hi = __ldg(q + 1);
+    return __funnelshift_r(lo, hi, sh * 8);
+}
+
+#endif // __CUDACC__

@@ -1,0 +1,342 @@
+// hvb_metrics.cu -- batched SAD / SAD4 / SSD / Hadamard-SATD over device-resident pictures.
+//
+// Reference semantics (bit-exact, see oracle/oracle_havoc.c for the CPU restatement):
+//   havoc_sad           havoc/sad.cpp:432-449     (u16: >> 2)
+//   havoc_sad_multiref  havoc/sad.cpp:513-542     (4 references, u16: each >> 2)
+//   havoc_ssd           havoc/ssd.cpp:28-43       (uint32 wrap, u16: >> 4)
+//   havoc_hadamard_satd havoc/hadamard.cpp:58-98  (2x2 / 4x4 (s+1)>>1 / 8x8 (s+2)>>2, u16: >> 2)
+//   measureSatd         turing/Measure.h:96-135   (tiling of a w x h block)
+//
+// Mapping: one warp per candidate.  These kernels are pure streaming reductions (every sample is
+// read once per candidate), so the bound is memory: 2*w*h*B algorithmic bytes per candidate
+// (5*w*h*B for SAD4).  Source rows are 4-byte aligned by construction (PU x0 is a multiple of 4,
+// plane rows are 256-byte aligned); reference rows are arbitrarily aligned and are read as two
+// aligned words + funnel shift.  Byte lanes are reduced with the SIMD-in-word video instructions
+// (VABSDIFF4 / dp4a), then a 5-step shuffle tree.
+#include "hvb_internal.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+template <typename Sample>
+__device__ __forceinline__ int sadBlock(const Sample *a, int sa, const Sample *b, int sb, int w, int h, int lane)
+{
+    int acc = 0;
+    if (sizeof(Sample) == 1 && !(w & 3))
+    {
+        const int wq = w >> 2, total = wq * h;
+        for (int i = lane; i < total; i += 32)
+        {
+            const int y = i / wq, x = (i - y * wq) << 2;
+            const uint32_t va = hvbLoad4u8(reinterpret_cast<const uint8_t *>(a) + y * sa + x);
+            const uint32_t vb = hvbLoad4u8(reinterpret_cast<const uint8_t *>(b) + y * sb + x);
+            acc = __vsadu4(va, vb) + acc;
+        }
+    }
+    else
+    {
+        const int total = w * h;
+        for (int i = lane; i < total; i += 32)
+        {
+            const int y = i / w, x = i - y * w;
+            acc += abs((int)a[y * sa + x] - (int)b[y * sb + x]);
+        }
+    }
+    return acc;
+}
+
+template <typename Sample>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    sadKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int warpsTotal = gridDim.x * kWarpsPerBlock;
+    for (int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n; t += warpsTotal)
+    {
+        const hvb_metric_task task = tasks[t];
+        int sa, sb;
+        const Sample *a = hvbBlockPtr<Sample>(planes, task.a, sa);
+        const Sample *b = hvbBlockPtr<Sample>(planes, task.b, sb);
+        int acc = hvbWarpSum(sadBlock<Sample>(a, sa, b, sb, task.w, task.h, lane));
+        if (sizeof(Sample) == 2) acc >>= 2;
+        if (lane == 0) out[t] = acc;
+    }
+}
+
+template <typename Sample>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    sad4Kernel(const HvbPlane *__restrict__ planes, const hvb_sad4_task *__restrict__ tasks, int n, int32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int warpsTotal = gridDim.x * kWarpsPerBlock;
+    for (int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n; t += warpsTotal)
+    {
+        const hvb_sad4_task task = tasks[t];
+        int ss;
+        const Sample *src = hvbBlockPtr<Sample>(planes, task.src, ss);
+        const HvbPlane &rp = planes[task.ref_pic * 3 + task.ref_cIdx];
+        const Sample *rbase = reinterpret_cast<const Sample *>(rp.base);
+        const int sr = rp.stride;
+        const int w = task.w, h = task.h;
+        int acc[4] = {0, 0, 0, 0};
+        const Sample *ref[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ref[k] = rbase + (intptr_t)task.ry[k] * sr + task.rx[k];
+
+        if (sizeof(Sample) == 1 && !(w & 3))
+        {
+            const int wq = w >> 2, total = wq * h;
+            for (int i = lane; i < total; i += 32)
+            {
+                const int y = i / wq, x = (i - y * wq) << 2;
+                const uint32_t vs = hvbLoad4u8(reinterpret_cast<const uint8_t *>(src) + y * ss + x);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    acc[k] = __vsadu4(vs, hvbLoad4u8(reinterpret_cast<const uint8_t *>(ref[k]) + y * sr + x)) + acc[k];
+            }
+        }
+        else
+        {
+            const int total = w * h;
+            for (int i = lane; i < total; i += 32)
+            {
+                const int y = i / w, x = i - y * w;
+                const int s = src[y * ss + x];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[k] += abs(s - (int)ref[k][y * sr + x]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            int v = hvbWarpSum(acc[k]);
+            if (sizeof(Sample) == 2) v >>= 2;
+            if (lane == 0) out[t * 4 + k] = v;
+        }
+    }
+}
+
+template <typename Sample>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    ssdKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, uint32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int warpsTotal = gridDim.x * kWarpsPerBlock;
+    for (int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n; t += warpsTotal)
+    {
+        const hvb_metric_task task = tasks[t];
+        int sa, sb;
+        const Sample *a = hvbBlockPtr<Sample>(planes, task.a, sa);
+        const Sample *b = hvbBlockPtr<Sample>(planes, task.b, sb);
+        const int w = task.w, h = task.h;
+        unsigned acc = 0;
+        if (sizeof(Sample) == 1 && !(w & 3))
+        {
+            const int wq = w >> 2, total = wq * h;
+            for (int i = lane; i < total; i += 32)
+            {
+                const int y = i / wq, x = (i - y * wq) << 2;
+                const uint32_t va = hvbLoad4u8(reinterpret_cast<const uint8_t *>(a) + y * sa + x);
+                const uint32_t vb = hvbLoad4u8(reinterpret_cast<const uint8_t *>(b) + y * sb + x);
+                const uint32_t d = __vabsdiffu4(va, vb);
+                acc = __dp4a(d, d, acc);
+            }
+        }
+        else
+        {
+            const int total = w * h;
+            for (int i = lane; i < total; i += 32)
+            {
+                const int y = i / w, x = i - y * w;
+                const int d = (int)a[y * sa + x] - (int)b[y * sb + x];
+                acc += (unsigned)(d * d);
+            }
+        }
+        acc = hvbWarpSumU(acc);
+        if (sizeof(Sample) == 2) acc >>= 4;
+        if (lane == 0) out[t] = acc;
+    }
+}
+
+} // namespace
+
+// One N x N Hadamard tile computed entirely in one thread's registers (N = 2, 4, 8).
+// Shared with the fused interpolation+SATD and intra-sweep kernels.
+template <typename SampleA, typename SampleB, int LOG2N>
+__device__ __forceinline__ int hvbSatdTile(const SampleA *a, int sa, const SampleB *b, int sb, int postShift)
+{
+    constexpr int N = 1 << LOG2N;
+    int m[N][N];
+#pragma unroll
+    for (int y = 0; y < N; ++y)
+#pragma unroll
+        for (int x = 0; x < N; ++x) m[y][x] = (int)a[y * sa + x] - (int)b[y * sb + x];
+
+        // rows
+#pragma unroll
+    for (int y = 0; y < N; ++y)
+#pragma unroll
+        for (int half = N / 2; half >= 1; half >>= 1)
+#pragma unroll
+            for (int base = 0; base < N; base += 2 * half)
+#pragma unroll
+                for (int j = 0; j < half; ++j)
+                {
+                    const int p = m[y][base + j], q = m[y][base + j + half];
+                    m[y][base + j] = p + q;
+                    m[y][base + j + half] = p - q;
+                }
+        // columns
+#pragma unroll
+    for (int x = 0; x < N; ++x)
+#pragma unroll
+        for (int half = N / 2; half >= 1; half >>= 1)
+#pragma unroll
+            for (int base = 0; base < N; base += 2 * half)
+#pragma unroll
+                for (int j = 0; j < half; ++j)
+                {
+                    const int p = m[base + j][x], q = m[base + j + half][x];
+                    m[base + j][x] = p + q;
+                    m[base + j + half][x] = p - q;
+                }
+    int acc = N / 4;
+#pragma unroll
+    for (int y = 0; y < N; ++y)
+#pragma unroll
+        for (int x = 0; x < N; ++x) acc += abs(m[y][x]);
+    // havoc/hadamard.cpp:93-96: normalise, then the 16-bit sample paths shift right by 2 per tile
+    return (acc >> (LOG2N - 1)) >> postShift;
+}
+
+template <typename SampleA, typename SampleB>
+__device__ __forceinline__ int hvbMeasureSatdLanes(const SampleA *a, int sa, const SampleB *b, int sb, int w, int h, int lane,
+                                                   int lanes, int postShift)
+{
+    // turing/Measure.h:96-135: tile size from the alignment of (w | h)
+    int acc = 0;
+    if ((w | h) & 3)
+    {
+        const int tw = w >> 1, tiles = tw * (h >> 1);
+        for (int t = lane; t < tiles; t += lanes)
+        {
+            const int ty = t / tw, tx = t - ty * tw;
+            acc += hvbSatdTile<SampleA, SampleB, 1>(a + 2 * ty * sa + 2 * tx, sa, b + 2 * ty * sb + 2 * tx, sb, postShift);
+        }
+    }
+    else if ((w | h) & 7)
+    {
+        const int tw = w >> 2, tiles = tw * (h >> 2);
+        for (int t = lane; t < tiles; t += lanes)
+        {
+            const int ty = t / tw, tx = t - ty * tw;
+            acc += hvbSatdTile<SampleA, SampleB, 2>(a + 4 * ty * sa + 4 * tx, sa, b + 4 * ty * sb + 4 * tx, sb, postShift);
+        }
+    }
+    else
+    {
+        const int tw = w >> 3, tiles = tw * (h >> 3);
+        for (int t = lane; t < tiles; t += lanes)
+        {
+            const int ty = t / tw, tx = t - ty * tw;
+            acc += hvbSatdTile<SampleA, SampleB, 3>(a + 8 * ty * sa + 8 * tx, sa, b + 8 * ty * sb + 8 * tx, sb, postShift);
+        }
+    }
+    return acc;
+}
+
+namespace {
+
+template <typename Sample>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    satdKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int warpsTotal = gridDim.x * kWarpsPerBlock;
+    for (int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n; t += warpsTotal)
+    {
+        const hvb_metric_task task = tasks[t];
+        int sa, sb;
+        const Sample *a = hvbBlockPtr<Sample>(planes, task.a, sa);
+        const Sample *b = hvbBlockPtr<Sample>(planes, task.b, sb);
+        int acc = hvbMeasureSatdLanes<Sample, Sample>(a, sa, b, sb, task.w, task.h, lane, 32, sizeof(Sample) == 2 ? 2 : 0);
+        acc = hvbWarpSum(acc);
+        if (lane == 0) out[t] = acc;
+    }
+}
+
+template <typename Task>
+int gridFor(hvb_context *ctx, int n)
+{
+    const int blocks = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int cap = ctx->smCount * 8; // 8 resident 256-thread CTAs per SM
+    return blocks < cap ? blocks : cap;
+}
+
+} // namespace
+
+#define HVB_DISPATCH_SAMPLE(ctx, kernel, grid, ...)                                                      \
+    do                                                                                                   \
+    {                                                                                                    \
+        if ((ctx)->bps == 1)                                                                             \
+            kernel<uint8_t><<<(grid), kWarpsPerBlock * 32, 0, (ctx)->stream>>>(__VA_ARGS__);             \
+        else                                                                                             \
+            kernel<uint16_t><<<(grid), kWarpsPerBlock * 32, 0, (ctx)->stream>>>(__VA_ARGS__);           \
+    } while (0)
+
+extern "C" int hvb_sad_batch(hvb_context *ctx, const hvb_metric_task *tasks, int n, int32_t *out, hvb_mem mem)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && out)));
+    if (!n) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    HvbStaged st;
+    int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(int32_t) * n, mem, &st);
+    if (rc) return rc;
+    HVB_DISPATCH_SAMPLE(ctx, sadKernel, gridFor<hvb_metric_task>(ctx, n), ctx->dPlanes,
+                        static_cast<const hvb_metric_task *>(st.dTasks), n, static_cast<int32_t *>(st.dOut));
+    HVB_LAUNCH_CHECK(ctx, "sadKernel");
+    return hvbStageOut(ctx, out, sizeof(int32_t) * n, mem, st);
+}
+
+extern "C" int hvb_sad4_batch(hvb_context *ctx, const hvb_sad4_task *tasks, int n, int32_t *out, hvb_mem mem)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && out)));
+    if (!n) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    HvbStaged st;
+    int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(int32_t) * 4 * n, mem, &st);
+    if (rc) return rc;
+    HVB_DISPATCH_SAMPLE(ctx, sad4Kernel, gridFor<hvb_sad4_task>(ctx, n), ctx->dPlanes,
+                        static_cast<const hvb_sad4_task *>(st.dTasks), n, static_cast<int32_t *>(st.dOut));
+    HVB_LAUNCH_CHECK(ctx, "sad4Kernel");
+    return hvbStageOut(ctx, out, sizeof(int32_t) * 4 * n, mem, st);
+}
+
+extern "C" int hvb_ssd_batch(hvb_context *ctx, const hvb_metric_task *tasks, int n, uint32_t *out, hvb_mem mem)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && out)));
+    if (!n) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    HvbStaged st;
+    int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(uint32_t) * n, mem, &st);
+    if (rc) return rc;
+    HVB_DISPATCH_SAMPLE(ctx, ssdKernel, gridFor<hvb_metric_task>(ctx, n), ctx->dPlanes,
+                        static_cast<const hvb_metric_task *>(st.dTasks), n, static_cast<uint32_t *>(st.dOut));
+    HVB_LAUNCH_CHECK(ctx, "ssdKernel");
+    return hvbStageOut(ctx, out, sizeof(uint32_t) * n, mem, st);
+}
+
+extern "C" int hvb_satd_batch(hvb_context *ctx, const hvb_metric_task *tasks, int n, int32_t *out, hvb_mem mem)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && out)));
+    if (!n) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    HvbStaged st;
+    int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(int32_t) * n, mem, &st);
+    if (rc) return rc;
+    HVB_DISPATCH_SAMPLE(ctx, satdKernel, gridFor<hvb_metric_task>(ctx, n), ctx->dPlanes,
+                        static_cast<const hvb_metric_task *>(st.dTasks), n, static_cast<int32_t *>(st.dOut));
+    HVB_LAUNCH_CHECK(ctx, "satdKernel");
+    return hvbStageOut(ctx, out, sizeof(int32_t) * n, mem, st);
+}
