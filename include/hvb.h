@@ -171,13 +171,16 @@ int hvb_intra_pred_batch(hvb_context *ctx, const hvb_intra_task *tasks, int n, h
 
 /* 35-mode SATD sweep of searchIntraPartition (turing/Search.hpp:39-267 via
  * Reconstruct.cpp:630-712): out[i][m] = SATD(src, intra(m)), m = 0..34.  nb_unfiltered /
- * nb_filtered select the reference array per mode by the filterFlag rule
- * (turing/IntraReferenceSamples.h filterFlag). */
+ * nb_filtered select the reference array per mode by the filterFlag rule (turing/Dsp.h:57-70);
+ * nb_filtered < 0 asks the kernel to derive the filtered array itself
+ * (turing/IntraReferenceSamples.h:373-419). */
 typedef struct
 {
     hvb_block src;
     int32_t nb_unfiltered, nb_filtered;
-    int8_t log2n, cIdx, reserved[6];
+    int8_t log2n, cIdx;
+    int8_t strong_intra_smoothing; /* sps flag, used when nb_filtered < 0 (filtered array derived on device) */
+    int8_t reserved[5];
 } hvb_intra_sweep_task; /* 24 bytes */
 int hvb_intra_satd35_batch(hvb_context *ctx, const hvb_intra_sweep_task *tasks, int n,
                            int32_t *out /* [n][35] */, hvb_mem mem);
@@ -236,13 +239,15 @@ typedef struct
     int32_t iqscale, iqshift;          /* inverse quantiser */
     int8_t scanIdx, reserved[3];
     int32_t rdoq_ctx;                  /* index of the RDOQ context snapshot (hvb_rdoq_contexts_upload) */
-} hvb_tu_task; /* 56 bytes */
+} hvb_tu_task; /* 60 bytes */
 
 typedef struct
 {
-    uint32_t ssd;
+    uint32_t ssd;     /* havoc_ssd(src, rec)  (Reconstruct.cpp:849-853) */
+    uint32_t ssdPred; /* havoc_ssd(src, pred) (Reconstruct.cpp:856) */
     int32_t cbf;
-} hvb_tu_result;
+    int32_t reserved;
+} hvb_tu_result; /* 16 bytes */
 int hvb_tu_chain_batch(hvb_context *ctx, const hvb_tu_task *tasks, int n, hvb_tu_result *out, hvb_mem mem);
 
 /* RDOQ inputs that are not pixels: a snapshot of the CABAC context states the reference's

@@ -152,4 +152,40 @@ int64_t orc_rate_of_mvd(int dx, int dy);
 }
 #endif
 
+/* ---- RDOQ (turing/Rdoq.cpp) ------------------------------------------------------------ */
+#ifdef __cplusplus
+extern "C" {
 #endif
+
+/* CABAC context states (ContextModel::state bytes, turing/ContextModel.h:30) that
+ * Rdoq::runQuantisation reads through estimateBits (Rdoq.cpp:26-31), and lambda as passed to the
+ * Rdoq constructor (Rdoq.h:170).  Same byte layout as hvb_rdoq_ctx in include/hvb.h. */
+typedef struct
+{
+    uint8_t sig_coeff_flag[44];
+    uint8_t greater1_flag[24];
+    uint8_t greater2_flag[6];
+    uint8_t coded_sub_block_flag[4];
+    uint8_t last_x_prefix[18];
+    uint8_t last_y_prefix[18];
+    uint8_t cbf_luma[2];
+    uint8_t cbf_cbcr[5];
+    uint8_t rqt_root_cbf[1];
+    uint8_t reserved[6];
+    double lambda;
+} orc_rdoq_ctx;
+
+/* turing/Rdoq.cpp:35-450 (runQuantisation) incl. sign-data hiding (:889-1023), with the constructor
+ * arithmetic of Rdoq.h:170-188.  Returns the OR of the coded levels (0 = no coded coefficient). */
+int orc_rdoq(int16_t *dst, const int16_t *src, const orc_rdoq_ctx *ctx, int quantiserScale,
+             int quantiserShift, int invQuantScale, int log2n, int cIdx, int scanIdx, int isIntra,
+             int sdh, int bitDepth);
+
+/* turing/ScanOrder.h: x (comp 0) / y (comp 1) of scan position `pos` in a (1<<log2)^2 block */
+int orc_scan_order(int log2, int scanIdx, int pos, int comp);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ORACLE_H */

@@ -230,3 +230,46 @@ class Ref:
 
 def have_ref() -> bool:
     return REF_LIB.exists()
+
+
+class RdoqCtx(C.Structure):
+    _fields_ = [("sig_coeff_flag", C.c_uint8 * 44), ("greater1_flag", C.c_uint8 * 24), ("greater2_flag", C.c_uint8 * 6),
+                ("coded_sub_block_flag", C.c_uint8 * 4), ("last_x_prefix", C.c_uint8 * 18),
+                ("last_y_prefix", C.c_uint8 * 18), ("cbf_luma", C.c_uint8 * 2), ("cbf_cbcr", C.c_uint8 * 5),
+                ("rqt_root_cbf", C.c_uint8 * 1), ("reserved", C.c_uint8 * 6), ("lambda_", C.c_double)]
+
+
+assert C.sizeof(RdoqCtx) == 136
+
+QUANT_SCALE = [26214, 23302, 20560, 18396, 16384, 14564]  # turing/QpState.h scaleLookup
+LEVEL_SCALE = [40, 45, 51, 57, 64, 72]                    # turing/QpState.h:85
+
+
+def quant_params(qp: int, log2n: int, bit_depth: int):
+    """(qscale, qshift, iqscale, iqshift) as the TU pipeline derives them (Reconstruct.cpp:779-786)."""
+    qscale = QUANT_SCALE[qp % 6]
+    qshift = 29 - bit_depth + qp // 6 - log2n
+    iqscale = LEVEL_SCALE[qp % 6] << (qp // 6)
+    iqshift = log2n - 1 + bit_depth - 8
+    return qscale, qshift, iqscale, iqshift
+
+
+def random_rdoq_ctx(rng, lam: float) -> np.ndarray:
+    """136-byte context snapshot with random legal CABAC states (0..125)."""
+    raw = rng.integers(0, 126, 136).astype(np.uint8)
+    raw[128:136] = np.frombuffer(np.float64(lam).tobytes(), np.uint8)
+    return raw
+
+
+def _rdoq(fn, dst, src, ctx_bytes, qscale, qshift, iqscale, log2n, c_idx, scan_idx, is_intra, sdh, bit_depth):
+    fn.argtypes = [vp, vp, vp] + [C.c_int] * 9
+    return fn(_ptr(dst), _ptr(src), _ptr(ctx_bytes), qscale, qshift, iqscale, log2n, c_idx, scan_idx, is_intra,
+              sdh, bit_depth)
+
+
+def oracle_rdoq(oracle: "Oracle", *a):
+    return _rdoq(oracle.lib.orc_rdoq, *a)
+
+
+def ref_rdoq(ref: "Ref", *a):
+    return _rdoq(ref.lib.ref_rdoq, *a)

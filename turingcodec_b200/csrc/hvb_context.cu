@@ -21,7 +21,7 @@ static_assert(sizeof(hvb_transform_task) == 16, "abi");
 static_assert(sizeof(hvb_quant_task) == 24, "abi");
 static_assert(sizeof(hvb_ita_task) == 24, "abi");
 static_assert(sizeof(hvb_tu_task) == 60, "abi");
-static_assert(sizeof(hvb_tu_result) == 8, "abi");
+static_assert(sizeof(hvb_tu_result) == 16, "abi");
 static_assert(sizeof(hvb_rdoq_ctx) == 136, "abi");
 static_assert(sizeof(hvb_rdoq_task) == 28, "abi");
 static_assert(sizeof(hvb_me_task) == 64, "abi");

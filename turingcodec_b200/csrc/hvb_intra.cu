@@ -1,0 +1,265 @@
+// hvb_intra.cu -- batched HEVC intra prediction and the 35-mode SATD sweep.
+//
+// Reference semantics (bit-exact):
+//   havoc::intra::Function      havoc/pred_intra.cpp:20282-20401 (planar / DC / angular, edge filters)
+//   neighbour addressing        havoc/pred_intra.cpp:43-51: p(x,y) = neighbours[x - y - 1]
+//   filterFlag                  turing/Dsp.h:57-70 (which modes use filtered reference samples)
+//   reference-sample filter     turing/IntraReferenceSamples.h:373-419 ([1 2 1] and strong bi-linear)
+//   35-mode sweep + SATD        turing/Reconstruct.cpp:630-701 (PredictIntraLumaBlock), Search.hpp:39-267
+//
+// The reference materialises every prediction into a stack buffer and then runs SATD on it, one mode
+// at a time.  Here a predicted sample is a pure function of (mode, x, y) and the 4n+1 neighbours, so
+// the sweep never stores a prediction: each lane owns one (mode, tile) job, evaluates the tile's
+// samples straight into the registers of a Hadamard butterfly and adds the result to its mode's sum.
+// Per partition that is (4n+1)B + n*n*B bytes in and 35 * 4 bytes out.
+#include "hvb_internal.cuh"
+#include "hvb_satd.cuh"
+
+namespace {
+
+constexpr int kWarps = 4;
+constexpr int kNbMax = 4 * 32 + 1;
+
+__device__ __constant__ int8_t kAngle[35] = {0,   0,   32,  26,  21,  17, 13, 9,  5,  2,  0,  -2, -5, -9, -13, -17, -21, -26,
+                                             -32, -26, -21, -17, -13, -9, -5, -2, 0,  2,  5,  9,  13, 17, 21,  26,  32};
+__device__ __constant__ int16_t kInvAngle[35] = {0,    0,    0,    0,    0,    0,    0,    0,    0,     0,     0,    -4096,
+                                                 -1638, -910, -630, -482, -390, -315, -256, -315, -390,  -482,  -630, -910,
+                                                 -1638, -4096, 0,   0,    0,    0,    0,    0,    0,     0,     0};
+
+// Reference samples of one partition: A[c + 1 + x] = p(x,-1), A[c] = p(-1,-1), A[c - 1 - y] = p(-1,y).
+struct Neighbours
+{
+    const int16_t *A;
+    int c; // = 2n
+    __device__ __forceinline__ int top(int x) const { return A[c + 1 + x]; }
+    __device__ __forceinline__ int left(int y) const { return A[c - 1 - y]; }
+    __device__ __forceinline__ int corner() const { return A[c]; }
+};
+
+// Projected 1-D reference of the angular modes (pred_intra.cpp:20330-20344 / :20368-20382),
+// evaluated on the fly: index i >= 0 walks the main side, i < 0 the inverse-angle projection.
+__device__ __forceinline__ int angularRef(const Neighbours &nb, int i, bool vertical, int inv)
+{
+    const int s = i >= 0 ? i : -((i * inv + 128) >> 8);
+    return vertical ? nb.A[nb.c + s] : nb.A[nb.c - s];
+}
+
+__device__ __forceinline__ int intraSample(const Neighbours &nb, int mode, int x, int y, int log2n, int dcVal, bool edge, int maxv)
+{
+    const int n = 1 << log2n;
+    if (mode == 0)
+        return ((n - 1 - x) * nb.left(y) + (x + 1) * nb.top(n) + (n - 1 - y) * nb.top(x) + (y + 1) * nb.left(n) + n) >> (log2n + 1);
+    if (mode == 1)
+    {
+        if (edge)
+        {
+            if (x == 0 && y == 0) return (nb.left(0) + 2 * dcVal + nb.top(0) + 2) >> 2;
+            if (y == 0) return (nb.top(x) + 3 * dcVal + 2) >> 2;
+            if (x == 0) return (nb.left(y) + 3 * dcVal + 2) >> 2;
+        }
+        return dcVal;
+    }
+    const bool vertical = mode >= 18;
+    if (edge && mode == 26 && x == 0) return hvbClip3(0, maxv, nb.top(0) + ((nb.left(y) - nb.corner()) >> 1));
+    if (edge && mode == 10 && y == 0) return hvbClip3(0, maxv, nb.left(0) + ((nb.top(x) - nb.corner()) >> 1));
+    const int angle = kAngle[mode], inv = kInvAngle[mode];
+    const int major = vertical ? y : x, minor = vertical ? x : y;
+    const int t = (major + 1) * angle;
+    const int idx = t >> 5, fact = t & 31;
+    const int r0 = angularRef(nb, minor + idx + 1, vertical, inv);
+    if (!fact) return r0;
+    const int r1 = angularRef(nb, minor + idx + 2, vertical, inv);
+    return ((32 - fact) * r0 + fact * r1 + 16) >> 5;
+}
+
+__device__ __forceinline__ int dcValue(const Neighbours &nb, int log2n, int lane)
+{
+    const int n = 1 << log2n;
+    int acc = 0;
+    for (int i = lane; i < n; i += 32) acc += nb.top(i) + nb.left(i);
+    return (hvbWarpSum(acc) + n) >> (log2n + 1);
+}
+
+// turing/Dsp.h:57-70 as the rule it tabulates: filter when the mode is further from pure
+// horizontal/vertical than the size-dependent threshold (8:7, 16:1, 32:0); planar always for n >= 8.
+__device__ __forceinline__ bool filterFlag(int cIdx, int mode, int n)
+{
+    if (cIdx != 0 || mode == 1 || n == 4) return false;
+    if (mode == 0) return true;
+    const int dist = min(abs(mode - 26), abs(mode - 10));
+    const int thres = n == 8 ? 7 : (n == 16 ? 1 : 0);
+    return dist > thres;
+}
+
+// turing/IntraReferenceSamples.h:373-419
+__device__ void filterNeighbours(int16_t *F, const int16_t *U, int n, int bitDepth, bool strongEnabled, int lane)
+{
+    const int c = 2 * n;
+    const Neighbours p{U, c};
+    bool strong = false;
+    if (strongEnabled && n == 32)
+        strong = abs(p.corner() + p.top(63) - 2 * p.top(31)) < (1 << (bitDepth - 5)) &&
+                 abs(p.corner() + p.left(63) - 2 * p.left(31)) < (1 << (bitDepth - 5));
+    for (int i = lane; i <= 4 * n; i += 32)
+    {
+        int v;
+        if (i == 0 || i == 4 * n)
+            v = U[i];
+        else if (strong)
+        {
+            if (i == c)
+                v = U[c];
+            else if (i > c) // top row, x = i - c - 1 in 0..62
+            {
+                const int x = i - c - 1;
+                v = ((63 - x) * p.corner() + (x + 1) * p.top(63) + 32) >> 6;
+            }
+            else
+            {
+                const int y = c - 1 - i;
+                v = ((63 - y) * p.corner() + (y + 1) * p.left(63) + 32) >> 6;
+            }
+        }
+        else
+            v = (U[i - 1] + 2 * U[i] + U[i + 1] + 2) >> 2;
+        F[i] = (int16_t)v;
+    }
+}
+
+template <typename Sample>
+__global__ void __launch_bounds__(kWarps * 32)
+    intraPredKernel(const HvbPlane *__restrict__ planes, const Sample *__restrict__ pool, const hvb_intra_task *__restrict__ tasks,
+                    int n, int bitDepth)
+{
+    __shared__ int16_t sNb[kWarps][kNbMax + 3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warpsTotal = gridDim.x * kWarps;
+    const int maxv = (1 << bitDepth) - 1;
+    for (int i = blockIdx.x * kWarps + warp; i < n; i += warpsTotal)
+    {
+        const hvb_intra_task t = tasks[i];
+        const int log2n = t.log2n, nn = 1 << log2n;
+        for (int k = lane; k <= 4 * nn; k += 32) sNb[warp][k] = (int16_t)pool[t.nb - 2 * nn + k];
+        __syncwarp();
+        const Neighbours nb{sNb[warp], 2 * nn};
+        const int dc = t.mode == 1 ? dcValue(nb, log2n, lane) : 0;
+        int sd;
+        Sample *dst = hvbBlockPtrW<Sample>(planes, t.dst, sd);
+        for (int j = lane; j < nn * nn; j += 32)
+        {
+            const int y = j >> log2n, x = j & (nn - 1);
+            dst[y * sd + x] = (Sample)intraSample(nb, t.mode, x, y, log2n, dc, t.edge_flag != 0, maxv);
+        }
+        __syncwarp();
+    }
+}
+
+template <typename Sample, int LOG2T>
+__device__ __forceinline__ int sweepTile(const Neighbours &nb, int mode, int log2n, int dc, bool edge, int maxv, const Sample *src,
+                                         int ss, int x0, int y0)
+{
+    constexpr int T = 1 << LOG2T;
+    int16_t pred[T * T];
+#pragma unroll
+    for (int y = 0; y < T; ++y)
+#pragma unroll
+        for (int x = 0; x < T; ++x) pred[y * T + x] = (int16_t)intraSample(nb, mode, x0 + x, y0 + y, log2n, dc, edge, maxv);
+    return hvbSatdTile<Sample, int16_t, LOG2T>(src + y0 * ss + x0, ss, pred, T, sizeof(Sample) == 2 ? 2 : 0);
+}
+
+template <typename Sample>
+__global__ void __launch_bounds__(kWarps * 32)
+    intraSweepKernel(const HvbPlane *__restrict__ planes, const Sample *__restrict__ pool,
+                     const hvb_intra_sweep_task *__restrict__ tasks, int n, int32_t *__restrict__ out, int bitDepth)
+{
+    __shared__ int16_t sU[kWarps][kNbMax + 3];
+    __shared__ int16_t sF[kWarps][kNbMax + 3];
+    __shared__ int sSum[kWarps][36];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warpsTotal = gridDim.x * kWarps;
+    const int maxv = (1 << bitDepth) - 1;
+    for (int i = blockIdx.x * kWarps + warp; i < n; i += warpsTotal)
+    {
+        const hvb_intra_sweep_task t = tasks[i];
+        const int log2n = t.log2n, nn = 1 << log2n;
+        for (int k = lane; k <= 4 * nn; k += 32)
+        {
+            sU[warp][k] = (int16_t)pool[t.nb_unfiltered - 2 * nn + k];
+            if (t.nb_filtered >= 0) sF[warp][k] = (int16_t)pool[t.nb_filtered - 2 * nn + k];
+        }
+        for (int k = lane; k < 36; k += 32) sSum[warp][k] = 0;
+        __syncwarp();
+        if (t.nb_filtered < 0) filterNeighbours(sF[warp], sU[warp], nn, bitDepth, t.strong_intra_smoothing != 0, lane);
+        __syncwarp();
+        const Neighbours nbU{sU[warp], 2 * nn}, nbF{sF[warp], 2 * nn};
+        const int dc = dcValue(nbU, log2n, lane);
+        const bool edge = t.cIdx == 0 && log2n < 5;
+        int ss;
+        const Sample *src = hvbBlockPtr<Sample>(planes, t.src, ss);
+
+        // PredictIntraLumaBlock tiles with 4x4 for log2n == 2 and 8x8 otherwise (Reconstruct.cpp:683-701)
+        const int log2t = log2n == 2 ? 2 : 3;
+        const int tilesPerRow = nn >> log2t, tiles = tilesPerRow * tilesPerRow;
+        const int jobs = 35 * tiles;
+        for (int j = lane; j < jobs; j += 32)
+        {
+            const int mode = j / tiles, tile = j - mode * tiles;
+            const int ty = tile / tilesPerRow, tx = tile - ty * tilesPerRow;
+            const Neighbours &nb = filterFlag(t.cIdx, mode, nn) ? nbF : nbU;
+            const int v = log2t == 2 ? sweepTile<Sample, 2>(nb, mode, log2n, dc, edge, maxv, src, ss, tx << 2, ty << 2)
+                                     : sweepTile<Sample, 3>(nb, mode, log2n, dc, edge, maxv, src, ss, tx << 3, ty << 3);
+            atomicAdd(&sSum[warp][mode], v);
+        }
+        __syncwarp();
+        for (int k = lane; k < 35; k += 32) out[i * 35 + k] = sSum[warp][k];
+        __syncwarp();
+    }
+}
+
+int gridWarps(hvb_context *ctx, int n)
+{
+    const int blocks = (n + kWarps - 1) / kWarps;
+    const int cap = ctx->smCount * 8;
+    return blocks < cap ? blocks : cap;
+}
+
+} // namespace
+
+extern "C" int hvb_intra_pred_batch(hvb_context *ctx, const hvb_intra_task *tasks, int n, hvb_mem mem)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || tasks) && ctx->samplePool);
+    if (!n) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    HvbStaged st;
+    int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, nullptr, 0, mem, &st);
+    if (rc) return rc;
+    const auto *dT = static_cast<const hvb_intra_task *>(st.dTasks);
+    if (ctx->bps == 1)
+        intraPredKernel<uint8_t><<<gridWarps(ctx, n), kWarps * 32, 0, ctx->stream>>>(
+            ctx->dPlanes, static_cast<const uint8_t *>(ctx->samplePool), dT, n, ctx->bitDepth);
+    else
+        intraPredKernel<uint16_t><<<gridWarps(ctx, n), kWarps * 32, 0, ctx->stream>>>(
+            ctx->dPlanes, static_cast<const uint16_t *>(ctx->samplePool), dT, n, ctx->bitDepth);
+    HVB_LAUNCH_CHECK(ctx, "intraPredKernel");
+    return hvbStageOut(ctx, nullptr, 0, mem, st);
+}
+
+extern "C" int hvb_intra_satd35_batch(hvb_context *ctx, const hvb_intra_sweep_task *tasks, int n, int32_t *out, hvb_mem mem)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && out)) && ctx->samplePool);
+    if (!n) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    HvbStaged st;
+    int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(int32_t) * 35 * n, mem, &st);
+    if (rc) return rc;
+    const auto *dT = static_cast<const hvb_intra_sweep_task *>(st.dTasks);
+    auto *dO = static_cast<int32_t *>(st.dOut);
+    if (ctx->bps == 1)
+        intraSweepKernel<uint8_t><<<gridWarps(ctx, n), kWarps * 32, 0, ctx->stream>>>(
+            ctx->dPlanes, static_cast<const uint8_t *>(ctx->samplePool), dT, n, dO, ctx->bitDepth);
+    else
+        intraSweepKernel<uint16_t><<<gridWarps(ctx, n), kWarps * 32, 0, ctx->stream>>>(
+            ctx->dPlanes, static_cast<const uint16_t *>(ctx->samplePool), dT, n, dO, ctx->bitDepth);
+    HVB_LAUNCH_CHECK(ctx, "intraSweepKernel");
+    return hvbStageOut(ctx, out, sizeof(int32_t) * 35 * n, mem, st);
+}

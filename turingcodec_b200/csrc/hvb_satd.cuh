@@ -1,0 +1,92 @@
+// hvb_satd.cuh -- register-resident Hadamard SATD tiles shared by the metric, fused
+// interpolation+SATD and intra-sweep kernels.
+//   havoc_hadamard_satd  havoc/hadamard.cpp:58-98
+//   measureSatd          turing/Measure.h:96-135
+#pragma once
+#include "hvb_internal.cuh"
+
+// One N x N Hadamard tile computed entirely in one thread's registers (N = 2, 4, 8).
+// Shared with the fused interpolation+SATD and intra-sweep kernels.
+template <typename SampleA, typename SampleB, int LOG2N>
+__device__ __forceinline__ int hvbSatdTile(const SampleA *a, int sa, const SampleB *b, int sb, int postShift)
+{
+    constexpr int N = 1 << LOG2N;
+    int m[N][N];
+#pragma unroll
+    for (int y = 0; y < N; ++y)
+#pragma unroll
+        for (int x = 0; x < N; ++x) m[y][x] = (int)a[y * sa + x] - (int)b[y * sb + x];
+
+        // rows
+#pragma unroll
+    for (int y = 0; y < N; ++y)
+#pragma unroll
+        for (int half = N / 2; half >= 1; half >>= 1)
+#pragma unroll
+            for (int base = 0; base < N; base += 2 * half)
+#pragma unroll
+                for (int j = 0; j < half; ++j)
+                {
+                    const int p = m[y][base + j], q = m[y][base + j + half];
+                    m[y][base + j] = p + q;
+                    m[y][base + j + half] = p - q;
+                }
+        // columns
+#pragma unroll
+    for (int x = 0; x < N; ++x)
+#pragma unroll
+        for (int half = N / 2; half >= 1; half >>= 1)
+#pragma unroll
+            for (int base = 0; base < N; base += 2 * half)
+#pragma unroll
+                for (int j = 0; j < half; ++j)
+                {
+                    const int p = m[base + j][x], q = m[base + j + half][x];
+                    m[base + j][x] = p + q;
+                    m[base + j + half][x] = p - q;
+                }
+    int acc = N / 4;
+#pragma unroll
+    for (int y = 0; y < N; ++y)
+#pragma unroll
+        for (int x = 0; x < N; ++x) acc += abs(m[y][x]);
+    // havoc/hadamard.cpp:93-96: normalise, then the 16-bit sample paths shift right by 2 per tile
+    return (acc >> (LOG2N - 1)) >> postShift;
+}
+
+template <typename SampleA, typename SampleB>
+__device__ __forceinline__ int hvbMeasureSatdLanes(const SampleA *a, int sa, const SampleB *b, int sb, int w, int h, int lane,
+                                                   int lanes, int postShift)
+{
+    // turing/Measure.h:96-135: tile size from the alignment of (w | h)
+    int acc = 0;
+    if ((w | h) & 3)
+    {
+        const int tw = w >> 1, tiles = tw * (h >> 1);
+        for (int t = lane; t < tiles; t += lanes)
+        {
+            const int ty = t / tw, tx = t - ty * tw;
+            acc += hvbSatdTile<SampleA, SampleB, 1>(a + 2 * ty * sa + 2 * tx, sa, b + 2 * ty * sb + 2 * tx, sb, postShift);
+        }
+    }
+    else if ((w | h) & 7)
+    {
+        const int tw = w >> 2, tiles = tw * (h >> 2);
+        for (int t = lane; t < tiles; t += lanes)
+        {
+            const int ty = t / tw, tx = t - ty * tw;
+            acc += hvbSatdTile<SampleA, SampleB, 2>(a + 4 * ty * sa + 4 * tx, sa, b + 4 * ty * sb + 4 * tx, sb, postShift);
+        }
+    }
+    else
+    {
+        const int tw = w >> 3, tiles = tw * (h >> 3);
+        for (int t = lane; t < tiles; t += lanes)
+        {
+            const int ty = t / tw, tx = t - ty * tw;
+            acc += hvbSatdTile<SampleA, SampleB, 3>(a + 8 * ty * sa + 8 * tx, sa, b + 8 * ty * sb + 8 * tx, sb, postShift);
+        }
+    }
+    return acc;
+}
+

@@ -1,0 +1,431 @@
+// hvb_tu.cu -- batched transform / quantisation primitives and the fused TU pipeline.
+//
+// Reference semantics (bit-exact):
+//   havoc::Transform (forward DCT-II 4..32, DST-VII 4)   havoc/transform.cpp:3071-3397
+//        two passes, shifts log2n-1+bd-8 and log2n+6, each result truncated to int16 WITH WRAP (:3071-3084)
+//   havoc::inverse_transform(_add)                        havoc/transform.cpp:50-401, transform.h:104-114
+//        two passes, shifts 7 and 20-bd, each clipped to int16; add to prediction, clip to bit depth
+//   havoc_quantize / havoc_quantize_inverse               havoc/quantize.cpp:278-304, :37-46
+//   TU pipeline                                           turing/Reconstruct.cpp:731-857 (inter), :180-356 (intra)
+//
+// The partial butterflies of the reference are a factorisation of plain integer matrix products
+// (C = M X M^T); integer sums are associative and nothing overflows int32, so the products are
+// evaluated directly: one warp per transform block, lanes across the output frequency (forward) or
+// output sample (inverse) index so that the matrix row is read conflict-free from shared memory and
+// the block operand is a broadcast.  The fused pipeline keeps residual, coefficients and levels in
+// the warp's shared-memory slice: per TU it reads src and pred (2 n^2 B), writes rec (n^2 B), the
+// levels (2 n^2) and 16 bytes of results; nothing intermediate touches HBM.
+#include "hvb_internal.cuh"
+
+namespace {
+
+constexpr int kWarps = 4;
+constexpr int kBlk = 32 * 32;
+
+// HEVC core transform: M32[k][i], generated from its 31 distinct magnitudes (see oracle_havoc.c dct_coeff).
+__device__ __constant__ int8_t kMag[33] = {64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
+                                           61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9,  4,  0};
+__device__ __constant__ int8_t kDst[4][4] = {{29, 55, 74, 84}, {74, 74, 0, -74}, {84, -29, -74, 55}, {55, -84, 74, -29}};
+
+struct Matrices
+{
+    int8_t m[32][32];  // m[k][i]
+    int8_t mt[32][32]; // mt[i][k] = m[k][i]
+    int8_t dst[4][4];  // dst[k][i]
+    int8_t dstT[4][4];
+};
+
+__device__ void initMatrices(Matrices &M)
+{
+    for (int idx = threadIdx.x; idx < 32 * 32; idx += blockDim.x)
+    {
+        const int k = idx >> 5, i = idx & 31;
+        int v;
+        if (k == 0)
+            v = 64;
+        else
+        {
+            int a = (k * (2 * i + 1)) & 127;
+            if (a > 64) a = 128 - a;
+            v = a > 32 ? -kMag[64 - a] : kMag[a];
+        }
+        M.m[k][i] = (int8_t)v;
+        M.mt[i][k] = (int8_t)v;
+    }
+    if (threadIdx.x < 16)
+    {
+        const int k = threadIdx.x >> 2, i = threadIdx.x & 3;
+        M.dst[k][i] = kDst[k][i];
+        M.dstT[i][k] = kDst[k][i];
+    }
+}
+
+// forward pass: out[k*n + j] = (int16)((sum_i M[k][i] * in[j*is + i] + add) >> shift)   (wraps)
+__device__ __forceinline__ void fwdPass(const Matrices &M, int16_t *out, const int16_t *in, int is, int log2n, bool dst, int shift,
+                                        int lane)
+{
+    const int n = 1 << log2n, step = 5 - log2n; // row k of the n-point matrix is row k << step of M32
+    const int add = 1 << (shift - 1);
+    const int k = lane & (n - 1), jj = lane >> log2n, jstep = 32 >> log2n;
+    if (n == 32)
+    {
+        for (int j = 0; j < 32; ++j)
+        {
+            int acc = add;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) acc += (int)M.mt[i][k] * (int)in[j * is + i];
+            out[k * 32 + j] = (int16_t)(acc >> shift);
+        }
+        return;
+    }
+    for (int j = jj; j < n; j += jstep)
+    {
+        int acc = add;
+        for (int i = 0; i < n; ++i)
+        {
+            const int c = dst ? M.dstT[i][k] : M.mt[i][k << step];
+            acc += c * (int)in[j * is + i];
+        }
+        out[k * n + j] = (int16_t)(acc >> shift);
+    }
+}
+
+// inverse pass: out[j*n + k] = clip16((sum_i M[i][k] * in[i*n + j] + add) >> shift)
+__device__ __forceinline__ void invPass(const Matrices &M, int16_t *out, const int16_t *in, int log2n, bool dst, int shift, int lane)
+{
+    const int n = 1 << log2n, step = 5 - log2n;
+    const int add = 1 << (shift - 1);
+    const int k = lane & (n - 1), jj = lane >> log2n, jstep = 32 >> log2n;
+    for (int j = jj; j < n; j += jstep)
+    {
+        int acc = add;
+        for (int i = 0; i < n; ++i)
+        {
+            const int c = dst ? M.dst[i][k] : M.m[i << step][k];
+            acc += c * (int)in[i * n + j];
+        }
+        out[j * n + k] = (int16_t)hvbClip3(-32768, 32767, acc >> shift);
+    }
+}
+
+__device__ __forceinline__ int quantOne(int v, int scale, int shift, int off)
+{
+    const int mag = (abs(v) * scale + off) >> shift;
+    return hvbClip3(-32768, 32767, v < 0 ? -mag : mag);
+}
+
+__device__ __forceinline__ int dequantOne(int v, int scale, int shift)
+{
+    return hvbClip3(-32768, 32767, (v * scale + (1 << (shift - 1))) >> shift);
+}
+
+// ---- stand-alone primitives over the coefficient pool ---------------------------------------
+
+__global__ void __launch_bounds__(kWarps * 32)
+    transformKernel(int16_t *__restrict__ pool, const hvb_transform_task *__restrict__ tasks, int n, int bitDepth, int inverse)
+{
+    __shared__ Matrices M;
+    __shared__ __align__(16) int16_t sA[kWarps][kBlk];
+    __shared__ __align__(16) int16_t sB[kWarps][kBlk];
+    initMatrices(M);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warpsTotal = gridDim.x * kWarps;
+    for (int t = blockIdx.x * kWarps + warp; t < n; t += warpsTotal)
+    {
+        const hvb_transform_task task = tasks[t];
+        const int log2n = task.log2n, nn = 1 << log2n, count = nn * nn;
+        const bool dst = task.trType != 0;
+        if (!inverse)
+        {
+            for (int i = lane; i < count; i += 32) sA[warp][i] = pool[task.src + (i >> log2n) * task.src_stride + (i & (nn - 1))];
+            __syncwarp();
+            fwdPass(M, sB[warp], sA[warp], nn, log2n, dst, log2n - 1 + bitDepth - 8, lane);
+            __syncwarp();
+            fwdPass(M, sA[warp], sB[warp], nn, log2n, dst, log2n + 6, lane);
+        }
+        else
+        {
+            for (int i = lane; i < count; i += 32) sA[warp][i] = pool[task.src + i];
+            __syncwarp();
+            invPass(M, sB[warp], sA[warp], log2n, dst, 7, lane);
+            __syncwarp();
+            invPass(M, sA[warp], sB[warp], log2n, dst, 20 - bitDepth, lane);
+        }
+        __syncwarp();
+        for (int i = lane; i < count; i += 32) pool[task.dst + i] = sA[warp][i];
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    quantKernel(int16_t *__restrict__ pool, const hvb_quant_task *__restrict__ tasks, int n, int32_t *__restrict__ cbf, int inverse)
+{
+    const int lane = threadIdx.x & 31;
+    const int warpsTotal = gridDim.x * 8;
+    for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < n; t += warpsTotal)
+    {
+        const hvb_quant_task task = tasks[t];
+        int any = 0;
+        if (!inverse)
+        {
+            const int off = task.offset << (task.shift - 16);
+            for (int i = lane; i < task.n; i += 32)
+            {
+                const int q = quantOne(pool[task.src + i], task.scale, task.shift, off);
+                any |= q;
+                pool[task.dst + i] = (int16_t)q;
+            }
+            any = __any_sync(0xffffffffu, any != 0);
+            if (lane == 0) cbf[t] = any;
+        }
+        else
+            for (int i = lane; i < task.n; i += 32) pool[task.dst + i] = (int16_t)dequantOne(pool[task.src + i], task.scale, task.shift);
+    }
+}
+
+template <typename Sample>
+__global__ void __launch_bounds__(kWarps * 32)
+    itaKernel(const HvbPlane *__restrict__ planes, const int16_t *__restrict__ pool, const hvb_ita_task *__restrict__ tasks, int n,
+              int bitDepth)
+{
+    __shared__ Matrices M;
+    __shared__ __align__(16) int16_t sA[kWarps][kBlk];
+    __shared__ __align__(16) int16_t sB[kWarps][kBlk];
+    initMatrices(M);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warpsTotal = gridDim.x * kWarps;
+    const int maxv = (1 << bitDepth) - 1;
+    for (int t = blockIdx.x * kWarps + warp; t < n; t += warpsTotal)
+    {
+        const hvb_ita_task task = tasks[t];
+        const int log2n = task.log2n, nn = 1 << log2n, count = nn * nn;
+        for (int i = lane; i < count; i += 32) sA[warp][i] = pool[task.coeffs + i];
+        __syncwarp();
+        invPass(M, sB[warp], sA[warp], log2n, task.trType != 0, 7, lane);
+        __syncwarp();
+        invPass(M, sA[warp], sB[warp], log2n, task.trType != 0, 20 - bitDepth, lane);
+        __syncwarp();
+        int sd, sp;
+        Sample *dst = hvbBlockPtrW<Sample>(planes, task.dst, sd);
+        const Sample *pred = hvbBlockPtr<Sample>(planes, task.pred, sp);
+        for (int i = lane; i < count; i += 32)
+        {
+            const int y = i >> log2n, x = i & (nn - 1);
+            dst[y * sd + x] = (Sample)hvbClip3(0, maxv, (int)pred[y * sp + x] + sA[warp][i]);
+        }
+        __syncwarp();
+    }
+}
+
+} // namespace
+
+// Rdoq::runQuantisation on a warp (hvb_rdoq.cu); levels are written to `dst` (n*n, smem or global).
+__device__ int hvbRdoqWarp(int16_t *dst, const int16_t *src, const hvb_rdoq_ctx *ctx, int qscale, int qshift, int iqscale, int log2n,
+                           int cIdx, int scanIdx, bool isIntra, bool sdh, int bitDepth, void *scratch, int lane);
+size_t hvbRdoqScratchBytesPerWarp();
+
+namespace {
+
+template <typename Sample>
+__global__ void __launch_bounds__(kWarps * 32)
+    tuChainKernel(const HvbPlane *__restrict__ planes, int16_t *__restrict__ pool, const hvb_rdoq_ctx *__restrict__ rdoqCtx,
+                  const hvb_tu_task *__restrict__ tasks, int n, hvb_tu_result *__restrict__ out, int bitDepth, char *scratch,
+                  size_t scratchPerWarp)
+{
+    __shared__ Matrices M;
+    __shared__ __align__(16) int16_t sA[kWarps][kBlk];
+    __shared__ __align__(16) int16_t sB[kWarps][kBlk];
+    initMatrices(M);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warpsTotal = gridDim.x * kWarps;
+    const int maxv = (1 << bitDepth) - 1;
+    for (int t = blockIdx.x * kWarps + warp; t < n; t += warpsTotal)
+    {
+        const hvb_tu_task task = tasks[t];
+        const int log2n = task.log2n, nn = 1 << log2n, count = nn * nn;
+        const bool dst = task.trType != 0;
+        int ss, sp, sr;
+        const Sample *src = hvbBlockPtr<Sample>(planes, task.src, ss);
+        const Sample *pred = hvbBlockPtr<Sample>(planes, task.pred, sp);
+        Sample *rec = hvbBlockPtrW<Sample>(planes, task.rec, sr);
+
+        // residual (Reconstruct.cpp:1275-1287) and SSD of the prediction (:856)
+        unsigned ssdPred = 0;
+        for (int i = lane; i < count; i += 32)
+        {
+            const int y = i >> log2n, x = i & (nn - 1);
+            const int d = (int)src[y * ss + x] - (int)pred[y * sp + x];
+            sA[warp][i] = (int16_t)d;
+            ssdPred += (unsigned)(d * d);
+        }
+        __syncwarp();
+        fwdPass(M, sB[warp], sA[warp], nn, log2n, dst, log2n - 1 + bitDepth - 8, lane);
+        __syncwarp();
+        fwdPass(M, sA[warp], sB[warp], nn, log2n, dst, log2n + 6, lane); // sA = coefficients
+        __syncwarp();
+
+        int cbf;
+        if (task.flags & 1)
+        {
+            cbf = hvbRdoqWarp(sB[warp], sA[warp], rdoqCtx + task.rdoq_ctx, task.qscale, task.qshift, task.iqscale, log2n, task.cIdx,
+                              task.scanIdx, (task.flags & 2) != 0, (task.flags & 4) != 0, bitDepth,
+                              scratch + (size_t)(blockIdx.x * kWarps + warp) * scratchPerWarp, lane);
+            cbf = cbf != 0;
+        }
+        else
+        {
+            const int off = task.qoffset << (task.qshift - 16);
+            int any = 0;
+            for (int i = lane; i < count; i += 32)
+            {
+                const int q = quantOne(sA[warp][i], task.qscale, task.qshift, off);
+                any |= q;
+                sB[warp][i] = (int16_t)q; // sB = levels
+            }
+            cbf = __any_sync(0xffffffffu, any != 0);
+        }
+        __syncwarp();
+        for (int i = lane; i < count; i += 32)
+        {
+            const int q = sB[warp][i];
+            pool[task.levels + i] = (int16_t)q;
+            sA[warp][i] = (int16_t)dequantOne(q, task.iqscale, task.iqshift); // Reconstruct.cpp:822-826
+        }
+        __syncwarp();
+        invPass(M, sB[warp], sA[warp], log2n, dst, 7, lane);
+        __syncwarp();
+        invPass(M, sA[warp], sB[warp], log2n, dst, 20 - bitDepth, lane);
+        __syncwarp();
+        unsigned ssd = 0;
+        for (int i = lane; i < count; i += 32)
+        {
+            const int y = i >> log2n, x = i & (nn - 1);
+            const int r = hvbClip3(0, maxv, (int)pred[y * sp + x] + sA[warp][i]);
+            rec[y * sr + x] = (Sample)r;
+            const int d = (int)src[y * ss + x] - r;
+            ssd += (unsigned)(d * d);
+        }
+        ssd = hvbWarpSumU(ssd);
+        ssdPred = hvbWarpSumU(ssdPred);
+        if (sizeof(Sample) == 2)
+        {
+            ssd >>= 4;
+            ssdPred >>= 4;
+        }
+        if (lane == 0)
+        {
+            hvb_tu_result r;
+            r.ssd = ssd;
+            r.ssdPred = ssdPred;
+            r.cbf = cbf;
+            r.reserved = 0;
+            out[t] = r;
+        }
+        __syncwarp();
+    }
+}
+
+int gridWarps(hvb_context *ctx, int n, int warps, int perSm)
+{
+    const int blocks = (n + warps - 1) / warps;
+    const int cap = ctx->smCount * perSm;
+    return blocks < cap ? blocks : cap;
+}
+
+int transformBatch(hvb_context *ctx, const hvb_transform_task *tasks, int n, hvb_mem mem, int inverse)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || tasks) && ctx->coeffPool);
+    if (!n) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    HvbStaged st;
+    int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, nullptr, 0, mem, &st);
+    if (rc) return rc;
+    transformKernel<<<gridWarps(ctx, n, kWarps, 4), kWarps * 32, 0, ctx->stream>>>(
+        ctx->coeffPool, static_cast<const hvb_transform_task *>(st.dTasks), n, ctx->bitDepth, inverse);
+    HVB_LAUNCH_CHECK(ctx, "transformKernel");
+    return hvbStageOut(ctx, nullptr, 0, mem, st);
+}
+
+} // namespace
+
+extern "C" int hvb_transform_fwd_batch(hvb_context *ctx, const hvb_transform_task *tasks, int n, hvb_mem mem)
+{
+    return transformBatch(ctx, tasks, n, mem, 0);
+}
+
+extern "C" int hvb_transform_inv_batch(hvb_context *ctx, const hvb_transform_task *tasks, int n, hvb_mem mem)
+{
+    return transformBatch(ctx, tasks, n, mem, 1);
+}
+
+extern "C" int hvb_quantize_batch(hvb_context *ctx, const hvb_quant_task *tasks, int n, int32_t *cbf, hvb_mem mem)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && cbf)) && ctx->coeffPool);
+    if (!n) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    HvbStaged st;
+    int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, cbf, sizeof(int32_t) * n, mem, &st);
+    if (rc) return rc;
+    quantKernel<<<gridWarps(ctx, n, 8, 8), 256, 0, ctx->stream>>>(ctx->coeffPool, static_cast<const hvb_quant_task *>(st.dTasks), n,
+                                                                  static_cast<int32_t *>(st.dOut), 0);
+    HVB_LAUNCH_CHECK(ctx, "quantKernel");
+    return hvbStageOut(ctx, cbf, sizeof(int32_t) * n, mem, st);
+}
+
+extern "C" int hvb_quantize_inverse_batch(hvb_context *ctx, const hvb_quant_task *tasks, int n, hvb_mem mem)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || tasks) && ctx->coeffPool);
+    if (!n) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    HvbStaged st;
+    int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, nullptr, 0, mem, &st);
+    if (rc) return rc;
+    quantKernel<<<gridWarps(ctx, n, 8, 8), 256, 0, ctx->stream>>>(ctx->coeffPool, static_cast<const hvb_quant_task *>(st.dTasks), n,
+                                                                  nullptr, 1);
+    HVB_LAUNCH_CHECK(ctx, "quantKernel(inverse)");
+    return hvbStageOut(ctx, nullptr, 0, mem, st);
+}
+
+extern "C" int hvb_inverse_transform_add_batch(hvb_context *ctx, const hvb_ita_task *tasks, int n, hvb_mem mem)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || tasks) && ctx->coeffPool);
+    if (!n) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    HvbStaged st;
+    int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, nullptr, 0, mem, &st);
+    if (rc) return rc;
+    const auto *dT = static_cast<const hvb_ita_task *>(st.dTasks);
+    if (ctx->bps == 1)
+        itaKernel<uint8_t><<<gridWarps(ctx, n, kWarps, 4), kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, dT, n, ctx->bitDepth);
+    else
+        itaKernel<uint16_t><<<gridWarps(ctx, n, kWarps, 4), kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, dT, n, ctx->bitDepth);
+    HVB_LAUNCH_CHECK(ctx, "itaKernel");
+    return hvbStageOut(ctx, nullptr, 0, mem, st);
+}
+
+extern "C" int hvb_tu_chain_batch(hvb_context *ctx, const hvb_tu_task *tasks, int n, hvb_tu_result *out, hvb_mem mem)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && out)) && ctx->coeffPool);
+    if (!n) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    const int grid = gridWarps(ctx, n, kWarps, 4);
+    const size_t perWarp = hvbRdoqScratchBytesPerWarp();
+    int rc = hvbEnsureScratch(ctx, perWarp * kWarps * (size_t)(ctx->smCount * 4));
+    if (rc) return rc;
+    HvbStaged st;
+    rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(hvb_tu_result) * n, mem, &st);
+    if (rc) return rc;
+    const auto *dT = static_cast<const hvb_tu_task *>(st.dTasks);
+    auto *dO = static_cast<hvb_tu_result *>(st.dOut);
+    if (ctx->bps == 1)
+        tuChainKernel<uint8_t><<<grid, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, ctx->rdoqCtx, dT, n, dO, ctx->bitDepth,
+                                                                      static_cast<char *>(ctx->scratch), perWarp);
+    else
+        tuChainKernel<uint16_t><<<grid, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, ctx->rdoqCtx, dT, n, dO, ctx->bitDepth,
+                                                                       static_cast<char *>(ctx->scratch), perWarp);
+    HVB_LAUNCH_CHECK(ctx, "tuChainKernel");
+    return hvbStageOut(ctx, out, sizeof(hvb_tu_result) * n, mem, st);
+}
