@@ -16,6 +16,7 @@
 // the warp's shared-memory slice: per TU it reads src and pred (2 n^2 B), writes rec (n^2 B), the
 // levels (2 n^2) and 16 bytes of results; nothing intermediate touches HBM.
 #include "hvb_internal.cuh"
+#include "hvb_rdoq.cuh"
 
 namespace {
 
@@ -219,15 +220,6 @@ __global__ void __launch_bounds__(kWarps * 32)
     }
 }
 
-} // namespace
-
-// Rdoq::runQuantisation on a warp (hvb_rdoq.cu); levels are written to `dst` (n*n, smem or global).
-__device__ int hvbRdoqWarp(int16_t *dst, const int16_t *src, const hvb_rdoq_ctx *ctx, int qscale, int qshift, int iqscale, int log2n,
-                           int cIdx, int scanIdx, bool isIntra, bool sdh, int bitDepth, void *scratch, int lane);
-size_t hvbRdoqScratchBytesPerWarp();
-
-namespace {
-
 template <typename Sample>
 __global__ void __launch_bounds__(kWarps * 32)
     tuChainKernel(const HvbPlane *__restrict__ planes, int16_t *__restrict__ pool, const hvb_rdoq_ctx *__restrict__ rdoqCtx,
@@ -272,7 +264,7 @@ __global__ void __launch_bounds__(kWarps * 32)
         {
             cbf = hvbRdoqWarp(sB[warp], sA[warp], rdoqCtx + task.rdoq_ctx, task.qscale, task.qshift, task.iqscale, log2n, task.cIdx,
                               task.scanIdx, (task.flags & 2) != 0, (task.flags & 4) != 0, bitDepth,
-                              scratch + (size_t)(blockIdx.x * kWarps + warp) * scratchPerWarp, lane);
+                              reinterpret_cast<HvbRdoqScratch *>(scratch + (size_t)(blockIdx.x * kWarps + warp) * scratchPerWarp), lane);
             cbf = cbf != 0;
         }
         else
@@ -324,6 +316,32 @@ __global__ void __launch_bounds__(kWarps * 32)
             r.reserved = 0;
             out[t] = r;
         }
+        __syncwarp();
+    }
+}
+
+// Rdoq::runQuantisation alone, on pool coefficients (one warp per block)
+__global__ void __launch_bounds__(kWarps * 32)
+    rdoqKernel(int16_t *__restrict__ pool, const hvb_rdoq_ctx *__restrict__ rdoqCtx, const hvb_rdoq_task *__restrict__ tasks, int n,
+               int32_t *__restrict__ cbf, int bitDepth, char *scratch, size_t scratchPerWarp)
+{
+    __shared__ __align__(16) int16_t sA[kWarps][kBlk];
+    __shared__ __align__(16) int16_t sB[kWarps][kBlk];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warpsTotal = gridDim.x * kWarps;
+    for (int t = blockIdx.x * kWarps + warp; t < n; t += warpsTotal)
+    {
+        const hvb_rdoq_task task = tasks[t];
+        const int count = 1 << (2 * task.log2n);
+        for (int i = lane; i < count; i += 32) sA[warp][i] = pool[task.src + i];
+        __syncwarp();
+        const int c = hvbRdoqWarp(sB[warp], sA[warp], rdoqCtx + task.rdoq_ctx, task.qscale, task.qshift, task.iqscale, task.log2n,
+                                  task.cIdx, task.scanIdx, (task.flags & 2) != 0, (task.flags & 4) != 0, bitDepth,
+                                  reinterpret_cast<HvbRdoqScratch *>(scratch + (size_t)(blockIdx.x * kWarps + warp) * scratchPerWarp),
+                                  lane);
+        __syncwarp();
+        for (int i = lane; i < count; i += 32) pool[task.dst + i] = sB[warp][i];
+        if (lane == 0) cbf[t] = c != 0;
         __syncwarp();
     }
 }
@@ -412,7 +430,7 @@ extern "C" int hvb_tu_chain_batch(hvb_context *ctx, const hvb_tu_task *tasks, in
     if (!n) return HVB_OK;
     cudaSetDevice(ctx->device);
     const int grid = gridWarps(ctx, n, kWarps, 4);
-    const size_t perWarp = hvbRdoqScratchBytesPerWarp();
+    const size_t perWarp = hvbRdoqScratchBytes();
     int rc = hvbEnsureScratch(ctx, perWarp * kWarps * (size_t)(ctx->smCount * 4));
     if (rc) return rc;
     HvbStaged st;
@@ -428,4 +446,23 @@ extern "C" int hvb_tu_chain_batch(hvb_context *ctx, const hvb_tu_task *tasks, in
                                                                        static_cast<char *>(ctx->scratch), perWarp);
     HVB_LAUNCH_CHECK(ctx, "tuChainKernel");
     return hvbStageOut(ctx, out, sizeof(hvb_tu_result) * n, mem, st);
+}
+
+extern "C" int hvb_rdoq_batch(hvb_context *ctx, const hvb_rdoq_task *tasks, int n, int32_t *cbf, hvb_mem mem)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && cbf)) && ctx->coeffPool && ctx->rdoqCtx);
+    if (!n) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    const int grid = gridWarps(ctx, n, kWarps, 4);
+    const size_t perWarp = hvbRdoqScratchBytes();
+    int rc = hvbEnsureScratch(ctx, perWarp * kWarps * (size_t)(ctx->smCount * 4));
+    if (rc) return rc;
+    HvbStaged st;
+    rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, cbf, sizeof(int32_t) * n, mem, &st);
+    if (rc) return rc;
+    rdoqKernel<<<grid, kWarps * 32, 0, ctx->stream>>>(ctx->coeffPool, ctx->rdoqCtx, static_cast<const hvb_rdoq_task *>(st.dTasks), n,
+                                                      static_cast<int32_t *>(st.dOut), ctx->bitDepth, static_cast<char *>(ctx->scratch),
+                                                      perWarp);
+    HVB_LAUNCH_CHECK(ctx, "rdoqKernel");
+    return hvbStageOut(ctx, cbf, sizeof(int32_t) * n, mem, st);
 }
