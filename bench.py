@@ -1,0 +1,446 @@
+#!/usr/bin/env python
+"""bench.py -- frame-pass throughput of the B200-native Turing-codec pixel hot path.
+
+One step = one pass of the hot path over one 3840x2160 8-bit frame at the reference's `--speed medium`
+settings (turingcodec_b200/workload.py): a uni-directional motion search (integer pattern search +
+1/2- and 1/4-pel refinement) for every PU of the CU quadtree, a 35-mode intra SATD sweep for every
+partition, and the TU pipeline (DCT -> RDOQ+SDH -> dequant -> IDCT+add -> SSD) for two candidates of
+every CU in luma and both chroma planes.  Three kernel launches per step.
+
+  value   frames/s with pictures, task and result arrays resident in HBM (CUDA events, max over ranks)
+  e2e     frames/s through the host-facing C-ABI (hvb_* with HVB_HOST): per step the source and
+          reference pictures are uploaded from pinned host memory, the task arrays go host->device and
+          every result array comes back device->host inside the timed region
+  roofline  for the dominant kernel: algorithmic bytes per launch (SURVEY.md 8(d) formulas) / its
+          average duration, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the same workload on the host cores through the reference's own havoc tables
+          (oracle/_ref, AVX2/xbyak JIT) when they were built, else the oracle's C port, on a bounded sample
+
+`--impl reference` times the CPU arm alone (rank 0 only under torchrun).
+NOTE this is the pixel hot path of SURVEY.md section 8, not a complete encoder: entropy coding and the
+mode-decision bookkeeping stay on the host in the reference and are out of scope.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "4K YUV420 8-bit hot-path frame passes per second (medium preset: ME + intra sweep + TU/RDOQ for one frame)"
+UNIT = "frames/s"
+N_PICS = 9  # source, reference, second prediction source, six reconstruction targets
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--width", type=int, default=3840)
+    p.add_argument("--height", type=int, default=2160)
+    p.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def pinned_empty(shape, dtype):
+    import torch
+    t = torch.empty(int(np.prod(shape)) * np.dtype(dtype).itemsize, dtype=torch.uint8, pin_memory=True)
+    return t.numpy().view(dtype).reshape(shape), t
+
+
+def build_inputs(width, height):
+    from turingcodec_b200 import synth
+    frames = [synth.frame(i, width, height, 8) for i in range(3)]
+    return frames
+
+
+class GpuArm:
+    def __init__(self, args, device):
+        import torch
+        from turingcodec_b200 import hvb, workload
+        self.torch, self.hvb = torch, hvb
+        self.device = device
+        torch.cuda.set_device(device)
+        self.ctx = hvb.Context(device, 1, 8)
+        self.stream = torch.cuda.Stream(device)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        w, h = args.width, args.height
+        self.frames = build_inputs(w, h)
+        # pictures: 0 source, 1 reference, 2 second prediction source, 3..8 reconstruction targets
+        self.pics = [self.ctx.picture_create(w, h, 96) for _ in range(N_PICS)]
+        self.pinned = []
+        for pic, f in zip(self.pics[:3], self.frames):
+            planes = []
+            for c, pl in enumerate(f):
+                arr, keep = pinned_empty(pl.shape, np.uint8)
+                arr[...] = pl
+                planes.append((arr, keep))
+                self.ctx.picture_upload(pic, c, arr)
+            self.ctx.picture_pad(pic)
+            self.pinned.append(planes)
+        self.fp = workload.frame_pass(self.frames[0][0], self.pics[0], self.pics[1], (self.pics[1], self.pics[2]),
+                                      tuple(self.pics[3:9]))
+        fp = self.fp
+        self.ctx.pool_upload(fp.neighbours)
+        self.ctx.rdoq_contexts_upload(fp.rdoq_ctx)
+        self.ctx.coeff_upload(np.zeros(1, np.int16), fp.coeff_count - 1)  # size the level pool
+        dev = torch.device("cuda", device)
+
+        def to_dev(a):
+            return torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(dev)
+
+        self.d_me, self.d_intra, self.d_tu = to_dev(fp.me), to_dev(fp.intra), to_dev(fp.tu)
+        self.o_me = torch.zeros(fp.me.size * hvb.me_result_t.itemsize, dtype=torch.uint8, device=dev)
+        self.o_intra = torch.zeros(fp.intra.size * 35, dtype=torch.int32, device=dev)
+        self.o_tu = torch.zeros(fp.tu.size * hvb.tu_result_t.itemsize, dtype=torch.uint8, device=dev)
+        # host result buffers for the e2e path
+        self.h_me = np.zeros(fp.me.size, hvb.me_result_t)
+        self.h_intra = np.zeros((fp.intra.size, 35), np.int32)
+        self.h_tu = np.zeros(fp.tu.size, hvb.tu_result_t)
+        self.kernel_ms = {"me": 0.0, "intra": 0.0, "tu": 0.0}
+        torch.cuda.synchronize(device)
+
+    # resident step: three launches
+    def step_resident(self, events=None):
+        hvb, fp = self.hvb, self.fp
+        if events is not None:
+            events[0].record(self.stream)
+        self.ctx.me_search(self.d_me.data_ptr(), fp.me.size, self.o_me.data_ptr(), hvb.DEVICE)
+        if events is not None:
+            events[1].record(self.stream)
+        self.ctx.intra_satd35(self.d_intra.data_ptr(), fp.intra.size, self.o_intra.data_ptr(), hvb.DEVICE)
+        if events is not None:
+            events[2].record(self.stream)
+        self.ctx.tu_chain(self.d_tu.data_ptr(), fp.tu.size, self.o_tu.data_ptr(), hvb.DEVICE)
+        if events is not None:
+            events[3].record(self.stream)
+
+    # host-facing step: upload pictures + neighbours, host task arrays in, host result arrays out
+    def step_e2e(self):
+        fp = self.fp
+        for pic, planes in zip(self.pics[:2], self.pinned[:2]):
+            for c, (arr, _) in enumerate(planes):
+                self.ctx.picture_upload(pic, c, arr)
+            self.ctx.picture_pad(pic)
+        self.ctx.pool_upload(fp.neighbours)
+        self.ctx.me_search(fp.me, out=self.h_me)
+        self.ctx.intra_satd35(fp.intra, out=self.h_intra)
+        self.ctx.tu_chain(fp.tu, out=self.h_tu)
+
+    def e2e_bytes(self):
+        fp = self.fp
+        frames = sum(arr.nbytes for planes in self.pinned[:2] for arr, _ in planes)
+        h2d = frames + fp.neighbours.nbytes + fp.me.nbytes + fp.intra.nbytes + fp.tu.nbytes
+        d2h = self.h_me.nbytes + self.h_intra.nbytes + self.h_tu.nbytes
+        return int(h2d), int(d2h)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle / reference tables)
+# ------------------------------------------------------------------------------------------------
+class CpuArm:
+    """Runs a bounded sample of the same frame pass through oracle_bench.c on the host threads."""
+
+    def __init__(self, args, fp=None, frames=None):
+        sys.path.insert(0, str(ROOT / "tests"))
+        import orc
+        from turingcodec_b200 import hvb, workload
+        self.hvb = hvb
+        self.oracle = orc.Oracle()
+        L = self.oracle.lib
+        self.kind = "port"
+        L.orc_bench_use_port()
+        self.ref = None
+        if orc.have_ref():
+            try:
+                self.ref = orc.Ref(use_asm=True)
+                R = self.ref.lib
+                ptr = lambda f: C.cast(f, C.c_void_p)
+                L.orc_bench_use_reference.argtypes = [C.c_void_p] * 9
+                L.orc_bench_use_reference(self.ref.h, ptr(R.ref_sad), ptr(R.ref_hadamard_satd), ptr(R.ref_pred_uni),
+                                          ptr(R.ref_pred_intra), ptr(R.ref_transform_fwd), ptr(R.ref_inverse_transform_add),
+                                          ptr(R.ref_quantize_inverse), ptr(R.ref_ssd))
+                self.kind = "reference"
+            except OSError:
+                self.ref = None
+        self.threads = int(L.orc_bench_threads())
+        w, h = args.width, args.height
+        self.frames = frames if frames is not None else build_inputs(w, h)
+        pad = 96
+        # host pictures 0..4 mirroring the GPU arm's ids; planes padded like the device ones, 64-byte aligned rows
+        self.planes = (C.c_void_p * 0)()
+        self.host = []
+        table = np.zeros((N_PICS * 3, 2), np.int64)
+        for pic in range(N_PICS):
+            for c in range(3):
+                pw, ph, pd = (w, h, pad) if c == 0 else (w // 2, h // 2, pad // 2)
+                stride = (pw + 2 * pd + 63) // 64 * 64 + 64
+                raw = np.zeros((ph + 2 * pd + 2) * stride + 64, np.uint8)
+                off = (-raw.ctypes.data) % 64
+                buf = raw[off:off + (ph + 2 * pd + 2) * stride].reshape(ph + 2 * pd + 2, stride)
+                x0 = (pd + 63) // 64 * 64
+                if pic < 3:
+                    buf[pd:pd + ph, x0:x0 + pw] = self.frames[pic][c]
+                    buf[pd:pd + ph, x0 - pd:x0] = buf[pd:pd + ph, x0:x0 + 1]
+                    buf[pd:pd + ph, x0 + pw:x0 + pw + pd] = buf[pd:pd + ph, x0 + pw - 1:x0 + pw]
+                    buf[:pd] = buf[pd]
+                    buf[pd + ph:pd + ph + pd] = buf[pd + ph - 1]
+                self.host.append((raw, buf))
+                table[pic * 3 + c] = (buf.ctypes.data + pd * stride + x0, stride)
+        self.table = table
+        self.fp = fp if fp is not None else workload.frame_pass(self.frames[0][0], 0, 1, (1, 2), tuple(range(3, 9)))
+        self.levels = np.zeros(self.fp.coeff_count, np.int16)
+        L.orc_bench_me.restype = C.c_double
+        L.orc_bench_intra.restype = C.c_double
+        L.orc_bench_tu.restype = C.c_double
+        L.orc_bench_me.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.orc_bench_intra.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.orc_bench_tu.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+
+    def run_fraction(self, frac: float):
+        """run the first `frac` of every task list (tasks are ordered depth-major, so strided sampling keeps the mix)"""
+        L, fp, hvb = self.oracle.lib, self.fp, self.hvb
+        stride = max(1, int(round(1.0 / frac)))
+        me = np.ascontiguousarray(fp.me[::stride])
+        intra = np.ascontiguousarray(fp.intra[::stride])
+        tu = np.ascontiguousarray(fp.tu[::stride])
+        o_me = np.zeros(me.size, hvb.me_result_t)
+        o_intra = np.zeros((intra.size, 35), np.int32)
+        o_tu = np.zeros(tu.size, hvb.tu_result_t)
+        p = self.table.ctypes.data
+        t = L.orc_bench_me(p, me.ctypes.data, me.size, o_me.ctypes.data, 1, 8)
+        t += L.orc_bench_intra(p, fp.neighbours.ctypes.data, intra.ctypes.data, intra.size, o_intra.ctypes.data, 1, 8)
+        t += L.orc_bench_tu(p, p, fp.rdoq_ctx.ctypes.data, tu.ctypes.data, tu.size, self.levels.ctypes.data, o_tu.ctypes.data, 1, 8)
+        return t, 1.0 / stride, (o_me, o_intra, o_tu, me, intra, tu)
+
+    def measure(self, target_seconds: float):
+        # calibrate on 1/512 of a frame, then size the sample for ~target_seconds of wall time
+        t, f, _ = self.run_fraction(1 / 512)
+        per_frame = t / f
+        frac = min(1.0, max(1 / 512, target_seconds / max(per_frame, 1e-9)))
+        t, f, _ = self.run_fraction(frac)
+        fps = f / t
+        return {"value": fps, "unit": UNIT, "cores": self.threads, "kind": self.kind,
+                "sample": f"every {int(round(1 / f))}-th task of one frame pass ({f:.4f} frame), {t:.1f} s on {self.threads} threads"}
+
+
+# ------------------------------------------------------------------------------------------------
+def peaks():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profile(kernel: str):
+    path = ROOT / "profiles" / "traffic.json"
+    if path.exists():
+        return json.loads(path.read_text()).get(kernel)
+    return None
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    arm = CpuArm(args)
+    steps = []
+    for _ in range(max(1, args.warmup if args.warmup < 2 else 1)):
+        arm.run_fraction(1 / 512)
+    budget = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps)))
+    res = None
+    t0 = time.time()
+    for _ in range(args.steps):
+        res = arm.measure(budget)
+        steps.append(res["value"])
+    fps = float(np.mean(steps))
+    line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"{args.width}x{args.height} YUV420 8-bit, medium preset, one hot-path frame pass per step",
+                       "units_per_step": arm.fp.units, "l2": "n/a (CPU arm)"},
+            "cpu_baseline": {**res, "value": fps},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.time() - t0}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from turingcodec_b200 import build
+    if not build.LIB.exists():
+        build.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    arm = GpuArm(args, local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(local)
+
+    # ---- resident throughput -------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        arm.step_resident()
+    barrier()
+    launches0 = arm.ctx.launch_count
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        barrier()
+        for k in range(args.steps):
+            arm.step_resident(ev[k])
+        barrier()
+    launches = arm.ctx.launch_count - launches0
+    total_ms = ev[0][0].elapsed_time(ev[-1][3])
+    kern = {"me": 0.0, "intra": 0.0, "tu": 0.0}
+    for k in range(args.steps):
+        kern["me"] += ev[k][0].elapsed_time(ev[k][1])
+        kern["intra"] += ev[k][1].elapsed_time(ev[k][2])
+        kern["tu"] += ev[k][2].elapsed_time(ev[k][3])
+    kern = {k: v / args.steps for k, v in kern.items()}
+    t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * 1000.0 / ms_per_step  # every rank processes its own frame per step (weak scaling)
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    from turingcodec_b200 import hvb, workload
+    me_out = arm.o_me.cpu().numpy().view(hvb.me_result_t)
+    fp = arm.fp
+    n_sad_samples = int((me_out["nSad"].astype(np.int64) * fp.me["w"].astype(np.int64) * fp.me["h"].astype(np.int64)).sum())
+    ab = workload.algorithmic_bytes(fp, 0)
+    alg = {"me": ab["me_fixed"] + n_sad_samples, "intra": ab["intra"], "tu": ab["tu"]}
+    dominant = max(kern, key=kern.get)
+    peak, peak_src = peaks()
+    achieved = alg[dominant] / (kern[dominant] * 1e-3) / 1e9
+    kernel_names = {"me": "meSearchKernel", "intra": "intraSweepKernel", "tu": "tuChainKernel"}
+    roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic_from_profile(kernel_names[dominant]), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dominant], "ms_per_launch": kern[dominant],
+                "all_kernels": {kernel_names[k]: {"ms": kern[k], "algorithmic_GBps": alg[k] / (kern[k] * 1e-3) / 1e9} for k in kern},
+                "note": "pictures (25 MB) stay L2-resident across the 100-300 candidates of a search, so algorithmic "
+                        "bytes exceed DRAM traffic by design; see DESIGN.md"}
+
+    # ---- end to end through the host-facing ABI ---------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        arm.ctx.set_stream(None)
+        arm.step_e2e()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_e2e = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            arm.step_e2e()
+        arm.ctx.sync()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([wall], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d, d2h = arm.e2e_bytes()
+        e2e = {"value": world * n_e2e / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": n_e2e, "timing": "host wall clock around blocking hvb_* calls (each returns after its results landed)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = CpuArm(args, fp=None, frames=arm.frames).measure(args.cpu_seconds)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"{args.width}x{args.height} YUV420 8-bit, medium preset, one hot-path frame pass per step "
+                                       "(configs[2] of BASELINE.json)", "units_per_step": fp.units,
+                           "l2": "per-step working set (tasks+results+levels+pictures) ~370 MB > 126 MB L2; no explicit flush",
+                           "parallelism": f"frames sharded over {world} GPU(s), no collective"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks.summary()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

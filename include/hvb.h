@@ -310,8 +310,10 @@ typedef struct
     int32_t mvpFlag;
     int64_t cost;                /* best integer-search cost (Q16) */
     int64_t costMvdZero[2];
-    int64_t subpelCost;
-    int32_t nSad, reserved;
+    int64_t subpelCost;          /* bestCost after subPelRefinement (valid when halfPel) */
+    int32_t nSad;                /* SAD evaluations performed (statistics; equals the reference's call count x4) */
+    int32_t flags;               /* bit 0: the integer search returned through MET (Search.hpp:2125), so the
+                                    caller must NOT update mvPreviousInteger2Nx2N and costMvdZero may be partial */
 } hvb_me_result; /* 56 bytes */
 int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, int n, hvb_me_result *out, hvb_mem mem);
 

@@ -132,7 +132,9 @@ typedef struct
 
 typedef struct
 {
-    orc_mv mv, mvd;
+    orc_mv mv, mvd;      /* after sub-pel refinement when enabled */
+    orc_mv mvInteger;    /* best integer vector (what mvPreviousInteger2Nx2N would receive) */
+    int earlyExit;       /* 1: fullPelMotionEstimation returned through MET (Search.hpp:2125) */
     int64_t cost;        /* best integer candidate cost (Q16) */
     int mvpFlag;
     int64_t costMvdZero[2];

@@ -49,7 +49,7 @@ class MeTask(C.Structure):
 
 class MeResult(C.Structure):
     _fields_ = [
-        ("mv", C.c_int16 * 2), ("mvd", C.c_int16 * 2),
+        ("mv", C.c_int16 * 2), ("mvd", C.c_int16 * 2), ("mvInteger", C.c_int16 * 2), ("earlyExit", C.c_int),
         ("cost", C.c_int64), ("mvpFlag", C.c_int),
         ("costMvdZero", C.c_int64 * 2), ("subpelCost", C.c_int64), ("nSad", C.c_int),
     ]

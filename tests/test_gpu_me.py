@@ -1,0 +1,104 @@
+"""GPU parity: the whole uni-directional PU motion search (integer pattern search + sub-pel refinement
+with their control flow) on the device vs the oracle's restatement of turing/Search.hpp -- every
+output field bit-exact, including the number of SAD evaluations (same path through the search)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import orc
+from gpu_common import H, PAD, W, Scene
+from turingcodec_b200 import hvb
+
+pytestmark = pytest.mark.gpu
+
+PU_SIZES = [(64, 64), (64, 32), (32, 64), (32, 32), (32, 16), (16, 32), (16, 16), (16, 8), (8, 16), (8, 8), (8, 4),
+            (4, 8), (32, 24), (24, 32), (16, 12), (12, 16), (64, 48), (48, 64), (64, 16), (16, 64), (32, 8), (8, 32),
+            (16, 4)]
+CTB = 64
+
+
+@pytest.fixture(scope="module", params=[(1, 8), (2, 10)], ids=["u8", "u16-10bit"])
+def scene(request):
+    s = Scene(*request.param)
+    yield s
+    s.close()
+
+
+def make_task(rng, scene, i):
+    w, h = PU_SIZES[i % len(PU_SIZES)]
+    x0 = int(rng.integers(0, (W - w) // 4 + 1)) * 4
+    y0 = int(rng.integers(0, (H - h) // 4 + 1)) * 4
+    t = np.zeros(1, hvb.me_task_t)[0]
+    t["src_pic"], t["ref_pic"] = scene.pics[0], scene.pics[1 + i % 2]
+    t["x0"], t["y0"], t["w"], t["h"] = x0, y0, w, h
+    spread = [2, 12, 40, 160][i % 4]
+    truth = np.array([12, 8]) * (1 + i % 2)  # synth.frame moves (+3,+2) samples per frame
+    for k in range(2):
+        if i % 3 == 1:  # predictors near the true motion: the MET early exits fire
+            t["mvp"][k]["x"], t["mvp"][k]["y"] = truth + rng.integers(-2, 3, 2)
+        else:
+            t["mvp"][k]["x"], t["mvp"][k]["y"] = rng.integers(-spread, spread + 1, 2)
+    t["rateMvpFlag"] = rng.integers(20000, 60000, 2)
+    t["lambda"] = int(rng.choice([0.05, 0.2, 0.6, 1.5]) * 65536 + 0.5)
+    # LimitFullPelMv (Search.hpp:1366-1407)
+    t["limitMin"]["x"], t["limitMin"]["y"] = -CTB - x0, -CTB - y0
+    t["limitMax"]["x"], t["limitMax"]["y"] = W + CTB - x0 - w, H + CTB - y0 - h
+    if i % 5 == 0:  # the wavefront restriction (concurrent frames > 1)
+        t["limitMax"]["x"] = min(int(t["limitMax"]["x"]), (x0 // CTB) * CTB + 3 * CTB - x0 - w - 15)
+        t["limitMax"]["y"] = min(int(t["limitMax"]["y"]), (y0 // CTB) * CTB + 2 * CTB - y0 - h - 15)
+    t["prev2Nx2N"]["x"], t["prev2Nx2N"]["y"] = rng.integers(-12, 13, 2) * 4
+    t["smallSearchWindow"] = i % 3 == 0
+    t["met"] = i % 2
+    t["log2CbSize"] = 3 + (max(w, h) > 8) + (max(w, h) > 16) + (max(w, h) > 32)
+    t["usePrev2Nx2N"] = (i // 2) % 2
+    t["halfPel"] = 1
+    t["quarterPel"] = i % 4 != 3
+    return t
+
+
+def oracle_search(oracle, scene, t):
+    ot, r = orc.MeTask(), orc.MeResult()
+    ot.x0, ot.y0, ot.w, ot.h = int(t["x0"]), int(t["y0"]), int(t["w"]), int(t["h"])
+    for k in range(2):
+        ot.mvp[2 * k], ot.mvp[2 * k + 1] = int(t["mvp"][k]["x"]), int(t["mvp"][k]["y"])
+        ot.rateMvpFlag[k] = int(t["rateMvpFlag"][k])
+    ot.lambda_ = int(t["lambda"])
+    ot.limitMin[0], ot.limitMin[1] = int(t["limitMin"]["x"]), int(t["limitMin"]["y"])
+    ot.limitMax[0], ot.limitMax[1] = int(t["limitMax"]["x"]), int(t["limitMax"]["y"])
+    ot.smallSearchWindow, ot.met, ot.log2CbSize = int(t["smallSearchWindow"]), int(t["met"]), int(t["log2CbSize"])
+    ot.usePrev2Nx2N = int(t["usePrev2Nx2N"])
+    ot.prev2Nx2N[0], ot.prev2Nx2N[1] = int(t["prev2Nx2N"]["x"]), int(t["prev2Nx2N"]["y"])
+    ot.halfPel, ot.quarterPel, ot.bitDepth = int(t["halfPel"]), int(t["quarterPel"]), scene.bd
+    src = scene.host[0][0]
+    ref = scene.host[int(t["ref_pic"]) - scene.pics[0]][0]
+    base = (PAD * src.shape[1] + PAD) * src.itemsize
+    oracle.lib.orc_me_search(C.c_void_p(src.ctypes.data + base), src.shape[1], C.c_void_p(ref.ctypes.data + base),
+                             ref.shape[1], C.byref(ot), C.byref(r), scene.bps)
+    return r
+
+
+def test_me_search_matches_oracle(scene, oracle):
+    rng = np.random.default_rng(51)
+    n = 230
+    tasks = np.zeros(n, hvb.me_task_t)
+    for i in range(n):
+        tasks[i] = make_task(rng, scene, i)
+    got = scene.ctx.me_search(tasks)
+    early = refined = 0
+    for i in range(n):
+        r = oracle_search(oracle, scene, tasks[i])
+        g = got[i]
+        key = (i, tuple(tasks[i][["x0", "y0", "w", "h"]]))
+        assert (int(g["mv"]["x"]), int(g["mv"]["y"])) == tuple(r.mv), key
+        assert (int(g["mvd"]["x"]), int(g["mvd"]["y"])) == tuple(r.mvd), key
+        assert (int(g["mvInteger"]["x"]), int(g["mvInteger"]["y"])) == tuple(r.mvInteger), key
+        assert int(g["mvpFlag"]) == r.mvpFlag and int(g["cost"]) == r.cost, key
+        assert int(g["subpelCost"]) == r.subpelCost, key
+        assert int(g["nSad"]) == r.nSad, key
+        assert (int(g["flags"]) & 1) == r.earlyExit, key
+        if not r.earlyExit:
+            assert list(g["costMvdZero"]) == list(r.costMvdZero), key
+        early += r.earlyExit
+        refined += tuple(r.mv) != tuple(r.mvInteger)
+    assert early > 5 and refined > n // 4  # both the MET exits and the sub-pel moves are exercised

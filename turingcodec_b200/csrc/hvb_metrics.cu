@@ -1,6 +1,6 @@
 // hvb_metrics.cu -- batched SAD / SAD4 / SSD / Hadamard-SATD over device-resident pictures.
 //
-// Reference semantics (bit-exact, see oracle/oracle_havoc.c for the CPU restatement):
+// Reference semantics (bit-exact):
 //   havoc_sad           havoc/sad.cpp:432-449     (u16: >> 2)
 //   havoc_sad_multiref  havoc/sad.cpp:513-542     (4 references, u16: each >> 2)
 //   havoc_ssd           havoc/ssd.cpp:28-43       (uint32 wrap, u16: >> 4)

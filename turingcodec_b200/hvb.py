@@ -57,7 +57,7 @@ me_task_t = np.dtype([("src_pic", "<i2"), ("ref_pic", "<i2"), ("x0", "<i2"), ("y
                       ("met", "u1"), ("log2CbSize", "u1"), ("usePrev2Nx2N", "u1"), ("halfPel", "u1"),
                       ("quarterPel", "u1"), ("reserved", "u1", 2)], align=True)
 me_result_t = np.dtype([("mv", mv_t), ("mvd", mv_t), ("mvInteger", mv_t), ("mvpFlag", "<i4"), ("cost", "<i8"),
-                        ("costMvdZero", "<i8", 2), ("subpelCost", "<i8"), ("nSad", "<i4"), ("reserved", "<i4")],
+                        ("costMvdZero", "<i8", 2), ("subpelCost", "<i8"), ("nSad", "<i4"), ("flags", "<i4")],
                        align=True)
 
 _SIZES = {
