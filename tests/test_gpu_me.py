@@ -101,4 +101,4 @@ def test_me_search_matches_oracle(scene, oracle):
             assert list(g["costMvdZero"]) == list(r.costMvdZero), key
         early += r.earlyExit
         refined += tuple(r.mv) != tuple(r.mvInteger)
-    assert early > 5 and refined > n // 4  # both the MET exits and the sub-pel moves are exercised
+    assert early > 5 and refined > 10, (early, refined)  # both the MET exits and the sub-pel moves are exercised

@@ -7,23 +7,57 @@
 //   subPelRefinement / patternSearch / costMv / costDistortionMv   :1965-2060, :2339-2357
 //   rateOf                    turing/Measure.h:177-220
 //   Cost / Lambda             turing/FixedPoint.h, Cost.h (Q16: int64 / int32)
+//   interpolation / SATD      havoc/pred_inter.cpp:76-202, havoc/hadamard.cpp:58-98, turing/Measure.h:96-135
 //
 // In the reference every pattern step is a host round trip: 4 candidate vectors -> one
 // havoc_sad_multiref call -> compare -> next origin.  A launch per call is hopeless (SURVEY.md
-// section 7), so the data-dependent loop itself runs on the device: a warp walks the reference's
-// exact candidate order for its PU, evaluating the candidates of one pattern call with the whole
-// warp and applying the reference's ordered `consider` (strict <, first minimum wins).  The source
-// block is held in registers for the life of the search (it is compared against 100-300
-// candidates), candidate blocks stream from the L2-resident reference window.  Per PU the
-// algorithmic traffic is w*h*B (source, once) + nSad * w*h*B (candidates) + 17 (w+7)(h+7)B (sub-pel).
+// section 7), so the data-dependent loop itself runs on the device.  A warp owns one PU and walks the
+// reference's exact sequence of pattern calls; what it parallelises is the INSIDE of each call:
+//
+//   integer stage   the (up to 16, raster: 32) candidates of one considerPattern call are evaluated at
+//                   once, 32/nCand lanes per candidate, then an ordered arg-min (cost, candidate index)
+//                   reproduces the reference's sequential `consider` (strict <, first minimum wins);
+//   sub-pel stage   the 9 half-pel (then 8 quarter-pel) candidates are evaluated at once: a job is one
+//                   (candidate, 8x8 tile) -- 8 lanes, lane j owns column j: it streams the 15 rows of the
+//                   8-tap horizontal filter through an 8-deep register window for the vertical filter,
+//                   subtracts the source column and runs the Hadamard butterfly vertically in
+//                   registers and horizontally with shuffles.  No prediction is ever stored.
+//
+// The source block lives in shared memory for the life of the search (it is compared against every
+// candidate); candidate blocks stream from the L2/L1-resident reference window.  Serial depth per PU
+// is the number of pattern calls (5-20), not the number of SADs (30-900).
+// Algorithmic traffic per PU: w*h*B (source, once) + nSad*w*h*B + 17 ((w+7)(h+7) + w*h) B.
 #include "hvb_internal.cuh"
-#include "hvb_satd.cuh"
-#include "hvb_interp.cuh"
 
 namespace {
 
-using namespace hvb_interp;
-constexpr int kWarps = 4;
+constexpr int kWarps = 8;
+constexpr int kSrcWords = 64 * 64 / 2; // u16 worst case: 2 samples per word
+
+// ---- sample-type helpers: 32-bit words of 4 (u8) or 2 (u16) samples -------------------------------
+template <typename Sample>
+struct Word;
+template <>
+struct Word<uint8_t>
+{
+    static constexpr int kLog2Spw = 2;
+    static __device__ __forceinline__ uint32_t load(const uint8_t *p) { return hvbLoad4u8(p); }
+    static __device__ __forceinline__ int sad(uint32_t a, uint32_t b, int acc) { return __vsadu4(a, b) + acc; }
+};
+template <>
+struct Word<uint16_t>
+{
+    static constexpr int kLog2Spw = 1;
+    static __device__ __forceinline__ uint32_t load(const uint16_t *p)
+    {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+        const uint32_t lo = __ldg(q);
+        if (!(a & 2)) return lo;
+        return __funnelshift_r(lo, __ldg(q + 1), 16);
+    }
+    static __device__ __forceinline__ int sad(uint32_t a, uint32_t b, int acc) { return __vsadu2(a, b) + acc; }
+};
 
 struct Cand
 {
@@ -39,84 +73,97 @@ __device__ __forceinline__ long long rateOfMvd(int dx, int dy)
     return (long long)(rx + ry + 1) << 17;
 }
 
+__device__ __forceinline__ long long shfl64(long long v, int srcLane)
+{
+    const int lo = __shfl_sync(0xffffffffu, (int)(v & 0xffffffffLL), srcLane);
+    const int hi = __shfl_sync(0xffffffffu, (int)(v >> 32), srcLane);
+    return ((long long)hi << 32) | (unsigned)lo;
+}
+
+__device__ __forceinline__ long long shflXor64(long long v, int m)
+{
+    const int lo = __shfl_xor_sync(0xffffffffu, (int)(v & 0xffffffffLL), m);
+    const int hi = __shfl_xor_sync(0xffffffffu, (int)(v >> 32), m);
+    return ((long long)hi << 32) | (unsigned)lo;
+}
+
+__device__ __constant__ int8_t kDiamond4[8] = {-4, 0, 0, 4, 4, 0, 0, -4};
+__device__ __constant__ int8_t kHexagon8[16] = {0, -8, 8, -4, 8, 4, 0, 8, -8, 4, -8, -4, -8, 4, -8, -4};
+__device__ __constant__ int8_t kDiamond16[32] = {0,  -4, 1,  -3, 2,  -2, 3,  -1, 4,  0, 3,  1,  2,  2,  1,  3,
+                                                 0,  4,  -1, 3,  -2, 2,  -3, 1,  -4, 0, -3, -1, -2, -2, -1, -3};
+__device__ __constant__ int8_t kSquare4[8] = {-4, -4, -4, 4, 4, 4, 4, -4};
+__device__ __constant__ int8_t kDiamond1[8] = {0, -1, -1, 0, 0, 1, 1, 0};
+// sub-pel patterns (Search.hpp:2346, :2352); entry 0 is the origin itself (tryOrigin)
+__device__ __constant__ int8_t kHalf9[18] = {0, 0, -2, -2, 0, -2, 2, -2, -2, 0, 2, 0, -2, 2, 0, 2, 2, 2};
+__device__ __constant__ int8_t kQuarter8[16] = {-1, -1, 0, -1, 1, -1, -1, 0, 1, 0, -1, 1, 0, 1, 1, 1};
+__device__ __constant__ int8_t kLumaTaps[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0},
+                                                  {-1, 4, -10, 58, 17, -5, 1, 0},
+                                                  {-1, 4, -11, 40, 40, -11, 4, -1},
+                                                  {0, 1, -5, 17, 58, -10, 4, -1}};
+
 template <typename Sample>
 struct Search
 {
     const hvb_me_task &t;
-    const Sample *src, *ref; // sample (x0, y0) of the source / reference plane
-    int ss, sr;
+    const Sample *ref; // sample (x0, y0) of the reference plane
+    int sr;
+    const uint32_t *srcWords; // shared: the PU packed as words, row-major, wpr words per row
+    const Sample *srcS;       // the same memory viewed as samples (row stride = w)
     int lane;
+    int wpr, words, wprInv; // words per row, words in the block, ceil(65536 / wpr)
     Cand best;
     int nSad;
-    uint32_t srcw[32]; // u8 fast path: this lane's words of the source block (w*h/4 words over 32 lanes)
-    bool cached;
 
-    __device__ Search(const hvb_me_task &task, const HvbPlane *planes, int lane_) : t(task), lane(lane_)
+    __device__ Search(const hvb_me_task &task, const HvbPlane *planes, uint32_t *smemSrc, int lane_) : t(task), lane(lane_)
     {
         const HvbPlane &sp = planes[t.src_pic * 3], &rp = planes[t.ref_pic * 3];
-        ss = sp.stride;
         sr = rp.stride;
-        src = reinterpret_cast<const Sample *>(sp.base) + (intptr_t)t.y0 * ss + t.x0;
         ref = reinterpret_cast<const Sample *>(rp.base) + (intptr_t)t.y0 * sr + t.x0;
+        const Sample *src = reinterpret_cast<const Sample *>(sp.base) + (intptr_t)t.y0 * sp.stride + t.x0;
+        wpr = t.w >> Word<Sample>::kLog2Spw;
+        words = wpr * t.h;
+        wprInv = (65536 + wpr - 1) / wpr;
+        for (int i = lane; i < words; i += 32)
+        {
+            const int y = (i * wprInv) >> 16, xw = i - y * wpr;
+            smemSrc[i] = Word<Sample>::load(src + y * sp.stride + (xw << Word<Sample>::kLog2Spw));
+        }
+        srcWords = smemSrc;
+        srcS = reinterpret_cast<const Sample *>(smemSrc);
         best.cost = 0x7fffffffffffffffLL;
         best.mv = best.mvd = hvb_mv{0, 0};
         best.mvpFlag = 0;
         nSad = 0;
-        cached = sizeof(Sample) == 1 && !(t.w & 3);
-        if (cached)
-        {
-            const int wq = t.w >> 2, total = wq * t.h;
-#pragma unroll
-            for (int k = 0; k < 32; ++k)
-            {
-                const int i = lane + 32 * k;
-                if (i < total)
-                {
-                    const int y = i / wq, x = (i - y * wq) << 2;
-                    srcw[k] = hvbLoad4u8(reinterpret_cast<const uint8_t *>(src) + y * ss + x);
-                }
-            }
-        }
+        __syncwarp();
     }
 
-    __device__ __forceinline__ void limit(hvb_mv &mv) const
+    __device__ __forceinline__ void limit(int &x, int &y) const
     {
-        mv.x = max(mv.x, t.limitMin.x);
-        mv.y = max(mv.y, t.limitMin.y);
-        mv.x = min(mv.x, t.limitMax.x);
-        mv.y = min(mv.y, t.limitMax.y);
+        x = min(max(x, (int)t.limitMin.x), (int)t.limitMax.x);
+        y = min(max(y, (int)t.limitMin.y), (int)t.limitMax.y);
     }
 
-    // warp-cooperative havoc_sad of the PU against the reference displaced by a full-pel vector
-    __device__ int sadAt(int mvx, int mvy)
+    // SADs of `nc` (1..32) full-pel candidates at once.  Lane c < nc passes candidate c's displacement and
+    // receives its SAD; the block's words are split over 32/nextpow2(nc) lanes per candidate.
+    __device__ int sadMulti(int nc, int mvx, int mvy)
     {
-        ++nSad;
-        const Sample *r = ref + (intptr_t)mvy * sr + mvx;
+        nSad += nc;
+        const int log2p = nc <= 1 ? 0 : 32 - __clz(nc - 1); // ceil(log2(nc))
+        const int lanesPer = 32 >> log2p;
+        const int cand = lane >> (5 - log2p), sub = lane & (lanesPer - 1);
+        const int cx = __shfl_sync(0xffffffffu, mvx, cand), cy = __shfl_sync(0xffffffffu, mvy, cand);
         int acc = 0;
-        if (cached)
+        if (cand < nc)
         {
-            const int wq = t.w >> 2, total = wq * t.h;
-#pragma unroll
-            for (int k = 0; k < 32; ++k)
+            const Sample *r = ref + (intptr_t)cy * sr + cx;
+            for (int i = sub; i < words; i += lanesPer)
             {
-                const int i = lane + 32 * k;
-                if (i < total)
-                {
-                    const int y = i / wq, x = (i - y * wq) << 2;
-                    acc = __vsadu4(srcw[k], hvbLoad4u8(reinterpret_cast<const uint8_t *>(r) + y * sr + x)) + acc;
-                }
+                const int y = (i * wprInv) >> 16, xw = i - y * wpr;
+                acc = Word<Sample>::sad(srcWords[i], Word<Sample>::load(r + y * sr + (xw << Word<Sample>::kLog2Spw)), acc);
             }
         }
-        else
-        {
-            const int w = t.w, total = t.w * t.h;
-            for (int i = lane; i < total; i += 32)
-            {
-                const int y = i / w, x = i - y * w;
-                acc += abs((int)src[y * ss + x] - (int)r[y * sr + x]);
-            }
-        }
-        acc = hvbWarpSum(acc);
+        for (int o = lanesPer >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        acc = __shfl_sync(0xffffffffu, acc, (lane << (5 - log2p)) & 31); // candidate `lane`'s group leader
         return sizeof(Sample) == 2 ? acc >> 2 : acc;
     }
 
@@ -140,8 +187,43 @@ struct Search
         return c;
     }
 
-    __device__ __forceinline__ bool consider(const Cand &c)
+    // The reference considers candidates one after the other with a strict `<`: the winner is the first
+    // candidate of least cost, and it replaces `best` only if it is strictly cheaper.  Lane c holds candidate c.
+    __device__ bool considerLanes(const Cand &mine, bool valid)
     {
+        long long cost = valid ? mine.cost : 0x7fffffffffffffffLL;
+        int who = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const long long oc = shflXor64(cost, o);
+            const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+            if (oc < cost || (oc == cost && ow < who))
+            {
+                cost = oc;
+                who = ow;
+            }
+        }
+        const bool improved = cost < best.cost;
+        // every lane takes part in the broadcast; only the decision is conditional
+        const int mvx = __shfl_sync(0xffffffffu, (int)mine.mv.x, who), mvy = __shfl_sync(0xffffffffu, (int)mine.mv.y, who);
+        const int dx = __shfl_sync(0xffffffffu, (int)mine.mvd.x, who), dy = __shfl_sync(0xffffffffu, (int)mine.mvd.y, who);
+        const int flag = __shfl_sync(0xffffffffu, mine.mvpFlag, who);
+        if (improved)
+        {
+            best.cost = cost;
+            best.mv = hvb_mv{(int16_t)mvx, (int16_t)mvy};
+            best.mvd = hvb_mv{(int16_t)dx, (int16_t)dy};
+            best.mvpFlag = flag;
+        }
+        return improved;
+    }
+
+    // one full-pel candidate given as a clamped full-pel vector: SAD with the whole warp, then consider
+    __device__ bool considerOne(Cand c, int fx, int fy)
+    {
+        const int sad = sadMulti(1, fx, fy);
+        c.cost += (long long)t.lambda * sad;
         if (c.cost < best.cost)
         {
             best = c;
@@ -150,37 +232,24 @@ struct Search
         return false;
     }
 
-    // StateMeFullPel::considerPattern (Search.hpp:1447-1482): `pattern` holds (x, y) pairs
+    // StateMeFullPel::considerPattern (Search.hpp:1447-1482): pattern entries j = 0, step, 2*step, ... < n
     __device__ bool considerPattern(hvb_mv origin, const int8_t *pattern, int n, int step, int dist)
     {
-        bool improved = false;
-        for (int j = 0; j < n; j += step)
+        const int nc = n / step;
+        int fx = 0, fy = 0;
+        if (lane < nc)
         {
-            const int8_t *p = pattern + 2 * j;
-            hvb_mv mv;
-            mv.x = (int16_t)((origin.x + dist * p[0]) / 4);
-            mv.y = (int16_t)((origin.y + dist * p[1]) / 4);
-            limit(mv);
-            const int sad = sadAt(mv.x, mv.y);
-            mv.x = (int16_t)(mv.x * 4);
-            mv.y = (int16_t)(mv.y * 4);
-            Cand c = makeCandidate(mv);
-            c.cost += (long long)t.lambda * sad;
-            improved |= consider(c);
+            const int8_t *p = pattern + 2 * lane * step;
+            fx = (int16_t)((origin.x + dist * p[0]) / 4);
+            fy = (int16_t)((origin.y + dist * p[1]) / 4);
+            limit(fx, fy);
         }
-        return improved;
+        const int sad = sadMulti(nc, fx, fy);
+        Cand c = makeCandidate(hvb_mv{(int16_t)(fx * 4), (int16_t)(fy * 4)});
+        c.cost += (long long)t.lambda * sad;
+        return considerLanes(c, lane < nc);
     }
 };
-
-__device__ __constant__ int8_t kDiamond4[8] = {-4, 0, 0, 4, 4, 0, 0, -4};
-__device__ __constant__ int8_t kHexagon8[16] = {0, -8, 8, -4, 8, 4, 0, 8, -8, 4, -8, -4, -8, 4, -8, -4};
-__device__ __constant__ int8_t kDiamond16[32] = {0,  -4, 1,  -3, 2,  -2, 3,  -1, 4,  0, 3,  1,  2,  2,  1,  3,
-                                                 0,  4,  -1, 3,  -2, 2,  -3, 1,  -4, 0, -3, -1, -2, -2, -1, -3};
-__device__ __constant__ int8_t kSquare4[8] = {-4, -4, -4, 4, 4, 4, 4, -4};
-__device__ __constant__ int8_t kLine4[8] = {0, 0, 1, 0, 2, 0, 3, 0};
-__device__ __constant__ int8_t kDiamond1[8] = {0, -1, -1, 0, 0, 1, 1, 0};
-__device__ __constant__ int8_t kHalf[16] = {-2, -2, 0, -2, 2, -2, -2, 0, 2, 0, -2, 2, 0, 2, 2, 2};
-__device__ __constant__ int8_t kQuarter[16] = {-1, -1, 0, -1, 1, -1, -1, 0, 1, 0, -1, 1, 0, 1, 1, 1};
 
 template <typename Sample>
 __device__ bool metTerminates(Search<Sample> &s)
@@ -199,36 +268,36 @@ __device__ bool fullPel(Search<Sample> &s, long long (&costMvdZero)[2])
     const int maxCounter = t.smallSearchWindow ? 2 : 3;
     const int raster = t.smallSearchWindow ? 120 : 240;
 
-    { // zero vector, not clamped (:2103-2129)
-        Cand c = s.makeCandidate(hvb_mv{0, 0});
-        c.cost += (long long)t.lambda * s.sadAt(0, 0);
-        if (s.consider(c) && t.met && metTerminates(s)) return true;
-    }
+    // zero vector, not clamped (:2103-2129)
+    if (s.considerOne(s.makeCandidate(hvb_mv{0, 0}), 0, 0) && t.met && metTerminates(s)) return true;
+
     for (int flag = 0; flag < 2; ++flag) // the predictors rounded to full-pel (:2131-2171)
     {
         Cand c;
         c.mvpFlag = flag;
-        c.mv.x = (int16_t)((int16_t)(t.mvp[flag].x + 1) >> 2);
-        c.mv.y = (int16_t)((int16_t)(t.mvp[flag].y + 1) >> 2);
-        s.limit(c.mv);
-        c.mv.x = (int16_t)(c.mv.x << 2);
-        c.mv.y = (int16_t)(c.mv.y << 2);
+        int fx = (int16_t)(t.mvp[flag].x + 1) >> 2, fy = (int16_t)(t.mvp[flag].y + 1) >> 2;
+        s.limit(fx, fy);
+        c.mv = hvb_mv{(int16_t)(fx << 2), (int16_t)(fy << 2)};
         c.mvd.x = (int16_t)(c.mv.x - t.mvp[flag].x);
         c.mvd.y = (int16_t)(c.mv.y - t.mvp[flag].y);
         c.cost = rateOfMvd(c.mvd.x, c.mvd.y) + t.rateMvpFlag[flag];
-        c.cost += (long long)t.lambda * s.sadAt(c.mv.x >> 2, c.mv.y >> 2);
+        const int sad = s.sadMulti(1, c.mv.x >> 2, c.mv.y >> 2);
+        c.cost += (long long)t.lambda * sad;
         costMvdZero[flag] = c.cost;
-        if (s.consider(c) && t.met && metTerminates(s)) return true;
+        bool better = false;
+        if (c.cost < s.best.cost)
+        {
+            s.best = c;
+            better = true;
+        }
+        if (better && t.met && metTerminates(s)) return true;
     }
     if (t.usePrev2Nx2N) // previous 2Nx2N integer vector (:2173-2198)
     {
-        hvb_mv mv{(int16_t)(t.prev2Nx2N.x >> 2), (int16_t)(t.prev2Nx2N.y >> 2)};
-        s.limit(mv);
-        mv.x = (int16_t)(mv.x << 2);
-        mv.y = (int16_t)(mv.y << 2);
-        Cand c = s.makeCandidate(mv);
-        c.cost += (long long)t.lambda * s.sadAt(mv.x >> 2, mv.y >> 2);
-        if (s.consider(c) && t.met && metTerminates(s)) return true;
+        int fx = t.prev2Nx2N.x >> 2, fy = t.prev2Nx2N.y >> 2;
+        s.limit(fx, fy);
+        const hvb_mv mv{(int16_t)(fx << 2), (int16_t)(fy << 2)};
+        if (s.considerOne(s.makeCandidate(mv), mv.x >> 2, mv.y >> 2) && t.met && metTerminates(s)) return true;
     }
 
     // star search (:2202-2247)
@@ -250,10 +319,25 @@ __device__ bool fullPel(Search<Sample> &s, long long (&costMvdZero)[2])
         distBest = 0;
         s.considerPattern(s.best.mv, kSquare4, 4, 1, 1);
     }
-    if (distBest > 5) // raster: absolute displacements on a 5-sample grid (:2258-2273)
-    {
-        for (int my = -raster; my <= raster; my += 20)
-            for (int mx = -raster; mx <= raster; mx += 80) s.considerPattern(hvb_mv{(int16_t)mx, (int16_t)my}, kLine4, 4, 1, 20);
+    if (distBest > 5) // raster (:2258-2273): rows of `line` patterns = a 5-sample grid of absolute displacements.
+    {                 // None of its candidates depends on `best`, so 32 of them are evaluated per round.
+        const int cols = 4 * ((2 * raster) / 80 + 1), rows = (2 * raster) / 20 + 1, total = rows * cols;
+        for (int base = 0; base < total; base += 32)
+        {
+            const int q = base + s.lane, nc = min(32, total - base);
+            int fx = 0, fy = 0;
+            if (q < total)
+            {
+                const int row = q / cols, col = q - row * cols;
+                fx = (-raster + 20 * col) / 4;
+                fy = (-raster + 20 * row) / 4;
+                s.limit(fx, fy);
+            }
+            const int sad = s.sadMulti(nc, fx, fy);
+            Cand c = s.makeCandidate(hvb_mv{(int16_t)(fx * 4), (int16_t)(fy * 4)});
+            c.cost += (long long)t.lambda * sad;
+            s.considerLanes(c, q < total);
+        }
         distBest = 5;
     }
     while (distBest > 0) // star refinement (:2276-2302)
@@ -274,73 +358,156 @@ __device__ bool fullPel(Search<Sample> &s, long long (&costMvdZero)[2])
     }
     if (!t.smallSearchWindow) // one-sample diamond until no improvement (:2303-2334)
     {
-        int j;
+        bool again;
         do
         {
-            hvb_mv mv[4];
-            int sad[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
+            int fx = 0, fy = 0;
+            if (s.lane < 4)
             {
-                mv[i].x = (int16_t)(s.best.mv.x / 4 + kDiamond1[2 * i]);
-                mv[i].y = (int16_t)(s.best.mv.y / 4 + kDiamond1[2 * i + 1]);
-                s.limit(mv[i]);
-                sad[i] = s.sadAt(mv[i].x, mv[i].y);
-                mv[i].x = (int16_t)(mv[i].x * 4);
-                mv[i].y = (int16_t)(mv[i].y * 4);
+                fx = (int16_t)(s.best.mv.x / 4 + kDiamond1[2 * s.lane]);
+                fy = (int16_t)(s.best.mv.y / 4 + kDiamond1[2 * s.lane + 1]);
+                s.limit(fx, fy);
             }
-            j = -1;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-            {
-                Cand c = s.makeCandidate(mv[i]);
-                c.cost += (long long)t.lambda * sad[i];
-                if (s.consider(c)) j = i;
-            }
-        } while (j >= 0);
+            const int sad = s.sadMulti(4, fx, fy);
+            Cand c = s.makeCandidate(hvb_mv{(int16_t)(fx * 4), (int16_t)(fy * 4)});
+            c.cost += (long long)t.lambda * sad;
+            again = s.considerLanes(c, s.lane < 4);
+        } while (again);
     }
     return false;
 }
 
-// costMv (Search.hpp:2003-2008): rateOf(mvd) + lambda * SATD(src, 8-tap prediction at quarter-pel mv)
-template <typename Sample>
-__device__ long long costMv(Search<Sample> &s, int16_t *mid, int16_t *pred, hvb_mv mv, hvb_mv mvd, int bitDepth)
+// ---- sub-pel stage -------------------------------------------------------------------------------
+
+// One column (lane j of a T-lane group) of one T x T tile of the 8-tap prediction at quarter-pel `mv`,
+// minus the source column, Hadamard-transformed; returns the tile's normalised SATD on every lane of the group.
+template <typename Sample, int LOG2T>
+__device__ __forceinline__ int tileSatd(const Search<Sample> &s, int tileX, int tileY, int mvx, int mvy, int j, int bitDepth)
 {
-    const hvb_me_task &t = s.t;
-    const int w = t.w, h = t.h;
+    constexpr int T = 1 << LOG2T;
     const int shift1 = min(4, bitDepth - 8), shift3 = max(2, 14 - bitDepth);
-    const Sample *r = s.ref + (intptr_t)(mv.y >> 2) * s.sr + (mv.x >> 2);
-    passH<Sample, 8>(mid, r, s.sr, w, h, mv.x & 3, shift1, s.lane);
-    __syncwarp();
-    int cy[8];
+    const int maxv = (1 << bitDepth) - 1;
+    const int xf = mvx & 3, yf = mvy & 3;
+    const Sample *R = s.ref + (intptr_t)(tileY * T + (mvy >> 2) - 3) * s.sr + (tileX * T + j + (mvx >> 2) - 3);
+    int cx[8], cy[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) cy[k] = coef<8>(mv.y & 3, k);
-    const int total = w * h, maxv = (1 << bitDepth) - 1;
-    for (int j = s.lane; j < total; j += 32)
+    for (int k = 0; k < 8; ++k)
     {
-        const int y = j / w, x = j - y * w;
-        pred[j] = (int16_t)hvbClip3(0, maxv, (passV<8>(mid, w, x, y, cy) + (1 << (5 + shift3))) >> (6 + shift3));
+        cx[k] = kLumaTaps[xf][k];
+        cy[k] = kLumaTaps[yf][k];
     }
-    __syncwarp();
-    int satd = hvbMeasureSatdLanes<Sample, int16_t>(s.src, s.ss, pred, w, w, h, s.lane, 32, sizeof(Sample) == 2 ? 2 : 0);
-    satd = hvbWarpSum(satd);
-    __syncwarp();
-    return rateOfMvd(mvd.x, mvd.y) + (long long)t.lambda * satd;
+    int d[T];
+    int win[8];
+#pragma unroll
+    for (int r = 0; r < T + 7; ++r)
+    {
+        // rows 0..2 and T+3.. are only needed by a vertical filter with a non-zero phase
+        int mid = 0;
+        if (yf || (r >= 3 && r < T + 3))
+        {
+            const Sample *p = R + r * s.sr;
+            if (xf)
+            {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) mid += cx[k] * (int)__ldg(p + k);
+                mid >>= shift1;
+            }
+            else
+                mid = ((int)__ldg(p + 3) << 6) >> shift1;
+        }
+#pragma unroll
+        for (int k = 0; k < 7; ++k) win[k] = win[k + 1];
+        win[7] = mid;
+        if (r >= 7)
+        {
+            int v = 0;
+            if (yf)
+            {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v += cy[k] * win[k];
+            }
+            else
+                v = 64 * win[3];
+            const int pred = hvbClip3(0, maxv, (v + (1 << (5 + shift3))) >> (6 + shift3));
+            d[r - 7] = (int)s.srcS[(tileY * T + r - 7) * s.t.w + tileX * T + j] - pred;
+        }
+    }
+    // vertical butterfly in registers
+#pragma unroll
+    for (int half = T / 2; half >= 1; half >>= 1)
+#pragma unroll
+        for (int base = 0; base < T; base += 2 * half)
+#pragma unroll
+            for (int i = 0; i < half; ++i)
+            {
+                const int a = d[base + i], b = d[base + i + half];
+                d[base + i] = a + b;
+                d[base + i + half] = a - b;
+            }
+    // horizontal butterfly across the T lanes of the group
+#pragma unroll
+    for (int m = 1; m < T; m <<= 1)
+#pragma unroll
+        for (int i = 0; i < T; ++i)
+        {
+            const int o = __shfl_xor_sync(0xffffffffu, d[i], m);
+            d[i] = (j & m) ? o - d[i] : d[i] + o;
+        }
+    int acc = 0;
+#pragma unroll
+    for (int i = 0; i < T; ++i) acc += abs(d[i]);
+#pragma unroll
+    for (int m = 1; m < T; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    // havoc/hadamard.cpp:81-97: 4x4 (s+1)>>1, 8x8 (s+2)>>2, 16-bit samples >> 2 more
+    acc = (acc + T / 4) >> (LOG2T - 1);
+    return sizeof(Sample) == 2 ? acc >> 2 : acc;
 }
 
-// patternSearch with maxIterations = 1 (Search.hpp:2011-2060)
-template <typename Sample>
-__device__ void patternSearch(Search<Sample> &s, int16_t *mid, int16_t *pred, const int8_t *pattern, bool tryOrigin, hvb_mv &mv,
-                              hvb_mv &mvd, long long &bestCost, int bitDepth)
+// measureSatd of the prediction at each of `nCand` quarter-pel vectors (sMv) against the source block
+template <typename Sample, int LOG2T>
+__device__ void subpelEval(const Search<Sample> &s, const int *sMvx, const int *sMvy, int nCand, int *sSatd, int bitDepth)
 {
-    if (tryOrigin) bestCost = costMv(s, mid, pred, mv, mvd, bitDepth);
-    int best = -1;
-    for (int i = 0; i < 8; ++i)
+    constexpr int T = 1 << LOG2T, kGroups = 32 / T;
+    const int tilesX = s.t.w >> LOG2T, tiles = tilesX * (s.t.h >> LOG2T), jobs = nCand * tiles;
+    const int group = s.lane / T, j = s.lane % T;
+    for (int base = 0; base < jobs; base += kGroups)
     {
-        const hvb_mv m{(int16_t)(mv.x + pattern[2 * i]), (int16_t)(mv.y + pattern[2 * i + 1])};
-        const hvb_mv d{(int16_t)(mvd.x + pattern[2 * i]), (int16_t)(mvd.y + pattern[2 * i + 1])};
-        const long long c = costMv(s, mid, pred, m, d, bitDepth);
-        if (c < bestCost)
+        const int job = base + group;
+        const bool valid = job < jobs;
+        const int jj = valid ? job : jobs - 1;
+        const int cand = jj / tiles, tile = jj - cand * tiles;
+        const int ty = tile / tilesX, tx = tile - ty * tilesX;
+        const int v = tileSatd<Sample, LOG2T>(s, tx, ty, sMvx[cand], sMvy[cand], j, bitDepth);
+        if (valid && j == 0) atomicAdd(&sSatd[cand], v);
+    }
+    __syncwarp();
+}
+
+// patternSearch with maxIterations = 1 (Search.hpp:2011-2060); all candidates of the pattern at once
+template <typename Sample>
+__device__ void patternSearch(Search<Sample> &s, int *sMvx, int *sMvy, int *sSatd, const int8_t *pattern, int n, bool tryOrigin,
+                              hvb_mv &mv, hvb_mv &mvd, long long &bestCost, int bitDepth)
+{
+    if (s.lane < n)
+    {
+        sMvx[s.lane] = mv.x + pattern[2 * s.lane];
+        sMvy[s.lane] = mv.y + pattern[2 * s.lane + 1];
+        sSatd[s.lane] = 0;
+    }
+    __syncwarp();
+    if (((s.t.w | s.t.h) & 7) == 0)
+        subpelEval<Sample, 3>(s, sMvx, sMvy, n, sSatd, bitDepth);
+    else
+        subpelEval<Sample, 2>(s, sMvx, sMvy, n, sSatd, bitDepth);
+    // costMv (:2003-2008) = rateOf(mvd) + lambda * SATD, considered in pattern order with a strict `<`
+    int best = -1;
+    for (int i = 0; i < n; ++i)
+    {
+        const int dx = pattern[2 * i], dy = pattern[2 * i + 1];
+        const long long c = rateOfMvd((int16_t)(mvd.x + dx), (int16_t)(mvd.y + dy)) + (long long)s.t.lambda * sSatd[i];
+        if (tryOrigin && i == 0)
+            bestCost = c; // entry 0 of the half-pel table is the origin
+        else if (c < bestCost)
         {
             best = i;
             bestCost = c;
@@ -353,6 +520,7 @@ __device__ void patternSearch(Search<Sample> &s, int16_t *mid, int16_t *pred, co
         mvd.x = (int16_t)(mvd.x + pattern[2 * best]);
         mvd.y = (int16_t)(mvd.y + pattern[2 * best + 1]);
     }
+    __syncwarp();
 }
 
 template <typename Sample>
@@ -360,15 +528,17 @@ __global__ void __launch_bounds__(kWarps * 32)
     meSearchKernel(const HvbPlane *__restrict__ planes, const hvb_me_task *__restrict__ tasks, int n, hvb_me_result *__restrict__ out,
                    int bitDepth)
 {
-    extern __shared__ __align__(16) unsigned char smemRaw[];
+    extern __shared__ __align__(16) uint32_t smemMe[];
+    constexpr int kWordsPerWarp = (sizeof(Sample) == 1 ? 64 * 64 / 4 : kSrcWords) + 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int16_t *mid = reinterpret_cast<int16_t *>(smemRaw + warp * kSmemPerWarp);
-    int16_t *pred = mid + kMidElems;
+    uint32_t *sSrc = smemMe + warp * kWordsPerWarp;
+    int *sScratch = reinterpret_cast<int *>(sSrc + kWordsPerWarp - 32);
+    int *sMvx = sScratch, *sMvy = sScratch + 10, *sSatd = sScratch + 20;
     const int warpsTotal = gridDim.x * kWarps;
     for (int i = blockIdx.x * kWarps + warp; i < n; i += warpsTotal)
     {
         const hvb_me_task t = tasks[i];
-        Search<Sample> s(t, planes, lane);
+        Search<Sample> s(t, planes, sSrc, lane);
         long long costMvdZero[2] = {0, 0};
         const bool early = fullPel(s, costMvdZero);
 
@@ -384,8 +554,8 @@ __global__ void __launch_bounds__(kWarps * 32)
         if (t.halfPel) // searchMotionUni (Search.hpp:1335-1347)
         {
             long long bestCost = 0;
-            patternSearch(s, mid, pred, kHalf, true, mv, mvd, bestCost, bitDepth);
-            if (t.quarterPel) patternSearch(s, mid, pred, kQuarter, false, mv, mvd, bestCost, bitDepth);
+            patternSearch(s, sMvx, sMvy, sSatd, kHalf9, 9, true, mv, mvd, bestCost, bitDepth);
+            if (t.quarterPel) patternSearch(s, sMvx, sMvy, sSatd, kQuarter8, 8, false, mv, mvd, bestCost, bitDepth);
             r.subpelCost = bestCost;
         }
         r.mv = mv;
@@ -406,19 +576,19 @@ extern "C" int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, i
     HvbStaged st;
     int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(hvb_me_result) * n, mem, &st);
     if (rc) return rc;
-    const int smem = kWarps * kSmemPerWarp;
     int blocks = (n + kWarps - 1) / kWarps;
-    const int cap = ctx->smCount * 3;
+    const int cap = ctx->smCount * 4;
     if (blocks > cap) blocks = cap;
     const auto *dT = static_cast<const hvb_me_task *>(st.dTasks);
     auto *dO = static_cast<hvb_me_result *>(st.dOut);
     if (ctx->bps == 1)
     {
-        cudaFuncSetAttribute(meSearchKernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        const int smem = kWarps * (64 * 64 / 4 + 32) * 4;
         meSearchKernel<uint8_t><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
     }
     else
     {
+        const int smem = kWarps * (kSrcWords + 32) * 4;
         cudaFuncSetAttribute(meSearchKernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         meSearchKernel<uint16_t><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
     }
