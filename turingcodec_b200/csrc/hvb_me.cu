@@ -33,6 +33,7 @@ namespace {
 
 constexpr int kWarps = 8;
 constexpr int kSrcWords = 64 * 64 / 2; // u16 worst case: 2 samples per word
+constexpr int kExtraWords = 32 + 15 * 32; // per warp: candidate scratch + the sub-pel horizontal-pass columns
 
 // ---- sample-type helpers: 32-bit words of 4 (u8) or 2 (u16) samples -------------------------------
 template <typename Sample>
@@ -113,6 +114,7 @@ struct Search
     int wpr, words, wprInv; // words per row, words in the block, ceil(65536 / wpr)
     Cand best;
     int nSad;
+    int *sMid; // shared: [15][32] ints, column `lane` is this lane's horizontal-pass output
 
     __device__ Search(const hvb_me_task &task, const HvbPlane *planes, uint32_t *smemSrc, int lane_) : t(task), lane(lane_)
     {
@@ -145,7 +147,7 @@ struct Search
 
     // SADs of `nc` (1..32) full-pel candidates at once.  Lane c < nc passes candidate c's displacement and
     // receives its SAD; the block's words are split over 32/nextpow2(nc) lanes per candidate.
-    __device__ int sadMulti(int nc, int mvx, int mvy)
+    __device__ __noinline__ int sadMulti(int nc, int mvx, int mvy)
     {
         nSad += nc;
         const int log2p = nc <= 1 ? 0 : 32 - __clz(nc - 1); // ceil(log2(nc))
@@ -189,7 +191,7 @@ struct Search
 
     // The reference considers candidates one after the other with a strict `<`: the winner is the first
     // candidate of least cost, and it replaces `best` only if it is strictly cheaper.  Lane c holds candidate c.
-    __device__ bool considerLanes(const Cand &mine, bool valid)
+    __device__ __noinline__ bool considerLanes(const Cand &mine, bool valid)
     {
         long long cost = valid ? mine.cost : 0x7fffffffffffffffLL;
         int who = lane;
@@ -233,7 +235,7 @@ struct Search
     }
 
     // StateMeFullPel::considerPattern (Search.hpp:1447-1482): pattern entries j = 0, step, 2*step, ... < n
-    __device__ bool considerPattern(hvb_mv origin, const int8_t *pattern, int n, int step, int dist)
+    __device__ __noinline__ bool considerPattern(hvb_mv origin, const int8_t *pattern, int n, int step, int dist)
     {
         const int nc = n / step;
         int fx = 0, fy = 0;
@@ -252,7 +254,7 @@ struct Search
 };
 
 template <typename Sample>
-__device__ bool metTerminates(Search<Sample> &s)
+__device__ __noinline__ bool metTerminates(Search<Sample> &s)
 {
     bool trigger = !s.considerPattern(s.best.mv, kDiamond4, 4, 1, 1);
     if (trigger && s.t.log2CbSize >= 5) trigger = !s.considerPattern(s.best.mv, kHexagon8, 8, 1, 1);
@@ -396,41 +398,46 @@ __device__ __forceinline__ int tileSatd(const Search<Sample> &s, int tileX, int 
         cx[k] = kLumaTaps[xf][k];
         cy[k] = kLumaTaps[yf][k];
     }
-    int d[T];
-    int win[8];
-#pragma unroll
-    for (int r = 0; r < T + 7; ++r)
+    // Horizontal pass: this lane's column of the (T+7)-row intermediate goes to the lane's own slots of the
+    // warp's shared scratch (no other lane reads them, so no barrier is needed).  The row loop stays rolled:
+    // the ncu capture of the fully unrolled version was dominated by instruction-cache misses.
+    // Rows 0..2 and T+3.. are only needed by a vertical filter with a non-zero phase.
+    int *mids = s.sMid + s.lane;
+    const int r0 = yf ? 0 : 3, r1 = yf ? T + 7 : T + 3;
+#pragma unroll 1
+    for (int r = r0; r < r1; ++r)
     {
-        // rows 0..2 and T+3.. are only needed by a vertical filter with a non-zero phase
-        int mid = 0;
-        if (yf || (r >= 3 && r < T + 3))
+        const Sample *p = R + r * s.sr;
+        int mid;
+        if (xf)
         {
-            const Sample *p = R + r * s.sr;
-            if (xf)
-            {
+            mid = 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) mid += cx[k] * (int)__ldg(p + k);
-                mid >>= shift1;
-            }
-            else
-                mid = ((int)__ldg(p + 3) << 6) >> shift1;
+            for (int k = 0; k < 8; ++k) mid += cx[k] * (int)__ldg(p + k);
+            mid >>= shift1;
         }
+        else
+            mid = ((int)__ldg(p + 3) << 6) >> shift1;
+        mids[r * 32] = mid;
+    }
+    int d[T];
+    const Sample *srcCol = s.srcS + (tileY * T) * s.t.w + tileX * T + j;
+    if (yf)
+    {
 #pragma unroll
-        for (int k = 0; k < 7; ++k) win[k] = win[k + 1];
-        win[7] = mid;
-        if (r >= 7)
+        for (int i = 0; i < T; ++i)
         {
             int v = 0;
-            if (yf)
-            {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v += cy[k] * win[k];
-            }
-            else
-                v = 64 * win[3];
-            const int pred = hvbClip3(0, maxv, (v + (1 << (5 + shift3))) >> (6 + shift3));
-            d[r - 7] = (int)s.srcS[(tileY * T + r - 7) * s.t.w + tileX * T + j] - pred;
+            for (int k = 0; k < 8; ++k) v += cy[k] * mids[(i + k) * 32];
+            d[i] = (int)srcCol[i * s.t.w] - hvbClip3(0, maxv, (v + (1 << (5 + shift3))) >> (6 + shift3));
         }
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < T; ++i)
+            d[i] = (int)srcCol[i * s.t.w] - hvbClip3(0, maxv, (64 * mids[(i + 3) * 32] + (1 << (5 + shift3))) >> (6 + shift3));
     }
     // vertical butterfly in registers
 #pragma unroll
@@ -485,7 +492,7 @@ __device__ void subpelEval(const Search<Sample> &s, const int *sMvx, const int *
 
 // patternSearch with maxIterations = 1 (Search.hpp:2011-2060); all candidates of the pattern at once
 template <typename Sample>
-__device__ void patternSearch(Search<Sample> &s, int *sMvx, int *sMvy, int *sSatd, const int8_t *pattern, int n, bool tryOrigin,
+__device__ __noinline__ void patternSearch(Search<Sample> &s, int *sMvx, int *sMvy, int *sSatd, const int8_t *pattern, int n, bool tryOrigin,
                               hvb_mv &mv, hvb_mv &mvd, long long &bestCost, int bitDepth)
 {
     if (s.lane < n)
@@ -529,16 +536,18 @@ __global__ void __launch_bounds__(kWarps * 32)
                    int bitDepth)
 {
     extern __shared__ __align__(16) uint32_t smemMe[];
-    constexpr int kWordsPerWarp = (sizeof(Sample) == 1 ? 64 * 64 / 4 : kSrcWords) + 32;
+    constexpr int kBlockWords = sizeof(Sample) == 1 ? 64 * 64 / 4 : kSrcWords;
+    constexpr int kWordsPerWarp = kBlockWords + kExtraWords;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *sSrc = smemMe + warp * kWordsPerWarp;
-    int *sScratch = reinterpret_cast<int *>(sSrc + kWordsPerWarp - 32);
+    int *sScratch = reinterpret_cast<int *>(sSrc + kBlockWords);
     int *sMvx = sScratch, *sMvy = sScratch + 10, *sSatd = sScratch + 20;
     const int warpsTotal = gridDim.x * kWarps;
     for (int i = blockIdx.x * kWarps + warp; i < n; i += warpsTotal)
     {
         const hvb_me_task t = tasks[i];
         Search<Sample> s(t, planes, sSrc, lane);
+        s.sMid = sScratch + 32;
         long long costMvdZero[2] = {0, 0};
         const bool early = fullPel(s, costMvdZero);
 
@@ -583,12 +592,13 @@ extern "C" int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, i
     auto *dO = static_cast<hvb_me_result *>(st.dOut);
     if (ctx->bps == 1)
     {
-        const int smem = kWarps * (64 * 64 / 4 + 32) * 4;
+        const int smem = kWarps * (64 * 64 / 4 + kExtraWords) * 4;
+        cudaFuncSetAttribute(meSearchKernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         meSearchKernel<uint8_t><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
     }
     else
     {
-        const int smem = kWarps * (kSrcWords + 32) * 4;
+        const int smem = kWarps * (kSrcWords + kExtraWords) * 4;
         cudaFuncSetAttribute(meSearchKernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         meSearchKernel<uint16_t><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
     }

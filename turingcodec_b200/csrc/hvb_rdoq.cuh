@@ -81,6 +81,13 @@ __device__ __forceinline__ void scanXY(int log2, int scanIdx, int pos, int &x, i
     }
 }
 
+__device__ __forceinline__ long long shflXor64(long long v, int m)
+{
+    const int lo = __shfl_xor_sync(0xffffffffu, (int)(v & 0xffffffffLL), m);
+    const int hi = __shfl_xor_sync(0xffffffffu, (int)(v >> 32), m);
+    return ((long long)hi << 32) | (unsigned)lo;
+}
+
 struct Engine
 {
     const hvb_rdoq_ctx *cx;
@@ -339,12 +346,24 @@ __device__ inline void signDataHiding(const Engine &e, int totalCg, int16_t *dst
 } // namespace hvb_rdoq
 
 // Runs on a full warp; dst/src are n*n int16 (shared or global); returns the OR of the coded levels on every lane.
+//
+// Structure (all lanes execute the same control flow; the level-coding state is kept identical on every lane):
+//   pre-pass   parallel: first non-zero rounding level in reverse scan order (lastSp) and the two
+//              "distortion if zero" sums the reference accumulates on the way there;
+//   stage 1    per 4x4 coefficient group, from lastSp's group down: 16 lanes derive everything that does not
+//              depend on the level-coding recurrence (position, |c|, rounding level, distortion, sig-flag
+//              context and its bit costs).  A group whose levels all round to zero -- the common case -- is then
+//              finished with two warp reductions; only groups containing non-zero levels walk their
+//              coefficients serially (the recurrence of Rdoq.cpp:762-803);
+//   stage 2    last-significant-position search, serial over the coded prefix;
+//   finish     parallel sign restoration, optional sign-data hiding.
 __device__ inline int hvbRdoqWarp(int16_t *dst, const int16_t *src, const hvb_rdoq_ctx *ctx, int qScale, int qShift, int iqScale,
                                   int log2, int cIdx, int scanIdx, bool isIntra, bool sdh, int bitDepth, HvbRdoqScratch *scratch,
                                   int lane)
 {
     using namespace hvb_rdoq;
     const int n = 1 << (2 * log2), totalCg = n >> 4, log2Cg = log2 - 2;
+    HvbRdoqScratch &s = *scratch;
 
     // scan table: coefficient-group order then the 4x4 order inside each group (Rdoq.cpp:399-412)
     for (int sp = lane; sp < n; sp += 32)
@@ -352,11 +371,10 @@ __device__ inline int hvbRdoqWarp(int16_t *dst, const int16_t *src, const hvb_rd
         int gx, gy, x, y;
         scanXY(log2Cg, scanIdx, sp >> 4, gx, gy);
         scanXY(2, scanIdx, sp & 15, x, y);
-        scratch->scan[sp] = (short)((((gy << 2) + y) << log2) + (gx << 2) + x);
+        s.scan[sp] = (short)((((gy << 2) + y) << log2) + (gx << 2) + x);
     }
     __syncwarp();
 
-    int cbf = 0, lastIdx = 0, lastSp = -1, absSum = 0;
     Engine e;
     e.cx = ctx;
     e.s = scratch;
@@ -364,7 +382,6 @@ __device__ inline int hvbRdoqWarp(int16_t *dst, const int16_t *src, const hvb_rd
     e.log2 = log2;
     e.cIdx = cIdx;
     e.scanIdx = scanIdx;
-    if (lane == 0)
     {
         // Rdoq::Rdoq (Rdoq.h:170-188); FixedPoint<int32,16>::set(double) = int32(d * 65536 + 0.5)
         const double lambda = ctx->lambda;
@@ -376,205 +393,270 @@ __device__ inline int hvbRdoqWarp(int16_t *dst, const int16_t *src, const hvb_rd
         e.iqScale = iqScale;
         e.iqShift = 20 - 14 - transformShift;
         e.iqOffset = 1 << (e.iqShift - 1);
+    }
 
-        HvbRdoqScratch &s = *scratch;
-        long long totalDist0 = 0, rdCostTu = 0;
-        long long rateCostCgSig[64];
-        unsigned long long csbf = 0;
-        int lastCg = -1;
-        int ctxSet = 0, g1Idx = 1, g1Cnt = 0, g2Cnt = 0, rice = 0;
-        const int g1Off = cIdx > 0 ? 16 : 0, g2Off = cIdx > 0 ? 4 : 0;
-        for (int i = 0; i < totalCg; ++i) rateCostCgSig[i] = 0;
+    // ---- pre-pass (Rdoq.cpp:104-118, :165-169: integer sums, any order gives the same value)
+    int lastSp = -1;
+    long long totalDist0 = 0;
+    for (int sp = lane; sp < n; sp += 32)
+    {
+        const int a = abs((int)src[s.scan[sp]]);
+        totalDist0 += e.dist(a);
+        if (((a * qScale + (1 << (qShift - 1))) >> qShift) > 0) lastSp = sp; // sp ascends: keeps this lane's maximum
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        lastSp = max(lastSp, __shfl_xor_sync(0xffffffffu, lastSp, o));
+        totalDist0 += shflXor64(totalDist0, o);
+    }
+    long long tailDist0 = 0; // what m_rdCostTu holds when the reverse scan reaches lastSp
+    for (int sp = lastSp + 1 + lane; sp < n; sp += 32)
+    {
+        const int pos = s.scan[sp];
+        tailDist0 += e.dist(abs((int)src[pos]));
+        dst[pos] = 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tailDist0 += shflXor64(tailDist0, o);
+    __syncwarp();
+    if (lastSp < 0) return 0; // every level rounds to zero (Rdoq.cpp:308-312); dst is all zero
 
-        // ---- stage 1 (Rdoq.cpp:89-305)
-        for (int cg = totalCg - 1; cg >= 0; --cg)
+    long long rdCostTu = tailDist0;
+    long long rateCostCgSig[64];
+    unsigned long long csbf = 0;
+    const int lastCg = lastSp >> 4;
+    int ctxSet = (lastSp < 16 || cIdx != 0) ? 0 : 2, g1Idx = 1, g1Cnt = 0, g2Cnt = 0, rice = 0;
+    const int g1Off = cIdx > 0 ? 16 : 0, g2Off = cIdx > 0 ? 4 : 0;
+    for (int i = 0; i < totalCg; ++i) rateCostCgSig[i] = 0;
+    const int kk = lane & 15; // lanes 16..31 mirror lanes 0..15
+
+    // ---- stage 1 (Rdoq.cpp:89-305), from the first coded position downwards
+    for (int cg = lastCg; cg >= 0; --cg)
+    {
+        int cgX, cgY, right, below;
+        scanXY(log2Cg, scanIdx, cg, cgX, cgY);
+        const int cgPos = cgY * (1 << log2Cg) + cgX;
+        cgNeighbours(csbf, cgX, cgY, log2, right, below);
+        const int prev = right + (below << 1);
+
+        // recurrence-free part of coefficient kk of this group
+        const int mySp = cg * 16 + kk, myPos = s.scan[mySp];
+        const int myA = abs((int)src[myPos]);
+        const int myScaled = myA * qScale;
+        const int myQ = mySp <= lastSp ? (myScaled + (1 << (qShift - 1))) >> qShift : 0;
+        const int mySc = sigCtxInc(prev, scanIdx, myPos & ((1 << log2) - 1), myPos >> log2, log2, cIdx);
+        const int myBits0 = bitsOf(0, ctx->sig_coeff_flag[mySc]), myBits1 = bitsOf(1, ctx->sig_coeff_flag[mySc]);
+        const long long myD0 = e.dist(myA);
+        const unsigned nzMask = __ballot_sync(0xffffffffu, myQ > 0) & 0xffffu;
+
+        const int cSig = (cIdx == 0 ? 0 : 2) + min(right + below, 1); // coded_sub_block_flag context (neighbours only)
+
+        if (nzMask == 0)
+        {
+            // Every level of the group rounds to zero (so this is not lastSp's group and all 16 positions are
+            // active): adjustLevel takes its q == 0 exit for each (Rdoq.cpp:466-476), the state does not move.
+            const long long myRateSig = e.lam(myBits0), myRd = myD0 + myRateSig;
+            if (lane < 16)
+            {
+                s.rdCostCoeff[mySp] = myRd;
+                s.rateCostSig[mySp] = myRateSig;
+                s.deltaU[myPos] = myScaled >> (qShift - 8);
+                s.sigDelta[myPos] = myBits1 - myBits0;
+                s.rateUp[myPos] = bitsOf(0, ctx->greater1_flag[4 * ctxSet + g1Idx + g1Off]);
+                s.rateDown[myPos] = 0;
+                dst[myPos] = 0;
+            }
+            long long sumRd = myRd, sumSig = myRateSig;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1)
+            {
+                sumRd += shflXor64(sumRd, o);
+                sumSig += shflXor64(sumSig, o);
+            }
+            rdCostTu += sumRd;
+            if (cg > 0)
+            {
+                // group boundary of updateEntropyCodingEngine (Rdoq.cpp:791-802)
+                rice = 0;
+                g1Cnt = 0;
+                g2Cnt = 0;
+                ctxSet = (cg == 1 || cIdx != 0) ? 0 : 2;
+                if (g1Idx == 0) ctxSet++;
+                g1Idx = 1;
+                // uncoded group: pay the cost of its flag, drop the significance costs (Rdoq.cpp:206-216)
+                const long long zero = e.lam(bitsOf(0, ctx->coded_sub_block_flag[cSig]));
+                rdCostTu += zero - sumSig;
+                rateCostCgSig[cg] = zero;
+            }
+            else
+                csbf |= 1ull << cgPos; // the DC group always counts as coded (Rdoq.cpp:299-303)
+            continue;
+        }
+
+        int nzBeforePos0 = 0;
+        long long cgDist0 = 0, cgRateSig = 0, cgRateSigPos0 = 0, cgRdCoeff = 0;
+        bool cgCoded = false;
+        for (int k = 15; k >= 0; --k)
+        {
+            const int sp = cg * 16 + k;
+            if (sp > lastSp) continue; // accounted for by the pre-pass (their rate terms are zero)
+            const int pos = __shfl_sync(0xffffffffu, myPos, k), a = __shfl_sync(0xffffffffu, myA, k);
+            const int q = __shfl_sync(0xffffffffu, myQ, k), sc = __shfl_sync(0xffffffffu, mySc, k);
+            const int scaled = a * qScale;
+            const long long d0 = e.dist(a);
+            const int g1Ctx = 4 * ctxSet + g1Idx + g1Off, g2Ctx = ctxSet + g2Off;
+            long long rdCost = 0, rateSig = 0;
+            const int level = adjustLevel(e, sp, a, q, sc, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt, sp == lastSp, rdCost, rateSig);
+            int up, down;
+            if (level > 0)
+            {
+                const int now = levelRate(e, level, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt);
+                up = levelRate(e, level + 1, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt) - now;
+                down = levelRate(e, level - 1, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt) - now;
+            }
+            else
+            {
+                up = bitsOf(0, ctx->greater1_flag[g1Ctx]);
+                down = 0;
+            }
+            if (lane == 0)
+            {
+                s.rdCostCoeff[sp] = rdCost;
+                s.rateCostSig[sp] = rateSig;
+                s.deltaU[pos] = (scaled - (level << qShift)) >> (qShift - 8);
+                s.sigDelta[pos] = sp != lastSp ? bitsOf(1, ctx->sig_coeff_flag[sc]) - bitsOf(0, ctx->sig_coeff_flag[sc]) : 0;
+                s.rateUp[pos] = up;
+                s.rateDown[pos] = down;
+                dst[pos] = (int16_t)level;
+            }
+            rdCostTu += rdCost;
+
+            // updateEntropyCodingEngine (Rdoq.cpp:762-803)
+            if (level >= baseLevel(g1Cnt, g2Cnt) && level > 3 * (1 << rice)) rice = min(rice + 1, 4);
+            if (level >= 1) g1Cnt++;
+            if (level > 1)
+            {
+                g1Idx = 0;
+                g2Cnt++;
+            }
+            else if (g1Idx < 3 && g1Idx > 0 && level)
+                g1Idx++;
+            if (k == 0 && sp > 0)
+            {
+                rice = 0;
+                g1Cnt = 0;
+                g2Cnt = 0;
+                ctxSet = (sp == 16 || cIdx != 0) ? 0 : 2;
+                if (g1Idx == 0) ctxSet++;
+                g1Idx = 1;
+            }
+
+            cgRateSig += rateSig;
+            if (k == 0) cgRateSigPos0 = rateSig;
+            if (level)
+            {
+                cgCoded = true;
+                cgRdCoeff += rdCost - rateSig;
+                cgDist0 += d0;
+                if (k != 0) nzBeforePos0++;
+            }
+        }
+        __syncwarp();
+        if (cgCoded) csbf |= 1ull << cgPos;
+
+        // coefficient-group zeroing (Rdoq.cpp:200-304)
+        if (cg)
+        {
+            const long long zero = e.lam(bitsOf(0, ctx->coded_sub_block_flag[cSig]));
+            if (!cgCoded)
+            {
+                rdCostTu += zero - cgRateSig;
+                rateCostCgSig[cg] = zero;
+            }
+            else if (cg < lastCg)
+            {
+                if (nzBeforePos0 == 0)
+                {
+                    rdCostTu -= cgRateSigPos0;
+                    cgRateSig -= cgRateSigPos0;
+                }
+                const long long one = e.lam(bitsOf(1, ctx->coded_sub_block_flag[cSig]));
+                const long long allZero = rdCostTu + zero + cgDist0 - cgRdCoeff - cgRateSig;
+                rdCostTu += one;
+                rateCostCgSig[cg] = one;
+                if (allZero < rdCostTu)
+                {
+                    csbf &= ~(1ull << cgPos);
+                    rdCostTu = allZero;
+                    rateCostCgSig[cg] = zero;
+                    if (lane < 16 && dst[myPos])
+                    {
+                        dst[myPos] = 0;
+                        s.rdCostCoeff[mySp] = myD0;
+                        s.rateCostSig[mySp] = 0;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        else
+            csbf |= 1ull << cgPos;
+    }
+
+    // ---- stage 2: last significant position (Rdoq.cpp:313-397)
+    int lastIdx = 0;
+    {
+        long long best;
+        {
+            const uint8_t st = (!isIntra && cIdx == 0) ? ctx->rqt_root_cbf[0] : (cIdx == 0 ? ctx->cbf_luma[1] : ctx->cbf_cbcr[0]);
+            best = totalDist0 + e.lam(bitsOf(0, st));
+            rdCostTu += e.lam(bitsOf(1, st));
+        }
+        bool found = false;
+        for (int cg = lastCg; cg >= 0 && !found; --cg)
         {
             int cgX, cgY;
             scanXY(log2Cg, scanIdx, cg, cgX, cgY);
             const int cgPos = cgY * (1 << log2Cg) + cgX;
-            int nzBeforePos0 = 0, right, below;
-            long long cgDist0 = 0, cgRateSig = 0, cgRateSigPos0 = 0, cgRdCoeff = 0;
-            cgNeighbours(csbf, cgX, cgY, log2, right, below);
-            const int prev = right + (below << 1);
-            bool cgCoded = false;
-
+            rdCostTu -= rateCostCgSig[cg];
+            if (!((csbf >> cgPos) & 1)) continue;
             for (int k = 15; k >= 0; --k)
             {
-                const int sp = cg * 16 + k, pos = s.scan[sp];
-                const int a = abs((int)src[pos]);
-                const int scaled = a * qScale;
-                const int q = (scaled + (1 << (qShift - 1))) >> qShift;
-                const long long d0 = e.dist(a);
-                totalDist0 += d0;
-                int level = q;
-                long long rdCost = 0, rateSig = 0;
-                if (q > 0 && lastSp < 0)
-                {
-                    lastSp = sp;
-                    ctxSet = (sp < 16 || cIdx != 0) ? 0 : 2;
-                    lastCg = cg;
-                }
-                if (lastSp >= 0)
-                {
-                    const int x = pos & ((1 << log2) - 1), y = pos >> log2;
-                    const int g1Ctx = 4 * ctxSet + g1Idx + g1Off, g2Ctx = ctxSet + g2Off;
-                    const int sc = sigCtxInc(prev, scanIdx, x, y, log2, cIdx);
-                    level = adjustLevel(e, sp, a, q, sc, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt, sp == lastSp, rdCost, rateSig);
-                    s.rdCostCoeff[sp] = rdCost;
-                    s.rateCostSig[sp] = rateSig;
-                    s.deltaU[pos] = (scaled - (level << qShift)) >> (qShift - 8);
-                    s.sigDelta[pos] = sp != lastSp ? bitsOf(1, ctx->sig_coeff_flag[sc]) - bitsOf(0, ctx->sig_coeff_flag[sc]) : 0;
-                    if (level > 0)
-                    {
-                        const int now = levelRate(e, level, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt);
-                        s.rateUp[pos] = levelRate(e, level + 1, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt) - now;
-                        s.rateDown[pos] = levelRate(e, level - 1, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt) - now;
-                    }
-                    else
-                    {
-                        s.rateUp[pos] = bitsOf(0, ctx->greater1_flag[g1Ctx]);
-                        s.rateDown[pos] = 0;
-                    }
-                    rdCostTu += rdCost;
-
-                    // updateEntropyCodingEngine (Rdoq.cpp:762-803)
-                    if (level >= baseLevel(g1Cnt, g2Cnt) && level > 3 * (1 << rice)) rice = min(rice + 1, 4);
-                    if (level >= 1) g1Cnt++;
-                    if (level > 1)
-                    {
-                        g1Idx = 0;
-                        g2Cnt++;
-                    }
-                    else if (g1Idx < 3 && g1Idx > 0 && level)
-                        g1Idx++;
-                    if ((sp & 15) == 0 && sp > 0)
-                    {
-                        rice = 0;
-                        g1Cnt = 0;
-                        g2Cnt = 0;
-                        ctxSet = (sp == 16 || cIdx != 0) ? 0 : 2;
-                        if (g1Idx == 0) ctxSet++;
-                        g1Idx = 1;
-                    }
-                }
-                else
-                    rdCostTu += d0;
-                dst[pos] = (int16_t)level;
-
-                cgRateSig += rateSig;
-                if (k == 0) cgRateSigPos0 = rateSig;
+                const int sp = cg * 16 + k;
+                if (sp > lastSp) continue;
+                const int pos = s.scan[sp];
+                const int level = dst[pos];
                 if (level)
                 {
-                    cgCoded = true;
-                    cgRdCoeff += rdCost - rateSig;
-                    cgDist0 += d0;
-                    if (k != 0) nzBeforePos0++;
-                }
-            }
-            if (cgCoded) csbf |= 1ull << cgPos;
-
-            // coefficient-group zeroing (Rdoq.cpp:200-304)
-            if (lastCg >= 0)
-            {
-                if (cg)
-                {
-                    cgNeighbours(csbf, cgX, cgY, log2, right, below);
-                    const int c = (cIdx == 0 ? 0 : 2) + min(right + below, 1);
-                    const long long zero = e.lam(bitsOf(0, ctx->coded_sub_block_flag[c]));
-                    if (!cgCoded)
+                    const int x = pos & ((1 << log2) - 1), y = pos >> log2;
+                    const long long lastCost = scanIdx == 2 ? lastPosCost(e, y, x) : lastPosCost(e, x, y);
+                    const long long total = rdCostTu + lastCost - s.rateCostSig[sp];
+                    if (total < best)
                     {
-                        rdCostTu += zero - cgRateSig;
-                        rateCostCgSig[cg] = zero;
+                        lastIdx = sp + 1;
+                        best = total;
                     }
-                    else if (cg < lastCg)
+                    if (level > 1)
                     {
-                        if (nzBeforePos0 == 0)
-                        {
-                            rdCostTu -= cgRateSigPos0;
-                            cgRateSig -= cgRateSigPos0;
-                        }
-                        const long long one = e.lam(bitsOf(1, ctx->coded_sub_block_flag[c]));
-                        long long allZero = rdCostTu + zero + cgDist0 - cgRdCoeff - cgRateSig;
-                        rdCostTu += one;
-                        rateCostCgSig[cg] = one;
-                        if (allZero < rdCostTu)
-                        {
-                            csbf &= ~(1ull << cgPos);
-                            rdCostTu = allZero;
-                            rateCostCgSig[cg] = zero;
-                            for (int k = 15; k >= 0; --k)
-                            {
-                                const int sp = cg * 16 + k, pos = s.scan[sp];
-                                if (dst[pos])
-                                {
-                                    dst[pos] = 0;
-                                    s.rdCostCoeff[sp] = e.dist0(sp);
-                                    s.rateCostSig[sp] = 0;
-                                }
-                            }
-                        }
+                        found = true;
+                        break;
                     }
+                    rdCostTu -= s.rdCostCoeff[sp];
+                    rdCostTu += e.dist0(sp);
                 }
                 else
-                    csbf |= 1ull << cgPos;
-            }
-        }
-
-        if (lastSp >= 0)
-        {
-            // ---- stage 2: last significant position (Rdoq.cpp:313-397)
-            long long best;
-            {
-                const uint8_t st = (!isIntra && cIdx == 0) ? ctx->rqt_root_cbf[0] : (cIdx == 0 ? ctx->cbf_luma[1] : ctx->cbf_cbcr[0]);
-                best = totalDist0 + e.lam(bitsOf(0, st));
-                rdCostTu += e.lam(bitsOf(1, st));
-            }
-            bool found = false;
-            for (int cg = lastCg; cg >= 0 && !found; --cg)
-            {
-                int cgX, cgY;
-                scanXY(log2Cg, scanIdx, cg, cgX, cgY);
-                const int cgPos = cgY * (1 << log2Cg) + cgX;
-                rdCostTu -= rateCostCgSig[cg];
-                if (!((csbf >> cgPos) & 1)) continue;
-                for (int k = 15; k >= 0; --k)
-                {
-                    const int sp = cg * 16 + k;
-                    if (sp > lastSp) continue;
-                    const int pos = s.scan[sp];
-                    if (dst[pos])
-                    {
-                        const int x = pos & ((1 << log2) - 1), y = pos >> log2;
-                        const long long lastCost = scanIdx == 2 ? lastPosCost(e, y, x) : lastPosCost(e, x, y);
-                        const long long total = rdCostTu + lastCost - s.rateCostSig[sp];
-                        if (total < best)
-                        {
-                            lastIdx = sp + 1;
-                            best = total;
-                        }
-                        if (dst[pos] > 1)
-                        {
-                            found = true;
-                            break;
-                        }
-                        rdCostTu -= s.rdCostCoeff[sp];
-                        rdCostTu += e.dist0(sp);
-                    }
-                    else
-                        rdCostTu -= s.rateCostSig[sp];
-                }
+                    rdCostTu -= s.rateCostSig[sp];
             }
         }
     }
-    lastIdx = __shfl_sync(0xffffffffu, lastIdx, 0);
-    lastSp = __shfl_sync(0xffffffffu, lastSp, 0);
     __syncwarp();
-    if (lastSp < 0) return 0; // every level rounded to zero: dst already holds zeros (Rdoq.cpp:308-312)
 
     // signs back, uncoded tail to zero (Rdoq.cpp:414-431) -- data parallel
+    int cbf = 0, absSum = 0;
     for (int sp = lane; sp <= lastSp; sp += 32)
     {
-        const int pos = scratch->scan[sp];
+        const int pos = s.scan[sp];
         if (sp < lastIdx)
         {
             const int level = dst[pos];

@@ -287,10 +287,14 @@ __global__ void __launch_bounds__(kWarps * 32)
             sA[warp][i] = (int16_t)dequantOne(q, task.iqscale, task.iqshift); // Reconstruct.cpp:822-826
         }
         __syncwarp();
-        invPass(M, sB[warp], sA[warp], log2n, dst, 7, lane);
-        __syncwarp();
-        invPass(M, sA[warp], sB[warp], log2n, dst, 20 - bitDepth, lane);
-        __syncwarp();
+        if (cbf)
+        {
+            invPass(M, sB[warp], sA[warp], log2n, dst, 7, lane);
+            __syncwarp();
+            invPass(M, sA[warp], sB[warp], log2n, dst, 20 - bitDepth, lane);
+            __syncwarp();
+        }
+        // all-zero levels: the inverse of a zero block is zero and sA already holds the (zero) dequantised block
         unsigned ssd = 0;
         for (int i = lane; i < count; i += 32)
         {

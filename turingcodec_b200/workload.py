@@ -137,6 +137,11 @@ def tu_tasks(width, height, src_pic, pred_pics, rec_pics, n_ctx, bit_depth=8, se
                 t = np.zeros(count, hvb.tu_task_t)
                 for name, pic in (("src", src_pic), ("pred", pred_pic), ("rec", rec_pic)):
                     t[name]["pic"], t[name]["cIdx"], t[name]["x"], t[name]["y"] = pic, c_idx, xs, ys
+                # the prediction is motion compensated: candidate k predicts from the picture k+1 frames away,
+                # displaced by the true global motion of synth.frame (+3,+2 luma samples per frame), so the
+                # residual is what an encoder sees after ME (noise + the independently moving centre layer)
+                t["pred"]["x"] += 3 * (cand + 1) // scale
+                t["pred"]["y"] += 2 * (cand + 1) // scale
                 t["levels"] = offset + np.arange(count) * n * n
                 t["log2n"], t["trType"], t["cIdx"] = log2n, 0, c_idx
                 t["flags"] = 1 | (is_intra << 1) | 4  # RDOQ + SDH (medium preset)
