@@ -1,4 +1,4 @@
-// hvb_rdoq.cuh -- rate-distortion optimised quantisation of one transform block on one warp.
+// hvb_rdoq.cuh -- rate-distortion optimised quantisation, one THREAD per transform block.
 //
 // Reference semantics (bit-exact): Rdoq::runQuantisation, turing/Rdoq.cpp:35-450, helpers :452-887,
 // signDataHiding :889-1023, constructor arithmetic turing/Rdoq.h:170-188; fixed-point cost algebra
@@ -7,26 +7,39 @@
 // ContextModel::getState() ^ bin = (state >> 1) ^ bin (Rdoq.cpp:26-31, ContextModel.h:58-61).
 //
 // The level decision of a coefficient depends on the CABAC level-coding state left behind by the
-// previous one (greater1/greater2 counters, Rice parameter, context set), so the walk over a block
-// is inherently serial (SURVEY.md section 7 "hard parts"); parallelism comes from running many
-// blocks at once.  The warp cooperates on what is parallel (scan table, sign restoration, zeroing)
-// and lane 0 walks the recurrence.  Per-coefficient state that the reference keeps in the Rdoq
-// object (40 KB per block) shrinks to two int64 and four int32 arrays in an L2-resident scratch
-// slice; "distortion if zero" is recomputed from the coefficient instead of stored, and the
-// reference's zero-initialised members are reproduced by construction (entries above the first
-// non-zero level are never written and read as zero) instead of a 40 KB memset per block.
+// previous one (greater1/greater2 counters, Rice parameter, context set), so the walk over one block
+// is inherently serial; parallelism has to come from running many blocks at
+// once.  The first version of this file gave a warp to each block and let lane 0 walk the recurrence:
+// the ncu capture showed 4 active threads per instruction and the kernel at 10x the cost of the
+// transforms around it.  Now the work is split by what is parallel:
+//
+//   warp, cooperative (hvbRdoqPrepass)   everything before the reverse scan meets its first non-zero
+//                                        rounding level: its position and the two "distortion if zero"
+//                                        sums the reference accumulates on the way (integer sums: any order);
+//   one thread per block (hvbRdoqThread) the recurrence, so a warp advances 32 blocks at a time.  A 4x4
+//                                        group whose levels all round to zero -- the common case -- costs
+//                                        two running sums; only groups with non-zero levels store
+//                                        per-coefficient records (the reference's 40 KB of Rdoq members per
+//                                        block shrink to 32 bytes per coefficient of a coded group).
 #pragma once
 #include "hvb_internal.cuh"
 
-struct HvbRdoqScratch
+// per-coefficient record: cost fields are indexed by scan position, sign-hiding fields by raster position
+struct HvbCoefRec
 {
-    long long rdCostCoeff[1024];
-    long long rateCostSig[1024];
-    int rateUp[1024], rateDown[1024], sigDelta[1024], deltaU[1024];
-    short scan[1024];
+    long long rdCost;  // m_rdCostCoeff
+    long long rateSig; // m_rateCostCoeffSig
+    int rateUp, rateDown, sigDelta, deltaU;
 };
 
-__host__ __device__ inline size_t hvbRdoqScratchBytes() { return (sizeof(HvbRdoqScratch) + 255) & ~size_t(255); }
+// result of the cooperative pre-pass of one block
+struct HvbRdoqMid
+{
+    int lastSp; // first position of the reverse scan whose rounding level is non-zero; -1: none; -2: block not RDOQ'd
+    int reserved;
+    long long totalDist0; // m_totalDistCoeff0
+    long long tailDist0;  // m_rdCostTu when the reverse scan reaches lastSp
+};
 
 namespace hvb_rdoq {
 
@@ -44,9 +57,16 @@ __device__ __constant__ int32_t kEntropyBits[128] = {
 
 __device__ __forceinline__ int bitsOf(int bin, uint8_t state) { return kEntropyBits[(state >> 1) ^ bin]; }
 
+__device__ __forceinline__ long long shflXor64(long long v, int m)
+{
+    const int lo = __shfl_xor_sync(0xffffffffu, (int)(v & 0xffffffffLL), m);
+    const int hi = __shfl_xor_sync(0xffffffffu, (int)(v >> 32), m);
+    return ((long long)hi << 32) | (unsigned)lo;
+}
+
 // scan position -> (x, y) inside a (1 << log2)^2 grid, log2 <= 3 (ScanOrder.h:32-101).
 // The up-right diagonal order is generated arithmetically: diagonal d holds min(d, n-1) - max(0, d-n+1) + 1 cells.
-__device__ __forceinline__ void scanXY(int log2, int scanIdx, int pos, int &x, int &y)
+__host__ __device__ inline void scanXY(int log2, int scanIdx, int pos, int &x, int &y)
 {
     const int n = 1 << log2;
     if (log2 == 0)
@@ -81,29 +101,54 @@ __device__ __forceinline__ void scanXY(int log2, int scanIdx, int pos, int &x, i
     }
 }
 
-__device__ __forceinline__ long long shflXor64(long long v, int m)
+// raster position of scan position sp of a (1 << log2)^2 block: group order, then the 4x4 order (Rdoq.cpp:399-412)
+__host__ __device__ inline int scanToRaster(int log2, int scanIdx, int sp)
 {
-    const int lo = __shfl_xor_sync(0xffffffffu, (int)(v & 0xffffffffLL), m);
-    const int hi = __shfl_xor_sync(0xffffffffu, (int)(v >> 32), m);
-    return ((long long)hi << 32) | (unsigned)lo;
+    int gx, gy, x, y;
+    scanXY(log2 - 2, scanIdx, sp >> 4, gx, gy);
+    scanXY(2, scanIdx, sp & 15, x, y);
+    return (((gy << 2) + y) << log2) + (gx << 2) + x;
 }
+
+// table of scanToRaster for log2 2..5 x scanIdx 0..2, 1024 entries each (filled by hvbRdoqInitTables)
+static __device__ short gScanTable[4 * 3 * 1024];
+__device__ __forceinline__ const short *scanTable(int log2, int scanIdx) { return gScanTable + ((log2 - 2) * 3 + scanIdx) * 1024; }
 
 struct Engine
 {
     const hvb_rdoq_ctx *cx;
-    HvbRdoqScratch *s;
+    HvbCoefRec *rec;
+    const short *scan;
     const int16_t *src;
     int lambda, distScale, shdFactor;
     int iqScale, iqShift, iqOffset;
     int log2, cIdx, scanIdx;
 
+    // Rdoq::Rdoq (Rdoq.h:170-188); FixedPoint<int32,16>::set(double) = int32(d * 65536 + 0.5)
+    __device__ __forceinline__ void init(const hvb_rdoq_ctx *ctx, int iqScale_, int log2_, int cIdx_, int scanIdx_, int bitDepth)
+    {
+        cx = ctx;
+        log2 = log2_;
+        cIdx = cIdx_;
+        scanIdx = scanIdx_;
+        scan = scanTable(log2_, scanIdx_);
+        const double lam = ctx->lambda;
+        lambda = (int)(lam * 65536 + 0.5);
+        shdFactor = (int)(iqScale_ * iqScale_ / lam / 16 + 0.5);
+        const int transformShift = 15 - bitDepth - log2_;
+        const int distShift = 15 - 2 * transformShift - 2 * (bitDepth - 8);
+        distScale = (int)((double)(1 << distShift) * 65536 + 0.5);
+        iqScale = iqScale_;
+        iqShift = 20 - 14 - transformShift;
+        iqOffset = 1 << (iqShift - 1);
+    }
     __device__ __forceinline__ long long lam(int rate) const { return (long long)lambda * rate; }
     __device__ __forceinline__ long long dist(int err) const
     {
         const int sq = (int)((unsigned)err * (unsigned)err);
         return (long long)sq * distScale;
     }
-    __device__ __forceinline__ long long dist0(int sp) const { return dist(abs((int)src[s->scan[sp]])); }
+    __device__ __forceinline__ long long dist0(int sp) const { return dist(abs((int)src[scan[sp]])); }
 };
 
 __device__ __forceinline__ int baseLevel(int g1Cnt, int g2Cnt) { return g1Cnt < 8 ? 2 + (g2Cnt < 1) : 1; }
@@ -205,8 +250,8 @@ __device__ inline int levelRate(const Engine &e, int level, int g1Ctx, int g2Ctx
 }
 
 // Rdoq.cpp:452-510
-__device__ inline int adjustLevel(Engine &e, int sp, int absCoeff, int q, int sigCtx, int g1Ctx, int g2Ctx, int rice, int g1Cnt,
-                                  int g2Cnt, bool isLast, long long &rdCost, long long &rateSig)
+__device__ inline int adjustLevel(const Engine &e, int absCoeff, int q, int sigCtx, int g1Ctx, int g2Ctx, int rice, int g1Cnt, int g2Cnt,
+                                  bool isLast, long long &rdCost, long long &rateSig)
 {
     long long sigCost = 0;
     int best = 0;
@@ -261,7 +306,7 @@ __device__ inline long long lastPosCost(const Engine &e, int xC, int yC)
     return e.lam(rate);
 }
 
-// neighbours right (bit 0) / below (bit 1) of coefficient group (xS, yS) in the 64-bit csbf mask
+// neighbours right / below of coefficient group (xS, yS) in the 64-bit csbf mask (Rdoq.cpp:601-617, :675-697)
 __device__ __forceinline__ void cgNeighbours(unsigned long long csbf, int xS, int yS, int log2, int &right, int &below)
 {
     const int wcg = 1 << (log2 - 2);
@@ -269,14 +314,13 @@ __device__ __forceinline__ void cgNeighbours(unsigned long long csbf, int xS, in
     below = yS < wcg - 1 ? (int)((csbf >> ((yS + 1) * wcg + xS)) & 1) : 0;
 }
 
-// Rdoq.cpp:889-1023
-__device__ inline void signDataHiding(const Engine &e, int totalCg, int16_t *dst)
+// Rdoq.cpp:889-1023.  Only groups that still hold a non-zero level are looked at, and those have records.
+__device__ inline void signDataHiding(const Engine &e, int lastCgCoded, int16_t *dst)
 {
-    const HvbRdoqScratch &s = *e.s;
     int lastCG = -1;
-    for (int cg = totalCg - 1; cg >= 0; --cg)
+    for (int cg = lastCgCoded; cg >= 0; --cg)
     {
-        const short *sc = s.scan + (cg << 4);
+        const short *sc = e.scan + (cg << 4);
         int firstNZ = 16, lastNZ = -1, absSum = 0;
         for (int k = 15; k >= 0; --k)
             if (dst[sc[k]])
@@ -284,6 +328,7 @@ __device__ inline void signDataHiding(const Engine &e, int totalCg, int16_t *dst
                 lastNZ = k;
                 break;
             }
+        if (lastNZ < 0) continue; // an empty group changes nothing (and cannot be the first coded one)
         for (int k = 0; k < 16; ++k)
             if (dst[sc[k]])
             {
@@ -291,7 +336,7 @@ __device__ inline void signDataHiding(const Engine &e, int totalCg, int16_t *dst
                 break;
             }
         for (int k = firstNZ; k <= lastNZ; ++k) absSum += dst[sc[k]];
-        if (lastNZ >= 0 && lastCG == -1) lastCG = 1;
+        if (lastCG == -1) lastCG = 1;
         if (lastNZ - firstNZ >= 4)
         {
             const int signbit = dst[sc[firstNZ]] > 0 ? 0 : 1;
@@ -302,11 +347,12 @@ __device__ inline void signDataHiding(const Engine &e, int totalCg, int16_t *dst
                 {
                     const int pos = sc[k];
                     const int level = dst[pos];
+                    const HvbCoefRec &r = e.rec[pos];
                     int cost, change;
                     if (level != 0)
                     {
-                        const int up = e.shdFactor * (-s.deltaU[pos]) + s.rateUp[pos];
-                        int down = e.shdFactor * s.deltaU[pos] + s.rateDown[pos] - (abs(level) == 1 ? ((1 << 15) + s.sigDelta[pos]) : 0);
+                        const int up = e.shdFactor * (-r.deltaU) + r.rateUp;
+                        int down = e.shdFactor * r.deltaU + r.rateDown - (abs(level) == 1 ? ((1 << 15) + r.sigDelta) : 0);
                         if (lastCG == 1 && lastNZ == k && abs(level) == 1) down -= 4 << 15;
                         if (up < down)
                         {
@@ -321,7 +367,7 @@ __device__ inline void signDataHiding(const Engine &e, int totalCg, int16_t *dst
                     }
                     else
                     {
-                        cost = e.shdFactor * (-abs(s.deltaU[pos])) + (1 << 15) + s.rateUp[pos] + s.sigDelta[pos];
+                        cost = e.shdFactor * (-abs(r.deltaU)) + (1 << 15) + r.rateUp + r.sigDelta;
                         change = 1;
                         if (k < firstNZ && (e.src[pos] >= 0 ? 0 : 1) != signbit) cost = 0x7fffffff;
                     }
@@ -345,91 +391,64 @@ __device__ inline void signDataHiding(const Engine &e, int totalCg, int16_t *dst
 
 } // namespace hvb_rdoq
 
-// Runs on a full warp; dst/src are n*n int16 (shared or global); returns the OR of the coded levels on every lane.
-//
-// Structure (all lanes execute the same control flow; the level-coding state is kept identical on every lane):
-//   pre-pass   parallel: first non-zero rounding level in reverse scan order (lastSp) and the two
-//              "distortion if zero" sums the reference accumulates on the way there;
-//   stage 1    per 4x4 coefficient group, from lastSp's group down: 16 lanes derive everything that does not
-//              depend on the level-coding recurrence (position, |c|, rounding level, distortion, sig-flag
-//              context and its bit costs).  A group whose levels all round to zero -- the common case -- is then
-//              finished with two warp reductions; only groups containing non-zero levels walk their
-//              coefficients serially (the recurrence of Rdoq.cpp:762-803);
-//   stage 2    last-significant-position search, serial over the coded prefix;
-//   finish     parallel sign restoration, optional sign-data hiding.
-__device__ inline int hvbRdoqWarp(int16_t *dst, const int16_t *src, const hvb_rdoq_ctx *ctx, int qScale, int qShift, int iqScale,
-                                  int log2, int cIdx, int scanIdx, bool isIntra, bool sdh, int bitDepth, HvbRdoqScratch *scratch,
-                                  int lane)
+// Cooperative pre-pass on a warp (Rdoq.cpp:104-118, :165-169).  Also writes zero levels everywhere, so the serial
+// stage only touches coded positions.  `dst` may be shared or global.
+__device__ inline HvbRdoqMid hvbRdoqPrepass(int16_t *dst, const int16_t *src, const hvb_rdoq_ctx *ctx, int qScale, int qShift, int iqScale,
+                                            int log2, int cIdx, int scanIdx, int bitDepth, int lane)
 {
     using namespace hvb_rdoq;
-    const int n = 1 << (2 * log2), totalCg = n >> 4, log2Cg = log2 - 2;
-    HvbRdoqScratch &s = *scratch;
-
-    // scan table: coefficient-group order then the 4x4 order inside each group (Rdoq.cpp:399-412)
-    for (int sp = lane; sp < n; sp += 32)
-    {
-        int gx, gy, x, y;
-        scanXY(log2Cg, scanIdx, sp >> 4, gx, gy);
-        scanXY(2, scanIdx, sp & 15, x, y);
-        s.scan[sp] = (short)((((gy << 2) + y) << log2) + (gx << 2) + x);
-    }
-    __syncwarp();
-
+    const int n = 1 << (2 * log2);
     Engine e;
-    e.cx = ctx;
-    e.s = scratch;
-    e.src = src;
-    e.log2 = log2;
-    e.cIdx = cIdx;
-    e.scanIdx = scanIdx;
-    {
-        // Rdoq::Rdoq (Rdoq.h:170-188); FixedPoint<int32,16>::set(double) = int32(d * 65536 + 0.5)
-        const double lambda = ctx->lambda;
-        e.lambda = (int)(lambda * 65536 + 0.5);
-        e.shdFactor = (int)(iqScale * iqScale / lambda / 16 + 0.5);
-        const int transformShift = 15 - bitDepth - log2;
-        const int distShift = 15 - 2 * transformShift - 2 * (bitDepth - 8);
-        e.distScale = (int)((double)(1 << distShift) * 65536 + 0.5);
-        e.iqScale = iqScale;
-        e.iqShift = 20 - 14 - transformShift;
-        e.iqOffset = 1 << (e.iqShift - 1);
-    }
-
-    // ---- pre-pass (Rdoq.cpp:104-118, :165-169: integer sums, any order gives the same value)
+    e.init(ctx, iqScale, log2, cIdx, scanIdx, bitDepth);
     int lastSp = -1;
-    long long totalDist0 = 0;
+    long long total = 0;
     for (int sp = lane; sp < n; sp += 32)
     {
-        const int a = abs((int)src[s.scan[sp]]);
-        totalDist0 += e.dist(a);
+        const int pos = e.scan[sp];
+        const int a = abs((int)src[pos]);
+        total += e.dist(a);
         if (((a * qScale + (1 << (qShift - 1))) >> qShift) > 0) lastSp = sp; // sp ascends: keeps this lane's maximum
+        dst[pos] = 0;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
     {
         lastSp = max(lastSp, __shfl_xor_sync(0xffffffffu, lastSp, o));
-        totalDist0 += shflXor64(totalDist0, o);
+        total += shflXor64(total, o);
     }
-    long long tailDist0 = 0; // what m_rdCostTu holds when the reverse scan reaches lastSp
-    for (int sp = lastSp + 1 + lane; sp < n; sp += 32)
-    {
-        const int pos = s.scan[sp];
-        tailDist0 += e.dist(abs((int)src[pos]));
-        dst[pos] = 0;
-    }
+    long long tail = 0;
+    for (int sp = lastSp + 1 + lane; sp < n; sp += 32) tail += e.dist(abs((int)src[e.scan[sp]]));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tailDist0 += shflXor64(tailDist0, o);
-    __syncwarp();
-    if (lastSp < 0) return 0; // every level rounds to zero (Rdoq.cpp:308-312); dst is all zero
+    for (int o = 16; o > 0; o >>= 1) tail += shflXor64(tail, o);
+    HvbRdoqMid m;
+    m.lastSp = lastSp;
+    m.reserved = 0;
+    m.totalDist0 = total;
+    m.tailDist0 = tail;
+    return m;
+}
 
-    long long rdCostTu = tailDist0;
+// The serial stages of Rdoq::runQuantisation for one block on one thread.  `dst` holds zeros on entry (pre-pass),
+// `rec` has room for n records.  Returns the OR of the coded levels.
+__device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_rdoq_ctx *ctx, const HvbRdoqMid &mid, int qScale, int qShift,
+                                    int iqScale, int log2, int cIdx, int scanIdx, bool isIntra, bool sdh, int bitDepth, HvbCoefRec *rec)
+{
+    using namespace hvb_rdoq;
+    const int lastSp = mid.lastSp;
+    if (lastSp < 0) return 0; // every level rounds to zero (Rdoq.cpp:308-312)
+    Engine e;
+    e.init(ctx, iqScale, log2, cIdx, scanIdx, bitDepth);
+    e.rec = rec;
+    e.src = src;
+    const int log2Cg = log2 - 2, mask = (1 << log2) - 1;
+
+    long long rdCostTu = mid.tailDist0;
     long long rateCostCgSig[64];
     unsigned long long csbf = 0;
     const int lastCg = lastSp >> 4;
     int ctxSet = (lastSp < 16 || cIdx != 0) ? 0 : 2, g1Idx = 1, g1Cnt = 0, g2Cnt = 0, rice = 0;
     const int g1Off = cIdx > 0 ? 16 : 0, g2Off = cIdx > 0 ? 4 : 0;
-    for (int i = 0; i < totalCg; ++i) rateCostCgSig[i] = 0;
-    const int kk = lane & 15; // lanes 16..31 mirror lanes 0..15
+    for (int i = 0; i <= lastCg; ++i) rateCostCgSig[i] = 0;
 
     // ---- stage 1 (Rdoq.cpp:89-305), from the first coded position downwards
     for (int cg = lastCg; cg >= 0; --cg)
@@ -439,58 +458,42 @@ __device__ inline int hvbRdoqWarp(int16_t *dst, const int16_t *src, const hvb_rd
         const int cgPos = cgY * (1 << log2Cg) + cgX;
         cgNeighbours(csbf, cgX, cgY, log2, right, below);
         const int prev = right + (below << 1);
-
-        // recurrence-free part of coefficient kk of this group
-        const int mySp = cg * 16 + kk, myPos = s.scan[mySp];
-        const int myA = abs((int)src[myPos]);
-        const int myScaled = myA * qScale;
-        const int myQ = mySp <= lastSp ? (myScaled + (1 << (qShift - 1))) >> qShift : 0;
-        const int mySc = sigCtxInc(prev, scanIdx, myPos & ((1 << log2) - 1), myPos >> log2, log2, cIdx);
-        const int myBits0 = bitsOf(0, ctx->sig_coeff_flag[mySc]), myBits1 = bitsOf(1, ctx->sig_coeff_flag[mySc]);
-        const long long myD0 = e.dist(myA);
-        const unsigned nzMask = __ballot_sync(0xffffffffu, myQ > 0) & 0xffffu;
-
         const int cSig = (cIdx == 0 ? 0 : 2) + min(right + below, 1); // coded_sub_block_flag context (neighbours only)
+        const short *sc = e.scan + (cg << 4);
 
-        if (nzMask == 0)
+        // A group whose levels all round to zero (never lastSp's group): adjustLevel takes its q == 0 exit for
+        // every coefficient (Rdoq.cpp:466-476), the state does not move, and since an uncoded group is skipped
+        // by stage 2 and by sign hiding, only the two sums are needed.
+        // (The DC group is always treated as coded, so stage 2 reads its records: it takes the general path.)
+        bool anyLevel = cg == 0;
+        long long sumRd = 0, sumSig = 0;
+        for (int k = 0; k < 16 && !anyLevel; ++k)
         {
-            // Every level of the group rounds to zero (so this is not lastSp's group and all 16 positions are
-            // active): adjustLevel takes its q == 0 exit for each (Rdoq.cpp:466-476), the state does not move.
-            const long long myRateSig = e.lam(myBits0), myRd = myD0 + myRateSig;
-            if (lane < 16)
+            const int pos = sc[k];
+            const int a = abs((int)src[pos]);
+            if ((cg * 16 + k <= lastSp) && ((a * qScale + (1 << (qShift - 1))) >> qShift) > 0)
             {
-                s.rdCostCoeff[mySp] = myRd;
-                s.rateCostSig[mySp] = myRateSig;
-                s.deltaU[myPos] = myScaled >> (qShift - 8);
-                s.sigDelta[myPos] = myBits1 - myBits0;
-                s.rateUp[myPos] = bitsOf(0, ctx->greater1_flag[4 * ctxSet + g1Idx + g1Off]);
-                s.rateDown[myPos] = 0;
-                dst[myPos] = 0;
+                anyLevel = true;
+                break;
             }
-            long long sumRd = myRd, sumSig = myRateSig;
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1)
-            {
-                sumRd += shflXor64(sumRd, o);
-                sumSig += shflXor64(sumSig, o);
-            }
+            const long long rs = e.lam(bitsOf(0, ctx->sig_coeff_flag[sigCtxInc(prev, scanIdx, pos & mask, pos >> log2, log2, cIdx)]));
+            sumSig += rs;
+            sumRd += e.dist(a) + rs;
+        }
+        if (!anyLevel)
+        {
             rdCostTu += sumRd;
-            if (cg > 0)
-            {
-                // group boundary of updateEntropyCodingEngine (Rdoq.cpp:791-802)
-                rice = 0;
-                g1Cnt = 0;
-                g2Cnt = 0;
-                ctxSet = (cg == 1 || cIdx != 0) ? 0 : 2;
-                if (g1Idx == 0) ctxSet++;
-                g1Idx = 1;
-                // uncoded group: pay the cost of its flag, drop the significance costs (Rdoq.cpp:206-216)
-                const long long zero = e.lam(bitsOf(0, ctx->coded_sub_block_flag[cSig]));
-                rdCostTu += zero - sumSig;
-                rateCostCgSig[cg] = zero;
-            }
-            else
-                csbf |= 1ull << cgPos; // the DC group always counts as coded (Rdoq.cpp:299-303)
+            // group boundary of updateEntropyCodingEngine (Rdoq.cpp:791-802); cg > 0 here
+            rice = 0;
+            g1Cnt = 0;
+            g2Cnt = 0;
+            ctxSet = (cg == 1 || cIdx != 0) ? 0 : 2;
+            if (g1Idx == 0) ctxSet++;
+            g1Idx = 1;
+            // uncoded group: pay for its flag, drop the significance costs (Rdoq.cpp:206-216)
+            const long long zero = e.lam(bitsOf(0, ctx->coded_sub_block_flag[cSig]));
+            rdCostTu += zero - sumSig;
+            rateCostCgSig[cg] = zero;
             continue;
         }
 
@@ -501,34 +504,31 @@ __device__ inline int hvbRdoqWarp(int16_t *dst, const int16_t *src, const hvb_rd
         {
             const int sp = cg * 16 + k;
             if (sp > lastSp) continue; // accounted for by the pre-pass (their rate terms are zero)
-            const int pos = __shfl_sync(0xffffffffu, myPos, k), a = __shfl_sync(0xffffffffu, myA, k);
-            const int q = __shfl_sync(0xffffffffu, myQ, k), sc = __shfl_sync(0xffffffffu, mySc, k);
+            const int pos = sc[k];
+            const int a = abs((int)src[pos]);
             const int scaled = a * qScale;
+            const int q = (scaled + (1 << (qShift - 1))) >> qShift;
+            const int sigCtx = sigCtxInc(prev, scanIdx, pos & mask, pos >> log2, log2, cIdx);
             const long long d0 = e.dist(a);
             const int g1Ctx = 4 * ctxSet + g1Idx + g1Off, g2Ctx = ctxSet + g2Off;
             long long rdCost = 0, rateSig = 0;
-            const int level = adjustLevel(e, sp, a, q, sc, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt, sp == lastSp, rdCost, rateSig);
-            int up, down;
+            const int level = adjustLevel(e, a, q, sigCtx, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt, sp == lastSp, rdCost, rateSig);
+            rec[sp].rdCost = rdCost;
+            rec[sp].rateSig = rateSig;
+            HvbCoefRec &r = rec[pos];
+            r.deltaU = (scaled - (level << qShift)) >> (qShift - 8);
+            r.sigDelta = sp != lastSp ? bitsOf(1, ctx->sig_coeff_flag[sigCtx]) - bitsOf(0, ctx->sig_coeff_flag[sigCtx]) : 0;
             if (level > 0)
             {
                 const int now = levelRate(e, level, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt);
-                up = levelRate(e, level + 1, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt) - now;
-                down = levelRate(e, level - 1, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt) - now;
+                r.rateUp = levelRate(e, level + 1, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt) - now;
+                r.rateDown = levelRate(e, level - 1, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt) - now;
+                dst[pos] = (int16_t)level;
             }
             else
             {
-                up = bitsOf(0, ctx->greater1_flag[g1Ctx]);
-                down = 0;
-            }
-            if (lane == 0)
-            {
-                s.rdCostCoeff[sp] = rdCost;
-                s.rateCostSig[sp] = rateSig;
-                s.deltaU[pos] = (scaled - (level << qShift)) >> (qShift - 8);
-                s.sigDelta[pos] = sp != lastSp ? bitsOf(1, ctx->sig_coeff_flag[sc]) - bitsOf(0, ctx->sig_coeff_flag[sc]) : 0;
-                s.rateUp[pos] = up;
-                s.rateDown[pos] = down;
-                dst[pos] = (int16_t)level;
+                r.rateUp = bitsOf(0, ctx->greater1_flag[g1Ctx]);
+                r.rateDown = 0;
             }
             rdCostTu += rdCost;
 
@@ -562,7 +562,6 @@ __device__ inline int hvbRdoqWarp(int16_t *dst, const int16_t *src, const hvb_rd
                 if (k != 0) nzBeforePos0++;
             }
         }
-        __syncwarp();
         if (cgCoded) csbf |= 1ull << cgPos;
 
         // coefficient-group zeroing (Rdoq.cpp:200-304)
@@ -587,16 +586,11 @@ __device__ inline int hvbRdoqWarp(int16_t *dst, const int16_t *src, const hvb_rd
                 rateCostCgSig[cg] = one;
                 if (allZero < rdCostTu)
                 {
+                    // the group is dropped: it becomes invisible to stage 2 and to sign hiding, so its records die with it
                     csbf &= ~(1ull << cgPos);
                     rdCostTu = allZero;
                     rateCostCgSig[cg] = zero;
-                    if (lane < 16 && dst[myPos])
-                    {
-                        dst[myPos] = 0;
-                        s.rdCostCoeff[mySp] = myD0;
-                        s.rateCostSig[mySp] = 0;
-                    }
-                    __syncwarp();
+                    for (int k = 0; k < 16; ++k) dst[sc[k]] = 0;
                 }
             }
         }
@@ -607,12 +601,9 @@ __device__ inline int hvbRdoqWarp(int16_t *dst, const int16_t *src, const hvb_rd
     // ---- stage 2: last significant position (Rdoq.cpp:313-397)
     int lastIdx = 0;
     {
-        long long best;
-        {
-            const uint8_t st = (!isIntra && cIdx == 0) ? ctx->rqt_root_cbf[0] : (cIdx == 0 ? ctx->cbf_luma[1] : ctx->cbf_cbcr[0]);
-            best = totalDist0 + e.lam(bitsOf(0, st));
-            rdCostTu += e.lam(bitsOf(1, st));
-        }
+        const uint8_t st = (!isIntra && cIdx == 0) ? ctx->rqt_root_cbf[0] : (cIdx == 0 ? ctx->cbf_luma[1] : ctx->cbf_cbcr[0]);
+        long long best = mid.totalDist0 + e.lam(bitsOf(0, st));
+        rdCostTu += e.lam(bitsOf(1, st));
         bool found = false;
         for (int cg = lastCg; cg >= 0 && !found; --cg)
         {
@@ -625,13 +616,13 @@ __device__ inline int hvbRdoqWarp(int16_t *dst, const int16_t *src, const hvb_rd
             {
                 const int sp = cg * 16 + k;
                 if (sp > lastSp) continue;
-                const int pos = s.scan[sp];
+                const int pos = e.scan[sp];
                 const int level = dst[pos];
                 if (level)
                 {
-                    const int x = pos & ((1 << log2) - 1), y = pos >> log2;
+                    const int x = pos & mask, y = pos >> log2;
                     const long long lastCost = scanIdx == 2 ? lastPosCost(e, y, x) : lastPosCost(e, x, y);
-                    const long long total = rdCostTu + lastCost - s.rateCostSig[sp];
+                    const long long total = rdCostTu + lastCost - rec[sp].rateSig;
                     if (total < best)
                     {
                         lastIdx = sp + 1;
@@ -642,36 +633,38 @@ __device__ inline int hvbRdoqWarp(int16_t *dst, const int16_t *src, const hvb_rd
                         found = true;
                         break;
                     }
-                    rdCostTu -= s.rdCostCoeff[sp];
+                    rdCostTu -= rec[sp].rdCost;
                     rdCostTu += e.dist0(sp);
                 }
                 else
-                    rdCostTu -= s.rateCostSig[sp];
+                    rdCostTu -= rec[sp].rateSig;
             }
         }
     }
-    __syncwarp();
 
-    // signs back, uncoded tail to zero (Rdoq.cpp:414-431) -- data parallel
+    // signs back, uncoded tail to zero (Rdoq.cpp:414-431).  Only coded groups can hold non-zero levels.
     int cbf = 0, absSum = 0;
-    for (int sp = lane; sp <= lastSp; sp += 32)
+    for (int cg = 0; cg <= lastCg; ++cg)
     {
-        const int pos = s.scan[sp];
-        if (sp < lastIdx)
+        int cgX, cgY;
+        scanXY(log2Cg, scanIdx, cg, cgX, cgY);
+        if (!((csbf >> (cgY * (1 << log2Cg) + cgX)) & 1)) continue;
+        const short *sc = e.scan + (cg << 4);
+        for (int k = 0; k < 16; ++k)
         {
+            const int sp = cg * 16 + k, pos = sc[k];
             const int level = dst[pos];
-            absSum += level;
-            cbf |= level;
-            dst[pos] = (int16_t)(src[pos] < 0 ? -level : level);
+            if (!level) continue;
+            if (sp < lastIdx)
+            {
+                absSum += level;
+                cbf |= level;
+                if (src[pos] < 0) dst[pos] = (int16_t)-level;
+            }
+            else
+                dst[pos] = 0;
         }
-        else
-            dst[pos] = 0;
     }
-    absSum = hvbWarpSum(absSum);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cbf |= __shfl_xor_sync(0xffffffffu, cbf, o);
-    __syncwarp();
-    if (sdh && absSum >= 2 && lane == 0) signDataHiding(e, totalCg, dst);
-    __syncwarp();
+    if (sdh && absSum >= 2) signDataHiding(e, lastCg, dst);
     return cbf;
 }

@@ -220,11 +220,22 @@ __global__ void __launch_bounds__(kWarps * 32)
     }
 }
 
+// ---- the fused TU pipeline, in three stages -----------------------------------------------------
+//
+//   front  (warp per TU)    residual, SSD of the prediction, forward transform; then either the plain
+//                           quantiser (levels + cbf, done) or the cooperative RDOQ pre-pass (coefficients
+//                           parked in a scratch pool, zero levels written);
+//   rdoq   (thread per TU)  the level-coding recurrence (hvb_rdoq.cuh) -- a warp advances 32 TUs;
+//   back   (warp per TU)    dequantise, inverse transform, add, clip, SSD of the reconstruction.
+//
+// The split exists because RDOQ is serial per block: with a warp per block 31 lanes idled through it and the
+// ncu capture showed it at 10x the cost of everything else in the pipeline.
+
 template <typename Sample>
 __global__ void __launch_bounds__(kWarps * 32)
-    tuChainKernel(const HvbPlane *__restrict__ planes, int16_t *__restrict__ pool, const hvb_rdoq_ctx *__restrict__ rdoqCtx,
-                  const hvb_tu_task *__restrict__ tasks, int n, hvb_tu_result *__restrict__ out, int bitDepth, char *scratch,
-                  size_t scratchPerWarp)
+    tuFrontKernel(const HvbPlane *__restrict__ planes, int16_t *__restrict__ pool, int16_t *__restrict__ coefTmp,
+                  const hvb_rdoq_ctx *__restrict__ rdoqCtx, const hvb_tu_task *__restrict__ tasks, int n, hvb_tu_result *__restrict__ out,
+                  HvbRdoqMid *__restrict__ mids, int bitDepth)
 {
     __shared__ Matrices M;
     __shared__ __align__(16) int16_t sA[kWarps][kBlk];
@@ -233,16 +244,14 @@ __global__ void __launch_bounds__(kWarps * 32)
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int warpsTotal = gridDim.x * kWarps;
-    const int maxv = (1 << bitDepth) - 1;
     for (int t = blockIdx.x * kWarps + warp; t < n; t += warpsTotal)
     {
         const hvb_tu_task task = tasks[t];
         const int log2n = task.log2n, nn = 1 << log2n, count = nn * nn;
         const bool dst = task.trType != 0;
-        int ss, sp, sr;
+        int ss, sp;
         const Sample *src = hvbBlockPtr<Sample>(planes, task.src, ss);
         const Sample *pred = hvbBlockPtr<Sample>(planes, task.pred, sp);
-        Sample *rec = hvbBlockPtrW<Sample>(planes, task.rec, sr);
 
         // residual (Reconstruct.cpp:1275-1287) and SSD of the prediction (:856)
         unsigned ssdPred = 0;
@@ -258,14 +267,16 @@ __global__ void __launch_bounds__(kWarps * 32)
         __syncwarp();
         fwdPass(M, sA[warp], sB[warp], nn, log2n, dst, log2n + 6, lane); // sA = coefficients
         __syncwarp();
+        ssdPred = hvbWarpSumU(ssdPred);
+        if (sizeof(Sample) == 2) ssdPred >>= 4;
 
-        int cbf;
+        HvbRdoqMid mid;
+        int cbf = 0;
         if (task.flags & 1)
         {
-            cbf = hvbRdoqWarp(sB[warp], sA[warp], rdoqCtx + task.rdoq_ctx, task.qscale, task.qshift, task.iqscale, log2n, task.cIdx,
-                              task.scanIdx, (task.flags & 2) != 0, (task.flags & 4) != 0, bitDepth,
-                              reinterpret_cast<HvbRdoqScratch *>(scratch + (size_t)(blockIdx.x * kWarps + warp) * scratchPerWarp), lane);
-            cbf = cbf != 0;
+            for (int i = lane; i < count; i += 32) coefTmp[task.levels + i] = sA[warp][i];
+            mid = hvbRdoqPrepass(pool + task.levels, sA[warp], rdoqCtx + task.rdoq_ctx, task.qscale, task.qshift, task.iqscale, log2n,
+                                 task.cIdx, task.scanIdx, bitDepth, lane);
         }
         else
         {
@@ -275,46 +286,18 @@ __global__ void __launch_bounds__(kWarps * 32)
             {
                 const int q = quantOne(sA[warp][i], task.qscale, task.qshift, off);
                 any |= q;
-                sB[warp][i] = (int16_t)q; // sB = levels
+                pool[task.levels + i] = (int16_t)q;
             }
             cbf = __any_sync(0xffffffffu, any != 0);
-        }
-        __syncwarp();
-        for (int i = lane; i < count; i += 32)
-        {
-            const int q = sB[warp][i];
-            pool[task.levels + i] = (int16_t)q;
-            sA[warp][i] = (int16_t)dequantOne(q, task.iqscale, task.iqshift); // Reconstruct.cpp:822-826
-        }
-        __syncwarp();
-        if (cbf)
-        {
-            invPass(M, sB[warp], sA[warp], log2n, dst, 7, lane);
-            __syncwarp();
-            invPass(M, sA[warp], sB[warp], log2n, dst, 20 - bitDepth, lane);
-            __syncwarp();
-        }
-        // all-zero levels: the inverse of a zero block is zero and sA already holds the (zero) dequantised block
-        unsigned ssd = 0;
-        for (int i = lane; i < count; i += 32)
-        {
-            const int y = i >> log2n, x = i & (nn - 1);
-            const int r = hvbClip3(0, maxv, (int)pred[y * sp + x] + sA[warp][i]);
-            rec[y * sr + x] = (Sample)r;
-            const int d = (int)src[y * ss + x] - r;
-            ssd += (unsigned)(d * d);
-        }
-        ssd = hvbWarpSumU(ssd);
-        ssdPred = hvbWarpSumU(ssdPred);
-        if (sizeof(Sample) == 2)
-        {
-            ssd >>= 4;
-            ssdPred >>= 4;
+            mid.lastSp = -2; // not an RDOQ block: the serial stage skips it
+            mid.reserved = 0;
+            mid.totalDist0 = mid.tailDist0 = 0;
         }
         if (lane == 0)
         {
+            mids[t] = mid;
             hvb_tu_result r;
-            r.ssd = ssd;
+            r.ssd = 0;
             r.ssdPred = ssdPred;
             r.cbf = cbf;
             r.reserved = 0;
@@ -324,30 +307,145 @@ __global__ void __launch_bounds__(kWarps * 32)
     }
 }
 
-// Rdoq::runQuantisation alone, on pool coefficients (one warp per block)
-__global__ void __launch_bounds__(kWarps * 32)
-    rdoqKernel(int16_t *__restrict__ pool, const hvb_rdoq_ctx *__restrict__ rdoqCtx, const hvb_rdoq_task *__restrict__ tasks, int n,
-               int32_t *__restrict__ cbf, int bitDepth, char *scratch, size_t scratchPerWarp)
+__global__ void __launch_bounds__(128)
+    tuRdoqKernel(int16_t *__restrict__ pool, const int16_t *__restrict__ coefTmp, HvbCoefRec *__restrict__ recs,
+                 const hvb_rdoq_ctx *__restrict__ rdoqCtx, const hvb_tu_task *__restrict__ tasks, int n, hvb_tu_result *__restrict__ out,
+                 const HvbRdoqMid *__restrict__ mids, int bitDepth)
 {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+    {
+        const HvbRdoqMid mid = mids[t];
+        if (mid.lastSp < 0) continue; // plain-quantised, or every level rounds to zero (cbf already 0)
+        const hvb_tu_task task = tasks[t];
+        const int c = hvbRdoqThread(pool + task.levels, coefTmp + task.levels, rdoqCtx + task.rdoq_ctx, mid, task.qscale, task.qshift,
+                                    task.iqscale, task.log2n, task.cIdx, task.scanIdx, (task.flags & 2) != 0, (task.flags & 4) != 0, bitDepth,
+                                    recs + task.levels);
+        out[t].cbf = c != 0;
+    }
+}
+
+template <typename Sample>
+__global__ void __launch_bounds__(kWarps * 32)
+    tuBackKernel(const HvbPlane *__restrict__ planes, const int16_t *__restrict__ pool, const hvb_tu_task *__restrict__ tasks, int n,
+                 hvb_tu_result *__restrict__ out, int bitDepth)
+{
+    __shared__ Matrices M;
     __shared__ __align__(16) int16_t sA[kWarps][kBlk];
     __shared__ __align__(16) int16_t sB[kWarps][kBlk];
+    initMatrices(M);
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int warpsTotal = gridDim.x * kWarps;
+    const int maxv = (1 << bitDepth) - 1;
     for (int t = blockIdx.x * kWarps + warp; t < n; t += warpsTotal)
     {
-        const hvb_rdoq_task task = tasks[t];
-        const int count = 1 << (2 * task.log2n);
-        for (int i = lane; i < count; i += 32) sA[warp][i] = pool[task.src + i];
-        __syncwarp();
-        const int c = hvbRdoqWarp(sB[warp], sA[warp], rdoqCtx + task.rdoq_ctx, task.qscale, task.qshift, task.iqscale, task.log2n,
-                                  task.cIdx, task.scanIdx, (task.flags & 2) != 0, (task.flags & 4) != 0, bitDepth,
-                                  reinterpret_cast<HvbRdoqScratch *>(scratch + (size_t)(blockIdx.x * kWarps + warp) * scratchPerWarp),
-                                  lane);
-        __syncwarp();
-        for (int i = lane; i < count; i += 32) pool[task.dst + i] = sB[warp][i];
-        if (lane == 0) cbf[t] = c != 0;
+        const hvb_tu_task task = tasks[t];
+        const int log2n = task.log2n, nn = 1 << log2n, count = nn * nn;
+        const bool dst = task.trType != 0;
+        const int cbf = out[t].cbf;
+        int ss, sp, sr;
+        const Sample *src = hvbBlockPtr<Sample>(planes, task.src, ss);
+        const Sample *pred = hvbBlockPtr<Sample>(planes, task.pred, sp);
+        Sample *rec = hvbBlockPtrW<Sample>(planes, task.rec, sr);
+        if (cbf)
+        {
+            for (int i = lane; i < count; i += 32)
+                sA[warp][i] = (int16_t)dequantOne(pool[task.levels + i], task.iqscale, task.iqshift); // Reconstruct.cpp:822-826
+            __syncwarp();
+            invPass(M, sB[warp], sA[warp], log2n, dst, 7, lane);
+            __syncwarp();
+            invPass(M, sA[warp], sB[warp], log2n, dst, 20 - bitDepth, lane);
+            __syncwarp();
+        }
+        // all-zero levels: the inverse transform of a zero block is zero, the reconstruction is the prediction
+        unsigned ssd = 0;
+        for (int i = lane; i < count; i += 32)
+        {
+            const int y = i >> log2n, x = i & (nn - 1);
+            const int r = cbf ? hvbClip3(0, maxv, (int)pred[y * sp + x] + sA[warp][i]) : (int)pred[y * sp + x];
+            rec[y * sr + x] = (Sample)r;
+            const int d = (int)src[y * ss + x] - r;
+            ssd += (unsigned)(d * d);
+        }
+        ssd = hvbWarpSumU(ssd);
+        if (sizeof(Sample) == 2) ssd >>= 4;
+        if (lane == 0) out[t].ssd = ssd;
         __syncwarp();
     }
+}
+
+// Rdoq::runQuantisation alone, on pool coefficients: cooperative pre-pass, then one thread per block
+__global__ void __launch_bounds__(kWarps * 32)
+    rdoqPrepassKernel(int16_t *__restrict__ pool, const hvb_rdoq_ctx *__restrict__ rdoqCtx, const hvb_rdoq_task *__restrict__ tasks, int n,
+                      HvbRdoqMid *__restrict__ mids, int32_t *__restrict__ cbf, int bitDepth)
+{
+    const int lane = threadIdx.x & 31;
+    const int warpsTotal = gridDim.x * kWarps;
+    for (int t = blockIdx.x * kWarps + (threadIdx.x >> 5); t < n; t += warpsTotal)
+    {
+        const hvb_rdoq_task task = tasks[t];
+        const HvbRdoqMid mid = hvbRdoqPrepass(pool + task.dst, pool + task.src, rdoqCtx + task.rdoq_ctx, task.qscale, task.qshift,
+                                              task.iqscale, task.log2n, task.cIdx, task.scanIdx, bitDepth, lane);
+        if (lane == 0)
+        {
+            mids[t] = mid;
+            cbf[t] = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+    rdoqThreadKernel(int16_t *__restrict__ pool, HvbCoefRec *__restrict__ recs, const hvb_rdoq_ctx *__restrict__ rdoqCtx,
+                     const hvb_rdoq_task *__restrict__ tasks, int n, const HvbRdoqMid *__restrict__ mids, int32_t *__restrict__ cbf,
+                     int bitDepth)
+{
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+    {
+        const HvbRdoqMid mid = mids[t];
+        if (mid.lastSp < 0) continue;
+        const hvb_rdoq_task task = tasks[t];
+        const int c = hvbRdoqThread(pool + task.dst, pool + task.src, rdoqCtx + task.rdoq_ctx, mid, task.qscale, task.qshift, task.iqscale,
+                                    task.log2n, task.cIdx, task.scanIdx, (task.flags & 2) != 0, (task.flags & 4) != 0, bitDepth,
+                                    recs + task.dst);
+        cbf[t] = c != 0;
+    }
+}
+
+// scan tables of hvb_rdoq.cuh, once per device
+int initRdoqTables(hvb_context *ctx)
+{
+    static bool done[64] = {};
+    if (ctx->device < 64 && done[ctx->device]) return HVB_OK;
+    std::vector<short> host(4 * 3 * 1024, 0);
+    for (int log2 = 2; log2 <= 5; ++log2)
+        for (int scanIdx = 0; scanIdx < 3; ++scanIdx)
+            for (int sp = 0; sp < (1 << (2 * log2)); ++sp)
+                host[((log2 - 2) * 3 + scanIdx) * 1024 + sp] = (short)hvb_rdoq::scanToRaster(log2, scanIdx, sp);
+    cudaError_t e = cudaMemcpyToSymbol(hvb_rdoq::gScanTable, host.data(), host.size() * sizeof(short));
+    if (e != cudaSuccess) return hvbCuda(ctx, e, "rdoq scan tables");
+    if (ctx->device < 64) done[ctx->device] = true;
+    return HVB_OK;
+}
+
+// scratch layout of the pipeline: [coefTmp: count int16][recs: count HvbCoefRec][mids: n HvbRdoqMid]
+struct ChainScratch
+{
+    int16_t *coefTmp;
+    HvbCoefRec *recs;
+    HvbRdoqMid *mids;
+};
+
+int chainScratch(hvb_context *ctx, size_t count, size_t n, bool needCoefTmp, ChainScratch *cs)
+{
+    const size_t coefBytes = needCoefTmp ? ((count * sizeof(int16_t) + 255) & ~size_t(255)) : 0;
+    const size_t recBytes = (count * sizeof(HvbCoefRec) + 255) & ~size_t(255);
+    int rc = hvbEnsureScratch(ctx, coefBytes + recBytes + n * sizeof(HvbRdoqMid));
+    if (rc) return rc;
+    char *base = static_cast<char *>(ctx->scratch);
+    cs->coefTmp = reinterpret_cast<int16_t *>(base);
+    cs->recs = reinterpret_cast<HvbCoefRec *>(base + coefBytes);
+    cs->mids = reinterpret_cast<HvbRdoqMid *>(base + coefBytes + recBytes);
+    return HVB_OK;
 }
 
 int gridWarps(hvb_context *ctx, int n, int warps, int perSm)
@@ -433,22 +531,33 @@ extern "C" int hvb_tu_chain_batch(hvb_context *ctx, const hvb_tu_task *tasks, in
     HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && out)) && ctx->coeffPool);
     if (!n) return HVB_OK;
     cudaSetDevice(ctx->device);
-    const int grid = gridWarps(ctx, n, kWarps, 4);
-    const size_t perWarp = hvbRdoqScratchBytes();
-    int rc = hvbEnsureScratch(ctx, perWarp * kWarps * (size_t)(ctx->smCount * 4));
+    int rc = initRdoqTables(ctx);
+    if (rc) return rc;
+    ChainScratch cs;
+    rc = chainScratch(ctx, ctx->coeffPoolCount, (size_t)n, true, &cs);
     if (rc) return rc;
     HvbStaged st;
     rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(hvb_tu_result) * n, mem, &st);
     if (rc) return rc;
     const auto *dT = static_cast<const hvb_tu_task *>(st.dTasks);
     auto *dO = static_cast<hvb_tu_result *>(st.dOut);
+    const int gridW = gridWarps(ctx, n, kWarps, 4);
+    int gridT = (n + 127) / 128;
+    if (gridT > ctx->smCount * 16) gridT = ctx->smCount * 16;
     if (ctx->bps == 1)
-        tuChainKernel<uint8_t><<<grid, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, ctx->rdoqCtx, dT, n, dO, ctx->bitDepth,
-                                                                      static_cast<char *>(ctx->scratch), perWarp);
+        tuFrontKernel<uint8_t><<<gridW, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, cs.coefTmp, ctx->rdoqCtx, dT, n, dO, cs.mids,
+                                                                       ctx->bitDepth);
     else
-        tuChainKernel<uint16_t><<<grid, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, ctx->rdoqCtx, dT, n, dO, ctx->bitDepth,
-                                                                       static_cast<char *>(ctx->scratch), perWarp);
-    HVB_LAUNCH_CHECK(ctx, "tuChainKernel");
+        tuFrontKernel<uint16_t><<<gridW, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, cs.coefTmp, ctx->rdoqCtx, dT, n, dO, cs.mids,
+                                                                        ctx->bitDepth);
+    HVB_LAUNCH_CHECK(ctx, "tuFrontKernel");
+    tuRdoqKernel<<<gridT, 128, 0, ctx->stream>>>(ctx->coeffPool, cs.coefTmp, cs.recs, ctx->rdoqCtx, dT, n, dO, cs.mids, ctx->bitDepth);
+    HVB_LAUNCH_CHECK(ctx, "tuRdoqKernel");
+    if (ctx->bps == 1)
+        tuBackKernel<uint8_t><<<gridW, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, dT, n, dO, ctx->bitDepth);
+    else
+        tuBackKernel<uint16_t><<<gridW, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, dT, n, dO, ctx->bitDepth);
+    HVB_LAUNCH_CHECK(ctx, "tuBackKernel");
     return hvbStageOut(ctx, out, sizeof(hvb_tu_result) * n, mem, st);
 }
 
@@ -457,16 +566,21 @@ extern "C" int hvb_rdoq_batch(hvb_context *ctx, const hvb_rdoq_task *tasks, int 
     HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && cbf)) && ctx->coeffPool && ctx->rdoqCtx);
     if (!n) return HVB_OK;
     cudaSetDevice(ctx->device);
-    const int grid = gridWarps(ctx, n, kWarps, 4);
-    const size_t perWarp = hvbRdoqScratchBytes();
-    int rc = hvbEnsureScratch(ctx, perWarp * kWarps * (size_t)(ctx->smCount * 4));
+    int rc = initRdoqTables(ctx);
+    if (rc) return rc;
+    ChainScratch cs;
+    rc = chainScratch(ctx, ctx->coeffPoolCount, (size_t)n, false, &cs);
     if (rc) return rc;
     HvbStaged st;
     rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, cbf, sizeof(int32_t) * n, mem, &st);
     if (rc) return rc;
-    rdoqKernel<<<grid, kWarps * 32, 0, ctx->stream>>>(ctx->coeffPool, ctx->rdoqCtx, static_cast<const hvb_rdoq_task *>(st.dTasks), n,
-                                                      static_cast<int32_t *>(st.dOut), ctx->bitDepth, static_cast<char *>(ctx->scratch),
-                                                      perWarp);
-    HVB_LAUNCH_CHECK(ctx, "rdoqKernel");
+    const auto *dT = static_cast<const hvb_rdoq_task *>(st.dTasks);
+    auto *dC = static_cast<int32_t *>(st.dOut);
+    int gridT = (n + 127) / 128;
+    if (gridT > ctx->smCount * 16) gridT = ctx->smCount * 16;
+    rdoqPrepassKernel<<<gridWarps(ctx, n, kWarps, 8), kWarps * 32, 0, ctx->stream>>>(ctx->coeffPool, ctx->rdoqCtx, dT, n, cs.mids, dC, ctx->bitDepth);
+    HVB_LAUNCH_CHECK(ctx, "rdoqPrepassKernel");
+    rdoqThreadKernel<<<gridT, 128, 0, ctx->stream>>>(ctx->coeffPool, cs.recs, ctx->rdoqCtx, dT, n, cs.mids, dC, ctx->bitDepth);
+    HVB_LAUNCH_CHECK(ctx, "rdoqThreadKernel");
     return hvbStageOut(ctx, cbf, sizeof(int32_t) * n, mem, st);
 }
