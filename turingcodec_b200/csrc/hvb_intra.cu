@@ -44,7 +44,11 @@ __device__ __forceinline__ int angularRef(const Neighbours &nb, int i, bool vert
     return vertical ? nb.A[nb.c + s] : nb.A[nb.c - s];
 }
 
-__device__ __forceinline__ int intraSample(const Neighbours &nb, int mode, int x, int y, int log2n, int dcVal, bool edge, int maxv)
+// `angle` / `inv` are kAngle[mode] / kInvAngle[mode], fetched once per job by the caller: with a different mode on
+// every lane the constant-bank read serialises, and the ncu capture had it at a third of all stall samples when it
+// sat inside the per-sample code.
+__device__ __forceinline__ int intraSample(const Neighbours &nb, int mode, int angle, int inv, int x, int y, int log2n, int dcVal, bool edge,
+                                           int maxv)
 {
     const int n = 1 << log2n;
     if (mode == 0)
@@ -62,7 +66,6 @@ __device__ __forceinline__ int intraSample(const Neighbours &nb, int mode, int x
     const bool vertical = mode >= 18;
     if (edge && mode == 26 && x == 0) return hvbClip3(0, maxv, nb.top(0) + ((nb.left(y) - nb.corner()) >> 1));
     if (edge && mode == 10 && y == 0) return hvbClip3(0, maxv, nb.left(0) + ((nb.top(x) - nb.corner()) >> 1));
-    const int angle = kAngle[mode], inv = kInvAngle[mode];
     const int major = vertical ? y : x, minor = vertical ? x : y;
     const int t = (major + 1) * angle;
     const int idx = t >> 5, fact = t & 31;
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(kWarps * 32)
         for (int j = lane; j < nn * nn; j += 32)
         {
             const int y = j >> log2n, x = j & (nn - 1);
-            dst[y * sd + x] = (Sample)intraSample(nb, t.mode, x, y, log2n, dc, t.edge_flag != 0, maxv);
+            dst[y * sd + x] = (Sample)intraSample(nb, t.mode, kAngle[t.mode], kInvAngle[t.mode], x, y, log2n, dc, t.edge_flag != 0, maxv);
         }
         __syncwarp();
     }
@@ -160,10 +163,11 @@ __device__ __forceinline__ int sweepTile(const Neighbours &nb, int mode, int log
 {
     constexpr int T = 1 << LOG2T;
     int16_t pred[T * T];
+    const int angle = kAngle[mode], inv = kInvAngle[mode];
 #pragma unroll
     for (int y = 0; y < T; ++y)
 #pragma unroll
-        for (int x = 0; x < T; ++x) pred[y * T + x] = (int16_t)intraSample(nb, mode, x0 + x, y0 + y, log2n, dc, edge, maxv);
+        for (int x = 0; x < T; ++x) pred[y * T + x] = (int16_t)intraSample(nb, mode, angle, inv, x0 + x, y0 + y, log2n, dc, edge, maxv);
     return hvbSatdTile<Sample, int16_t, LOG2T>(src + y0 * ss + x0, ss, pred, T, sizeof(Sample) == 2 ? 2 : 0);
 }
 
