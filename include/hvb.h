@@ -76,6 +76,12 @@ int hvb_picture_upload(hvb_context *ctx, int pic, int cIdx, const void *host, in
                        int y0, int rows);
 int hvb_picture_download(hvb_context *ctx, int pic, int cIdx, void *host, intptr_t stride,
                          int y0, int rows);
+/* rectangle variants (x0,y0,w,h in samples of that plane; the rectangle may lie in the padding):
+ * what the per-block table shim and the encoder's per-CTU reconstruction commit (turing/Write.h:828-830) use */
+int hvb_picture_upload_rect(hvb_context *ctx, int pic, int cIdx, const void *host, intptr_t stride,
+                            int x0, int y0, int w, int h);
+int hvb_picture_download_rect(hvb_context *ctx, int pic, int cIdx, void *host, intptr_t stride,
+                              int x0, int y0, int w, int h);
 /* replicate edge samples into the padding of all three planes (turing/Padding.h) */
 int hvb_picture_pad(hvb_context *ctx, int pic);
 /* raw device view of a plane: pointer to sample (0,0) and stride in samples (for zero-copy fills) */

@@ -69,7 +69,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as pool:
             list(pool.map(lambda so: _compile(nvcc, so[0], so[1], verbose), jobs))
     if jobs or not LIB.exists():
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs)]
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-soname=libhvb.so", "-o", str(LIB),
+               *map(str, objs)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")

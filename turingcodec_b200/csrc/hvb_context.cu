@@ -237,6 +237,36 @@ extern "C" int hvb_picture_download(hvb_context *ctx, int pic, int cIdx, void *h
     return planeCopy(ctx, pic, cIdx, host, stride, y0, rows, false);
 }
 
+static int rectCopy(hvb_context *ctx, int pic, int cIdx, void *host, intptr_t stride, int x0, int y0, int w, int h, bool upload)
+{
+    HVB_CHECK_ARGS(ctx, pic >= 0 && pic < HVB_MAX_PICTURES && ctx->pictures[pic].live && cIdx >= 0 && cIdx < 3 && host);
+    const HvbPlane &pl = ctx->pictures[pic].plane[cIdx];
+    HVB_CHECK_ARGS(ctx, w >= 0 && h >= 0 && stride >= w && x0 >= -pl.pad && y0 >= -pl.pad && x0 + w <= pl.width + pl.pad &&
+                            y0 + h <= pl.height + pl.pad);
+    if (!w || !h) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    char *dev = static_cast<char *>(pl.base) + ((intptr_t)y0 * pl.stride + x0) * ctx->bps;
+    cudaError_t e;
+    if (upload)
+        e = cudaMemcpy2DAsync(dev, (size_t)pl.stride * ctx->bps, host, (size_t)stride * ctx->bps, (size_t)w * ctx->bps, h,
+                              cudaMemcpyHostToDevice, ctx->stream);
+    else
+        e = cudaMemcpy2DAsync(host, (size_t)stride * ctx->bps, dev, (size_t)pl.stride * ctx->bps, (size_t)w * ctx->bps, h,
+                              cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    return hvbCuda(ctx, e, upload ? "hvb_picture_upload_rect" : "hvb_picture_download_rect");
+}
+
+extern "C" int hvb_picture_upload_rect(hvb_context *ctx, int pic, int cIdx, const void *host, intptr_t stride, int x0, int y0, int w, int h)
+{
+    return rectCopy(ctx, pic, cIdx, const_cast<void *>(host), stride, x0, y0, w, h, true);
+}
+
+extern "C" int hvb_picture_download_rect(hvb_context *ctx, int pic, int cIdx, void *host, intptr_t stride, int x0, int y0, int w, int h)
+{
+    return rectCopy(ctx, pic, cIdx, host, stride, x0, y0, w, h, false);
+}
+
 extern "C" int hvb_picture_plane(hvb_context *ctx, int pic, int cIdx, void **dev_ptr, intptr_t *stride)
 {
     HVB_CHECK_ARGS(ctx, pic >= 0 && pic < HVB_MAX_PICTURES && ctx->pictures[pic].live && cIdx >= 0 && cIdx < 3);

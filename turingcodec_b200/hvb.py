@@ -102,6 +102,8 @@ def load_library() -> C.CDLL:
     lib.hvb_picture_upload.argtypes = [vp, i32, i32, vp, C.c_ssize_t, i32, i32]
     lib.hvb_picture_download.argtypes = [vp, i32, i32, vp, C.c_ssize_t, i32, i32]
     lib.hvb_picture_pad.argtypes = [vp, i32]
+    lib.hvb_picture_upload_rect.argtypes = [vp, i32, i32, vp, C.c_ssize_t, i32, i32, i32, i32]
+    lib.hvb_picture_download_rect.argtypes = [vp, i32, i32, vp, C.c_ssize_t, i32, i32, i32, i32]
     lib.hvb_picture_plane.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_ssize_t)]
     lib.hvb_pool_upload.argtypes = [vp, vp, C.c_size_t, C.c_size_t]
     lib.hvb_coeff_upload.argtypes = [vp, vp, C.c_size_t, C.c_size_t]
