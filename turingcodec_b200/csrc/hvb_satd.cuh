@@ -12,10 +12,30 @@ __device__ __forceinline__ int hvbSatdTile(const SampleA *a, int sa, const Sampl
 {
     constexpr int N = 1 << LOG2N;
     int m[N][N];
+    if (N == 8 && sizeof(SampleA) == 1 && sizeof(SampleB) == 1 &&
+        !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | (uintptr_t)sa | (uintptr_t)sb) & 7))
+    {
+        // both 8-bit rows 8-byte aligned: one 64-bit load per row per operand instead of eight byte loads
 #pragma unroll
-    for (int y = 0; y < N; ++y)
+        for (int y = 0; y < N; ++y)
+        {
+            const uint2 va = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(a) + y * sa));
+            const uint2 vb = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(b) + y * sb));
 #pragma unroll
-        for (int x = 0; x < N; ++x) m[y][x] = (int)a[y * sa + x] - (int)b[y * sb + x];
+            for (int x = 0; x < 4; ++x)
+            {
+                m[y][x] = (int)((va.x >> (8 * x)) & 0xff) - (int)((vb.x >> (8 * x)) & 0xff);
+                m[y][x + 4] = (int)((va.y >> (8 * x)) & 0xff) - (int)((vb.y >> (8 * x)) & 0xff);
+            }
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int y = 0; y < N; ++y)
+#pragma unroll
+            for (int x = 0; x < N; ++x) m[y][x] = (int)a[y * sa + x] - (int)b[y * sb + x];
+    }
 
         // rows
 #pragma unroll
@@ -89,4 +109,5 @@ __device__ __forceinline__ int hvbMeasureSatdLanes(const SampleA *a, int sa, con
     }
     return acc;
 }
+
 
