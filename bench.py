@@ -165,10 +165,20 @@ class GpuArm:
         self.o_me = torch.zeros(fp.me.size * hvb.me_result_t.itemsize, dtype=torch.uint8, device=dev)
         self.o_intra = torch.zeros(fp.intra.size * 35, dtype=torch.int32, device=dev)
         self.o_tu = torch.zeros(fp.tu.size * hvb.tu_result_t.itemsize, dtype=torch.uint8, device=dev)
-        # host result buffers for the e2e path
-        self.h_me = np.zeros(fp.me.size, hvb.me_result_t)
-        self.h_intra = np.zeros((fp.intra.size, 35), np.int32)
-        self.h_tu = np.zeros(fp.tu.size, hvb.tu_result_t)
+        # e2e path: task arrays, neighbours and result buffers live in page-locked host memory (the encoder's arena),
+        # so the C-ABI copies from / to them directly
+        self._keep = []
+
+        def pin(arr):
+            view, keep = pinned_empty(arr.shape, arr.dtype)
+            view[...] = arr
+            self._keep.append(keep)
+            return view
+
+        self.p_me, self.p_intra, self.p_tu, self.p_nb = pin(fp.me), pin(fp.intra), pin(fp.tu), pin(fp.neighbours)
+        self.h_me = pin(np.zeros(fp.me.size, hvb.me_result_t))
+        self.h_intra = pin(np.zeros((fp.intra.size, 35), np.int32))
+        self.h_tu = pin(np.zeros(fp.tu.size, hvb.tu_result_t))
         self.kernel_ms = {"me": 0.0, "intra": 0.0, "tu": 0.0}
         torch.cuda.synchronize(device)
 
@@ -194,10 +204,10 @@ class GpuArm:
             for c, (arr, _) in enumerate(planes):
                 self.ctx.picture_upload(pic, c, arr)
             self.ctx.picture_pad(pic)
-        self.ctx.pool_upload(fp.neighbours)
-        self.ctx.me_search(fp.me, out=self.h_me)
-        self.ctx.intra_satd35(fp.intra, out=self.h_intra)
-        self.ctx.tu_chain(fp.tu, out=self.h_tu)
+        self.ctx.pool_upload(self.p_nb)
+        self.ctx.me_search(self.p_me, out=self.h_me)
+        self.ctx.intra_satd35(self.p_intra, out=self.h_intra)
+        self.ctx.tu_chain(self.p_tu, out=self.h_tu)
 
     def e2e_bytes(self):
         fp = self.fp
@@ -305,10 +315,40 @@ def peaks():
 
 
 def traffic_from_profile(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/traffic.json)"""
     path = ROOT / "profiles" / "traffic.json"
-    if path.exists():
-        return json.loads(path.read_text()).get(kernel)
-    return None
+    if not path.exists():
+        return None
+    table = json.loads(path.read_text())
+    parts = [table.get(k) for k in kernel.split("+")]
+    return None if any(p is None for p in parts) else float(sum(parts))
+
+
+def reference_encoder_fps(width, height, frames=6):
+    """The reference's real encoder (oracle/_ref/turing_ref, built unmodified by oracle/Makefile `encoder`) on the same
+    synthetic content at `--speed medium`, all host threads: context for the hot-path numbers, not their baseline."""
+    exe = ROOT / "oracle" / "_ref" / "turing_ref"
+    if not exe.exists():
+        return None
+    import tempfile
+    from turingcodec_b200 import synth
+    with tempfile.TemporaryDirectory() as tmp:
+        clip = Path(tmp) / "clip.yuv"
+        base = synth.frame(0, width, height, 8)
+        with open(clip, "wb") as f:
+            for i in range(frames):
+                for c, plane in enumerate(base):
+                    sh = (2 * i, 3 * i) if c == 0 else (i, (3 * i) // 2)
+                    f.write(np.roll(plane, sh, (0, 1)).tobytes())
+        cmd = [str(exe), "encode", "--input-res", f"{width}x{height}", "--frame-rate", "30", "--frames", str(frames), "--speed", "medium",
+               "-o", str(Path(tmp) / "out.bit"), str(clip)]
+        t0 = time.time()
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        wall = time.time() - t0
+        if res.returncode != 0:
+            return {"error": (res.stdout + res.stderr)[-300:]}
+        return {"fps": frames / wall, "frames": frames, "wall_s": wall, "threads": os.cpu_count(),
+                "cmd": "turing_ref encode --speed medium (AVX2/xbyak JIT, threads auto, concurrent-frames 4)"}
 
 
 def run_reference(args, rank):
@@ -331,6 +371,7 @@ def run_reference(args, rank):
             "config": {"workload": f"{args.width}x{args.height} YUV420 8-bit, medium preset, one hot-path frame pass per step",
                        "units_per_step": arm.fp.units, "l2": "n/a (CPU arm)"},
             "cpu_baseline": {**res, "value": fps},
+            "reference_encoder": reference_encoder_fps(args.width, args.height),
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
     print(json.dumps(line))
@@ -395,7 +436,7 @@ def main():
     dominant = max(kern, key=kern.get)
     peak, peak_src = peaks()
     achieved = alg[dominant] / (kern[dominant] * 1e-3) / 1e9
-    kernel_names = {"me": "meSearchKernel", "intra": "intraSweepKernel", "tu": "tuChainKernel"}
+    kernel_names = {"me": "meSearchKernel", "intra": "intraSweepKernel", "tu": "tuFrontKernel+tuRdoqKernel+tuBackKernel"}
     roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic_from_profile(kernel_names[dominant]), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dominant], "ms_per_launch": kern[dominant],

@@ -339,8 +339,15 @@ static void tu_body(void *a, int i)
         const b_plane *sp = &planes[t->src.pic * 3 + t->src.cIdx], *pp = &planes[t->pred.pic * 3 + t->pred.cIdx];
         const b_plane *rp = &recPlanes[t->rec.pic * 3 + t->rec.cIdx];
         const char *src = (const char *)sp->base + ((intptr_t)t->src.y * sp->stride + t->src.x) * bps;
-        const char *pred = (const char *)pp->base + ((intptr_t)t->pred.y * pp->stride + t->pred.x) * bps;
+        const char *predPic = (const char *)pp->base + ((intptr_t)t->pred.y * pp->stride + t->pred.x) * bps;
         char *rec = (char *)rp->base + ((intptr_t)t->rec.y * rp->stride + t->rec.x) * bps;
+        /* the encoder keeps predictions in 32-byte aligned cache pieces (turing/ReconstructionCache.h) and the
+         * reference's SIMD bodies rely on it: stage the (motion-compensated, hence unaligned) block the same way */
+        uint16_t predBuf[32 * 32] __attribute__((aligned(32)));
+        for (int y = 0; y < nn; ++y) memcpy((char *)predBuf + (size_t)y * nn * bps, predPic + (size_t)y * pp->stride * bps, (size_t)nn * bps);
+        const char *pred = (const char *)predBuf;
+        const b_plane predPlane = {predBuf, nn};
+        pp = &predPlane;
         int16_t res[1024] __attribute__((aligned(32))), coeffs[1024] __attribute__((aligned(32)));
         int16_t deq[1024] __attribute__((aligned(32)));
         int16_t *levels = levelPool + t->levels;

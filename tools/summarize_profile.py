@@ -35,7 +35,7 @@ with open(out + "_kernels.csv", "w", newline="") as f:
     w.writerow([units[idx[k]] for k in keep])
     for r in rows[2:]:
         w.writerow([r[idx[k]] for k in keep])
-        name = re.sub(r"<.*", "", r[idx["Kernel Name"]].split("::")[-1]).strip()
+        name = re.sub(r"[<(].*", "", r[idx["Kernel Name"]].split("::")[-1]).strip()
         total = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + \
             to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
         traffic.setdefault(name, []).append(total)

@@ -391,6 +391,17 @@ extern "C" int hvb_rdoq_contexts_upload(hvb_context *ctx, const hvb_rdoq_ctx *sn
     return hvbCuda(ctx, e, "hvb_rdoq_contexts_upload");
 }
 
+static bool isPinned(const void *p)
+{
+    cudaPointerAttributes attr;
+    if (!p || cudaPointerGetAttributes(&attr, p) != cudaSuccess)
+    {
+        cudaGetLastError(); // unregistered host memory reports an error on older runtimes: clear it
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
 int hvbStageIn(hvb_context *ctx, const void *tasks, size_t inBytes, void *out, size_t outBytes, hvb_mem mem, HvbStaged *st)
 {
     int rc = hvbSyncPlanes(ctx);
@@ -418,8 +429,15 @@ int hvbStageIn(hvb_context *ctx, const void *tasks, size_t inBytes, void *out, s
         if (e != cudaSuccess) return hvbCuda(ctx, e, "staging buffers");
         ctx->hostStageBytes = ctx->devStageBytes = cap;
     }
-    memcpy(ctx->hostStage, tasks, inBytes);
-    cudaError_t e = cudaMemcpyAsync(ctx->devStage, ctx->hostStage, inBytes, cudaMemcpyHostToDevice, ctx->stream);
+    // Page-locked caller memory (cudaHostAlloc / cudaHostRegister, e.g. an encoder's task arena) is copied from
+    // directly; pageable memory goes through the context's pinned staging buffer first.
+    const void *hostSrc = tasks;
+    if (!isPinned(tasks))
+    {
+        memcpy(ctx->hostStage, tasks, inBytes);
+        hostSrc = ctx->hostStage;
+    }
+    cudaError_t e = cudaMemcpyAsync(ctx->devStage, hostSrc, inBytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) return hvbCuda(ctx, e, "stage in");
     st->dTasks = ctx->devStage;
     st->dOut = static_cast<char *>(ctx->devStage) + inPad;
@@ -431,9 +449,10 @@ int hvbStageOut(hvb_context *ctx, void *out, size_t outBytes, hvb_mem mem, const
 {
     if (mem == HVB_DEVICE) return HVB_OK;
     cudaError_t e = cudaSuccess;
-    if (outBytes) e = cudaMemcpyAsync(st.hOutPinned, st.dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream);
+    const bool direct = outBytes && isPinned(out);
+    if (outBytes) e = cudaMemcpyAsync(direct ? out : st.hOutPinned, st.dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return hvbCuda(ctx, e, "stage out");
-    if (outBytes) memcpy(out, st.hOutPinned, outBytes);
+    if (outBytes && !direct) memcpy(out, st.hOutPinned, outBytes);
     return HVB_OK;
 }
