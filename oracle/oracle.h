@@ -190,4 +190,9 @@ int orc_scan_order(int log2, int scanIdx, int pos, int comp);
 }
 #endif
 
+/* turing/Dsp.h:57-70 (filterFlag) as a rule, and turing/IntraReferenceSamples.h:373-419 (filter) on a
+ * 4n+1 neighbour array whose corner sits at index 2n (left(y) at 2n-1-y, top(x) at 2n+1+x), samples widened to u16. */
+int orc_intra_filter_flag(int cIdx, int mode, int n);
+void orc_intra_filter_neighbours(uint16_t *f, const uint16_t *u, int n, int bitDepth, int strongEnabled);
+
 #endif /* ORACLE_H */

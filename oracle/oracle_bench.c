@@ -227,7 +227,7 @@ double orc_bench_me(const b_plane *planes /* [pic*3 + cIdx] */, const b_me_task 
 
 /* ---- loop D ------------------------------------------------------------------------------- */
 
-static int filter_flag(int cIdx, int mode, int n)
+int orc_intra_filter_flag(int cIdx, int mode, int n)
 {
     if (cIdx != 0 || mode == 1 || n == 4) return 0;
     if (mode == 0) return 1;
@@ -236,7 +236,7 @@ static int filter_flag(int cIdx, int mode, int n)
 }
 
 /* turing/IntraReferenceSamples.h:373-419 on an array whose corner sits at index 2n */
-static void filter_neighbours(uint16_t *f, const uint16_t *u, int n, int bitDepth, int strongEnabled)
+void orc_intra_filter_neighbours(uint16_t *f, const uint16_t *u, int n, int bitDepth, int strongEnabled)
 {
     const int c = 2 * n;
     int strong = 0;
@@ -279,7 +279,7 @@ static void intra_body(void *a, int i)
         uint8_t u8[129 + 1], f8[129 + 1];
         for (int k = 0; k <= 4 * nn; ++k)
             u16[k] = bps == 1 ? ((const uint8_t *)pool)[t->nb_unfiltered - c + k] : ((const uint16_t *)pool)[t->nb_unfiltered - c + k];
-        filter_neighbours(f16, u16, nn, bitDepth, t->strong);
+        orc_intra_filter_neighbours(f16, u16, nn, bitDepth, t->strong);
         for (int k = 0; k <= 4 * nn; ++k) { u8[k] = (uint8_t)u16[k]; f8[k] = (uint8_t)f16[k]; }
         const b_plane *sp = &planes[t->src.pic * 3 + t->src.cIdx];
         const char *src = (const char *)sp->base + ((intptr_t)t->src.y * sp->stride + t->src.x) * bps;
@@ -288,7 +288,7 @@ static void intra_body(void *a, int i)
         const int edge = t->cIdx == 0 && t->log2n < 5;
         for (int mode = 0; mode < 35; ++mode)
         {
-            const int ff = filter_flag(t->cIdx, mode, nn);
+            const int ff = orc_intra_filter_flag(t->cIdx, mode, nn);
             const void *nb = bps == 1 ? (const void *)((ff ? f8 : u8) + c + 1) : (const void *)((ff ? f16 : u16) + c + 1);
             if (prim.handle) prim.pred_intra(prim.handle, pred, nn, nb, mode, t->log2n, bitDepth, t->cIdx, bps);
             else orc_pred_intra(pred, nn, nb, mode, t->log2n, bitDepth, edge, bps);

@@ -11,9 +11,9 @@
  *
  * Everything the reference reads from encoder state is an explicit field of orc_me_task.
  *
- * PARITY STATUS OF THIS FILE: the primitives it calls (SAD, interpolation, SATD) are pinned; the
- * control flow restated here could not be executed against the reference in isolation (it is a
- * template over the encoder's handler type) -- see DESIGN.md "oracle pinning".
+ * PARITY STATUS OF THIS FILE: pinned.  tests/test_oracle_search_pin.py runs the reference's own templates
+ * (oracle/ref_shim_search.cpp instantiates them unmodified with a state-only stand-in handler) on the same
+ * pictures and per-PU state and requires every output to be equal.
  */
 #include "oracle.h"
 #include <stdlib.h>

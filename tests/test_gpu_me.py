@@ -102,3 +102,52 @@ def test_me_search_matches_oracle(scene, oracle):
         early += r.earlyExit
         refined += tuple(r.mv) != tuple(r.mvInteger)
     assert early > 5 and refined > 10, (early, refined)  # both the MET exits and the sub-pel moves are exercised
+
+
+@pytest.mark.parametrize("jit", [False, True], ids=["ref-c", "ref-jit"])
+def test_me_search_matches_reference_templates(scene, jit):
+    """The device search against the UNMODIFIED reference templates themselves (oracle/_ref/libsearch_ref.so,
+    see test_oracle_search_pin.py), without the oracle in between."""
+    import test_oracle_search_pin as pin
+    if not pin.LIB.exists():
+        pytest.skip("oracle/_ref/libsearch_ref.so not built")
+    lib = C.CDLL(str(pin.LIB))
+    lib.ref_search_batch.argtypes = [C.POINTER(pin.RefPictures), C.POINTER(pin.RefTask), C.POINTER(pin.RefResult), C.c_int]
+    lib.havoc_instruction_set_support.restype = C.c_int
+    rng = np.random.default_rng(99)
+    n = 460
+    for distance in (1, 2):
+        src, ref = scene.host[0][0], scene.host[distance][0]
+        base = (PAD * src.shape[1] + PAD) * src.itemsize
+        pics = pin.RefPictures(src.ctypes.data + base, ref.ctypes.data + base, src.shape[1], ref.shape[1], W, H, PAD,
+                               scene.bps, lib.havoc_instruction_set_support() if jit else 3, CTB, int(jit))
+        rtasks = (pin.RefTask * n)(*[pin.make_ref_task(rng, i, scene.bd, distance) for i in range(n)])
+        want = (pin.RefResult * n)()
+        assert lib.ref_search_batch(C.byref(pics), rtasks, want, n) == 0
+        tasks = np.zeros(n, hvb.me_task_t)
+        for i in range(n):
+            o, t = pin.oracle_task(rtasks[i], want[i]), tasks[i]
+            t["src_pic"], t["ref_pic"] = scene.pics[0], scene.pics[distance]
+            t["x0"], t["y0"], t["w"], t["h"] = o.x0, o.y0, o.w, o.h
+            for k in range(2):
+                t["mvp"][k]["x"], t["mvp"][k]["y"] = o.mvp[2 * k], o.mvp[2 * k + 1]
+            t["rateMvpFlag"] = (o.rateMvpFlag[0], o.rateMvpFlag[1])
+            t["lambda"] = o.lambda_
+            t["limitMin"]["x"], t["limitMin"]["y"] = o.limitMin[0], o.limitMin[1]
+            t["limitMax"]["x"], t["limitMax"]["y"] = o.limitMax[0], o.limitMax[1]
+            t["prev2Nx2N"]["x"], t["prev2Nx2N"]["y"] = o.prev2Nx2N[0], o.prev2Nx2N[1]
+            t["smallSearchWindow"], t["met"], t["log2CbSize"] = o.smallSearchWindow, o.met, o.log2CbSize
+            t["usePrev2Nx2N"], t["halfPel"], t["quarterPel"] = o.usePrev2Nx2N, o.halfPel, o.quarterPel
+        got = scene.ctx.me_search(tasks)
+        for i in range(n):
+            g, r = got[i], want[i]
+            key = (distance, i, tuple(tasks[i][["x0", "y0", "w", "h"]]))
+            assert (int(g["mv"]["x"]), int(g["mv"]["y"])) == tuple(r.mv), key
+            assert (int(g["mvd"]["x"]), int(g["mvd"]["y"])) == tuple(r.mvd), key
+            assert (int(g["mvInteger"]["x"]), int(g["mvInteger"]["y"])) == tuple(r.mvInteger), key
+            assert int(g["mvpFlag"]) == r.mvpFlag and int(g["cost"]) == r.cost, key
+            early = int(g["flags"]) & 1
+            if not early:
+                assert list(g["costMvdZero"]) == list(r.costMvdZero), key
+            changed = tuple(r.prev2Nx2NAfter) != tuple(rtasks[i].prev2Nx2N)
+            assert not (changed and (early or rtasks[i].partMode != 0)), key

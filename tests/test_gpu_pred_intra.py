@@ -149,29 +149,7 @@ def test_intra_pred_all_modes(scene, oracle):
                 assert np.array_equal(got[cy:cy + n, cx:cx + n], want), (c_idx, log2n, int(t[i]["mode"]))
 
 
-def filter_flag(c_idx, mode, n):
-    """turing/Dsp.h:57-70"""
-    lookup = [0b111000, 0, 0b111000] + [0b110000] * 6 + [0b100000, 0, 0b100000] + [0b110000] * 6 + [0b111000] + \
-             [0b110000] * 6 + [0b100000, 0, 0b100000] + [0b110000] * 6 + [0b111000]
-    return c_idx == 0 and bool(lookup[mode] & n)
-
-
-def filtered_neighbours(u, n, bd, strong_enabled):
-    """turing/IntraReferenceSamples.h:373-419 on an array whose corner is at index 2n"""
-    c = 2 * n
-    u = u.astype(np.int64)
-    f = u.copy()
-    top = lambda x: u[c + 1 + x]
-    left = lambda y: u[c - 1 - y]
-    strong = strong_enabled and n == 32 and abs(u[c] + top(63) - 2 * top(31)) < (1 << (bd - 5)) and \
-        abs(u[c] + left(63) - 2 * left(31)) < (1 << (bd - 5))
-    if strong:
-        for k in range(63):
-            f[c - 1 - k] = ((63 - k) * u[c] + (k + 1) * left(63) + 32) >> 6
-            f[c + 1 + k] = ((63 - k) * u[c] + (k + 1) * top(63) + 32) >> 6
-    else:
-        f[1:4 * n] = (u[0:4 * n - 1] + 2 * u[1:4 * n] + u[2:4 * n + 1] + 2) >> 2
-    return f
+from orc import filter_flag, filtered_neighbours  # noqa: E402  (pinned in test_oracle_pin_intra_filter.py)
 
 
 @pytest.mark.parametrize("derive_filtered", [True, False])

@@ -2,7 +2,7 @@
 // the batched C-ABI.  Every table slot gets a host function with the reference's signature
 // (include/havoc_b200.h) that stages its operands into small device pictures, issues a batch of ONE
 // through hvb_*, and copies the result back.  It exists to prove the boundary: the unmodified encoder
-// objects link against it and every pixel primitive then runs on the B200 (oracle/Makefile `encoder`
+// objects link against it and every pixel primitive then runs on the B200 (the test-side `encoder` make
 // target, tests/test_gpu_dropin.py).  It is not the fast path -- that is the batched ABI.
 //
 // Table filling mirrors turing/StateFunctionTables.h:63-92 and the populate bodies it calls
