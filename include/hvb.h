@@ -286,6 +286,21 @@ typedef struct
 } hvb_rdoq_task; /* 28 bytes */
 int hvb_rdoq_batch(hvb_context *ctx, const hvb_rdoq_task *tasks, int n, int32_t *cbf, hvb_mem mem);
 
+/* The distortion half of measurePuCost (turing/Search.hpp:1668-1682): predictInter without weighted prediction
+ * (turing/Dsp.h:866-915 -> predictUni :769-806 / predictBi :808-864; luma origin clamped by clipMvLumaComponent
+ * :723-731, chroma origin = luma origin >> 1, chroma phase = mv & 7) followed by measureSatd of Y, Cb and Cr against
+ * the source picture (turing/Measure.h:96-176; a chroma block that is not a multiple of 4 contributes 0).
+ * out[i] = {satdY, satdCb, satdCr}; the caller adds the PU's rate and multiplies by lambda (:1703).  When dst_pic >= 0
+ * the three predicted blocks are also stored there (what predictInter leaves in the reconstructed picture). */
+typedef struct
+{
+    int16_t src_pic, dst_pic;
+    int16_t ref_pic[2];          /* L0, L1; < 0: list not used (uni-prediction from the other) */
+    int16_t x0, y0, w, h;        /* PU in luma samples */
+    int16_t mvx[2], mvy[2];      /* quarter-pel luma vectors of L0, L1 */
+} hvb_pu_cost_task; /* 24 bytes */
+int hvb_pu_cost_batch(hvb_context *ctx, const hvb_pu_cost_task *tasks, int n, int32_t *out /* [n][3] */, hvb_mem mem);
+
 /* ---- motion search (hot loops A + B with their control flow) ------------------------------ */
 
 typedef struct
@@ -322,6 +337,36 @@ typedef struct
                                     caller must NOT update mvPreviousInteger2Nx2N and costMvdZero may be partial */
 } hvb_me_result; /* 56 bytes */
 int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, int n, hvb_me_result *out, hvb_mem mem);
+
+/* One searchMotionBi call (turing/Search.hpp:1498-1653): refine list X's vector of a bi-predicted PU against the
+ * "ideal" block 2*src - pred(other list) -- uni prediction from the other list (:1518-1534), SubtractBi (:1541-1548),
+ * the exhaustive (2r+1)^2 integer grid with its SAD4 grouping (:1551-1625) and the 3x3 half / quarter rounds
+ * (:1628-1650).  The caller chains L0 then L1 as Search<prediction_unit>::searchBi does (:1805-1823), feeding the
+ * refined vector of one call into `mvOther` of the next.  Shares its first 56 bytes with hvb_me_task. */
+typedef struct
+{
+    int16_t src_pic, ref_pic;    /* ref_pic: list X's reference picture */
+    int16_t x0, y0, w, h;
+    hvb_mv mvp[2];               /* list X's AMVP predictors */
+    int16_t other_pic, reserved0;/* the other list's reference picture */
+    int64_t rateMvpFlag[2];
+    int32_t lambda;              /* Lambda (Q16) of getReciprocalSqrtLambda * 0.5 (:1568) */
+    hvb_mv limitMin, limitMax;   /* LimitFullPelMv of the PU */
+    hvb_mv mvStart;              /* puData.mv(X): the uni-directional result for this list, quarter-pel */
+    hvb_mv mvOther;              /* puData.mv(1 - X) */
+    uint8_t smallWindow;         /* Speed::useBiSmallSearchWindow(): range 1 instead of 5 */
+    uint8_t halfPel, quarterPel, reserved1;
+} hvb_me_bi_task; /* 64 bytes */
+
+typedef struct
+{
+    hvb_mv mv, mvd;              /* refined vector and its mvd against the cheaper predictor */
+    hvb_mv mvInteger;            /* best of the integer grid */
+    int32_t mvpFlag;
+    int64_t cost;                /* cost of the winner of the last round (Q16) */
+    int32_t nSad, reserved;
+} hvb_me_bi_result; /* 32 bytes */
+int hvb_me_bi_search_batch(hvb_context *ctx, const hvb_me_bi_task *tasks, int n, hvb_me_bi_result *out, hvb_mem mem);
 
 #ifdef __cplusplus
 }

@@ -147,6 +147,53 @@ typedef struct
 void orc_me_search(const void *srcPlane, intptr_t stride_src, const void *refPlane, intptr_t stride_ref,
                    const orc_me_task *task, orc_me_result *out, int bps);
 
+/* one searchMotionBi call (turing/Search.hpp:1498-1653): refine the vector of list X of a bi-predicted PU */
+typedef struct
+{
+    int x0, y0, w, h;
+    orc_mv mvOther;  /* puData.mv(1 - X): the other list's vector, quarter-pel */
+    orc_mv mvStart;  /* puData.mv(X): where the refinement starts (the uni-directional result) */
+    orc_mv mvp[2];
+    int64_t rateMvpFlag[2];
+    int32_t lambda;  /* Lambda::set(getReciprocalSqrtLambda * 0.5) */
+    orc_mv limitMin, limitMax;
+    int smallWindow; /* speed->useBiSmallSearchWindow(): range 1 instead of 5 */
+    int halfPel, quarterPel, bitDepth;
+} orc_me_bi_task;
+
+typedef struct
+{
+    orc_mv mv, mvd, mvInteger;
+    int mvpFlag;
+    int64_t cost;
+    int nSad;
+} orc_me_bi_result;
+
+/* ref = list X's reference plane, other = list (1-X)'s; all three are plane origins */
+void orc_me_bi_search(const void *srcPlane, intptr_t stride_src, const void *refPlane, intptr_t stride_ref,
+                      const void *otherPlane, intptr_t stride_other, const orc_me_bi_task *task,
+                      orc_me_bi_result *out, int bps);
+
+/* the distortion half of measurePuCost (turing/Search.hpp:1668-1682): predictInter + SATD of Y, Cb, Cr */
+typedef struct
+{
+    const void *p;   /* sample (0,0) of a padded plane */
+    intptr_t stride; /* in samples */
+} orc_plane;
+
+typedef struct
+{
+    int x0, y0, w, h;       /* PU, luma samples */
+    int predFlag[2];
+    orc_mv mv[2];           /* quarter-pel luma vectors */
+    int picWidth, picHeight;
+    int bitDepthY, bitDepthC;
+} orc_pu_cost_task;
+
+/* predOut (optional, may be NULL / hold NULLs): receives the predicted w x h (w/2 x h/2) blocks, contiguous */
+void orc_pu_cost(const orc_plane src[3], const orc_plane ref0[3], const orc_plane ref1[3], const orc_pu_cost_task *task,
+                 int32_t satd[3], void *predOut[3], int bps);
+
 /* turing/Measure.h:177-220: rateOf(mvd) as a Q16 Cost. */
 int64_t orc_rate_of_mvd(int dx, int dy);
 

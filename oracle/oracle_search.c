@@ -17,6 +17,7 @@
  */
 #include "oracle.h"
 #include <stdlib.h>
+#include <string.h>
 #include <limits.h>
 
 typedef struct
@@ -357,4 +358,160 @@ void orc_me_search(const void *srcPlane, intptr_t ss, const void *refPlane, intp
     out->mv = mv;
     out->mvd = mvd;
     out->nSad = s.nSad;
+}
+
+/* ---- searchMotionBi (turing/Search.hpp:1498-1653) ------------------------------------------------
+ * Refines the vector of one list of a bi-predicted PU against the "ideal" block 2*src - predOther:
+ *   :1518-1534  uni prediction from the OTHER list (integer part clamped by LimitFullPelMv)
+ *   :1541-1548  SubtractBi at bit depth 6 + 2*sizeof(Sample)  (8 for u8, 10 for u16 whatever BitDepthY is)
+ *   :1551-1625  exhaustive (2r+1)^2 integer grid, r = 1 (small window) or 5; SADs come from SAD4 calls on
+ *               groups of four columns whose members are clamped individually AFTER adding the offset to
+ *               the already clamped group base (so a clamped base and its candidate vector can disagree)
+ *   :1628-1650  3x3 half- then 3x3 quarter-sample refinement, best cost reset before each, SATD against the
+ *               ideal block, lambda = Lambda(reciprocalSqrtLambda * 0.5) throughout */
+void orc_me_bi_search(const void *srcPlane, intptr_t ss, const void *refPlane, intptr_t sr, const void *otherPlane,
+                      intptr_t so, const orc_me_bi_task *b, orc_me_bi_result *out, int bps)
+{
+    orc_me_task t;
+    search s;
+    uint16_t other[64 * 64 + 64] __attribute__((aligned(32))), ideal[64 * 64 + 64] __attribute__((aligned(32)));
+    uint16_t pred[64 * 64 + 64] __attribute__((aligned(32)));
+
+    t.x0 = b->x0, t.y0 = b->y0, t.w = b->w, t.h = b->h;
+    t.mvp[0] = b->mvp[0], t.mvp[1] = b->mvp[1];
+    t.rateMvpFlag[0] = b->rateMvpFlag[0], t.rateMvpFlag[1] = b->rateMvpFlag[1];
+    t.lambda = b->lambda;
+    t.limitMin = b->limitMin, t.limitMax = b->limitMax;
+    t.bitDepth = b->bitDepth;
+    s.t = &t;
+    s.bps = bps;
+    s.ss = 64;
+    s.sr = sr;
+    s.src = (const char *)ideal;
+    s.ref = (const char *)refPlane + ((intptr_t)b->y0 * sr + b->x0) * bps;
+    s.nSad = 0;
+
+    /* prediction from the other list */
+    {
+        orc_mv mv = {(int16_t)(b->mvOther.x >> 2), (int16_t)(b->mvOther.y >> 2)};
+        limit(&s, &mv);
+        const char *p = (const char *)otherPlane + ((intptr_t)(b->y0 + mv.y) * so + b->x0 + mv.x) * bps;
+        orc_pred_uni(other, 64, p, so, b->w, b->h, b->mvOther.x & 3, b->mvOther.y & 3, b->bitDepth, 8, bps);
+    }
+    orc_subtract_bi(ideal, 64, other, 64, (const char *)srcPlane + ((intptr_t)b->y0 * ss + b->x0) * bps, ss, b->w, b->h,
+                    6 + 2 * bps, bps);
+
+    orc_mv start = {(int16_t)((int16_t)(b->mvStart.x + 1) >> 2), (int16_t)((int16_t)(b->mvStart.y + 1) >> 2)};
+    limit(&s, &start);
+    orc_mv group[4] = {start, start, start, start};
+    const orc_mv origin = {(int16_t)(start.x << 2), (int16_t)(start.y << 2)};
+    s.best.mv = origin;
+    s.best.mvd.x = s.best.mvd.y = 0;
+    s.best.mvpFlag = 0;
+    s.best.cost = INT64_MAX;
+
+    const int range = b->smallWindow ? 1 : 5;
+    for (int y = -range; y <= range; ++y)
+    {
+        int sads[4] = {0, 0, 0, 0};
+        for (int x = -range; x <= range; ++x)
+        {
+            orc_mv mv = {(int16_t)((int16_t)(origin.x + 4 * x) >> 2), (int16_t)((int16_t)(origin.y + 4 * y) >> 2)};
+            limit(&s, &mv);
+            const int i = (x + range) % 4;
+            if (i == 0)
+            {
+                group[0] = mv;
+                for (int k = 1; k < 4; ++k)
+                {
+                    group[k] = mv;
+                    group[k].x = (int16_t)(group[k].x + k);
+                    limit(&s, &group[k]);
+                }
+                for (int k = 0; k < 4; ++k) sads[k] = sad_at(&s, group[k].x, group[k].y);
+            }
+            mv.x = (int16_t)(mv.x << 2);
+            mv.y = (int16_t)(mv.y << 2);
+            cand c = make_candidate(&s, mv);
+            c.cost += (int64_t)t.lambda * sads[i];
+            consider(&s, &c);
+        }
+    }
+    out->mvInteger = s.best.mv;
+
+    if (b->halfPel)
+    {
+        const int refinement = b->quarterPel ? 1 : 2;
+        for (int step = 2; step; step -= refinement)
+        {
+            const orc_mv o = s.best.mv;
+            s.best.cost = INT64_MAX;
+            for (int y = -step; y <= step; y += step)
+                for (int x = -step; x <= step; x += step)
+                {
+                    orc_mv mv = {(int16_t)(o.x + x), (int16_t)(o.y + y)};
+                    cand c = make_candidate(&s, mv);
+                    orc_pred_uni(pred, 64, ref_at(&s, mv.x >> 2, mv.y >> 2), sr, b->w, b->h, mv.x & 3, mv.y & 3, b->bitDepth, 8, bps);
+                    c.cost += (int64_t)t.lambda * orc_measure_satd(ideal, 64, pred, 64, b->w, b->h, bps);
+                    consider(&s, &c);
+                }
+        }
+    }
+    out->mv = s.best.mv;
+    out->mvd = s.best.mvd;
+    out->mvpFlag = s.best.mvpFlag;
+    out->cost = s.best.cost;
+    out->nSad = s.nSad;
+}
+
+/* ---- the distortion half of measurePuCost (turing/Search.hpp:1668-1682) ----------------------------
+ * predictInter without weighted prediction (turing/Dsp.h:866-915):
+ *   predictUni (:769-806) / predictBi (:808-864): luma block origin = clipMvLumaComponent(xPb + (mv >> 2)) (:723-731),
+ *   chroma origin = luma origin >> 1, chroma vector = the luma vector read in eighth-samples (mv*2/SubWidthC),
+ *   8-tap luma, 4-tap chroma;
+ * then Compute<Satd, prediction_unit> (turing/Measure.h:141-176): measureSatd of the PU in Y, Cb, Cr, where a
+ * chroma block whose width|height is not a multiple of 4 contributes 0. */
+static int clip_mv_luma_component(int component, int nPbSize, int pictureSize)
+{
+    if (component + nPbSize + 4 < 0) return -nPbSize - 4;
+    if (component > pictureSize + 2) return pictureSize + 2;
+    return component;
+}
+
+void orc_pu_cost(const orc_plane src[3], const orc_plane ref0[3], const orc_plane ref1[3], const orc_pu_cost_task *t,
+                 int32_t satd[3], void *predOut[3], int bps)
+{
+    uint16_t pred[64 * 64 + 64] __attribute__((aligned(32)));
+    const orc_plane *refs[2] = {ref0, ref1};
+    const int lists = (t->predFlag[0] ? 1 : 0) + (t->predFlag[1] ? 1 : 0);
+    int bx[2], by[2];
+    for (int l = 0; l < 2; ++l)
+    {
+        bx[l] = clip_mv_luma_component(t->x0 + (t->mv[l].x >> 2), t->w, t->picWidth);
+        by[l] = clip_mv_luma_component(t->y0 + (t->mv[l].y >> 2), t->h, t->picHeight);
+    }
+    for (int c = 0; c < 3; ++c)
+    {
+        const int sh = c ? 1 : 0, w = t->w >> sh, h = t->h >> sh, taps = c ? 4 : 8, mask = c ? 7 : 3;
+        const int bd = c ? t->bitDepthC : t->bitDepthY;
+        const char *p[2] = {0, 0};
+        for (int l = 0; l < 2; ++l)
+            if (t->predFlag[l])
+                p[l] = (const char *)refs[l][c].p + ((intptr_t)(by[l] >> sh) * refs[l][c].stride + (bx[l] >> sh)) * bps;
+        if (lists == 2)
+        {
+            /* havocPredBi takes ONE stride for both references (pred_inter.h:63); pictures share their geometry */
+            orc_pred_bi(pred, 64, p[0], p[1], refs[0][c].stride, w, h, t->mv[0].x & mask, t->mv[0].y & mask, t->mv[1].x & mask,
+                        t->mv[1].y & mask, bd, taps, bps);
+        }
+        else
+        {
+            const int l = t->predFlag[0] ? 0 : 1;
+            orc_pred_uni(pred, 64, p[l], refs[l][c].stride, w, h, t->mv[l].x & mask, t->mv[l].y & mask, bd, taps, bps);
+        }
+        const char *s = (const char *)src[c].p + ((intptr_t)(t->y0 >> sh) * src[c].stride + (t->x0 >> sh)) * bps;
+        satd[c] = (c && ((w | h) & 3)) ? 0 : orc_measure_satd(s, src[c].stride, pred, 64, w, h, bps);
+        if (predOut && predOut[c])
+            for (int y = 0; y < h; ++y) memcpy((char *)predOut[c] + (size_t)y * w * bps, (const char *)pred + (size_t)y * 64 * bps, (size_t)w * bps);
+    }
 }

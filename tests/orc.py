@@ -301,3 +301,38 @@ def filtered_neighbours(u, n, bd, strong_enabled):
     else:
         f[1:4 * n] = (u[0:4 * n - 1] + 2 * u[1:4 * n] + u[2:4 * n + 1] + 2) >> 2
     return f
+
+
+class MeBiTask(C.Structure):
+    _fields_ = [
+        ("x0", C.c_int), ("y0", C.c_int), ("w", C.c_int), ("h", C.c_int),
+        ("mvOther", C.c_int16 * 2), ("mvStart", C.c_int16 * 2), ("mvp", C.c_int16 * 4),
+        ("rateMvpFlag", C.c_int64 * 2), ("lambda_", C.c_int32),
+        ("limitMin", C.c_int16 * 2), ("limitMax", C.c_int16 * 2),
+        ("smallWindow", C.c_int), ("halfPel", C.c_int), ("quarterPel", C.c_int), ("bitDepth", C.c_int),
+    ]
+
+
+class MeBiResult(C.Structure):
+    _fields_ = [("mv", C.c_int16 * 2), ("mvd", C.c_int16 * 2), ("mvInteger", C.c_int16 * 2), ("mvpFlag", C.c_int),
+                ("cost", C.c_int64), ("nSad", C.c_int)]
+
+
+class Plane(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("stride", C.c_ssize_t)]
+
+
+class PuCostTask(C.Structure):
+    _fields_ = [("x0", C.c_int), ("y0", C.c_int), ("w", C.c_int), ("h", C.c_int), ("predFlag", C.c_int * 2),
+                ("mv", C.c_int16 * 4), ("picWidth", C.c_int), ("picHeight", C.c_int), ("bitDepthY", C.c_int),
+                ("bitDepthC", C.c_int)]
+
+
+def planes3(padded, pad):
+    """(Plane * 3) over three edge-padded numpy planes (luma padded by `pad`, chroma by pad // 2)"""
+    out = (Plane * 3)()
+    for c, a in enumerate(padded):
+        pd = pad if c == 0 else pad // 2
+        out[c].p = a.ctypes.data + (pd * a.shape[1] + pd) * a.itemsize
+        out[c].stride = a.shape[1]
+    return out

@@ -151,3 +151,110 @@ def test_me_search_matches_reference_templates(scene, jit):
                 assert list(g["costMvdZero"]) == list(r.costMvdZero), key
             changed = tuple(r.prev2Nx2NAfter) != tuple(rtasks[i].prev2Nx2N)
             assert not (changed and (early or rtasks[i].partMode != 0)), key
+
+
+# ---- searchMotionBi on the device ------------------------------------------------------------------------------
+
+def fill_bi(t, o, src_pic, ref_pic, other_pic):
+    """orc.MeBiTask -> hvb_me_bi_task"""
+    t["src_pic"], t["ref_pic"], t["other_pic"] = src_pic, ref_pic, other_pic
+    t["x0"], t["y0"], t["w"], t["h"] = o.x0, o.y0, o.w, o.h
+    for k in range(2):
+        t["mvp"][k]["x"], t["mvp"][k]["y"] = o.mvp[2 * k], o.mvp[2 * k + 1]
+    t["rateMvpFlag"] = (o.rateMvpFlag[0], o.rateMvpFlag[1])
+    t["lambda"] = o.lambda_
+    t["limitMin"]["x"], t["limitMin"]["y"] = o.limitMin[0], o.limitMin[1]
+    t["limitMax"]["x"], t["limitMax"]["y"] = o.limitMax[0], o.limitMax[1]
+    t["mvStart"]["x"], t["mvStart"]["y"] = o.mvStart[0], o.mvStart[1]
+    t["mvOther"]["x"], t["mvOther"]["y"] = o.mvOther[0], o.mvOther[1]
+    t["smallWindow"], t["halfPel"], t["quarterPel"] = o.smallWindow, o.halfPel, o.quarterPel
+
+
+def test_me_bi_search_matches_oracle(scene, oracle):
+    rng = np.random.default_rng(77)
+    n = 300
+    tasks = np.zeros(n, hvb.me_bi_task_t)
+    otasks = []
+    for i in range(n):
+        w, h = PU_SIZES[i % len(PU_SIZES)]
+        o = orc.MeBiTask()
+        o.x0 = int(rng.integers(0, (W - w) // 4 + 1)) * 4
+        o.y0 = int(rng.integers(0, (H - h) // 4 + 1)) * 4
+        if i % 7 == 3:  # picture corners: the clamps and the SAD4-group quirk
+            o.x0, o.y0 = (0, 0) if i % 2 else (W - w, H - h)
+        o.w, o.h = w, h
+        far = i % 5 == 0
+        for name, truth in (("mvStart", (12, 8)), ("mvOther", (24, 16))):
+            v = np.array(truth) + (rng.integers(-300, 301, 2) if far else rng.integers(-9, 10, 2))
+            getattr(o, name)[0], getattr(o, name)[1] = int(v[0]), int(v[1])
+        for k in range(4):
+            o.mvp[k] = int((12, 8)[k % 2] + rng.integers(-20, 21))
+        o.rateMvpFlag[0], o.rateMvpFlag[1] = int(rng.integers(20000, 60000)), int(rng.integers(20000, 60000))
+        o.lambda_ = int(rng.choice([0.025, 0.1, 0.3, 0.75]) * 65536 + 0.5)
+        o.limitMin[0], o.limitMin[1] = -CTB - o.x0, -CTB - o.y0
+        o.limitMax[0], o.limitMax[1] = W + CTB - o.x0 - w, H + CTB - o.y0 - h
+        if i % 4 == 0:
+            o.limitMax[0] = min(o.limitMax[0], (o.x0 // CTB) * CTB + 3 * CTB - o.x0 - w - 15)
+            o.limitMax[1] = min(o.limitMax[1], (o.y0 // CTB) * CTB + 2 * CTB - o.y0 - h - 15)
+        o.smallWindow, o.halfPel, o.quarterPel, o.bitDepth = i % 3 == 0, 1, i % 4 != 1, scene.bd
+        fill_bi(tasks[i], o, scene.pics[0], scene.pics[1], scene.pics[2])
+        otasks.append(o)
+    got = scene.ctx.me_bi_search(tasks)
+    src, ref, other = (scene.host[k][0] for k in range(3))
+    base = (PAD * src.shape[1] + PAD) * src.itemsize
+    moved = 0
+    for i, o in enumerate(otasks):
+        r = orc.MeBiResult()
+        oracle.lib.orc_me_bi_search(C.c_void_p(src.ctypes.data + base), src.shape[1], C.c_void_p(ref.ctypes.data + base),
+                                    ref.shape[1], C.c_void_p(other.ctypes.data + base), other.shape[1], C.byref(o),
+                                    C.byref(r), scene.bps)
+        g = got[i]
+        key = (i, (o.x0, o.y0, o.w, o.h), o.smallWindow, o.quarterPel)
+        assert (int(g["mvInteger"]["x"]), int(g["mvInteger"]["y"])) == tuple(r.mvInteger), key
+        assert (int(g["mv"]["x"]), int(g["mv"]["y"])) == tuple(r.mv), key
+        assert (int(g["mvd"]["x"]), int(g["mvd"]["y"])) == tuple(r.mvd), key
+        assert int(g["mvpFlag"]) == r.mvpFlag and int(g["cost"]) == r.cost, key
+        assert int(g["nSad"]) == r.nSad, key
+        moved += tuple(r.mv) != tuple(r.mvInteger)
+    assert moved > 30, moved
+
+
+def test_me_bi_search_chain_matches_reference_templates(scene):
+    """searchBi's L0 -> L1 chain (Search.hpp:1805-1823) on the device against the unmodified reference template."""
+    import test_oracle_search_pin as pin
+    if not pin.LIB.exists():
+        pytest.skip("oracle/_ref/libsearch_ref.so not built")
+    lib = C.CDLL(str(pin.LIB))
+    lib.havoc_instruction_set_support.restype = C.c_int
+    lib.ref_search_bi_batch.argtypes = [C.POINTER(pin.RefPictures), C.c_void_p, C.c_ssize_t, C.POINTER(pin.RefBiTask),
+                                        C.POINTER(pin.RefBiResult), C.c_int]
+    rng = np.random.default_rng(123)
+    n = 320
+    src, ref0, ref1 = (scene.host[k][0] for k in range(3))
+    base = (PAD * src.shape[1] + PAD) * src.itemsize
+    pics = pin.RefPictures(src.ctypes.data + base, ref0.ctypes.data + base, src.shape[1], ref0.shape[1], W, H, PAD,
+                           scene.bps, 3, CTB, 0)
+    rtasks = (pin.RefBiTask * n)(*[pin.make_bi_task(rng, i, scene.bd) for i in range(n)])
+    want = (pin.RefBiResult * n)()
+    assert lib.ref_search_bi_batch(C.byref(pics), ref1.ctypes.data + base, ref1.shape[1], rtasks, want, n) == 0
+
+    mvs = [pin.bi_vectors(t) for t in rtasks]
+    mvd = [[(t.mvd[0], t.mvd[1]), (t.mvd[2], t.mvd[3])] for t in rtasks]
+    flag = [[t.mvpFlag[0], t.mvpFlag[1]] for t in rtasks]
+    for lst in (0, 1):  # one batch per list; the second uses the first's refined vectors, as the encoder would
+        idx = [i for i in range(n) if lst == 0 or rtasks[i].chain]
+        tasks = np.zeros(len(idx), hvb.me_bi_task_t)
+        for k, i in enumerate(idx):
+            o = pin.oracle_bi_task(rtasks[i], want[i], lst, mvs[i][lst], mvs[i][1 - lst])
+            fill_bi(tasks[k], o, scene.pics[0], scene.pics[1 + lst], scene.pics[2 - lst])
+        got = scene.ctx.me_bi_search(tasks)
+        for k, i in enumerate(idx):
+            mvs[i] = list(mvs[i])
+            mvs[i][lst] = (int(got[k]["mv"]["x"]), int(got[k]["mv"]["y"]))
+            mvd[i][lst] = (int(got[k]["mvd"]["x"]), int(got[k]["mvd"]["y"]))
+            flag[i][lst] = int(got[k]["mvpFlag"])
+    for i in range(n):
+        r = want[i]
+        key = (i, (rtasks[i].x0, rtasks[i].y0, rtasks[i].w, rtasks[i].h), rtasks[i].speed, rtasks[i].chain)
+        assert mvd[i] == [(r.mvd[0], r.mvd[1]), (r.mvd[2], r.mvd[3])], key
+        assert flag[i] == [r.mvpFlag[0], r.mvpFlag[1]], key

@@ -164,3 +164,112 @@ def test_search_control_flow_matches_reference(searchref, oracle, tag, bps, bit_
             refined += tuple(g.mv) != tuple(g.mvInteger)
             moved += tuple(g.mvInteger) != (0, 0)
         assert early > 10 and refined > 20 and moved > 100, (early, refined, moved)
+
+
+# ---- searchMotionBi (Search.hpp:1498-1653) ------------------------------------------------------------------
+
+class RefBiTask(C.Structure):
+    _fields_ = [("x0", C.c_int), ("y0", C.c_int), ("w", C.c_int), ("h", C.c_int),
+                ("mvp", C.c_int16 * 8), ("mvd", C.c_int16 * 4), ("mvpFlag", C.c_int * 2), ("mvpFlagState", C.c_int),
+                ("reciprocalSqrtLambda", C.c_double), ("speed", C.c_int), ("concurrentFrames", C.c_int),
+                ("xCtb", C.c_int), ("yCtb", C.c_int), ("bitDepth", C.c_int), ("chain", C.c_int)]
+
+
+class RefBiResult(C.Structure):
+    _fields_ = [("mvd", C.c_int16 * 4), ("mvpFlag", C.c_int * 2), ("rateMvpFlag", C.c_int64 * 2),
+                ("lambdaHalf", C.c_int32), ("reserved", C.c_int32)]
+
+
+def make_bi_task(rng, i, bit_depth):
+    t = RefBiTask()
+    w, h = PU_SIZES[i % len(PU_SIZES)]
+    if w + h == 12:  # bi-prediction is not allowed for 8x4 / 4x8 (Search.hpp:1872)
+        w, h = 8, 8
+    t.x0 = int(rng.integers(0, (W - w) // 4 + 1)) * 4
+    t.y0 = int(rng.integers(0, (H - h) // 4 + 1)) * 4
+    t.w, t.h = w, h
+    if i % 7 == 3:  # hug a picture corner so that the LimitFullPelMv clamps (and their SAD4 grouping quirk) engage
+        t.x0, t.y0 = (0, 0) if i % 2 else (W - w, H - h)
+    # list 0 points one frame back, list 1 two frames back (synth motion is +3,+2 samples per frame)
+    for lst, truth in ((0, np.array([12, 8])), (1, np.array([24, 16]))):
+        spread = [1, 3, 9, 30][i % 4]
+        for k in range(2):
+            v = truth + rng.integers(-spread, spread + 1, 2)
+            t.mvp[lst * 4 + k * 2], t.mvp[lst * 4 + k * 2 + 1] = int(v[0]), int(v[1])
+        d = rng.integers(-6, 7, 2) if i % 5 else rng.integers(-300, 301, 2)  # a few far outside: clamping
+        t.mvd[lst * 2], t.mvd[lst * 2 + 1] = int(d[0]), int(d[1])
+        t.mvpFlag[lst] = int(rng.integers(0, 2))
+    t.mvpFlagState = int(rng.integers(0, 126))
+    t.reciprocalSqrtLambda = float(rng.choice([0.05, 0.11, 0.2, 0.37, 0.6, 1.5]))
+    t.speed = i % 3
+    t.concurrentFrames = 4 if i % 5 == 0 else 1
+    t.xCtb, t.yCtb = (t.x0 // CTB) * CTB, (t.y0 // CTB) * CTB
+    t.bitDepth = bit_depth
+    t.chain = i % 2
+    return t
+
+
+def oracle_bi_task(t: RefBiTask, r: RefBiResult, lst: int, mv_this, mv_other) -> orc.MeBiTask:
+    o = orc.MeBiTask()
+    o.x0, o.y0, o.w, o.h = t.x0, t.y0, t.w, t.h
+    o.mvOther[0], o.mvOther[1] = mv_other
+    o.mvStart[0], o.mvStart[1] = mv_this
+    for k in range(4):
+        o.mvp[k] = t.mvp[lst * 4 + k]
+    o.rateMvpFlag[0], o.rateMvpFlag[1] = r.rateMvpFlag[0], r.rateMvpFlag[1]
+    o.lambda_ = r.lambdaHalf
+    o.limitMin[0], o.limitMin[1] = -CTB - t.x0, -CTB - t.y0
+    o.limitMax[0], o.limitMax[1] = W + CTB - t.x0 - t.w, H + CTB - t.y0 - t.h
+    if t.concurrentFrames > 1:
+        o.limitMax[0] = min(o.limitMax[0], t.xCtb + 3 * CTB - t.x0 - t.w - 15)
+        o.limitMax[1] = min(o.limitMax[1], t.yCtb + 2 * CTB - t.y0 - t.h - 15)
+    o.smallWindow = int(t.speed >= 2)   # Speed::useBiSmallSearchWindow
+    o.halfPel, o.quarterPel = 1, int(t.speed <= 1)
+    o.bitDepth = t.bitDepth
+    return o
+
+
+def s16(v):
+    return ((int(v) + 0x8000) & 0xFFFF) - 0x8000
+
+
+def bi_vectors(t: RefBiTask):
+    """puData.mv(X) = mvp[X][flag] + mvd (turing/Mvp.h:781-799), int16 arithmetic"""
+    return [(s16(t.mvp[l * 4 + t.mvpFlag[l] * 2] + t.mvd[l * 2]), s16(t.mvp[l * 4 + t.mvpFlag[l] * 2 + 1] + t.mvd[l * 2 + 1]))
+            for l in range(2)]
+
+
+@pytest.mark.parametrize("tag,bps,bit_depth,jit,lzcnt", CASES, ids=[c[0] for c in CASES])
+def test_bi_search_matches_reference(searchref, oracle, tag, bps, bit_depth, jit, lzcnt):
+    searchref.ref_search_bi_batch.argtypes = [C.POINTER(RefPictures), C.c_void_p, C.c_ssize_t, C.POINTER(RefBiTask),
+                                              C.POINTER(RefBiResult), C.c_int]
+    rng = np.random.default_rng(17 + bps + lzcnt)
+    n = 360
+    src, ref0, ref1 = planes(bps, bit_depth, 0), planes(bps, bit_depth, 1), planes(bps, bit_depth, 2)
+    base = (PAD * src.shape[1] + PAD) * src.itemsize
+    pics = RefPictures(src.ctypes.data + base, ref0.ctypes.data + base, src.shape[1], ref0.shape[1], W, H, PAD, bps,
+                       searchref.havoc_instruction_set_support() if jit else 3, CTB, lzcnt)
+    tasks = (RefBiTask * n)(*[make_bi_task(rng, i, bit_depth) for i in range(n)])
+    results = (RefBiResult * n)()
+    assert searchref.ref_search_bi_batch(C.byref(pics), ref1.ctypes.data + base, ref1.shape[1], tasks, results, n) == 0
+
+    refs = [ref0, ref1]
+    moved = 0
+    for i in range(n):
+        t, r = tasks[i], results[i]
+        mv = bi_vectors(t)
+        want_mvd = [(t.mvd[0], t.mvd[1]), (t.mvd[2], t.mvd[3])]
+        want_flag = [t.mvpFlag[0], t.mvpFlag[1]]
+        for lst in ((0, 1) if t.chain else (0,)):
+            o, g = oracle_bi_task(t, r, lst, mv[lst], mv[1 - lst]), orc.MeBiResult()
+            oracle.lib.orc_me_bi_search(C.c_void_p(src.ctypes.data + base), src.shape[1],
+                                        C.c_void_p(refs[lst].ctypes.data + base), refs[lst].shape[1],
+                                        C.c_void_p(refs[1 - lst].ctypes.data + base), refs[1 - lst].shape[1],
+                                        C.byref(o), C.byref(g), bps)
+            moved += tuple(g.mv) != mv[lst]
+            mv[lst] = tuple(g.mv)
+            want_mvd[lst], want_flag[lst] = tuple(g.mvd), g.mvpFlag
+        key = (tag, i, (t.x0, t.y0, t.w, t.h), t.speed, t.chain)
+        assert [(r.mvd[0], r.mvd[1]), (r.mvd[2], r.mvd[3])] == want_mvd, key
+        assert [r.mvpFlag[0], r.mvpFlag[1]] == want_flag, key
+    assert moved > 100, moved

@@ -26,6 +26,9 @@ static_assert(sizeof(hvb_rdoq_ctx) == 136, "abi");
 static_assert(sizeof(hvb_rdoq_task) == 28, "abi");
 static_assert(sizeof(hvb_me_task) == 64, "abi");
 static_assert(sizeof(hvb_me_result) == 56, "abi");
+static_assert(sizeof(hvb_me_bi_task) == 64, "abi");
+static_assert(sizeof(hvb_me_bi_result) == 32, "abi");
+static_assert(sizeof(hvb_pu_cost_task) == 24, "abi");
 
 int hvbFail(hvb_context *ctx, int status, const char *what)
 {

@@ -116,7 +116,9 @@ struct Search
     int nSad;
     int *sMid; // shared: [15][32] ints, column `lane` is this lane's horizontal-pass output
 
-    __device__ Search(const hvb_me_task &task, const HvbPlane *planes, uint32_t *smemSrc, int lane_) : t(task), lane(lane_)
+    // loadSource = false: the caller fills the shared block itself (the bi search compares against 2*src - predOther)
+    __device__ Search(const hvb_me_task &task, const HvbPlane *planes, uint32_t *smemSrc, int lane_, bool loadSource = true)
+        : t(task), lane(lane_)
     {
         const HvbPlane &sp = planes[t.src_pic * 3], &rp = planes[t.ref_pic * 3];
         sr = rp.stride;
@@ -125,7 +127,7 @@ struct Search
         wpr = t.w >> Word<Sample>::kLog2Spw;
         words = wpr * t.h;
         wprInv = (65536 + wpr - 1) / wpr;
-        for (int i = lane; i < words; i += 32)
+        for (int i = lane; loadSource && i < words; i += 32)
         {
             const int y = (i * wprInv) >> 16, xw = i - y * wpr;
             smemSrc[i] = Word<Sample>::load(src + y * sp.stride + (xw << Word<Sample>::kLog2Spw));
@@ -575,6 +577,160 @@ __global__ void __launch_bounds__(kWarps * 32)
     }
 }
 
+// ---- bi-directional refinement: searchMotionBi (turing/Search.hpp:1498-1653) -------------------------
+//
+// One call refines list X's vector of a bi-predicted PU against the "ideal" block 2*src - predOther.  The warp
+// builds that block in its shared source slot (8-tap prediction from the other list, SubtractBi at bit depth
+// 6 + 2*sizeof(Sample)), then runs the reference's exhaustive (2r+1)^2 integer grid 32 candidates at a time and
+// the two 3x3 fractional rounds 9 candidates at a time, each followed by the ordered arg-min.
+
+// hvb_me_bi_task shares its first 56 bytes with hvb_me_task (pictures, block, predictors, rates, lambda, limits),
+// so the Search<> machinery reads it through that type.
+static_assert(offsetof(hvb_me_bi_task, mvp) == offsetof(hvb_me_task, mvp) &&
+              offsetof(hvb_me_bi_task, rateMvpFlag) == offsetof(hvb_me_task, rateMvpFlag) &&
+              offsetof(hvb_me_bi_task, lambda) == offsetof(hvb_me_task, lambda) &&
+              offsetof(hvb_me_bi_task, limitMin) == offsetof(hvb_me_task, limitMin) &&
+              offsetof(hvb_me_bi_task, limitMax) == offsetof(hvb_me_task, limitMax) &&
+              sizeof(hvb_me_bi_task) == sizeof(hvb_me_task), "hvb_me_bi_task must overlay hvb_me_task");
+
+// column q, rows r0..r0+3 of the 8-tap prediction at quarter-pel (mvx, mvy); `R` = sample (0,0) of the block in the
+// reference plane.  Registers only: 11 horizontally filtered values feed 4 vertical filters.
+template <typename Sample>
+__device__ __forceinline__ void predColumn4(const Sample *R, int sr, int q, int r0, int mvx, int mvy, int bitDepth, int (&out)[4])
+{
+    const int shift1 = min(4, bitDepth - 8), shift3 = max(2, 14 - bitDepth);
+    const int maxv = (1 << bitDepth) - 1;
+    const int xf = mvx & 3, yf = mvy & 3;
+    const Sample *p0 = R + (intptr_t)(r0 + (mvy >> 2) - 3) * sr + (q + (mvx >> 2) - 3);
+    int mids[11];
+#pragma unroll
+    for (int r = 0; r < 11; ++r)
+    {
+        const Sample *p = p0 + r * sr;
+        int mid = 0;
+        if (xf)
+        {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mid += kLumaTaps[xf][k] * (int)__ldg(p + k);
+        }
+        else
+            mid = (int)__ldg(p + 3) << 6;
+        mids[r] = mid >> shift1;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        int v = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += kLumaTaps[yf][k] * mids[i + k];
+        out[i] = hvbClip3(0, maxv, (v + (1 << (5 + shift3))) >> (6 + shift3));
+    }
+}
+
+template <typename Sample>
+__global__ void __launch_bounds__(kWarps * 32)
+    meBiSearchKernel(const HvbPlane *__restrict__ planes, const hvb_me_bi_task *__restrict__ tasks, int n,
+                     hvb_me_bi_result *__restrict__ out, int bitDepth)
+{
+    extern __shared__ __align__(16) uint32_t smemMe[];
+    constexpr int kBlockWords = sizeof(Sample) == 1 ? 64 * 64 / 4 : kSrcWords;
+    constexpr int kWordsPerWarp = kBlockWords + kExtraWords;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *sSrc = smemMe + warp * kWordsPerWarp;
+    int *sScratch = reinterpret_cast<int *>(sSrc + kBlockWords);
+    int *sMvx = sScratch, *sMvy = sScratch + 10, *sSatd = sScratch + 20;
+    const int warpsTotal = gridDim.x * kWarps;
+    for (int i = blockIdx.x * kWarps + warp; i < n; i += warpsTotal)
+    {
+        const hvb_me_bi_task bt = tasks[i];
+        const hvb_me_task &t = reinterpret_cast<const hvb_me_task &>(bt);
+        Search<Sample> s(t, planes, sSrc, lane, false);
+        s.sMid = sScratch + 32;
+
+        // ---- ideal block (:1518-1548) ----
+        {
+            const HvbPlane &sp = planes[bt.src_pic * 3], &op = planes[bt.other_pic * 3];
+            const Sample *src = reinterpret_cast<const Sample *>(sp.base) + (intptr_t)bt.y0 * sp.stride + bt.x0;
+            int ox = bt.mvOther.x >> 2, oy = bt.mvOther.y >> 2;
+            s.limit(ox, oy); // only the integer part is clamped; the fraction is kept
+            const int omvx = (ox << 2) | (bt.mvOther.x & 3), omvy = (oy << 2) | (bt.mvOther.y & 3);
+            const Sample *other = reinterpret_cast<const Sample *>(op.base) + (intptr_t)bt.y0 * op.stride + bt.x0;
+            Sample *ideal = reinterpret_cast<Sample *>(sSrc);
+            const int idealMax = (1 << (6 + 2 * (int)sizeof(Sample))) - 1;
+            const int jobs = bt.w * (bt.h >> 2);
+            for (int job = lane; job < jobs; job += 32)
+            {
+                const int strip = job / bt.w, q = job - strip * bt.w;
+                int pred[4];
+                predColumn4<Sample>(other, op.stride, q, strip * 4, omvx, omvy, bitDepth, pred);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                {
+                    const int y = strip * 4 + k;
+                    ideal[y * bt.w + q] = (Sample)hvbClip3(0, idealMax, 2 * (int)__ldg(src + (intptr_t)y * sp.stride + q) - pred[k]);
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- exhaustive integer grid (:1551-1625) ----
+        int sx = (int16_t)(bt.mvStart.x + 1) >> 2, sy = (int16_t)(bt.mvStart.y + 1) >> 2;
+        s.limit(sx, sy);
+        s.best.mv = hvb_mv{(int16_t)(sx << 2), (int16_t)(sy << 2)};
+        const int range = bt.smallWindow ? 1 : 5, side = 2 * range + 1, total = side * side;
+        for (int base = 0; base < total; base += 32)
+        {
+            const int q = min(base + lane, total - 1), nc = min(32, total - base);
+            const int row = q / side, col = q - row * side, k = col & 3;
+            int cx = sx + col - range, cy = sy + row - range; // the candidate's own vector
+            s.limit(cx, cy);
+            // its SAD comes from member k of a SAD4 group whose base was clamped BEFORE k was added (:1590-1608)
+            int px = sx + (col - k) - range, py = sy + row - range;
+            s.limit(px, py);
+            px += k;
+            s.limit(px, py);
+            const int sad = s.sadMulti(nc, px, py);
+            Cand c = s.makeCandidate(hvb_mv{(int16_t)(cx << 2), (int16_t)(cy << 2)});
+            c.cost += (long long)bt.lambda * sad;
+            s.considerLanes(c, base + lane < total);
+        }
+        hvb_me_bi_result r;
+        r.mvInteger = s.best.mv;
+        r.nSad = side * ((side + 3) / 4) * 4; // what the reference's SAD4 calls evaluate
+        r.reserved = 0;
+
+        // ---- fractional rounds (:1628-1650): 3x3 at half- then quarter-sample spacing, best cost reset before each ----
+        if (bt.halfPel)
+            for (int step = 2; step > 0; step -= bt.quarterPel ? 1 : 2)
+            {
+                const hvb_mv origin = s.best.mv;
+                s.best.cost = 0x7fffffffffffffffLL;
+                if (lane < 9)
+                {
+                    sMvx[lane] = origin.x + (lane % 3 - 1) * step;
+                    sMvy[lane] = origin.y + (lane / 3 - 1) * step;
+                    sSatd[lane] = 0;
+                }
+                __syncwarp();
+                if (((bt.w | bt.h) & 7) == 0)
+                    subpelEval<Sample, 3>(s, sMvx, sMvy, 9, sSatd, bitDepth);
+                else
+                    subpelEval<Sample, 2>(s, sMvx, sMvy, 9, sSatd, bitDepth);
+                const int me = min(lane, 8);
+                Cand c = s.makeCandidate(hvb_mv{(int16_t)sMvx[me], (int16_t)sMvy[me]});
+                c.cost += (long long)bt.lambda * sSatd[me];
+                s.considerLanes(c, lane < 9);
+                __syncwarp();
+            }
+        r.mv = s.best.mv;
+        r.mvd = s.best.mvd;
+        r.mvpFlag = s.best.mvpFlag;
+        r.cost = s.best.cost;
+        if (lane == 0) out[i] = r;
+        __syncwarp();
+    }
+}
+
 } // namespace
 
 extern "C" int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, int n, hvb_me_result *out, hvb_mem mem)
@@ -604,4 +760,33 @@ extern "C" int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, i
     }
     HVB_LAUNCH_CHECK(ctx, "meSearchKernel");
     return hvbStageOut(ctx, out, sizeof(hvb_me_result) * n, mem, st);
+}
+
+extern "C" int hvb_me_bi_search_batch(hvb_context *ctx, const hvb_me_bi_task *tasks, int n, hvb_me_bi_result *out, hvb_mem mem)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && out)));
+    if (!n) return HVB_OK;
+    cudaSetDevice(ctx->device);
+    HvbStaged st;
+    int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(hvb_me_bi_result) * n, mem, &st);
+    if (rc) return rc;
+    int blocks = (n + kWarps - 1) / kWarps;
+    const int cap = ctx->smCount * 4;
+    if (blocks > cap) blocks = cap;
+    const auto *dT = static_cast<const hvb_me_bi_task *>(st.dTasks);
+    auto *dO = static_cast<hvb_me_bi_result *>(st.dOut);
+    if (ctx->bps == 1)
+    {
+        const int smem = kWarps * (64 * 64 / 4 + kExtraWords) * 4;
+        cudaFuncSetAttribute(meBiSearchKernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        meBiSearchKernel<uint8_t><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
+    }
+    else
+    {
+        const int smem = kWarps * (kSrcWords + kExtraWords) * 4;
+        cudaFuncSetAttribute(meBiSearchKernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        meBiSearchKernel<uint16_t><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
+    }
+    HVB_LAUNCH_CHECK(ctx, "meBiSearchKernel");
+    return hvbStageOut(ctx, out, sizeof(hvb_me_bi_result) * n, mem, st);
 }

@@ -56,6 +56,15 @@ me_task_t = np.dtype([("src_pic", "<i2"), ("ref_pic", "<i2"), ("x0", "<i2"), ("y
                       ("limitMin", mv_t), ("limitMax", mv_t), ("prev2Nx2N", mv_t), ("smallSearchWindow", "u1"),
                       ("met", "u1"), ("log2CbSize", "u1"), ("usePrev2Nx2N", "u1"), ("halfPel", "u1"),
                       ("quarterPel", "u1"), ("reserved", "u1", 2)], align=True)
+pu_cost_task_t = np.dtype([("src_pic", "<i2"), ("dst_pic", "<i2"), ("ref_pic", "<i2", 2), ("x0", "<i2"), ("y0", "<i2"),
+                           ("w", "<i2"), ("h", "<i2"), ("mvx", "<i2", 2), ("mvy", "<i2", 2)], align=True)
+me_bi_task_t = np.dtype([("src_pic", "<i2"), ("ref_pic", "<i2"), ("x0", "<i2"), ("y0", "<i2"), ("w", "<i2"),
+                         ("h", "<i2"), ("mvp", mv_t, 2), ("other_pic", "<i2"), ("reserved0", "<i2"),
+                         ("rateMvpFlag", "<i8", 2), ("lambda", "<i4"), ("limitMin", mv_t), ("limitMax", mv_t),
+                         ("mvStart", mv_t), ("mvOther", mv_t), ("smallWindow", "u1"), ("halfPel", "u1"),
+                         ("quarterPel", "u1"), ("reserved1", "u1")], align=True)
+me_bi_result_t = np.dtype([("mv", mv_t), ("mvd", mv_t), ("mvInteger", mv_t), ("mvpFlag", "<i4"), ("cost", "<i8"),
+                           ("nSad", "<i4"), ("reserved", "<i4")], align=True)
 me_result_t = np.dtype([("mv", mv_t), ("mvd", mv_t), ("mvInteger", mv_t), ("mvpFlag", "<i4"), ("cost", "<i8"),
                         ("costMvdZero", "<i8", 2), ("subpelCost", "<i8"), ("nSad", "<i4"), ("flags", "<i4")],
                        align=True)
@@ -66,6 +75,7 @@ _SIZES = {
     "intra_sweep": (intra_sweep_task_t, 24), "transform": (transform_task_t, 16), "quant": (quant_task_t, 24),
     "ita": (ita_task_t, 24), "tu": (tu_task_t, 60), "tu_result": (tu_result_t, 16), "rdoq_ctx": (rdoq_ctx_t, 136),
     "rdoq": (rdoq_task_t, 28), "me": (me_task_t, 64), "me_result": (me_result_t, 56),
+    "pu_cost": (pu_cost_task_t, 24), "me_bi": (me_bi_task_t, 64), "me_bi_result": (me_bi_result_t, 32),
 }
 for _name, (_dt, _size) in _SIZES.items():
     assert _dt.itemsize == _size, (_name, _dt.itemsize, _size)
@@ -111,7 +121,7 @@ def load_library() -> C.CDLL:
     lib.hvb_rdoq_contexts_upload.argtypes = [vp, vp, i32, i32]
     for name in ("hvb_sad_batch", "hvb_ssd_batch", "hvb_satd_batch", "hvb_sad4_batch", "hvb_interp_satd_batch",
                  "hvb_intra_satd35_batch", "hvb_quantize_batch", "hvb_tu_chain_batch", "hvb_rdoq_batch",
-                 "hvb_me_search_batch"):
+                 "hvb_me_search_batch", "hvb_me_bi_search_batch", "hvb_pu_cost_batch"):
         if hasattr(lib, name):
             getattr(lib, name).argtypes = [vp, vp, i32, vp, i32]
     for name in ("hvb_pred_batch", "hvb_subtract_bi_batch", "hvb_intra_pred_batch", "hvb_transform_fwd_batch",
@@ -296,3 +306,10 @@ class Context:
 
     def me_search(self, tasks, n=None, out=None, mem=HOST):
         return self._with_out("hvb_me_search_batch", tasks, n, out, me_result_t, lambda k: (k,), mem)
+
+    def pu_cost(self, tasks, n=None, out=None, mem=HOST):
+        """-> int32 [n][3]: SATD of Y, Cb, Cr of each PU's inter prediction"""
+        return self._with_out("hvb_pu_cost_batch", tasks, n, out, np.int32, lambda k: (k, 3), mem)
+
+    def me_bi_search(self, tasks, n=None, out=None, mem=HOST):
+        return self._with_out("hvb_me_bi_search_batch", tasks, n, out, me_bi_result_t, lambda k: (k,), mem)
