@@ -68,7 +68,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if jobs:
         with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as pool:
             list(pool.map(lambda so: _compile(nvcc, so[0], so[1], verbose), jobs))
-    if jobs or not LIB.exists():
+    if jobs or not LIB.exists() or LIB.stat().st_mtime < max(o.stat().st_mtime for o in objs):
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-soname=libhvb.so", "-o", str(LIB),
                *map(str, objs)]
         res = subprocess.run(cmd, capture_output=True, text=True)

@@ -28,12 +28,20 @@
 // is the number of pattern calls (5-20), not the number of SADs (30-900).
 // Algorithmic traffic per PU: w*h*B (source, once) + nSad*w*h*B + 17 ((w+7)(h+7) + w*h) B.
 #include "hvb_internal.cuh"
+#include "hvb_subpel.cuh"
 
 namespace {
 
 constexpr int kWarps = 8;
 constexpr int kSrcWords = 64 * 64 / 2; // u16 worst case: 2 samples per word
-constexpr int kExtraWords = 32 + 15 * 32; // per warp: candidate scratch + the sub-pel horizontal-pass columns
+// per warp: candidate scratch (32 words) + the sub-pel workspace: 8 bit: interpolation planes and candidate
+// predictions (hvb_subpel.cuh); 16 bit: the horizontal-pass columns [15][32]
+constexpr int kSubpelWords = subpel::kScratchBytes / 4 > 15 * 32 ? subpel::kScratchBytes / 4 : 15 * 32;
+constexpr int kExtraWords = 32 + kSubpelWords;
+// candidate index of grid position (dy + 1) * 3 + dx + 1 in the reference's pattern order (Search.hpp:2346, :2352)
+__device__ __constant__ int8_t kCandHalfUni[9] = {1, 2, 3, 4, 0, 5, 6, 7, 8};
+__device__ __constant__ int8_t kCandQuarterUni[9] = {0, 1, 2, 3, -1, 4, 5, 6, 7};
+__device__ __constant__ int8_t kCandGrid[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
 
 // ---- sample-type helpers: 32-bit words of 4 (u8) or 2 (u16) samples -------------------------------
 template <typename Sample>
@@ -504,7 +512,11 @@ __device__ __noinline__ void patternSearch(Search<Sample> &s, int *sMvx, int *sM
         sSatd[s.lane] = 0;
     }
     __syncwarp();
-    if (((s.t.w | s.t.h) & 7) == 0)
+    if (sizeof(Sample) == 1) // 8 bit: shared interpolation planes + tensor-core SATD (hvb_subpel.cuh)
+        subpel::evalRound(reinterpret_cast<const uint8_t *>(s.srcS), s.t.w, s.t.h, reinterpret_cast<const uint8_t *>(s.ref), s.sr, mv.x,
+                          mv.y, tryOrigin ? 2 : 1, tryOrigin ? kCandHalfUni : kCandQuarterUni, n, reinterpret_cast<uint8_t *>(s.sMid),
+                          sSatd, s.lane);
+    else if (((s.t.w | s.t.h) & 7) == 0)
         subpelEval<Sample, 3>(s, sMvx, sMvy, n, sSatd, bitDepth);
     else
         subpelEval<Sample, 2>(s, sMvx, sMvy, n, sSatd, bitDepth);
@@ -532,14 +544,16 @@ __device__ __noinline__ void patternSearch(Search<Sample> &s, int *sMvx, int *sM
     __syncwarp();
 }
 
-template <typename Sample>
+// kFused: the sub-pel refinement runs in this kernel (16-bit pictures); otherwise the kernel stops after the integer
+// search and hvb_me_subpel.cu refines the whole batch in a second launch (8-bit pictures).
+template <typename Sample, bool kFused>
 __global__ void __launch_bounds__(kWarps * 32)
     meSearchKernel(const HvbPlane *__restrict__ planes, const hvb_me_task *__restrict__ tasks, int n, hvb_me_result *__restrict__ out,
                    int bitDepth)
 {
     extern __shared__ __align__(16) uint32_t smemMe[];
     constexpr int kBlockWords = sizeof(Sample) == 1 ? 64 * 64 / 4 : kSrcWords;
-    constexpr int kWordsPerWarp = kBlockWords + kExtraWords;
+    constexpr int kWordsPerWarp = kBlockWords + (kFused ? kExtraWords : 0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *sSrc = smemMe + warp * kWordsPerWarp;
     int *sScratch = reinterpret_cast<int *>(sSrc + kBlockWords);
@@ -562,7 +576,7 @@ __global__ void __launch_bounds__(kWarps * 32)
         r.subpelCost = 0;
         r.flags = early ? 1 : 0; // bit 0: returned through MET -> mvPreviousInteger2Nx2N is not updated
         hvb_mv mv = s.best.mv, mvd = s.best.mvd;
-        if (t.halfPel) // searchMotionUni (Search.hpp:1335-1347)
+        if (kFused && t.halfPel) // searchMotionUni (Search.hpp:1335-1347)
         {
             long long bestCost = 0;
             patternSearch(s, sMvx, sMvy, sSatd, kHalf9, 9, true, mv, mvd, bestCost, bitDepth);
@@ -712,7 +726,10 @@ __global__ void __launch_bounds__(kWarps * 32)
                     sSatd[lane] = 0;
                 }
                 __syncwarp();
-                if (((bt.w | bt.h) & 7) == 0)
+                if (sizeof(Sample) == 1)
+                    subpel::evalRound(reinterpret_cast<const uint8_t *>(s.srcS), bt.w, bt.h, reinterpret_cast<const uint8_t *>(s.ref), s.sr,
+                                      origin.x, origin.y, step, kCandGrid, 9, reinterpret_cast<uint8_t *>(s.sMid), sSatd, lane);
+                else if (((bt.w | bt.h) & 7) == 0)
                     subpelEval<Sample, 3>(s, sMvx, sMvy, 9, sSatd, bitDepth);
                 else
                     subpelEval<Sample, 2>(s, sMvx, sMvy, 9, sSatd, bitDepth);
@@ -733,6 +750,8 @@ __global__ void __launch_bounds__(kWarps * 32)
 
 } // namespace
 
+int hvbLaunchMeSubpel(hvb_context *ctx, const hvb_me_task *dTasks, int n, hvb_me_result *dOut); // hvb_me_subpel.cu
+
 extern "C" int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, int n, hvb_me_result *out, hvb_mem mem)
 {
     HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && out)));
@@ -748,17 +767,24 @@ extern "C" int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, i
     auto *dO = static_cast<hvb_me_result *>(st.dOut);
     if (ctx->bps == 1)
     {
-        const int smem = kWarps * (64 * 64 / 4 + kExtraWords) * 4;
-        cudaFuncSetAttribute(meSearchKernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        meSearchKernel<uint8_t><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
+        // integer search, then the sub-pel refinement of the whole batch (hvb_me_subpel.cu) on the same stream
+        const int smem = kWarps * (64 * 64 / 4) * 4;
+        cudaFuncSetAttribute(meSearchKernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        int perSm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, meSearchKernel<uint8_t, false>, kWarps * 32, smem);
+        blocks = min((n + kWarps - 1) / kWarps, ctx->smCount * max(perSm, 1));
+        meSearchKernel<uint8_t, false><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
+        HVB_LAUNCH_CHECK(ctx, "meSearchKernel");
+        rc = hvbLaunchMeSubpel(ctx, dT, n, dO);
+        if (rc) return rc;
     }
     else
     {
         const int smem = kWarps * (kSrcWords + kExtraWords) * 4;
-        cudaFuncSetAttribute(meSearchKernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        meSearchKernel<uint16_t><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
+        cudaFuncSetAttribute(meSearchKernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        meSearchKernel<uint16_t, true><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
+        HVB_LAUNCH_CHECK(ctx, "meSearchKernel");
     }
-    HVB_LAUNCH_CHECK(ctx, "meSearchKernel");
     return hvbStageOut(ctx, out, sizeof(hvb_me_result) * n, mem, st);
 }
 

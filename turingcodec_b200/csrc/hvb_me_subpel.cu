@@ -1,0 +1,596 @@
+// hvb_me_subpel.cu -- the sub-pel refinement of the uni-directional motion search for 8-bit pictures, as its
+// own kernel behind the integer search (hvb_me.cu): one launch refines every PU of the batch.
+//
+// Reference semantics (bit-exact decisions):
+//   subPelRefinement / patternSearch / costMv / costDistortionMv   turing/Search.hpp:1965-2060, :2339-2357
+//   HavocPredUni 8-tap    havoc/pred_inter.cpp:76-202
+//   measureSatd, hadamard turing/Measure.h:96-135, havoc/hadamard.cpp:58-98
+//   rateOf(mvd)           turing/Measure.h:177-220
+//
+// Work decomposition.  A PU is cut into UNITS: 8x8 blocks when both dimensions are multiples of 8 (the
+// reference then measures SATD in 8x8 Hadamard tiles), otherwise 8x4 or 4x8 blocks of two 4x4 tiles.  A warp
+// owns four consecutive PUs of the task array and walks the concatenation of their units four at a time, so a
+// batch of 8x8 PUs fills the warp exactly like one 16x16 PU does.  Per group of four units and per round
+// (half-pel: 9 candidates around the integer vector; quarter-pel: 8 around the half-pel winner):
+//
+//   H pass   64 (unit, support row) jobs, two per lane: the row's 20 bytes are loaded once as aligned words;
+//            every output is two IDP.4A (u8 samples x s8 taps).  The half-pel round needs one filtered plane
+//            (9 columns: the -1/2 and +1/2 candidates are the same plane one sample apart) plus the integer
+//            samples; the quarter-pel round three planes.  Intermediates are the reference's 16-bit `mid`
+//            values, stored column-major in shared memory.
+//   V pass   (unit, plane, column) jobs: a lane loads its column (4 x LDS.64) and slides the 8-tap window down
+//            it, 4 IDP.2A (s16 x s8) per output.  In the half-pel round each distinct (column, row) is computed
+//            once (9x9 for the diagonal candidates) and the candidates read it at an offset.
+//   SATD     the Hadamard transform of an 8x8 (4x4) tile is a product with the 64x64 (16x16) Kronecker matrix
+//            H (x) H, so eight (unit, candidate) tiles at a time are one [H | -H] x [src ; pred] integer GEMM on
+//            the tensor cores (IMMA m16n8k32, s8 x u8 -> s32) with fragments read from the 8-bit blocks in shared
+//            memory; sum |.| is invariant to the row order of H, so the Sylvester matrix (-1)^popc(m & k) is
+//            used and every A fragment register is one of four per-lane constants.
+//
+// Decisions (cost = rateOf(mvd) + lambda * SATD, candidates in the reference's pattern order, strict <) are taken
+// by one lane per PU between the rounds.
+#include "hvb_internal.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kGroup = 4;                 // units per group = PUs per warp chunk
+constexpr int kColStride = 20;            // halfwords per mid column: 16 support rows + 4 (40 bytes: 8-byte aligned, odd/2 banks)
+constexpr int kPlaneHalfwords = 9 * kColStride;
+constexpr int kUnitMidBytes = 3 * kPlaneHalfwords * 2;      // 1080
+constexpr int kPredRow = 12;              // half-pel round: bytes per prediction row (9 columns + pad)
+constexpr int kPredPlane = 112;           // 9 rows x 12, padded
+constexpr int kUnitPredBytes = 512;       // half-pel: 4 planes x 112; quarter-pel: 8 candidates x 8 rows x 8
+constexpr int kUnitSrcBytes = 64;
+
+struct UnitDesc
+{
+    const uint8_t *ref; // sample (0,0) of the unit in the reference plane at the integer part of the round's centre
+    int slot;           // PU of the chunk (0..3) the unit belongs to
+    int uwuh;           // uw | uh << 8 | valid << 16 (padding units of the last group repeat the last unit and are not summed)
+};
+
+struct WarpSmem
+{
+    int16_t mids[kGroup][3 * kPlaneHalfwords];
+    uint8_t preds[kGroup][kUnitPredBytes];
+    uint8_t src[kGroup][kUnitSrcBytes];
+    UnitDesc unit[kGroup];
+    int satd[kGroup][12];
+    // per PU of the chunk
+    int cx[kGroup], cy[kGroup];   // centre of the current round, quarter samples
+    int units[kGroup];            // units of this PU in the current (round, tile mode) pass
+    int geom[kGroup];             // uw | uh << 8 | unitsX << 16
+    const uint8_t *refBase[kGroup]; // sample (x0, y0) of the reference plane
+    const uint8_t *srcBase[kGroup];
+    int stride[kGroup];           // reference stride; source stride in srcStride
+    int srcStride[kGroup];
+};
+
+// 8-tap luma filters (havoc/pred_inter.cpp:39-69) packed as s8x4 words, taps 0..3 and 4..7
+__device__ __constant__ uint32_t kTapWords[4][2] = {{0x40000000u, 0x00000000u},
+                                                    {0x3af604ffu, 0x0001fb11u},
+                                                    {0x28f504ffu, 0xff04f528u},
+                                                    {0x11fb0100u, 0xff04f63au}};
+// candidates in the reference's pattern order (Search.hpp:2346, :2352) as grid indices (dy + 1) * 3 + dx + 1
+__device__ __constant__ int8_t kHalfOrder[9] = {4, 0, 1, 2, 3, 5, 6, 7, 8};
+__device__ __constant__ int8_t kQuarterOrder[8] = {0, 1, 2, 3, 5, 6, 7, 8};
+
+__device__ __forceinline__ int dp4aUS(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ int clip8(int v) { return min(max(v, 0), 255); }
+
+__device__ __forceinline__ int vFilter(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t t0, uint32_t t1)
+{
+    int acc = 1 << 11; // 2^(5 + shift3), shift3 = 6 at 8 bit
+    acc = __dp2a_lo((int)p0, (int)t0, acc);
+    acc = __dp2a_hi((int)p1, (int)t0, acc);
+    acc = __dp2a_lo((int)p2, (int)t1, acc);
+    acc = __dp2a_hi((int)p3, (int)t1, acc);
+    return clip8(acc >> 12);
+}
+
+__device__ __forceinline__ long long rateOfMvd(int dx, int dy)
+{
+    const int rx = 32 - __clz(abs(dx)), ry = 32 - __clz(abs(dy));
+    return (long long)(rx + ry + 1) << 17;
+}
+
+__device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// A-fragment register (m-tile mt, k-step ks, reg) holds A[m][k..k+3], m = 16 mt + (lane >> 2) + 8 (reg & 1),
+// k = 32 ks + 4 (lane & 3) + 16 (reg >> 1), entries (-1)^popc(m & k): the byte pattern depends on m & 3, the sign on
+// the other bits, of which two products involve the lane; the rest is compile-time in the unrolled loops.
+struct HadamardA
+{
+    uint32_t e[2], o[2]; // [negated], registers with reg & 1 == 0 / 1
+    __device__ __forceinline__ explicit HadamardA(int lane)
+    {
+        const int g = lane >> 2, t = lane & 3;
+        const uint32_t pat = (g & 2) ? ((g & 1) ? 0x01ffff01u : 0xffff0101u) : ((g & 1) ? 0xff01ff01u : 0x01010101u);
+        const int q0 = (g >> 2) & t & 1, q1 = q0 ^ (t >> 1);
+        e[0] = q0 ? pat ^ 0xfefefefeu : pat;
+        e[1] = e[0] ^ 0xfefefefeu;
+        o[0] = q1 ? pat ^ 0xfefefefeu : pat;
+        o[1] = o[0] ^ 0xfefefefeu;
+    }
+};
+
+// 4 prediction bytes at `p + off` where p is word aligned and off is 0 or 1
+__device__ __forceinline__ uint32_t loadPred4(const uint8_t *p, int off)
+{
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
+    const uint32_t lo = q[0];
+    return off ? __funnelshift_r(lo, q[1], 8) : lo;
+}
+
+// ---- H pass ---------------------------------------------------------------------------------------------------
+// HALF: plane 0 = integer samples << 6 (columns 0..uw-1), plane 1 = half-pel columns x - 1/2 (x = 0..uw), and the
+// candidates that need no vertical filter: P00 (plane 0 of preds) and PB (plane 1 of preds).
+// QUARTER: planes v = 0..2 at the horizontal quarter offsets hx + v - 1.
+template <bool HALF>
+__device__ __forceinline__ void hPass(WarpSmem &s, int lane)
+{
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j)
+    {
+        const int job = lane + 32 * j, u = job >> 4, r = job & 15;
+        const UnitDesc d = s.unit[u];
+        const int uw = d.uwuh & 0xff, uh = (d.uwuh >> 8) & 0xff;
+        if (r >= uh + 8) continue;
+        const int slot = d.slot;
+        const uint8_t *p = d.ref + (intptr_t)(r - 4) * s.stride[slot] - 4;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+        const unsigned sh = (unsigned)(a & 3) * 8;
+        uint32_t w[6], v[5];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) w[i] = __ldg(q + i);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], sh);
+        int16_t *mid = s.mids[u] + r;
+        if (HALF)
+        {
+            const uint32_t t0 = kTapWords[2][0], t1 = kTapWords[2][1];
+            uint8_t *pb = s.preds[u] + kPredPlane + (r - 4) * kPredRow, *p00 = s.preds[u] + (r - 4) * kPredRow;
+            const bool body = r >= 4 && r < 4 + uh;
+#pragma unroll
+            for (int c = 0; c < 9; ++c)
+                if (c <= uw)
+                {
+                    const int k = c >> 2, sft = (c & 3) * 8;
+                    const uint32_t lo = sft ? __funnelshift_r(v[k], v[k + 1], sft) : v[k];
+                    const uint32_t hi = sft ? __funnelshift_r(v[k + 1], v[k + 2 < 5 ? k + 2 : 4], sft) : v[k + 1];
+                    const int m = dp4aUS(hi, t1, dp4aUS(lo, t0, 0));
+                    mid[kPlaneHalfwords + c * kColStride] = (int16_t)m;
+                    if (body) pb[c] = (uint8_t)clip8((m + 32) >> 6);
+                }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < uw)
+                {
+                    const int smp = (v[(c + 4) >> 2] >> (((c + 4) & 3) * 8)) & 0xff;
+                    mid[c * kColStride] = (int16_t)(smp << 6);
+                    if (body) p00[c] = (uint8_t)smp;
+                }
+        }
+        else
+        {
+            const int hx = s.cx[slot] & 3;
+#pragma unroll 1
+            for (int pl = 0; pl < 3; ++pl)
+            {
+                const int xq = hx + pl - 1, fx = xq & 3;
+                const uint32_t t0 = kTapWords[fx][0], t1 = kTapWords[fx][1];
+                // column c reads bytes c + (xq >> 2) + 1 .. + 8 of the row
+                uint32_t sv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sv[i] = xq >= 0 ? __funnelshift_r(v[i], v[i + 1], 8) : v[i];
+                int16_t *mp = mid + pl * kPlaneHalfwords;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < uw)
+                    {
+                        const int k = c >> 2, sft = (c & 3) * 8;
+                        const uint32_t lo = sft ? __funnelshift_r(sv[k], sv[k + 1], sft) : sv[k];
+                        const uint32_t hi = sft ? __funnelshift_r(sv[k + 1], sv[k + 2 < 4 ? k + 2 : 3], sft) : sv[k + 1];
+                        mp[c * kColStride] = (int16_t)dp4aUS(hi, t1, dp4aUS(lo, t0, 0));
+                    }
+            }
+        }
+    }
+}
+
+// the 8 words of a mid column (support rows 0..15) and the 8-tap window slid down it.  Output row r reads support
+// rows r + j0 .. r + j0 + 7 (j0 = 0 or 1).
+struct Column
+{
+    uint32_t w[8], x[7];
+    __device__ __forceinline__ void load(const int16_t *col, int j0)
+    {
+        const uint2 *q = reinterpret_cast<const uint2 *>(col);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            const uint2 t = q[i];
+            w[2 * i] = t.x;
+            w[2 * i + 1] = t.y;
+        }
+        if (j0)
+        {
+#pragma unroll
+            for (int i = 0; i < 7; ++i) w[i] = __funnelshift_r(w[i], w[i + 1], 16);
+            w[7] >>= 16;
+        }
+#pragma unroll
+        for (int i = 0; i < 7; ++i) x[i] = __funnelshift_r(w[i], w[i + 1], 16);
+    }
+    template <int R>
+    __device__ __forceinline__ int out(uint32_t t0, uint32_t t1) const
+    {
+        constexpr int k = R >> 1;
+        if (R & 1) return vFilter(x[k], x[k + 1], x[k + 2], x[k + 3 < 7 ? k + 3 : 6], t0, t1);
+        return vFilter(w[k], w[k + 1], w[k + 2], w[k + 3 < 8 ? k + 3 : 7], t0, t1);
+    }
+};
+
+// ---- V pass, half-pel round: PC (plane 2 of preds) = vertical half-pel of the integer columns, (uh+1) x uw;
+// PD (plane 3) = vertical half-pel of the half-pel columns, (uh+1) x (uw+1).  17 column jobs per unit.
+__device__ __forceinline__ void vPassHalf(WarpSmem &s, int lane)
+{
+    const uint32_t t0 = kTapWords[2][0], t1 = kTapWords[2][1];
+#pragma unroll 1
+    for (int it = 0; it < 3; ++it)
+    {
+        const int job = lane + 32 * it;
+        if (job >= kGroup * 17) break;
+        const int u = (job * 3856) >> 16, k = job - u * 17; // / 17
+        const int uw = s.unit[u].uwuh & 0xff, uh = (s.unit[u].uwuh >> 8) & 0xff;
+        const int pd = k >= 8, c = pd ? k - 8 : k;
+        if (c >= uw + pd) continue;
+        Column col;
+        col.load(s.mids[u] + pd * kPlaneHalfwords + c * kColStride, 0);
+        uint8_t *dst = s.preds[u] + (2 + pd) * kPredPlane + c;
+        // rows 0..uh: output r is the half-sample position between picture rows r-1 and r
+        dst[0 * kPredRow] = (uint8_t)col.out<0>(t0, t1);
+        dst[1 * kPredRow] = (uint8_t)col.out<1>(t0, t1);
+        dst[2 * kPredRow] = (uint8_t)col.out<2>(t0, t1);
+        dst[3 * kPredRow] = (uint8_t)col.out<3>(t0, t1);
+        dst[4 * kPredRow] = (uint8_t)col.out<4>(t0, t1);
+        if (uh > 4)
+        {
+            dst[5 * kPredRow] = (uint8_t)col.out<5>(t0, t1);
+            dst[6 * kPredRow] = (uint8_t)col.out<6>(t0, t1);
+            dst[7 * kPredRow] = (uint8_t)col.out<7>(t0, t1);
+            dst[8 * kPredRow] = (uint8_t)col.out<8>(t0, t1);
+        }
+    }
+}
+
+// ---- V pass, quarter-pel round: candidate q (grid index gi = q + (q >= 4)) = plane gi % 3 at the vertical quarter
+// offset hy + gi / 3 - 1; (unit, candidate, column) jobs; preds[u][q][r][c], 8 bytes per row.
+__device__ __forceinline__ void vPassQuarter(WarpSmem &s, int lane)
+{
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it)
+    {
+        const int job = lane + 32 * it, u = job >> 6, q = (job >> 3) & 7, c = job & 7;
+        const UnitDesc d = s.unit[u];
+        const int uw = d.uwuh & 0xff, uh = (d.uwuh >> 8) & 0xff;
+        if (c >= uw) continue;
+        const int gi = q + (q >= 4), pl = gi % 3, yq = (s.cy[d.slot] & 3) + gi / 3 - 1;
+        const uint32_t t0 = kTapWords[yq & 3][0], t1 = kTapWords[yq & 3][1];
+        Column col;
+        col.load(s.mids[u] + pl * kPlaneHalfwords + c * kColStride, (yq >> 2) + 1);
+        uint8_t *dst = s.preds[u] + q * 64 + c;
+        dst[0 * 8] = (uint8_t)col.out<0>(t0, t1);
+        dst[1 * 8] = (uint8_t)col.out<1>(t0, t1);
+        dst[2 * 8] = (uint8_t)col.out<2>(t0, t1);
+        dst[3 * 8] = (uint8_t)col.out<3>(t0, t1);
+        if (uh > 4)
+        {
+            dst[4 * 8] = (uint8_t)col.out<4>(t0, t1);
+            dst[5 * 8] = (uint8_t)col.out<5>(t0, t1);
+            dst[6 * 8] = (uint8_t)col.out<6>(t0, t1);
+            dst[7 * 8] = (uint8_t)col.out<7>(t0, t1);
+        }
+    }
+}
+
+// where candidate gi of the half-pel round lives: pointer to its sample (0,0) rounded down to a word, and the
+// byte offset (0 or 1) of its columns
+__device__ __forceinline__ const uint8_t *halfCand(const uint8_t *preds, int gi, int &off)
+{
+    const int dxi = gi % 3, dyi = gi / 3;
+    const int plane = dxi == 1 ? (dyi == 1 ? 0 : 2) : (dyi == 1 ? 1 : 3);
+    off = dxi == 2;
+    return preds + plane * kPredPlane + (dyi == 2) * kPredRow;
+}
+
+// ---- SATD of every (unit, candidate) of the group on the tensor cores -----------------------------------------
+template <bool HALF, bool T8>
+__device__ __forceinline__ void satdPass(WarpSmem &s, const HadamardA &A, int lane)
+{
+    constexpr int ncand = HALF ? 9 : 8;
+    constexpr int ncols = kGroup * ncand * (T8 ? 1 : 2);
+    const int g = lane >> 2, t = lane & 3;
+    const unsigned mask = 0x11111111u << t; // the 8 lanes that hold the same two columns
+#pragma unroll 1
+    for (int base = 0; base < ncols; base += 8)
+    {
+        const int col = min(base + g, ncols - 1);
+        const int tile = T8 ? 0 : col & 1, uc = T8 ? col : col >> 1;
+        const int u = HALF ? (uc * 7282) >> 16 : uc >> 3; // / 9
+        const int cand = uc - u * ncand;
+        const int gi = HALF ? cand : cand + (cand >= 4);
+        const int uw = s.unit[u].uwuh & 0xff;
+        int off = 0, prow = 8;
+        const uint8_t *P;
+        if (HALF)
+        {
+            P = halfCand(s.preds[u], gi, off);
+            prow = kPredRow;
+        }
+        else
+            P = s.preds[u] + cand * 64;
+        const uint8_t *S = s.src[u];
+        int s0, s1;
+        if (T8)
+        {
+            // k = 32 ks + 4 t + j (+16): tile row 4 ks + (t >> 1) (+2), tile column 4 (t & 1) + j
+            const int row = t >> 1, cx = (t & 1) * 4;
+            uint32_t b[4][2];
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+            {
+                b[ks][0] = *reinterpret_cast<const uint32_t *>(S + (ks * 4 + row) * 8 + cx);
+                b[ks][1] = *reinterpret_cast<const uint32_t *>(S + (ks * 4 + row + 2) * 8 + cx);
+                b[ks + 2][0] = loadPred4(P + (ks * 4 + row) * prow + cx, off);
+                b[ks + 2][1] = loadPred4(P + (ks * 4 + row + 2) * prow + cx, off);
+            }
+            s0 = s1 = 0;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+            {
+                int acc[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                {
+                    const int n01 = (((mt >> 1) & ks) ^ (ks >> 1)) & 1; // bit 5 of m & k, and the prediction half of [H | -H]
+                    const int n23 = n01 ^ (mt & 1);                     // bit 4 of m & k
+                    imma16832(acc, A.e[n01], A.o[n01], A.e[n23], A.o[n23], b[ks][0], b[ks][1]);
+                }
+                s0 = __sad(acc[0], 0, __sad(acc[2], 0, (unsigned)s0));
+                s1 = __sad(acc[1], 0, __sad(acc[3], 0, (unsigned)s1));
+            }
+        }
+        else
+        {
+            // two 4x4 tiles per unit: side by side in an 8x4 unit, stacked in a 4x8 unit; K = 16 + 16 is one k-step
+            const int tx = uw == 8 ? tile * 4 : 0, ty = uw == 8 ? 0 : tile * 4;
+            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(S + (ty + t) * 8 + tx);
+            const uint32_t b1 = loadPred4(P + (ty + t) * prow + tx, off);
+            int acc[4] = {0, 0, 0, 0};
+            imma16832(acc, A.e[0], A.o[0], A.e[1], A.o[1], b0, b1);
+            s0 = __sad(acc[0], 0, __sad(acc[2], 0, 0u));
+            s1 = __sad(acc[1], 0, __sad(acc[3], 0, 0u));
+        }
+        s0 = __reduce_add_sync(mask, s0);
+        s1 = __reduce_add_sync(mask, s1);
+        if (g == 0)
+        {
+            // havoc/hadamard.cpp:81-97: 4x4 (s + 1) >> 1, 8x8 (s + 2) >> 2; lane t reports columns base + 2t, + 2t + 1
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+            {
+                const int c2 = base + 2 * t + e;
+                if (c2 < ncols)
+                {
+                    const int uc2 = T8 ? c2 : c2 >> 1;
+                    const int u2 = HALF ? (uc2 * 7282) >> 16 : uc2 >> 3;
+                    const int cand2 = uc2 - u2 * ncand;
+                    const int slot = s.unit[u2].slot;
+                    const int v = ((e ? s1 : s0) + (T8 ? 2 : 1)) >> (T8 ? 2 : 1);
+                    if (s.unit[u2].uwuh >> 16) atomicAdd(&s.satd[slot][HALF ? cand2 : cand2 + (cand2 >= 4)], v);
+                }
+            }
+        }
+    }
+}
+
+// one round over every unit of the chunk's PUs of one tile mode
+template <bool HALF, bool T8>
+__device__ __forceinline__ void roundPass(WarpSmem &s, const HadamardA &A, int lane)
+{
+    // units of the participating PUs, concatenated
+    const int n0 = s.units[0], n1 = n0 + s.units[1], n2 = n1 + s.units[2], total = n2 + s.units[3];
+#pragma unroll 1
+    for (int base = 0; base < total; base += kGroup)
+    {
+        if (lane < kGroup)
+        {
+            const int id = base + lane;
+            const int uid = min(id, total - 1);
+            const int slot = (uid >= n0) + (uid >= n1) + (uid >= n2);
+            const int local = uid - (slot == 0 ? 0 : slot == 1 ? n0 : slot == 2 ? n1 : n2);
+            const int geom = s.geom[slot], uw = geom & 0xff, uh = (geom >> 8) & 0xff, unitsX = geom >> 16;
+            const int uy = local / unitsX, ux = local - uy * unitsX;
+            UnitDesc d;
+            d.ref = s.refBase[slot] + (intptr_t)(uy * uh + (s.cy[slot] >> 2)) * s.stride[slot] + ux * uw + (s.cx[slot] >> 2);
+            d.slot = slot;
+            d.uwuh = (geom & 0xffff) | (id < total) << 16;
+            s.unit[lane] = d;
+        }
+        {
+            // the source units: 4 x 8 rows of 8 bytes
+            const int u = lane >> 3, r = lane & 7;
+            const int id = min(base + u, total - 1);
+            const int slot = (id >= n0) + (id >= n1) + (id >= n2);
+            const int local = id - (slot == 0 ? 0 : slot == 1 ? n0 : slot == 2 ? n1 : n2);
+            const int geom = s.geom[slot], uw = geom & 0xff, uh = (geom >> 8) & 0xff, unitsX = geom >> 16;
+            const int uy = local / unitsX, ux = local - uy * unitsX;
+            if (r < uh)
+            {
+                const uint32_t *sp = reinterpret_cast<const uint32_t *>(s.srcBase[slot] + (intptr_t)(uy * uh + r) * s.srcStride[slot] + ux * uw);
+                uint32_t *dp = reinterpret_cast<uint32_t *>(s.src[u] + r * 8);
+                dp[0] = __ldg(sp);
+                if (uw == 8) dp[1] = __ldg(sp + 1);
+            }
+        }
+        __syncwarp();
+        hPass<HALF>(s, lane);
+        __syncwarp();
+        if (HALF)
+            vPassHalf(s, lane);
+        else
+            vPassQuarter(s, lane);
+        __syncwarp();
+        satdPass<HALF, T8>(s, A, lane);
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+    meSubpelKernel(const HvbPlane *__restrict__ planes, const hvb_me_task *__restrict__ tasks, int n, hvb_me_result *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint8_t smemSubpel[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpSmem &s = reinterpret_cast<WarpSmem *>(smemSubpel)[warp];
+    const HadamardA A(lane);
+    const int chunks = (n + kGroup - 1) / kGroup, warpsTotal = gridDim.x * kWarps;
+    for (int chunk = blockIdx.x * kWarps + warp; chunk < chunks; chunk += warpsTotal)
+    {
+        // lane k < 4 owns PU 4 chunk + k for the bookkeeping
+        const int i = chunk * kGroup + lane;
+        const bool mine = lane < kGroup && i < n;
+        int w = 8, h = 8, lambda = 0, halfPel = 0, quarterPel = 0, tiles8 = 1;
+        hvb_mv mv{0, 0}, mvd{0, 0};
+        long long bestCost = 0;
+        if (mine)
+        {
+            const hvb_me_task &t = tasks[i];
+            w = t.w;
+            h = t.h;
+            lambda = t.lambda;
+            halfPel = t.halfPel;
+            quarterPel = t.halfPel && t.quarterPel;
+            tiles8 = ((w | h) & 7) == 0;
+            mv = out[i].mv; // the integer search left its winner here
+            mvd = out[i].mvd;
+            const HvbPlane &sp = planes[t.src_pic * 3], &rp = planes[t.ref_pic * 3];
+            s.refBase[lane] = reinterpret_cast<const uint8_t *>(rp.base) + (intptr_t)t.y0 * rp.stride + t.x0;
+            s.srcBase[lane] = reinterpret_cast<const uint8_t *>(sp.base) + (intptr_t)t.y0 * sp.stride + t.x0;
+            s.stride[lane] = rp.stride;
+            s.srcStride[lane] = sp.stride;
+            const int uw = tiles8 ? 8 : ((w & 7) ? 4 : 8), uh = tiles8 ? 8 : (uw == 8 ? 4 : 8);
+            s.geom[lane] = uw | uh << 8 | (w / uw) << 16;
+        }
+        else if (lane < kGroup)
+        {
+            s.geom[lane] = 8 | 8 << 8 | 1 << 16;
+            s.refBase[lane] = s.srcBase[lane] = nullptr;
+            s.stride[lane] = s.srcStride[lane] = 0;
+        }
+        const int nUnits = mine ? (w * h) >> (tiles8 ? 6 : 5) : 0;
+#pragma unroll 1
+        for (int round = 0; round < 2; ++round)
+        {
+            const bool takesPart = round == 0 ? halfPel : quarterPel;
+            if (!__any_sync(0xffffffffu, takesPart)) break;
+            if (lane < kGroup)
+            {
+                s.cx[lane] = mv.x;
+                s.cy[lane] = mv.y;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) s.satd[lane][c] = 0;
+            }
+#pragma unroll 1
+            for (int mode = 0; mode < 2; ++mode) // 8x8-tile PUs, then 4x4-tile PUs
+            {
+                const bool now = takesPart && (mode == 0 ? tiles8 : !tiles8);
+                if (!__any_sync(0xffffffffu, now)) continue;
+                if (lane < kGroup) s.units[lane] = now ? nUnits : 0;
+                __syncwarp();
+                if (round == 0)
+                {
+                    if (mode == 0)
+                        roundPass<true, true>(s, A, lane);
+                    else
+                        roundPass<true, false>(s, A, lane);
+                }
+                else
+                {
+                    if (mode == 0)
+                        roundPass<false, true>(s, A, lane);
+                    else
+                        roundPass<false, false>(s, A, lane);
+                }
+            }
+            __syncwarp();
+            if (mine && takesPart)
+            {
+                // patternSearch with maxIterations = 1 (Search.hpp:2011-2060): costMv = rateOf(mvd) + lambda * SATD
+                const int step = round == 0 ? 2 : 1, ncand = round == 0 ? 9 : 8;
+                int best = -1;
+                for (int k = 0; k < ncand; ++k)
+                {
+                    const int gi = round == 0 ? kHalfOrder[k] : kQuarterOrder[k];
+                    const int dx = (gi % 3 - 1) * step, dy = (gi / 3 - 1) * step;
+                    const long long c = rateOfMvd((int16_t)(mvd.x + dx), (int16_t)(mvd.y + dy)) + (long long)lambda * s.satd[lane][gi];
+                    if (round == 0 && k == 0)
+                        bestCost = c; // the origin (tryOrigin)
+                    else if (c < bestCost)
+                    {
+                        best = gi;
+                        bestCost = c;
+                    }
+                }
+                if (best >= 0)
+                {
+                    const int dx = (best % 3 - 1) * step, dy = (best / 3 - 1) * step;
+                    mv.x = (int16_t)(mv.x + dx);
+                    mv.y = (int16_t)(mv.y + dy);
+                    mvd.x = (int16_t)(mvd.x + dx);
+                    mvd.y = (int16_t)(mvd.y + dy);
+                }
+            }
+            __syncwarp();
+        }
+        if (mine && halfPel)
+        {
+            out[i].mv = mv;
+            out[i].mvd = mvd;
+            out[i].subpelCost = bestCost;
+        }
+        __syncwarp();
+    }
+}
+
+} // namespace
+
+// called by hvb_me_search_batch (hvb_me.cu) after the integer search of an 8-bit batch, on the same stream
+int hvbLaunchMeSubpel(hvb_context *ctx, const hvb_me_task *dTasks, int n, hvb_me_result *dOut)
+{
+    const int chunks = (n + kGroup - 1) / kGroup;
+    int blocks = (chunks + kWarps - 1) / kWarps;
+    const int smem = kWarps * (int)sizeof(WarpSmem);
+    static_assert(sizeof(WarpSmem) % 16 == 0, "per-warp shared slices must stay 16-byte aligned");
+    cudaFuncSetAttribute(meSubpelKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int perSm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, meSubpelKernel, kWarps * 32, smem);
+    const int cap = ctx->smCount * (perSm > 0 ? perSm : 1);
+    if (blocks > cap) blocks = cap;
+    meSubpelKernel<<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dTasks, n, dOut);
+    HVB_LAUNCH_CHECK(ctx, "meSubpelKernel");
+    return HVB_OK;
+}
