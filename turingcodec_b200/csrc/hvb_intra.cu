@@ -220,6 +220,256 @@ __global__ void __launch_bounds__(kWarps * 32)
     }
 }
 
+
+// ---- 8-bit sweep: predictions to shared memory row by row, SATD on the integer tensor cores --------------------
+//
+// The sum of absolute Hadamard coefficients of a tile equals that of the transposed tile, and a horizontal mode's
+// prediction is the transpose of the vertical mode 36 - m evaluated on mirrored neighbours (left <-> top).  So
+// modes 2..17 are swept on the transposed source tile and all 33 angular modes run the same "row of the
+// vertical-mode formula" code: the row's two interpolation weights are constant and its samples slide along
+// the (projected) reference.  A lane owns one (mode, tile row); the T predicted bytes go to shared memory where
+// the (mode, tile) blocks are the B fragments of a [H | -H] x [src ; pred] IMMA, 8 modes at a time
+// (hvb_me_subpel.cu has the same construction).
+struct SweepSmem
+{
+    int16_t front[8]; // mode 2's last row computes index -1 of U for a weight-0 sample; keep it inside the struct
+    int16_t U[kNbMax + 7], F[kNbMax + 7];
+    uint8_t pred[35][64];
+    uint8_t src[2][64]; // [0] the tile, [1] the transposed source's tile
+    int sum[36];
+};
+
+struct HadamardA8
+{
+    uint32_t e[2], o[2];
+    __device__ __forceinline__ explicit HadamardA8(int lane)
+    {
+        const int g = lane >> 2, t = lane & 3;
+        const uint32_t pat = (g & 2) ? ((g & 1) ? 0x01ffff01u : 0xffff0101u) : ((g & 1) ? 0xff01ff01u : 0x01010101u);
+        const int q0 = (g >> 2) & t & 1, q1 = q0 ^ (t >> 1);
+        e[0] = q0 ? pat ^ 0xfefefefeu : pat;
+        e[1] = e[0] ^ 0xfefefefeu;
+        o[0] = q1 ? pat ^ 0xfefefefeu : pat;
+        o[1] = o[0] ^ 0xfefefefeu;
+    }
+};
+
+__device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// T samples of row yy, columns x0 .. x0+T-1, of mode `mode` in its own frame (transposed for modes 2..17)
+template <int T>
+__device__ __forceinline__ void sweepRow(const SweepSmem &s, int mode, int cIdx, int log2n, int dc, bool edge, int x0, int yy, int (&out)[T])
+{
+    const int n = 1 << log2n, c = 2 * n;
+    const int16_t *A = filterFlag(cIdx, mode, n) ? s.F : s.U;
+    if (mode >= 2)
+    {
+        const bool vertical = mode >= 18;
+        const int angle = kAngle[mode], inv = kInvAngle[mode];
+        const int t = (yy + 1) * angle, idx = t >> 5, fact = t & 31;
+        int prev;
+        {
+            const int i = x0 + idx + 1, sft = i >= 0 ? i : -((i * inv + 128) >> 8);
+            prev = vertical ? A[c + sft] : A[c - sft];
+        }
+#pragma unroll
+        for (int x = 0; x < T; ++x)
+        {
+            // when fact == 0 the reference does not read the second sample; reading it is harmless (the arrays are
+            // padded) and (32 r0 + 16) >> 5 == r0
+            const int i = x0 + x + idx + 2, sft = i >= 0 ? i : -((i * inv + 128) >> 8);
+            const int next = vertical ? A[c + sft] : A[c - sft];
+            out[x] = ((32 - fact) * prev + fact * next + 16) >> 5;
+            prev = next;
+        }
+        if (edge && (mode == 26 || mode == 10) && x0 == 0)
+        {
+            // pred_intra.cpp:20354-20358 / :20392-20396; for mode 10 in the mirrored frame the roles of top and left swap
+            const int top0 = vertical ? A[c + 1] : A[c - 1], side = vertical ? A[c - 1 - yy] : A[c + 1 + yy];
+            out[0] = hvbClip3(0, 255, top0 + ((side - A[c]) >> 1));
+        }
+    }
+    else if (mode == 1)
+    {
+#pragma unroll
+        for (int x = 0; x < T; ++x)
+        {
+            const int xx = x0 + x;
+            int v = dc;
+            if (edge)
+            {
+                if (xx == 0 && yy == 0)
+                    v = (A[c - 1] + 2 * dc + A[c + 1] + 2) >> 2;
+                else if (yy == 0)
+                    v = (A[c + 1 + xx] + 3 * dc + 2) >> 2;
+                else if (xx == 0)
+                    v = (A[c - 1 - yy] + 3 * dc + 2) >> 2;
+            }
+            out[x] = v;
+        }
+    }
+    else
+    {
+        const int left = A[c - 1 - yy], topN = A[c + 1 + n], leftN = A[c - 1 - n];
+#pragma unroll
+        for (int x = 0; x < T; ++x)
+        {
+            const int xx = x0 + x;
+            out[x] = ((n - 1 - xx) * left + (xx + 1) * topN + (n - 1 - yy) * A[c + 1 + xx] + (yy + 1) * leftN + n) >> (log2n + 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+    intraSweepKernel8(const HvbPlane *__restrict__ planes, const uint8_t *__restrict__ pool, const hvb_intra_sweep_task *__restrict__ tasks,
+                      int n, int32_t *__restrict__ out)
+{
+    __shared__ __align__(16) SweepSmem sAll[kWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SweepSmem &s = sAll[warp];
+    const HadamardA8 A(lane);
+    const int g = lane >> 2, tq = lane & 3;
+    const unsigned mask = 0x11111111u << tq;
+    const int warpsTotal = gridDim.x * kWarps;
+    for (int i = blockIdx.x * kWarps + warp; i < n; i += warpsTotal)
+    {
+        const hvb_intra_sweep_task t = tasks[i];
+        const int log2n = t.log2n, nn = 1 << log2n;
+        for (int k = lane; k <= 4 * nn; k += 32)
+        {
+            s.U[k] = (int16_t)pool[t.nb_unfiltered - 2 * nn + k];
+            if (t.nb_filtered >= 0) s.F[k] = (int16_t)pool[t.nb_filtered - 2 * nn + k];
+        }
+        if (lane < 6) // padding read (never used) by the fact == 0 rows
+            s.U[4 * nn + 1 + lane] = s.F[4 * nn + 1 + lane] = 0;
+        for (int k = lane; k < 36; k += 32) s.sum[k] = 0;
+        __syncwarp();
+        if (t.nb_filtered < 0) filterNeighbours(s.F, s.U, nn, 8, t.strong_intra_smoothing != 0, lane);
+        __syncwarp();
+        const Neighbours nbU{s.U, 2 * nn};
+        const int dc = dcValue(nbU, log2n, lane);
+        const bool edge = t.cIdx == 0 && log2n < 5;
+        int ss;
+        const uint8_t *src = hvbBlockPtr<uint8_t>(planes, t.src, ss);
+
+        if (log2n == 2)
+        {
+            // one 4x4 tile: 35 x 4 row jobs, then 5 groups of 8 modes, one IMMA each (K = 16 source + 16 prediction)
+            if (lane < 16)
+            {
+                const int r = lane >> 2, cc = lane & 3;
+                const uint8_t v = src[r * ss + cc];
+                s.src[0][r * 4 + cc] = v;
+                s.src[1][cc * 4 + r] = v;
+            }
+            for (int job = lane; job < 35 * 4; job += 32)
+            {
+                const int mode = job >> 2, r = job & 3;
+                int o[4];
+                sweepRow<4>(s, mode, t.cIdx, 2, dc, edge, 0, r, o);
+                *reinterpret_cast<uint32_t *>(&s.pred[mode][r * 4]) = o[0] | o[1] << 8 | o[2] << 16 | o[3] << 24;
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int base = 0; base < 40; base += 8)
+            {
+                const int mode = min(base + g, 34);
+                const uint8_t *S = s.src[mode >= 2 && mode < 18];
+                const uint32_t b0 = *reinterpret_cast<const uint32_t *>(S + tq * 4);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t *>(&s.pred[mode][tq * 4]);
+                int acc[4] = {0, 0, 0, 0};
+                imma16832(acc, A.e[0], A.o[0], A.e[1], A.o[1], b0, b1);
+                int s0 = __sad(acc[0], 0, __sad(acc[2], 0, 0u)), s1 = __sad(acc[1], 0, __sad(acc[3], 0, 0u));
+                s0 = __reduce_add_sync(mask, s0);
+                s1 = __reduce_add_sync(mask, s1);
+                if (g == 0)
+                {
+                    const int m0 = base + 2 * tq;
+                    if (m0 < 35) s.sum[m0] = (s0 + 1) >> 1;
+                    if (m0 + 1 < 35) s.sum[m0 + 1] = (s1 + 1) >> 1;
+                }
+            }
+        }
+        else
+        {
+            const int tilesPerRow = nn >> 3;
+#pragma unroll 1
+            for (int ty = 0; ty < tilesPerRow; ++ty)
+#pragma unroll 1
+                for (int tx = 0; tx < tilesPerRow; ++tx)
+                {
+                    {
+                        // the tile (two words per row) and the tile of the transposed source at the same tile coordinates
+                        const int r = lane >> 2, cc = (lane & 3) * 2;
+                        const uint8_t *p = src + (ty * 8 + r) * ss + tx * 8 + cc;
+                        *reinterpret_cast<uint16_t *>(&s.src[0][r * 8 + cc]) = *reinterpret_cast<const uint16_t *>(p);
+                        const uint8_t *q = src + (tx * 8 + cc) * ss + ty * 8 + r; // srcT(x = tx*8+cc, y = ty*8+r) = src(x = ty*8+r, y = tx*8+cc)
+                        s.src[1][r * 8 + cc] = q[0];
+                        s.src[1][r * 8 + cc + 1] = q[ss];
+                    }
+                    for (int job = lane; job < 35 * 8; job += 32)
+                    {
+                        const int mode = job >> 3, r = job & 7;
+                        int o[8];
+                        sweepRow<8>(s, mode, t.cIdx, log2n, dc, edge, tx * 8, ty * 8 + r, o);
+                        uint2 w;
+                        w.x = o[0] | o[1] << 8 | o[2] << 16 | o[3] << 24;
+                        w.y = o[4] | o[5] << 8 | o[6] << 16 | o[7] << 24;
+                        *reinterpret_cast<uint2 *>(&s.pred[mode][r * 8]) = w;
+                    }
+                    __syncwarp();
+#pragma unroll 1
+                    for (int base = 0; base < 40; base += 8)
+                    {
+                        const int mode = min(base + g, 34);
+                        const uint8_t *S = s.src[mode >= 2 && mode < 18], *P = s.pred[mode];
+                        const int row = tq >> 1, cx = (tq & 1) * 4;
+                        uint32_t b[4][2];
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks)
+                        {
+                            b[ks][0] = *reinterpret_cast<const uint32_t *>(S + (ks * 4 + row) * 8 + cx);
+                            b[ks][1] = *reinterpret_cast<const uint32_t *>(S + (ks * 4 + row + 2) * 8 + cx);
+                            b[ks + 2][0] = *reinterpret_cast<const uint32_t *>(P + (ks * 4 + row) * 8 + cx);
+                            b[ks + 2][1] = *reinterpret_cast<const uint32_t *>(P + (ks * 4 + row + 2) * 8 + cx);
+                        }
+                        int s0 = 0, s1 = 0;
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt)
+                        {
+                            int acc[4] = {0, 0, 0, 0};
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                            {
+                                const int n01 = (((mt >> 1) & ks) ^ (ks >> 1)) & 1, n23 = n01 ^ (mt & 1);
+                                imma16832(acc, A.e[n01], A.o[n01], A.e[n23], A.o[n23], b[ks][0], b[ks][1]);
+                            }
+                            s0 = __sad(acc[0], 0, __sad(acc[2], 0, (unsigned)s0));
+                            s1 = __sad(acc[1], 0, __sad(acc[3], 0, (unsigned)s1));
+                        }
+                        s0 = __reduce_add_sync(mask, s0);
+                        s1 = __reduce_add_sync(mask, s1);
+                        if (g == 0)
+                        {
+                            const int m0 = base + 2 * tq;
+                            if (m0 < 35) s.sum[m0] += (s0 + 2) >> 2;
+                            if (m0 + 1 < 35) s.sum[m0 + 1] += (s1 + 2) >> 2;
+                        }
+                    }
+                    __syncwarp();
+                }
+        }
+        __syncwarp();
+        for (int k = lane; k < 35; k += 32) out[i * 35 + k] = s.sum[k];
+        __syncwarp();
+    }
+}
+
 int gridWarps(hvb_context *ctx, int n)
 {
     const int blocks = (n + kWarps - 1) / kWarps;
@@ -259,8 +509,12 @@ extern "C" int hvb_intra_satd35_batch(hvb_context *ctx, const hvb_intra_sweep_ta
     const auto *dT = static_cast<const hvb_intra_sweep_task *>(st.dTasks);
     auto *dO = static_cast<int32_t *>(st.dOut);
     if (ctx->bps == 1)
-        intraSweepKernel<uint8_t><<<gridWarps(ctx, n), kWarps * 32, 0, ctx->stream>>>(
-            ctx->dPlanes, static_cast<const uint8_t *>(ctx->samplePool), dT, n, dO, ctx->bitDepth);
+    {
+        int perSm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, intraSweepKernel8, kWarps * 32, 0);
+        const int blocks = min((n + kWarps - 1) / kWarps, ctx->smCount * max(perSm, 1));
+        intraSweepKernel8<<<blocks, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, static_cast<const uint8_t *>(ctx->samplePool), dT, n, dO);
+    }
     else
         intraSweepKernel<uint16_t><<<gridWarps(ctx, n), kWarps * 32, 0, ctx->stream>>>(
             ctx->dPlanes, static_cast<const uint16_t *>(ctx->samplePool), dT, n, dO, ctx->bitDepth);
