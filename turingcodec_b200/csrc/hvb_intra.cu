@@ -261,6 +261,17 @@ __device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1,
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// The 8 lanes that share (lane & 3) hold partial sums of accumulator columns 2t (s0) and 2t+1 (s1): exchange so that
+// even g carries column 2t and odd g column 2t+1, then two more butterfly steps.  Lane (g < 2, t) ends with column 2t + g.
+__device__ __forceinline__ int columnSums(int s0, int s1, int g)
+{
+    int sum = (g & 1) ? s1 : s0;
+    sum += __shfl_xor_sync(0xffffffffu, (g & 1) ? s0 : s1, 4);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+    return sum;
+}
+
 // T samples of row yy, columns x0 .. x0+T-1, of mode `mode` in its own frame (transposed for modes 2..17)
 template <int T>
 __device__ __forceinline__ void sweepRow(const SweepSmem &s, int mode, int cIdx, int log2n, int dc, bool edge, int x0, int yy, int (&out)[T])
@@ -334,7 +345,6 @@ __global__ void __launch_bounds__(kWarps * 32)
     SweepSmem &s = sAll[warp];
     const HadamardA8 A(lane);
     const int g = lane >> 2, tq = lane & 3;
-    const unsigned mask = 0x11111111u << tq;
     const int warpsTotal = gridDim.x * kWarps;
     for (int i = blockIdx.x * kWarps + warp; i < n; i += warpsTotal)
     {
@@ -385,14 +395,8 @@ __global__ void __launch_bounds__(kWarps * 32)
                 int acc[4] = {0, 0, 0, 0};
                 imma16832(acc, A.e[0], A.o[0], A.e[1], A.o[1], b0, b1);
                 int s0 = __sad(acc[0], 0, __sad(acc[2], 0, 0u)), s1 = __sad(acc[1], 0, __sad(acc[3], 0, 0u));
-                s0 = __reduce_add_sync(mask, s0);
-                s1 = __reduce_add_sync(mask, s1);
-                if (g == 0)
-                {
-                    const int m0 = base + 2 * tq;
-                    if (m0 < 35) s.sum[m0] = (s0 + 1) >> 1;
-                    if (m0 + 1 < 35) s.sum[m0 + 1] = (s1 + 1) >> 1;
-                }
+                const int sum = columnSums(s0, s1, g);
+                if (g < 2 && base + 2 * tq + g < 35) s.sum[base + 2 * tq + g] = (sum + 1) >> 1;
             }
         }
         else
@@ -452,14 +456,8 @@ __global__ void __launch_bounds__(kWarps * 32)
                             s0 = __sad(acc[0], 0, __sad(acc[2], 0, (unsigned)s0));
                             s1 = __sad(acc[1], 0, __sad(acc[3], 0, (unsigned)s1));
                         }
-                        s0 = __reduce_add_sync(mask, s0);
-                        s1 = __reduce_add_sync(mask, s1);
-                        if (g == 0)
-                        {
-                            const int m0 = base + 2 * tq;
-                            if (m0 < 35) s.sum[m0] += (s0 + 2) >> 2;
-                            if (m0 + 1 < 35) s.sum[m0 + 1] += (s1 + 2) >> 2;
-                        }
+                        const int sum = columnSums(s0, s1, g);
+                        if (g < 2 && base + 2 * tq + g < 35) s.sum[base + 2 * tq + g] += (sum + 2) >> 2;
                     }
                     __syncwarp();
                 }

@@ -83,7 +83,7 @@ __device__ __forceinline__ int dp4aUS(uint32_t a, uint32_t b, int c)
     return d;
 }
 
-__device__ __forceinline__ int clip8(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ int clip8(int v) { return __vimin_s32_relu(v, 255); } // max(min(v, 255), 0), one VIMNMX
 
 __device__ __forceinline__ int vFilter(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t t0, uint32_t t1)
 {
@@ -324,7 +324,6 @@ __device__ __forceinline__ void satdPass(WarpSmem &s, const HadamardA &A, int la
     constexpr int ncand = HALF ? 9 : 8;
     constexpr int ncols = kGroup * ncand * (T8 ? 1 : 2);
     const int g = lane >> 2, t = lane & 3;
-    const unsigned mask = 0x11111111u << t; // the 8 lanes that hold the same two columns
 #pragma unroll 1
     for (int base = 0; base < ncols; base += 8)
     {
@@ -385,24 +384,24 @@ __device__ __forceinline__ void satdPass(WarpSmem &s, const HadamardA &A, int la
             s0 = __sad(acc[0], 0, __sad(acc[2], 0, 0u));
             s1 = __sad(acc[1], 0, __sad(acc[3], 0, 0u));
         }
-        s0 = __reduce_add_sync(mask, s0);
-        s1 = __reduce_add_sync(mask, s1);
-        if (g == 0)
+        // The 8 lanes that share t hold partial sums of columns 2t (s0) and 2t+1 (s1).  First exchange so that even
+        // g carries column 2t and odd g column 2t+1, then two more butterfly steps: 3 shuffles for both sums.
+        int sum = (g & 1) ? s1 : s0;
+        sum += __shfl_xor_sync(0xffffffffu, (g & 1) ? s0 : s1, 4);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+        if (g < 2)
         {
-            // havoc/hadamard.cpp:81-97: 4x4 (s + 1) >> 1, 8x8 (s + 2) >> 2; lane t reports columns base + 2t, + 2t + 1
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
+            // havoc/hadamard.cpp:81-97: 4x4 (s + 1) >> 1, 8x8 (s + 2) >> 2; lane (g, t) reports column base + 2t + g
+            const int c2 = base + 2 * t + g;
+            if (c2 < ncols)
             {
-                const int c2 = base + 2 * t + e;
-                if (c2 < ncols)
-                {
-                    const int uc2 = T8 ? c2 : c2 >> 1;
-                    const int u2 = HALF ? (uc2 * 7282) >> 16 : uc2 >> 3;
-                    const int cand2 = uc2 - u2 * ncand;
-                    const int slot = s.unit[u2].slot;
-                    const int v = ((e ? s1 : s0) + (T8 ? 2 : 1)) >> (T8 ? 2 : 1);
-                    if (s.unit[u2].uwuh >> 16) atomicAdd(&s.satd[slot][HALF ? cand2 : cand2 + (cand2 >= 4)], v);
-                }
+                const int uc2 = T8 ? c2 : c2 >> 1;
+                const int u2 = HALF ? (uc2 * 7282) >> 16 : uc2 >> 3;
+                const int cand2 = uc2 - u2 * ncand;
+                const int slot = s.unit[u2].slot;
+                const int v = (sum + (T8 ? 2 : 1)) >> (T8 ? 2 : 1);
+                if (s.unit[u2].uwuh >> 16) atomicAdd(&s.satd[slot][HALF ? cand2 : cand2 + (cand2 >= 4)], v);
             }
         }
     }

@@ -43,7 +43,8 @@ struct HvbRdoqMid
 
 namespace hvb_rdoq {
 
-__device__ __constant__ int32_t kEntropyBits[128] = {
+// in global memory, read through L1: the index differs from thread to thread and a constant-bank read serialises per address
+static __device__ const int32_t kEntropyBits[128] = {
     0x07b23, 0x085f9, 0x074a0, 0x08cbc, 0x06ee4, 0x09354, 0x067f4, 0x09c1b, 0x060b0, 0x0a62a, 0x05a9c, 0x0af5b, 0x0548d,
     0x0b955, 0x04f56, 0x0c2a9, 0x04a87, 0x0cbf7, 0x045d6, 0x0d5c3, 0x04144, 0x0e01b, 0x03d88, 0x0e937, 0x039e0, 0x0f2cd,
     0x03663, 0x0fc9e, 0x03347, 0x10600, 0x03050, 0x10f95, 0x02d4d, 0x11a02, 0x02ad3, 0x12333, 0x0286e, 0x12cad, 0x02604,
@@ -55,7 +56,7 @@ __device__ __constant__ int32_t kEntropyBits[128] = {
     0x00672, 0x26f23, 0x005e8, 0x27ef8, 0x005ba, 0x284b5, 0x0055e, 0x29057, 0x0050c, 0x29bab, 0x004c1, 0x2a674, 0x004a7,
     0x2aa5e, 0x0046f, 0x2b32f, 0x0041f, 0x2c0ad, 0x003e7, 0x2ca8d, 0x003ba, 0x2d323, 0x0010c, 0x3bfbb};
 
-__device__ __forceinline__ int bitsOf(int bin, uint8_t state) { return kEntropyBits[(state >> 1) ^ bin]; }
+__device__ __forceinline__ int bitsOf(int bin, uint8_t state) { return __ldg(&kEntropyBits[(state >> 1) ^ bin]); }
 
 __device__ __forceinline__ long long shflXor64(long long v, int m)
 {

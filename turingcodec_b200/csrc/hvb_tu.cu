@@ -231,11 +231,49 @@ __global__ void __launch_bounds__(kWarps * 32)
 // The split exists because RDOQ is serial per block: with a warp per block 31 lanes idled through it and the
 // ncu capture showed it at 10x the cost of everything else in the pipeline.
 
+// The serial stage gives a thread to each block, so a warp runs as long as its longest block and diverges wherever
+// the 32 walks differ.  The work of a walk grows with the position of the first non-zero level (lastSp), which the
+// front stage knows: it files every RDOQ block under a bucket of similar lastSp (two per octave), a small kernel
+// turns the bucket counts into an ordering (longest first), and the serial stage takes its blocks in that order.
+constexpr int kRdoqBuckets = 24;
+__device__ __forceinline__ int rdoqBucket(int lastSp)
+{
+    const int v = lastSp + 1, e = 31 - __clz(v);
+    return 2 * e + (e ? (v >> (e - 1)) & 1 : 0);
+}
+
+// counts[kRdoqBuckets] filled by the front stage; cursors[kRdoqBuckets] zero on entry.  Ranks are taken inside the
+// block first (shared-memory atomics), then one global atomic per bucket and block reserves the block's range.
+__global__ void __launch_bounds__(256)
+    tuOrderKernel(const HvbRdoqMid *__restrict__ mids, int n, const int *__restrict__ counts, int *__restrict__ cursors, int *__restrict__ order)
+{
+    __shared__ int sOffset[kRdoqBuckets], sLocal[kRdoqBuckets];
+    if (threadIdx.x < kRdoqBuckets) sLocal[threadIdx.x] = 0;
+    if (threadIdx.x == 0)
+    {
+        int acc = 0;
+        for (int b = kRdoqBuckets - 1; b >= 0; --b)
+        {
+            sOffset[b] = acc;
+            acc += counts[b];
+        }
+    }
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int key = t < n ? mids[t].reserved : -1;
+    const int rank = key >= 0 ? atomicAdd(&sLocal[key], 1) : 0;
+    __syncthreads();
+    if (threadIdx.x < kRdoqBuckets && sLocal[threadIdx.x])
+        sOffset[threadIdx.x] += atomicAdd(&cursors[threadIdx.x], sLocal[threadIdx.x]);
+    __syncthreads();
+    if (key >= 0) order[sOffset[key] + rank] = t;
+}
+
 template <typename Sample>
 __global__ void __launch_bounds__(kWarps * 32)
     tuFrontKernel(const HvbPlane *__restrict__ planes, int16_t *__restrict__ pool, int16_t *__restrict__ coefTmp,
                   const hvb_rdoq_ctx *__restrict__ rdoqCtx, const hvb_tu_task *__restrict__ tasks, int n, hvb_tu_result *__restrict__ out,
-                  HvbRdoqMid *__restrict__ mids, int bitDepth)
+                  HvbRdoqMid *__restrict__ mids, int *__restrict__ bucketCounts, int bitDepth)
 {
     __shared__ Matrices M;
     __shared__ __align__(16) int16_t sA[kWarps][kBlk];
@@ -295,6 +333,8 @@ __global__ void __launch_bounds__(kWarps * 32)
         }
         if (lane == 0)
         {
+            mid.reserved = mid.lastSp >= 0 ? rdoqBucket(mid.lastSp) : -1;
+            if (mid.lastSp >= 0) atomicAdd(&bucketCounts[mid.reserved], 1);
             mids[t] = mid;
             hvb_tu_result r;
             r.ssd = 0;
@@ -310,12 +350,15 @@ __global__ void __launch_bounds__(kWarps * 32)
 __global__ void __launch_bounds__(128)
     tuRdoqKernel(int16_t *__restrict__ pool, const int16_t *__restrict__ coefTmp, HvbCoefRec *__restrict__ recs,
                  const hvb_rdoq_ctx *__restrict__ rdoqCtx, const hvb_tu_task *__restrict__ tasks, int n, hvb_tu_result *__restrict__ out,
-                 const HvbRdoqMid *__restrict__ mids, int bitDepth)
+                 const HvbRdoqMid *__restrict__ mids, const int *__restrict__ bucketCounts, const int *__restrict__ order, int bitDepth)
 {
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+    // blocks that are plain-quantised, or whose levels all round to zero (cbf already 0), are not in the ordering
+    int total = 0;
+    for (int b = 0; b < kRdoqBuckets; ++b) total += bucketCounts[b];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x)
     {
+        const int t = order[idx];
         const HvbRdoqMid mid = mids[t];
-        if (mid.lastSp < 0) continue; // plain-quantised, or every level rounds to zero (cbf already 0)
         const hvb_tu_task task = tasks[t];
         const int c = hvbRdoqThread(pool + task.levels, coefTmp + task.levels, rdoqCtx + task.rdoq_ctx, mid, task.qscale, task.qshift,
                                     task.iqscale, task.log2n, task.cIdx, task.scanIdx, (task.flags & 2) != 0, (task.flags & 4) != 0, bitDepth,
@@ -433,18 +476,23 @@ struct ChainScratch
     int16_t *coefTmp;
     HvbCoefRec *recs;
     HvbRdoqMid *mids;
+    int *buckets; // [2][kRdoqBuckets]: counts, cursors
+    int *order;   // [n]
 };
 
 int chainScratch(hvb_context *ctx, size_t count, size_t n, bool needCoefTmp, ChainScratch *cs)
 {
     const size_t coefBytes = needCoefTmp ? ((count * sizeof(int16_t) + 255) & ~size_t(255)) : 0;
     const size_t recBytes = (count * sizeof(HvbCoefRec) + 255) & ~size_t(255);
-    int rc = hvbEnsureScratch(ctx, coefBytes + recBytes + n * sizeof(HvbRdoqMid));
+    const size_t midBytes = (n * sizeof(HvbRdoqMid) + 255) & ~size_t(255);
+    int rc = hvbEnsureScratch(ctx, coefBytes + recBytes + midBytes + 256 + n * sizeof(int));
     if (rc) return rc;
     char *base = static_cast<char *>(ctx->scratch);
     cs->coefTmp = reinterpret_cast<int16_t *>(base);
     cs->recs = reinterpret_cast<HvbCoefRec *>(base + coefBytes);
     cs->mids = reinterpret_cast<HvbRdoqMid *>(base + coefBytes + recBytes);
+    cs->buckets = reinterpret_cast<int *>(base + coefBytes + recBytes + midBytes);
+    cs->order = cs->buckets + 64;
     return HVB_OK;
 }
 
@@ -541,17 +589,21 @@ extern "C" int hvb_tu_chain_batch(hvb_context *ctx, const hvb_tu_task *tasks, in
     if (rc) return rc;
     const auto *dT = static_cast<const hvb_tu_task *>(st.dTasks);
     auto *dO = static_cast<hvb_tu_result *>(st.dOut);
-    const int gridW = gridWarps(ctx, n, kWarps, 4);
+    const int gridW = gridWarps(ctx, n, kWarps, 8);
     int gridT = (n + 127) / 128;
     if (gridT > ctx->smCount * 16) gridT = ctx->smCount * 16;
+    cudaMemsetAsync(cs.buckets, 0, 2 * kRdoqBuckets * sizeof(int), ctx->stream);
     if (ctx->bps == 1)
         tuFrontKernel<uint8_t><<<gridW, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, cs.coefTmp, ctx->rdoqCtx, dT, n, dO, cs.mids,
-                                                                       ctx->bitDepth);
+                                                                       cs.buckets, ctx->bitDepth);
     else
         tuFrontKernel<uint16_t><<<gridW, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, cs.coefTmp, ctx->rdoqCtx, dT, n, dO, cs.mids,
-                                                                        ctx->bitDepth);
+                                                                        cs.buckets, ctx->bitDepth);
     HVB_LAUNCH_CHECK(ctx, "tuFrontKernel");
-    tuRdoqKernel<<<gridT, 128, 0, ctx->stream>>>(ctx->coeffPool, cs.coefTmp, cs.recs, ctx->rdoqCtx, dT, n, dO, cs.mids, ctx->bitDepth);
+    tuOrderKernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(cs.mids, n, cs.buckets, cs.buckets + kRdoqBuckets, cs.order);
+    HVB_LAUNCH_CHECK(ctx, "tuOrderKernel");
+    tuRdoqKernel<<<gridT, 128, 0, ctx->stream>>>(ctx->coeffPool, cs.coefTmp, cs.recs, ctx->rdoqCtx, dT, n, dO, cs.mids, cs.buckets, cs.order,
+                                                 ctx->bitDepth);
     HVB_LAUNCH_CHECK(ctx, "tuRdoqKernel");
     if (ctx->bps == 1)
         tuBackKernel<uint8_t><<<gridW, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, dT, n, dO, ctx->bitDepth);
