@@ -74,6 +74,7 @@ extern "C" int hvb_create(int device, int bytes_per_sample, int bit_depth, hvb_c
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->dPlanes, sizeof(HvbPlane) * HVB_MAX_PICTURES * 3);
     if (e == cudaSuccess) e = cudaMemset(ctx->dPlanes, 0, sizeof(HvbPlane) * HVB_MAX_PICTURES * 3);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->workCursors, 64 * sizeof(int));
     int sms = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess)
@@ -96,6 +97,7 @@ extern "C" void hvb_destroy(hvb_context *ctx)
         for (int c = 0; c < 3; ++c)
             if (p.alloc[c]) cudaFree(p.alloc[c]);
     if (ctx->dPlanes) cudaFree(ctx->dPlanes);
+    if (ctx->workCursors) cudaFree(ctx->workCursors);
     if (ctx->hostStage) cudaFreeHost(ctx->hostStage);
     if (ctx->devStage) cudaFree(ctx->devStage);
     if (ctx->samplePool) cudaFree(ctx->samplePool);

@@ -47,6 +47,7 @@ struct hvb_context
     HvbPicture pictures[HVB_MAX_PICTURES];
     HvbPlane *dPlanes = nullptr; // [HVB_MAX_PICTURES*3] mirrored on device
     bool planesDirty = true;
+    int *workCursors = nullptr; // [64] device-side task cursors of the persistent kernels (zeroed on the stream before each use)
 
     // staging for HVB_HOST calls
     void *hostStage = nullptr;  // pinned

@@ -562,6 +562,7 @@ __global__ void __launch_bounds__(kWarps * 32)
     for (int i = blockIdx.x * kWarps + warp; i < n; i += warpsTotal)
     {
         const hvb_me_task t = tasks[i];
+        if (!kFused && t.w <= 8 && t.h <= 8) continue; // 8-bit PUs up to 8x8 are searched four per warp by hvb_me_small.cu
         Search<Sample> s(t, planes, sSrc, lane);
         s.sMid = sScratch + 32;
         long long costMvdZero[2] = {0, 0};
@@ -751,6 +752,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 } // namespace
 
 int hvbLaunchMeSubpel(hvb_context *ctx, const hvb_me_task *dTasks, int n, hvb_me_result *dOut); // hvb_me_subpel.cu
+int hvbLaunchMeSmall(hvb_context *ctx, const hvb_me_task *dTasks, int n, hvb_me_result *dOut);  // hvb_me_small.cu
 
 extern "C" int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, int n, hvb_me_result *out, hvb_mem mem)
 {
@@ -767,7 +769,10 @@ extern "C" int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, i
     auto *dO = static_cast<hvb_me_result *>(st.dOut);
     if (ctx->bps == 1)
     {
-        // integer search, then the sub-pel refinement of the whole batch (hvb_me_subpel.cu) on the same stream
+        // integer search -- PUs up to 8x8 four per warp (hvb_me_small.cu), the larger ones a warp each -- then the
+        // sub-pel refinement of the whole batch (hvb_me_subpel.cu), all on the same stream
+        rc = hvbLaunchMeSmall(ctx, dT, n, dO);
+        if (rc) return rc;
         const int smem = kWarps * (64 * 64 / 4) * 4;
         cudaFuncSetAttribute(meSearchKernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         int perSm = 1;
