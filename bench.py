@@ -5,8 +5,8 @@ One step = one pass of the hot path over one 3840x2160 8-bit frame at the refere
 settings (turingcodec_b200/workload.py): a uni-directional motion search (integer pattern search +
 1/2- and 1/4-pel refinement) for every PU of the CU quadtree, a 35-mode intra SATD sweep for every
 partition, and the TU pipeline (DCT -> RDOQ+SDH -> dequant -> IDCT+add -> SSD) for two candidates of
-every CU in luma and both chroma planes.  Six kernel launches per step (integer search, sub-pel refinement,
-intra sweep, TU front / RDOQ / back).
+every CU in luma and both chroma planes.  Eight kernel launches per step (small-PU and large-PU integer search,
+sub-pel refinement, intra sweep, TU front / order / RDOQ / back).
 
   value   frames/s with pictures, task and result arrays resident in HBM (CUDA events, max over ranks)
   e2e     frames/s through the host-facing C-ABI (hvb_* with HVB_HOST): per step the source and
@@ -447,7 +447,7 @@ def main():
     dominant = max(kern, key=kern.get)
     peak, peak_src = peaks()
     achieved = alg[dominant] / (kern[dominant] * 1e-3) / 1e9
-    kernel_names = {"me": "meSearchKernel+meSubpelKernel", "intra": "intraSweepKernel8", "tu": "tuFrontKernel+tuRdoqKernel+tuBackKernel"}
+    kernel_names = {"me": "meSearchSmallKernel+meSearchKernel+meSubpelKernel", "intra": "intraSweepKernel8", "tu": "tuFrontKernel+tuRdoqKernel+tuBackKernel"}
     roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic_from_profile(kernel_names[dominant]), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dominant], "ms_per_launch": kern[dominant],
