@@ -194,6 +194,125 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 
 namespace {
 
+// ---- 8-bit SATD of 8x8-tiled blocks on the integer tensor cores ---------------------------------------------------
+// sum |H d H^T| over a tile = sum |(H (x) H) vec(a) - (H (x) H) vec(b)|: eight tiles at a time are one
+// [H | -H] x [a ; b] product (IMMA m16n8k32, s8 x u8 -> s32, M = 64, K = 64 + 64), the B fragments loaded straight
+// from the two pictures (a lane reads 4 bytes of a tile row; the eight tiles of a group are neighbours in the block,
+// so a load instruction covers whole 32-byte sectors), the A fragments four per-lane constants (-1)^popc(m & k).
+// See hvb_me_subpel.cu for the derivation; ~7 instructions per tile instead of ~16 for the register butterfly.
+// Here the K index is laid out so that a lane's two B registers of a k-step are one whole tile row: position bits
+// [row | col] = [ks, t1, t0 | reg, j1, j0], i.e. lane (g, t) loads rows t and t + 4 of tile g with one 64-bit load each.
+// A register (m-tile mt, k-step ks, reg r) is then x[mt & 1][r], negated when ((mt >> 1) & ks) ^ (ks >> 1) is odd.
+struct HadamardFrag
+{
+    uint32_t x[2][4];
+    __device__ __forceinline__ explicit HadamardFrag(int lane)
+    {
+        const int g = lane >> 2, t = lane & 3, t0 = t & 1, t1 = t >> 1, g2 = g >> 2;
+        const uint32_t pat = (g & 2) ? ((g & 1) ? 0x01ffff01u : 0xffff0101u) : ((g & 1) ? 0xff01ff01u : 0x01010101u);
+#pragma unroll
+        for (int m0 = 0; m0 < 2; ++m0)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) x[m0][r] = (((r & 1) & t0) ^ ((r >> 1) & g2) ^ (m0 & t1)) ? pat ^ 0xfefefefeu : pat;
+    }
+};
+
+__device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// 8 bytes of a tile row: one 64-bit load when the row is 8-byte aligned, else three aligned words and two funnel shifts
+__device__ __forceinline__ uint2 loadRow8(const uint8_t *p)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    if ((a & 7) == 0) return __ldg(reinterpret_cast<const uint2 *>(p));
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+    const unsigned sh = (unsigned)(a & 3) * 8;
+    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1);
+    if (sh == 0) return make_uint2(w0, w1);
+    const uint32_t w2 = __ldg(q + 2);
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+
+struct TileRows
+{
+    uint2 r[4]; // a rows t, t+4; b rows t, t+4
+};
+
+__device__ __forceinline__ TileRows loadGroup(const uint8_t *a, int sa, const uint8_t *b, int sb, int tilesX, int tiles, int base, int g, int t)
+{
+    const int tile = min(base + g, tiles - 1);
+    const int ty = tile / tilesX, tx = tile - ty * tilesX;
+    const uint8_t *S = a + (intptr_t)(ty * 8 + t) * sa + tx * 8, *P = b + (intptr_t)(ty * 8 + t) * sb + tx * 8;
+    TileRows f;
+    f.r[0] = loadRow8(S);
+    f.r[1] = loadRow8(S + 4 * sa);
+    f.r[2] = loadRow8(P);
+    f.r[3] = loadRow8(P + 4 * sb);
+    return f;
+}
+
+// SATD of a w x h block pair (w, h multiples of 8) in 8x8 tiles; the result is valid on every lane
+__device__ __forceinline__ int satdMmaWarp(const uint8_t *a, int sa, const uint8_t *b, int sb, int w, int h, const HadamardFrag &A, int lane)
+{
+    const int tilesX = w >> 3, tiles = tilesX * (h >> 3);
+    const int g = lane >> 2, t = lane & 3;
+    int total = 0;
+    TileRows f = loadGroup(a, sa, b, sb, tilesX, tiles, 0, g, t);
+    for (int base = 0; base < tiles; base += 8)
+    {
+        // the next group's rows are in flight while this group's products run.  (Requesting four groups ahead was
+        // measured slower, 39 % vs 52 % of HBM peak on 64x64 blocks: the registers cost more occupancy than the depth buys.)
+        TileRows next = f;
+        if (base + 8 < tiles) next = loadGroup(a, sa, b, sb, tilesX, tiles, base + 8, g, t);
+        int s0 = 0, s1 = 0;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+        {
+            int acc[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+            {
+                const uint32_t neg = ((((mt >> 1) & ks) ^ (ks >> 1)) & 1) ? 0xfefefefeu : 0u;
+                imma16832(acc, A.x[mt & 1][0] ^ neg, A.x[mt & 1][1] ^ neg, A.x[mt & 1][2] ^ neg, A.x[mt & 1][3] ^ neg, f.r[ks].x, f.r[ks].y);
+            }
+            s0 = __sad(acc[0], 0, __sad(acc[2], 0, (unsigned)s0));
+            s1 = __sad(acc[1], 0, __sad(acc[3], 0, (unsigned)s1));
+        }
+        // column 2t + (g & 1) of the group, summed over the 8 lanes that share t
+        int sum = (g & 1) ? s1 : s0;
+        sum += __shfl_xor_sync(0xffffffffu, (g & 1) ? s0 : s1, 4);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+        if (g < 2 && base + 2 * t + g < tiles) total += (sum + 2) >> 2; // havoc/hadamard.cpp:319-323
+        f = next;
+    }
+    return hvbWarpSum(total);
+}
+
+// 8-bit blocks whose sides are multiples of 8 (the other blocks of the batch belong to satdKernel)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+    satdMmaKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int warpsTotal = gridDim.x * kWarpsPerBlock;
+    const HadamardFrag A(lane);
+    for (int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n; t += warpsTotal)
+    {
+        const hvb_metric_task task = tasks[t];
+        if ((task.w | task.h) & 7) continue;
+        int sa, sb;
+        const uint8_t *a = hvbBlockPtr<uint8_t>(planes, task.a, sa);
+        const uint8_t *b = hvbBlockPtr<uint8_t>(planes, task.b, sb);
+        const int acc = satdMmaWarp(a, sa, b, sb, task.w, task.h, A, lane);
+        if (lane == 0) out[t] = acc;
+    }
+}
+
+// one register-resident Hadamard tile per lane: 16-bit samples, and the 4x4 / 2x2 tiled blocks of 8-bit batches
 template <typename Sample>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     satdKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out)
@@ -203,12 +322,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     for (int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n; t += warpsTotal)
     {
         const hvb_metric_task task = tasks[t];
+        if (sizeof(Sample) == 1 && ((task.w | task.h) & 7) == 0) continue; // satdMmaKernel
         int sa, sb;
         const Sample *a = hvbBlockPtr<Sample>(planes, task.a, sa);
         const Sample *b = hvbBlockPtr<Sample>(planes, task.b, sb);
-        // one register-resident Hadamard tile per lane.  (A row-per-lane variant with the vertical butterfly in
-        // shuffles was measured at 0.93 vs 1.48 TB/s on 32x32 blocks and dropped: 27 shuffles per tile row cost more
-        // than the idle lanes; at ~700 instructions per 128 bytes the kernel sits on the issue roofline near 50% of HBM.)
         int acc = hvbMeasureSatdLanes<Sample, Sample>(a, sa, b, sb, task.w, task.h, lane, 32, sizeof(Sample) == 2 ? 2 : 0);
         acc = hvbWarpSum(acc);
         if (lane == 0) out[t] = acc;
@@ -284,6 +401,15 @@ extern "C" int hvb_satd_batch(hvb_context *ctx, const hvb_metric_task *tasks, in
     HvbStaged st;
     int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(int32_t) * n, mem, &st);
     if (rc) return rc;
+    if (ctx->bps == 1)
+    {
+        int perSm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, satdMmaKernel, kWarpsPerBlock * 32, 0);
+        const int blocks = min((n + kWarpsPerBlock - 1) / kWarpsPerBlock, ctx->smCount * max(perSm, 1));
+        satdMmaKernel<<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->dPlanes, static_cast<const hvb_metric_task *>(st.dTasks), n,
+                                                                      static_cast<int32_t *>(st.dOut));
+        HVB_LAUNCH_CHECK(ctx, "satdMmaKernel");
+    }
     HVB_DISPATCH_SAMPLE(ctx, satdKernel, gridFor<hvb_metric_task>(ctx, n), ctx->dPlanes,
                         static_cast<const hvb_metric_task *>(st.dTasks), n, static_cast<int32_t *>(st.dOut));
     HVB_LAUNCH_CHECK(ctx, "satdKernel");
