@@ -39,3 +39,26 @@ def test_frame_pass_equals_oracle():
     assert 0.05 < o_tu["cbf"].mean() < 0.95
     assert 0.05 < (o_me["flags"] & 1).mean() < 0.999
     gpu.ctx.close()
+
+
+def test_pipelined_frame_pass_equals_blocking():
+    """hvb_set_pipelined: the same host-facing pass with copies and kernels overlapped (three steps in flight through the
+    ring of staging slots) delivers exactly what the blocking calls deliver."""
+    import bench
+    args = SimpleNamespace(width=640, height=384)
+    gpu = bench.GpuArm(args, 0)
+    gpu.ctx.set_stream(None)
+    gpu.step_e2e()
+    want = {k: getattr(gpu, k).copy() for k in ("h_me", "h_intra", "h_tu")}
+    levels = gpu.ctx.coeff_download(gpu.fp.coeff_count)
+    for k in ("h_me", "h_intra", "h_tu"):
+        getattr(gpu, k).view(np.uint8)[...] = 0xA5
+    gpu.ctx.set_pipelined(True)
+    for _ in range(3):
+        gpu.step_e2e()
+    gpu.ctx.sync()
+    for k in ("h_me", "h_intra", "h_tu"):
+        assert np.array_equal(getattr(gpu, k).view(np.uint8), want[k].view(np.uint8)), k
+    gpu.ctx.set_pipelined(False)
+    assert np.array_equal(gpu.ctx.coeff_download(gpu.fp.coeff_count), levels)
+    gpu.ctx.close()

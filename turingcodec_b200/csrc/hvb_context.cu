@@ -98,6 +98,15 @@ extern "C" void hvb_destroy(hvb_context *ctx)
             if (p.alloc[c]) cudaFree(p.alloc[c]);
     if (ctx->dPlanes) cudaFree(ctx->dPlanes);
     if (ctx->workCursors) cudaFree(ctx->workCursors);
+    for (auto &slot : ctx->slots)
+    {
+        if (slot.dev) cudaFree(slot.dev);
+        if (slot.done) cudaEventDestroy(slot.done);
+    }
+    if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
+    if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
+    if (ctx->evIn) cudaEventDestroy(ctx->evIn);
+    if (ctx->evCompute) cudaEventDestroy(ctx->evCompute);
     if (ctx->hostStage) cudaFreeHost(ctx->hostStage);
     if (ctx->devStage) cudaFree(ctx->devStage);
     if (ctx->samplePool) cudaFree(ctx->samplePool);
@@ -120,7 +129,49 @@ extern "C" int hvb_set_stream(hvb_context *ctx, void *cuda_stream)
 extern "C" int hvb_sync(hvb_context *ctx)
 {
     if (!ctx) return HVB_ERR_INVALID;
-    return hvbCuda(ctx, cudaStreamSynchronize(ctx->stream), "hvb_sync");
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && ctx->copyIn) e = cudaStreamSynchronize(ctx->copyIn);
+    if (e == cudaSuccess && ctx->copyOut) e = cudaStreamSynchronize(ctx->copyOut);
+    for (auto &slot : ctx->slots) slot.busy = false;
+    return hvbCuda(ctx, e, "hvb_sync");
+}
+
+extern "C" int hvb_set_pipelined(hvb_context *ctx, int on)
+{
+    if (!ctx) return HVB_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    int rc = hvb_sync(ctx);
+    if (rc) return rc;
+    if (on && !ctx->copyIn)
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evIn, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evCompute, cudaEventDisableTiming);
+        for (auto &slot : ctx->slots)
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming);
+        if (e != cudaSuccess) return hvbCuda(ctx, e, "hvb_set_pipelined");
+    }
+    ctx->pipelined = on != 0;
+    return HVB_OK;
+}
+
+int hvbUpload(hvb_context *ctx, void *dev, size_t devPitch, const void *host, size_t hostPitch, size_t widthBytes, size_t rows,
+              const char *what)
+{
+    cudaSetDevice(ctx->device);
+    if (ctx->pipelined && hvbIsPinned(host))
+    {
+        cudaError_t e = cudaEventRecord(ctx->evCompute, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyIn, ctx->evCompute, 0);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(dev, devPitch, host, hostPitch, widthBytes, rows, cudaMemcpyHostToDevice, ctx->copyIn);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->evIn, ctx->copyIn);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->evIn, 0);
+        return hvbCuda(ctx, e, what);
+    }
+    cudaError_t e = cudaMemcpy2DAsync(dev, devPitch, host, hostPitch, widthBytes, rows, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // the host buffer may be pageable
+    return hvbCuda(ctx, e, what);
 }
 
 extern "C" int64_t hvb_launch_count(hvb_context *ctx) { return ctx ? ctx->launches : 0; }
@@ -221,15 +272,13 @@ static int planeCopy(hvb_context *ctx, int pic, int cIdx, void *host, intptr_t s
     cudaSetDevice(ctx->device);
     char *dev = static_cast<char *>(pl.base) + (size_t)y0 * pl.stride * ctx->bps;
     char *h = static_cast<char *>(host) + (size_t)y0 * stride * ctx->bps;
-    cudaError_t e;
     if (upload)
-        e = cudaMemcpy2DAsync(dev, (size_t)pl.stride * ctx->bps, h, (size_t)stride * ctx->bps,
-                              (size_t)pl.width * ctx->bps, rows, cudaMemcpyHostToDevice, ctx->stream);
-    else
-        e = cudaMemcpy2DAsync(h, (size_t)stride * ctx->bps, dev, (size_t)pl.stride * ctx->bps,
-                              (size_t)pl.width * ctx->bps, rows, cudaMemcpyDeviceToHost, ctx->stream);
+        return hvbUpload(ctx, dev, (size_t)pl.stride * ctx->bps, h, (size_t)stride * ctx->bps, (size_t)pl.width * ctx->bps, rows,
+                         "hvb_picture_upload");
+    cudaError_t e = cudaMemcpy2DAsync(h, (size_t)stride * ctx->bps, dev, (size_t)pl.stride * ctx->bps, (size_t)pl.width * ctx->bps, rows,
+                                      cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // host buffer may be pageable
-    return hvbCuda(ctx, e, upload ? "hvb_picture_upload" : "hvb_picture_download");
+    return hvbCuda(ctx, e, "hvb_picture_download");
 }
 
 extern "C" int hvb_picture_upload(hvb_context *ctx, int pic, int cIdx, const void *host, intptr_t stride, int y0, int rows)
@@ -360,10 +409,9 @@ extern "C" int hvb_pool_upload(hvb_context *ctx, const void *samples, size_t cou
     HVB_CHECK_ARGS(ctx, samples || !count);
     int rc = hvbEnsureSamplePool(ctx, offset + count + 64);
     if (rc) return rc;
-    cudaError_t e = cudaMemcpyAsync(static_cast<char *>(ctx->samplePool) + offset * ctx->bps, samples, count * ctx->bps,
-                                    cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    return hvbCuda(ctx, e, "hvb_pool_upload");
+    if (!count) return HVB_OK;
+    return hvbUpload(ctx, static_cast<char *>(ctx->samplePool) + offset * ctx->bps, count * ctx->bps, samples, count * ctx->bps,
+                     count * ctx->bps, 1, "hvb_pool_upload");
 }
 
 extern "C" int hvb_coeff_upload(hvb_context *ctx, const int16_t *data, size_t count, size_t offset)
@@ -396,7 +444,7 @@ extern "C" int hvb_rdoq_contexts_upload(hvb_context *ctx, const hvb_rdoq_ctx *sn
     return hvbCuda(ctx, e, "hvb_rdoq_contexts_upload");
 }
 
-static bool isPinned(const void *p)
+bool hvbIsPinned(const void *p)
 {
     cudaPointerAttributes attr;
     if (!p || cudaPointerGetAttributes(&attr, p) != cudaSuccess)
@@ -420,6 +468,35 @@ int hvbStageIn(hvb_context *ctx, const void *tasks, size_t inBytes, void *out, s
     cudaSetDevice(ctx->device);
     const size_t inPad = (inBytes + 255) & ~size_t(255);
     const size_t total = inPad + ((outBytes + 255) & ~size_t(255));
+    if (ctx->pipelined && hvbIsPinned(tasks) && (!outBytes || hvbIsPinned(out)))
+    {
+        // a slot of the ring: task copy on the copy-in stream, kernels wait for it; hvbStageOut sends the results back
+        // on the copy-out stream and the call returns without waiting
+        const int id = ctx->nextSlot;
+        ctx->nextSlot = (ctx->nextSlot + 1) % 4;
+        hvb_context::Slot &slot = ctx->slots[id];
+        cudaError_t e = cudaSuccess;
+        if (slot.busy) e = cudaEventSynchronize(slot.done);
+        slot.busy = false;
+        if (e == cudaSuccess && slot.bytes < total)
+        {
+            if (slot.dev) e = cudaFree(slot.dev);
+            slot.dev = nullptr;
+            slot.bytes = 0;
+            size_t cap = 1 << 20;
+            while (cap < total) cap *= 2;
+            if (e == cudaSuccess) e = cudaMalloc(&slot.dev, cap);
+            if (e == cudaSuccess) slot.bytes = cap;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(slot.dev, tasks, inBytes, cudaMemcpyHostToDevice, ctx->copyIn);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->evIn, ctx->copyIn);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->evIn, 0);
+        if (e != cudaSuccess) return hvbCuda(ctx, e, "stage in (pipelined)");
+        st->dTasks = slot.dev;
+        st->dOut = static_cast<char *>(slot.dev) + inPad;
+        st->slot = id;
+        return HVB_OK;
+    }
     if (ctx->hostStageBytes < total)
     {
         cudaStreamSynchronize(ctx->stream);
@@ -437,7 +514,7 @@ int hvbStageIn(hvb_context *ctx, const void *tasks, size_t inBytes, void *out, s
     // Page-locked caller memory (cudaHostAlloc / cudaHostRegister, e.g. an encoder's task arena) is copied from
     // directly; pageable memory goes through the context's pinned staging buffer first.
     const void *hostSrc = tasks;
-    if (!isPinned(tasks))
+    if (!hvbIsPinned(tasks))
     {
         memcpy(ctx->hostStage, tasks, inBytes);
         hostSrc = ctx->hostStage;
@@ -454,7 +531,17 @@ int hvbStageOut(hvb_context *ctx, void *out, size_t outBytes, hvb_mem mem, const
 {
     if (mem == HVB_DEVICE) return HVB_OK;
     cudaError_t e = cudaSuccess;
-    const bool direct = outBytes && isPinned(out);
+    if (st.slot >= 0)
+    {
+        hvb_context::Slot &slot = ctx->slots[st.slot];
+        e = cudaEventRecord(ctx->evCompute, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyOut, ctx->evCompute, 0);
+        if (e == cudaSuccess && outBytes) e = cudaMemcpyAsync(out, st.dOut, outBytes, cudaMemcpyDeviceToHost, ctx->copyOut);
+        if (e == cudaSuccess) e = cudaEventRecord(slot.done, ctx->copyOut);
+        slot.busy = true;
+        return hvbCuda(ctx, e, "stage out (pipelined)");
+    }
+    const bool direct = outBytes && hvbIsPinned(out);
     if (outBytes) e = cudaMemcpyAsync(direct ? out : st.hOutPinned, st.dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return hvbCuda(ctx, e, "stage out");

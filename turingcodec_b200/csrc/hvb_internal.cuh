@@ -49,6 +49,19 @@ struct hvb_context
     bool planesDirty = true;
     int *workCursors = nullptr; // [64] device-side task cursors of the persistent kernels (zeroed on the stream before each use)
 
+    // pipelined host mode (hvb_set_pipelined): copies on their own streams, a ring of staging slots
+    bool pipelined = false;
+    cudaStream_t copyIn = nullptr, copyOut = nullptr;
+    cudaEvent_t evIn = nullptr, evCompute = nullptr; // stream-to-stream dependencies (re-recorded per use)
+    struct Slot
+    {
+        void *dev = nullptr;
+        size_t bytes = 0;
+        cudaEvent_t done = nullptr; // the call that used the slot has delivered its results
+        bool busy = false;
+    } slots[4];
+    int nextSlot = 0;
+
     // staging for HVB_HOST calls
     void *hostStage = nullptr;  // pinned
     size_t hostStageBytes = 0;
@@ -73,6 +86,12 @@ int hvbSyncPlanes(hvb_context *ctx);
 int hvbEnsureScratch(hvb_context *ctx, size_t bytes);
 int hvbEnsureCoeffPool(hvb_context *ctx, size_t count);
 int hvbEnsureSamplePool(hvb_context *ctx, size_t count);
+// Enqueue a host->device copy of caller memory.  Pipelined mode + page-locked source: on the copy-in stream, behind
+// every kernel enqueued so far (they may read the destination), the compute stream then waits for it; no host wait.
+// Otherwise on the compute stream, followed by a host wait (the source may be pageable).
+int hvbUpload(hvb_context *ctx, void *dev, size_t devPitch, const void *host, size_t hostPitch, size_t widthBytes, size_t rows,
+              const char *what);
+bool hvbIsPinned(const void *p);
 
 // Stage `inBytes` of tasks to the device when mem == HVB_HOST and reserve `outBytes` of device
 // result space behind them.  Returns device pointers for both.
@@ -81,6 +100,7 @@ struct HvbStaged
     const void *dTasks = nullptr;
     void *dOut = nullptr;
     void *hOutPinned = nullptr;
+    int slot = -1; // >= 0: pipelined call, results are delivered asynchronously
 };
 int hvbStageIn(hvb_context *ctx, const void *tasks, size_t inBytes, void *out, size_t outBytes,
                hvb_mem mem, HvbStaged *st);

@@ -104,6 +104,7 @@ def load_library() -> C.CDLL:
     lib.hvb_last_error.restype = C.c_char_p
     lib.hvb_set_stream.argtypes = [vp, vp]
     lib.hvb_sync.argtypes = [vp]
+    lib.hvb_set_pipelined.argtypes = [vp, C.c_int]
     lib.hvb_launch_count.argtypes = [vp]
     lib.hvb_launch_count.restype = i64
     lib.hvb_device_ok.argtypes = [i32]
@@ -182,6 +183,10 @@ class Context:
 
     def sync(self):
         self._check(self.lib.hvb_sync(self.h), "hvb_sync")
+
+    def set_pipelined(self, on: bool):
+        """HOST calls on page-locked arrays only enqueue (copies overlap the kernels); results are valid after sync()."""
+        self._check(self.lib.hvb_set_pipelined(self.h, int(bool(on))), "hvb_set_pipelined")
 
     @property
     def launch_count(self) -> int:
