@@ -28,12 +28,14 @@ __device__ __constant__ int8_t kMag[33] = {64, 90, 90, 90, 89, 88, 87, 85, 83, 8
                                            61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9,  4,  0};
 __device__ __constant__ int8_t kDst[4][4] = {{29, 55, 74, 84}, {74, 74, 0, -74}, {84, -29, -74, 55}, {55, -84, 74, -29}};
 
-struct Matrices
+struct alignas(16) Matrices
 {
     int8_t m[32][32];  // m[k][i]
     int8_t mt[32][32]; // mt[i][k] = m[k][i]
     int8_t dst[4][4];  // dst[k][i]
     int8_t dstT[4][4];
+    int8_t m16[16][16];  // the 16-point matrix (rows 0, 2, 4, .. of m, first 16 columns) and its transpose, compact:
+    int8_t m16t[16][16]; // A-fragment rows of the tensor-core passes must be contiguous
 };
 
 __device__ void initMatrices(Matrices &M)
@@ -52,6 +54,11 @@ __device__ void initMatrices(Matrices &M)
         }
         M.m[k][i] = (int8_t)v;
         M.mt[i][k] = (int8_t)v;
+        if (!(k & 1) && i < 16)
+        {
+            M.m16[k >> 1][i] = (int8_t)v;
+            M.m16t[i][k >> 1] = (int8_t)v;
+        }
     }
     if (threadIdx.x < 16)
     {
@@ -91,6 +98,118 @@ __device__ __forceinline__ void fwdPass(const Matrices &M, int16_t *out, const i
     }
 }
 
+// ---- 16- and 32-point passes on the integer tensor cores ----------------------------------------------------------
+// out[k][j] = f((sum_i A[k][i] * in[j][i] + add) >> shift), all three N x N row-major; f wraps to int16 (forward
+// transform, transform.cpp:3071-3084) or clips (inverse).  A is a transform matrix (int8); the 16-bit operand is split
+// into a low (unsigned) and a high (signed) byte plane on the fly, in = 256 hi + lo, so a pass is two IMMA m16n8k32
+// products per 16x8 output tile -- s8 x u8 and s8 x s8 -- recombined in the epilogue (exact: integer sums).
+//   forward  pass p:  A = M,   in = previous result              (fwdPass semantics: out[k][j] = sum_i M[k][i] in[j][i])
+//   inverse  pass 1:  A = M^T, in = dequantised levels TRANSPOSED -> out = reference's first-pass result transposed
+//   inverse  pass 2:  A = M^T, in = that, TRANSPOSE_OUT          -> the residual in natural layout
+__device__ __forceinline__ void immaS8U8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void immaS8S8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int N, bool CLIP, bool TRANSPOSE_OUT>
+__device__ __forceinline__ void mmaPass(const int8_t *A, int16_t *out, const int16_t *in, int shift, int lane)
+{
+    const int g = lane >> 2, t = lane & 3;
+    const int add = 1 << (shift - 1);
+    // A fragments: rows mt*16 + g (+8), columns 4t.. (+16)
+    uint32_t a[N / 16][4];
+#pragma unroll
+    for (int mt = 0; mt < N / 16; ++mt)
+    {
+        const int8_t *r0 = A + (mt * 16 + g) * N + 4 * t;
+        a[mt][0] = *reinterpret_cast<const uint32_t *>(r0);
+        a[mt][1] = *reinterpret_cast<const uint32_t *>(r0 + 8 * N);
+        a[mt][2] = N == 32 ? *reinterpret_cast<const uint32_t *>(r0 + 16) : 0u;
+        a[mt][3] = N == 32 ? *reinterpret_cast<const uint32_t *>(r0 + 8 * N + 16) : 0u;
+    }
+#pragma unroll
+    for (int nt = 0; nt < N / 8; ++nt)
+    {
+        // B fragments of column j = nt*8 + g: in[j][4t .. 4t+3] (and [16 + 4t ..]) as byte planes
+        const int16_t *row = in + (nt * 8 + g) * N + 4 * t;
+        const uint2 w0 = *reinterpret_cast<const uint2 *>(row);
+        const uint32_t lo0 = __byte_perm(w0.x, w0.y, 0x6420), hi0 = __byte_perm(w0.x, w0.y, 0x7531);
+        uint32_t lo1 = 0, hi1 = 0;
+        if (N == 32)
+        {
+            const uint2 w1 = *reinterpret_cast<const uint2 *>(row + 16);
+            lo1 = __byte_perm(w1.x, w1.y, 0x6420);
+            hi1 = __byte_perm(w1.x, w1.y, 0x7531);
+        }
+#pragma unroll
+        for (int mt = 0; mt < N / 16; ++mt)
+        {
+            int cl[4] = {0, 0, 0, 0}, ch[4] = {0, 0, 0, 0};
+            immaS8U8(cl, a[mt][0], a[mt][1], a[mt][2], a[mt][3], lo0, lo1);
+            immaS8S8(ch, a[mt][0], a[mt][1], a[mt][2], a[mt][3], hi0, hi1);
+            int v[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+            {
+                const int x = (cl[r] + (ch[r] << 8) + add) >> shift;
+                v[r] = CLIP ? hvbClip3(-32768, 32767, x) : (int)(int16_t)x;
+            }
+            const int k = mt * 16 + g, j = nt * 8 + 2 * t;
+            if (TRANSPOSE_OUT)
+            {
+                out[j * N + k] = (int16_t)v[0];
+                out[(j + 1) * N + k] = (int16_t)v[1];
+                out[j * N + k + 8] = (int16_t)v[2];
+                out[(j + 1) * N + k + 8] = (int16_t)v[3];
+            }
+            else
+            {
+                *reinterpret_cast<uint32_t *>(out + k * N + j) = (uint32_t)(v[0] & 0xffff) | ((uint32_t)v[1] << 16);
+                *reinterpret_cast<uint32_t *>(out + (k + 8) * N + j) = (uint32_t)(v[2] & 0xffff) | ((uint32_t)v[3] << 16);
+            }
+        }
+    }
+}
+
+// forward transform of the block in sA (through sB) -- tensor cores for the 16- and 32-point DCT, matrix products in
+// shared memory otherwise
+__device__ __forceinline__ void forwardTransform(const Matrices &M, int16_t *sA, int16_t *sB, int log2n, bool dst, int bitDepth, int lane)
+{
+    const int nn = 1 << log2n, shift1 = log2n - 1 + bitDepth - 8, shift2 = log2n + 6;
+    if (log2n == 5)
+    {
+        mmaPass<32, false, false>(&M.m[0][0], sB, sA, shift1, lane);
+        __syncwarp();
+        mmaPass<32, false, false>(&M.m[0][0], sA, sB, shift2, lane);
+    }
+    else if (log2n == 4)
+    {
+        mmaPass<16, false, false>(&M.m16[0][0], sB, sA, shift1, lane);
+        __syncwarp();
+        mmaPass<16, false, false>(&M.m16[0][0], sA, sB, shift2, lane);
+    }
+    else
+    {
+        fwdPass(M, sB, sA, nn, log2n, dst, shift1, lane);
+        __syncwarp();
+        fwdPass(M, sA, sB, nn, log2n, dst, shift2, lane);
+    }
+}
+
+// does inverseTransform want its input transposed (in[j][i] = coefficient (row i, column j))?
+__device__ __forceinline__ bool inverseWantsTransposed(int log2n) { return log2n >= 4; }
+
+// inverse transform of the coefficients in sA (through sB); the residual ends in sA in natural layout
+__device__ __forceinline__ void inverseTransform(const Matrices &M, int16_t *sA, int16_t *sB, int log2n, bool dst, int bitDepth, int lane);
+
 // inverse pass: out[j*n + k] = clip16((sum_i M[i][k] * in[i*n + j] + add) >> shift)
 __device__ __forceinline__ void invPass(const Matrices &M, int16_t *out, const int16_t *in, int log2n, bool dst, int shift, int lane)
 {
@@ -106,6 +225,28 @@ __device__ __forceinline__ void invPass(const Matrices &M, int16_t *out, const i
             acc += c * (int)in[i * n + j];
         }
         out[j * n + k] = (int16_t)hvbClip3(-32768, 32767, acc >> shift);
+    }
+}
+
+__device__ __forceinline__ void inverseTransform(const Matrices &M, int16_t *sA, int16_t *sB, int log2n, bool dst, int bitDepth, int lane)
+{
+    if (log2n == 5)
+    {
+        mmaPass<32, true, false>(&M.mt[0][0], sB, sA, 7, lane);
+        __syncwarp();
+        mmaPass<32, true, true>(&M.mt[0][0], sA, sB, 20 - bitDepth, lane);
+    }
+    else if (log2n == 4)
+    {
+        mmaPass<16, true, false>(&M.m16t[0][0], sB, sA, 7, lane);
+        __syncwarp();
+        mmaPass<16, true, true>(&M.m16t[0][0], sA, sB, 20 - bitDepth, lane);
+    }
+    else
+    {
+        invPass(M, sB, sA, log2n, dst, 7, lane);
+        __syncwarp();
+        invPass(M, sA, sB, log2n, dst, 20 - bitDepth, lane);
     }
 }
 
@@ -141,17 +282,14 @@ __global__ void __launch_bounds__(kWarps * 32)
         {
             for (int i = lane; i < count; i += 32) sA[warp][i] = pool[task.src + (i >> log2n) * task.src_stride + (i & (nn - 1))];
             __syncwarp();
-            fwdPass(M, sB[warp], sA[warp], nn, log2n, dst, log2n - 1 + bitDepth - 8, lane);
-            __syncwarp();
-            fwdPass(M, sA[warp], sB[warp], nn, log2n, dst, log2n + 6, lane);
+            forwardTransform(M, sA[warp], sB[warp], log2n, dst, bitDepth, lane);
         }
         else
         {
-            for (int i = lane; i < count; i += 32) sA[warp][i] = pool[task.src + i];
+            const bool tr = inverseWantsTransposed(log2n) && !dst;
+            for (int i = lane; i < count; i += 32) sA[warp][tr ? ((i & (nn - 1)) << log2n) + (i >> log2n) : i] = pool[task.src + i];
             __syncwarp();
-            invPass(M, sB[warp], sA[warp], log2n, dst, 7, lane);
-            __syncwarp();
-            invPass(M, sA[warp], sB[warp], log2n, dst, 20 - bitDepth, lane);
+            inverseTransform(M, sA[warp], sB[warp], log2n, dst, bitDepth, lane);
         }
         __syncwarp();
         for (int i = lane; i < count; i += 32) pool[task.dst + i] = sA[warp][i];
@@ -202,11 +340,10 @@ __global__ void __launch_bounds__(kWarps * 32)
     {
         const hvb_ita_task task = tasks[t];
         const int log2n = task.log2n, nn = 1 << log2n, count = nn * nn;
-        for (int i = lane; i < count; i += 32) sA[warp][i] = pool[task.coeffs + i];
+        const bool tr = inverseWantsTransposed(log2n) && task.trType == 0;
+        for (int i = lane; i < count; i += 32) sA[warp][tr ? ((i & (nn - 1)) << log2n) + (i >> log2n) : i] = pool[task.coeffs + i];
         __syncwarp();
-        invPass(M, sB[warp], sA[warp], log2n, task.trType != 0, 7, lane);
-        __syncwarp();
-        invPass(M, sA[warp], sB[warp], log2n, task.trType != 0, 20 - bitDepth, lane);
+        inverseTransform(M, sA[warp], sB[warp], log2n, task.trType != 0, bitDepth, lane);
         __syncwarp();
         int sd, sp;
         Sample *dst = hvbBlockPtrW<Sample>(planes, task.dst, sd);
@@ -301,9 +438,7 @@ __global__ void __launch_bounds__(kWarps * 32)
             ssdPred += (unsigned)(d * d);
         }
         __syncwarp();
-        fwdPass(M, sB[warp], sA[warp], nn, log2n, dst, log2n - 1 + bitDepth - 8, lane);
-        __syncwarp();
-        fwdPass(M, sA[warp], sB[warp], nn, log2n, dst, log2n + 6, lane); // sA = coefficients
+        forwardTransform(M, sA[warp], sB[warp], log2n, dst, bitDepth, lane); // sA = coefficients
         __syncwarp();
         ssdPred = hvbWarpSumU(ssdPred);
         if (sizeof(Sample) == 2) ssdPred >>= 4;
@@ -392,12 +527,14 @@ __global__ void __launch_bounds__(kWarps * 32)
         Sample *rec = hvbBlockPtrW<Sample>(planes, task.rec, sr);
         if (cbf)
         {
+            const bool tr = inverseWantsTransposed(log2n) && !dst;
             for (int i = lane; i < count; i += 32)
-                sA[warp][i] = (int16_t)dequantOne(pool[task.levels + i], task.iqscale, task.iqshift); // Reconstruct.cpp:822-826
+            {
+                const int v = dequantOne(pool[task.levels + i], task.iqscale, task.iqshift); // Reconstruct.cpp:822-826
+                sA[warp][tr ? ((i & (nn - 1)) << log2n) + (i >> log2n) : i] = (int16_t)v;
+            }
             __syncwarp();
-            invPass(M, sB[warp], sA[warp], log2n, dst, 7, lane);
-            __syncwarp();
-            invPass(M, sA[warp], sB[warp], log2n, dst, 20 - bitDepth, lane);
+            inverseTransform(M, sA[warp], sB[warp], log2n, dst, bitDepth, lane);
             __syncwarp();
         }
         // all-zero levels: the inverse transform of a zero block is zero, the reconstruction is the prediction
