@@ -335,6 +335,26 @@ def traffic_from_profile(kernel: str):
     return None if any(p is None for p in parts) else float(sum(parts))
 
 
+def ncu_evidence():
+    """What the committed ncu capture (profiles/*_kernels.csv, newest) says about each kernel of the pass: issue-slot use,
+    DRAM throughput and occupancy -- the pass is issue / latency bound, so these explain `roofline.frac` (an HBM fraction)."""
+    import csv
+    import re
+    files = sorted((ROOT / "profiles").glob("*_4k_kernels.csv"))
+    if not files:
+        return None
+    rows = list(csv.reader(files[-1].open()))
+    hdr = rows[0]
+    want = {"gpu__time_duration.sum": "ms", "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct", "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_pct"}
+    out = {"source": files[-1].name}
+    for r in rows[2:]:
+        name = re.sub(r"[<(].*", "", r[0].split("::")[-1]).strip()
+        out[name] = {v: float(r[hdr.index(k)].replace(",", "")) for k, v in want.items() if k in hdr}
+    return out
+
+
 def reference_encoder_fps(width, height, frames=6):
     """The reference's real encoder (oracle/_ref/turing_ref, built unmodified by oracle/Makefile `encoder`) on the same
     synthetic content at `--speed medium`, all host threads: context for the hot-path numbers, not their baseline."""
@@ -452,6 +472,7 @@ def main():
                 "frac": achieved / peak, "traffic": traffic_from_profile(kernel_names[dominant]), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dominant], "ms_per_launch": kern[dominant],
                 "all_kernels": {kernel_names[k]: {"ms": kern[k], "algorithmic_GBps": alg[k] / (kern[k] * 1e-3) / 1e9} for k in kern},
+                "ncu": ncu_evidence(),
                 "note": "pictures (25 MB) stay L2-resident across the 100-300 candidates of a search, so algorithmic "
                         "bytes exceed DRAM traffic by design; see DESIGN.md"}
 

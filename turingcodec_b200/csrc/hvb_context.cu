@@ -112,6 +112,7 @@ extern "C" void hvb_destroy(hvb_context *ctx)
     if (ctx->samplePool) cudaFree(ctx->samplePool);
     if (ctx->coeffPool) cudaFree(ctx->coeffPool);
     if (ctx->rdoqCtx) cudaFree(ctx->rdoqCtx);
+    if (ctx->rdoqBits) cudaFree(ctx->rdoqBits);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     delete ctx;
@@ -439,9 +440,13 @@ extern "C" int hvb_rdoq_contexts_upload(hvb_context *ctx, const hvb_rdoq_ctx *sn
     int rc = growDevice(ctx, &ctx->rdoqCtx, &have, (size_t)first + count, sizeof(hvb_rdoq_ctx), "rdoq contexts");
     if (rc) return rc;
     ctx->rdoqCtxCount = (int)have;
+    rc = growDevice(ctx, &ctx->rdoqBits, &ctx->rdoqBitsCount, have * sizeof(hvb_rdoq_ctx), sizeof(int2), "rdoq bit costs");
+    if (rc) return rc;
     cudaError_t e = cudaMemcpyAsync(ctx->rdoqCtx + first, snapshots, sizeof(hvb_rdoq_ctx) * count, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    return hvbCuda(ctx, e, "hvb_rdoq_contexts_upload");
+    if (e != cudaSuccess) return hvbCuda(ctx, e, "hvb_rdoq_contexts_upload");
+    rc = hvbLaunchRdoqBits(ctx, first, count); // {bits(0), bits(1)} per state byte: what the RDOQ walk actually reads
+    if (rc) return rc;
+    return hvbCuda(ctx, cudaStreamSynchronize(ctx->stream), "hvb_rdoq_contexts_upload");
 }
 
 bool hvbIsPinned(const void *p)

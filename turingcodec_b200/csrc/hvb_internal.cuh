@@ -75,6 +75,8 @@ struct hvb_context
     size_t coeffPoolCount = 0;
     hvb_rdoq_ctx *rdoqCtx = nullptr;
     int rdoqCtxCount = 0;
+    int2 *rdoqBits = nullptr; // [rdoqCtxCount * sizeof(hvb_rdoq_ctx)] bit costs of both bins per context state byte
+    size_t rdoqBitsCount = 0;
     void *scratch = nullptr; // kernel workspace (RDOQ per-TU state, ...)
     size_t scratchBytes = 0;
 };
@@ -86,6 +88,7 @@ int hvbSyncPlanes(hvb_context *ctx);
 int hvbEnsureScratch(hvb_context *ctx, size_t bytes);
 int hvbEnsureCoeffPool(hvb_context *ctx, size_t count);
 int hvbEnsureSamplePool(hvb_context *ctx, size_t count);
+int hvbLaunchRdoqBits(hvb_context *ctx, int first, int count); // hvb_tu.cu
 // Enqueue a host->device copy of caller memory.  Pipelined mode + page-locked source: on the copy-in stream, behind
 // every kernel enqueued so far (they may read the destination), the compute stream then waits for it; no host wait.
 // Otherwise on the compute stream, followed by a host wait (the source may be pageable).

@@ -56,7 +56,8 @@ static __device__ const int32_t kEntropyBits[128] = {
     0x00672, 0x26f23, 0x005e8, 0x27ef8, 0x005ba, 0x284b5, 0x0055e, 0x29057, 0x0050c, 0x29bab, 0x004c1, 0x2a674, 0x004a7,
     0x2aa5e, 0x0046f, 0x2b32f, 0x0041f, 0x2c0ad, 0x003e7, 0x2ca8d, 0x003ba, 0x2d323, 0x0010c, 0x3bfbb};
 
-__device__ __forceinline__ int bitsOf(int bin, uint8_t state) { return __ldg(&kEntropyBits[(state >> 1) ^ bin]); }
+struct Engine;
+__device__ __forceinline__ int bitsOf(const Engine &e, int bin, const uint8_t &state);
 
 __device__ __forceinline__ long long shflXor64(long long v, int m)
 {
@@ -118,6 +119,7 @@ __device__ __forceinline__ const short *scanTable(int log2, int scanIdx) { retur
 struct Engine
 {
     const hvb_rdoq_ctx *cx;
+    const int2 *bits; // per state byte of *cx: {bits of bin 0, bits of bin 1} (hvbLaunchRdoqBits), one load instead of two dependent ones
     HvbCoefRec *rec;
     const short *scan;
     const int16_t *src;
@@ -151,6 +153,13 @@ struct Engine
     }
     __device__ __forceinline__ long long dist0(int sp) const { return dist(abs((int)src[scan[sp]])); }
 };
+
+// the bit cost of coding `bin` with the context whose state byte is `state` (a member of *e.cx)
+__device__ __forceinline__ int bitsOf(const Engine &e, int bin, const uint8_t &state)
+{
+    const int2 v = __ldg(e.bits + (&state - reinterpret_cast<const uint8_t *>(e.cx)));
+    return bin ? v.y : v.x;
+}
 
 __device__ __forceinline__ int baseLevel(int g1Cnt, int g2Cnt) { return g1Cnt < 8 ? 2 + (g2Cnt < 1) : 1; }
 
@@ -206,14 +215,14 @@ __device__ inline long long levelRateCost(const Engine &e, int level, int g1Ctx,
         }
         if (g1Cnt < 8)
         {
-            rate += bitsOf(1, e.cx->greater1_flag[g1Ctx]);
-            if (g2Cnt < 1) rate += bitsOf(1, e.cx->greater2_flag[g2Ctx]);
+            rate += bitsOf(e, 1, e.cx->greater1_flag[g1Ctx]);
+            if (g2Cnt < 1) rate += bitsOf(e, 1, e.cx->greater2_flag[g2Ctx]);
         }
     }
     else if (level == 1)
-        rate += bitsOf(0, e.cx->greater1_flag[g1Ctx]);
+        rate += bitsOf(e, 0, e.cx->greater1_flag[g1Ctx]);
     else if (level == 2)
-        rate += bitsOf(1, e.cx->greater1_flag[g1Ctx]) + bitsOf(0, e.cx->greater2_flag[g2Ctx]);
+        rate += bitsOf(e, 1, e.cx->greater1_flag[g1Ctx]) + bitsOf(e, 0, e.cx->greater2_flag[g2Ctx]);
     return e.lam(rate);
 }
 
@@ -239,14 +248,14 @@ __device__ inline int levelRate(const Engine &e, int level, int g1Ctx, int g2Ctx
         rate += (min(symbol >> (rice + 1), maxPrefix) + rice) << 15;
         if (g1Cnt < 8)
         {
-            rate += bitsOf(1, e.cx->greater1_flag[g1Ctx]);
-            if (g2Cnt < 1) rate += bitsOf(1, e.cx->greater2_flag[g2Ctx]);
+            rate += bitsOf(e, 1, e.cx->greater1_flag[g1Ctx]);
+            if (g2Cnt < 1) rate += bitsOf(e, 1, e.cx->greater2_flag[g2Ctx]);
         }
     }
     else if (level == 1)
-        rate += bitsOf(0, e.cx->greater1_flag[g1Ctx]);
+        rate += bitsOf(e, 0, e.cx->greater1_flag[g1Ctx]);
     else if (level == 2)
-        rate += bitsOf(1, e.cx->greater1_flag[g1Ctx]) + bitsOf(0, e.cx->greater2_flag[g2Ctx]);
+        rate += bitsOf(e, 1, e.cx->greater1_flag[g1Ctx]) + bitsOf(e, 0, e.cx->greater2_flag[g2Ctx]);
     return rate;
 }
 
@@ -258,13 +267,13 @@ __device__ inline int adjustLevel(const Engine &e, int absCoeff, int q, int sigC
     int best = 0;
     if (!isLast && q < 3)
     {
-        rateSig = e.lam(bitsOf(0, e.cx->sig_coeff_flag[sigCtx]));
+        rateSig = e.lam(bitsOf(e, 0, e.cx->sig_coeff_flag[sigCtx]));
         rdCost = e.dist(absCoeff) + rateSig;
         if (q == 0) return 0;
     }
     else
         rdCost = 0x7fffffffffffffffLL;
-    if (!isLast) sigCost = e.lam(bitsOf(1, e.cx->sig_coeff_flag[sigCtx]));
+    if (!isLast) sigCost = e.lam(bitsOf(e, 1, e.cx->sig_coeff_flag[sigCtx]));
     const int lowest = q > 1 ? q - 1 : 1;
     for (int level = q; level >= lowest; --level)
     {
@@ -298,10 +307,10 @@ __device__ inline long long lastPosCost(const Engine &e, int xC, int yC)
 {
     const int lx = lastLen(xC), ly = lastLen(yC);
     int rate = 0;
-    for (int i = 0; i < lx; ++i) rate += bitsOf(1, e.cx->last_x_prefix[lastPrefixCtx(i, e.cIdx, e.log2)]);
-    if (lx < 9) rate += bitsOf(0, e.cx->last_x_prefix[lastPrefixCtx(lx, e.cIdx, e.log2)]);
-    for (int i = 0; i < ly; ++i) rate += bitsOf(1, e.cx->last_y_prefix[lastPrefixCtx(i, e.cIdx, e.log2)]);
-    if (ly < 9) rate += bitsOf(0, e.cx->last_y_prefix[lastPrefixCtx(ly, e.cIdx, e.log2)]);
+    for (int i = 0; i < lx; ++i) rate += bitsOf(e, 1, e.cx->last_x_prefix[lastPrefixCtx(i, e.cIdx, e.log2)]);
+    if (lx < 9) rate += bitsOf(e, 0, e.cx->last_x_prefix[lastPrefixCtx(lx, e.cIdx, e.log2)]);
+    for (int i = 0; i < ly; ++i) rate += bitsOf(e, 1, e.cx->last_y_prefix[lastPrefixCtx(i, e.cIdx, e.log2)]);
+    if (ly < 9) rate += bitsOf(e, 0, e.cx->last_y_prefix[lastPrefixCtx(ly, e.cIdx, e.log2)]);
     if (lx > 3) rate += 32768 * ((lx - 2) >> 1);
     if (ly > 3) rate += 32768 * ((ly - 2) >> 1);
     return e.lam(rate);
@@ -432,7 +441,8 @@ __device__ inline HvbRdoqMid hvbRdoqPrepass(int16_t *dst, const int16_t *src, co
 // The serial stages of Rdoq::runQuantisation for one block on one thread.  `dst` holds zeros on entry (pre-pass),
 // `rec` has room for n records.  Returns the OR of the coded levels.
 __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_rdoq_ctx *ctx, const HvbRdoqMid &mid, int qScale, int qShift,
-                                    int iqScale, int log2, int cIdx, int scanIdx, bool isIntra, bool sdh, int bitDepth, HvbCoefRec *rec)
+                                    int iqScale, int log2, int cIdx, int scanIdx, bool isIntra, bool sdh, int bitDepth, HvbCoefRec *rec,
+                                    const int2 *bits)
 {
     using namespace hvb_rdoq;
     const int lastSp = mid.lastSp;
@@ -441,6 +451,7 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
     e.init(ctx, iqScale, log2, cIdx, scanIdx, bitDepth);
     e.rec = rec;
     e.src = src;
+    e.bits = bits;
     const int log2Cg = log2 - 2, mask = (1 << log2) - 1;
 
     long long rdCostTu = mid.tailDist0;
@@ -477,7 +488,7 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
                 anyLevel = true;
                 break;
             }
-            const long long rs = e.lam(bitsOf(0, ctx->sig_coeff_flag[sigCtxInc(prev, scanIdx, pos & mask, pos >> log2, log2, cIdx)]));
+            const long long rs = e.lam(bitsOf(e, 0, ctx->sig_coeff_flag[sigCtxInc(prev, scanIdx, pos & mask, pos >> log2, log2, cIdx)]));
             sumSig += rs;
             sumRd += e.dist(a) + rs;
         }
@@ -492,7 +503,7 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
             if (g1Idx == 0) ctxSet++;
             g1Idx = 1;
             // uncoded group: pay for its flag, drop the significance costs (Rdoq.cpp:206-216)
-            const long long zero = e.lam(bitsOf(0, ctx->coded_sub_block_flag[cSig]));
+            const long long zero = e.lam(bitsOf(e, 0, ctx->coded_sub_block_flag[cSig]));
             rdCostTu += zero - sumSig;
             rateCostCgSig[cg] = zero;
             continue;
@@ -518,7 +529,7 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
             rec[sp].rateSig = rateSig;
             HvbCoefRec &r = rec[pos];
             r.deltaU = (scaled - (level << qShift)) >> (qShift - 8);
-            r.sigDelta = sp != lastSp ? bitsOf(1, ctx->sig_coeff_flag[sigCtx]) - bitsOf(0, ctx->sig_coeff_flag[sigCtx]) : 0;
+            r.sigDelta = sp != lastSp ? bitsOf(e, 1, ctx->sig_coeff_flag[sigCtx]) - bitsOf(e, 0, ctx->sig_coeff_flag[sigCtx]) : 0;
             if (level > 0)
             {
                 const int now = levelRate(e, level, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt);
@@ -528,7 +539,7 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
             }
             else
             {
-                r.rateUp = bitsOf(0, ctx->greater1_flag[g1Ctx]);
+                r.rateUp = bitsOf(e, 0, ctx->greater1_flag[g1Ctx]);
                 r.rateDown = 0;
             }
             rdCostTu += rdCost;
@@ -568,7 +579,7 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
         // coefficient-group zeroing (Rdoq.cpp:200-304)
         if (cg)
         {
-            const long long zero = e.lam(bitsOf(0, ctx->coded_sub_block_flag[cSig]));
+            const long long zero = e.lam(bitsOf(e, 0, ctx->coded_sub_block_flag[cSig]));
             if (!cgCoded)
             {
                 rdCostTu += zero - cgRateSig;
@@ -581,7 +592,7 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
                     rdCostTu -= cgRateSigPos0;
                     cgRateSig -= cgRateSigPos0;
                 }
-                const long long one = e.lam(bitsOf(1, ctx->coded_sub_block_flag[cSig]));
+                const long long one = e.lam(bitsOf(e, 1, ctx->coded_sub_block_flag[cSig]));
                 const long long allZero = rdCostTu + zero + cgDist0 - cgRdCoeff - cgRateSig;
                 rdCostTu += one;
                 rateCostCgSig[cg] = one;
@@ -602,9 +613,9 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
     // ---- stage 2: last significant position (Rdoq.cpp:313-397)
     int lastIdx = 0;
     {
-        const uint8_t st = (!isIntra && cIdx == 0) ? ctx->rqt_root_cbf[0] : (cIdx == 0 ? ctx->cbf_luma[1] : ctx->cbf_cbcr[0]);
-        long long best = mid.totalDist0 + e.lam(bitsOf(0, st));
-        rdCostTu += e.lam(bitsOf(1, st));
+        const uint8_t &st = (!isIntra && cIdx == 0) ? ctx->rqt_root_cbf[0] : (cIdx == 0 ? ctx->cbf_luma[1] : ctx->cbf_cbcr[0]);
+        long long best = mid.totalDist0 + e.lam(bitsOf(e, 0, st));
+        rdCostTu += e.lam(bitsOf(e, 1, st));
         bool found = false;
         for (int cg = lastCg; cg >= 0 && !found; --cg)
         {
