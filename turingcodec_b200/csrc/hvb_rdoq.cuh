@@ -24,7 +24,7 @@
 #pragma once
 #include "hvb_internal.cuh"
 
-// per-coefficient record: cost fields are indexed by scan position, sign-hiding fields by raster position
+// per-coefficient record, indexed by scan position
 struct HvbCoefRec
 {
     long long rdCost;  // m_rdCostCoeff
@@ -357,7 +357,7 @@ __device__ inline void signDataHiding(const Engine &e, int lastCgCoded, int16_t 
                 {
                     const int pos = sc[k];
                     const int level = dst[pos];
-                    const HvbCoefRec &r = e.rec[pos];
+                    const HvbCoefRec &r = e.rec[(cg << 4) + k];
                     int cost, change;
                     if (level != 0)
                     {
@@ -527,7 +527,7 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
             const int level = adjustLevel(e, a, q, sigCtx, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt, sp == lastSp, rdCost, rateSig);
             rec[sp].rdCost = rdCost;
             rec[sp].rateSig = rateSig;
-            HvbCoefRec &r = rec[pos];
+            HvbCoefRec &r = rec[sp]; // everything about a coefficient in one 32-byte record (one sector), indexed by scan position
             r.deltaU = (scaled - (level << qShift)) >> (qShift - 8);
             r.sigDelta = sp != lastSp ? bitsOf(e, 1, ctx->sig_coeff_flag[sigCtx]) - bitsOf(e, 0, ctx->sig_coeff_flag[sigCtx]) : 0;
             if (level > 0)
