@@ -63,9 +63,10 @@ int hvb_sync(hvb_context *ctx);
 /* Pipelined host mode.  Off (default): every HVB_HOST call returns after its results have landed.  On: a batch call
  * whose task and result arrays are page-locked (cudaHostAlloc / cudaHostRegister -- an encoder's arena) only enqueues
  * work -- tasks go up on a copy-in stream, the kernels run on the context's stream, the results come back on a copy-out
- * stream, through a ring of four staging slots -- and returns; picture / pool uploads from page-locked memory are
- * enqueued behind the kernels already issued.  Results and source buffers belong to the library until hvb_sync()
- * returns.  Calls with pageable buffers keep the blocking behaviour. */
+ * stream, through a ring of four staging slots -- and returns; picture / pool uploads from page-locked memory go on the
+ * copy-in stream too: batches issued AFTER an upload see it, batches issued BEFORE it are not waited for, so upload into
+ * pictures / pool regions that no batch in flight reads (double-buffer).  Results and source buffers belong to the
+ * library until hvb_sync() returns.  Calls with pageable buffers keep the blocking behaviour. */
 int hvb_set_pipelined(hvb_context *ctx, int on);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t hvb_launch_count(hvb_context *ctx);

@@ -54,8 +54,8 @@ def test_pipelined_frame_pass_equals_blocking():
     for k in ("h_me", "h_intra", "h_tu"):
         getattr(gpu, k).view(np.uint8)[...] = 0xA5
     gpu.ctx.set_pipelined(True)
-    for _ in range(3):
-        gpu.step_e2e()
+    for k in range(3):
+        gpu.step_e2e(k)  # alternates between the two upload sets: step k+1's copies overlap step k's kernels
     gpu.ctx.sync()
     for k in ("h_me", "h_intra", "h_tu"):
         assert np.array_equal(getattr(gpu, k).view(np.uint8), want[k].view(np.uint8)), k

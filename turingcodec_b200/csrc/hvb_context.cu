@@ -163,9 +163,9 @@ int hvbUpload(hvb_context *ctx, void *dev, size_t devPitch, const void *host, si
     cudaSetDevice(ctx->device);
     if (ctx->pipelined && hvbIsPinned(host))
     {
-        cudaError_t e = cudaEventRecord(ctx->evCompute, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copyIn, ctx->evCompute, 0);
-        if (e == cudaSuccess) e = cudaMemcpy2DAsync(dev, devPitch, host, hostPitch, widthBytes, rows, cudaMemcpyHostToDevice, ctx->copyIn);
+        // Not ordered against batches issued EARLIER: like any asynchronous copy, the caller must not overwrite what work
+        // in flight still reads (an encoder uploads the next frame into a free picture while the previous one is searched).
+        cudaError_t e = cudaMemcpy2DAsync(dev, devPitch, host, hostPitch, widthBytes, rows, cudaMemcpyHostToDevice, ctx->copyIn);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->evIn, ctx->copyIn);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->evIn, 0);
         return hvbCuda(ctx, e, what);

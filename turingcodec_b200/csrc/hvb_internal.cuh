@@ -89,8 +89,8 @@ int hvbEnsureScratch(hvb_context *ctx, size_t bytes);
 int hvbEnsureCoeffPool(hvb_context *ctx, size_t count);
 int hvbEnsureSamplePool(hvb_context *ctx, size_t count);
 int hvbLaunchRdoqBits(hvb_context *ctx, int first, int count); // hvb_tu.cu
-// Enqueue a host->device copy of caller memory.  Pipelined mode + page-locked source: on the copy-in stream, behind
-// every kernel enqueued so far (they may read the destination), the compute stream then waits for it; no host wait.
+// Enqueue a host->device copy of caller memory.  Pipelined mode + page-locked source: on the copy-in stream (ordered after
+// earlier uploads, not after earlier batches); the compute stream waits for it before anything issued later; no host wait.
 // Otherwise on the compute stream, followed by a host wait (the source may be pageable).
 int hvbUpload(hvb_context *ctx, void *dev, size_t devPitch, const void *host, size_t hostPitch, size_t widthBytes, size_t rows,
               const char *what);
