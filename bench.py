@@ -51,6 +51,8 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--width", type=int, default=3840)
     p.add_argument("--height", type=int, default=2160)
+    p.add_argument("--bit-depth", type=int, default=8, choices=[8, 10],
+                   help="10: the 16-bit sample path (BASELINE.json configs[3]); the headline metric is the 8-bit pass")
     p.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     p.add_argument("--no-e2e", action="store_true")
@@ -121,9 +123,14 @@ def pinned_empty(shape, dtype):
     return t.numpy().view(dtype).reshape(shape), t
 
 
-def build_inputs(width, height):
+def bit_depth_of(args):
+    return int(getattr(args, "bit_depth", 8))
+
+
+def build_inputs(width, height, bit_depth=8):
     from turingcodec_b200 import synth
-    frames = [synth.frame(i, width, height, 8) for i in range(3)]
+    dtype = np.uint8 if bit_depth == 8 else np.uint16
+    frames = [[pl.astype(dtype) for pl in synth.frame(i, width, height, bit_depth)] for i in range(3)]
     return frames
 
 
@@ -134,25 +141,27 @@ class GpuArm:
         self.torch, self.hvb = torch, hvb
         self.device = device
         torch.cuda.set_device(device)
-        self.ctx = hvb.Context(device, 1, 8)
+        bd = bit_depth_of(args)
+        self.bps, self.dtype = (1, np.uint8) if bd == 8 else (2, np.uint16)
+        self.ctx = hvb.Context(device, self.bps, bd)
         self.stream = torch.cuda.Stream(device)
         self.ctx.set_stream(self.stream.cuda_stream)
         w, h = args.width, args.height
-        self.frames = build_inputs(w, h)
+        self.frames = build_inputs(w, h, bd)
         # pictures: 0 source, 1 reference, 2 second prediction source, 3..8 reconstruction targets
         self.pics = [self.ctx.picture_create(w, h, 96) for _ in range(N_PICS)]
         self.pinned = []
         for pic, f in zip(self.pics[:3], self.frames):
             planes = []
             for c, pl in enumerate(f):
-                arr, keep = pinned_empty(pl.shape, np.uint8)
+                arr, keep = pinned_empty(pl.shape, self.dtype)
                 arr[...] = pl
                 planes.append((arr, keep))
                 self.ctx.picture_upload(pic, c, arr)
             self.ctx.picture_pad(pic)
             self.pinned.append(planes)
         self.fp = workload.frame_pass(self.frames[0][0], self.pics[0], self.pics[1], (self.pics[1], self.pics[2]),
-                                      tuple(self.pics[3:9]))
+                                      tuple(self.pics[3:9]), bit_depth=bd)
         fp = self.fp
         self.ctx.pool_upload(fp.neighbours)
         self.ctx.rdoq_contexts_upload(fp.rdoq_ctx)
@@ -264,7 +273,9 @@ class CpuArm:
                 self.ref = None
         self.threads = int(L.orc_bench_threads())
         w, h = args.width, args.height
-        self.frames = frames if frames is not None else build_inputs(w, h)
+        self.bd = bit_depth_of(args)
+        self.bps, dtype = (1, np.uint8) if self.bd == 8 else (2, np.uint16)
+        self.frames = frames if frames is not None else build_inputs(w, h, self.bd)
         pad = 96
         # host pictures 0..4 mirroring the GPU arm's ids; planes padded like the device ones, 64-byte aligned rows
         self.planes = (C.c_void_p * 0)()
@@ -274,8 +285,8 @@ class CpuArm:
             for c in range(3):
                 pw, ph, pd = (w, h, pad) if c == 0 else (w // 2, h // 2, pad // 2)
                 stride = (pw + 2 * pd + 63) // 64 * 64 + 64
-                raw = np.zeros((ph + 2 * pd + 2) * stride + 64, np.uint8)
-                off = (-raw.ctypes.data) % 64
+                raw = np.zeros((ph + 2 * pd + 2) * stride + 64, dtype)
+                off = ((-raw.ctypes.data) % 64) // self.bps
                 buf = raw[off:off + (ph + 2 * pd + 2) * stride].reshape(ph + 2 * pd + 2, stride)
                 x0 = (pd + 63) // 64 * 64
                 if pic < 3:
@@ -285,9 +296,9 @@ class CpuArm:
                     buf[:pd] = buf[pd]
                     buf[pd + ph:pd + ph + pd] = buf[pd + ph - 1]
                 self.host.append((raw, buf))
-                table[pic * 3 + c] = (buf.ctypes.data + pd * stride + x0, stride)
+                table[pic * 3 + c] = (buf.ctypes.data + (pd * stride + x0) * self.bps, stride)
         self.table = table
-        self.fp = fp if fp is not None else workload.frame_pass(self.frames[0][0], 0, 1, (1, 2), tuple(range(3, 9)))
+        self.fp = fp if fp is not None else workload.frame_pass(self.frames[0][0], 0, 1, (1, 2), tuple(range(3, 9)), bit_depth=self.bd)
         self.levels = np.zeros(self.fp.coeff_count, np.int16)
         L.orc_bench_me.restype = C.c_double
         L.orc_bench_intra.restype = C.c_double
@@ -307,9 +318,9 @@ class CpuArm:
         o_intra = np.zeros((intra.size, 35), np.int32)
         o_tu = np.zeros(tu.size, hvb.tu_result_t)
         p = self.table.ctypes.data
-        t = L.orc_bench_me(p, me.ctypes.data, me.size, o_me.ctypes.data, 1, 8)
-        t += L.orc_bench_intra(p, fp.neighbours.ctypes.data, intra.ctypes.data, intra.size, o_intra.ctypes.data, 1, 8)
-        t += L.orc_bench_tu(p, p, fp.rdoq_ctx.ctypes.data, tu.ctypes.data, tu.size, self.levels.ctypes.data, o_tu.ctypes.data, 1, 8)
+        t = L.orc_bench_me(p, me.ctypes.data, me.size, o_me.ctypes.data, self.bps, self.bd)
+        t += L.orc_bench_intra(p, fp.neighbours.ctypes.data, intra.ctypes.data, intra.size, o_intra.ctypes.data, self.bps, self.bd)
+        t += L.orc_bench_tu(p, p, fp.rdoq_ctx.ctypes.data, tu.ctypes.data, tu.size, self.levels.ctypes.data, o_tu.ctypes.data, self.bps, self.bd)
         return t, 1.0 / stride, (o_me, o_intra, o_tu, me, intra, tu)
 
     def measure(self, target_seconds: float):
@@ -478,8 +489,8 @@ def main():
     me_out = arm.o_me.cpu().numpy().view(hvb.me_result_t)
     fp = arm.fp
     n_sad_samples = int((me_out["nSad"].astype(np.int64) * fp.me["w"].astype(np.int64) * fp.me["h"].astype(np.int64)).sum())
-    ab = workload.algorithmic_bytes(fp, 0)
-    alg = {"me": ab["me_fixed"] + n_sad_samples, "intra": ab["intra"], "tu": ab["tu"]}
+    ab = workload.algorithmic_bytes(fp, 0, arm.bps)
+    alg = {"me": ab["me_fixed"] + n_sad_samples * arm.bps, "intra": ab["intra"], "tu": ab["tu"]}
     dominant = max(kern, key=kern.get)
     peak, peak_src = peaks()
     achieved = alg[dominant] / (kern[dominant] * 1e-3) / 1e9
@@ -528,9 +539,10 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": f"{args.width}x{args.height} YUV420 8-bit, medium preset, one hot-path frame pass per step "
-                                       "(configs[2] of BASELINE.json)", "units_per_step": fp.units,
+                "vs_baseline": None, "dtype": "u8" if args.bit_depth == 8 else "u16", "data": "synthetic",
+                "config": {"workload": f"{args.width}x{args.height} YUV420 {args.bit_depth}-bit, medium preset, one hot-path frame pass per step "
+                                       + ("(configs[2] of BASELINE.json)" if args.bit_depth == 8 else "(16-bit sample path of configs[3])"),
+                           "units_per_step": fp.units,
                            "l2": "per-step working set (tasks+results+levels+pictures) ~370 MB > 126 MB L2; no explicit flush",
                            "parallelism": f"frames sharded over {world} GPU(s), no collective"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),

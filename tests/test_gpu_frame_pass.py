@@ -15,10 +15,12 @@ sys.path.insert(0, str(ROOT))
 pytestmark = pytest.mark.gpu
 
 
-def test_frame_pass_equals_oracle():
+@pytest.mark.parametrize("bit_depth, width, height", [(8, 640, 384), (10, 384, 256)], ids=["8bit", "10bit-u16"])
+def test_frame_pass_equals_oracle(bit_depth, width, height):
+    """8 bit: BASELINE.json configs[2] at a size the CPU finishes in seconds; 10 bit: the 16-bit sample path of configs[3]."""
     import bench
     from turingcodec_b200 import hvb
-    args = SimpleNamespace(width=640, height=384)
+    args = SimpleNamespace(width=width, height=height, bit_depth=bit_depth)
     gpu = bench.GpuArm(args, 0)
     gpu.ctx.set_stream(None)
     gpu.step_e2e()  # host-facing path: uploads, three launches, downloads

@@ -168,10 +168,10 @@ def rdoq_contexts(n_ctx: int, seed=11) -> np.ndarray:
     return c
 
 
-def frame_pass(y_plane: np.ndarray, src_pic: int, ref_pic: int, pred_pics, rec_pics, n_ctx: int = 64) -> FramePass:
+def frame_pass(y_plane: np.ndarray, src_pic: int, ref_pic: int, pred_pics, rec_pics, n_ctx: int = 64, bit_depth: int = 8) -> FramePass:
     height, width = y_plane.shape
     intra, pool = intra_tasks(y_plane, src_pic)
-    tu, coeff_count = tu_tasks(width, height, src_pic, pred_pics, rec_pics, n_ctx)
+    tu, coeff_count = tu_tasks(width, height, src_pic, pred_pics, rec_pics, n_ctx, bit_depth=bit_depth)
     return FramePass(me=me_tasks(width, height, src_pic, ref_pic), intra=intra, tu=tu, neighbours=pool,
                      rdoq_ctx=rdoq_contexts(n_ctx), coeff_count=coeff_count)
 
