@@ -161,6 +161,17 @@ __device__ __forceinline__ int bitsOf(const Engine &e, int bin, const uint8_t &s
     return bin ? v.y : v.x;
 }
 
+// both bins' bit costs of the three contexts a coefficient's decision reads, requested together (independent loads)
+// instead of one by one inside the rate functions
+struct CoefBits
+{
+    int2 sig, g1, g2;
+};
+__device__ __forceinline__ int2 bitsBoth(const Engine &e, const uint8_t &state)
+{
+    return __ldg(e.bits + (&state - reinterpret_cast<const uint8_t *>(e.cx)));
+}
+
 __device__ __forceinline__ int baseLevel(int g1Cnt, int g2Cnt) { return g1Cnt < 8 ? 2 + (g2Cnt < 1) : 1; }
 
 // Rdoq.cpp:512-598
@@ -194,7 +205,7 @@ __device__ inline int sigCtxInc(int prevCsbf, int scanIdx, int xC, int yC, int l
 }
 
 // Rdoq.cpp:619-673
-__device__ inline long long levelRateCost(const Engine &e, int level, int g1Ctx, int g2Ctx, int rice, int g1Cnt, int g2Cnt)
+__device__ inline long long levelRateCost(const Engine &e, int level, const CoefBits &cb, int rice, int g1Cnt, int g2Cnt)
 {
     int rate = 32768;
     const int base = baseLevel(g1Cnt, g2Cnt);
@@ -215,19 +226,19 @@ __device__ inline long long levelRateCost(const Engine &e, int level, int g1Ctx,
         }
         if (g1Cnt < 8)
         {
-            rate += bitsOf(e, 1, e.cx->greater1_flag[g1Ctx]);
-            if (g2Cnt < 1) rate += bitsOf(e, 1, e.cx->greater2_flag[g2Ctx]);
+            rate += cb.g1.y;
+            if (g2Cnt < 1) rate += cb.g2.y;
         }
     }
     else if (level == 1)
-        rate += bitsOf(e, 0, e.cx->greater1_flag[g1Ctx]);
+        rate += cb.g1.x;
     else if (level == 2)
-        rate += bitsOf(e, 1, e.cx->greater1_flag[g1Ctx]) + bitsOf(e, 0, e.cx->greater2_flag[g2Ctx]);
+        rate += cb.g1.y + cb.g2.x;
     return e.lam(rate);
 }
 
 // Rdoq.cpp:805-870
-__device__ inline int levelRate(const Engine &e, int level, int g1Ctx, int g2Ctx, int rice, int g1Cnt, int g2Cnt)
+__device__ inline int levelRate(const Engine &e, int level, const CoefBits &cb, int rice, int g1Cnt, int g2Cnt)
 {
     int rate = 0;
     const int base = baseLevel(g1Cnt, g2Cnt);
@@ -248,37 +259,37 @@ __device__ inline int levelRate(const Engine &e, int level, int g1Ctx, int g2Ctx
         rate += (min(symbol >> (rice + 1), maxPrefix) + rice) << 15;
         if (g1Cnt < 8)
         {
-            rate += bitsOf(e, 1, e.cx->greater1_flag[g1Ctx]);
-            if (g2Cnt < 1) rate += bitsOf(e, 1, e.cx->greater2_flag[g2Ctx]);
+            rate += cb.g1.y;
+            if (g2Cnt < 1) rate += cb.g2.y;
         }
     }
     else if (level == 1)
-        rate += bitsOf(e, 0, e.cx->greater1_flag[g1Ctx]);
+        rate += cb.g1.x;
     else if (level == 2)
-        rate += bitsOf(e, 1, e.cx->greater1_flag[g1Ctx]) + bitsOf(e, 0, e.cx->greater2_flag[g2Ctx]);
+        rate += cb.g1.y + cb.g2.x;
     return rate;
 }
 
 // Rdoq.cpp:452-510
-__device__ inline int adjustLevel(const Engine &e, int absCoeff, int q, int sigCtx, int g1Ctx, int g2Ctx, int rice, int g1Cnt, int g2Cnt,
-                                  bool isLast, long long &rdCost, long long &rateSig)
+__device__ inline int adjustLevel(const Engine &e, int absCoeff, int q, const CoefBits &cb, int rice, int g1Cnt, int g2Cnt, bool isLast,
+                                  long long &rdCost, long long &rateSig)
 {
     long long sigCost = 0;
     int best = 0;
     if (!isLast && q < 3)
     {
-        rateSig = e.lam(bitsOf(e, 0, e.cx->sig_coeff_flag[sigCtx]));
+        rateSig = e.lam(cb.sig.x);
         rdCost = e.dist(absCoeff) + rateSig;
         if (q == 0) return 0;
     }
     else
         rdCost = 0x7fffffffffffffffLL;
-    if (!isLast) sigCost = e.lam(bitsOf(e, 1, e.cx->sig_coeff_flag[sigCtx]));
+    if (!isLast) sigCost = e.lam(cb.sig.y);
     const int lowest = q > 1 ? q - 1 : 1;
     for (int level = q; level >= lowest; --level)
     {
         const int recon = hvbClip3(-32768, 32767, (hvbClip3(-32768, 32767, level) * e.iqScale + e.iqOffset) >> e.iqShift);
-        const long long c = e.dist(absCoeff - recon) + levelRateCost(e, level, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt) + sigCost;
+        const long long c = e.dist(absCoeff - recon) + levelRateCost(e, level, cb, rice, g1Cnt, g2Cnt) + sigCost;
         if (c < rdCost)
         {
             best = level;
@@ -523,23 +534,24 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
             const int sigCtx = sigCtxInc(prev, scanIdx, pos & mask, pos >> log2, log2, cIdx);
             const long long d0 = e.dist(a);
             const int g1Ctx = 4 * ctxSet + g1Idx + g1Off, g2Ctx = ctxSet + g2Off;
+            const CoefBits cb{bitsBoth(e, ctx->sig_coeff_flag[sigCtx]), bitsBoth(e, ctx->greater1_flag[g1Ctx]), bitsBoth(e, ctx->greater2_flag[g2Ctx])};
             long long rdCost = 0, rateSig = 0;
-            const int level = adjustLevel(e, a, q, sigCtx, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt, sp == lastSp, rdCost, rateSig);
+            const int level = adjustLevel(e, a, q, cb, rice, g1Cnt, g2Cnt, sp == lastSp, rdCost, rateSig);
             rec[sp].rdCost = rdCost;
             rec[sp].rateSig = rateSig;
             HvbCoefRec &r = rec[sp]; // everything about a coefficient in one 32-byte record (one sector), indexed by scan position
             r.deltaU = (scaled - (level << qShift)) >> (qShift - 8);
-            r.sigDelta = sp != lastSp ? bitsOf(e, 1, ctx->sig_coeff_flag[sigCtx]) - bitsOf(e, 0, ctx->sig_coeff_flag[sigCtx]) : 0;
+            r.sigDelta = sp != lastSp ? cb.sig.y - cb.sig.x : 0;
             if (level > 0)
             {
-                const int now = levelRate(e, level, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt);
-                r.rateUp = levelRate(e, level + 1, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt) - now;
-                r.rateDown = levelRate(e, level - 1, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt) - now;
+                const int now = levelRate(e, level, cb, rice, g1Cnt, g2Cnt);
+                r.rateUp = levelRate(e, level + 1, cb, rice, g1Cnt, g2Cnt) - now;
+                r.rateDown = levelRate(e, level - 1, cb, rice, g1Cnt, g2Cnt) - now;
                 dst[pos] = (int16_t)level;
             }
             else
             {
-                r.rateUp = bitsOf(e, 0, ctx->greater1_flag[g1Ctx]);
+                r.rateUp = cb.g1.x;
                 r.rateDown = 0;
             }
             rdCostTu += rdCost;
