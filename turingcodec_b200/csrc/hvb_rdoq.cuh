@@ -490,18 +490,25 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
         // (The DC group is always treated as coded, so stage 2 reads its records: it takes the general path.)
         bool anyLevel = cg == 0;
         long long sumRd = 0, sumSig = 0;
-        for (int k = 0; k < 16 && !anyLevel; ++k)
+        // four coefficients at a time: their loads are independent of each other (the early exit sits between the quads)
+        for (int k0 = 0; k0 < 16 && !anyLevel; k0 += 4)
         {
-            const int pos = sc[k];
-            const int a = abs((int)src[pos]);
-            if ((cg * 16 + k <= lastSp) && ((a * qScale + (1 << (qShift - 1))) >> qShift) > 0)
+            int pos4[4], a4[4], bits4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pos4[j] = sc[k0 + j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a4[j] = abs((int)src[pos4[j]]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                bits4[j] = bitsOf(e, 0, ctx->sig_coeff_flag[sigCtxInc(prev, scanIdx, pos4[j] & mask, pos4[j] >> log2, log2, cIdx)]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
             {
-                anyLevel = true;
-                break;
+                if ((cg * 16 + k0 + j <= lastSp) && ((a4[j] * qScale + (1 << (qShift - 1))) >> qShift) > 0) anyLevel = true;
+                const long long rs = e.lam(bits4[j]);
+                sumSig += rs;
+                sumRd += e.dist(a4[j]) + rs;
             }
-            const long long rs = e.lam(bitsOf(e, 0, ctx->sig_coeff_flag[sigCtxInc(prev, scanIdx, pos & mask, pos >> log2, log2, cIdx)]));
-            sumSig += rs;
-            sumRd += e.dist(a) + rs;
         }
         if (!anyLevel)
         {
@@ -523,12 +530,19 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
         int nzBeforePos0 = 0;
         long long cgDist0 = 0, cgRateSig = 0, cgRateSigPos0 = 0, cgRdCoeff = 0;
         bool cgCoded = false;
-        for (int k = 15; k >= 0; --k)
+        // positions beyond lastSp (only in its own group) are accounted for by the pre-pass: their rate terms are zero.
+        // The next coefficient is requested one iteration ahead of the chain of decisions that consumes it.
+        const int kStart = cg == lastCg ? (lastSp & 15) : 15;
+        int posNext = sc[kStart], aNext = abs((int)src[posNext]);
+        for (int k = kStart; k >= 0; --k)
         {
             const int sp = cg * 16 + k;
-            if (sp > lastSp) continue; // accounted for by the pre-pass (their rate terms are zero)
-            const int pos = sc[k];
-            const int a = abs((int)src[pos]);
+            const int pos = posNext, a = aNext;
+            if (k > 0)
+            {
+                posNext = sc[k - 1];
+                aNext = abs((int)src[posNext]);
+            }
             const int scaled = a * qScale;
             const int q = (scaled + (1 << (qShift - 1))) >> qShift;
             const int sigCtx = sigCtxInc(prev, scanIdx, pos & mask, pos >> log2, log2, cIdx);
