@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(kWarps * 32)
     for (int i = blockIdx.x * kWarps + warp; i < n; i += warpsTotal)
     {
         const hvb_me_task t = tasks[i];
-        if (!kFused && t.w <= 8 && t.h <= 8) continue; // 8-bit PUs up to 8x8 are searched four per warp by hvb_me_small.cu
+        if (sizeof(Sample) == 1 && !kFused && t.w <= 8 && t.h <= 8) continue; // 8-bit PUs up to 8x8: hvb_me_small.cu, four per warp
         Search<Sample> s(t, planes, sSrc, lane);
         s.sMid = sScratch + 32;
         long long costMvdZero[2] = {0, 0};
@@ -823,10 +823,16 @@ extern "C" int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, i
     }
     else
     {
-        const int smem = kWarps * (kSrcWords + kExtraWords) * 4;
-        cudaFuncSetAttribute(meSearchKernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        meSearchKernel<uint16_t, true><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
+        // 16-bit samples: integer search a warp per PU, then the same sub-pel kernel (template on the sample type)
+        const int smem = kWarps * kSrcWords * 4;
+        cudaFuncSetAttribute(meSearchKernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        int perSm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, meSearchKernel<uint16_t, false>, kWarps * 32, smem);
+        blocks = min((n + kWarps - 1) / kWarps, ctx->smCount * max(perSm, 1));
+        meSearchKernel<uint16_t, false><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
         HVB_LAUNCH_CHECK(ctx, "meSearchKernel");
+        rc = hvbLaunchMeSubpel(ctx, dT, n, dO);
+        if (rc) return rc;
     }
     return hvbStageOut(ctx, out, sizeof(hvb_me_result) * n, mem, st);
 }

@@ -1,5 +1,6 @@
-// hvb_me_subpel.cu -- the sub-pel refinement of the uni-directional motion search for 8-bit pictures, as its
-// own kernel behind the integer search (hvb_me.cu): one launch refines every PU of the batch.
+// hvb_me_subpel.cu -- the sub-pel refinement of the uni-directional motion search as its own kernel behind the integer
+// search (hvb_me.cu): one launch refines every PU of the batch.  8-bit and 16-bit samples (template on the sample type;
+// the text below describes the 8-bit arithmetic, the 16-bit differences are noted where they occur).
 //
 // Reference semantics (bit-exact decisions):
 //   subPelRefinement / patternSearch / costMv / costDistortionMv   turing/Search.hpp:1965-2060, :2339-2357
@@ -38,31 +39,33 @@ constexpr int kGroup = 4;                 // units per group = PUs per warp chun
 constexpr int kColStride = 20;            // halfwords per mid column: 16 support rows + 4 (40 bytes: 8-byte aligned, odd/2 banks)
 constexpr int kPlaneHalfwords = 9 * kColStride;
 constexpr int kUnitMidBytes = 3 * kPlaneHalfwords * 2;      // 1080
-constexpr int kPredRow = 12;              // half-pel round: bytes per prediction row (9 columns + pad)
-constexpr int kPredPlane = 112;           // 9 rows x 12, padded
-constexpr int kUnitPredBytes = 512;       // half-pel: 4 planes x 112; quarter-pel: 8 candidates x 8 rows x 8
-constexpr int kUnitSrcBytes = 64;
+constexpr int kPredRow = 12;              // half-pel round: samples per prediction row (9 columns + pad)
+constexpr int kPredPlane = 112;           // 9 rows x 12, padded (samples)
+constexpr int kUnitPredSamples = 512;     // half-pel: 4 planes x 112; quarter-pel: 8 candidates x 8 rows x 8
+constexpr int kUnitSrcSamples = 64;
 
+template <typename Sample>
 struct UnitDesc
 {
-    const uint8_t *ref; // sample (0,0) of the unit in the reference plane at the integer part of the round's centre
+    const Sample *ref; // sample (0,0) of the unit in the reference plane at the integer part of the round's centre
     int slot;           // PU of the chunk (0..3) the unit belongs to
     int uwuh;           // uw | uh << 8 | valid << 16 (padding units of the last group repeat the last unit and are not summed)
 };
 
+template <typename Sample>
 struct WarpSmem
 {
     int16_t mids[kGroup][3 * kPlaneHalfwords];
-    uint8_t preds[kGroup][kUnitPredBytes];
-    uint8_t src[kGroup][kUnitSrcBytes];
-    UnitDesc unit[kGroup];
+    Sample preds[kGroup][kUnitPredSamples];
+    Sample src[kGroup][kUnitSrcSamples];
+    UnitDesc<Sample> unit[kGroup];
     int satd[kGroup][12];
     // per PU of the chunk
     int cx[kGroup], cy[kGroup];   // centre of the current round, quarter samples
     int units[kGroup];            // units of this PU in the current (round, tile mode) pass
     int geom[kGroup];             // uw | uh << 8 | unitsX << 16
-    const uint8_t *refBase[kGroup]; // sample (x0, y0) of the reference plane
-    const uint8_t *srcBase[kGroup];
+    const Sample *refBase[kGroup]; // sample (x0, y0) of the reference plane
+    const Sample *srcBase[kGroup];
     int stride[kGroup];           // reference stride; source stride in srcStride
     int srcStride[kGroup];
 };
@@ -83,16 +86,30 @@ __device__ __forceinline__ int dp4aUS(uint32_t a, uint32_t b, int c)
     return d;
 }
 
-__device__ __forceinline__ int clip8(int v) { return __vimin_s32_relu(v, 255); } // max(min(v, 255), 0), one VIMNMX
-
-__device__ __forceinline__ int vFilter(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t t0, uint32_t t1)
+// 8 taps over four (s16, s16) pairs
+__device__ __forceinline__ int tap8(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t t0, uint32_t t1, int acc)
 {
-    int acc = 1 << 11; // 2^(5 + shift3), shift3 = 6 at 8 bit
     acc = __dp2a_lo((int)p0, (int)t0, acc);
     acc = __dp2a_hi((int)p1, (int)t0, acc);
     acc = __dp2a_lo((int)p2, (int)t1, acc);
     acc = __dp2a_hi((int)p3, (int)t1, acc);
-    return clip8(acc >> 12);
+    return acc;
+}
+
+// arithmetic of one bit depth (havoc/pred_inter.cpp:76-110): shift1 = min(4, bd - 8), shift3 = max(2, 14 - bd)
+struct Depth
+{
+    int shift1, shift3, maxv;
+    __device__ __forceinline__ explicit Depth(int bd) : shift1(min(4, bd - 8)), shift3(max(2, 14 - bd)), maxv((1 << bd) - 1) {}
+    // second-stage output from the 8-tap sum of mids
+    __device__ __forceinline__ int out(int sum) const { return __vimin_s32_relu((sum + (1 << (5 + shift3))) >> (6 + shift3), maxv); }
+    // the same for a zero vertical phase (taps {0,0,0,64,..}) applied to one mid
+    __device__ __forceinline__ int outCopy(int mid) const { return __vimin_s32_relu((mid + (1 << (shift3 - 1))) >> shift3, maxv); }
+};
+
+__device__ __forceinline__ int vFilter(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t t0, uint32_t t1, const Depth &D)
+{
+    return D.out(tap8(p0, p1, p2, p3, t0, t1, 0));
 }
 
 __device__ __forceinline__ long long rateOfMvd(int dx, int dy)
@@ -126,86 +143,170 @@ struct HadamardA
     }
 };
 
-// 4 prediction bytes at `p + off` where p is word aligned and off is 0 or 1
-__device__ __forceinline__ uint32_t loadPred4(const uint8_t *p, int off)
+// B-fragment register(s) for 4 consecutive samples at `p + off` (p aligned to 4 samples, off = 0 or 1).
+// 8 bit: one word.  16 bit: the samples' low bytes and high bytes as two words (the products run on both planes).
+struct Frag
+{
+    uint32_t lo, hi;
+};
+__device__ __forceinline__ Frag loadFrag(const uint8_t *p, int off)
 {
     const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
     const uint32_t lo = q[0];
-    return off ? __funnelshift_r(lo, q[1], 8) : lo;
+    return Frag{off ? __funnelshift_r(lo, q[1], 8) : lo, 0u};
+}
+__device__ __forceinline__ Frag loadFrag(const uint16_t *p, int off)
+{
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
+    uint32_t x = q[0], y = q[1];
+    if (off)
+    {
+        const uint32_t z = q[2];
+        x = __funnelshift_r(x, y, 16);
+        y = __funnelshift_r(y, z, 16);
+    }
+    return Frag{__byte_perm(x, y, 0x6420), __byte_perm(x, y, 0x7531)};
 }
 
 // ---- H pass ---------------------------------------------------------------------------------------------------
 // HALF: plane 0 = integer samples << 6 (columns 0..uw-1), plane 1 = half-pel columns x - 1/2 (x = 0..uw), and the
 // candidates that need no vertical filter: P00 (plane 0 of preds) and PB (plane 1 of preds).
 // QUARTER: planes v = 0..2 at the horizontal quarter offsets hx + v - 1.
-template <bool HALF>
-__device__ __forceinline__ void hPass(WarpSmem &s, int lane)
+template <typename Sample, bool HALF>
+__device__ __forceinline__ void hPass(WarpSmem<Sample> &s, const Depth &D, int lane)
 {
 #pragma unroll 1
     for (int j = 0; j < 2; ++j)
     {
         const int job = lane + 32 * j, u = job >> 4, r = job & 15;
-        const UnitDesc d = s.unit[u];
+        const UnitDesc<Sample> d = s.unit[u];
         const int uw = d.uwuh & 0xff, uh = (d.uwuh >> 8) & 0xff;
         if (r >= uh + 8) continue;
         const int slot = d.slot;
-        const uint8_t *p = d.ref + (intptr_t)(r - 4) * s.stride[slot] - 4;
+        const Sample *p = d.ref + (intptr_t)(r - 4) * s.stride[slot] - 4;
         const uintptr_t a = reinterpret_cast<uintptr_t>(p);
         const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
         const unsigned sh = (unsigned)(a & 3) * 8;
-        uint32_t w[6], v[5];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) w[i] = __ldg(q + i);
-#pragma unroll
-        for (int i = 0; i < 5; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], sh);
         int16_t *mid = s.mids[u] + r;
-        if (HALF)
+        const bool body = r >= 4 && r < 4 + uh;
+        Sample *pb = s.preds[u] + kPredPlane + (r - 4) * kPredRow, *p00 = s.preds[u] + (r - 4) * kPredRow;
+        if (sizeof(Sample) == 1)
         {
-            const uint32_t t0 = kTapWords[2][0], t1 = kTapWords[2][1];
-            uint8_t *pb = s.preds[u] + kPredPlane + (r - 4) * kPredRow, *p00 = s.preds[u] + (r - 4) * kPredRow;
-            const bool body = r >= 4 && r < 4 + uh;
+            // 8 bit: 20 bytes of the row, every output two IDP.4A (u8 samples x s8 taps); shift1 = 0
+            uint32_t w[6], v[5];
 #pragma unroll
-            for (int c = 0; c < 9; ++c)
-                if (c <= uw)
-                {
-                    const int k = c >> 2, sft = (c & 3) * 8;
-                    const uint32_t lo = sft ? __funnelshift_r(v[k], v[k + 1], sft) : v[k];
-                    const uint32_t hi = sft ? __funnelshift_r(v[k + 1], v[k + 2 < 5 ? k + 2 : 4], sft) : v[k + 1];
-                    const int m = dp4aUS(hi, t1, dp4aUS(lo, t0, 0));
-                    mid[kPlaneHalfwords + c * kColStride] = (int16_t)m;
-                    if (body) pb[c] = (uint8_t)clip8((m + 32) >> 6);
-                }
+            for (int i = 0; i < 6; ++i) w[i] = __ldg(q + i);
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if (c < uw)
-                {
-                    const int smp = (v[(c + 4) >> 2] >> (((c + 4) & 3) * 8)) & 0xff;
-                    mid[c * kColStride] = (int16_t)(smp << 6);
-                    if (body) p00[c] = (uint8_t)smp;
-                }
-        }
-        else
-        {
-            const int hx = s.cx[slot] & 3;
-#pragma unroll 1
-            for (int pl = 0; pl < 3; ++pl)
+            for (int i = 0; i < 5; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], sh);
+            if (HALF)
             {
-                const int xq = hx + pl - 1, fx = xq & 3;
-                const uint32_t t0 = kTapWords[fx][0], t1 = kTapWords[fx][1];
-                // column c reads bytes c + (xq >> 2) + 1 .. + 8 of the row
-                uint32_t sv[4];
+                const uint32_t t0 = kTapWords[2][0], t1 = kTapWords[2][1];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) sv[i] = xq >= 0 ? __funnelshift_r(v[i], v[i + 1], 8) : v[i];
-                int16_t *mp = mid + pl * kPlaneHalfwords;
+                for (int c = 0; c < 9; ++c)
+                    if (c <= uw)
+                    {
+                        const int k = c >> 2, sft = (c & 3) * 8;
+                        const uint32_t lo = sft ? __funnelshift_r(v[k], v[k + 1], sft) : v[k];
+                        const uint32_t hi = sft ? __funnelshift_r(v[k + 1], v[k + 2 < 5 ? k + 2 : 4], sft) : v[k + 1];
+                        const int m = dp4aUS(hi, t1, dp4aUS(lo, t0, 0));
+                        mid[kPlaneHalfwords + c * kColStride] = (int16_t)m;
+                        if (body) pb[c] = (Sample)D.outCopy(m);
+                    }
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
                     if (c < uw)
                     {
-                        const int k = c >> 2, sft = (c & 3) * 8;
-                        const uint32_t lo = sft ? __funnelshift_r(sv[k], sv[k + 1], sft) : sv[k];
-                        const uint32_t hi = sft ? __funnelshift_r(sv[k + 1], sv[k + 2 < 4 ? k + 2 : 3], sft) : sv[k + 1];
-                        mp[c * kColStride] = (int16_t)dp4aUS(hi, t1, dp4aUS(lo, t0, 0));
+                        const int smp = (v[(c + 4) >> 2] >> (((c + 4) & 3) * 8)) & 0xff;
+                        mid[c * kColStride] = (int16_t)(smp << 6);
+                        if (body) p00[c] = (Sample)smp;
                     }
+            }
+            else
+            {
+                const int hx = s.cx[slot] & 3;
+#pragma unroll 1
+                for (int pl = 0; pl < 3; ++pl)
+                {
+                    const int xq = hx + pl - 1, fx = xq & 3;
+                    const uint32_t t0 = kTapWords[fx][0], t1 = kTapWords[fx][1];
+                    // column c reads bytes c + (xq >> 2) + 1 .. + 8 of the row
+                    uint32_t sv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) sv[i] = xq >= 0 ? __funnelshift_r(v[i], v[i + 1], 8) : v[i];
+                    int16_t *mp = mid + pl * kPlaneHalfwords;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (c < uw)
+                        {
+                            const int k = c >> 2, sft = (c & 3) * 8;
+                            const uint32_t lo = sft ? __funnelshift_r(sv[k], sv[k + 1], sft) : sv[k];
+                            const uint32_t hi = sft ? __funnelshift_r(sv[k + 1], sv[k + 2 < 4 ? k + 2 : 3], sft) : sv[k + 1];
+                            mp[c * kColStride] = (int16_t)dp4aUS(hi, t1, dp4aUS(lo, t0, 0));
+                        }
+                }
+            }
+        }
+        else
+        {
+            // 16 bit: 18 samples of the row as 9 words (two samples each), every output four IDP.2A (s16 samples x s8
+            // taps), then >> shift1
+            uint32_t w[10], v[9];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) w[i] = __ldg(q + i);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], sh);
+            if (HALF)
+            {
+                const uint32_t t0 = kTapWords[2][0], t1 = kTapWords[2][1];
+#pragma unroll
+                for (int c = 0; c < 9; ++c)
+                    if (c <= uw)
+                    {
+                        const int k = c >> 1;
+                        const bool odd = c & 1;
+                        const uint32_t p0 = odd ? __funnelshift_r(v[k], v[k + 1], 16) : v[k];
+                        const uint32_t p1 = odd ? __funnelshift_r(v[k + 1], v[k + 2], 16) : v[k + 1];
+                        const uint32_t p2 = odd ? __funnelshift_r(v[k + 2], v[k + 3], 16) : v[k + 2];
+                        const uint32_t p3 = odd ? __funnelshift_r(v[k + 3], v[k + 4 < 9 ? k + 4 : 8], 16) : v[k + 3];
+                        const int m = tap8(p0, p1, p2, p3, t0, t1, 0) >> D.shift1;
+                        mid[kPlaneHalfwords + c * kColStride] = (int16_t)m;
+                        if (body) pb[c] = (Sample)D.outCopy(m);
+                    }
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < uw)
+                    {
+                        const int smp = (v[(c + 4) >> 1] >> (((c + 4) & 1) * 16)) & 0xffff;
+                        mid[c * kColStride] = (int16_t)(smp << (6 - D.shift1));
+                        if (body) p00[c] = (Sample)smp;
+                    }
+            }
+            else
+            {
+                const int hx = s.cx[slot] & 3;
+#pragma unroll 1
+                for (int pl = 0; pl < 3; ++pl)
+                {
+                    const int xq = hx + pl - 1, fx = xq & 3;
+                    const uint32_t t0 = kTapWords[fx][0], t1 = kTapWords[fx][1];
+                    // column c reads samples c + (xq >> 2) + 1 .. + 8 of the row
+                    uint32_t sv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sv[i] = xq >= 0 ? __funnelshift_r(v[i], v[i + 1], 16) : v[i];
+                    int16_t *mp = mid + pl * kPlaneHalfwords;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (c < uw)
+                        {
+                            const int k = c >> 1;
+                            const bool odd = c & 1;
+                            const uint32_t p0 = odd ? __funnelshift_r(sv[k], sv[k + 1], 16) : sv[k];
+                            const uint32_t p1 = odd ? __funnelshift_r(sv[k + 1], sv[k + 2], 16) : sv[k + 1];
+                            const uint32_t p2 = odd ? __funnelshift_r(sv[k + 2], sv[k + 3], 16) : sv[k + 2];
+                            const uint32_t p3 = odd ? __funnelshift_r(sv[k + 3], sv[k + 4 < 8 ? k + 4 : 7], 16) : sv[k + 3];
+                            mp[c * kColStride] = (int16_t)(tap8(p0, p1, p2, p3, t0, t1, 0) >> D.shift1);
+                        }
+                }
             }
         }
     }
@@ -236,17 +337,18 @@ struct Column
         for (int i = 0; i < 7; ++i) x[i] = __funnelshift_r(w[i], w[i + 1], 16);
     }
     template <int R>
-    __device__ __forceinline__ int out(uint32_t t0, uint32_t t1) const
+    __device__ __forceinline__ int out(uint32_t t0, uint32_t t1, const Depth &D) const
     {
         constexpr int k = R >> 1;
-        if (R & 1) return vFilter(x[k], x[k + 1], x[k + 2], x[k + 3 < 7 ? k + 3 : 6], t0, t1);
-        return vFilter(w[k], w[k + 1], w[k + 2], w[k + 3 < 8 ? k + 3 : 7], t0, t1);
+        if (R & 1) return vFilter(x[k], x[k + 1], x[k + 2], x[k + 3 < 7 ? k + 3 : 6], t0, t1, D);
+        return vFilter(w[k], w[k + 1], w[k + 2], w[k + 3 < 8 ? k + 3 : 7], t0, t1, D);
     }
 };
 
 // ---- V pass, half-pel round: PC (plane 2 of preds) = vertical half-pel of the integer columns, (uh+1) x uw;
 // PD (plane 3) = vertical half-pel of the half-pel columns, (uh+1) x (uw+1).  17 column jobs per unit.
-__device__ __forceinline__ void vPassHalf(WarpSmem &s, int lane)
+template <typename Sample>
+__device__ __forceinline__ void vPassHalf(WarpSmem<Sample> &s, const Depth &D, int lane)
 {
     const uint32_t t0 = kTapWords[2][0], t1 = kTapWords[2][1];
 #pragma unroll 1
@@ -260,56 +362,58 @@ __device__ __forceinline__ void vPassHalf(WarpSmem &s, int lane)
         if (c >= uw + pd) continue;
         Column col;
         col.load(s.mids[u] + pd * kPlaneHalfwords + c * kColStride, 0);
-        uint8_t *dst = s.preds[u] + (2 + pd) * kPredPlane + c;
+        Sample *dst = s.preds[u] + (2 + pd) * kPredPlane + c;
         // rows 0..uh: output r is the half-sample position between picture rows r-1 and r
-        dst[0 * kPredRow] = (uint8_t)col.out<0>(t0, t1);
-        dst[1 * kPredRow] = (uint8_t)col.out<1>(t0, t1);
-        dst[2 * kPredRow] = (uint8_t)col.out<2>(t0, t1);
-        dst[3 * kPredRow] = (uint8_t)col.out<3>(t0, t1);
-        dst[4 * kPredRow] = (uint8_t)col.out<4>(t0, t1);
+        dst[0 * kPredRow] = (Sample)col.out<0>(t0, t1, D);
+        dst[1 * kPredRow] = (Sample)col.out<1>(t0, t1, D);
+        dst[2 * kPredRow] = (Sample)col.out<2>(t0, t1, D);
+        dst[3 * kPredRow] = (Sample)col.out<3>(t0, t1, D);
+        dst[4 * kPredRow] = (Sample)col.out<4>(t0, t1, D);
         if (uh > 4)
         {
-            dst[5 * kPredRow] = (uint8_t)col.out<5>(t0, t1);
-            dst[6 * kPredRow] = (uint8_t)col.out<6>(t0, t1);
-            dst[7 * kPredRow] = (uint8_t)col.out<7>(t0, t1);
-            dst[8 * kPredRow] = (uint8_t)col.out<8>(t0, t1);
+            dst[5 * kPredRow] = (Sample)col.out<5>(t0, t1, D);
+            dst[6 * kPredRow] = (Sample)col.out<6>(t0, t1, D);
+            dst[7 * kPredRow] = (Sample)col.out<7>(t0, t1, D);
+            dst[8 * kPredRow] = (Sample)col.out<8>(t0, t1, D);
         }
     }
 }
 
 // ---- V pass, quarter-pel round: candidate q (grid index gi = q + (q >= 4)) = plane gi % 3 at the vertical quarter
 // offset hy + gi / 3 - 1; (unit, candidate, column) jobs; preds[u][q][r][c], 8 bytes per row.
-__device__ __forceinline__ void vPassQuarter(WarpSmem &s, int lane)
+template <typename Sample>
+__device__ __forceinline__ void vPassQuarter(WarpSmem<Sample> &s, const Depth &D, int lane)
 {
 #pragma unroll 1
     for (int it = 0; it < 8; ++it)
     {
         const int job = lane + 32 * it, u = job >> 6, q = (job >> 3) & 7, c = job & 7;
-        const UnitDesc d = s.unit[u];
+        const UnitDesc<Sample> d = s.unit[u];
         const int uw = d.uwuh & 0xff, uh = (d.uwuh >> 8) & 0xff;
         if (c >= uw) continue;
         const int gi = q + (q >= 4), pl = gi % 3, yq = (s.cy[d.slot] & 3) + gi / 3 - 1;
         const uint32_t t0 = kTapWords[yq & 3][0], t1 = kTapWords[yq & 3][1];
         Column col;
         col.load(s.mids[u] + pl * kPlaneHalfwords + c * kColStride, (yq >> 2) + 1);
-        uint8_t *dst = s.preds[u] + q * 64 + c;
-        dst[0 * 8] = (uint8_t)col.out<0>(t0, t1);
-        dst[1 * 8] = (uint8_t)col.out<1>(t0, t1);
-        dst[2 * 8] = (uint8_t)col.out<2>(t0, t1);
-        dst[3 * 8] = (uint8_t)col.out<3>(t0, t1);
+        Sample *dst = s.preds[u] + q * 64 + c;
+        dst[0 * 8] = (Sample)col.out<0>(t0, t1, D);
+        dst[1 * 8] = (Sample)col.out<1>(t0, t1, D);
+        dst[2 * 8] = (Sample)col.out<2>(t0, t1, D);
+        dst[3 * 8] = (Sample)col.out<3>(t0, t1, D);
         if (uh > 4)
         {
-            dst[4 * 8] = (uint8_t)col.out<4>(t0, t1);
-            dst[5 * 8] = (uint8_t)col.out<5>(t0, t1);
-            dst[6 * 8] = (uint8_t)col.out<6>(t0, t1);
-            dst[7 * 8] = (uint8_t)col.out<7>(t0, t1);
+            dst[4 * 8] = (Sample)col.out<4>(t0, t1, D);
+            dst[5 * 8] = (Sample)col.out<5>(t0, t1, D);
+            dst[6 * 8] = (Sample)col.out<6>(t0, t1, D);
+            dst[7 * 8] = (Sample)col.out<7>(t0, t1, D);
         }
     }
 }
 
 // where candidate gi of the half-pel round lives: pointer to its sample (0,0) rounded down to a word, and the
-// byte offset (0 or 1) of its columns
-__device__ __forceinline__ const uint8_t *halfCand(const uint8_t *preds, int gi, int &off)
+// sample offset (0 or 1) of its columns
+template <typename Sample>
+__device__ __forceinline__ const Sample *halfCand(const Sample *preds, int gi, int &off)
 {
     const int dxi = gi % 3, dyi = gi / 3;
     const int plane = dxi == 1 ? (dyi == 1 ? 0 : 2) : (dyi == 1 ? 1 : 3);
@@ -318,11 +422,12 @@ __device__ __forceinline__ const uint8_t *halfCand(const uint8_t *preds, int gi,
 }
 
 // ---- SATD of every (unit, candidate) of the group on the tensor cores -----------------------------------------
-template <bool HALF, bool T8>
-__device__ __forceinline__ void satdPass(WarpSmem &s, const HadamardA &A, int lane)
+template <typename Sample, bool HALF, bool T8>
+__device__ __forceinline__ void satdPass(WarpSmem<Sample> &s, const HadamardA &A, int lane)
 {
     constexpr int ncand = HALF ? 9 : 8;
     constexpr int ncols = kGroup * ncand * (T8 ? 1 : 2);
+    constexpr bool k16 = sizeof(Sample) == 2;
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll 1
     for (int base = 0; base < ncols; base += 8)
@@ -334,7 +439,7 @@ __device__ __forceinline__ void satdPass(WarpSmem &s, const HadamardA &A, int la
         const int gi = HALF ? cand : cand + (cand >= 4);
         const int uw = s.unit[u].uwuh & 0xff;
         int off = 0, prow = 8;
-        const uint8_t *P;
+        const Sample *P;
         if (HALF)
         {
             P = halfCand(s.preds[u], gi, off);
@@ -342,33 +447,37 @@ __device__ __forceinline__ void satdPass(WarpSmem &s, const HadamardA &A, int la
         }
         else
             P = s.preds[u] + cand * 64;
-        const uint8_t *S = s.src[u];
+        const Sample *S = s.src[u];
         int s0, s1;
         if (T8)
         {
             // k = 32 ks + 4 t + j (+16): tile row 4 ks + (t >> 1) (+2), tile column 4 (t & 1) + j
             const int row = t >> 1, cx = (t & 1) * 4;
-            uint32_t b[4][2];
+            Frag b[4][2];
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks)
             {
-                b[ks][0] = *reinterpret_cast<const uint32_t *>(S + (ks * 4 + row) * 8 + cx);
-                b[ks][1] = *reinterpret_cast<const uint32_t *>(S + (ks * 4 + row + 2) * 8 + cx);
-                b[ks + 2][0] = loadPred4(P + (ks * 4 + row) * prow + cx, off);
-                b[ks + 2][1] = loadPred4(P + (ks * 4 + row + 2) * prow + cx, off);
+                b[ks][0] = loadFrag(S + (ks * 4 + row) * 8 + cx, 0);
+                b[ks][1] = loadFrag(S + (ks * 4 + row + 2) * 8 + cx, 0);
+                b[ks + 2][0] = loadFrag(P + (ks * 4 + row) * prow + cx, off);
+                b[ks + 2][1] = loadFrag(P + (ks * 4 + row + 2) * prow + cx, off);
             }
             s0 = s1 = 0;
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt)
             {
-                int acc[4] = {0, 0, 0, 0};
+                int acc[4] = {0, 0, 0, 0}, ach[4] = {0, 0, 0, 0};
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                 {
                     const int n01 = (((mt >> 1) & ks) ^ (ks >> 1)) & 1; // bit 5 of m & k, and the prediction half of [H | -H]
                     const int n23 = n01 ^ (mt & 1);                     // bit 4 of m & k
-                    imma16832(acc, A.e[n01], A.o[n01], A.e[n23], A.o[n23], b[ks][0], b[ks][1]);
+                    imma16832(acc, A.e[n01], A.o[n01], A.e[n23], A.o[n23], b[ks][0].lo, b[ks][1].lo);
+                    if (k16) imma16832(ach, A.e[n01], A.o[n01], A.e[n23], A.o[n23], b[ks][0].hi, b[ks][1].hi);
                 }
+                if (k16)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc[r] += ach[r] << 8;
                 s0 = __sad(acc[0], 0, __sad(acc[2], 0, (unsigned)s0));
                 s1 = __sad(acc[1], 0, __sad(acc[3], 0, (unsigned)s1));
             }
@@ -377,10 +486,17 @@ __device__ __forceinline__ void satdPass(WarpSmem &s, const HadamardA &A, int la
         {
             // two 4x4 tiles per unit: side by side in an 8x4 unit, stacked in a 4x8 unit; K = 16 + 16 is one k-step
             const int tx = uw == 8 ? tile * 4 : 0, ty = uw == 8 ? 0 : tile * 4;
-            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(S + (ty + t) * 8 + tx);
-            const uint32_t b1 = loadPred4(P + (ty + t) * prow + tx, off);
+            const Frag b0 = loadFrag(S + (ty + t) * 8 + tx, 0);
+            const Frag b1 = loadFrag(P + (ty + t) * prow + tx, off);
             int acc[4] = {0, 0, 0, 0};
-            imma16832(acc, A.e[0], A.o[0], A.e[1], A.o[1], b0, b1);
+            imma16832(acc, A.e[0], A.o[0], A.e[1], A.o[1], b0.lo, b1.lo);
+            if (k16)
+            {
+                int ach[4] = {0, 0, 0, 0};
+                imma16832(ach, A.e[0], A.o[0], A.e[1], A.o[1], b0.hi, b1.hi);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[r] += ach[r] << 8;
+            }
             s0 = __sad(acc[0], 0, __sad(acc[2], 0, 0u));
             s1 = __sad(acc[1], 0, __sad(acc[3], 0, 0u));
         }
@@ -392,7 +508,8 @@ __device__ __forceinline__ void satdPass(WarpSmem &s, const HadamardA &A, int la
         sum += __shfl_xor_sync(0xffffffffu, sum, 16);
         if (g < 2)
         {
-            // havoc/hadamard.cpp:81-97: 4x4 (s + 1) >> 1, 8x8 (s + 2) >> 2; lane (g, t) reports column base + 2t + g
+            // havoc/hadamard.cpp:81-97: 4x4 (s + 1) >> 1, 8x8 (s + 2) >> 2, 16-bit samples >> 2 more; lane (g, t) reports
+            // column base + 2t + g
             const int c2 = base + 2 * t + g;
             if (c2 < ncols)
             {
@@ -400,7 +517,8 @@ __device__ __forceinline__ void satdPass(WarpSmem &s, const HadamardA &A, int la
                 const int u2 = HALF ? (uc2 * 7282) >> 16 : uc2 >> 3;
                 const int cand2 = uc2 - u2 * ncand;
                 const int slot = s.unit[u2].slot;
-                const int v = (sum + (T8 ? 2 : 1)) >> (T8 ? 2 : 1);
+                int v = (sum + (T8 ? 2 : 1)) >> (T8 ? 2 : 1);
+                if (k16) v >>= 2;
                 if (s.unit[u2].uwuh >> 16) atomicAdd(&s.satd[slot][HALF ? cand2 : cand2 + (cand2 >= 4)], v);
             }
         }
@@ -408,8 +526,8 @@ __device__ __forceinline__ void satdPass(WarpSmem &s, const HadamardA &A, int la
 }
 
 // one round over every unit of the chunk's PUs of one tile mode
-template <bool HALF, bool T8>
-__device__ __forceinline__ void roundPass(WarpSmem &s, const HadamardA &A, int lane)
+template <typename Sample, bool HALF, bool T8>
+__device__ __forceinline__ void roundPass(WarpSmem<Sample> &s, const HadamardA &A, const Depth &D, int lane)
 {
     // units of the participating PUs, concatenated
     const int n0 = s.units[0], n1 = n0 + s.units[1], n2 = n1 + s.units[2], total = n2 + s.units[3];
@@ -424,14 +542,14 @@ __device__ __forceinline__ void roundPass(WarpSmem &s, const HadamardA &A, int l
             const int local = uid - (slot == 0 ? 0 : slot == 1 ? n0 : slot == 2 ? n1 : n2);
             const int geom = s.geom[slot], uw = geom & 0xff, uh = (geom >> 8) & 0xff, unitsX = geom >> 16;
             const int uy = local / unitsX, ux = local - uy * unitsX;
-            UnitDesc d;
+            UnitDesc<Sample> d;
             d.ref = s.refBase[slot] + (intptr_t)(uy * uh + (s.cy[slot] >> 2)) * s.stride[slot] + ux * uw + (s.cx[slot] >> 2);
             d.slot = slot;
             d.uwuh = (geom & 0xffff) | (id < total) << 16;
             s.unit[lane] = d;
         }
         {
-            // the source units: 4 x 8 rows of 8 bytes
+            // the source units: 4 x 8 rows of 8 samples
             const int u = lane >> 3, r = lane & 7;
             const int id = min(base + u, total - 1);
             const int slot = (id >= n0) + (id >= n1) + (id >= n2);
@@ -440,32 +558,38 @@ __device__ __forceinline__ void roundPass(WarpSmem &s, const HadamardA &A, int l
             const int uy = local / unitsX, ux = local - uy * unitsX;
             if (r < uh)
             {
+                // x0 is a multiple of 4 samples and the plane rows are 256-byte aligned: word loads (two words per 4 samples at 16 bit)
                 const uint32_t *sp = reinterpret_cast<const uint32_t *>(s.srcBase[slot] + (intptr_t)(uy * uh + r) * s.srcStride[slot] + ux * uw);
                 uint32_t *dp = reinterpret_cast<uint32_t *>(s.src[u] + r * 8);
-                dp[0] = __ldg(sp);
-                if (uw == 8) dp[1] = __ldg(sp + 1);
+                constexpr int kWordsPer4 = sizeof(Sample); // words per 4 samples
+#pragma unroll
+                for (int k = 0; k < 2 * kWordsPer4; ++k)
+                    if (k < kWordsPer4 || uw == 8) dp[k] = __ldg(sp + k);
             }
         }
         __syncwarp();
-        hPass<HALF>(s, lane);
+        hPass<Sample, HALF>(s, D, lane);
         __syncwarp();
         if (HALF)
-            vPassHalf(s, lane);
+            vPassHalf(s, D, lane);
         else
-            vPassQuarter(s, lane);
+            vPassQuarter(s, D, lane);
         __syncwarp();
-        satdPass<HALF, T8>(s, A, lane);
+        satdPass<Sample, HALF, T8>(s, A, lane);
         __syncwarp();
     }
 }
 
+template <typename Sample>
 __global__ void __launch_bounds__(kWarps * 32)
-    meSubpelKernel(const HvbPlane *__restrict__ planes, const hvb_me_task *__restrict__ tasks, int n, hvb_me_result *__restrict__ out)
+    meSubpelKernel(const HvbPlane *__restrict__ planes, const hvb_me_task *__restrict__ tasks, int n, hvb_me_result *__restrict__ out,
+                   int bitDepth)
 {
     extern __shared__ __align__(16) uint8_t smemSubpel[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpSmem &s = reinterpret_cast<WarpSmem *>(smemSubpel)[warp];
+    WarpSmem<Sample> &s = reinterpret_cast<WarpSmem<Sample> *>(smemSubpel)[warp];
     const HadamardA A(lane);
+    const Depth D(sizeof(Sample) == 1 ? 8 : bitDepth);
     const int chunks = (n + kGroup - 1) / kGroup, warpsTotal = gridDim.x * kWarps;
     for (int chunk = blockIdx.x * kWarps + warp; chunk < chunks; chunk += warpsTotal)
     {
@@ -487,8 +611,8 @@ __global__ void __launch_bounds__(kWarps * 32)
             mv = out[i].mv; // the integer search left its winner here
             mvd = out[i].mvd;
             const HvbPlane &sp = planes[t.src_pic * 3], &rp = planes[t.ref_pic * 3];
-            s.refBase[lane] = reinterpret_cast<const uint8_t *>(rp.base) + (intptr_t)t.y0 * rp.stride + t.x0;
-            s.srcBase[lane] = reinterpret_cast<const uint8_t *>(sp.base) + (intptr_t)t.y0 * sp.stride + t.x0;
+            s.refBase[lane] = reinterpret_cast<const Sample *>(rp.base) + (intptr_t)t.y0 * rp.stride + t.x0;
+            s.srcBase[lane] = reinterpret_cast<const Sample *>(sp.base) + (intptr_t)t.y0 * sp.stride + t.x0;
             s.stride[lane] = rp.stride;
             s.srcStride[lane] = sp.stride;
             const int uw = tiles8 ? 8 : ((w & 7) ? 4 : 8), uh = tiles8 ? 8 : (uw == 8 ? 4 : 8);
@@ -523,16 +647,16 @@ __global__ void __launch_bounds__(kWarps * 32)
                 if (round == 0)
                 {
                     if (mode == 0)
-                        roundPass<true, true>(s, A, lane);
+                        roundPass<Sample, true, true>(s, A, D, lane);
                     else
-                        roundPass<true, false>(s, A, lane);
+                        roundPass<Sample, true, false>(s, A, D, lane);
                 }
                 else
                 {
                     if (mode == 0)
-                        roundPass<false, true>(s, A, lane);
+                        roundPass<Sample, false, true>(s, A, D, lane);
                     else
-                        roundPass<false, false>(s, A, lane);
+                        roundPass<Sample, false, false>(s, A, D, lane);
                 }
             }
             __syncwarp();
@@ -577,19 +701,25 @@ __global__ void __launch_bounds__(kWarps * 32)
 
 } // namespace
 
-// called by hvb_me_search_batch (hvb_me.cu) after the integer search of an 8-bit batch, on the same stream
-int hvbLaunchMeSubpel(hvb_context *ctx, const hvb_me_task *dTasks, int n, hvb_me_result *dOut)
+// called by hvb_me_search_batch (hvb_me.cu) after the integer search, on the same stream
+template <typename Sample>
+static int launchMeSubpel(hvb_context *ctx, const hvb_me_task *dTasks, int n, hvb_me_result *dOut)
 {
     const int chunks = (n + kGroup - 1) / kGroup;
     int blocks = (chunks + kWarps - 1) / kWarps;
-    const int smem = kWarps * (int)sizeof(WarpSmem);
-    static_assert(sizeof(WarpSmem) % 16 == 0, "per-warp shared slices must stay 16-byte aligned");
-    cudaFuncSetAttribute(meSubpelKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = kWarps * (int)sizeof(WarpSmem<Sample>);
+    static_assert(sizeof(WarpSmem<Sample>) % 16 == 0, "per-warp shared slices must stay 16-byte aligned");
+    cudaFuncSetAttribute(meSubpelKernel<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int perSm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, meSubpelKernel, kWarps * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, meSubpelKernel<Sample>, kWarps * 32, smem);
     const int cap = ctx->smCount * (perSm > 0 ? perSm : 1);
     if (blocks > cap) blocks = cap;
-    meSubpelKernel<<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dTasks, n, dOut);
+    meSubpelKernel<Sample><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dTasks, n, dOut, ctx->bitDepth);
     HVB_LAUNCH_CHECK(ctx, "meSubpelKernel");
     return HVB_OK;
+}
+
+int hvbLaunchMeSubpel(hvb_context *ctx, const hvb_me_task *dTasks, int n, hvb_me_result *dOut)
+{
+    return ctx->bps == 1 ? launchMeSubpel<uint8_t>(ctx, dTasks, n, dOut) : launchMeSubpel<uint16_t>(ctx, dTasks, n, dOut);
 }
