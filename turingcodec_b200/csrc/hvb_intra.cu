@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 }
 
 
-// ---- 8-bit sweep: predictions to shared memory row by row, SATD on the integer tensor cores --------------------
+// ---- the sweep: predictions to shared memory row by row, SATD on the integer tensor cores (8- and 16-bit samples) ----
 //
 // The sum of absolute Hadamard coefficients of a tile equals that of the transposed tile, and a horizontal mode's
 // prediction is the transpose of the vertical mode 36 - m evaluated on mirrored neighbours (left <-> top).  So
@@ -230,12 +230,13 @@ __global__ void __launch_bounds__(kWarps * 32)
 // the (projected) reference.  A lane owns one (mode, tile row); the T predicted bytes go to shared memory where
 // the (mode, tile) blocks are the B fragments of a [H | -H] x [src ; pred] IMMA, 8 modes at a time
 // (hvb_me_subpel.cu has the same construction).
+template <typename Sample>
 struct SweepSmem
 {
     int16_t front[8]; // mode 2's last row computes index -1 of U for a weight-0 sample; keep it inside the struct
     int16_t U[kNbMax + 7], F[kNbMax + 7];
-    uint8_t pred[35][64];
-    uint8_t src[2][64]; // [0] the tile, [1] the transposed source's tile
+    Sample pred[35][64];
+    Sample src[2][64]; // [0] the tile, [1] the transposed source's tile
     int sum[36];
 };
 
@@ -272,9 +273,33 @@ __device__ __forceinline__ int columnSums(int s0, int s1, int g)
     return sum;
 }
 
+// B-fragment register(s) for 4 consecutive samples at p (aligned to 4 samples): 8 bit one word; 16 bit the low bytes and
+// the high bytes as two words, the product runs on both planes and the sums are recombined (hvb_me_subpel.cu)
+struct SweepFrag
+{
+    uint32_t lo, hi;
+};
+__device__ __forceinline__ SweepFrag sweepFrag(const uint8_t *p) { return SweepFrag{*reinterpret_cast<const uint32_t *>(p), 0u}; }
+__device__ __forceinline__ SweepFrag sweepFrag(const uint16_t *p)
+{
+    const uint2 w = *reinterpret_cast<const uint2 *>(p);
+    return SweepFrag{__byte_perm(w.x, w.y, 0x6420), __byte_perm(w.x, w.y, 0x7531)};
+}
+__device__ __forceinline__ void storeRow4(uint8_t *p, const int (&o)[4]) { *reinterpret_cast<uint32_t *>(p) = o[0] | o[1] << 8 | o[2] << 16 | o[3] << 24; }
+__device__ __forceinline__ void storeRow4(uint16_t *p, const int (&o)[4]) { *reinterpret_cast<uint2 *>(p) = make_uint2(o[0] | o[1] << 16, o[2] | o[3] << 16); }
+__device__ __forceinline__ void storeRow8(uint8_t *p, const int (&o)[8])
+{
+    *reinterpret_cast<uint2 *>(p) = make_uint2(o[0] | o[1] << 8 | o[2] << 16 | o[3] << 24, o[4] | o[5] << 8 | o[6] << 16 | o[7] << 24);
+}
+__device__ __forceinline__ void storeRow8(uint16_t *p, const int (&o)[8])
+{
+    *reinterpret_cast<uint4 *>(p) = make_uint4(o[0] | o[1] << 16, o[2] | o[3] << 16, o[4] | o[5] << 16, o[6] | o[7] << 16);
+}
+
 // T samples of row yy, columns x0 .. x0+T-1, of mode `mode` in its own frame (transposed for modes 2..17)
-template <int T>
-__device__ __forceinline__ void sweepRow(const SweepSmem &s, int mode, int cIdx, int log2n, int dc, bool edge, int x0, int yy, int (&out)[T])
+template <int T, typename Sample>
+__device__ __forceinline__ void sweepRow(const SweepSmem<Sample> &s, int mode, int cIdx, int log2n, int dc, bool edge, int maxv, int x0, int yy,
+                                         int (&out)[T])
 {
     const int n = 1 << log2n, c = 2 * n;
     const int16_t *A = filterFlag(cIdx, mode, n) ? s.F : s.U;
@@ -302,7 +327,7 @@ __device__ __forceinline__ void sweepRow(const SweepSmem &s, int mode, int cIdx,
         {
             // pred_intra.cpp:20354-20358 / :20392-20396; for mode 10 in the mirrored frame the roles of top and left swap
             const int top0 = vertical ? A[c + 1] : A[c - 1], side = vertical ? A[c - 1 - yy] : A[c + 1 + yy];
-            out[0] = hvbClip3(0, 255, top0 + ((side - A[c]) >> 1));
+            out[0] = hvbClip3(0, maxv, top0 + ((side - A[c]) >> 1));
         }
     }
     else if (mode == 1)
@@ -336,13 +361,16 @@ __device__ __forceinline__ void sweepRow(const SweepSmem &s, int mode, int cIdx,
     }
 }
 
+template <typename Sample>
 __global__ void __launch_bounds__(kWarps * 32)
-    intraSweepKernel8(const HvbPlane *__restrict__ planes, const uint8_t *__restrict__ pool, const hvb_intra_sweep_task *__restrict__ tasks,
-                      int n, int32_t *__restrict__ out)
+    intraSweepKernel8(const HvbPlane *__restrict__ planes, const Sample *__restrict__ pool, const hvb_intra_sweep_task *__restrict__ tasks,
+                      int n, int32_t *__restrict__ out, int bitDepth)
 {
-    __shared__ __align__(16) SweepSmem sAll[kWarps];
+    __shared__ __align__(16) SweepSmem<Sample> sAll[kWarps];
+    constexpr bool k16 = sizeof(Sample) == 2;
+    const int maxv = (1 << bitDepth) - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    SweepSmem &s = sAll[warp];
+    SweepSmem<Sample> &s = sAll[warp];
     const HadamardA8 A(lane);
     const int g = lane >> 2, tq = lane & 3;
     const int warpsTotal = gridDim.x * kWarps;
@@ -359,13 +387,13 @@ __global__ void __launch_bounds__(kWarps * 32)
             s.U[4 * nn + 1 + lane] = s.F[4 * nn + 1 + lane] = 0;
         for (int k = lane; k < 36; k += 32) s.sum[k] = 0;
         __syncwarp();
-        if (t.nb_filtered < 0) filterNeighbours(s.F, s.U, nn, 8, t.strong_intra_smoothing != 0, lane);
+        if (t.nb_filtered < 0) filterNeighbours(s.F, s.U, nn, bitDepth, t.strong_intra_smoothing != 0, lane);
         __syncwarp();
         const Neighbours nbU{s.U, 2 * nn};
         const int dc = dcValue(nbU, log2n, lane);
         const bool edge = t.cIdx == 0 && log2n < 5;
         int ss;
-        const uint8_t *src = hvbBlockPtr<uint8_t>(planes, t.src, ss);
+        const Sample *src = hvbBlockPtr<Sample>(planes, t.src, ss);
 
         if (log2n == 2)
         {
@@ -373,7 +401,7 @@ __global__ void __launch_bounds__(kWarps * 32)
             if (lane < 16)
             {
                 const int r = lane >> 2, cc = lane & 3;
-                const uint8_t v = src[r * ss + cc];
+                const Sample v = src[r * ss + cc];
                 s.src[0][r * 4 + cc] = v;
                 s.src[1][cc * 4 + r] = v;
             }
@@ -381,22 +409,28 @@ __global__ void __launch_bounds__(kWarps * 32)
             {
                 const int mode = job >> 2, r = job & 3;
                 int o[4];
-                sweepRow<4>(s, mode, t.cIdx, 2, dc, edge, 0, r, o);
-                *reinterpret_cast<uint32_t *>(&s.pred[mode][r * 4]) = o[0] | o[1] << 8 | o[2] << 16 | o[3] << 24;
+                sweepRow<4>(s, mode, t.cIdx, 2, dc, edge, maxv, 0, r, o);
+                storeRow4(&s.pred[mode][r * 4], o);
             }
             __syncwarp();
 #pragma unroll 1
             for (int base = 0; base < 40; base += 8)
             {
                 const int mode = min(base + g, 34);
-                const uint8_t *S = s.src[mode >= 2 && mode < 18];
-                const uint32_t b0 = *reinterpret_cast<const uint32_t *>(S + tq * 4);
-                const uint32_t b1 = *reinterpret_cast<const uint32_t *>(&s.pred[mode][tq * 4]);
+                const Sample *S = s.src[mode >= 2 && mode < 18];
+                const SweepFrag b0 = sweepFrag(S + tq * 4), b1 = sweepFrag(&s.pred[mode][tq * 4]);
                 int acc[4] = {0, 0, 0, 0};
-                imma16832(acc, A.e[0], A.o[0], A.e[1], A.o[1], b0, b1);
+                imma16832(acc, A.e[0], A.o[0], A.e[1], A.o[1], b0.lo, b1.lo);
+                if (k16)
+                {
+                    int ach[4] = {0, 0, 0, 0};
+                    imma16832(ach, A.e[0], A.o[0], A.e[1], A.o[1], b0.hi, b1.hi);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc[r] += ach[r] << 8;
+                }
                 int s0 = __sad(acc[0], 0, __sad(acc[2], 0, 0u)), s1 = __sad(acc[1], 0, __sad(acc[3], 0, 0u));
                 const int sum = columnSums(s0, s1, g);
-                if (g < 2 && base + 2 * tq + g < 35) s.sum[base + 2 * tq + g] = (sum + 1) >> 1;
+                if (g < 2 && base + 2 * tq + g < 35) s.sum[base + 2 * tq + g] = ((sum + 1) >> 1) >> (k16 ? 2 : 0);
             }
         }
         else
@@ -410,9 +444,10 @@ __global__ void __launch_bounds__(kWarps * 32)
                     {
                         // the tile (two words per row) and the tile of the transposed source at the same tile coordinates
                         const int r = lane >> 2, cc = (lane & 3) * 2;
-                        const uint8_t *p = src + (ty * 8 + r) * ss + tx * 8 + cc;
-                        *reinterpret_cast<uint16_t *>(&s.src[0][r * 8 + cc]) = *reinterpret_cast<const uint16_t *>(p);
-                        const uint8_t *q = src + (tx * 8 + cc) * ss + ty * 8 + r; // srcT(x = tx*8+cc, y = ty*8+r) = src(x = ty*8+r, y = tx*8+cc)
+                        const Sample *p = src + (ty * 8 + r) * ss + tx * 8 + cc;
+                        s.src[0][r * 8 + cc] = p[0];
+                        s.src[0][r * 8 + cc + 1] = p[1];
+                        const Sample *q = src + (tx * 8 + cc) * ss + ty * 8 + r; // srcT(x = tx*8+cc, y = ty*8+r) = src(x = ty*8+r, y = tx*8+cc)
                         s.src[1][r * 8 + cc] = q[0];
                         s.src[1][r * 8 + cc + 1] = q[ss];
                     }
@@ -420,44 +455,45 @@ __global__ void __launch_bounds__(kWarps * 32)
                     {
                         const int mode = job >> 3, r = job & 7;
                         int o[8];
-                        sweepRow<8>(s, mode, t.cIdx, log2n, dc, edge, tx * 8, ty * 8 + r, o);
-                        uint2 w;
-                        w.x = o[0] | o[1] << 8 | o[2] << 16 | o[3] << 24;
-                        w.y = o[4] | o[5] << 8 | o[6] << 16 | o[7] << 24;
-                        *reinterpret_cast<uint2 *>(&s.pred[mode][r * 8]) = w;
+                        sweepRow<8>(s, mode, t.cIdx, log2n, dc, edge, maxv, tx * 8, ty * 8 + r, o);
+                        storeRow8(&s.pred[mode][r * 8], o);
                     }
                     __syncwarp();
 #pragma unroll 1
                     for (int base = 0; base < 40; base += 8)
                     {
                         const int mode = min(base + g, 34);
-                        const uint8_t *S = s.src[mode >= 2 && mode < 18], *P = s.pred[mode];
+                        const Sample *S = s.src[mode >= 2 && mode < 18], *P = s.pred[mode];
                         const int row = tq >> 1, cx = (tq & 1) * 4;
-                        uint32_t b[4][2];
+                        SweepFrag b[4][2];
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks)
                         {
-                            b[ks][0] = *reinterpret_cast<const uint32_t *>(S + (ks * 4 + row) * 8 + cx);
-                            b[ks][1] = *reinterpret_cast<const uint32_t *>(S + (ks * 4 + row + 2) * 8 + cx);
-                            b[ks + 2][0] = *reinterpret_cast<const uint32_t *>(P + (ks * 4 + row) * 8 + cx);
-                            b[ks + 2][1] = *reinterpret_cast<const uint32_t *>(P + (ks * 4 + row + 2) * 8 + cx);
+                            b[ks][0] = sweepFrag(S + (ks * 4 + row) * 8 + cx);
+                            b[ks][1] = sweepFrag(S + (ks * 4 + row + 2) * 8 + cx);
+                            b[ks + 2][0] = sweepFrag(P + (ks * 4 + row) * 8 + cx);
+                            b[ks + 2][1] = sweepFrag(P + (ks * 4 + row + 2) * 8 + cx);
                         }
                         int s0 = 0, s1 = 0;
 #pragma unroll
                         for (int mt = 0; mt < 4; ++mt)
                         {
-                            int acc[4] = {0, 0, 0, 0};
+                            int acc[4] = {0, 0, 0, 0}, ach[4] = {0, 0, 0, 0};
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks)
                             {
                                 const int n01 = (((mt >> 1) & ks) ^ (ks >> 1)) & 1, n23 = n01 ^ (mt & 1);
-                                imma16832(acc, A.e[n01], A.o[n01], A.e[n23], A.o[n23], b[ks][0], b[ks][1]);
+                                imma16832(acc, A.e[n01], A.o[n01], A.e[n23], A.o[n23], b[ks][0].lo, b[ks][1].lo);
+                                if (k16) imma16832(ach, A.e[n01], A.o[n01], A.e[n23], A.o[n23], b[ks][0].hi, b[ks][1].hi);
                             }
+                            if (k16)
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) acc[r] += ach[r] << 8;
                             s0 = __sad(acc[0], 0, __sad(acc[2], 0, (unsigned)s0));
                             s1 = __sad(acc[1], 0, __sad(acc[3], 0, (unsigned)s1));
                         }
                         const int sum = columnSums(s0, s1, g);
-                        if (g < 2 && base + 2 * tq + g < 35) s.sum[base + 2 * tq + g] += (sum + 2) >> 2;
+                        if (g < 2 && base + 2 * tq + g < 35) s.sum[base + 2 * tq + g] += ((sum + 2) >> 2) >> (k16 ? 2 : 0);
                     }
                     __syncwarp();
                 }
@@ -506,16 +542,21 @@ extern "C" int hvb_intra_satd35_batch(hvb_context *ctx, const hvb_intra_sweep_ta
     if (rc) return rc;
     const auto *dT = static_cast<const hvb_intra_sweep_task *>(st.dTasks);
     auto *dO = static_cast<int32_t *>(st.dOut);
+    int perSm = 1;
     if (ctx->bps == 1)
     {
-        int perSm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, intraSweepKernel8, kWarps * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, intraSweepKernel8<uint8_t>, kWarps * 32, 0);
         const int blocks = min((n + kWarps - 1) / kWarps, ctx->smCount * max(perSm, 1));
-        intraSweepKernel8<<<blocks, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, static_cast<const uint8_t *>(ctx->samplePool), dT, n, dO);
+        intraSweepKernel8<uint8_t><<<blocks, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, static_cast<const uint8_t *>(ctx->samplePool), dT, n, dO,
+                                                                           ctx->bitDepth);
     }
     else
-        intraSweepKernel<uint16_t><<<gridWarps(ctx, n), kWarps * 32, 0, ctx->stream>>>(
-            ctx->dPlanes, static_cast<const uint16_t *>(ctx->samplePool), dT, n, dO, ctx->bitDepth);
+    {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, intraSweepKernel8<uint16_t>, kWarps * 32, 0);
+        const int blocks = min((n + kWarps - 1) / kWarps, ctx->smCount * max(perSm, 1));
+        intraSweepKernel8<uint16_t><<<blocks, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, static_cast<const uint16_t *>(ctx->samplePool), dT, n,
+                                                                            dO, ctx->bitDepth);
+    }
     HVB_LAUNCH_CHECK(ctx, "intraSweepKernel");
     return hvbStageOut(ctx, out, sizeof(int32_t) * 35 * n, mem, st);
 }
