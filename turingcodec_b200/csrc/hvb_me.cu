@@ -168,41 +168,41 @@ struct Search
         if (cand < nc)
         {
             const Sample *r = ref + (intptr_t)cy * sr + cx;
-            if (sizeof(Sample) == 1 && (wpr == 4 || wpr == 8 || wpr == 16))
+            if (wpr == 4 || wpr == 8 || wpr == 16 || wpr == 32)
             {
-                // 8-bit blocks 16, 32 or 64 wide: a lane takes 16 bytes of a row at a time -- five aligned words of the
+                // rows of 16, 32, 64 (128) bytes: a lane takes 16 bytes of a row at a time -- five aligned words of the
                 // candidate (all requested before the first use), four funnel shifts, one 128-bit read of the source
-                const int log2upr = wpr == 4 ? 0 : (wpr == 8 ? 1 : 2), units = t.h << log2upr;
+                const int log2upr = wpr == 4 ? 0 : (wpr == 8 ? 1 : (wpr == 16 ? 2 : 3)), units = t.h << log2upr;
                 const uintptr_t a0 = reinterpret_cast<uintptr_t>(r);
                 const unsigned sh = (unsigned)(a0 & 3) * 8;
                 const uint32_t *q0 = reinterpret_cast<const uint32_t *>(a0 & ~uintptr_t(3));
-                const int srw = sr >> 2;
+                const int srwB = (sr * (int)sizeof(Sample)) >> 2; // row stride in words
                 for (int u = sub; u < units; u += lanesPer)
                 {
                     const int y = u >> log2upr, xu = u & ((1 << log2upr) - 1);
-                    const uint32_t *q = q0 + y * srw + xu * 4;
+                    const uint32_t *q = q0 + y * srwB + xu * 4;
                     const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3), w4 = __ldg(q + 4);
                     const uint4 s4 = *reinterpret_cast<const uint4 *>(srcWords + y * wpr + xu * 4);
-                    acc = __vsadu4(s4.x, __funnelshift_r(w0, w1, sh)) + acc;
-                    acc = __vsadu4(s4.y, __funnelshift_r(w1, w2, sh)) + acc;
-                    acc = __vsadu4(s4.z, __funnelshift_r(w2, w3, sh)) + acc;
-                    acc = __vsadu4(s4.w, __funnelshift_r(w3, w4, sh)) + acc;
+                    acc = Word<Sample>::sad(s4.x, __funnelshift_r(w0, w1, sh), acc);
+                    acc = Word<Sample>::sad(s4.y, __funnelshift_r(w1, w2, sh), acc);
+                    acc = Word<Sample>::sad(s4.z, __funnelshift_r(w2, w3, sh), acc);
+                    acc = Word<Sample>::sad(s4.w, __funnelshift_r(w3, w4, sh), acc);
                 }
             }
-            else if (sizeof(Sample) == 1 && wpr == 2)
+            else if (wpr == 2)
             {
-                // 8 wide: a lane takes a whole row (three aligned words, two funnel shifts)
+                // rows of 8 bytes: a lane takes a whole row (three aligned words, two funnel shifts)
                 const uintptr_t a0 = reinterpret_cast<uintptr_t>(r);
                 const unsigned sh = (unsigned)(a0 & 3) * 8;
                 const uint32_t *q0 = reinterpret_cast<const uint32_t *>(a0 & ~uintptr_t(3));
-                const int srw = sr >> 2;
+                const int srwB = (sr * (int)sizeof(Sample)) >> 2;
                 for (int y = sub; y < t.h; y += lanesPer)
                 {
-                    const uint32_t *q = q0 + y * srw;
+                    const uint32_t *q = q0 + y * srwB;
                     const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
                     const uint2 s2 = *reinterpret_cast<const uint2 *>(srcWords + y * 2);
-                    acc = __vsadu4(s2.x, __funnelshift_r(w0, w1, sh)) + acc;
-                    acc = __vsadu4(s2.y, __funnelshift_r(w1, w2, sh)) + acc;
+                    acc = Word<Sample>::sad(s2.x, __funnelshift_r(w0, w1, sh), acc);
+                    acc = Word<Sample>::sad(s2.y, __funnelshift_r(w1, w2, sh), acc);
                 }
             }
             else
