@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(kWarps * 32)
     for (int i = blockIdx.x * kWarps + warp; i < n; i += warpsTotal)
     {
         const hvb_me_task t = tasks[i];
-        if (sizeof(Sample) == 1 && !kFused && t.w <= 8 && t.h <= 8) continue; // 8-bit PUs up to 8x8: hvb_me_small.cu, four per warp
+        if (!kFused && t.w <= 8 && t.h <= 8) continue; // PUs up to 8x8: hvb_me_small.cu, four per warp
         Search<Sample> s(t, planes, sSrc, lane);
         s.sMid = sScratch + 32;
         long long costMvdZero[2] = {0, 0};
@@ -823,7 +823,9 @@ extern "C" int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, i
     }
     else
     {
-        // 16-bit samples: integer search a warp per PU, then the same sub-pel kernel (template on the sample type)
+        // 16-bit samples: the same three kernels (templates on the sample type)
+        rc = hvbLaunchMeSmall(ctx, dT, n, dO);
+        if (rc) return rc;
         const int smem = kWarps * kSrcWords * 4;
         cudaFuncSetAttribute(meSearchKernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         int perSm = 1;

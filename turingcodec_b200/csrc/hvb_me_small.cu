@@ -1,5 +1,5 @@
-// hvb_me_small.cu -- the integer motion search for PUs of at most 8x8 samples (8x8, 8x4, 4x8) in 8-bit pictures:
-// four searches per warp, one lane per candidate.
+// hvb_me_small.cu -- the integer motion search for PUs of at most 8x8 samples (8x8, 8x4, 4x8): four searches per warp, one
+// lane per candidate.  Template on the sample type (8-bit: source block in 16 registers; 16-bit: in shared memory).
 //
 // Reference semantics (bit-exact decisions, same path through the search, same SAD count):
 //   fullPelMotionEstimation                          turing/Search.hpp:2064-2336
@@ -54,17 +54,22 @@ __device__ __forceinline__ long long rateOfMvd(int dx, int dy)
     return (long long)(rx + ry + 1) << 17;
 }
 
+template <typename Sample>
 struct SmallSmem
 {
     hvb_me_task task[kWarps][kGroups];
+    uint32_t src[sizeof(Sample) == 2 ? kWarps * kGroups : 1][8][4]; // 16-bit samples: the groups' source blocks, 16 bytes per row
     int8_t patterns[72];
 };
 
+template <typename Sample>
 __global__ void __launch_bounds__(kWarps * 32, 6)
     meSearchSmallKernel(const HvbPlane *__restrict__ planes, const hvb_me_task *__restrict__ tasks, int n, hvb_me_result *__restrict__ out,
                         int *__restrict__ cursor)
 {
-    __shared__ __align__(16) SmallSmem sm;
+    __shared__ __align__(16) SmallSmem<Sample> sm;
+    constexpr bool k16 = sizeof(Sample) == 2;
+    uint32_t (*sSrc)[4] = sm.src[k16 ? (threadIdx.x >> 5) * kGroups + ((threadIdx.x & 31) >> 3) : 0];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane >> 3, l8 = lane & 7, base8 = lane & 24;
     if (threadIdx.x < 72) sm.patterns[threadIdx.x] = kPatterns[threadIdx.x];
@@ -78,8 +83,8 @@ __global__ void __launch_bounds__(kWarps * 32, 6)
     int i = -1, cur = 0, end = 0;
     bool mine = false;
     int phase = PH_DONE;
-    uint32_t src[8][2];
-    const uint8_t *ref = nullptr;
+    uint32_t src[8][2]; // 8-bit samples only
+    const Sample *ref = nullptr;
     int sr = 0, w = 8, h = 8, lambda = 0, window = 64, maxCounter = 3, raster = 240, rasterCols = 28, rasterTotal = 700;
     // search state (identical in the 8 lanes of a group)
     long long bestCost = 0x7fffffffffffffffLL, costMvdZero0 = 0, costMvdZero1 = 0;
@@ -139,19 +144,40 @@ __global__ void __launch_bounds__(kWarps * 32, 6)
                 h = t.h;
                 const HvbPlane &sp = planes[t.src_pic * 3], &rp = planes[t.ref_pic * 3];
                 sr = rp.stride;
-                ref = reinterpret_cast<const uint8_t *>(rp.base) + (intptr_t)t.y0 * sr + t.x0;
+                ref = reinterpret_cast<const Sample *>(rp.base) + (intptr_t)t.y0 * sr + t.x0;
                 // the source block: x0 is a multiple of 4 and the plane rows are 256-byte aligned
-                const uint8_t *s0 = reinterpret_cast<const uint8_t *>(sp.base) + (intptr_t)t.y0 * sp.stride + t.x0;
-#pragma unroll
-                for (int y = 0; y < 8; ++y)
+                const Sample *s0 = reinterpret_cast<const Sample *>(sp.base) + (intptr_t)t.y0 * sp.stride + t.x0;
+                if (!k16)
                 {
-                    src[y][0] = src[y][1] = 0;
-                    if (y < h)
+#pragma unroll
+                    for (int y = 0; y < 8; ++y)
                     {
-                        const uint32_t *q = reinterpret_cast<const uint32_t *>(s0 + (intptr_t)y * sp.stride);
-                        src[y][0] = __ldg(q);
-                        if (w == 8) src[y][1] = __ldg(q + 1);
+                        src[y][0] = src[y][1] = 0;
+                        if (y < h)
+                        {
+                            const uint32_t *q = reinterpret_cast<const uint32_t *>(s0 + (intptr_t)y * sp.stride);
+                            src[y][0] = __ldg(q);
+                            if (w == 8) src[y][1] = __ldg(q + 1);
+                        }
                     }
+                }
+                else
+                {
+                    // lane l stages row l (zero beyond the block; those words are masked on the candidate side too)
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (l8 < h)
+                    {
+                        const uint32_t *q = reinterpret_cast<const uint32_t *>(s0 + (intptr_t)l8 * sp.stride);
+                        v.x = __ldg(q);
+                        v.y = __ldg(q + 1);
+                        if (w == 8)
+                        {
+                            v.z = __ldg(q + 2);
+                            v.w = __ldg(q + 3);
+                        }
+                    }
+                    *reinterpret_cast<uint4 *>(sSrc[l8]) = v;
+                    __syncwarp(groupMask);
                 }
                 lambda = t.lambda;
                 window = t.smallSearchWindow ? 32 : 64;
@@ -262,36 +288,64 @@ __global__ void __launch_bounds__(kWarps * 32, 6)
                 // SAD of the block at (fx, fy)
                 int sad = 0;
                 {
-                    const uint8_t *r = ref + (intptr_t)fy * sr + fx;
+                    const Sample *r = ref + (intptr_t)fy * sr + fx;
                     const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(r) & 3) * 8;
                     const uint32_t *q = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(r) & ~uintptr_t(3));
-                    const int srw = sr >> 2;
-                    // four rows at a time, every load issued before the first use (12 independent loads in flight);
-                    // rows beyond h re-read row 0 and are not summed, the second word of a 4-wide block is masked
+                    const int srw = (sr * (int)sizeof(Sample)) >> 2;
+                    // four rows at a time, every load issued before the first use; rows beyond h re-read row 0 and are not
+                    // summed, the words beyond a 4-wide block are masked
 #pragma unroll
                     for (int half = 0; half < 2; ++half)
                     {
                         if (half && h <= 4) break;
-                        uint32_t wv[4][3];
-#pragma unroll
-                        for (int yy = 0; yy < 4; ++yy)
+                        if (!k16)
                         {
-                            const int y = half * 4 + yy;
-                            const uint32_t *qr = q + (y < h ? y : 0) * srw;
-                            wv[yy][0] = __ldg(qr);
-                            wv[yy][1] = __ldg(qr + 1);
-                            wv[yy][2] = __ldg(qr + 2);
+                            uint32_t wv[4][3];
+#pragma unroll
+                            for (int yy = 0; yy < 4; ++yy)
+                            {
+                                const int y = half * 4 + yy;
+                                const uint32_t *qr = q + (y < h ? y : 0) * srw;
+                                wv[yy][0] = __ldg(qr);
+                                wv[yy][1] = __ldg(qr + 1);
+                                wv[yy][2] = __ldg(qr + 2);
+                            }
+#pragma unroll
+                            for (int yy = 0; yy < 4; ++yy)
+                            {
+                                const int y = half * 4 + yy;
+                                const uint32_t v0 = __funnelshift_r(wv[yy][0], wv[yy][1], sh);
+                                const uint32_t v1 = w == 8 ? __funnelshift_r(wv[yy][1], wv[yy][2], sh) : 0u;
+                                const int rowSad = __vsadu4(src[y][1], v1) + __vsadu4(src[y][0], v0);
+                                sad += y < h ? rowSad : 0;
+                            }
                         }
-#pragma unroll
-                        for (int yy = 0; yy < 4; ++yy)
+                        else
                         {
-                            const int y = half * 4 + yy;
-                            const uint32_t v0 = __funnelshift_r(wv[yy][0], wv[yy][1], sh);
-                            const uint32_t v1 = w == 8 ? __funnelshift_r(wv[yy][1], wv[yy][2], sh) : 0u;
-                            const int rowSad = __vsadu4(src[y][1], v1) + __vsadu4(src[y][0], v0);
-                            sad += y < h ? rowSad : 0;
+                            const uint32_t m = w == 8 ? ~0u : 0u;
+                            uint32_t wv[4][5];
+#pragma unroll
+                            for (int yy = 0; yy < 4; ++yy)
+                            {
+                                const int y = half * 4 + yy;
+                                const uint32_t *qr = q + (y < h ? y : 0) * srw;
+#pragma unroll
+                                for (int k = 0; k < 5; ++k) wv[yy][k] = __ldg(qr + k);
+                            }
+#pragma unroll
+                            for (int yy = 0; yy < 4; ++yy)
+                            {
+                                const int y = half * 4 + yy;
+                                const uint4 sv = *reinterpret_cast<const uint4 *>(sSrc[y]); // broadcast within the group
+                                int rowSad = __vsadu2(sv.x, __funnelshift_r(wv[yy][0], wv[yy][1], sh));
+                                rowSad = __vsadu2(sv.y, __funnelshift_r(wv[yy][1], wv[yy][2], sh)) + rowSad;
+                                rowSad = __vsadu2(sv.z, __funnelshift_r(wv[yy][2], wv[yy][3], sh) & m) + rowSad;
+                                rowSad = __vsadu2(sv.w, __funnelshift_r(wv[yy][3], wv[yy][4], sh) & m) + rowSad;
+                                sad += y < h ? rowSad : 0;
+                            }
                         }
                     }
+                    if (k16) sad >>= 2; // havoc/sad.cpp:446-447: 16-bit samples
                 }
                 // the candidate (MvCandidate, Search.hpp:1262-1298; the predictor candidates :2131-2171 are tied to theirs)
                 const int mvx = fx * 4, mvy = fy * 4;
@@ -492,16 +546,22 @@ __global__ void __launch_bounds__(kWarps * 32, 6)
 } // namespace
 
 // called by hvb_me_search_batch (hvb_me.cu) for 8-bit batches, before the warp-per-PU kernel takes the larger PUs
-int hvbLaunchMeSmall(hvb_context *ctx, const hvb_me_task *dTasks, int n, hvb_me_result *dOut)
+template <typename Sample>
+static int launchMeSmall(hvb_context *ctx, const hvb_me_task *dTasks, int n, hvb_me_result *dOut)
 {
     int perSm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, meSearchSmallKernel, kWarps * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, meSearchSmallKernel<Sample>, kWarps * 32, 0);
     // persistent: every group pulls PUs from the cursor until the batch is exhausted
     int blocks = (n + kWarps * kGroups - 1) / (kWarps * kGroups);
     const int cap = ctx->smCount * (perSm > 0 ? perSm : 1);
     if (blocks > cap) blocks = cap;
     cudaMemsetAsync(ctx->workCursors, 0, sizeof(int), ctx->stream);
-    meSearchSmallKernel<<<blocks, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, dTasks, n, dOut, ctx->workCursors);
+    meSearchSmallKernel<Sample><<<blocks, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, dTasks, n, dOut, ctx->workCursors);
     HVB_LAUNCH_CHECK(ctx, "meSearchSmallKernel");
     return HVB_OK;
+}
+
+int hvbLaunchMeSmall(hvb_context *ctx, const hvb_me_task *dTasks, int n, hvb_me_result *dOut)
+{
+    return ctx->bps == 1 ? launchMeSmall<uint8_t>(ctx, dTasks, n, dOut) : launchMeSmall<uint16_t>(ctx, dTasks, n, dOut);
 }
