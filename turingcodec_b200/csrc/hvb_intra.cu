@@ -8,12 +8,10 @@
 //   35-mode sweep + SATD        turing/Reconstruct.cpp:630-701 (PredictIntraLumaBlock), Search.hpp:39-267
 //
 // The reference materialises every prediction into a stack buffer and then runs SATD on it, one mode
-// at a time.  Here a predicted sample is a pure function of (mode, x, y) and the 4n+1 neighbours, so
-// the sweep never stores a prediction: each lane owns one (mode, tile) job, evaluates the tile's
-// samples straight into the registers of a Hadamard butterfly and adds the result to its mode's sum.
-// Per partition that is (4n+1)B + n*n*B bytes in and 35 * 4 bytes out.
+// at a time.  Here a predicted sample is a pure function of (mode, x, y) and the 4n+1 neighbours: the sweep
+// generates the 35 predictions of a tile row-wise into shared memory and takes their SATDs on the integer
+// tensor cores (see "the sweep" below).  Per partition that is (4n+1)B + n*n*B bytes in and 35 * 4 bytes out.
 #include "hvb_internal.cuh"
-#include "hvb_satd.cuh"
 
 namespace {
 
@@ -156,70 +154,6 @@ __global__ void __launch_bounds__(kWarps * 32)
         __syncwarp();
     }
 }
-
-template <typename Sample, int LOG2T>
-__device__ __forceinline__ int sweepTile(const Neighbours &nb, int mode, int log2n, int dc, bool edge, int maxv, const Sample *src,
-                                         int ss, int x0, int y0)
-{
-    constexpr int T = 1 << LOG2T;
-    int16_t pred[T * T];
-    const int angle = kAngle[mode], inv = kInvAngle[mode];
-#pragma unroll
-    for (int y = 0; y < T; ++y)
-#pragma unroll
-        for (int x = 0; x < T; ++x) pred[y * T + x] = (int16_t)intraSample(nb, mode, angle, inv, x0 + x, y0 + y, log2n, dc, edge, maxv);
-    return hvbSatdTile<Sample, int16_t, LOG2T>(src + y0 * ss + x0, ss, pred, T, sizeof(Sample) == 2 ? 2 : 0);
-}
-
-template <typename Sample>
-__global__ void __launch_bounds__(kWarps * 32)
-    intraSweepKernel(const HvbPlane *__restrict__ planes, const Sample *__restrict__ pool,
-                     const hvb_intra_sweep_task *__restrict__ tasks, int n, int32_t *__restrict__ out, int bitDepth)
-{
-    __shared__ int16_t sU[kWarps][kNbMax + 3];
-    __shared__ int16_t sF[kWarps][kNbMax + 3];
-    __shared__ int sSum[kWarps][36];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int warpsTotal = gridDim.x * kWarps;
-    const int maxv = (1 << bitDepth) - 1;
-    for (int i = blockIdx.x * kWarps + warp; i < n; i += warpsTotal)
-    {
-        const hvb_intra_sweep_task t = tasks[i];
-        const int log2n = t.log2n, nn = 1 << log2n;
-        for (int k = lane; k <= 4 * nn; k += 32)
-        {
-            sU[warp][k] = (int16_t)pool[t.nb_unfiltered - 2 * nn + k];
-            if (t.nb_filtered >= 0) sF[warp][k] = (int16_t)pool[t.nb_filtered - 2 * nn + k];
-        }
-        for (int k = lane; k < 36; k += 32) sSum[warp][k] = 0;
-        __syncwarp();
-        if (t.nb_filtered < 0) filterNeighbours(sF[warp], sU[warp], nn, bitDepth, t.strong_intra_smoothing != 0, lane);
-        __syncwarp();
-        const Neighbours nbU{sU[warp], 2 * nn}, nbF{sF[warp], 2 * nn};
-        const int dc = dcValue(nbU, log2n, lane);
-        const bool edge = t.cIdx == 0 && log2n < 5;
-        int ss;
-        const Sample *src = hvbBlockPtr<Sample>(planes, t.src, ss);
-
-        // PredictIntraLumaBlock tiles with 4x4 for log2n == 2 and 8x8 otherwise (Reconstruct.cpp:683-701)
-        const int log2t = log2n == 2 ? 2 : 3;
-        const int tilesPerRow = nn >> log2t, tiles = tilesPerRow * tilesPerRow;
-        const int jobs = 35 * tiles;
-        for (int j = lane; j < jobs; j += 32)
-        {
-            const int mode = j / tiles, tile = j - mode * tiles;
-            const int ty = tile / tilesPerRow, tx = tile - ty * tilesPerRow;
-            const Neighbours &nb = filterFlag(t.cIdx, mode, nn) ? nbF : nbU;
-            const int v = log2t == 2 ? sweepTile<Sample, 2>(nb, mode, log2n, dc, edge, maxv, src, ss, tx << 2, ty << 2)
-                                     : sweepTile<Sample, 3>(nb, mode, log2n, dc, edge, maxv, src, ss, tx << 3, ty << 3);
-            atomicAdd(&sSum[warp][mode], v);
-        }
-        __syncwarp();
-        for (int k = lane; k < 35; k += 32) out[i * 35 + k] = sSum[warp][k];
-        __syncwarp();
-    }
-}
-
 
 // ---- the sweep: predictions to shared memory row by row, SATD on the integer tensor cores (8- and 16-bit samples) ----
 //

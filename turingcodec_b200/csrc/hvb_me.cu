@@ -1,5 +1,6 @@
-// hvb_me.cu -- batched uni-directional motion search: the integer pattern search and the sub-pel
-// refinement WITH their control flow, one warp per prediction unit.
+// hvb_me.cu -- batched motion search WITH its control flow: the integer pattern search of the PUs larger than 8x8, one
+// warp per prediction unit (smaller PUs: hvb_me_small.cu; the sub-pel refinement of every PU: hvb_me_subpel.cu), and
+// the bi-directional refinement (searchMotionBi), whose fractional rounds keep the in-kernel sub-pel evaluation below.
 //
 // Reference semantics (bit-exact decisions):
 //   fullPelMotionEstimation   turing/Search.hpp:2064-2336
@@ -39,8 +40,6 @@ constexpr int kSrcWords = 64 * 64 / 2; // u16 worst case: 2 samples per word
 constexpr int kSubpelWords = subpel::kScratchBytes / 4 > 15 * 32 ? subpel::kScratchBytes / 4 : 15 * 32;
 constexpr int kExtraWords = 32 + kSubpelWords;
 // candidate index of grid position (dy + 1) * 3 + dx + 1 in the reference's pattern order (Search.hpp:2346, :2352)
-__device__ __constant__ int8_t kCandHalfUni[9] = {1, 2, 3, 4, 0, 5, 6, 7, 8};
-__device__ __constant__ int8_t kCandQuarterUni[9] = {0, 1, 2, 3, -1, 4, 5, 6, 7};
 __device__ __constant__ int8_t kCandGrid[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
 
 // ---- sample-type helpers: 32-bit words of 4 (u8) or 2 (u16) samples -------------------------------
@@ -82,13 +81,6 @@ __device__ __forceinline__ long long rateOfMvd(int dx, int dy)
     return (long long)(rx + ry + 1) << 17;
 }
 
-__device__ __forceinline__ long long shfl64(long long v, int srcLane)
-{
-    const int lo = __shfl_sync(0xffffffffu, (int)(v & 0xffffffffLL), srcLane);
-    const int hi = __shfl_sync(0xffffffffu, (int)(v >> 32), srcLane);
-    return ((long long)hi << 32) | (unsigned)lo;
-}
-
 __device__ __forceinline__ long long shflXor64(long long v, int m)
 {
     const int lo = __shfl_xor_sync(0xffffffffu, (int)(v & 0xffffffffLL), m);
@@ -102,9 +94,6 @@ __device__ __constant__ int8_t kDiamond16[32] = {0,  -4, 1,  -3, 2,  -2, 3,  -1,
                                                  0,  4,  -1, 3,  -2, 2,  -3, 1,  -4, 0, -3, -1, -2, -2, -1, -3};
 __device__ __constant__ int8_t kSquare4[8] = {-4, -4, -4, 4, 4, 4, 4, -4};
 __device__ __constant__ int8_t kDiamond1[8] = {0, -1, -1, 0, 0, 1, 1, 0};
-// sub-pel patterns (Search.hpp:2346, :2352); entry 0 is the origin itself (tryOrigin)
-__device__ __constant__ int8_t kHalf9[18] = {0, 0, -2, -2, 0, -2, 2, -2, -2, 0, 2, 0, -2, 2, 0, 2, 2, 2};
-__device__ __constant__ int8_t kQuarter8[16] = {-1, -1, 0, -1, 1, -1, -1, 0, 1, 0, -1, 1, 0, 1, 1, 1};
 __device__ __constant__ int8_t kLumaTaps[4][8] = {{0, 0, 0, 64, 0, 0, 0, 0},
                                                   {-1, 4, -10, 58, 17, -5, 1, 0},
                                                   {-1, 4, -11, 40, 40, -11, 4, -1},
@@ -538,71 +527,24 @@ __device__ void subpelEval(const Search<Sample> &s, const int *sMvx, const int *
     __syncwarp();
 }
 
-// patternSearch with maxIterations = 1 (Search.hpp:2011-2060); all candidates of the pattern at once
+// The integer search of the PUs larger than 8x8, a warp each (the smaller ones: hvb_me_small.cu); hvb_me_subpel.cu then
+// refines the whole batch in its own launch.
 template <typename Sample>
-__device__ __noinline__ void patternSearch(Search<Sample> &s, int *sMvx, int *sMvy, int *sSatd, const int8_t *pattern, int n, bool tryOrigin,
-                              hvb_mv &mv, hvb_mv &mvd, long long &bestCost, int bitDepth)
-{
-    if (s.lane < n)
-    {
-        sMvx[s.lane] = mv.x + pattern[2 * s.lane];
-        sMvy[s.lane] = mv.y + pattern[2 * s.lane + 1];
-        sSatd[s.lane] = 0;
-    }
-    __syncwarp();
-    if (sizeof(Sample) == 1) // 8 bit: shared interpolation planes + tensor-core SATD (hvb_subpel.cuh)
-        subpel::evalRound(reinterpret_cast<const uint8_t *>(s.srcS), s.t.w, s.t.h, reinterpret_cast<const uint8_t *>(s.ref), s.sr, mv.x,
-                          mv.y, tryOrigin ? 2 : 1, tryOrigin ? kCandHalfUni : kCandQuarterUni, n, reinterpret_cast<uint8_t *>(s.sMid),
-                          sSatd, s.lane);
-    else if (((s.t.w | s.t.h) & 7) == 0)
-        subpelEval<Sample, 3>(s, sMvx, sMvy, n, sSatd, bitDepth);
-    else
-        subpelEval<Sample, 2>(s, sMvx, sMvy, n, sSatd, bitDepth);
-    // costMv (:2003-2008) = rateOf(mvd) + lambda * SATD, considered in pattern order with a strict `<`
-    int best = -1;
-    for (int i = 0; i < n; ++i)
-    {
-        const int dx = pattern[2 * i], dy = pattern[2 * i + 1];
-        const long long c = rateOfMvd((int16_t)(mvd.x + dx), (int16_t)(mvd.y + dy)) + (long long)s.t.lambda * sSatd[i];
-        if (tryOrigin && i == 0)
-            bestCost = c; // entry 0 of the half-pel table is the origin
-        else if (c < bestCost)
-        {
-            best = i;
-            bestCost = c;
-        }
-    }
-    if (best >= 0)
-    {
-        mv.x = (int16_t)(mv.x + pattern[2 * best]);
-        mv.y = (int16_t)(mv.y + pattern[2 * best + 1]);
-        mvd.x = (int16_t)(mvd.x + pattern[2 * best]);
-        mvd.y = (int16_t)(mvd.y + pattern[2 * best + 1]);
-    }
-    __syncwarp();
-}
-
-// kFused: the sub-pel refinement runs in this kernel (16-bit pictures); otherwise the kernel stops after the integer
-// search and hvb_me_subpel.cu refines the whole batch in a second launch (8-bit pictures).
-template <typename Sample, bool kFused>
 __global__ void __launch_bounds__(kWarps * 32)
     meSearchKernel(const HvbPlane *__restrict__ planes, const hvb_me_task *__restrict__ tasks, int n, hvb_me_result *__restrict__ out,
                    int bitDepth)
 {
     extern __shared__ __align__(16) uint32_t smemMe[];
     constexpr int kBlockWords = sizeof(Sample) == 1 ? 64 * 64 / 4 : kSrcWords;
-    constexpr int kWordsPerWarp = kBlockWords + (kFused ? kExtraWords : 0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *sSrc = smemMe + warp * kWordsPerWarp;
-    int *sScratch = reinterpret_cast<int *>(sSrc + kBlockWords);
-    int *sMvx = sScratch, *sMvy = sScratch + 10, *sSatd = sScratch + 20;
+    uint32_t *sSrc = smemMe + warp * kBlockWords;
     const int warpsTotal = gridDim.x * kWarps;
     for (int i = blockIdx.x * kWarps + warp; i < n; i += warpsTotal)
     {
         const hvb_me_task t = tasks[i];
-        if (!kFused && t.w <= 8 && t.h <= 8) continue; // PUs up to 8x8: hvb_me_small.cu, four per warp
+        if (t.w <= 8 && t.h <= 8) continue; // PUs up to 8x8: hvb_me_small.cu, four per warp
         Search<Sample> s(t, planes, sSrc, lane);
-        s.sMid = sScratch + 32;
+        s.sMid = nullptr;
         long long costMvdZero[2] = {0, 0};
         const bool early = fullPel(s, costMvdZero);
 
@@ -614,14 +556,7 @@ __global__ void __launch_bounds__(kWarps * 32)
         r.costMvdZero[1] = costMvdZero[1];
         r.subpelCost = 0;
         r.flags = early ? 1 : 0; // bit 0: returned through MET -> mvPreviousInteger2Nx2N is not updated
-        hvb_mv mv = s.best.mv, mvd = s.best.mvd;
-        if (kFused && t.halfPel) // searchMotionUni (Search.hpp:1335-1347)
-        {
-            long long bestCost = 0;
-            patternSearch(s, sMvx, sMvy, sSatd, kHalf9, 9, true, mv, mvd, bestCost, bitDepth);
-            if (t.quarterPel) patternSearch(s, sMvx, sMvy, sSatd, kQuarter8, 8, false, mv, mvd, bestCost, bitDepth);
-            r.subpelCost = bestCost;
-        }
+        const hvb_mv mv = s.best.mv, mvd = s.best.mvd; // the sub-pel kernel starts from here
         r.mv = mv;
         r.mvd = mvd;
         r.nSad = s.nSad;
@@ -812,11 +747,11 @@ extern "C" int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, i
         rc = hvbLaunchMeSmall(ctx, dT, n, dO);
         if (rc) return rc;
         const int smem = kWarps * (64 * 64 / 4) * 4;
-        cudaFuncSetAttribute(meSearchKernel<uint8_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(meSearchKernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         int perSm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, meSearchKernel<uint8_t, false>, kWarps * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, meSearchKernel<uint8_t>, kWarps * 32, smem);
         blocks = min((n + kWarps - 1) / kWarps, ctx->smCount * max(perSm, 1));
-        meSearchKernel<uint8_t, false><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
+        meSearchKernel<uint8_t><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
         HVB_LAUNCH_CHECK(ctx, "meSearchKernel");
         rc = hvbLaunchMeSubpel(ctx, dT, n, dO);
         if (rc) return rc;
@@ -827,11 +762,11 @@ extern "C" int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, i
         rc = hvbLaunchMeSmall(ctx, dT, n, dO);
         if (rc) return rc;
         const int smem = kWarps * kSrcWords * 4;
-        cudaFuncSetAttribute(meSearchKernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(meSearchKernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         int perSm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, meSearchKernel<uint16_t, false>, kWarps * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, meSearchKernel<uint16_t>, kWarps * 32, smem);
         blocks = min((n + kWarps - 1) / kWarps, ctx->smCount * max(perSm, 1));
-        meSearchKernel<uint16_t, false><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
+        meSearchKernel<uint16_t><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
         HVB_LAUNCH_CHECK(ctx, "meSearchKernel");
         rc = hvbLaunchMeSubpel(ctx, dT, n, dO);
         if (rc) return rc;
