@@ -29,18 +29,11 @@
 // is the number of pattern calls (5-20), not the number of SADs (30-900).
 // Algorithmic traffic per PU: w*h*B (source, once) + nSad*w*h*B + 17 ((w+7)(h+7) + w*h) B.
 #include "hvb_internal.cuh"
-#include "hvb_subpel.cuh"
 
 namespace {
 
 constexpr int kWarps = 8;
 constexpr int kSrcWords = 64 * 64 / 2; // u16 worst case: 2 samples per word
-// per warp: candidate scratch (32 words) + the sub-pel workspace: 8 bit: interpolation planes and candidate
-// predictions (hvb_subpel.cuh); 16 bit: the horizontal-pass columns [15][32]
-constexpr int kSubpelWords = subpel::kScratchBytes / 4 > 15 * 32 ? subpel::kScratchBytes / 4 : 15 * 32;
-constexpr int kExtraWords = 32 + kSubpelWords;
-// candidate index of grid position (dy + 1) * 3 + dx + 1 in the reference's pattern order (Search.hpp:2346, :2352)
-__device__ __constant__ int8_t kCandGrid[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
 
 // ---- sample-type helpers: 32-bit words of 4 (u8) or 2 (u16) samples -------------------------------
 template <typename Sample>
@@ -111,7 +104,6 @@ struct Search
     int wpr, words, wprInv; // words per row, words in the block, ceil(65536 / wpr)
     Cand best;
     int nSad;
-    int *sMid; // shared: [15][32] ints, column `lane` is this lane's horizontal-pass output
 
     // loadSource = false: the caller fills the shared block itself (the bi search compares against 2*src - predOther)
     __device__ Search(const hvb_me_task &task, const HvbPlane *planes, uint32_t *smemSrc, int lane_, bool loadSource = true)
@@ -416,117 +408,6 @@ __device__ bool fullPel(Search<Sample> &s, long long (&costMvdZero)[2])
     return false;
 }
 
-// ---- sub-pel stage -------------------------------------------------------------------------------
-
-// One column (lane j of a T-lane group) of one T x T tile of the 8-tap prediction at quarter-pel `mv`,
-// minus the source column, Hadamard-transformed; returns the tile's normalised SATD on every lane of the group.
-template <typename Sample, int LOG2T>
-__device__ __forceinline__ int tileSatd(const Search<Sample> &s, int tileX, int tileY, int mvx, int mvy, int j, int bitDepth)
-{
-    constexpr int T = 1 << LOG2T;
-    const int shift1 = min(4, bitDepth - 8), shift3 = max(2, 14 - bitDepth);
-    const int maxv = (1 << bitDepth) - 1;
-    const int xf = mvx & 3, yf = mvy & 3;
-    const Sample *R = s.ref + (intptr_t)(tileY * T + (mvy >> 2) - 3) * s.sr + (tileX * T + j + (mvx >> 2) - 3);
-    int cx[8], cy[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-    {
-        cx[k] = kLumaTaps[xf][k];
-        cy[k] = kLumaTaps[yf][k];
-    }
-    // Horizontal pass: this lane's column of the (T+7)-row intermediate goes to the lane's own slots of the
-    // warp's shared scratch (no other lane reads them, so no barrier is needed).  The row loop stays rolled:
-    // the ncu capture of the fully unrolled version was dominated by instruction-cache misses.
-    // Rows 0..2 and T+3.. are only needed by a vertical filter with a non-zero phase.
-    int *mids = s.sMid + s.lane;
-    const int r0 = yf ? 0 : 3, r1 = yf ? T + 7 : T + 3;
-#pragma unroll 1
-    for (int r = r0; r < r1; ++r)
-    {
-        const Sample *p = R + r * s.sr;
-        int mid;
-        if (xf)
-        {
-            mid = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) mid += cx[k] * (int)__ldg(p + k);
-            mid >>= shift1;
-        }
-        else
-            mid = ((int)__ldg(p + 3) << 6) >> shift1;
-        mids[r * 32] = mid;
-    }
-    int d[T];
-    const Sample *srcCol = s.srcS + (tileY * T) * s.t.w + tileX * T + j;
-    if (yf)
-    {
-#pragma unroll
-        for (int i = 0; i < T; ++i)
-        {
-            int v = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v += cy[k] * mids[(i + k) * 32];
-            d[i] = (int)srcCol[i * s.t.w] - hvbClip3(0, maxv, (v + (1 << (5 + shift3))) >> (6 + shift3));
-        }
-    }
-    else
-    {
-#pragma unroll
-        for (int i = 0; i < T; ++i)
-            d[i] = (int)srcCol[i * s.t.w] - hvbClip3(0, maxv, (64 * mids[(i + 3) * 32] + (1 << (5 + shift3))) >> (6 + shift3));
-    }
-    // vertical butterfly in registers
-#pragma unroll
-    for (int half = T / 2; half >= 1; half >>= 1)
-#pragma unroll
-        for (int base = 0; base < T; base += 2 * half)
-#pragma unroll
-            for (int i = 0; i < half; ++i)
-            {
-                const int a = d[base + i], b = d[base + i + half];
-                d[base + i] = a + b;
-                d[base + i + half] = a - b;
-            }
-    // horizontal butterfly across the T lanes of the group
-#pragma unroll
-    for (int m = 1; m < T; m <<= 1)
-#pragma unroll
-        for (int i = 0; i < T; ++i)
-        {
-            const int o = __shfl_xor_sync(0xffffffffu, d[i], m);
-            d[i] = (j & m) ? o - d[i] : d[i] + o;
-        }
-    int acc = 0;
-#pragma unroll
-    for (int i = 0; i < T; ++i) acc += abs(d[i]);
-#pragma unroll
-    for (int m = 1; m < T; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
-    // havoc/hadamard.cpp:81-97: 4x4 (s+1)>>1, 8x8 (s+2)>>2, 16-bit samples >> 2 more
-    acc = (acc + T / 4) >> (LOG2T - 1);
-    return sizeof(Sample) == 2 ? acc >> 2 : acc;
-}
-
-// measureSatd of the prediction at each of `nCand` quarter-pel vectors (sMv) against the source block
-template <typename Sample, int LOG2T>
-__device__ void subpelEval(const Search<Sample> &s, const int *sMvx, const int *sMvy, int nCand, int *sSatd, int bitDepth)
-{
-    constexpr int T = 1 << LOG2T, kGroups = 32 / T;
-    const int tilesX = s.t.w >> LOG2T, tiles = tilesX * (s.t.h >> LOG2T), jobs = nCand * tiles;
-    const int group = s.lane / T, j = s.lane % T;
-    for (int base = 0; base < jobs; base += kGroups)
-    {
-        const int job = base + group;
-        const bool valid = job < jobs;
-        const int jj = valid ? job : jobs - 1;
-        const int cand = jj / tiles, tile = jj - cand * tiles;
-        const int ty = tile / tilesX, tx = tile - ty * tilesX;
-        const int v = tileSatd<Sample, LOG2T>(s, tx, ty, sMvx[cand], sMvy[cand], j, bitDepth);
-        if (valid && j == 0) atomicAdd(&sSatd[cand], v);
-    }
-    __syncwarp();
-}
-
 // The integer search of the PUs larger than 8x8, a warp each (the smaller ones: hvb_me_small.cu); hvb_me_subpel.cu then
 // refines the whole batch in its own launch.
 template <typename Sample>
@@ -544,7 +425,6 @@ __global__ void __launch_bounds__(kWarps * 32)
         const hvb_me_task t = tasks[i];
         if (t.w <= 8 && t.h <= 8) continue; // PUs up to 8x8: hvb_me_small.cu, four per warp
         Search<Sample> s(t, planes, sSrc, lane);
-        s.sMid = nullptr;
         long long costMvdZero[2] = {0, 0};
         const bool early = fullPel(s, costMvdZero);
 
@@ -622,18 +502,14 @@ __global__ void __launch_bounds__(kWarps * 32)
 {
     extern __shared__ __align__(16) uint32_t smemMe[];
     constexpr int kBlockWords = sizeof(Sample) == 1 ? 64 * 64 / 4 : kSrcWords;
-    constexpr int kWordsPerWarp = kBlockWords + kExtraWords;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *sSrc = smemMe + warp * kWordsPerWarp;
-    int *sScratch = reinterpret_cast<int *>(sSrc + kBlockWords);
-    int *sMvx = sScratch, *sMvy = sScratch + 10, *sSatd = sScratch + 20;
+    uint32_t *sSrc = smemMe + warp * kBlockWords;
     const int warpsTotal = gridDim.x * kWarps;
     for (int i = blockIdx.x * kWarps + warp; i < n; i += warpsTotal)
     {
         const hvb_me_bi_task bt = tasks[i];
         const hvb_me_task &t = reinterpret_cast<const hvb_me_task &>(bt);
         Search<Sample> s(t, planes, sSrc, lane, false);
-        s.sMid = sScratch + 32;
 
         // ---- ideal block (:1518-1548) ----
         {
@@ -687,32 +563,7 @@ __global__ void __launch_bounds__(kWarps * 32)
         r.nSad = side * ((side + 3) / 4) * 4; // what the reference's SAD4 calls evaluate
         r.reserved = 0;
 
-        // ---- fractional rounds (:1628-1650): 3x3 at half- then quarter-sample spacing, best cost reset before each ----
-        if (bt.halfPel)
-            for (int step = 2; step > 0; step -= bt.quarterPel ? 1 : 2)
-            {
-                const hvb_mv origin = s.best.mv;
-                s.best.cost = 0x7fffffffffffffffLL;
-                if (lane < 9)
-                {
-                    sMvx[lane] = origin.x + (lane % 3 - 1) * step;
-                    sMvy[lane] = origin.y + (lane / 3 - 1) * step;
-                    sSatd[lane] = 0;
-                }
-                __syncwarp();
-                if (sizeof(Sample) == 1)
-                    subpel::evalRound(reinterpret_cast<const uint8_t *>(s.srcS), bt.w, bt.h, reinterpret_cast<const uint8_t *>(s.ref), s.sr,
-                                      origin.x, origin.y, step, kCandGrid, 9, reinterpret_cast<uint8_t *>(s.sMid), sSatd, lane);
-                else if (((bt.w | bt.h) & 7) == 0)
-                    subpelEval<Sample, 3>(s, sMvx, sMvy, 9, sSatd, bitDepth);
-                else
-                    subpelEval<Sample, 2>(s, sMvx, sMvy, 9, sSatd, bitDepth);
-                const int me = min(lane, 8);
-                Cand c = s.makeCandidate(hvb_mv{(int16_t)sMvx[me], (int16_t)sMvy[me]});
-                c.cost += (long long)bt.lambda * sSatd[me];
-                s.considerLanes(c, lane < 9);
-                __syncwarp();
-            }
+        // the fractional rounds (:1628-1650) run in hvb_me_subpel.cu's kernel (BI = true), from mvInteger
         r.mv = s.best.mv;
         r.mvd = s.best.mvd;
         r.mvpFlag = s.best.mvpFlag;
@@ -774,6 +625,8 @@ extern "C" int hvb_me_search_batch(hvb_context *ctx, const hvb_me_task *tasks, i
     return hvbStageOut(ctx, out, sizeof(hvb_me_result) * n, mem, st);
 }
 
+int hvbLaunchMeBiSubpel(hvb_context *ctx, const hvb_me_bi_task *dTasks, int n, hvb_me_bi_result *dOut); // hvb_me_subpel.cu
+
 extern "C" int hvb_me_bi_search_batch(hvb_context *ctx, const hvb_me_bi_task *tasks, int n, hvb_me_bi_result *out, hvb_mem mem)
 {
     HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && out)));
@@ -789,16 +642,18 @@ extern "C" int hvb_me_bi_search_batch(hvb_context *ctx, const hvb_me_bi_task *ta
     auto *dO = static_cast<hvb_me_bi_result *>(st.dOut);
     if (ctx->bps == 1)
     {
-        const int smem = kWarps * (64 * 64 / 4 + kExtraWords) * 4;
+        const int smem = kWarps * (64 * 64 / 4) * 4;
         cudaFuncSetAttribute(meBiSearchKernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         meBiSearchKernel<uint8_t><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
     }
     else
     {
-        const int smem = kWarps * (kSrcWords + kExtraWords) * 4;
+        const int smem = kWarps * kSrcWords * 4;
         cudaFuncSetAttribute(meBiSearchKernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         meBiSearchKernel<uint16_t><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
     }
     HVB_LAUNCH_CHECK(ctx, "meBiSearchKernel");
+    rc = hvbLaunchMeBiSubpel(ctx, dT, n, dO);
+    if (rc) return rc;
     return hvbStageOut(ctx, out, sizeof(hvb_me_bi_result) * n, mem, st);
 }

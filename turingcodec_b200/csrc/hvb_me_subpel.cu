@@ -41,7 +41,7 @@ constexpr int kPlaneHalfwords = 9 * kColStride;
 constexpr int kUnitMidBytes = 3 * kPlaneHalfwords * 2;      // 1080
 constexpr int kPredRow = 12;              // half-pel round: samples per prediction row (9 columns + pad)
 constexpr int kPredPlane = 112;           // 9 rows x 12, padded (samples)
-constexpr int kUnitPredSamples = 512;     // half-pel: 4 planes x 112; quarter-pel: 8 candidates x 8 rows x 8
+constexpr int kUnitPredSamples = 576;     // half-pel: 4 planes x 112; quarter-pel: 8 (bi: 9) candidates x 8 rows x 8
 constexpr int kUnitSrcSamples = 64;
 
 template <typename Sample>
@@ -49,7 +49,8 @@ struct UnitDesc
 {
     const Sample *ref; // sample (0,0) of the unit in the reference plane at the integer part of the round's centre
     int slot;           // PU of the chunk (0..3) the unit belongs to
-    int uwuh;           // uw | uh << 8 | valid << 16 (padding units of the last group repeat the last unit and are not summed)
+    int uwuh;           // uw | uh << 8 | valid << 16 | x offset in the PU << 17 | y offset << 24 (padding units of the last group
+                        // repeat the last unit and are not summed)
 };
 
 template <typename Sample>
@@ -68,6 +69,10 @@ struct WarpSmem
     const Sample *srcBase[kGroup];
     int stride[kGroup];           // reference stride; source stride in srcStride
     int srcStride[kGroup];
+    // bi-prediction refinement only: the other list's picture at (x0, y0), its stride and its (clamped) vector
+    const Sample *otherBase[kGroup];
+    int otherStride[kGroup];
+    int omvx[kGroup], omvy[kGroup];
 };
 
 // 8-tap luma filters (havoc/pred_inter.cpp:39-69) packed as s8x4 words, taps 0..3 and 4..7
@@ -381,17 +386,19 @@ __device__ __forceinline__ void vPassHalf(WarpSmem<Sample> &s, const Depth &D, i
 
 // ---- V pass, quarter-pel round: candidate q (grid index gi = q + (q >= 4)) = plane gi % 3 at the vertical quarter
 // offset hy + gi / 3 - 1; (unit, candidate, column) jobs; preds[u][q][r][c], 8 bytes per row.
-template <typename Sample>
+template <typename Sample, bool NINE>
 __device__ __forceinline__ void vPassQuarter(WarpSmem<Sample> &s, const Depth &D, int lane)
 {
 #pragma unroll 1
-    for (int it = 0; it < 8; ++it)
+    for (int it = 0; it < (NINE ? 9 : 8); ++it)
     {
-        const int job = lane + 32 * it, u = job >> 6, q = (job >> 3) & 7, c = job & 7;
+        // uni: 8 candidates (the centre is not re-evaluated); bi: the whole 3x3 grid
+        const int job = lane + 32 * it, c = job & 7, uq = job >> 3;
+        const int u = NINE ? (uq * 7282) >> 16 : uq >> 3, q = NINE ? uq - 9 * u : uq & 7;
         const UnitDesc<Sample> d = s.unit[u];
         const int uw = d.uwuh & 0xff, uh = (d.uwuh >> 8) & 0xff;
         if (c >= uw) continue;
-        const int gi = q + (q >= 4), pl = gi % 3, yq = (s.cy[d.slot] & 3) + gi / 3 - 1;
+        const int gi = NINE ? q : q + (q >= 4), pl = gi % 3, yq = (s.cy[d.slot] & 3) + gi / 3 - 1;
         const uint32_t t0 = kTapWords[yq & 3][0], t1 = kTapWords[yq & 3][1];
         Column col;
         col.load(s.mids[u] + pl * kPlaneHalfwords + c * kColStride, (yq >> 2) + 1);
@@ -422,10 +429,11 @@ __device__ __forceinline__ const Sample *halfCand(const Sample *preds, int gi, i
 }
 
 // ---- SATD of every (unit, candidate) of the group on the tensor cores -----------------------------------------
-template <typename Sample, bool HALF, bool T8>
+template <typename Sample, bool HALF, bool T8, bool NINE>
 __device__ __forceinline__ void satdPass(WarpSmem<Sample> &s, const HadamardA &A, int lane)
 {
-    constexpr int ncand = HALF ? 9 : 8;
+    constexpr int ncand = (HALF || NINE) ? 9 : 8;
+    constexpr bool kDiv9 = ncand == 9;
     constexpr int ncols = kGroup * ncand * (T8 ? 1 : 2);
     constexpr bool k16 = sizeof(Sample) == 2;
     const int g = lane >> 2, t = lane & 3;
@@ -434,9 +442,9 @@ __device__ __forceinline__ void satdPass(WarpSmem<Sample> &s, const HadamardA &A
     {
         const int col = min(base + g, ncols - 1);
         const int tile = T8 ? 0 : col & 1, uc = T8 ? col : col >> 1;
-        const int u = HALF ? (uc * 7282) >> 16 : uc >> 3; // / 9
+        const int u = kDiv9 ? (uc * 7282) >> 16 : uc >> 3; // / 9
         const int cand = uc - u * ncand;
-        const int gi = HALF ? cand : cand + (cand >= 4);
+        const int gi = kDiv9 ? cand : cand + (cand >= 4);
         const int uw = s.unit[u].uwuh & 0xff;
         int off = 0, prow = 8;
         const Sample *P;
@@ -514,19 +522,103 @@ __device__ __forceinline__ void satdPass(WarpSmem<Sample> &s, const HadamardA &A
             if (c2 < ncols)
             {
                 const int uc2 = T8 ? c2 : c2 >> 1;
-                const int u2 = HALF ? (uc2 * 7282) >> 16 : uc2 >> 3;
+                const int u2 = kDiv9 ? (uc2 * 7282) >> 16 : uc2 >> 3;
                 const int cand2 = uc2 - u2 * ncand;
                 const int slot = s.unit[u2].slot;
                 int v = (sum + (T8 ? 2 : 1)) >> (T8 ? 2 : 1);
                 if (k16) v >>= 2;
-                if (s.unit[u2].uwuh >> 16) atomicAdd(&s.satd[slot][HALF ? cand2 : cand2 + (cand2 >= 4)], v);
+                if ((s.unit[u2].uwuh >> 16) & 1) atomicAdd(&s.satd[slot][kDiv9 ? cand2 : cand2 + (cand2 >= 4)], v);
             }
         }
     }
 }
 
+// ---- bi-prediction refinement: the "source" is the ideal block 2 * src - pred(other list) (Search.hpp:1518-1548) -------
+// Each unit's 8-tap prediction from the other list's picture at its (fractional) vector is rebuilt here -- one
+// horizontal plane, one vertical pass, 1/8 of a quarter-pel round -- and SubtractBi'd into the unit's source slot.
+template <typename Sample>
+__device__ __forceinline__ void idealPass(WarpSmem<Sample> &s, const Depth &D, int lane)
+{
+    // H: (unit, support row) jobs, plane 0 of the unit's mids
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j)
+    {
+        const int job = lane + 32 * j, u = job >> 4, r = job & 15;
+        const UnitDesc<Sample> d = s.unit[u];
+        const int uw = d.uwuh & 0xff, uh = (d.uwuh >> 8) & 0xff, slot = d.slot;
+        if (r >= uh + 8) continue;
+        const int ux = (d.uwuh >> 17) & 0x7f, uy = (d.uwuh >> 24) & 0x7f; // the unit's offset in the PU
+        const int mvx = s.omvx[slot], mvy = s.omvy[slot], fx = mvx & 3;
+        const Sample *p = s.otherBase[slot] + (intptr_t)(uy + (mvy >> 2) + r - 4) * s.otherStride[slot] + ux + (mvx >> 2) - 3;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+        const unsigned sh = (unsigned)(a & 3) * 8;
+        const uint32_t t0 = kTapWords[fx][0], t1 = kTapWords[fx][1];
+        int16_t *mp = s.mids[u] + r;
+        if (sizeof(Sample) == 1)
+        {
+            uint32_t w[5], v[4];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) w[i] = __ldg(q + i);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], sh);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < uw)
+                {
+                    const int k = c >> 2, sft = (c & 3) * 8;
+                    const uint32_t lo = sft ? __funnelshift_r(v[k], v[k + 1], sft) : v[k];
+                    const uint32_t hi = sft ? __funnelshift_r(v[k + 1], v[k + 2 < 4 ? k + 2 : 3], sft) : v[k + 1];
+                    mp[c * kColStride] = (int16_t)dp4aUS(hi, t1, dp4aUS(lo, t0, 0));
+                }
+        }
+        else
+        {
+            uint32_t w[9], v[8];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) w[i] = __ldg(q + i);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], sh);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < uw)
+                {
+                    const int k = c >> 1;
+                    const bool odd = c & 1;
+                    const uint32_t p0 = odd ? __funnelshift_r(v[k], v[k + 1], 16) : v[k];
+                    const uint32_t p1 = odd ? __funnelshift_r(v[k + 1], v[k + 2], 16) : v[k + 1];
+                    const uint32_t p2 = odd ? __funnelshift_r(v[k + 2], v[k + 3], 16) : v[k + 2];
+                    const uint32_t p3 = odd ? __funnelshift_r(v[k + 3], v[k + 4 < 8 ? k + 4 : 7], 16) : v[k + 3];
+                    mp[c * kColStride] = (int16_t)(tap8(p0, p1, p2, p3, t0, t1, 0) >> D.shift1);
+                }
+        }
+    }
+    __syncwarp();
+    // V + SubtractBi: (unit, column) jobs; support row 0 is picture row -4, so output row r reads rows r + 1 .. r + 8
+    {
+        const int u = lane >> 3, c = lane & 7;
+        const UnitDesc<Sample> d = s.unit[u];
+        const int uw = d.uwuh & 0xff, uh = (d.uwuh >> 8) & 0xff;
+        if (c < uw)
+        {
+            const int fy = s.omvy[d.slot] & 3;
+            const uint32_t t0 = kTapWords[fy][0], t1 = kTapWords[fy][1];
+            const int idealMax = (1 << (6 + 2 * (int)sizeof(Sample))) - 1; // SubtractBi's bit depth (Search.hpp:1541-1548)
+            Column col;
+            col.load(s.mids[u] + c * kColStride, 1);
+            Sample *dst = s.src[u] + c;
+            const int pred[8] = {col.template out<0>(t0, t1, D), col.template out<1>(t0, t1, D), col.template out<2>(t0, t1, D),
+                                 col.template out<3>(t0, t1, D), col.template out<4>(t0, t1, D), col.template out<5>(t0, t1, D),
+                                 col.template out<6>(t0, t1, D), col.template out<7>(t0, t1, D)};
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < uh) dst[r * 8] = (Sample)min(max(2 * (int)dst[r * 8] - pred[r], 0), idealMax);
+        }
+    }
+}
+
 // one round over every unit of the chunk's PUs of one tile mode
-template <typename Sample, bool HALF, bool T8>
+template <typename Sample, bool HALF, bool T8, bool BI>
 __device__ __forceinline__ void roundPass(WarpSmem<Sample> &s, const HadamardA &A, const Depth &D, int lane)
 {
     // units of the participating PUs, concatenated
@@ -545,7 +637,7 @@ __device__ __forceinline__ void roundPass(WarpSmem<Sample> &s, const HadamardA &
             UnitDesc<Sample> d;
             d.ref = s.refBase[slot] + (intptr_t)(uy * uh + (s.cy[slot] >> 2)) * s.stride[slot] + ux * uw + (s.cx[slot] >> 2);
             d.slot = slot;
-            d.uwuh = (geom & 0xffff) | (id < total) << 16;
+            d.uwuh = (geom & 0xffff) | (id < total) << 16 | (ux * uw) << 17 | (uy * uh) << 24;
             s.unit[lane] = d;
         }
         {
@@ -568,35 +660,47 @@ __device__ __forceinline__ void roundPass(WarpSmem<Sample> &s, const HadamardA &
             }
         }
         __syncwarp();
+        if (BI)
+        {
+            idealPass(s, D, lane);
+            __syncwarp();
+        }
         hPass<Sample, HALF>(s, D, lane);
         __syncwarp();
         if (HALF)
             vPassHalf(s, D, lane);
         else
-            vPassQuarter(s, D, lane);
+            vPassQuarter<Sample, BI>(s, D, lane);
         __syncwarp();
-        satdPass<Sample, HALF, T8>(s, A, lane);
+        satdPass<Sample, HALF, T8, BI>(s, A, lane);
         __syncwarp();
     }
 }
 
-template <typename Sample>
+// BI = false: uni-directional search (hvb_me_task / hvb_me_result).  BI = true: the fractional rounds of searchMotionBi
+// (hvb_me_bi_task / hvb_me_bi_result, Search.hpp:1628-1650): the source is the ideal block, both rounds evaluate the
+// whole 3x3 grid with the best cost reset before each, a candidate's rate is that of its cheaper predictor.
+template <typename Sample, bool BI>
 __global__ void __launch_bounds__(kWarps * 32)
-    meSubpelKernel(const HvbPlane *__restrict__ planes, const hvb_me_task *__restrict__ tasks, int n, hvb_me_result *__restrict__ out,
-                   int bitDepth)
+    meSubpelKernel(const HvbPlane *__restrict__ planes, const void *__restrict__ tasksV, int n, void *__restrict__ outV, int bitDepth)
 {
     extern __shared__ __align__(16) uint8_t smemSubpel[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpSmem<Sample> &s = reinterpret_cast<WarpSmem<Sample> *>(smemSubpel)[warp];
     const HadamardA A(lane);
     const Depth D(sizeof(Sample) == 1 ? 8 : bitDepth);
+    // hvb_me_bi_task shares its first 56 bytes (pictures, block, predictors, rates, lambda, limits) with hvb_me_task
+    const hvb_me_task *tasks = static_cast<const hvb_me_task *>(tasksV);
+    const hvb_me_bi_task *biTasks = static_cast<const hvb_me_bi_task *>(tasksV);
+    hvb_me_result *out = static_cast<hvb_me_result *>(outV);
+    hvb_me_bi_result *biOut = static_cast<hvb_me_bi_result *>(outV);
     const int chunks = (n + kGroup - 1) / kGroup, warpsTotal = gridDim.x * kWarps;
     for (int chunk = blockIdx.x * kWarps + warp; chunk < chunks; chunk += warpsTotal)
     {
         // lane k < 4 owns PU 4 chunk + k for the bookkeeping
         const int i = chunk * kGroup + lane;
         const bool mine = lane < kGroup && i < n;
-        int w = 8, h = 8, lambda = 0, halfPel = 0, quarterPel = 0, tiles8 = 1;
+        int w = 8, h = 8, lambda = 0, halfPel = 0, quarterPel = 0, tiles8 = 1, mvpFlag = 0;
         hvb_mv mv{0, 0}, mvd{0, 0};
         long long bestCost = 0;
         if (mine)
@@ -605,11 +709,29 @@ __global__ void __launch_bounds__(kWarps * 32)
             w = t.w;
             h = t.h;
             lambda = t.lambda;
-            halfPel = t.halfPel;
-            quarterPel = t.halfPel && t.quarterPel;
+            if (BI)
+            {
+                const hvb_me_bi_task &bt = biTasks[i];
+                halfPel = bt.halfPel;
+                quarterPel = bt.halfPel && bt.quarterPel;
+                mv = biOut[i].mvInteger; // the integer grid left its winner here
+                const HvbPlane &op = planes[bt.other_pic * 3];
+                s.otherBase[lane] = reinterpret_cast<const Sample *>(op.base) + (intptr_t)bt.y0 * op.stride + bt.x0;
+                s.otherStride[lane] = op.stride;
+                // only the integer part of the other list's vector is clamped; the fraction is kept (:1518-1534)
+                const int ox = min(max(bt.mvOther.x >> 2, (int)bt.limitMin.x), (int)bt.limitMax.x);
+                const int oy = min(max(bt.mvOther.y >> 2, (int)bt.limitMin.y), (int)bt.limitMax.y);
+                s.omvx[lane] = (ox << 2) | (bt.mvOther.x & 3);
+                s.omvy[lane] = (oy << 2) | (bt.mvOther.y & 3);
+            }
+            else
+            {
+                halfPel = t.halfPel;
+                quarterPel = t.halfPel && t.quarterPel;
+                mv = out[i].mv; // the integer search left its winner here
+                mvd = out[i].mvd;
+            }
             tiles8 = ((w | h) & 7) == 0;
-            mv = out[i].mv; // the integer search left its winner here
-            mvd = out[i].mvd;
             const HvbPlane &sp = planes[t.src_pic * 3], &rp = planes[t.ref_pic * 3];
             s.refBase[lane] = reinterpret_cast<const Sample *>(rp.base) + (intptr_t)t.y0 * rp.stride + t.x0;
             s.srcBase[lane] = reinterpret_cast<const Sample *>(sp.base) + (intptr_t)t.y0 * sp.stride + t.x0;
@@ -621,8 +743,9 @@ __global__ void __launch_bounds__(kWarps * 32)
         else if (lane < kGroup)
         {
             s.geom[lane] = 8 | 8 << 8 | 1 << 16;
-            s.refBase[lane] = s.srcBase[lane] = nullptr;
-            s.stride[lane] = s.srcStride[lane] = 0;
+            s.refBase[lane] = s.srcBase[lane] = s.otherBase[lane] = nullptr;
+            s.stride[lane] = s.srcStride[lane] = s.otherStride[lane] = 0;
+            s.omvx[lane] = s.omvy[lane] = 0;
         }
         const int nUnits = mine ? (w * h) >> (tiles8 ? 6 : 5) : 0;
 #pragma unroll 1
@@ -647,53 +770,97 @@ __global__ void __launch_bounds__(kWarps * 32)
                 if (round == 0)
                 {
                     if (mode == 0)
-                        roundPass<Sample, true, true>(s, A, D, lane);
+                        roundPass<Sample, true, true, BI>(s, A, D, lane);
                     else
-                        roundPass<Sample, true, false>(s, A, D, lane);
+                        roundPass<Sample, true, false, BI>(s, A, D, lane);
                 }
                 else
                 {
                     if (mode == 0)
-                        roundPass<Sample, false, true>(s, A, D, lane);
+                        roundPass<Sample, false, true, BI>(s, A, D, lane);
                     else
-                        roundPass<Sample, false, false>(s, A, D, lane);
+                        roundPass<Sample, false, false, BI>(s, A, D, lane);
                 }
             }
             __syncwarp();
             if (mine && takesPart)
             {
-                // patternSearch with maxIterations = 1 (Search.hpp:2011-2060): costMv = rateOf(mvd) + lambda * SATD
-                const int step = round == 0 ? 2 : 1, ncand = round == 0 ? 9 : 8;
-                int best = -1;
-                for (int k = 0; k < ncand; ++k)
+                const int step = round == 0 ? 2 : 1;
+                if (BI)
                 {
-                    const int gi = round == 0 ? kHalfOrder[k] : kQuarterOrder[k];
-                    const int dx = (gi % 3 - 1) * step, dy = (gi / 3 - 1) * step;
-                    const long long c = rateOfMvd((int16_t)(mvd.x + dx), (int16_t)(mvd.y + dy)) + (long long)lambda * s.satd[lane][gi];
-                    if (round == 0 && k == 0)
-                        bestCost = c; // the origin (tryOrigin)
-                    else if (c < bestCost)
+                    // 3x3 grid in raster order, best cost reset (Search.hpp:1628-1650); MvCandidate picks the cheaper predictor
+                    const hvb_me_task &t = tasks[i];
+                    const hvb_mv origin = mv;
+                    bestCost = 0x7fffffffffffffffLL;
+                    for (int gi = 0; gi < 9; ++gi)
                     {
-                        best = gi;
-                        bestCost = c;
+                        const int cx = origin.x + (gi % 3 - 1) * step, cy = origin.y + (gi / 3 - 1) * step;
+                        int dx = (int16_t)(cx - t.mvp[0].x), dy = (int16_t)(cy - t.mvp[0].y), flag = 0;
+                        long long c = rateOfMvd(dx, dy) + t.rateMvpFlag[0];
+                        const int dx1 = (int16_t)(cx - t.mvp[1].x), dy1 = (int16_t)(cy - t.mvp[1].y);
+                        const long long c1 = rateOfMvd(dx1, dy1) + t.rateMvpFlag[1];
+                        if (c1 < c)
+                        {
+                            c = c1;
+                            dx = dx1;
+                            dy = dy1;
+                            flag = 1;
+                        }
+                        c += (long long)lambda * s.satd[lane][gi];
+                        if (c < bestCost)
+                        {
+                            bestCost = c;
+                            mv = hvb_mv{(int16_t)cx, (int16_t)cy};
+                            mvd = hvb_mv{(int16_t)dx, (int16_t)dy};
+                            mvpFlag = flag;
+                        }
                     }
                 }
-                if (best >= 0)
+                else
                 {
-                    const int dx = (best % 3 - 1) * step, dy = (best / 3 - 1) * step;
-                    mv.x = (int16_t)(mv.x + dx);
-                    mv.y = (int16_t)(mv.y + dy);
-                    mvd.x = (int16_t)(mvd.x + dx);
-                    mvd.y = (int16_t)(mvd.y + dy);
+                    // patternSearch with maxIterations = 1 (Search.hpp:2011-2060): costMv = rateOf(mvd) + lambda * SATD
+                    const int ncand = round == 0 ? 9 : 8;
+                    int best = -1;
+                    for (int k = 0; k < ncand; ++k)
+                    {
+                        const int gi = round == 0 ? kHalfOrder[k] : kQuarterOrder[k];
+                        const int dx = (gi % 3 - 1) * step, dy = (gi / 3 - 1) * step;
+                        const long long c = rateOfMvd((int16_t)(mvd.x + dx), (int16_t)(mvd.y + dy)) + (long long)lambda * s.satd[lane][gi];
+                        if (round == 0 && k == 0)
+                            bestCost = c; // the origin (tryOrigin)
+                        else if (c < bestCost)
+                        {
+                            best = gi;
+                            bestCost = c;
+                        }
+                    }
+                    if (best >= 0)
+                    {
+                        const int dx = (best % 3 - 1) * step, dy = (best / 3 - 1) * step;
+                        mv.x = (int16_t)(mv.x + dx);
+                        mv.y = (int16_t)(mv.y + dy);
+                        mvd.x = (int16_t)(mvd.x + dx);
+                        mvd.y = (int16_t)(mvd.y + dy);
+                    }
                 }
             }
             __syncwarp();
         }
         if (mine && halfPel)
         {
-            out[i].mv = mv;
-            out[i].mvd = mvd;
-            out[i].subpelCost = bestCost;
+            if (BI)
+            {
+                biOut[i].mv = mv;
+                biOut[i].mvd = mvd;
+                biOut[i].mvpFlag = mvpFlag;
+                biOut[i].cost = bestCost;
+            }
+            else
+            {
+                out[i].mv = mv;
+                out[i].mvd = mvd;
+                out[i].subpelCost = bestCost;
+            }
         }
         __syncwarp();
     }
@@ -701,25 +868,30 @@ __global__ void __launch_bounds__(kWarps * 32)
 
 } // namespace
 
-// called by hvb_me_search_batch (hvb_me.cu) after the integer search, on the same stream
-template <typename Sample>
-static int launchMeSubpel(hvb_context *ctx, const hvb_me_task *dTasks, int n, hvb_me_result *dOut)
+// called by hvb_me_search_batch / hvb_me_bi_search_batch (hvb_me.cu) after the integer stage, on the same stream
+template <typename Sample, bool BI>
+static int launchMeSubpel(hvb_context *ctx, const void *dTasks, int n, void *dOut)
 {
     const int chunks = (n + kGroup - 1) / kGroup;
     int blocks = (chunks + kWarps - 1) / kWarps;
     const int smem = kWarps * (int)sizeof(WarpSmem<Sample>);
     static_assert(sizeof(WarpSmem<Sample>) % 16 == 0, "per-warp shared slices must stay 16-byte aligned");
-    cudaFuncSetAttribute(meSubpelKernel<Sample>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(meSubpelKernel<Sample, BI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int perSm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, meSubpelKernel<Sample>, kWarps * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, meSubpelKernel<Sample, BI>, kWarps * 32, smem);
     const int cap = ctx->smCount * (perSm > 0 ? perSm : 1);
     if (blocks > cap) blocks = cap;
-    meSubpelKernel<Sample><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dTasks, n, dOut, ctx->bitDepth);
+    meSubpelKernel<Sample, BI><<<blocks, kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dTasks, n, dOut, ctx->bitDepth);
     HVB_LAUNCH_CHECK(ctx, "meSubpelKernel");
     return HVB_OK;
 }
 
 int hvbLaunchMeSubpel(hvb_context *ctx, const hvb_me_task *dTasks, int n, hvb_me_result *dOut)
 {
-    return ctx->bps == 1 ? launchMeSubpel<uint8_t>(ctx, dTasks, n, dOut) : launchMeSubpel<uint16_t>(ctx, dTasks, n, dOut);
+    return ctx->bps == 1 ? launchMeSubpel<uint8_t, false>(ctx, dTasks, n, dOut) : launchMeSubpel<uint16_t, false>(ctx, dTasks, n, dOut);
+}
+
+int hvbLaunchMeBiSubpel(hvb_context *ctx, const hvb_me_bi_task *dTasks, int n, hvb_me_bi_result *dOut)
+{
+    return ctx->bps == 1 ? launchMeSubpel<uint8_t, true>(ctx, dTasks, n, dOut) : launchMeSubpel<uint16_t, true>(ctx, dTasks, n, dOut);
 }
