@@ -53,11 +53,11 @@ struct UnitDesc
                         // repeat the last unit and are not summed)
 };
 
-template <typename Sample>
-struct WarpSmem
+template <typename Sample, bool BI>
+struct alignas(16) WarpSmem
 {
     int16_t mids[kGroup][3 * kPlaneHalfwords];
-    Sample preds[kGroup][kUnitPredSamples];
+    Sample preds[kGroup][BI ? kUnitPredSamples : 512]; // the uni search keeps four 256-thread blocks per SM at 8 bit
     Sample src[kGroup][kUnitSrcSamples];
     UnitDesc<Sample> unit[kGroup];
     int satd[kGroup][12];
@@ -70,9 +70,9 @@ struct WarpSmem
     int stride[kGroup];           // reference stride; source stride in srcStride
     int srcStride[kGroup];
     // bi-prediction refinement only: the other list's picture at (x0, y0), its stride and its (clamped) vector
-    const Sample *otherBase[kGroup];
-    int otherStride[kGroup];
-    int omvx[kGroup], omvy[kGroup];
+    const Sample *otherBase[BI ? kGroup : 1];
+    int otherStride[BI ? kGroup : 1];
+    int omvx[BI ? kGroup : 1], omvy[BI ? kGroup : 1];
 };
 
 // 8-tap luma filters (havoc/pred_inter.cpp:39-69) packed as s8x4 words, taps 0..3 and 4..7
@@ -177,8 +177,8 @@ __device__ __forceinline__ Frag loadFrag(const uint16_t *p, int off)
 // HALF: plane 0 = integer samples << 6 (columns 0..uw-1), plane 1 = half-pel columns x - 1/2 (x = 0..uw), and the
 // candidates that need no vertical filter: P00 (plane 0 of preds) and PB (plane 1 of preds).
 // QUARTER: planes v = 0..2 at the horizontal quarter offsets hx + v - 1.
-template <typename Sample, bool HALF>
-__device__ __forceinline__ void hPass(WarpSmem<Sample> &s, const Depth &D, int lane)
+template <typename Sample, bool HALF, bool BI>
+__device__ __forceinline__ void hPass(WarpSmem<Sample, BI> &s, const Depth &D, int lane)
 {
 #pragma unroll 1
     for (int j = 0; j < 2; ++j)
@@ -352,8 +352,8 @@ struct Column
 
 // ---- V pass, half-pel round: PC (plane 2 of preds) = vertical half-pel of the integer columns, (uh+1) x uw;
 // PD (plane 3) = vertical half-pel of the half-pel columns, (uh+1) x (uw+1).  17 column jobs per unit.
-template <typename Sample>
-__device__ __forceinline__ void vPassHalf(WarpSmem<Sample> &s, const Depth &D, int lane)
+template <typename Sample, bool BI>
+__device__ __forceinline__ void vPassHalf(WarpSmem<Sample, BI> &s, const Depth &D, int lane)
 {
     const uint32_t t0 = kTapWords[2][0], t1 = kTapWords[2][1];
 #pragma unroll 1
@@ -387,7 +387,7 @@ __device__ __forceinline__ void vPassHalf(WarpSmem<Sample> &s, const Depth &D, i
 // ---- V pass, quarter-pel round: candidate q (grid index gi = q + (q >= 4)) = plane gi % 3 at the vertical quarter
 // offset hy + gi / 3 - 1; (unit, candidate, column) jobs; preds[u][q][r][c], 8 bytes per row.
 template <typename Sample, bool NINE>
-__device__ __forceinline__ void vPassQuarter(WarpSmem<Sample> &s, const Depth &D, int lane)
+__device__ __forceinline__ void vPassQuarter(WarpSmem<Sample, NINE> &s, const Depth &D, int lane)
 {
 #pragma unroll 1
     for (int it = 0; it < (NINE ? 9 : 8); ++it)
@@ -430,7 +430,7 @@ __device__ __forceinline__ const Sample *halfCand(const Sample *preds, int gi, i
 
 // ---- SATD of every (unit, candidate) of the group on the tensor cores -----------------------------------------
 template <typename Sample, bool HALF, bool T8, bool NINE>
-__device__ __forceinline__ void satdPass(WarpSmem<Sample> &s, const HadamardA &A, int lane)
+__device__ __forceinline__ void satdPass(WarpSmem<Sample, NINE> &s, const HadamardA &A, int lane)
 {
     constexpr int ncand = (HALF || NINE) ? 9 : 8;
     constexpr bool kDiv9 = ncand == 9;
@@ -537,7 +537,7 @@ __device__ __forceinline__ void satdPass(WarpSmem<Sample> &s, const HadamardA &A
 // Each unit's 8-tap prediction from the other list's picture at its (fractional) vector is rebuilt here -- one
 // horizontal plane, one vertical pass, 1/8 of a quarter-pel round -- and SubtractBi'd into the unit's source slot.
 template <typename Sample>
-__device__ __forceinline__ void idealPass(WarpSmem<Sample> &s, const Depth &D, int lane)
+__device__ __forceinline__ void idealPass(WarpSmem<Sample, true> &s, const Depth &D, int lane)
 {
     // H: (unit, support row) jobs, plane 0 of the unit's mids
 #pragma unroll 1
@@ -619,7 +619,7 @@ __device__ __forceinline__ void idealPass(WarpSmem<Sample> &s, const Depth &D, i
 
 // one round over every unit of the chunk's PUs of one tile mode
 template <typename Sample, bool HALF, bool T8, bool BI>
-__device__ __forceinline__ void roundPass(WarpSmem<Sample> &s, const HadamardA &A, const Depth &D, int lane)
+__device__ __forceinline__ void roundPass(WarpSmem<Sample, BI> &s, const HadamardA &A, const Depth &D, int lane)
 {
     // units of the participating PUs, concatenated
     const int n0 = s.units[0], n1 = n0 + s.units[1], n2 = n1 + s.units[2], total = n2 + s.units[3];
@@ -660,12 +660,12 @@ __device__ __forceinline__ void roundPass(WarpSmem<Sample> &s, const HadamardA &
             }
         }
         __syncwarp();
-        if (BI)
+        if constexpr (BI)
         {
             idealPass(s, D, lane);
             __syncwarp();
         }
-        hPass<Sample, HALF>(s, D, lane);
+        hPass<Sample, HALF, BI>(s, D, lane);
         __syncwarp();
         if (HALF)
             vPassHalf(s, D, lane);
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 {
     extern __shared__ __align__(16) uint8_t smemSubpel[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpSmem<Sample> &s = reinterpret_cast<WarpSmem<Sample> *>(smemSubpel)[warp];
+    WarpSmem<Sample, BI> &s = reinterpret_cast<WarpSmem<Sample, BI> *>(smemSubpel)[warp];
     const HadamardA A(lane);
     const Depth D(sizeof(Sample) == 1 ? 8 : bitDepth);
     // hvb_me_bi_task shares its first 56 bytes (pictures, block, predictors, rates, lambda, limits) with hvb_me_task
@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(kWarps * 32)
             w = t.w;
             h = t.h;
             lambda = t.lambda;
-            if (BI)
+            if constexpr (BI)
             {
                 const hvb_me_bi_task &bt = biTasks[i];
                 halfPel = bt.halfPel;
@@ -743,9 +743,13 @@ __global__ void __launch_bounds__(kWarps * 32)
         else if (lane < kGroup)
         {
             s.geom[lane] = 8 | 8 << 8 | 1 << 16;
-            s.refBase[lane] = s.srcBase[lane] = s.otherBase[lane] = nullptr;
-            s.stride[lane] = s.srcStride[lane] = s.otherStride[lane] = 0;
-            s.omvx[lane] = s.omvy[lane] = 0;
+            s.refBase[lane] = s.srcBase[lane] = nullptr;
+            s.stride[lane] = s.srcStride[lane] = 0;
+            if constexpr (BI)
+            {
+                s.otherBase[lane] = nullptr;
+                s.otherStride[lane] = s.omvx[lane] = s.omvy[lane] = 0;
+            }
         }
         const int nUnits = mine ? (w * h) >> (tiles8 ? 6 : 5) : 0;
 #pragma unroll 1
@@ -874,8 +878,8 @@ static int launchMeSubpel(hvb_context *ctx, const void *dTasks, int n, void *dOu
 {
     const int chunks = (n + kGroup - 1) / kGroup;
     int blocks = (chunks + kWarps - 1) / kWarps;
-    const int smem = kWarps * (int)sizeof(WarpSmem<Sample>);
-    static_assert(sizeof(WarpSmem<Sample>) % 16 == 0, "per-warp shared slices must stay 16-byte aligned");
+    const int smem = kWarps * (int)sizeof(WarpSmem<Sample, BI>);
+    static_assert(sizeof(WarpSmem<Sample, BI>) % 16 == 0, "per-warp shared slices must stay 16-byte aligned");
     cudaFuncSetAttribute(meSubpelKernel<Sample, BI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int perSm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, meSubpelKernel<Sample, BI>, kWarps * 32, smem);
