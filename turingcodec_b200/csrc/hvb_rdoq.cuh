@@ -335,78 +335,76 @@ __device__ __forceinline__ void cgNeighbours(unsigned long long csbf, int xS, in
     below = yS < wcg - 1 ? (int)((csbf >> ((yS + 1) * wcg + xS)) & 1) : 0;
 }
 
-// Rdoq.cpp:889-1023.  Only groups that still hold a non-zero level are looked at, and those have records.
-__device__ inline void signDataHiding(const Engine &e, int lastCgCoded, int16_t *dst)
+// Rdoq.cpp:889-1023 for ONE coefficient group whose final levels are in registers (lv[k], scan order; negMask bit k: the
+// coefficient at scan position k is negative).  `lastCG` is the reference's state: 1 for the first group (from the top)
+// that still holds a level, 0 afterwards.  The reference guards the whole step with "sum of levels >= 2"; a group is only
+// ever touched when it holds two levels at least 4 scan positions apart, which implies that sum, so the guard is
+// not needed here and the step can run while the group's levels are still in registers.
+__device__ __forceinline__ void signDataHidingGroup(const Engine &e, int cg, const int (&lv)[16], unsigned nzMask, unsigned negMask, int lastCG,
+                                                    int16_t *dst)
 {
-    int lastCG = -1;
-    for (int cg = lastCgCoded; cg >= 0; --cg)
+    const int lastNZ = 31 - __clz(nzMask), firstNZ = __ffs(nzMask) - 1;
+    if (lastNZ - firstNZ < 4) return;
+    int absSum = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) absSum += lv[k];
+    const int signbit = (negMask >> firstNZ) & 1;
+    if (signbit == (absSum & 1)) return;
+    const short *sc = e.scan + (cg << 4);
+    const int kStart = lastCG == 1 ? lastNZ : 15;
+    int minCost = 0x7fffffff, minK = -1, finalChange = 0;
+#pragma unroll
+    for (int q4 = 3; q4 >= 0; --q4)
     {
-        const short *sc = e.scan + (cg << 4);
-        int firstNZ = 16, lastNZ = -1, absSum = 0;
-        for (int k = 15; k >= 0; --k)
-            if (dst[sc[k]])
-            {
-                lastNZ = k;
-                break;
-            }
-        if (lastNZ < 0) continue; // an empty group changes nothing (and cannot be the first coded one)
-        for (int k = 0; k < 16; ++k)
-            if (dst[sc[k]])
-            {
-                firstNZ = k;
-                break;
-            }
-        for (int k = firstNZ; k <= lastNZ; ++k) absSum += dst[sc[k]];
-        if (lastCG == -1) lastCG = 1;
-        if (lastNZ - firstNZ >= 4)
+        if (4 * q4 > kStart) continue;
+        // {rateUp, rateDown, sigDelta, deltaU} of the quad's four coefficients, requested together
+        int4 r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] = *reinterpret_cast<const int4 *>(&e.rec[(cg << 4) + 4 * q4 + j].rateUp);
+#pragma unroll
+        for (int j = 3; j >= 0; --j)
         {
-            const int signbit = dst[sc[firstNZ]] > 0 ? 0 : 1;
-            if (signbit != (absSum & 1))
+            const int k = 4 * q4 + j;
+            if (k > kStart) continue;
+            const int level = lv[k];
+            const int rateUp = r[j].x, rateDown = r[j].y, sigDelta = r[j].z, deltaU = r[j].w;
+            int cost, change;
+            if (level != 0)
             {
-                int minCost = 0x7fffffff, minPos = -1, finalChange = 0;
-                for (int k = (lastCG == 1 ? lastNZ : 15); k >= 0; --k)
+                const int up = e.shdFactor * (-deltaU) + rateUp;
+                int down = e.shdFactor * deltaU + rateDown - (abs(level) == 1 ? ((1 << 15) + sigDelta) : 0);
+                if (lastCG == 1 && lastNZ == k && abs(level) == 1) down -= 4 << 15;
+                if (up < down)
                 {
-                    const int pos = sc[k];
-                    const int level = dst[pos];
-                    const HvbCoefRec &r = e.rec[(cg << 4) + k];
-                    int cost, change;
-                    if (level != 0)
-                    {
-                        const int up = e.shdFactor * (-r.deltaU) + r.rateUp;
-                        int down = e.shdFactor * r.deltaU + r.rateDown - (abs(level) == 1 ? ((1 << 15) + r.sigDelta) : 0);
-                        if (lastCG == 1 && lastNZ == k && abs(level) == 1) down -= 4 << 15;
-                        if (up < down)
-                        {
-                            cost = up;
-                            change = 1;
-                        }
-                        else
-                        {
-                            change = -1;
-                            cost = (k == firstNZ && abs(level) == 1) ? 0x7fffffff : down;
-                        }
-                    }
-                    else
-                    {
-                        cost = e.shdFactor * (-abs(r.deltaU)) + (1 << 15) + r.rateUp + r.sigDelta;
-                        change = 1;
-                        if (k < firstNZ && (e.src[pos] >= 0 ? 0 : 1) != signbit) cost = 0x7fffffff;
-                    }
-                    if (cost < minCost)
-                    {
-                        minCost = cost;
-                        finalChange = change;
-                        minPos = pos;
-                    }
+                    cost = up;
+                    change = 1;
                 }
-                if (minPos >= 0)
+                else
                 {
-                    if (dst[minPos] == 32767 || dst[minPos] == -32768) finalChange = -1;
-                    dst[minPos] = (int16_t)(e.src[minPos] >= 0 ? dst[minPos] + finalChange : dst[minPos] - finalChange);
+                    change = -1;
+                    cost = (k == firstNZ && abs(level) == 1) ? 0x7fffffff : down;
                 }
+            }
+            else
+            {
+                cost = e.shdFactor * (-abs(deltaU)) + (1 << 15) + rateUp + sigDelta;
+                change = 1;
+                if (k < firstNZ && (int)((negMask >> k) & 1) != signbit) cost = 0x7fffffff;
+            }
+            if (cost < minCost)
+            {
+                minCost = cost;
+                finalChange = change;
+                minK = k;
             }
         }
-        if (lastCG == 1) lastCG = 0;
+    }
+    if (minK >= 0)
+    {
+        const int minPos = sc[minK];
+        const int cur = dst[minPos];
+        if (cur == 32767 || cur == -32768) finalChange = -1;
+        dst[minPos] = (int16_t)(((negMask >> minK) & 1) ? cur - finalChange : cur + finalChange);
     }
 }
 
@@ -650,59 +648,102 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
             const int cgPos = cgY * (1 << log2Cg) + cgX;
             rdCostTu -= rateCostCgSig[cg];
             if (!((csbf >> cgPos) & 1)) continue;
-            for (int k = 15; k >= 0; --k)
+            // four positions at a time: their levels and records are requested together, then consumed in order
+            const int kStart = cg == lastCg ? (lastSp & 15) : 15;
+#pragma unroll 1
+            for (int q4 = kStart >> 2; q4 >= 0 && !found; --q4)
             {
-                const int sp = cg * 16 + k;
-                if (sp > lastSp) continue;
-                const int pos = e.scan[sp];
-                const int level = dst[pos];
-                if (level)
+                int p4[4], l4[4];
+                longlong2 c4[4]; // {rdCost, rateSig}
+#pragma unroll
+                for (int j = 0; j < 4; ++j) p4[j] = e.scan[cg * 16 + 4 * q4 + j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) l4[j] = dst[p4[j]];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c4[j] = *reinterpret_cast<const longlong2 *>(&rec[cg * 16 + 4 * q4 + j].rdCost);
+#pragma unroll
+                for (int j = 3; j >= 0; --j)
                 {
-                    const int x = pos & mask, y = pos >> log2;
-                    const long long lastCost = scanIdx == 2 ? lastPosCost(e, y, x) : lastPosCost(e, x, y);
-                    const long long total = rdCostTu + lastCost - rec[sp].rateSig;
-                    if (total < best)
+                    const int k = 4 * q4 + j, sp = cg * 16 + k;
+                    if (k > kStart || found) continue;
+                    const int pos = p4[j], level = l4[j];
+                    if (level)
                     {
-                        lastIdx = sp + 1;
-                        best = total;
+                        const int x = pos & mask, y = pos >> log2;
+                        const long long lastCost = scanIdx == 2 ? lastPosCost(e, y, x) : lastPosCost(e, x, y);
+                        const long long total = rdCostTu + lastCost - c4[j].y;
+                        if (total < best)
+                        {
+                            lastIdx = sp + 1;
+                            best = total;
+                        }
+                        if (level > 1)
+                        {
+                            found = true;
+                            continue;
+                        }
+                        rdCostTu -= c4[j].x;
+                        rdCostTu += e.dist0(sp);
                     }
-                    if (level > 1)
-                    {
-                        found = true;
-                        break;
-                    }
-                    rdCostTu -= rec[sp].rdCost;
-                    rdCostTu += e.dist0(sp);
+                    else
+                        rdCostTu -= c4[j].y;
                 }
-                else
-                    rdCostTu -= rec[sp].rateSig;
             }
         }
     }
 
-    // signs back, uncoded tail to zero (Rdoq.cpp:414-431).  Only coded groups can hold non-zero levels.
-    int cbf = 0, absSum = 0;
-    for (int cg = 0; cg <= lastCg; ++cg)
+    // signs back, uncoded tail to zero (Rdoq.cpp:414-431), and sign-data hiding (:889-1023) of each group while its final
+    // levels are in registers.  Only coded groups can hold non-zero levels; from the top, as sign hiding walks them.
+    int cbf = 0, lastCGstate = -1;
+    for (int cg = lastCg; cg >= 0; --cg)
     {
         int cgX, cgY;
         scanXY(log2Cg, scanIdx, cg, cgX, cgY);
         if (!((csbf >> (cgY * (1 << log2Cg) + cgX)) & 1)) continue;
         const short *sc = e.scan + (cg << 4);
-        for (int k = 0; k < 16; ++k)
+        int lv[16];
+        unsigned nzMask = 0, negMask = 0;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
         {
-            const int sp = cg * 16 + k, pos = sc[k];
-            const int level = dst[pos];
-            if (!level) continue;
-            if (sp < lastIdx)
+            int p4[4], l4[4], s4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p4[j] = sc[4 * q4 + j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) l4[j] = dst[p4[j]];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s4[j] = src[p4[j]];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
             {
-                absSum += level;
-                cbf |= level;
-                if (src[pos] < 0) dst[pos] = (int16_t)-level;
+                const int k = 4 * q4 + j, sp = cg * 16 + k;
+                int level = l4[j];
+                if (level)
+                {
+                    if (sp < lastIdx)
+                    {
+                        cbf |= level;
+                        if (s4[j] < 0)
+                        {
+                            level = -level;
+                            dst[p4[j]] = (int16_t)level;
+                        }
+                    }
+                    else
+                    {
+                        level = 0;
+                        dst[p4[j]] = 0;
+                    }
+                }
+                lv[k] = level;
+                nzMask |= (unsigned)(level != 0) << k;
+                negMask |= (unsigned)(s4[j] < 0) << k;
             }
-            else
-                dst[pos] = 0;
         }
+        if (!sdh || !nzMask) continue; // an empty group changes nothing (and cannot be the first coded one)
+        if (lastCGstate == -1) lastCGstate = 1;
+        signDataHidingGroup(e, cg, lv, nzMask, negMask, lastCGstate, dst);
+        if (lastCGstate == 1) lastCGstate = 0;
     }
-    if (sdh && absSum >= 2) signDataHiding(e, lastCg, dst);
     return cbf;
 }
