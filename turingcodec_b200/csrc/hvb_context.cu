@@ -113,6 +113,7 @@ extern "C" void hvb_destroy(hvb_context *ctx)
     if (ctx->coeffPool) cudaFree(ctx->coeffPool);
     if (ctx->rdoqCtx) cudaFree(ctx->rdoqCtx);
     if (ctx->rdoqBits) cudaFree(ctx->rdoqBits);
+    if (ctx->rdoqLast) cudaFree(ctx->rdoqLast);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     delete ctx;
@@ -441,6 +442,8 @@ extern "C" int hvb_rdoq_contexts_upload(hvb_context *ctx, const hvb_rdoq_ctx *sn
     if (rc) return rc;
     ctx->rdoqCtxCount = (int)have;
     rc = growDevice(ctx, &ctx->rdoqBits, &ctx->rdoqBitsCount, have * sizeof(hvb_rdoq_ctx), sizeof(int2), "rdoq bit costs");
+    if (rc) return rc;
+    rc = growDevice(ctx, &ctx->rdoqLast, &ctx->rdoqLastCount, have * 160, sizeof(int), "rdoq last-position rates");
     if (rc) return rc;
     cudaError_t e = cudaMemcpyAsync(ctx->rdoqCtx + first, snapshots, sizeof(hvb_rdoq_ctx) * count, cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) return hvbCuda(ctx, e, "hvb_rdoq_contexts_upload");

@@ -77,6 +77,8 @@ struct hvb_context
     int rdoqCtxCount = 0;
     int2 *rdoqBits = nullptr; // [rdoqCtxCount * sizeof(hvb_rdoq_ctx)] bit costs of both bins per context state byte
     size_t rdoqBitsCount = 0;
+    int *rdoqLast = nullptr; // [rdoqCtxCount * 160] last-position prefix rates per snapshot (hvb_rdoq.cuh lastPrefixRate)
+    size_t rdoqLastCount = 0;
     void *scratch = nullptr; // kernel workspace (RDOQ per-TU state, ...)
     size_t scratchBytes = 0;
 };

@@ -120,6 +120,7 @@ struct Engine
 {
     const hvb_rdoq_ctx *cx;
     const int2 *bits; // per state byte of *cx: {bits of bin 0, bits of bin 1} (hvbLaunchRdoqBits), one load instead of two dependent ones
+    const int *lastTab; // this block's (cIdx != 0, log2) slice of the last-position rate table: [0..9] x prefix, [10..19] y prefix
     HvbCoefRec *rec;
     const short *scan;
     const int16_t *src;
@@ -313,18 +314,24 @@ __device__ __forceinline__ int lastLen(int v) // binarisationLengthForPosition (
     return v < 4 ? v : (v < 6 ? 4 : (v < 8 ? 5 : (v < 12 ? 6 : (v < 16 ? 7 : (v < 24 ? 8 : 9)))));
 }
 
-// Rdoq.cpp:699-740
-__device__ inline long long lastPosCost(const Engine &e, int xC, int yC)
+// Rdoq.cpp:699-740: the rate of a last-significant-coefficient prefix of binarisation length `len` (0..9) in one direction,
+// for one context snapshot.  It depends on the snapshot, the colour plane class and the block size only, so it is tabulated
+// when the snapshots are uploaded (hvbLaunchRdoqBits) instead of being summed bin by bin -- up to 20 dependent lookups --
+// for every candidate last position.
+constexpr int kLastTabPerCtx = 2 * 4 * 20; // [cIdx != 0][log2 - 2][x: 0..9, y: 10..19]
+__device__ inline int lastPrefixRate(const hvb_rdoq_ctx &cx, bool isY, int len, int cIdx, int log2)
 {
-    const int lx = lastLen(xC), ly = lastLen(yC);
+    const uint8_t *prefix = isY ? cx.last_y_prefix : cx.last_x_prefix;
     int rate = 0;
-    for (int i = 0; i < lx; ++i) rate += bitsOf(e, 1, e.cx->last_x_prefix[lastPrefixCtx(i, e.cIdx, e.log2)]);
-    if (lx < 9) rate += bitsOf(e, 0, e.cx->last_x_prefix[lastPrefixCtx(lx, e.cIdx, e.log2)]);
-    for (int i = 0; i < ly; ++i) rate += bitsOf(e, 1, e.cx->last_y_prefix[lastPrefixCtx(i, e.cIdx, e.log2)]);
-    if (ly < 9) rate += bitsOf(e, 0, e.cx->last_y_prefix[lastPrefixCtx(ly, e.cIdx, e.log2)]);
-    if (lx > 3) rate += 32768 * ((lx - 2) >> 1);
-    if (ly > 3) rate += 32768 * ((ly - 2) >> 1);
-    return e.lam(rate);
+    for (int i = 0; i < len; ++i) rate += kEntropyBits[(prefix[lastPrefixCtx(i, cIdx, log2)] >> 1) ^ 1];
+    if (len < 9) rate += kEntropyBits[prefix[lastPrefixCtx(len, cIdx, log2)] >> 1];
+    if (len > 3) rate += 32768 * ((len - 2) >> 1);
+    return rate;
+}
+
+__device__ __forceinline__ long long lastPosCost(const Engine &e, int xC, int yC)
+{
+    return e.lam(__ldg(e.lastTab + lastLen(xC)) + __ldg(e.lastTab + 10 + lastLen(yC)));
 }
 
 // neighbours right / below of coefficient group (xS, yS) in the 64-bit csbf mask (Rdoq.cpp:601-617, :675-697)
@@ -451,7 +458,7 @@ __device__ inline HvbRdoqMid hvbRdoqPrepass(int16_t *dst, const int16_t *src, co
 // `rec` has room for n records.  Returns the OR of the coded levels.
 __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_rdoq_ctx *ctx, const HvbRdoqMid &mid, int qScale, int qShift,
                                     int iqScale, int log2, int cIdx, int scanIdx, bool isIntra, bool sdh, int bitDepth, HvbCoefRec *rec,
-                                    const int2 *bits)
+                                    const int2 *bits, const int *lastTab)
 {
     using namespace hvb_rdoq;
     const int lastSp = mid.lastSp;
@@ -461,6 +468,7 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
     e.rec = rec;
     e.src = src;
     e.bits = bits;
+    e.lastTab = lastTab + ((cIdx ? 4 : 0) + (log2 - 2)) * 20;
     const int log2Cg = log2 - 2, mask = (1 << log2) - 1;
 
     long long rdCostTu = mid.tailDist0;

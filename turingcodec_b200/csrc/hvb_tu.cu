@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(128)
     tuRdoqKernel(int16_t *__restrict__ pool, const int16_t *__restrict__ coefTmp, HvbCoefRec *__restrict__ recs,
                  const hvb_rdoq_ctx *__restrict__ rdoqCtx, const hvb_tu_task *__restrict__ tasks, int n, hvb_tu_result *__restrict__ out,
                  const HvbRdoqMid *__restrict__ mids, const int *__restrict__ bucketCounts, const int *__restrict__ order, int bitDepth,
-                 const int2 *__restrict__ rdoqBits)
+                 const int2 *__restrict__ rdoqBits, const int *__restrict__ rdoqLast)
 {
     // blocks that are plain-quantised, or whose levels all round to zero (cbf already 0), are not in the ordering
     int total = 0;
@@ -498,7 +498,8 @@ __global__ void __launch_bounds__(128)
         const hvb_tu_task task = tasks[t];
         const int c = hvbRdoqThread(pool + task.levels, coefTmp + task.levels, rdoqCtx + task.rdoq_ctx, mid, task.qscale, task.qshift,
                                     task.iqscale, task.log2n, task.cIdx, task.scanIdx, (task.flags & 2) != 0, (task.flags & 4) != 0, bitDepth,
-                                    recs + task.levels, rdoqBits + (size_t)task.rdoq_ctx * sizeof(hvb_rdoq_ctx));
+                                    recs + task.levels, rdoqBits + (size_t)task.rdoq_ctx * sizeof(hvb_rdoq_ctx),
+                                    rdoqLast + (size_t)task.rdoq_ctx * hvb_rdoq::kLastTabPerCtx);
         out[t].cbf = c != 0;
     }
 }
@@ -578,7 +579,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 __global__ void __launch_bounds__(128)
     rdoqThreadKernel(int16_t *__restrict__ pool, HvbCoefRec *__restrict__ recs, const hvb_rdoq_ctx *__restrict__ rdoqCtx,
                      const hvb_rdoq_task *__restrict__ tasks, int n, const HvbRdoqMid *__restrict__ mids, int32_t *__restrict__ cbf,
-                     int bitDepth, const int2 *__restrict__ rdoqBits)
+                     int bitDepth, const int2 *__restrict__ rdoqBits, const int *__restrict__ rdoqLast)
 {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
     {
@@ -587,7 +588,8 @@ __global__ void __launch_bounds__(128)
         const hvb_rdoq_task task = tasks[t];
         const int c = hvbRdoqThread(pool + task.dst, pool + task.src, rdoqCtx + task.rdoq_ctx, mid, task.qscale, task.qshift, task.iqscale,
                                     task.log2n, task.cIdx, task.scanIdx, (task.flags & 2) != 0, (task.flags & 4) != 0, bitDepth,
-                                    recs + task.dst, rdoqBits + (size_t)task.rdoq_ctx * sizeof(hvb_rdoq_ctx));
+                                    recs + task.dst, rdoqBits + (size_t)task.rdoq_ctx * sizeof(hvb_rdoq_ctx),
+                                    rdoqLast + (size_t)task.rdoq_ctx * hvb_rdoq::kLastTabPerCtx);
         cbf[t] = c != 0;
     }
 }
@@ -601,12 +603,25 @@ __global__ void rdoqBitsKernel(const hvb_rdoq_ctx *__restrict__ snapshots, int2 
     bits[i] = make_int2(hvb_rdoq::kEntropyBits[state >> 1], hvb_rdoq::kEntropyBits[(state >> 1) ^ 1]);
 }
 
+// the last-position prefix rates of every uploaded snapshot (hvb_rdoq::lastPrefixRate): [ctx][cIdx != 0][log2 - 2][x 0..9, y 10..19]
+__global__ void rdoqLastKernel(const hvb_rdoq_ctx *__restrict__ snapshots, int *__restrict__ table, int count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count * hvb_rdoq::kLastTabPerCtx) return;
+    const int c = i / hvb_rdoq::kLastTabPerCtx, r = i - c * hvb_rdoq::kLastTabPerCtx;
+    const int chroma = r / 80, log2 = 2 + (r % 80) / 20, e = r % 20;
+    table[i] = hvb_rdoq::lastPrefixRate(snapshots[c], e >= 10, e % 10, chroma, log2);
+}
+
 } // namespace
 int hvbLaunchRdoqBits(hvb_context *ctx, int first, int count)
 {
     const int bytes = count * (int)sizeof(hvb_rdoq_ctx);
     rdoqBitsKernel<<<(bytes + 255) / 256, 256, 0, ctx->stream>>>(ctx->rdoqCtx + first, ctx->rdoqBits + (size_t)first * sizeof(hvb_rdoq_ctx), bytes);
     HVB_LAUNCH_CHECK(ctx, "rdoqBitsKernel");
+    const int entries = count * hvb_rdoq::kLastTabPerCtx;
+    rdoqLastKernel<<<(entries + 255) / 256, 256, 0, ctx->stream>>>(ctx->rdoqCtx + first, ctx->rdoqLast + (size_t)first * hvb_rdoq::kLastTabPerCtx, count);
+    HVB_LAUNCH_CHECK(ctx, "rdoqLastKernel");
     return HVB_OK;
 }
 namespace {
@@ -760,7 +775,7 @@ extern "C" int hvb_tu_chain_batch(hvb_context *ctx, const hvb_tu_task *tasks, in
     tuOrderKernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(cs.mids, n, cs.buckets, cs.buckets + kRdoqBuckets, cs.order);
     HVB_LAUNCH_CHECK(ctx, "tuOrderKernel");
     tuRdoqKernel<<<gridT, 128, 0, ctx->stream>>>(ctx->coeffPool, cs.coefTmp, cs.recs, ctx->rdoqCtx, dT, n, dO, cs.mids, cs.buckets, cs.order,
-                                                 ctx->bitDepth, ctx->rdoqBits);
+                                                 ctx->bitDepth, ctx->rdoqBits, ctx->rdoqLast);
     HVB_LAUNCH_CHECK(ctx, "tuRdoqKernel");
     if (ctx->bps == 1)
         tuBackKernel<uint8_t><<<gridW, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, dT, n, dO, ctx->bitDepth);
@@ -789,7 +804,7 @@ extern "C" int hvb_rdoq_batch(hvb_context *ctx, const hvb_rdoq_task *tasks, int 
     if (gridT > ctx->smCount * 16) gridT = ctx->smCount * 16;
     rdoqPrepassKernel<<<gridWarps(ctx, n, kWarps, 8), kWarps * 32, 0, ctx->stream>>>(ctx->coeffPool, ctx->rdoqCtx, dT, n, cs.mids, dC, ctx->bitDepth);
     HVB_LAUNCH_CHECK(ctx, "rdoqPrepassKernel");
-    rdoqThreadKernel<<<gridT, 128, 0, ctx->stream>>>(ctx->coeffPool, cs.recs, ctx->rdoqCtx, dT, n, cs.mids, dC, ctx->bitDepth, ctx->rdoqBits);
+    rdoqThreadKernel<<<gridT, 128, 0, ctx->stream>>>(ctx->coeffPool, cs.recs, ctx->rdoqCtx, dT, n, cs.mids, dC, ctx->bitDepth, ctx->rdoqBits, ctx->rdoqLast);
     HVB_LAUNCH_CHECK(ctx, "rdoqThreadKernel");
     return hvbStageOut(ctx, cbf, sizeof(int32_t) * n, mem, st);
 }
