@@ -152,7 +152,6 @@ struct Engine
         const int sq = (int)((unsigned)err * (unsigned)err);
         return (long long)sq * distScale;
     }
-    __device__ __forceinline__ long long dist0(int sp) const { return dist(abs((int)src[scan[sp]])); }
 };
 
 // the bit cost of coding `bin` with the context whose state byte is `state` (a member of *e.cx)
@@ -669,6 +668,9 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
                 for (int j = 0; j < 4; ++j) l4[j] = dst[p4[j]];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) c4[j] = *reinterpret_cast<const longlong2 *>(&rec[cg * 16 + 4 * q4 + j].rdCost);
+                int a4[4]; // |coefficient|: the "distortion if zero" of a level-1 coefficient that stage 2 walks past
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a4[j] = abs((int)src[p4[j]]);
 #pragma unroll
                 for (int j = 3; j >= 0; --j)
                 {
@@ -691,7 +693,7 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
                             continue;
                         }
                         rdCostTu -= c4[j].x;
-                        rdCostTu += e.dist0(sp);
+                        rdCostTu += e.dist(a4[j]);
                     }
                     else
                         rdCostTu -= c4[j].y;
