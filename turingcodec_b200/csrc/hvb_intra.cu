@@ -242,20 +242,38 @@ __device__ __forceinline__ void sweepRow(const SweepSmem<Sample> &s, int mode, i
         const bool vertical = mode >= 18;
         const int angle = kAngle[mode], inv = kInvAngle[mode];
         const int t = (yy + 1) * angle, idx = t >> 5, fact = t & 31;
-        int prev;
+        const int i0 = x0 + idx + 1;
+        if (i0 >= 0)
         {
-            const int i = x0 + idx + 1, sft = i >= 0 ? i : -((i * inv + 128) >> 8);
-            prev = vertical ? A[c + sft] : A[c - sft];
-        }
+            // the whole row reads the main side: consecutive reference samples, no projection
+            const int16_t *R = A + c + (vertical ? i0 : -i0);
+            const int dir = vertical ? 1 : -1;
+            int prev = R[0];
 #pragma unroll
-        for (int x = 0; x < T; ++x)
+            for (int x = 0; x < T; ++x)
+            {
+                // when fact == 0 the reference does not read the second sample; reading it is harmless (the arrays are
+                // padded) and (32 r0 + 16) >> 5 == r0
+                const int next = R[dir * (x + 1)];
+                out[x] = ((32 - fact) * prev + fact * next + 16) >> 5;
+                prev = next;
+            }
+        }
+        else
         {
-            // when fact == 0 the reference does not read the second sample; reading it is harmless (the arrays are
-            // padded) and (32 r0 + 16) >> 5 == r0
-            const int i = x0 + x + idx + 2, sft = i >= 0 ? i : -((i * inv + 128) >> 8);
-            const int next = vertical ? A[c + sft] : A[c - sft];
-            out[x] = ((32 - fact) * prev + fact * next + 16) >> 5;
-            prev = next;
+            int prev;
+            {
+                const int sft = -((i0 * inv + 128) >> 8);
+                prev = vertical ? A[c + sft] : A[c - sft];
+            }
+#pragma unroll
+            for (int x = 0; x < T; ++x)
+            {
+                const int i = i0 + x + 1, sft = i >= 0 ? i : -((i * inv + 128) >> 8);
+                const int next = vertical ? A[c + sft] : A[c - sft];
+                out[x] = ((32 - fact) * prev + fact * next + 16) >> 5;
+                prev = next;
+            }
         }
         if (edge && (mode == 26 || mode == 10) && x0 == 0)
         {

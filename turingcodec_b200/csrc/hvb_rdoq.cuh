@@ -204,6 +204,44 @@ __device__ inline int sigCtxInc(int prevCsbf, int scanIdx, int xC, int yC, int l
     return cIdx == 0 ? inc : 27 + inc;
 }
 
+// sigCtxInc for the 16 scan positions of one coefficient group without decoding positions.  Inside a group the increment
+// is base(group) + f(neighbour pattern, xP, yP) with f in {0, 1, 2}; (xP, yP) of scan position k is fixed by the scan, so f
+// is two bits per k of a word chosen by (scanIdx, neighbour pattern).  4x4 blocks: ctxIdxMap, four bits per k.  (Generated
+// from sigCtxInc above and checked against it for every block size, plane class, scan, group and pattern.)
+static __device__ const uint32_t kSigF[3][4] = {{0x556u, 0x1090926u, 0x10619au, 0xaaaaaaaau},
+                                                {0x10516u, 0x55aau, 0x6060606u, 0xaaaaaaaau},
+                                                {0x10516u, 0x6060606u, 0x55aau, 0xaaaaaaaau}};
+static __device__ const unsigned long long kSigMap4[3] = {0x8885875467436120ull, 0x8877886654325410ull, 0x8855884476317620ull};
+
+struct GroupSigCtx
+{
+    unsigned long long bits; // 2 (or 4) bits per scan position
+    int base, dc, shift;     // dc: context of the block's DC coefficient (group 0, position 0), -1 elsewhere
+    __device__ __forceinline__ GroupSigCtx(int prev, int scanIdx, int cg, int cgX, int cgY, int log2, int cIdx)
+    {
+        const int plane = cIdx == 0 ? 0 : 27;
+        if (log2 == 2)
+        {
+            bits = __ldg(&kSigMap4[scanIdx]);
+            base = plane;
+            dc = -1;
+            shift = 2; // 4 bits per position
+        }
+        else
+        {
+            bits = __ldg(&kSigF[scanIdx][prev]);
+            base = cIdx == 0 ? (cgX + cgY > 0 ? 3 : 0) + (log2 == 3 ? (scanIdx == 0 ? 9 : 15) : 21) : 27 + (log2 == 3 ? 9 : 12);
+            dc = cg == 0 ? plane : -1;
+            shift = 1;
+        }
+    }
+    __device__ __forceinline__ int at(int k) const
+    {
+        if (k == 0 && dc >= 0) return dc;
+        return base + (int)((bits >> (k << shift)) & (shift == 2 ? 15 : 3));
+    }
+};
+
 // Rdoq.cpp:619-673
 __device__ inline long long levelRateCost(const Engine &e, int level, const CoefBits &cb, int rice, int g1Cnt, int g2Cnt)
 {
@@ -488,6 +526,7 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
         const int prev = right + (below << 1);
         const int cSig = (cIdx == 0 ? 0 : 2) + min(right + below, 1); // coded_sub_block_flag context (neighbours only)
         const short *sc = e.scan + (cg << 4);
+        const GroupSigCtx sig(prev, scanIdx, cg, cgX, cgY, log2, cIdx);
 
         // A group whose levels all round to zero (never lastSp's group): adjustLevel takes its q == 0 exit for
         // every coefficient (Rdoq.cpp:466-476), the state does not move, and since an uncoded group is skipped
@@ -505,7 +544,7 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
             for (int j = 0; j < 4; ++j) a4[j] = abs((int)src[pos4[j]]);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                bits4[j] = bitsOf(e, 0, ctx->sig_coeff_flag[sigCtxInc(prev, scanIdx, pos4[j] & mask, pos4[j] >> log2, log2, cIdx)]);
+                bits4[j] = bitsOf(e, 0, ctx->sig_coeff_flag[sig.at(k0 + j)]);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
             {
@@ -550,7 +589,7 @@ __device__ inline int hvbRdoqThread(int16_t *dst, const int16_t *src, const hvb_
             }
             const int scaled = a * qScale;
             const int q = (scaled + (1 << (qShift - 1))) >> qShift;
-            const int sigCtx = sigCtxInc(prev, scanIdx, pos & mask, pos >> log2, log2, cIdx);
+            const int sigCtx = sig.at(k);
             const long long d0 = e.dist(a);
             const int g1Ctx = 4 * ctxSet + g1Idx + g1Off, g2Ctx = ctxSet + g2Off;
             const CoefBits cb{bitsBoth(e, ctx->sig_coeff_flag[sigCtx]), bitsBoth(e, ctx->greater1_flag[g1Ctx]), bitsBoth(e, ctx->greater2_flag[g2Ctx])};
