@@ -15,6 +15,7 @@
 // (VABSDIFF4 / dp4a), then a 5-step shuffle tree.
 #include "hvb_internal.cuh"
 #include "hvb_satd.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -237,37 +238,102 @@ __device__ __forceinline__ uint2 loadRow8(const uint8_t *p)
     return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
 }
 
-struct TileRows
+// ---- the streaming form: tile rows staged through shared memory by asynchronous copies ---------------------------
+// A warp treats the tile groups of all its tasks as ONE stream and keeps STAGES - 1 groups (1 KB each: rows t and
+// t + 4 of tile g from both pictures, 8 bytes per copy, a lane's four copies land in slots only that lane reads, so no
+// warp synchronisation is needed -- cp.async.wait_group orders a lane's own copies) in flight ahead of the group whose
+// products run.  Bytes in flight no longer cost registers, and the pipeline does not drain at block boundaries (a
+// 32x32 block is two groups).  Rows that are not 8-byte aligned take the register path (loadGroup) into the same slots.
+struct SatdCursor
 {
-    uint2 r[4]; // a rows t, t+4; b rows t, t+4
+    int t, base, tiles, tilesX, sa, sb;
+    const uint8_t *a, *b;
 };
 
-__device__ __forceinline__ TileRows loadGroup(const uint8_t *a, int sa, const uint8_t *b, int sb, int tilesX, int tiles, int base, int g, int t)
+// position the cursor on the first task at or after c.t (stepping by `step`) that this kernel owns
+__device__ __forceinline__ void satdCursorOpen(SatdCursor &c, const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks,
+                                               int n, int step)
 {
-    const int tile = min(base + g, tiles - 1);
-    const int ty = tile / tilesX, tx = tile - ty * tilesX;
-    const uint8_t *S = a + (intptr_t)(ty * 8 + t) * sa + tx * 8, *P = b + (intptr_t)(ty * 8 + t) * sb + tx * 8;
-    TileRows f;
-    f.r[0] = loadRow8(S);
-    f.r[1] = loadRow8(S + 4 * sa);
-    f.r[2] = loadRow8(P);
-    f.r[3] = loadRow8(P + 4 * sb);
-    return f;
+    while (c.t < n)
+    {
+        const hvb_metric_task task = tasks[c.t];
+        if (!((task.w | task.h) & 7))
+        {
+            c.a = hvbBlockPtr<uint8_t>(planes, task.a, c.sa);
+            c.b = hvbBlockPtr<uint8_t>(planes, task.b, c.sb);
+            c.tilesX = task.w >> 3;
+            c.tiles = c.tilesX * (task.h >> 3);
+            c.base = 0;
+            return;
+        }
+        c.t += step;
+    }
 }
 
-// SATD of a w x h block pair (w, h multiples of 8) in 8x8 tiles; the result is valid on every lane
-__device__ __forceinline__ int satdMmaWarp(const uint8_t *a, int sa, const uint8_t *b, int sb, int w, int h, const HadamardFrag &A, int lane)
+__device__ __forceinline__ void cpAsync8(uint32_t dst, const void *src)
 {
-    const int tilesX = w >> 3, tiles = tilesX * (h >> 3);
-    const int g = lane >> 2, t = lane & 3;
-    int total = 0;
-    TileRows f = loadGroup(a, sa, b, sb, tilesX, tiles, 0, g, t);
-    for (int base = 0; base < tiles; base += 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// 8-bit blocks whose sides are multiples of 8 (the other blocks of the batch belong to satdKernel)
+template <int STAGES>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+    satdMmaKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint2 satdStage[]; // [warp][stage][part 0..3][lane]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int step = gridDim.x * kWarpsPerBlock;
+    const HadamardFrag A(lane);
+    uint2 *mine = satdStage + warp * STAGES * 128 + lane;
+    const uint32_t mineAddr = (uint32_t)__cvta_generic_to_shared(mine);
+
+    SatdCursor issue, use;
+    issue.t = use.t = blockIdx.x * kWarpsPerBlock + warp;
+    satdCursorOpen(issue, planes, tasks, n, step);
+    satdCursorOpen(use, planes, tasks, n, step);
+
+    auto issueGroup = [&](int slot) {
+        if (issue.t < n)
+        {
+            const int tile = min(issue.base + g, issue.tiles - 1);
+            const int ty = tile / issue.tilesX, tx = tile - ty * issue.tilesX;
+            const uint8_t *S = issue.a + (intptr_t)(ty * 8 + t) * issue.sa + tx * 8, *P = issue.b + (intptr_t)(ty * 8 + t) * issue.sb + tx * 8;
+            if (!((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(P) | (uintptr_t)issue.sa | (uintptr_t)issue.sb) & 7))
+            {
+                const uint32_t dst = mineAddr + slot * 1024;
+                cpAsync8(dst, S);
+                cpAsync8(dst + 256, S + 4 * issue.sa);
+                cpAsync8(dst + 512, P);
+                cpAsync8(dst + 768, P + 4 * issue.sb);
+            }
+            else
+            {
+                uint2 *dst = mine + slot * 128;
+                dst[0] = loadRow8(S);
+                dst[32] = loadRow8(S + 4 * issue.sa);
+                dst[64] = loadRow8(P);
+                dst[96] = loadRow8(P + 4 * issue.sb);
+            }
+            issue.base += 8;
+            if (issue.base >= issue.tiles)
+            {
+                issue.t += step;
+                satdCursorOpen(issue, planes, tasks, n, step);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issueGroup(s);
+    int slot = 0, total = 0;
+    while (use.t < n)
     {
-        // the next group's rows are in flight while this group's products run.  (Requesting four groups ahead was
-        // measured slower, 39 % vs 52 % of HBM peak on 64x64 blocks: the registers cost more occupancy than the depth buys.)
-        TileRows next = f;
-        if (base + 8 < tiles) next = loadGroup(a, sa, b, sb, tilesX, tiles, base + 8, g, t);
+        issueGroup(slot == 0 ? STAGES - 1 : slot - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+        const uint2 *src = mine + slot * 128;
+        const uint2 r0 = src[0], r1 = src[32], r2 = src[64], r3 = src[96];
+        const uint32_t bx[4] = {r0.x, r1.x, r2.x, r3.x}, by[4] = {r0.y, r1.y, r2.y, r3.y};
         int s0 = 0, s1 = 0;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
@@ -277,7 +343,7 @@ __device__ __forceinline__ int satdMmaWarp(const uint8_t *a, int sa, const uint8
             for (int ks = 0; ks < 4; ++ks)
             {
                 const uint32_t neg = ((((mt >> 1) & ks) ^ (ks >> 1)) & 1) ? 0xfefefefeu : 0u;
-                imma16832(acc, A.x[mt & 1][0] ^ neg, A.x[mt & 1][1] ^ neg, A.x[mt & 1][2] ^ neg, A.x[mt & 1][3] ^ neg, f.r[ks].x, f.r[ks].y);
+                imma16832(acc, A.x[mt & 1][0] ^ neg, A.x[mt & 1][1] ^ neg, A.x[mt & 1][2] ^ neg, A.x[mt & 1][3] ^ neg, bx[ks], by[ks]);
             }
             s0 = __sad(acc[0], 0, __sad(acc[2], 0, (unsigned)s0));
             s1 = __sad(acc[1], 0, __sad(acc[3], 0, (unsigned)s1));
@@ -287,29 +353,19 @@ __device__ __forceinline__ int satdMmaWarp(const uint8_t *a, int sa, const uint8
         sum += __shfl_xor_sync(0xffffffffu, (g & 1) ? s0 : s1, 4);
         sum += __shfl_xor_sync(0xffffffffu, sum, 8);
         sum += __shfl_xor_sync(0xffffffffu, sum, 16);
-        if (g < 2 && base + 2 * t + g < tiles) total += (sum + 2) >> 2; // havoc/hadamard.cpp:319-323
-        f = next;
+        if (g < 2 && use.base + 2 * t + g < use.tiles) total += (sum + 2) >> 2; // havoc/hadamard.cpp:319-323
+        use.base += 8;
+        if (use.base >= use.tiles)
+        {
+            total = hvbWarpSum(total);
+            if (lane == 0) out[use.t] = total;
+            total = 0;
+            use.t += step;
+            satdCursorOpen(use, planes, tasks, n, step);
+        }
+        slot = slot == STAGES - 1 ? 0 : slot + 1;
     }
-    return hvbWarpSum(total);
-}
-
-// 8-bit blocks whose sides are multiples of 8 (the other blocks of the batch belong to satdKernel)
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
-    satdMmaKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out)
-{
-    const int lane = threadIdx.x & 31;
-    const int warpsTotal = gridDim.x * kWarpsPerBlock;
-    const HadamardFrag A(lane);
-    for (int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n; t += warpsTotal)
-    {
-        const hvb_metric_task task = tasks[t];
-        if ((task.w | task.h) & 7) continue;
-        int sa, sb;
-        const uint8_t *a = hvbBlockPtr<uint8_t>(planes, task.a, sa);
-        const uint8_t *b = hvbBlockPtr<uint8_t>(planes, task.b, sb);
-        const int acc = satdMmaWarp(a, sa, b, sb, task.w, task.h, A, lane);
-        if (lane == 0) out[t] = acc;
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // one register-resident Hadamard tile per lane: 16-bit samples, and the 4x4 / 2x2 tiled blocks of 8-bit batches
@@ -403,11 +459,27 @@ extern "C" int hvb_satd_batch(hvb_context *ctx, const hvb_metric_task *tasks, in
     if (rc) return rc;
     if (ctx->bps == 1)
     {
-        int perSm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, satdMmaKernel, kWarpsPerBlock * 32, 0);
-        const int blocks = min((n + kWarpsPerBlock - 1) / kWarpsPerBlock, ctx->smCount * max(perSm, 1));
-        satdMmaKernel<<<blocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->dPlanes, static_cast<const hvb_metric_task *>(st.dTasks), n,
-                                                                      static_cast<int32_t *>(st.dOut));
+        const auto *dT = static_cast<const hvb_metric_task *>(st.dTasks);
+        auto *dO = static_cast<int32_t *>(st.dOut);
+        const int stagesEnv = getenv("HVB_SATD_STAGES") ? atoi(getenv("HVB_SATD_STAGES")) : 4;
+#define HVB_SATD_LAUNCH(STAGES)                                                                                                  \
+    {                                                                                                                            \
+        const int smem = kWarpsPerBlock * STAGES * 1024;                                                                         \
+        cudaFuncSetAttribute(satdMmaKernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                          \
+        int perSm = 1;                                                                                                           \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, satdMmaKernel<STAGES>, kWarpsPerBlock * 32, smem);                 \
+        const int blocks = min((n + kWarpsPerBlock - 1) / kWarpsPerBlock, ctx->smCount * max(perSm, 1));                         \
+        satdMmaKernel<STAGES><<<blocks, kWarpsPerBlock * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO);                      \
+    }
+        switch (stagesEnv)
+        {
+        case 2: HVB_SATD_LAUNCH(2) break;
+        case 3: HVB_SATD_LAUNCH(3) break;
+        case 6: HVB_SATD_LAUNCH(6) break;
+        case 8: HVB_SATD_LAUNCH(8) break;
+        default: HVB_SATD_LAUNCH(4) break;
+        }
+#undef HVB_SATD_LAUNCH
         HVB_LAUNCH_CHECK(ctx, "satdMmaKernel");
     }
     HVB_DISPATCH_SAMPLE(ctx, satdKernel, gridFor<hvb_metric_task>(ctx, n), ctx->dPlanes,

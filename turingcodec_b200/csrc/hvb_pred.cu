@@ -322,7 +322,7 @@ extern "C" int hvb_subtract_bi_batch(hvb_context *ctx, const hvb_subtract_bi_tas
     return hvbStageOut(ctx, nullptr, 0, mem, st);
 }
 
-extern "C" int hvb_pu_cost_batch(hvb_context *ctx, const hvb_pu_cost_task *tasks, int n, int32_t *out, hvb_mem mem)
+int hvbPuCostBatchV1(hvb_context *ctx, const hvb_pu_cost_task *tasks, int n, int32_t *out, hvb_mem mem)
 {
     HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && out)));
     if (!n) return HVB_OK;
