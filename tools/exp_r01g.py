@@ -1,4 +1,5 @@
-"""Throw-away A/B runner: SATD staging depth sweep and PU-cost kernel generations, one process."""
+"""Throw-away runner of the last GPU call of round 1: PU-cost timing, SATD staging depth sweep; --ncu: one launch of
+each kernel on a reduced working set for an ncu capture."""
 import json
 import os
 import sys
@@ -11,6 +12,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from turingcodec_b200 import hvb, synth, workload  # noqa: E402
 
+NCU = "--ncu" in sys.argv
 ctx = hvb.Context(0, 1, 8)
 stream = torch.cuda.Stream()
 ctx.set_stream(stream.cuda_stream)
@@ -29,7 +31,7 @@ def timed(fn, d_tasks, n, d_out, reps=5, warm=2):
     return e0.elapsed_time(e1) / reps
 
 
-# ---- PU cost: v2 vs v1 on the bench's PU list, results compared
+# ---- PU cost on the bench's PU list: one uni- and one bi-predicted evaluation per PU
 pics = [ctx.picture_create(W, H, 96) for _ in range(4)]
 for i, pic in enumerate(pics[:3]):
     ctx.upload_yuv(pic, *synth.frame(i, W, H, 8))
@@ -45,35 +47,33 @@ for k in range(2):
     t["mvx"][:, 0], t["mvy"][:, 0] = 12 + rng.integers(-4, 5, me.size), 8 + rng.integers(-4, 5, me.size)
     t["mvx"][:, 1], t["mvy"][:, 1] = 24 + rng.integers(-4, 5, me.size), 16 + rng.integers(-4, 5, me.size)
 d = torch.from_numpy(pu.view(np.uint8).reshape(-1).copy()).cuda()
-outs = {}
-for gen in ("v2", "v1"):
-    if gen == "v1":
-        os.environ["HVB_PUCOST_V1"] = "1"
-    o = torch.zeros(pu.size * 3, dtype=torch.int32, device="cuda")
+o = torch.zeros(pu.size * 3, dtype=torch.int32, device="cuda")
+if NCU:
+    ctx.pu_cost(d.data_ptr(), pu.size, o.data_ptr(), hvb.DEVICE)
+    torch.cuda.synchronize()
+else:
     ms = timed(ctx.pu_cost, d, pu.size, o, reps=3)
-    outs[gen] = o.cpu().numpy()
-    print(json.dumps({"kernel": "puCostKernel", "gen": gen, "tasks": int(pu.size), "ms": round(ms, 3)}), flush=True)
-os.environ.pop("HVB_PUCOST_V1", None)
-bad = np.nonzero((outs["v1"] != outs["v2"]).reshape(-1, 3).any(axis=1))[0]
-print(json.dumps({"pu_cost_v1_vs_v2_mismatches": int(bad.size), "of": int(pu.size)}))
-for i in bad[:12]:
-    print("  mismatch", int(i), pu[i], outs["v1"].reshape(-1, 3)[i], outs["v2"].reshape(-1, 3)[i])
+    print(json.dumps({"kernel": "puCostKernel", "tasks": int(pu.size), "ms": round(ms, 3), "checksum": int(o.sum().item())}), flush=True)
+    for sel, name in ((slice(0, None, 2), "uni"), (slice(1, None, 2), "bi")):
+        part = np.ascontiguousarray(pu[sel])
+        dp = torch.from_numpy(part.view(np.uint8).reshape(-1).copy()).cuda()
+        ms = timed(ctx.pu_cost, dp, part.size, o, reps=3)
+        print(json.dumps({"kernel": "puCostKernel", "list": name, "tasks": int(part.size), "ms": round(ms, 3)}), flush=True)
 for pic in pics:
     ctx.picture_destroy(pic)
 
 # ---- streaming SATD: staging depth sweep
-pairs = 120
+pairs = 30 if NCU else 120
 spics = [ctx.picture_create(W, H, 0) for _ in range(2 * pairs)]
 host = np.random.default_rng(0).integers(0, 256, (H, W), dtype=np.uint8)
 for pic in spics:
     ctx.picture_upload(pic, 0, np.roll(host, pic, 1))
 peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
-for n in (64, 32, 16, 8):
+for n in ((64,) if NCU else (64, 32)):
     xs, ys = np.meshgrid(np.arange(W // n) * n, np.arange(H // n) * n)
     per_pair = xs.size
-    npairs = pairs if n >= 32 else 30
-    tasks = np.zeros(per_pair * npairs, hvb.metric_task_t)
-    for k in range(npairs):
+    tasks = np.zeros(per_pair * pairs, hvb.metric_task_t)
+    for k in range(pairs):
         t = tasks[k * per_pair:(k + 1) * per_pair]
         t["a"]["pic"], t["b"]["pic"] = spics[2 * k], spics[2 * k + 1]
         t["a"]["x"] = t["b"]["x"] = xs.reshape(-1)
@@ -81,6 +81,10 @@ for n in (64, 32, 16, 8):
         t["w"] = t["h"] = n
     d_tasks = torch.from_numpy(tasks.view(np.uint8).reshape(-1).copy()).cuda()
     d_out = torch.zeros(tasks.size, dtype=torch.int32, device="cuda")
+    if NCU:
+        ctx.satd(d_tasks.data_ptr(), tasks.size, d_out.data_ptr(), hvb.DEVICE)
+        torch.cuda.synchronize()
+        break
     alg = 2.0 * n * n * tasks.size + 4 * tasks.size + tasks.nbytes
     ref = None
     for stages in (4, 2, 3, 6, 8):
@@ -91,5 +95,4 @@ for n in (64, 32, 16, 8):
             ref = got
         print(json.dumps({"kernel": "satd", "block": n, "stages": stages, "ms": round(ms, 4), "GBps": round(alg / ms / 1e6, 1),
                           "frac": round(alg / ms / 1e6 / peak, 4), "same": bool(np.array_equal(ref, got))}), flush=True)
-    ms = timed(ctx.sad, d_tasks, tasks.size, d_out)
-    print(json.dumps({"kernel": "sad", "block": n, "ms": round(ms, 4), "frac": round(alg / ms / 1e6 / peak, 4)}), flush=True)
+    os.environ.pop("HVB_SATD_STAGES", None)

@@ -243,16 +243,19 @@ __device__ __forceinline__ uint2 loadRow8(const uint8_t *p)
 // t + 4 of tile g from both pictures, 8 bytes per copy, a lane's four copies land in slots only that lane reads, so no
 // warp synchronisation is needed -- cp.async.wait_group orders a lane's own copies) in flight ahead of the group whose
 // products run.  Bytes in flight no longer cost registers, and the pipeline does not drain at block boundaries (a
-// 32x32 block is two groups).  Rows that are not 8-byte aligned take the register path (loadGroup) into the same slots.
+// 32x32 block is two groups).  Rows that are not 8-byte aligned take the register path (loadRow8) into the same slots.
+// Only the issuing side walks the task array; what the consuming side needs of a group in flight -- its task and its
+// place in the block -- travels in a register queue as deep as the pipeline.
 struct SatdCursor
 {
     int t, base, tiles, tilesX, sa, sb;
+    unsigned recip; // ceil(2^32 / tilesX): umulhi(tile, recip) = tile / tilesX for tile < 2^16, tilesX > 1
     const uint8_t *a, *b;
 };
 
 // position the cursor on the first task at or after c.t (stepping by `step`) that this kernel owns
 __device__ __forceinline__ void satdCursorOpen(SatdCursor &c, const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks,
-                                               int n, int step)
+                                               int n, int step, int *__restrict__ leftover)
 {
     while (c.t < n)
     {
@@ -262,10 +265,12 @@ __device__ __forceinline__ void satdCursorOpen(SatdCursor &c, const HvbPlane *__
             c.a = hvbBlockPtr<uint8_t>(planes, task.a, c.sa);
             c.b = hvbBlockPtr<uint8_t>(planes, task.b, c.sb);
             c.tilesX = task.w >> 3;
+            c.recip = c.tilesX > 1 ? 0xffffffffu / (unsigned)c.tilesX + 1u : 0u;
             c.tiles = c.tilesX * (task.h >> 3);
             c.base = 0;
             return;
         }
+        *leftover = 1; // a block for satdKernel (every lane stores the same value)
         c.t += step;
     }
 }
@@ -278,7 +283,8 @@ __device__ __forceinline__ void cpAsync8(uint32_t dst, const void *src)
 // 8-bit blocks whose sides are multiples of 8 (the other blocks of the batch belong to satdKernel)
 template <int STAGES>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
-    satdMmaKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out)
+    satdMmaKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out,
+                  int *__restrict__ leftover)
 {
     extern __shared__ __align__(16) uint2 satdStage[]; // [warp][stage][part 0..3][lane]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -287,16 +293,20 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
     uint2 *mine = satdStage + warp * STAGES * 128 + lane;
     const uint32_t mineAddr = (uint32_t)__cvta_generic_to_shared(mine);
 
-    SatdCursor issue, use;
-    issue.t = use.t = blockIdx.x * kWarpsPerBlock + warp;
-    satdCursorOpen(issue, planes, tasks, n, step);
-    satdCursorOpen(use, planes, tasks, n, step);
+    SatdCursor issue;
+    issue.t = blockIdx.x * kWarpsPerBlock + warp;
+    satdCursorOpen(issue, planes, tasks, n, step, leftover);
 
-    auto issueGroup = [&](int slot) {
+    // requests one group into `slot`; (qt, qb) = its task (>= n: none left) and the tiles its block has left, this group included
+    auto issueGroup = [&](int slot, int &qt, int &qb) {
+        qt = issue.t;
+        qb = 0;
         if (issue.t < n)
         {
+            qb = issue.tiles - issue.base;
             const int tile = min(issue.base + g, issue.tiles - 1);
-            const int ty = tile / issue.tilesX, tx = tile - ty * issue.tilesX;
+            const int ty = issue.tilesX == 1 ? tile : issue.tiles < 65536 ? (int)__umulhi((unsigned)tile, issue.recip) : tile / issue.tilesX;
+            const int tx = tile - ty * issue.tilesX;
             const uint8_t *S = issue.a + (intptr_t)(ty * 8 + t) * issue.sa + tx * 8, *P = issue.b + (intptr_t)(ty * 8 + t) * issue.sb + tx * 8;
             if (!((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(P) | (uintptr_t)issue.sa | (uintptr_t)issue.sb) & 7))
             {
@@ -318,18 +328,20 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
             if (issue.base >= issue.tiles)
             {
                 issue.t += step;
-                satdCursorOpen(issue, planes, tasks, n, step);
+                satdCursorOpen(issue, planes, tasks, n, step, leftover);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
+    int qt[STAGES - 1], qb[STAGES - 1]; // the groups in flight, oldest first
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) issueGroup(s);
+    for (int s = 0; s < STAGES - 1; ++s) issueGroup(s, qt[s], qb[s]);
     int slot = 0, total = 0;
-    while (use.t < n)
+    while (qt[0] < n)
     {
-        issueGroup(slot == 0 ? STAGES - 1 : slot - 1);
+        int nt, nb;
+        issueGroup(slot == 0 ? STAGES - 1 : slot - 1, nt, nb);
         asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
         const uint2 *src = mine + slot * 128;
         const uint2 r0 = src[0], r1 = src[32], r2 = src[64], r3 = src[96];
@@ -353,16 +365,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
         sum += __shfl_xor_sync(0xffffffffu, (g & 1) ? s0 : s1, 4);
         sum += __shfl_xor_sync(0xffffffffu, sum, 8);
         sum += __shfl_xor_sync(0xffffffffu, sum, 16);
-        if (g < 2 && use.base + 2 * t + g < use.tiles) total += (sum + 2) >> 2; // havoc/hadamard.cpp:319-323
-        use.base += 8;
-        if (use.base >= use.tiles)
+        if (g < 2 && 2 * t + g < qb[0]) total += (sum + 2) >> 2; // havoc/hadamard.cpp:319-323
+        if (qb[0] <= 8)
         {
             total = hvbWarpSum(total);
-            if (lane == 0) out[use.t] = total;
+            if (lane == 0) out[qt[0]] = total;
             total = 0;
-            use.t += step;
-            satdCursorOpen(use, planes, tasks, n, step);
         }
+#pragma unroll
+        for (int s = 0; s + 1 < STAGES - 1; ++s)
+        {
+            qt[s] = qt[s + 1];
+            qb[s] = qb[s + 1];
+        }
+        qt[STAGES - 2] = nt;
+        qb[STAGES - 2] = nb;
         slot = slot == STAGES - 1 ? 0 : slot + 1;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -371,8 +388,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 // one register-resident Hadamard tile per lane: 16-bit samples, and the 4x4 / 2x2 tiled blocks of 8-bit batches
 template <typename Sample>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-    satdKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out)
+    satdKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out,
+               const int *__restrict__ leftover)
 {
+    // 8-bit batches: satdMmaKernel ran first on this stream and noted whether it left any block to this kernel
+    if (leftover && *leftover == 0) return;
     const int lane = threadIdx.x & 31;
     const int warpsTotal = gridDim.x * kWarpsPerBlock;
     for (int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n; t += warpsTotal)
@@ -457,10 +477,13 @@ extern "C" int hvb_satd_batch(hvb_context *ctx, const hvb_metric_task *tasks, in
     HvbStaged st;
     int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(int32_t) * n, mem, &st);
     if (rc) return rc;
+    int *leftover = nullptr;
     if (ctx->bps == 1)
     {
         const auto *dT = static_cast<const hvb_metric_task *>(st.dTasks);
         auto *dO = static_cast<int32_t *>(st.dOut);
+        leftover = ctx->workCursors + 2;
+        cudaMemsetAsync(leftover, 0, sizeof(int), ctx->stream);
         const int stagesEnv = getenv("HVB_SATD_STAGES") ? atoi(getenv("HVB_SATD_STAGES")) : 4;
 #define HVB_SATD_LAUNCH(STAGES)                                                                                                  \
     {                                                                                                                            \
@@ -469,7 +492,7 @@ extern "C" int hvb_satd_batch(hvb_context *ctx, const hvb_metric_task *tasks, in
         int perSm = 1;                                                                                                           \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, satdMmaKernel<STAGES>, kWarpsPerBlock * 32, smem);                 \
         const int blocks = min((n + kWarpsPerBlock - 1) / kWarpsPerBlock, ctx->smCount * max(perSm, 1));                         \
-        satdMmaKernel<STAGES><<<blocks, kWarpsPerBlock * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO);                      \
+        satdMmaKernel<STAGES><<<blocks, kWarpsPerBlock * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, leftover);            \
     }
         switch (stagesEnv)
         {
@@ -483,7 +506,7 @@ extern "C" int hvb_satd_batch(hvb_context *ctx, const hvb_metric_task *tasks, in
         HVB_LAUNCH_CHECK(ctx, "satdMmaKernel");
     }
     HVB_DISPATCH_SAMPLE(ctx, satdKernel, gridFor<hvb_metric_task>(ctx, n), ctx->dPlanes,
-                        static_cast<const hvb_metric_task *>(st.dTasks), n, static_cast<int32_t *>(st.dOut));
+                        static_cast<const hvb_metric_task *>(st.dTasks), n, static_cast<int32_t *>(st.dOut), leftover);
     HVB_LAUNCH_CHECK(ctx, "satdKernel");
     return hvbStageOut(ctx, out, sizeof(int32_t) * n, mem, st);
 }

@@ -1,5 +1,5 @@
-// hvb_pred.cu -- batched HEVC inter prediction (uni / bi), SubtractBi and the fused
-// interpolation + SATD used by sub-pel motion refinement.
+// hvb_pred.cu -- batched HEVC inter prediction (uni / bi), SubtractBi and the stand-alone fused
+// interpolation + SATD (the sub-pel refinement of the search is hvb_me_subpel.cu, the PU cost hvb_pu_cost.cu).
 //
 // Reference semantics (bit-exact):
 //   HavocPredUni   havoc/pred_inter.cpp:76-202   copy / h / v / hv, 8-tap luma, 4-tap chroma
@@ -148,105 +148,6 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// ---- measurePuCost's distortion: predictInter + SATD of Y, Cb, Cr (turing/Search.hpp:1668-1682) ----------------
-// predictUni / predictBi (turing/Dsp.h:769-864): the luma block origin is xPb + (mv >> 2) clamped by
-// clipMvLumaComponent (:723-731); the chroma origin is that value >> 1 and the chroma phase is mv & 7.
-
-__device__ __forceinline__ int clipMvLumaComponent(int component, int nPbSize, int pictureSize)
-{
-    if (component + nPbSize + 4 < 0) return -nPbSize - 4;
-    if (component > pictureSize + 2) return pictureSize + 2;
-    return component;
-}
-
-// one colour component of one PU: prediction into the warp's shared tile (optionally stored), SATD against the source
-template <typename Sample, int TAPS>
-__device__ int puComponent(int16_t *smem, const HvbPlane *planes, const hvb_pu_cost_task &t, int cIdx, const int (&bx)[2],
-                           const int (&by)[2], int bitDepth, int lane)
-{
-    int16_t *mid = smem, *pred = smem + kMidElems;
-    const int sh = cIdx ? 1 : 0, w = t.w >> sh, h = t.h >> sh, total = w * h;
-    const int fracMask = TAPS == 8 ? 3 : 7;
-    const int shift1 = min(4, bitDepth - 8), shift3 = max(2, 14 - bitDepth);
-    const int maxv = (1 << bitDepth) - 1;
-    const bool bi = t.ref_pic[0] >= 0 && t.ref_pic[1] >= 0;
-    bool first = true;
-    for (int r = 0; r < 2; ++r)
-    {
-        if (t.ref_pic[r] < 0) continue;
-        const HvbPlane &rp = planes[t.ref_pic[r] * 3 + cIdx];
-        const Sample *ref = reinterpret_cast<const Sample *>(rp.base) + (intptr_t)(by[r] >> sh) * rp.stride + (bx[r] >> sh);
-        passH<Sample, TAPS>(mid, ref, rp.stride, w, h, t.mvx[r] & fracMask, shift1, lane);
-        __syncwarp();
-        int cy[TAPS];
-#pragma unroll
-        for (int k = 0; k < TAPS; ++k) cy[k] = coef<TAPS>(t.mvy[r] & fracMask, k);
-        for (int i = lane; i < total; i += 32)
-        {
-            const int y = i / w, x = i - y * w;
-            const int v = passV<TAPS>(mid, w, x, y, cy);
-            if (!bi)
-                pred[i] = (int16_t)hvbClip3(0, maxv, (v + (1 << (5 + shift3))) >> (6 + shift3));
-            else if (first)
-                pred[i] = (int16_t)(v >> 6);
-            else
-                pred[i] = (int16_t)hvbClip3(0, maxv, ((int)pred[i] + (v >> 6) + (1 << shift3)) >> (shift3 + 1));
-        }
-        __syncwarp();
-        first = false;
-    }
-    if (t.dst_pic >= 0)
-    {
-        const HvbPlane &dp = planes[t.dst_pic * 3 + cIdx];
-        Sample *dst = reinterpret_cast<Sample *>(dp.base) + (intptr_t)(t.y0 >> sh) * dp.stride + (t.x0 >> sh);
-        for (int i = lane; i < total; i += 32)
-        {
-            const int y = i / w, x = i - y * w;
-            dst[y * dp.stride + x] = (Sample)pred[i];
-        }
-    }
-    if (cIdx && ((w | h) & 3)) return 0; // Compute<Satd, Rectangle> (turing/Measure.h:156-160)
-    const HvbPlane &sp = planes[t.src_pic * 3 + cIdx];
-    const Sample *src = reinterpret_cast<const Sample *>(sp.base) + (intptr_t)(t.y0 >> sh) * sp.stride + (t.x0 >> sh);
-    const int acc = hvbMeasureSatdLanes<Sample, int16_t>(src, sp.stride, pred, w, w, h, lane, 32, sizeof(Sample) == 2 ? 2 : 0);
-    return hvbWarpSum(acc);
-}
-
-template <typename Sample>
-__global__ void __launch_bounds__(kWarps * 32)
-    puCostKernel(const HvbPlane *__restrict__ planes, const hvb_pu_cost_task *__restrict__ tasks, int n, int32_t *__restrict__ out,
-                 int bitDepth)
-{
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int16_t *smem = reinterpret_cast<int16_t *>(smemRaw + warp * kSmemPerWarp);
-    const int warpsTotal = gridDim.x * kWarps;
-    for (int i = blockIdx.x * kWarps + warp; i < n; i += warpsTotal)
-    {
-        const hvb_pu_cost_task t = tasks[i];
-        int bx[2] = {0, 0}, by[2] = {0, 0};
-        for (int r = 0; r < 2; ++r)
-            if (t.ref_pic[r] >= 0)
-            {
-                const HvbPlane &rp = planes[t.ref_pic[r] * 3];
-                bx[r] = clipMvLumaComponent(t.x0 + (t.mvx[r] >> 2), t.w, rp.width);
-                by[r] = clipMvLumaComponent(t.y0 + (t.mvy[r] >> 2), t.h, rp.height);
-            }
-        const int y = puComponent<Sample, 8>(smem, planes, t, 0, bx, by, bitDepth, lane);
-        __syncwarp();
-        const int cb = puComponent<Sample, 4>(smem, planes, t, 1, bx, by, bitDepth, lane);
-        __syncwarp();
-        const int cr = puComponent<Sample, 4>(smem, planes, t, 2, bx, by, bitDepth, lane);
-        __syncwarp();
-        if (lane == 0)
-        {
-            out[3 * i] = y;
-            out[3 * i + 1] = cb;
-            out[3 * i + 2] = cr;
-        }
-    }
-}
-
 int gridWarps(hvb_context *ctx, int n, int warps, int perSm)
 {
     const int blocks = (n + warps - 1) / warps;
@@ -320,29 +221,4 @@ extern "C" int hvb_subtract_bi_batch(hvb_context *ctx, const hvb_subtract_bi_tas
         subtractBiKernel<uint16_t><<<gridWarps(ctx, n, 8, 8), 256, 0, ctx->stream>>>(ctx->dPlanes, dT, n, ctx->bitDepth);
     HVB_LAUNCH_CHECK(ctx, "subtractBiKernel");
     return hvbStageOut(ctx, nullptr, 0, mem, st);
-}
-
-int hvbPuCostBatchV1(hvb_context *ctx, const hvb_pu_cost_task *tasks, int n, int32_t *out, hvb_mem mem)
-{
-    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && out)));
-    if (!n) return HVB_OK;
-    cudaSetDevice(ctx->device);
-    HvbStaged st;
-    int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(int32_t) * 3 * n, mem, &st);
-    if (rc) return rc;
-    const int smem = kWarps * kSmemPerWarp;
-    const auto *dT = static_cast<const hvb_pu_cost_task *>(st.dTasks);
-    auto *dO = static_cast<int32_t *>(st.dOut);
-    if (ctx->bps == 1)
-    {
-        cudaFuncSetAttribute(puCostKernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        puCostKernel<uint8_t><<<gridWarps(ctx, n, kWarps, 3), kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
-    }
-    else
-    {
-        cudaFuncSetAttribute(puCostKernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        puCostKernel<uint16_t><<<gridWarps(ctx, n, kWarps, 3), kWarps * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
-    }
-    HVB_LAUNCH_CHECK(ctx, "puCostKernel");
-    return hvbStageOut(ctx, out, sizeof(int32_t) * 3 * n, mem, st);
 }

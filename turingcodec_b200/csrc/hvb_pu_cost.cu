@@ -25,7 +25,6 @@
 // block per warp), which is what lets 48 warps per SM hide the latency of the reference-picture reads.
 #include "hvb_internal.cuh"
 #include "hvb_unit.cuh"
-#include <cstdlib>
 
 namespace {
 
@@ -426,12 +425,8 @@ int launch(hvb_context *ctx, const hvb_pu_cost_task *dTasks, int n, int32_t *dOu
 
 } // namespace
 
-int hvbPuCostBatchV1(hvb_context *ctx, const hvb_pu_cost_task *tasks, int n, int32_t *out, hvb_mem mem);
-
 extern "C" int hvb_pu_cost_batch(hvb_context *ctx, const hvb_pu_cost_task *tasks, int n, int32_t *out, hvb_mem mem)
 {
-    const bool v1 = getenv("HVB_PUCOST_V1") != nullptr; // A/B of the first-generation kernel, to be removed
-    if (v1) return hvbPuCostBatchV1(ctx, tasks, n, out, mem);
     HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && out)));
     if (!n) return HVB_OK;
     cudaSetDevice(ctx->device);
