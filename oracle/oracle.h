@@ -233,6 +233,16 @@ int orc_rdoq(int16_t *dst, const int16_t *src, const orc_rdoq_ctx *ctx, int quan
 /* turing/ScanOrder.h: x (comp 0) / y (comp 1) of scan position `pos` in a (1<<log2)^2 block */
 int orc_scan_order(int log2, int scanIdx, int pos, int comp);
 
+/* ---- in-loop deblocking, pixel pass ---------------------------------- */
+
+/* turing/LoopFilter.h:739-777 (Picture::deblock<edgeType>) with :229-423 (Luma/ChromaBlockEdge): filters the edges of
+ * type `edgeType` (0 vertical, 1 horizontal) of the 8x8 blocks [xBegin/8, xEnd/8) x [yBegin/8, yEnd/8) in place, 4:2:0.
+ * blocks = (data, packedBs) byte pairs of LoopFilter::Block (:50-90), blockStride records per row; ctuOffsets =
+ * (slice_tc_offset_div2, slice_beta_offset_div2) per CTU, raster order.  Pinned: tests/test_oracle_pin_loopfilter.py. */
+void orc_deblock(void *const planes[3], const intptr_t strides[3], int bps, int bitDepthY, int bitDepthC, const uint8_t *blocks,
+                 int blockStride, const int8_t *ctuOffsets, int picWidthInCtbs, int ctbLog2, int cbQpOffset, int crQpOffset,
+                 int edgeType, int xBegin, int yBegin, int xEnd, int yEnd);
+
 #ifdef __cplusplus
 }
 #endif

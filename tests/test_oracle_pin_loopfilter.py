@@ -1,0 +1,110 @@
+"""Pins the oracle's deblocking pixel pass (oracle/oracle_loopfilter.c) against the UNMODIFIED reference templates --
+LoopFilter::Picture::deblock<edgeType> with LumaBlockEdge / ChromaBlockEdge (turing/LoopFilter.h:165-423, :739-777),
+driven by oracle/ref_shim_loopfilter.cpp inside oracle/_ref/libhavoc_ref.so -- on blocky pictures with random boundary
+strengths, QPs, filter-disable bits (pcm / transquant bypass), slice tc / beta offsets and chroma QP offsets at 8, 9
+and 10 bit: whole-picture passes (vertical edges, then horizontal) and the per-CTU regions of TaskDeblock::run
+(turing/TaskDeblock.cpp:104-127) must leave identical pictures."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import orc
+
+W, H, CTB_LOG2 = 176, 144, 6  # 3 x 3 CTUs of 64, the last row / column partial
+
+
+@pytest.fixture(scope="module")
+def reflib():
+    if not orc.REF_LIB.exists():
+        pytest.skip("oracle/_ref/libhavoc_ref.so not built")
+    lib = C.CDLL(str(orc.REF_LIB))
+    if not hasattr(lib, "ref_deblock"):
+        pytest.skip("libhavoc_ref.so predates ref_shim_loopfilter.cpp (make -C oracle ref)")
+    return lib
+
+
+def make_case(rng, bps, bit_depth, reflib):
+    """-> planes (list of 3 arrays), block records, CTU offsets, grid stride"""
+    dtype = np.uint8 if bps == 1 else np.uint16
+    top = (1 << bit_depth) - 1
+    planes = []
+    for c in range(3):
+        w, h = (W, H) if c == 0 else (W // 2, H // 2)
+        n = 8 if c == 0 else 4
+        # a level per block (so that edges are real), a gentle ramp and a little noise: all three filters
+        # (strong, normal, normal with p1/q1) and the "no filtering" exits occur
+        level = rng.integers(top // 4, 3 * top // 4, (h // n + 1, w // n + 1))
+        base = np.kron(level, np.ones((n, n), np.int64))[:h, :w]
+        step = rng.integers(0, 6 << (bit_depth - 8), (h // n + 1, w // n + 1))
+        jump = np.kron(step * rng.choice([-1, 1], step.shape), np.ones((n, n), np.int64))[:h, :w]
+        base = np.where(rng.random((h, w)) < 0.5, base, base[0, 0] + jump)
+        noise = rng.integers(-2 << (bit_depth - 8), (2 << (bit_depth - 8)) + 1, (h, w))
+        planes.append(np.clip(base + noise, 0, top).astype(dtype))
+    wc, hc = -(-W >> CTB_LOG2), -(-H >> CTB_LOG2)
+    stride, rows = C.c_int(), C.c_int()
+    reflib.ref_deblock_grid(wc, hc, CTB_LOG2, C.byref(stride), C.byref(rows))
+    stride, rows = stride.value, rows.value
+    blocks = np.zeros((rows, stride, 2), np.uint8)
+    qp = rng.integers(18, 46, (rows, stride))
+    disable = rng.random((rows, stride)) < 0.1
+    blocks[..., 0] = ((qp << 1) | disable).astype(np.uint8)
+    bs = rng.choice([0, 1, 2], (rows, stride, 4), p=[0.3, 0.35, 0.35])  # [vertical pos 0, 1, horizontal pos 0, 1]
+    bs[:, 0, 0:2] = 0  # no picture-boundary edges (the encoder never sets them: processCu / neighbour availability)
+    bs[0, :, 2:4] = 0
+    blocks[..., 1] = (bs[..., 0] | bs[..., 1] << 2 | bs[..., 2] << 4 | bs[..., 3] << 6).astype(np.uint8)
+    ctu = rng.integers(-3, 4, (wc * hc, 2)).astype(np.int8)
+    return planes, blocks, ctu, stride, (wc, hc)
+
+
+def call(fn, is_ref, planes, bps, bit_depth, blocks, ctu, stride, ctbs, offsets, edge, region):
+    ptrs = (C.c_void_p * 3)(*[p.ctypes.data for p in planes])
+    strides = (C.c_ssize_t * 3)(*[p.shape[1] for p in planes])
+    b, o = blocks.ctypes.data_as(C.c_void_p), ctu.ctypes.data_as(C.c_void_p)
+    if is_ref:
+        fn(ptrs, strides, bps, bit_depth, bit_depth, ctbs[0], ctbs[1], CTB_LOG2, offsets[0], offsets[1], b, o, edge, *region)
+    else:
+        fn(ptrs, strides, bps, bit_depth, bit_depth, b, stride, o, ctbs[0], CTB_LOG2, offsets[0], offsets[1], edge, *region)
+
+
+@pytest.mark.parametrize("bps,bit_depth", [(1, 8), (2, 10), (2, 9)])
+def test_whole_picture_passes_match_reference(reflib, oracle, bps, bit_depth):
+    rng = np.random.default_rng(200 + bit_depth)
+    changed = strong_like = 0
+    for trial in range(12):
+        planes, blocks, ctu, stride, ctbs = make_case(rng, bps, bit_depth, reflib)
+        offsets = tuple(int(v) for v in rng.integers(-4, 5, 2))
+        want = [p.copy() for p in planes]
+        got = [p.copy() for p in planes]
+        for edge in (0, 1):  # H.265 8.7.2: every vertical edge of the picture, then every horizontal edge
+            call(reflib.ref_deblock, True, want, bps, bit_depth, blocks, ctu, stride, ctbs, offsets, edge, (0, 0, W, H))
+            call(oracle.lib.orc_deblock, False, got, bps, bit_depth, blocks, ctu, stride, ctbs, offsets, edge, (0, 0, W, H))
+            for c in range(3):
+                assert np.array_equal(got[c], want[c]), (trial, edge, c)
+            if edge == 0:  # after the vertical pass, columns 2 mod 8 (q2) can only have moved in the strong filter
+                strong_like += int((want[0] != planes[0])[:, 2::8].sum())
+        changed += sum(int((w != p).sum()) for w, p in zip(want, planes))
+    assert changed > 20000 and strong_like > 200
+
+
+def test_ctu_regions_of_task_deblock_match_whole_picture(reflib, oracle):
+    """TaskDeblock::run walks the CTUs in raster order, vertical edges of a region shifted by 8 then the horizontal edges
+    of the CTU (turing/TaskDeblock.cpp:104-127); the result is the whole-picture two-pass result, for the reference and
+    for the oracle alike."""
+    rng = np.random.default_rng(77)
+    planes, blocks, ctu, stride, ctbs = make_case(rng, 1, 8, reflib)
+    whole = [p.copy() for p in planes]
+    for edge in (0, 1):
+        call(oracle.lib.orc_deblock, False, whole, 1, 8, blocks, ctu, stride, ctbs, (1, -2), edge, (0, 0, W, H))
+    for fn, is_ref in ((reflib.ref_deblock, True), (oracle.lib.orc_deblock, False)):
+        got = [p.copy() for p in planes]
+        n = 1 << CTB_LOG2
+        for ry in range(ctbs[1]):
+            for rx in range(ctbs[0]):
+                x0, y0 = rx * n, ry * n
+                ver = (x0 + (8 if rx else 0), y0 + (8 if ry else 0), min(x0 + n + 8, W), min(y0 + n + 8, H))
+                hor = (x0, y0 + (8 if ry else 0), min(x0 + n, W), min(y0 + n + 8, H))
+                call(fn, is_ref, got, 1, 8, blocks, ctu, stride, ctbs, (1, -2), 0, ver)
+                call(fn, is_ref, got, 1, 8, blocks, ctu, stride, ctbs, (1, -2), 1, hor)
+        for c in range(3):
+            assert np.array_equal(got[c], whole[c]), (is_ref, c)
