@@ -376,6 +376,40 @@ typedef struct
 } hvb_me_bi_result; /* 32 bytes */
 int hvb_me_bi_search_batch(hvb_context *ctx, const hvb_me_bi_task *tasks, int n, hvb_me_bi_result *out, hvb_mem mem);
 
+/* ---- in-loop deblocking, pixel pass (first GPU verification pending) ---- */
+
+/* LoopFilter::Block (turing/LoopFilter.h:50-90), one per 8x8 luma block as the encoder's process*() calls leave it:
+ * data = QpY << 1 | (pcm-with-loop-filter-disabled or cu_transquant_bypass), packedBs = four 2-bit boundary strengths,
+ * bits 4*edgeType + 2*position (edgeType 0: the block's left edge, 1: its top edge; position: which 4-sample half). */
+typedef struct
+{
+    int8_t data;
+    uint8_t packedBs;
+} hvb_deblock_block; /* 2 bytes */
+/* the two members of LoopFilter::Ctu (turing/LoopFilter.h:92-96) the deblocking filter reads, per CTU in raster order */
+typedef struct
+{
+    int8_t tc_offset_div2, beta_offset_div2;
+} hvb_deblock_ctu; /* 2 bytes */
+/* Side information of picture `pic` (host arrays; kept on the device until replaced or the picture is destroyed).
+ * blockStride x blockRows is the reference's grid: ((PicWidthInCtbsY << CtbLog2SizeY) >> 3) + 1 records per row
+ * (turing/LoopFilter.h:436-443).  Edges on the picture boundary must carry strength 0, as the encoder leaves them. */
+int hvb_deblock_info_upload(hvb_context *ctx, int pic, const hvb_deblock_block *blocks, int blockStride, int blockRows,
+                            const hvb_deblock_ctu *ctus, int picWidthInCtbs, int picHeightInCtbs, int ctbLog2);
+/* One call of LoopFilter::Picture::deblock<edgeType>(h, recL, recCb, recCr, xBegin, yBegin, xEnd, yEnd)
+ * (turing/LoopFilter.h:739-777): the edges of that type of the 8x8 blocks [xBegin/8, xEnd/8) x [yBegin/8, yEnd/8),
+ * luma and 4:2:0 chroma, filtered in place.  The tasks of one batch run concurrently and must not share samples: all
+ * vertical-edge regions of a picture (disjoint regions, e.g. TaskDeblock's per-CTU ones, turing/TaskDeblock.cpp:104-114)
+ * in one call, the horizontal-edge regions in the next (H.265 8.7.2: horizontal edges see the vertical pass's output). */
+typedef struct
+{
+    int16_t pic;
+    int16_t edgeType; /* 0: vertical edges, 1: horizontal edges */
+    int16_t xBegin, yBegin, xEnd, yEnd; /* luma samples */
+    int16_t cbQpOffset, crQpOffset;     /* pps_cb_qp_offset, pps_cr_qp_offset */
+} hvb_deblock_task; /* 16 bytes */
+int hvb_deblock_batch(hvb_context *ctx, const hvb_deblock_task *tasks, int n, hvb_mem mem);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,8 +24,8 @@ def reflib():
     return lib
 
 
-def make_case(rng, bps, bit_depth, reflib):
-    """-> planes (list of 3 arrays), block records, CTU offsets, grid stride"""
+def make_case(rng, bps, bit_depth):
+    """-> planes (list of 3 arrays), block records [rows][stride][data, packedBs], CTU offsets, grid stride, CTUs (w, h)"""
     dtype = np.uint8 if bps == 1 else np.uint16
     top = (1 << bit_depth) - 1
     planes = []
@@ -41,9 +41,7 @@ def make_case(rng, bps, bit_depth, reflib):
         noise = rng.integers(-amp, amp + 1, (h, w))
         planes.append(np.clip(base + noise, 0, top).astype(dtype))
     wc, hc = -(-W >> CTB_LOG2), -(-H >> CTB_LOG2)
-    stride, rows = C.c_int(), C.c_int()
-    reflib.ref_deblock_grid(wc, hc, CTB_LOG2, C.byref(stride), C.byref(rows))
-    stride, rows = stride.value, rows.value
+    stride, rows = ((wc << CTB_LOG2) >> 3) + 1, ((hc << CTB_LOG2) >> 3) + 1  # turing/LoopFilter.h:436-443
     blocks = np.zeros((rows, stride, 2), np.uint8)
     qp = rng.integers(18, 46, (rows, stride))
     disable = rng.random((rows, stride)) < 0.1
@@ -54,6 +52,24 @@ def make_case(rng, bps, bit_depth, reflib):
     blocks[..., 1] = (bs[..., 0] | bs[..., 1] << 2 | bs[..., 2] << 4 | bs[..., 3] << 6).astype(np.uint8)
     ctu = rng.integers(-3, 4, (wc * hc, 2)).astype(np.int8)
     return planes, blocks, ctu, stride, (wc, hc)
+
+
+def test_grid_geometry_is_the_reference_s(reflib):
+    stride, rows = C.c_int(), C.c_int()
+    wc, hc = -(-W >> CTB_LOG2), -(-H >> CTB_LOG2)
+    reflib.ref_deblock_grid(wc, hc, CTB_LOG2, C.byref(stride), C.byref(rows))
+    assert (stride.value, rows.value) == (((wc << CTB_LOG2) >> 3) + 1, ((hc << CTB_LOG2) >> 3) + 1)
+
+
+def ctu_regions(ctbs):
+    """the regions TaskDeblock::run filters per CTU (turing/TaskDeblock.cpp:104-127): [(vertical, horizontal)] in raster order"""
+    n, out = 1 << CTB_LOG2, []
+    for ry in range(ctbs[1]):
+        for rx in range(ctbs[0]):
+            x0, y0 = rx * n, ry * n
+            out.append(((x0 + (8 if rx else 0), y0 + (8 if ry else 0), min(x0 + n + 8, W), min(y0 + n + 8, H)),
+                        (x0, y0 + (8 if ry else 0), min(x0 + n, W), min(y0 + n + 8, H))))
+    return out
 
 
 def call(fn, is_ref, planes, bps, bit_depth, blocks, ctu, stride, ctbs, offsets, edge, region):
@@ -71,7 +87,7 @@ def test_whole_picture_passes_match_reference(reflib, oracle, bps, bit_depth):
     rng = np.random.default_rng(200 + bit_depth)
     changed = strong_like = 0
     for trial in range(12):
-        planes, blocks, ctu, stride, ctbs = make_case(rng, bps, bit_depth, reflib)
+        planes, blocks, ctu, stride, ctbs = make_case(rng, bps, bit_depth)
         offsets = tuple(int(v) for v in rng.integers(-4, 5, 2))
         want = [p.copy() for p in planes]
         got = [p.copy() for p in planes]
@@ -91,19 +107,14 @@ def test_ctu_regions_of_task_deblock_match_whole_picture(reflib, oracle):
     of the CTU (turing/TaskDeblock.cpp:104-127); the result is the whole-picture two-pass result, for the reference and
     for the oracle alike."""
     rng = np.random.default_rng(77)
-    planes, blocks, ctu, stride, ctbs = make_case(rng, 1, 8, reflib)
+    planes, blocks, ctu, stride, ctbs = make_case(rng, 1, 8)
     whole = [p.copy() for p in planes]
     for edge in (0, 1):
         call(oracle.lib.orc_deblock, False, whole, 1, 8, blocks, ctu, stride, ctbs, (1, -2), edge, (0, 0, W, H))
     for fn, is_ref in ((reflib.ref_deblock, True), (oracle.lib.orc_deblock, False)):
         got = [p.copy() for p in planes]
-        n = 1 << CTB_LOG2
-        for ry in range(ctbs[1]):
-            for rx in range(ctbs[0]):
-                x0, y0 = rx * n, ry * n
-                ver = (x0 + (8 if rx else 0), y0 + (8 if ry else 0), min(x0 + n + 8, W), min(y0 + n + 8, H))
-                hor = (x0, y0 + (8 if ry else 0), min(x0 + n, W), min(y0 + n + 8, H))
-                call(fn, is_ref, got, 1, 8, blocks, ctu, stride, ctbs, (1, -2), 0, ver)
-                call(fn, is_ref, got, 1, 8, blocks, ctu, stride, ctbs, (1, -2), 1, hor)
+        for ver, hor in ctu_regions(ctbs):
+            call(fn, is_ref, got, 1, 8, blocks, ctu, stride, ctbs, (1, -2), 0, ver)
+            call(fn, is_ref, got, 1, 8, blocks, ctu, stride, ctbs, (1, -2), 1, hor)
         for c in range(3):
             assert np.array_equal(got[c], whole[c]), (is_ref, c)

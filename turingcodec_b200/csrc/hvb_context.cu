@@ -94,9 +94,13 @@ extern "C" void hvb_destroy(hvb_context *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &p : ctx->pictures)
+    {
         for (int c = 0; c < 3; ++c)
             if (p.alloc[c]) cudaFree(p.alloc[c]);
+        if (p.lfInfo) cudaFree(p.lfInfo);
+    }
     if (ctx->dPlanes) cudaFree(ctx->dPlanes);
+    if (ctx->dLoopInfo) cudaFree(ctx->dLoopInfo);
     if (ctx->workCursors) cudaFree(ctx->workCursors);
     for (auto &slot : ctx->slots)
     {
@@ -242,6 +246,15 @@ extern "C" int hvb_picture_destroy(hvb_context *ctx, int pic)
     {
         cudaFree(p.alloc[c]);
         p.alloc[c] = nullptr;
+    }
+    if (p.lfInfo)
+    {
+        // the device table entry goes with it: a later hvb_deblock_batch on a recycled id must find no stale pointers
+        cudaFree(p.lfInfo);
+        p.lfInfo = nullptr;
+        p.lfBytes = 0;
+        ctx->loopInfoHost[pic] = HvbLoopInfo{};
+        if (ctx->dLoopInfo) cudaMemset(ctx->dLoopInfo + pic, 0, sizeof(HvbLoopInfo));
     }
     p.live = false;
     ctx->planesDirty = true;

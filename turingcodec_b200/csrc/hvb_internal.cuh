@@ -31,6 +31,16 @@ struct HvbPicture
     void *alloc[3] = {nullptr, nullptr, nullptr};
     size_t allocBytes[3] = {0, 0, 0};
     HvbPlane plane[3];
+    void *lfInfo = nullptr; // deblocking side information (hvb_deblock_info_upload): block records, then CTU records
+    size_t lfBytes = 0;
+};
+
+// device-side view of a picture's deblocking side information (hvb_loopfilter.cu)
+struct HvbLoopInfo
+{
+    const hvb_deblock_block *blocks;
+    const hvb_deblock_ctu *ctus;
+    int32_t blockStride, blockRows, widthInCtbs, ctbLog2;
 };
 
 struct hvb_context
@@ -47,6 +57,8 @@ struct hvb_context
     HvbPicture pictures[HVB_MAX_PICTURES];
     HvbPlane *dPlanes = nullptr; // [HVB_MAX_PICTURES*3] mirrored on device
     bool planesDirty = true;
+    HvbLoopInfo *dLoopInfo = nullptr; // [HVB_MAX_PICTURES] on the device, allocated by the first hvb_deblock_info_upload
+    HvbLoopInfo loopInfoHost[HVB_MAX_PICTURES] = {};
     int *workCursors = nullptr; // [64] device-side task cursors of the persistent kernels (zeroed on the stream before each use)
 
     // pipelined host mode (hvb_set_pipelined): copies on their own streams, a ring of staging slots

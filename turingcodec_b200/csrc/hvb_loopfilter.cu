@@ -1,0 +1,327 @@
+// hvb_loopfilter.cu -- the pixel pass of the in-loop deblocking filter on device-resident reconstructed pictures
+// (the first row "next" after the hot path; it gates reference-picture availability,
+// turing/TaskEncodeSubstream.cpp:81,91, so keeping it on the device removes the per-CTU reconstruction round trip).
+//
+// Reference semantics (bit-exact):
+//   LoopFilter::Picture::deblock<edgeType>   turing/LoopFilter.h:739-777  (region walk over 8x8 blocks, 4:2:0 chroma rule)
+//   LumaBlockEdge   decisions + filters      turing/LoopFilter.h:229-357  (H.265 8.7.2.5.3, .6, .7)
+//   ChromaBlockEdge                          turing/LoopFilter.h:359-423  (H.265 8.7.2.5.5, .8)
+//   LoopFilter::Block / Ctu                  turing/LoopFilter.h:50-163
+//   per-CTU regions                          turing/TaskDeblock.cpp:104-127
+//
+// Mapping.  Edges of one type never share samples (they lie 8 apart and a filter reads 4 and writes 3 samples each side),
+// so an edge SEGMENT -- four lines across one 8x8 block boundary -- is a thread's unit of work, with all of its samples
+// in registers between one load and one store.  Vertical edges: consecutive threads take consecutive blocks of a block row
+// (8 bytes per line each: whole 256-byte rows per warp); horizontal edges: consecutive threads take consecutive groups of
+// four columns (one 32-bit word per row each).  Chroma segments (4:2:0: every second luma block edge, strength 2 only) are
+// further jobs of the same launch.  The side information (LoopFilter::Block per 8x8 block, the slice's tc / beta offsets
+// per CTU) is uploaded per picture; tasks are regions, exactly the arguments of Picture::deblock.
+//
+// Status: written after the round's GPU budget was spent; parity is established on the CPU side only (oracle pinned
+// against the reference templates, tests/test_oracle_pin_loopfilter.py); tests/test_gpu_zz_loopfilter.py is the device
+// parity test and has not yet run on a GPU.
+#include "hvb_internal.cuh"
+
+namespace {
+
+__device__ __constant__ uint8_t kBeta[52] = {0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15,
+                                             16, 17, 18, 20, 22, 24, 26, 28, 30, 32, 34, 36, 38, 40, 42, 44, 46, 48, 50, 52, 54, 56, 58, 60, 62, 64};
+__device__ __constant__ uint8_t kTc[54] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1,  1,  1,  1,
+                                           2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 5, 5, 6, 6, 7, 8, 9, 10, 11, 13, 14, 16, 18, 20, 22, 24};
+__device__ __constant__ uint8_t kQpCMid[13] = {29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37};
+
+__device__ __forceinline__ int chromaQp(int qPi) { return qPi < 30 ? qPi : (qPi > 42 ? qPi - 6 : kQpCMid[qPi - 30]); }
+
+// four consecutive samples at a 4-sample-aligned address
+__device__ __forceinline__ void load4(const uint8_t *p, int (&v)[4])
+{
+    const uint32_t w = *reinterpret_cast<const uint32_t *>(p);
+    v[0] = w & 0xff;
+    v[1] = (w >> 8) & 0xff;
+    v[2] = (w >> 16) & 0xff;
+    v[3] = w >> 24;
+}
+__device__ __forceinline__ void load4(const uint16_t *p, int (&v)[4])
+{
+    const uint2 w = *reinterpret_cast<const uint2 *>(p);
+    v[0] = w.x & 0xffff;
+    v[1] = w.x >> 16;
+    v[2] = w.y & 0xffff;
+    v[3] = w.y >> 16;
+}
+__device__ __forceinline__ void store4(uint8_t *p, const int (&v)[4])
+{
+    *reinterpret_cast<uint32_t *>(p) = (uint32_t)v[0] | (uint32_t)v[1] << 8 | (uint32_t)v[2] << 16 | (uint32_t)v[3] << 24;
+}
+__device__ __forceinline__ void store4(uint16_t *p, const int (&v)[4])
+{
+    *reinterpret_cast<uint2 *>(p) = make_uint2((uint32_t)v[0] | (uint32_t)v[1] << 16, (uint32_t)v[2] | (uint32_t)v[3] << 16);
+}
+
+struct Side
+{
+    int qp;
+    bool enabled;
+    __device__ __forceinline__ explicit Side(hvb_deblock_block b) : qp(b.data >> 1), enabled(!(b.data & 1)) {}
+};
+
+// decisions and filters of one luma segment; s[line][p3 p2 p1 p0 q0 q1 q2 q3] is updated in place
+__device__ __forceinline__ void lumaSegment(int (&s)[4][8], int bS, Side P, Side Q, int tcOffsetDiv2, int betaOffsetDiv2, int bitDepth)
+{
+    const int qPL = (Q.qp + P.qp + 1) >> 1;
+    const int beta = kBeta[hvbClip3(0, 51, qPL + 2 * betaOffsetDiv2)] << (bitDepth - 8);
+    const int tC = kTc[hvbClip3(0, 53, qPL + 2 * (bS - 1) + 2 * tcOffsetDiv2)] << (bitDepth - 8);
+    const int maxv = (1 << bitDepth) - 1;
+    const int dp0 = abs(s[0][1] - 2 * s[0][2] + s[0][3]), dp3 = abs(s[3][1] - 2 * s[3][2] + s[3][3]);
+    const int dq0 = abs(s[0][6] - 2 * s[0][5] + s[0][4]), dq3 = abs(s[3][6] - 2 * s[3][5] + s[3][4]);
+    if (dp0 + dq0 + dp3 + dq3 >= beta) return;
+    const bool strong0 = 2 * (dp0 + dq0) < (beta >> 2) && abs(s[0][0] - s[0][3]) + abs(s[0][4] - s[0][7]) < (beta >> 3) &&
+                         abs(s[0][3] - s[0][4]) < ((5 * tC + 1) >> 1);
+    const bool strong3 = 2 * (dp3 + dq3) < (beta >> 2) && abs(s[3][0] - s[3][3]) + abs(s[3][4] - s[3][7]) < (beta >> 3) &&
+                         abs(s[3][3] - s[3][4]) < ((5 * tC + 1) >> 1);
+    const bool strong = strong0 && strong3;
+    const int sideThreshold = (beta + (beta >> 1)) >> 3;
+    const bool dEp = dp0 + dp3 < sideThreshold, dEq = dq0 + dq3 < sideThreshold;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        const int p3 = s[k][0], p2 = s[k][1], p1 = s[k][2], p0 = s[k][3], q0 = s[k][4], q1 = s[k][5], q2 = s[k][6], q3 = s[k][7];
+        if (strong)
+        {
+            if (P.enabled)
+            {
+                s[k][3] = hvbClip3(p0 - 2 * tC, p0 + 2 * tC, (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+                s[k][2] = hvbClip3(p1 - 2 * tC, p1 + 2 * tC, (p2 + p1 + p0 + q0 + 2) >> 2);
+                s[k][1] = hvbClip3(p2 - 2 * tC, p2 + 2 * tC, (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+            }
+            if (Q.enabled)
+            {
+                s[k][4] = hvbClip3(q0 - 2 * tC, q0 + 2 * tC, (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+                s[k][5] = hvbClip3(q1 - 2 * tC, q1 + 2 * tC, (p0 + q0 + q1 + q2 + 2) >> 2);
+                s[k][6] = hvbClip3(q2 - 2 * tC, q2 + 2 * tC, (p0 + q0 + q1 + 3 * q2 + 2 * q3 + 4) >> 3);
+            }
+        }
+        else
+        {
+            int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
+            if (abs(delta) < tC * 10)
+            {
+                delta = hvbClip3(-tC, tC, delta);
+                if (P.enabled) s[k][3] = hvbClip3(0, maxv, p0 + delta);
+                if (Q.enabled) s[k][4] = hvbClip3(0, maxv, q0 - delta);
+                if (dEp && P.enabled) s[k][2] = hvbClip3(0, maxv, p1 + hvbClip3(-(tC >> 1), tC >> 1, (((p2 + p0 + 1) >> 1) - p1 + delta) >> 1));
+                if (dEq && Q.enabled) s[k][5] = hvbClip3(0, maxv, q1 + hvbClip3(-(tC >> 1), tC >> 1, (((q2 + q0 + 1) >> 1) - q1 - delta) >> 1));
+            }
+        }
+    }
+}
+
+template <typename Sample>
+__global__ void __launch_bounds__(256)
+    deblockKernel(const HvbPlane *__restrict__ planes, const HvbLoopInfo *__restrict__ info, const hvb_deblock_task *__restrict__ tasks, int n,
+                  int bitDepth)
+{
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    for (int ti = 0; ti < n; ++ti)
+    {
+        const hvb_deblock_task t = tasks[ti];
+        const HvbLoopInfo li = info[t.pic];
+        const int bx0 = t.xBegin / 8, by0 = t.yBegin / 8, nbx = t.xEnd / 8 - bx0, nby = t.yEnd / 8 - by0;
+        if (nbx <= 0 || nby <= 0 || !li.blocks) continue;
+        const int edge = t.edgeType;
+        const int lumaJobs = nbx * nby * 2, jobs = 2 * lumaJobs;
+        for (int job = gtid; job < jobs; job += gthreads)
+        {
+            const bool chroma = job >= lumaJobs;
+            const int j = chroma ? job - lumaJobs : job;
+            // luma: (block row, position, block) for vertical edges, (block row, block, position) for horizontal ones;
+            // chroma: (block row, component, block)
+            const int byi = j / (2 * nbx), r = j - byi * 2 * nbx;
+            int bxi, sel;
+            if (chroma || edge == 0)
+            {
+                sel = r / nbx;
+                bxi = r - sel * nbx;
+            }
+            else
+            {
+                bxi = r >> 1;
+                sel = r & 1;
+            }
+            const int bx = bx0 + bxi, by = by0 + byi;
+            const hvb_deblock_block qb = li.blocks[(intptr_t)by * li.blockStride + bx];
+            const int bS = (qb.packedBs >> (4 * edge + (chroma ? 0 : 2 * sel))) & 3;
+            if (chroma ? (bS != 2 || ((edge == 0 ? bx : by) & 1)) : bS == 0) continue;
+            const hvb_deblock_block pb = li.blocks[edge == 0 ? (intptr_t)by * li.blockStride + bx - 1 : (intptr_t)(by - 1) * li.blockStride + bx];
+            const Side P(pb), Q(qb);
+            const hvb_deblock_ctu ctu = li.ctus[li.widthInCtbs * ((by << 3) >> li.ctbLog2) + ((bx << 3) >> li.ctbLog2)];
+
+            if (!chroma)
+            {
+                const HvbPlane &pl = planes[t.pic * 3];
+                Sample *base = reinterpret_cast<Sample *>(pl.base);
+                const intptr_t stride = pl.stride;
+                int s[4][8];
+                if (edge == 0)
+                {
+                    Sample *line = base + (intptr_t)(8 * by + 4 * sel) * stride + 8 * bx - 4;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        int a[4], b[4];
+                        load4(line + k * stride, a);
+                        load4(line + k * stride + 4, b);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) s[k][i] = a[i], s[k][4 + i] = b[i];
+                    }
+                    lumaSegment(s, bS, P, Q, ctu.tc_offset_div2, ctu.beta_offset_div2, bitDepth);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const int a[4] = {s[k][0], s[k][1], s[k][2], s[k][3]}, b[4] = {s[k][4], s[k][5], s[k][6], s[k][7]};
+                        store4(line + k * stride, a);
+                        store4(line + k * stride + 4, b);
+                    }
+                }
+                else
+                {
+                    Sample *col = base + (intptr_t)(8 * by - 4) * stride + 8 * bx + 4 * sel;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                    {
+                        int a[4];
+                        load4(col + i * stride, a);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) s[k][i] = a[k];
+                    }
+                    lumaSegment(s, bS, P, Q, ctu.tc_offset_div2, ctu.beta_offset_div2, bitDepth);
+#pragma unroll
+                    for (int i = 1; i < 7; ++i)
+                    {
+                        const int a[4] = {s[0][i], s[1][i], s[2][i], s[3][i]};
+                        store4(col + i * stride, a);
+                    }
+                }
+            }
+            else
+            {
+                // one segment of four chroma lines per 8-sample luma edge; c = 1 + sel
+                const HvbPlane &pl = planes[t.pic * 3 + 1 + sel];
+                Sample *base = reinterpret_cast<Sample *>(pl.base);
+                const intptr_t stride = pl.stride;
+                const int QpC = chromaQp(((Q.qp + P.qp + 1) >> 1) + (sel ? t.crQpOffset : t.cbQpOffset));
+                const int tC = kTc[hvbClip3(0, 53, QpC + 2 + 2 * ctu.tc_offset_div2)] << (bitDepth - 8);
+                const int maxv = (1 << bitDepth) - 1;
+                int c[4][4]; // [line][p1 p0 q0 q1]
+                if (edge == 0)
+                {
+                    Sample *line = base + (intptr_t)(4 * by) * stride + 4 * bx - 4;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        int a[4], b[4];
+                        load4(line + k * stride, a);
+                        load4(line + k * stride + 4, b);
+                        const int delta = hvbClip3(-tC, tC, (((b[0] - a[3]) << 2) + a[2] - b[1] + 4) >> 3);
+                        if (P.enabled) a[3] = hvbClip3(0, maxv, a[3] + delta);
+                        if (Q.enabled) b[0] = hvbClip3(0, maxv, b[0] - delta);
+                        store4(line + k * stride, a);
+                        store4(line + k * stride + 4, b);
+                    }
+                }
+                else
+                {
+                    Sample *col = base + (intptr_t)(4 * by - 2) * stride + 4 * bx;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                    {
+                        int a[4];
+                        load4(col + i * stride, a);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) c[k][i] = a[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                    {
+                        const int delta = hvbClip3(-tC, tC, (((c[k][2] - c[k][1]) << 2) + c[k][0] - c[k][3] + 4) >> 3);
+                        const int p0 = c[k][1], q0 = c[k][2];
+                        if (P.enabled) c[k][1] = hvbClip3(0, maxv, p0 + delta);
+                        if (Q.enabled) c[k][2] = hvbClip3(0, maxv, q0 - delta);
+                    }
+#pragma unroll
+                    for (int i = 1; i < 3; ++i)
+                    {
+                        const int a[4] = {c[0][i], c[1][i], c[2][i], c[3][i]};
+                        store4(col + i * stride, a);
+                    }
+                }
+            }
+        }
+    }
+}
+
+} // namespace
+
+extern "C" int hvb_deblock_info_upload(hvb_context *ctx, int pic, const hvb_deblock_block *blocks, int blockStride, int blockRows,
+                                       const hvb_deblock_ctu *ctus, int picWidthInCtbs, int picHeightInCtbs, int ctbLog2)
+{
+    HVB_CHECK_ARGS(ctx, pic >= 0 && pic < HVB_MAX_PICTURES && ctx->pictures[pic].live);
+    HVB_CHECK_ARGS(ctx, blocks && ctus && blockStride > 0 && blockRows > 0 && picWidthInCtbs > 0 && picHeightInCtbs > 0 && ctbLog2 >= 4 && ctbLog2 <= 6);
+    cudaSetDevice(ctx->device);
+    HvbPicture &p = ctx->pictures[pic];
+    const size_t blockBytes = sizeof(hvb_deblock_block) * (size_t)blockStride * blockRows;
+    const size_t ctuBytes = sizeof(hvb_deblock_ctu) * (size_t)picWidthInCtbs * picHeightInCtbs;
+    cudaError_t e = cudaSuccess;
+    if (!ctx->dLoopInfo)
+    {
+        e = cudaMalloc(&ctx->dLoopInfo, sizeof(HvbLoopInfo) * HVB_MAX_PICTURES);
+        if (e == cudaSuccess) e = cudaMemsetAsync(ctx->dLoopInfo, 0, sizeof(HvbLoopInfo) * HVB_MAX_PICTURES, ctx->stream);
+        if (e != cudaSuccess) return hvbCuda(ctx, e, "loop-filter table");
+    }
+    if (p.lfBytes < blockBytes + ctuBytes + 256)
+    {
+        cudaStreamSynchronize(ctx->stream);
+        if (p.lfInfo) cudaFree(p.lfInfo);
+        p.lfInfo = nullptr;
+        p.lfBytes = 0;
+        e = cudaMalloc(&p.lfInfo, blockBytes + ctuBytes + 256);
+        if (e != cudaSuccess) return hvbCuda(ctx, e, "loop-filter side information");
+        p.lfBytes = blockBytes + ctuBytes + 256;
+    }
+    char *dBlocks = static_cast<char *>(p.lfInfo), *dCtus = dBlocks + ((blockBytes + 255) & ~size_t(255));
+    int rc = hvbUpload(ctx, dBlocks, blockBytes, blocks, blockBytes, blockBytes, 1, "deblock blocks");
+    if (rc) return rc;
+    rc = hvbUpload(ctx, dCtus, ctuBytes, ctus, ctuBytes, ctuBytes, 1, "deblock ctus");
+    if (rc) return rc;
+    HvbLoopInfo li;
+    li.blocks = reinterpret_cast<const hvb_deblock_block *>(dBlocks);
+    li.ctus = reinterpret_cast<const hvb_deblock_ctu *>(dCtus);
+    li.blockStride = blockStride;
+    li.blockRows = blockRows;
+    li.widthInCtbs = picWidthInCtbs;
+    li.ctbLog2 = ctbLog2;
+    // a 32-byte kernel-argument-sized record: copied from a context-owned staging copy that outlives the call
+    ctx->loopInfoHost[pic] = li;
+    e = cudaMemcpyAsync(ctx->dLoopInfo + pic, &ctx->loopInfoHost[pic], sizeof(li), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return hvbCuda(ctx, e, "loop-filter table entry");
+    return HVB_OK;
+}
+
+extern "C" int hvb_deblock_batch(hvb_context *ctx, const hvb_deblock_task *tasks, int n, hvb_mem mem)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || tasks));
+    if (!n) return HVB_OK;
+    if (!ctx->dLoopInfo) return hvbFail(ctx, HVB_ERR_INVALID, "hvb_deblock_batch before hvb_deblock_info_upload");
+    cudaSetDevice(ctx->device);
+    HvbStaged st;
+    int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, nullptr, 0, mem, &st);
+    if (rc) return rc;
+    const auto *dT = static_cast<const hvb_deblock_task *>(st.dTasks);
+    const int blocks = ctx->smCount * 8;
+    if (ctx->bps == 1)
+        deblockKernel<uint8_t><<<blocks, 256, 0, ctx->stream>>>(ctx->dPlanes, ctx->dLoopInfo, dT, n, ctx->bitDepth);
+    else
+        deblockKernel<uint16_t><<<blocks, 256, 0, ctx->stream>>>(ctx->dPlanes, ctx->dLoopInfo, dT, n, ctx->bitDepth);
+    HVB_LAUNCH_CHECK(ctx, "deblockKernel");
+    return hvbStageOut(ctx, nullptr, 0, mem, st);
+}

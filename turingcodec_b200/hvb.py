@@ -58,6 +58,10 @@ me_task_t = np.dtype([("src_pic", "<i2"), ("ref_pic", "<i2"), ("x0", "<i2"), ("y
                       ("quarterPel", "u1"), ("reserved", "u1", 2)], align=True)
 pu_cost_task_t = np.dtype([("src_pic", "<i2"), ("dst_pic", "<i2"), ("ref_pic", "<i2", 2), ("x0", "<i2"), ("y0", "<i2"),
                            ("w", "<i2"), ("h", "<i2"), ("mvx", "<i2", 2), ("mvy", "<i2", 2)], align=True)
+deblock_block_t = np.dtype([("data", "i1"), ("packedBs", "u1")], align=True)
+deblock_ctu_t = np.dtype([("tc_offset_div2", "i1"), ("beta_offset_div2", "i1")], align=True)
+deblock_task_t = np.dtype([("pic", "<i2"), ("edgeType", "<i2"), ("xBegin", "<i2"), ("yBegin", "<i2"), ("xEnd", "<i2"),
+                           ("yEnd", "<i2"), ("cbQpOffset", "<i2"), ("crQpOffset", "<i2")], align=True)
 me_bi_task_t = np.dtype([("src_pic", "<i2"), ("ref_pic", "<i2"), ("x0", "<i2"), ("y0", "<i2"), ("w", "<i2"),
                          ("h", "<i2"), ("mvp", mv_t, 2), ("other_pic", "<i2"), ("reserved0", "<i2"),
                          ("rateMvpFlag", "<i8", 2), ("lambda", "<i4"), ("limitMin", mv_t), ("limitMax", mv_t),
@@ -125,8 +129,10 @@ def load_library() -> C.CDLL:
                  "hvb_me_search_batch", "hvb_me_bi_search_batch", "hvb_pu_cost_batch"):
         if hasattr(lib, name):
             getattr(lib, name).argtypes = [vp, vp, i32, vp, i32]
+    if hasattr(lib, "hvb_deblock_info_upload"):
+        lib.hvb_deblock_info_upload.argtypes = [vp, i32, vp, i32, i32, vp, i32, i32, i32]
     for name in ("hvb_pred_batch", "hvb_subtract_bi_batch", "hvb_intra_pred_batch", "hvb_transform_fwd_batch",
-                 "hvb_transform_inv_batch", "hvb_quantize_inverse_batch", "hvb_inverse_transform_add_batch"):
+                 "hvb_transform_inv_batch", "hvb_quantize_inverse_batch", "hvb_inverse_transform_add_batch", "hvb_deblock_batch"):
         if hasattr(lib, name):
             getattr(lib, name).argtypes = [vp, vp, i32, i32]
     _lib = lib
@@ -315,6 +321,17 @@ class Context:
     def pu_cost(self, tasks, n=None, out=None, mem=HOST):
         """-> int32 [n][3]: SATD of Y, Cb, Cr of each PU's inter prediction"""
         return self._with_out("hvb_pu_cost_batch", tasks, n, out, np.int32, lambda k: (k, 3), mem)
+
+    def deblock_info_upload(self, pic: int, blocks: np.ndarray, ctus: np.ndarray, pic_width_in_ctbs: int, pic_height_in_ctbs: int,
+                            ctb_log2: int):
+        """blocks: [rows][stride] of deblock_block_t (the reference's 8x8 grid), ctus: [n] of deblock_ctu_t"""
+        blocks = np.ascontiguousarray(blocks, dtype=deblock_block_t)
+        ctus = np.ascontiguousarray(ctus, dtype=deblock_ctu_t)
+        self._check(self.lib.hvb_deblock_info_upload(self.h, pic, _as_ptr(blocks), blocks.shape[1], blocks.shape[0], _as_ptr(ctus),
+                                                     pic_width_in_ctbs, pic_height_in_ctbs, ctb_log2), "hvb_deblock_info_upload")
+
+    def deblock(self, tasks, n=None, mem=HOST):
+        self._no_out("hvb_deblock_batch", tasks, n, mem)
 
     def me_bi_search(self, tasks, n=None, out=None, mem=HOST):
         return self._with_out("hvb_me_bi_search_batch", tasks, n, out, me_bi_result_t, lambda k: (k,), mem)
