@@ -1,0 +1,118 @@
+"""The device deblocking kernel's own source, executed on the CPU, against the pinned oracle.
+
+csrc/hvb_loopfilter.cu's kernel uses no warp-level primitive and walks its jobs in a grid-stride loop, so with a grid of
+ONE thread its body is an ordinary sequential program.  This test cuts the kernel (the anonymous namespace of the .cu
+file, verbatim) out of the source, compiles it with g++ against the CUDA headers' host definitions (blockIdx / gridDim
+become constants of a 1-thread grid) and runs it on host memory: job decomposition, vector load / store packing, the
+decisions and the three filters are then checked bit-for-bit without a GPU.  What it cannot see is device-only behaviour
+(alignment faults, the launch itself) -- tests/test_gpu_zz_loopfilter.py covers that on a B200.  Nothing here is product
+code: the emulation library is built in a temporary directory."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import orc
+import test_oracle_pin_loopfilter as pin
+from turingcodec_b200 import hvb
+
+ROOT = Path(__file__).resolve().parent.parent
+CUDA_INC = Path("/usr/local/cuda/include")
+
+PRELUDE = r'''
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdlib>
+#include "hvb.h"
+#define __launch_bounds__(...)
+struct HvbPlane { void *base; int32_t stride; int32_t width, height; int32_t pad; int32_t reserved; };
+struct HvbLoopInfo { const hvb_deblock_block *blocks; const hvb_deblock_ctu *ctus; int32_t blockStride, blockRows, widthInCtbs, ctbLog2; };
+static inline int hvbClip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+static const uint3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0};
+static const dim3 blockDim(1), gridDim(1);
+'''
+ENTRY = r'''
+extern "C" void emu_deblock(const HvbPlane *planes, const HvbLoopInfo *info, const hvb_deblock_task *tasks, int n, int bitDepth, int bps)
+{
+    if (bps == 1) deblockKernel<uint8_t>(planes, info, tasks, n, bitDepth);
+    else deblockKernel<uint16_t>(planes, info, tasks, n, bitDepth);
+}
+'''
+
+
+class Plane(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("stride", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("pad", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class LoopInfo(C.Structure):
+    _fields_ = [("blocks", C.c_void_p), ("ctus", C.c_void_p), ("blockStride", C.c_int32), ("blockRows", C.c_int32),
+                ("widthInCtbs", C.c_int32), ("ctbLog2", C.c_int32)]
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    if not (CUDA_INC / "cuda_runtime.h").exists():
+        pytest.skip("CUDA headers not found")
+    src = (ROOT / "turingcodec_b200" / "csrc" / "hvb_loopfilter.cu").read_text()
+    kernel = src[src.index("namespace {"):src.index("} // namespace") + len("} // namespace")]
+    assert "deblockKernel" in kernel and "__shfl" not in kernel and "__syncthreads" not in kernel
+    d = tmp_path_factory.mktemp("emu_loopfilter")
+    (d / "emu.cpp").write_text(PRELUDE + kernel + ENTRY)
+    subprocess.run(["g++", "-O1", "-fPIC", "-shared", "-w", "-std=c++17", f"-I{CUDA_INC}", f"-I{ROOT / 'include'}", str(d / "emu.cpp"),
+                    "-o", str(d / "emu.so")], check=True, capture_output=True)
+    return C.CDLL(str(d / "emu.so"))
+
+
+def run_kernel(emu, planes, bps, bit_depth, blocks, ctu, ctbs, tasks):
+    """planes: arrays whose rows are 256-byte aligned like device pictures (the kernel's vector accesses assume it)"""
+    table = (Plane * 3)(*[Plane(p.ctypes.data, p.strides[0] // p.itemsize, p.shape[1], p.shape[0], 0, 0) for p in planes])
+    b = np.zeros(blocks.shape[:2], hvb.deblock_block_t)
+    b["data"], b["packedBs"] = blocks[..., 0].view(np.int8), blocks[..., 1]
+    c = np.zeros(ctu.shape[0], hvb.deblock_ctu_t)
+    c["tc_offset_div2"], c["beta_offset_div2"] = ctu[:, 0], ctu[:, 1]
+    info = LoopInfo(b.ctypes.data, c.ctypes.data, b.shape[1], b.shape[0], ctbs[0], pin.CTB_LOG2)
+    tasks = np.ascontiguousarray(tasks, dtype=hvb.deblock_task_t)
+    emu.emu_deblock(table, C.byref(info), C.c_void_p(tasks.ctypes.data), tasks.size, bit_depth, bps)
+
+
+def aligned_copy(plane):
+    """a copy whose rows start on 256-byte boundaries (pitch a multiple of 256 bytes), as hvb pictures are laid out"""
+    pitch = -(-plane.shape[1] * plane.itemsize // 256) * 256
+    raw = np.zeros(plane.shape[0] * pitch + 256, np.uint8)
+    off = (-raw.ctypes.data) % 256
+    view = raw[off:off + plane.shape[0] * pitch].view(plane.dtype).reshape(plane.shape[0], pitch // plane.itemsize)[:, :plane.shape[1]]
+    view[...] = plane
+    return view
+
+
+def task(edge, region, offsets):
+    t = np.zeros(1, hvb.deblock_task_t)
+    t["pic"], t["edgeType"] = 0, edge
+    t["xBegin"], t["yBegin"], t["xEnd"], t["yEnd"] = region
+    t["cbQpOffset"], t["crQpOffset"] = offsets
+    return t
+
+
+@pytest.mark.parametrize("bps,bit_depth", [(1, 8), (2, 10), (2, 9)])
+def test_kernel_source_on_cpu_matches_oracle(emu, oracle, bps, bit_depth):
+    rng = np.random.default_rng(400 + bit_depth)
+    for trial in range(8):
+        planes, blocks, ctu, stride, ctbs = pin.make_case(rng, bps, bit_depth)
+        offsets = tuple(int(v) for v in rng.integers(-4, 5, 2))
+        want = [p.copy() for p in planes]
+        whole = [aligned_copy(p) for p in planes]
+        for edge in (0, 1):
+            pin.call(oracle.lib.orc_deblock, False, want, bps, bit_depth, blocks, ctu, stride, ctbs, offsets, edge, (0, 0, pin.W, pin.H))
+            run_kernel(emu, whole, bps, bit_depth, blocks, ctu, ctbs, task(edge, (0, 0, pin.W, pin.H), offsets))
+            for c in range(3):
+                assert np.array_equal(whole[c], want[c]), (trial, edge, c)
+        # TaskDeblock's per-CTU regions, every vertical region in one batch and every horizontal region in the next
+        regional = [aligned_copy(p) for p in planes]
+        regions = pin.ctu_regions(ctbs)
+        for edge in (0, 1):
+            run_kernel(emu, regional, bps, bit_depth, blocks, ctu, ctbs, np.concatenate([task(edge, r[edge], offsets) for r in regions]))
+        for c in range(3):
+            assert np.array_equal(regional[c], want[c]), (trial, "regions", c)
