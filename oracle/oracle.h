@@ -243,6 +243,25 @@ void orc_deblock(void *const planes[3], const intptr_t strides[3], int bps, int 
                  int blockStride, const int8_t *ctuOffsets, int picWidthInCtbs, int ctbLog2, int cbQpOffset, int crQpOffset,
                  int edgeType, int xBegin, int yBegin, int xEnd, int yEnd);
 
+/* One CTU's SAO parameters and neighbourhood as LoopFilter::Ctu holds them (turing/LoopFilter.h:92-163, :476-534):
+ * left/top/right/bottom in luma samples, the four corner availabilities, per component SaoTypeIdx, SaoEoClass or
+ * sao_band_position, and SaoOffsetVal[1..4] (already scaled by 1 << (bitDepth - min(bitDepth, 10))). */
+typedef struct
+{
+    int16_t left, top, right, bottom;
+    uint8_t topLeft, topRight, bottomLeft, bottomRight;
+    struct
+    {
+        int8_t typeIdx, classOrBand;
+        int16_t offset[4];
+    } plane[3];
+} orc_sao_ctu; /* 42 bytes */
+
+/* turing/LoopFilter.h:885-1017 (filterBlockSao) over every CTU of the picture, in applySaoCTU's order (:794-811): SAO of
+ * `src` (the deblocked picture) into `dst`, visible samples only.  Pinned: tests/test_oracle_pin_loopfilter.py. */
+void orc_sao(void *const dst[3], void *const src[3], const intptr_t strides[3], int bps, int bitDepthY, int bitDepthC, int picWidth,
+             int picHeight, int ctbLog2, const uint8_t *blocks, int blockStride, const orc_sao_ctu *ctus, int lumaFlag, int chromaFlag);
+
 #ifdef __cplusplus
 }
 #endif

@@ -168,3 +168,97 @@ void orc_deblock(void *const planes[3], const intptr_t strides[3], int bps, int 
             }
         }
 }
+
+/* ---- sample adaptive offset, application ------------------------------------------------------------------------------
+ *   LoopFilter::Picture::filterBlockSao          turing/LoopFilter.h:885-1017  (per CTU and component)
+ *   sao_filter_edge / sao_filter_band            turing/sao.cpp:35-92          (H.265 8.7.3)
+ *   restoreUnfilteredRegions                     turing/LoopFilter.h:849-877   (pcm / transquant-bypass blocks)
+ *   Ctu neighbourhood (left/top/right/bottom, corner flags)   turing/LoopFilter.h:92-98, :476-534
+ *
+ * The reference filters a whole CTU, copies the disabled 8x8 blocks back and then "undoes" runs of samples on the CTU's
+ * top row / left column / last column / last row according to which neighbouring CTUs are available.  Restated here per
+ * SAMPLE of the visible picture: a sample keeps its deblocked value when its CTU's type is 0, when its 8x8 block is
+ * disabled, or (edge offset only) when it lies in one of those four runs; otherwise it gets the band or edge offset.
+ * Samples outside the picture (the reference's full-CTB copies and its luma-sized clip of chroma CTUs,
+ * LoopFilter.h:894-896, reach there) are not produced: nothing reads them before the padding pass overwrites them.  */
+static int sao_sign(int v) { return (v > 0) - (v < 0); }
+
+void orc_sao(void *const dst[3], void *const src[3], const intptr_t strides[3], int bps, int bitDepthY, int bitDepthC, int picWidth,
+             int picHeight, int ctbLog2, const uint8_t *blocks, int blockStride, const orc_sao_ctu *ctus, int lumaFlag, int chromaFlag)
+{
+    static const int8_t hOff[4] = {-1, 0, -1, 1}, vOff[4] = {0, -1, -1, -1};
+    const int widthInCtbs = (picWidth + (1 << ctbLog2) - 1) >> ctbLog2, heightInCtbs = (picHeight + (1 << ctbLog2) - 1) >> ctbLog2;
+    for (int c = 0; c < 3; ++c)
+    {
+        if (!(c ? chromaFlag : lumaFlag)) continue;
+        const int sh = c ? 1 : 0, n = (1 << ctbLog2) >> sh, bitDepth = c ? bitDepthC : bitDepthY, maxv = (1 << bitDepth) - 1;
+        const int w = picWidth >> sh, h = picHeight >> sh;
+        const plane_t d = {dst[c], strides[c], bps}, s = {src[c], strides[c], bps};
+        for (int ry = 0; ry < heightInCtbs; ++ry)
+            for (int rx = 0; rx < widthInCtbs; ++rx)
+            {
+                const orc_sao_ctu *ctu = &ctus[ry * widthInCtbs + rx];
+                const int type = ctu->plane[c].typeIdx, x0 = rx * n, y0 = ry * n;
+                /* the four undo runs of an edge-offset CTU (LoopFilter.h:917-992) */
+                int undoT = 0, undoL = 0, undoR = 0, undoB = 0, right = ctu->right >> sh, bottom = ctu->bottom >> sh;
+                const int eo = ctu->plane[c].classOrBand;
+                if (type == 2)
+                {
+                    const int availL = (ctu->left >> sh) < x0, availR = right > x0 + n, availT = (ctu->top >> sh) < y0, availB = bottom > y0 + n;
+                    if (eo == 2)
+                    {
+                        if (!ctu->topLeft) ++undoT, ++undoL;
+                        if (!ctu->bottomRight) ++undoR, ++undoB;
+                    }
+                    if (eo != 1)
+                    {
+                        if (!availL) undoL = n;
+                        if (!availR) undoR = n;
+                    }
+                    if (eo != 0)
+                    {
+                        if (!availT) undoT = n;
+                        if (!availB) undoB = n;
+                    }
+                    if (eo == 3)
+                    {
+                        if (ctu->topRight) --undoT, --undoR;
+                        if (ctu->bottomLeft) --undoL, --undoB;
+                    }
+                    if (right > x0 + n) right = x0 + n;
+                    if (bottom > y0 + n) bottom = y0 + n;
+                }
+                for (int y = y0; y < y0 + n && y < h; ++y)
+                    for (int x = x0; x < x0 + n && x < w; ++x)
+                    {
+                        const intptr_t at = (intptr_t)y * s.stride + x;
+                        const int v = get(&s, at);
+                        const uint8_t *block = blocks + 2 * ((intptr_t)((y << sh) >> 3) * blockStride + ((x << sh) >> 3));
+                        int out = v;
+                        if (type && !(block[0] & 1))
+                        {
+                            if (type == 1)
+                            {
+                                const int k = ((v >> (bitDepth - 5)) - eo) & 31; /* band index relative to sao_band_position */
+                                if (k < 4) out = clip3(0, maxv, v + ctu->plane[c].offset[k]);
+                            }
+                            else
+                            {
+                                const int lx = x - x0, ly = y - y0;
+                                const int undone = (ly == 0 && lx < undoT) || (lx == 0 && ly < undoL) || (x == right - 1 && ly >= n - undoR) ||
+                                                   (y == bottom - 1 && lx >= n - undoB);
+                                if (!undone)
+                                {
+                                    const intptr_t step = (intptr_t)vOff[eo] * s.stride + hOff[eo];
+                                    const int idx = 2 + sao_sign(v - get(&s, at + step)) + sao_sign(v - get(&s, at - step));
+                                    /* edgeIdx 0,1,2 -> 1,2,0 (H.265 8.7.3.2): categories 1..4 index SaoOffsetVal, a flat sample gets none */
+                                    static const int8_t category[5] = {1, 2, 0, 3, 4};
+                                    if (category[idx]) out = clip3(0, maxv, v + ctu->plane[c].offset[category[idx] - 1]);
+                                }
+                            }
+                        }
+                        put(&d, at, out);
+                    }
+            }
+    }
+}

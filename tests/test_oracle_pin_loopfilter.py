@@ -118,3 +118,96 @@ def test_ctu_regions_of_task_deblock_match_whole_picture(reflib, oracle):
             call(fn, is_ref, got, 1, 8, blocks, ctu, stride, ctbs, (1, -2), 1, hor)
         for c in range(3):
             assert np.array_equal(got[c], whole[c]), (is_ref, c)
+
+
+# ---- sample adaptive offset ---------------------------------------------------------------------------------------------
+
+class SaoPlane(C.Structure):
+    _pack_ = 1
+    _fields_ = [("typeIdx", C.c_int8), ("classOrBand", C.c_int8), ("offset", C.c_int16 * 4)]
+
+
+class SaoCtu(C.Structure):
+    _pack_ = 1
+    _fields_ = [("left", C.c_int16), ("top", C.c_int16), ("right", C.c_int16), ("bottom", C.c_int16),
+                ("topLeft", C.c_uint8), ("topRight", C.c_uint8), ("bottomLeft", C.c_uint8), ("bottomRight", C.c_uint8),
+                ("plane", SaoPlane * 3)]
+
+
+SAO_PAD = 80  # samples of margin around every plane: the reference's whole-CTB passes reach outside a partial CTU
+
+
+def make_sao_case(rng, bps, bit_depth):
+    """-> padded planes (random margins), visible-area slices, block records, CTU records"""
+    assert C.sizeof(SaoCtu) == 42
+    dtype = np.uint8 if bps == 1 else np.uint16
+    top = (1 << bit_depth) - 1
+    padded, views = [], []
+    for c in range(3):
+        w, h = (W, H) if c == 0 else (W // 2, H // 2)
+        # smooth texture + noise: every edge category and many bands occur; a few samples at the range limits for the clip
+        yy, xx = np.mgrid[0:h + 2 * SAO_PAD, 0:w + 2 * SAO_PAD]
+        tex = (top / 2 + top / 4 * np.sin(xx / 7.0) * np.cos(yy / 5.0)).astype(np.int64) + rng.integers(-3, 4, xx.shape) * (1 << (bit_depth - 8))
+        tex[rng.random(tex.shape) < 0.01] = top
+        tex[rng.random(tex.shape) < 0.01] = 0
+        a = np.clip(tex, 0, top).astype(dtype)
+        padded.append(a)
+        views.append((slice(SAO_PAD, SAO_PAD + h), slice(SAO_PAD, SAO_PAD + w)))
+    wc, hc = -(-W >> CTB_LOG2), -(-H >> CTB_LOG2)
+    stride, rows = ((wc << CTB_LOG2) >> 3) + 1, ((hc << CTB_LOG2) >> 3) + 1
+    blocks = np.zeros((rows, stride, 2), np.uint8)
+    blocks[..., 0] = ((rng.integers(20, 40, (rows, stride)) << 1) | (rng.random((rows, stride)) < 0.1)).astype(np.uint8)
+    n = 1 << CTB_LOG2
+    ctus = (SaoCtu * (wc * hc))()
+    for ry in range(hc):
+        for rx in range(wc):
+            t = ctus[ry * wc + rx]
+            x0, y0 = rx * n, ry * n
+            # picture limits, or a slice / tile boundary without loop filtering across it (LoopFilter.h:476-534)
+            t.left = x0 if (rx and rng.random() < 0.25) else 0
+            t.top = y0 if (ry and rng.random() < 0.25) else 0
+            t.right = x0 + n if (rx < wc - 1 and rng.random() < 0.25) else W
+            t.bottom = y0 + n if (ry < hc - 1 and rng.random() < 0.25) else H
+            t.topLeft = int(rx > 0 and ry > 0 and rng.random() < 0.7)
+            t.topRight = int(rx < wc - 1 and ry > 0 and rng.random() < 0.7)
+            t.bottomLeft = int(rx > 0 and ry < hc - 1 and rng.random() < 0.7)
+            t.bottomRight = int(rx < wc - 1 and ry < hc - 1 and rng.random() < 0.7)
+            for c in range(3):
+                t.plane[c].typeIdx = int(rng.integers(0, 3))
+                t.plane[c].classOrBand = int(rng.integers(0, 4)) if t.plane[c].typeIdx == 2 else int(rng.integers(0, 32))
+                for k in range(4):
+                    t.plane[c].offset[k] = int(rng.integers(-7, 8)) << (bit_depth - min(bit_depth, 10))
+    return padded, views, blocks, stride, ctus
+
+
+def sao_call(fn, is_ref, dst, src, bps, bit_depth, blocks, stride, ctus, luma_flag, chroma_flag):
+    def origin(a):
+        return a.ctypes.data + (SAO_PAD * a.shape[1] + SAO_PAD) * a.itemsize
+    d = (C.c_void_p * 3)(*[origin(a) for a in dst])
+    s = (C.c_void_p * 3)(*[origin(a) for a in src])
+    strides = (C.c_ssize_t * 3)(*[a.shape[1] for a in src])
+    b = blocks.ctypes.data_as(C.c_void_p)
+    if is_ref:
+        fn(d, s, strides, bps, bit_depth, bit_depth, W, H, CTB_LOG2, b, ctus, luma_flag, chroma_flag)
+    else:
+        fn(d, s, strides, bps, bit_depth, bit_depth, W, H, CTB_LOG2, b, stride, ctus, luma_flag, chroma_flag)
+
+
+@pytest.mark.parametrize("bps,bit_depth", [(1, 8), (2, 10), (2, 9)])
+def test_sao_matches_reference(reflib, oracle, bps, bit_depth):
+    if not hasattr(reflib, "ref_sao"):
+        pytest.skip("libhavoc_ref.so predates ref_sao (make -C oracle ref)")
+    rng = np.random.default_rng(500 + bit_depth)
+    changed = kept = 0
+    for trial in range(10):
+        src, views, blocks, stride, ctus = make_sao_case(rng, bps, bit_depth)
+        flags = (1, 1) if trial < 8 else ((1, 0) if trial == 8 else (0, 1))  # slice_sao_luma_flag, slice_sao_chroma_flag
+        want = [a.copy() for a in src]  # the encoder filters from a copy of the deblocked picture back into it (TaskSao.cpp:96-121)
+        got = [a.copy() for a in src]
+        sao_call(reflib.ref_sao, True, want, src, bps, bit_depth, blocks, stride, ctus, *flags)
+        sao_call(oracle.lib.orc_sao, False, got, src, bps, bit_depth, blocks, stride, ctus, *flags)
+        for c in range(3):
+            assert np.array_equal(got[c][views[c]], want[c][views[c]]), (trial, c)
+            changed += int((want[c][views[c]] != src[c][views[c]]).sum())
+            kept += int((want[c][views[c]] == src[c][views[c]]).sum())
+    assert changed > 20000 and kept > 100000, (changed, kept)
