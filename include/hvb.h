@@ -410,6 +410,39 @@ typedef struct
 } hvb_deblock_task; /* 16 bytes */
 int hvb_deblock_batch(hvb_context *ctx, const hvb_deblock_task *tasks, int n, hvb_mem mem);
 
+/* ---- sample adaptive offset, application (first GPU verification pending) ---- */
+
+/* One CTU's SAO parameters and neighbourhood as LoopFilter::Ctu holds them (turing/LoopFilter.h:92-163, :476-534):
+ * left/top/right/bottom = luma-sample limits of the area whose samples may be read across the CTU's borders (picture
+ * limits, or the CTU's own border where a slice / tile boundary forbids it), the four corner CTUs' availability, and per
+ * component SaoTypeIdx (0 off, 1 band, 2 edge), SaoEoClass or sao_band_position, SaoOffsetVal[1..4] (already scaled
+ * by 1 << (bitDepth - min(bitDepth, 10)), LoopFilter.h:157-160). */
+typedef struct
+{
+    int16_t left, top, right, bottom;
+    uint8_t topLeft, topRight, bottomLeft, bottomRight;
+    struct
+    {
+        int8_t typeIdx, classOrBand;
+        int16_t offset[4];
+    } plane[3];
+} hvb_sao_ctu; /* 42 bytes */
+/* SAO records of every CTU of picture `pic`, raster order (host array).  The disabled-block bits (pcm / transquant bypass,
+ * restoreUnfilteredRegions, turing/LoopFilter.h:849-877) and the CTB geometry are those of hvb_deblock_info_upload, which
+ * must have been called for `pic`. */
+int hvb_sao_info_upload(hvb_context *ctx, int pic, const hvb_sao_ctu *ctus, int n);
+/* LoopFilter::Picture::applySaoCTU (turing/LoopFilter.h:794-811 -> filterBlockSao :885-1017, sao_filter_edge / _band of
+ * turing/sao.cpp) for the CTUs [ctuBegin, ctuEnd) of dst_pic in raster order: SAO of src_pic (a copy of the deblocked
+ * picture, turing/TaskSao.cpp:96-121) into dst_pic, whose side information is used; visible samples only. */
+typedef struct
+{
+    int16_t src_pic, dst_pic;
+    int16_t ctuBegin, ctuEnd;
+    uint8_t lumaFlag, chromaFlag; /* slice_sao_luma_flag, slice_sao_chroma_flag */
+    int16_t reserved;
+} hvb_sao_task; /* 12 bytes */
+int hvb_sao_batch(hvb_context *ctx, const hvb_sao_task *tasks, int n, hvb_mem mem);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,8 +1,10 @@
-"""GPU parity of the deblocking pixel pass (hvb_deblock_batch) against the oracle, which
-tests/test_oracle_pin_loopfilter.py pins against the reference's own LoopFilter templates: whole-picture passes (all
-vertical edges, then all horizontal edges) and the per-CTU regions of TaskDeblock::run as two batches, 8 and 10 bit.
+"""GPU parity of the in-loop filters' pixel passes (hvb_deblock_batch, hvb_sao_batch) against the
+oracle, which tests/test_oracle_pin_loopfilter.py pins against the reference's own LoopFilter templates: deblocking as
+whole-picture passes (all vertical edges, then all horizontal edges) and as the per-CTU regions of TaskDeblock::run in two
+batches; SAO from a copy of the picture into the picture, in two CTU ranges; 8 and 10 bit.
 
-STATUS: this kernel was written after round 1's GPU budget was spent and has not run on a GPU yet.  The file sorts last
+STATUS: these kernels were written after round 1's GPU budget was spent and have not run on a GPU yet; their own source,
+executed on the CPU, is bit-exact against the oracle (tests/test_host_emulated_loopfilter.py).  The file sorts last
 and is marked xfail(strict=False) so that an undiscovered bug cannot mask the verified suite in front of it; the marker
 is to be removed at the first GPU run of round 2 (XPASS in the report means the kernel is bit-exact as written)."""
 import numpy as np
@@ -12,7 +14,7 @@ import test_oracle_pin_loopfilter as pin
 from turingcodec_b200 import hvb
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first GPU run of hvb_deblock_batch (written without GPU access)")]
+              pytest.mark.xfail(strict=False, reason="first GPU run of hvb_deblock_batch / hvb_sao_batch (written without GPU access)")]
 
 
 def upload(ctx, pic, planes):
@@ -63,5 +65,37 @@ def test_deblock_matches_oracle(oracle, bps, bit_depth):
             for c in range(3):
                 got = ctx.picture_download(pic, c, planes[c].shape[1], planes[c].shape[0])
                 assert np.array_equal(got, want[c]), (trial, "regions", c)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("bps,bit_depth", [(1, 8), (2, 10)])
+def test_sao_matches_oracle(oracle, bps, bit_depth):
+    """hvb_sao_batch: SAO of a copy of the deblocked picture into the reconstructed picture, two CTU ranges per picture"""
+    rng = np.random.default_rng(700 + bit_depth)
+    wc, hc = -(-pin.W >> pin.CTB_LOG2), -(-pin.H >> pin.CTB_LOG2)
+    ctx = hvb.Context(0, bps, bit_depth)
+    try:
+        src_pic, dst_pic = ctx.picture_create(pin.W, pin.H, 16), ctx.picture_create(pin.W, pin.H, 16)
+        for trial in range(6):
+            src, views, blocks, stride, ctus = pin.make_sao_case(rng, bps, bit_depth)
+            flags = (1, 1) if trial < 4 else ((1, 0) if trial == 4 else (0, 1))
+            want = [a.copy() for a in src]
+            pin.sao_call(oracle.lib.orc_sao, False, want, src, bps, bit_depth, blocks, stride, ctus, *flags)
+            visible = [np.ascontiguousarray(a[v]) for a, v in zip(src, views)]
+            for pic in (src_pic, dst_pic):
+                upload(ctx, pic, visible)
+                ctx.picture_pad(pic)  # the edge classes read one sample beyond the picture before the undo runs discard the result
+            b, _ = records(blocks, np.zeros((wc * hc, 2), np.int8))
+            ctx.deblock_info_upload(dst_pic, b, np.zeros(wc * hc, hvb.deblock_ctu_t), wc, hc, pin.CTB_LOG2)
+            ctx.sao_info_upload(dst_pic, np.frombuffer(bytes(ctus), dtype=hvb.sao_ctu_t).copy())
+            tasks = np.zeros(2, hvb.sao_task_t)
+            tasks["src_pic"], tasks["dst_pic"] = src_pic, dst_pic
+            tasks["ctuBegin"], tasks["ctuEnd"] = (0, wc), (wc, wc * hc)
+            tasks["lumaFlag"], tasks["chromaFlag"] = flags
+            ctx.sao(tasks)
+            for c in range(3):
+                got = ctx.picture_download(dst_pic, c, visible[c].shape[1], visible[c].shape[0])
+                assert np.array_equal(got, want[c][views[c]]), (trial, c)
     finally:
         ctx.close()

@@ -1,7 +1,7 @@
-"""The device deblocking kernel's own source, executed on the CPU, against the pinned oracle.
+"""The device in-loop-filter kernels' own source (deblocking, SAO application), executed on the CPU, against the pinned oracle.
 
-csrc/hvb_loopfilter.cu's kernel uses no warp-level primitive and walks its jobs in a grid-stride loop, so with a grid of
-ONE thread its body is an ordinary sequential program.  This test cuts the kernel (the anonymous namespace of the .cu
+csrc/hvb_loopfilter.cu's kernels use no warp-level primitive and walk their jobs in grid-stride loops, so with a grid of
+ONE thread their bodies are ordinary sequential programs.  This test cuts the kernels (the anonymous namespace of the .cu
 file, verbatim) out of the source, compiles it with g++ against the CUDA headers' host definitions (blockIdx / gridDim
 become constants of a 1-thread grid) and runs it on host memory: job decomposition, vector load / store packing, the
 decisions and the three filters are then checked bit-for-bit without a GPU.  What it cannot see is device-only behaviour
@@ -23,12 +23,14 @@ CUDA_INC = Path("/usr/local/cuda/include")
 
 PRELUDE = r'''
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include "hvb.h"
 #define __launch_bounds__(...)
-struct HvbPlane { void *base; int32_t stride; int32_t width, height; int32_t pad; int32_t reserved; };
-struct HvbLoopInfo { const hvb_deblock_block *blocks; const hvb_deblock_ctu *ctus; int32_t blockStride, blockRows, widthInCtbs, ctbLog2; };
+using std::max;
+using std::min;
+@STRUCTS@
 static inline int hvbClip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 static const uint3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0};
 static const dim3 blockDim(1), gridDim(1);
@@ -39,6 +41,13 @@ extern "C" void emu_deblock(const HvbPlane *planes, const HvbLoopInfo *info, con
     if (bps == 1) deblockKernel<uint8_t>(planes, info, tasks, n, bitDepth);
     else deblockKernel<uint16_t>(planes, info, tasks, n, bitDepth);
 }
+extern "C" void emu_sao(const HvbPlane *planes, const HvbLoopInfo *info, const hvb_sao_task *tasks, int n, int bitDepth, int bps)
+{
+    if (bps == 1) saoKernel<uint8_t>(planes, info, tasks, n, bitDepth);
+    else saoKernel<uint16_t>(planes, info, tasks, n, bitDepth);
+}
+extern "C" int emu_sizeof_plane() { return sizeof(HvbPlane); }
+extern "C" int emu_sizeof_loop_info() { return sizeof(HvbLoopInfo); }
 '''
 
 
@@ -48,8 +57,14 @@ class Plane(C.Structure):
 
 
 class LoopInfo(C.Structure):
-    _fields_ = [("blocks", C.c_void_p), ("ctus", C.c_void_p), ("blockStride", C.c_int32), ("blockRows", C.c_int32),
-                ("widthInCtbs", C.c_int32), ("ctbLog2", C.c_int32)]
+    _fields_ = [("blocks", C.c_void_p), ("ctus", C.c_void_p), ("sao", C.c_void_p), ("blockStride", C.c_int32), ("blockRows", C.c_int32),
+                ("widthInCtbs", C.c_int32), ("ctbLog2", C.c_int32), ("saoCount", C.c_int32), ("reserved", C.c_int32)]
+
+
+def struct_text(header: str, name: str) -> str:
+    """the definition of `struct name { ... };` as csrc/hvb_internal.cuh has it, so that the emulation cannot drift from it"""
+    start = header.index(f"struct {name}\n{{")
+    return header[start:header.index("};", start) + 2]
 
 
 @pytest.fixture(scope="module")
@@ -59,11 +74,15 @@ def emu(tmp_path_factory):
     src = (ROOT / "turingcodec_b200" / "csrc" / "hvb_loopfilter.cu").read_text()
     kernel = src[src.index("namespace {"):src.index("} // namespace") + len("} // namespace")]
     assert "deblockKernel" in kernel and "__shfl" not in kernel and "__syncthreads" not in kernel
+    internal = (ROOT / "turingcodec_b200" / "csrc" / "hvb_internal.cuh").read_text()
+    structs = struct_text(internal, "HvbPlane") + "\n" + struct_text(internal, "HvbLoopInfo")
     d = tmp_path_factory.mktemp("emu_loopfilter")
-    (d / "emu.cpp").write_text(PRELUDE + kernel + ENTRY)
+    (d / "emu.cpp").write_text(PRELUDE.replace("@STRUCTS@", structs) + kernel + ENTRY)
     subprocess.run(["g++", "-O1", "-fPIC", "-shared", "-w", "-std=c++17", f"-I{CUDA_INC}", f"-I{ROOT / 'include'}", str(d / "emu.cpp"),
                     "-o", str(d / "emu.so")], check=True, capture_output=True)
-    return C.CDLL(str(d / "emu.so"))
+    lib = C.CDLL(str(d / "emu.so"))
+    assert lib.emu_sizeof_plane() == C.sizeof(Plane) and lib.emu_sizeof_loop_info() == C.sizeof(LoopInfo)
+    return lib
 
 
 def run_kernel(emu, planes, bps, bit_depth, blocks, ctu, ctbs, tasks):
@@ -73,7 +92,7 @@ def run_kernel(emu, planes, bps, bit_depth, blocks, ctu, ctbs, tasks):
     b["data"], b["packedBs"] = blocks[..., 0].view(np.int8), blocks[..., 1]
     c = np.zeros(ctu.shape[0], hvb.deblock_ctu_t)
     c["tc_offset_div2"], c["beta_offset_div2"] = ctu[:, 0], ctu[:, 1]
-    info = LoopInfo(b.ctypes.data, c.ctypes.data, b.shape[1], b.shape[0], ctbs[0], pin.CTB_LOG2)
+    info = LoopInfo(b.ctypes.data, c.ctypes.data, None, b.shape[1], b.shape[0], ctbs[0], pin.CTB_LOG2, 0, 0)
     tasks = np.ascontiguousarray(tasks, dtype=hvb.deblock_task_t)
     emu.emu_deblock(table, C.byref(info), C.c_void_p(tasks.ctypes.data), tasks.size, bit_depth, bps)
 
@@ -116,3 +135,43 @@ def test_kernel_source_on_cpu_matches_oracle(emu, oracle, bps, bit_depth):
             run_kernel(emu, regional, bps, bit_depth, blocks, ctu, ctbs, np.concatenate([task(edge, r[edge], offsets) for r in regions]))
         for c in range(3):
             assert np.array_equal(regional[c], want[c]), (trial, "regions", c)
+
+
+def sao_records(ctus):
+    """test_oracle_pin_loopfilter's ctypes records -> hvb.sao_ctu_t (same 42-byte layout)"""
+    out = np.frombuffer(bytes(ctus), dtype=hvb.sao_ctu_t).copy()
+    assert out.size == len(ctus)
+    return out
+
+
+@pytest.mark.parametrize("bps,bit_depth", [(1, 8), (2, 10), (2, 9)])
+def test_sao_kernel_source_on_cpu_matches_oracle(emu, oracle, bps, bit_depth):
+    rng = np.random.default_rng(600 + bit_depth)
+    wc, hc = -(-pin.W >> pin.CTB_LOG2), -(-pin.H >> pin.CTB_LOG2)
+    for trial in range(8):
+        src, views, blocks, stride, ctus = pin.make_sao_case(rng, bps, bit_depth)
+        flags = (1, 1) if trial < 6 else ((1, 0) if trial == 6 else (0, 1))
+        want = [a.copy() for a in src]
+        pin.sao_call(oracle.lib.orc_sao, False, want, src, bps, bit_depth, blocks, stride, ctus, *flags)
+        # pictures 0 (source) and 1 (destination), rows 256-byte aligned, margins as in the padded host copies
+        pad = pin.SAO_PAD
+        host = [aligned_copy(a) for a in src] + [aligned_copy(a) for a in src]
+        table = (Plane * 6)()
+        for i, a in enumerate(host):
+            w, h = a.shape[1] - 2 * pad, a.shape[0] - 2 * pad
+            pitch = a.strides[0] // a.itemsize
+            assert (a.ctypes.data + (pad * pitch + pad) * a.itemsize) % 8 == 0  # hvb pictures: sample (0,0) of a row is 256-byte aligned
+            table[i] = Plane(a.ctypes.data + (pad * pitch + pad) * a.itemsize, pitch, w, h, pad, 0)
+        b = np.zeros(blocks.shape[:2], hvb.deblock_block_t)
+        b["data"], b["packedBs"] = blocks[..., 0].view(np.int8), blocks[..., 1]
+        rec = sao_records(ctus)
+        info = (LoopInfo * 2)()
+        info[1] = LoopInfo(b.ctypes.data, None, rec.ctypes.data, b.shape[1], b.shape[0], wc, pin.CTB_LOG2, rec.size, 0)
+        # two tasks splitting the CTUs, as two TaskSao rows would
+        tasks = np.zeros(2, hvb.sao_task_t)
+        tasks["src_pic"], tasks["dst_pic"] = 0, 1
+        tasks["ctuBegin"], tasks["ctuEnd"] = (0, wc), (wc, wc * hc)
+        tasks["lumaFlag"], tasks["chromaFlag"] = flags
+        emu.emu_sao(table, info, C.c_void_p(tasks.ctypes.data), tasks.size, bit_depth, bps)
+        for c in range(3):
+            assert np.array_equal(host[3 + c][views[c]], want[c][views[c]]), (trial, c)

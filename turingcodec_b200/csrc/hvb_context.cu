@@ -98,6 +98,7 @@ extern "C" void hvb_destroy(hvb_context *ctx)
         for (int c = 0; c < 3; ++c)
             if (p.alloc[c]) cudaFree(p.alloc[c]);
         if (p.lfInfo) cudaFree(p.lfInfo);
+        if (p.saoInfo) cudaFree(p.saoInfo);
     }
     if (ctx->dPlanes) cudaFree(ctx->dPlanes);
     if (ctx->dLoopInfo) cudaFree(ctx->dLoopInfo);
@@ -247,12 +248,13 @@ extern "C" int hvb_picture_destroy(hvb_context *ctx, int pic)
         cudaFree(p.alloc[c]);
         p.alloc[c] = nullptr;
     }
-    if (p.lfInfo)
+    if (p.lfInfo || p.saoInfo)
     {
         // the device table entry goes with it: a later hvb_deblock_batch on a recycled id must find no stale pointers
-        cudaFree(p.lfInfo);
-        p.lfInfo = nullptr;
-        p.lfBytes = 0;
+        if (p.lfInfo) cudaFree(p.lfInfo);
+        if (p.saoInfo) cudaFree(p.saoInfo);
+        p.lfInfo = p.saoInfo = nullptr;
+        p.lfBytes = p.saoBytes = 0;
         ctx->loopInfoHost[pic] = HvbLoopInfo{};
         if (ctx->dLoopInfo) cudaMemset(ctx->dLoopInfo + pic, 0, sizeof(HvbLoopInfo));
     }

@@ -33,6 +33,8 @@ struct HvbPicture
     HvbPlane plane[3];
     void *lfInfo = nullptr; // deblocking side information (hvb_deblock_info_upload): block records, then CTU records
     size_t lfBytes = 0;
+    void *saoInfo = nullptr; // SAO records per CTU (hvb_sao_info_upload)
+    size_t saoBytes = 0;
 };
 
 // device-side view of a picture's deblocking side information (hvb_loopfilter.cu)
@@ -40,7 +42,8 @@ struct HvbLoopInfo
 {
     const hvb_deblock_block *blocks;
     const hvb_deblock_ctu *ctus;
-    int32_t blockStride, blockRows, widthInCtbs, ctbLog2;
+    const hvb_sao_ctu *sao;
+    int32_t blockStride, blockRows, widthInCtbs, ctbLog2, saoCount, reserved;
 };
 
 struct hvb_context

@@ -1,4 +1,4 @@
-// hvb_loopfilter.cu -- the pixel pass of the in-loop deblocking filter on device-resident reconstructed pictures
+// hvb_loopfilter.cu -- the pixel passes of the in-loop filters (deblocking, SAO application) on device-resident reconstructed pictures
 // (the first row "next" after the hot path; it gates reference-picture availability,
 // turing/TaskEncodeSubstream.cpp:81,91, so keeping it on the device removes the per-CTU reconstruction round trip).
 //
@@ -8,6 +8,7 @@
 //   ChromaBlockEdge                          turing/LoopFilter.h:359-423  (H.265 8.7.2.5.5, .8)
 //   LoopFilter::Block / Ctu                  turing/LoopFilter.h:50-163
 //   per-CTU regions                          turing/TaskDeblock.cpp:104-127
+//   filterBlockSao, restoreUnfilteredRegions turing/LoopFilter.h:849-1017 (SAO; sao_filter_edge / _band: turing/sao.cpp:35-92)
 //
 // Mapping.  Edges of one type never share samples (they lie 8 apart and a filter reads 4 and writes 3 samples each side),
 // so an edge SEGMENT -- four lines across one 8x8 block boundary -- is a thread's unit of work, with all of its samples
@@ -16,6 +17,11 @@
 // four columns (one 32-bit word per row each).  Chroma segments (4:2:0: every second luma block edge, strength 2 only) are
 // further jobs of the same launch.  The side information (LoopFilter::Block per 8x8 block, the slice's tc / beta offsets
 // per CTU) is uploaded per picture; tasks are regions, exactly the arguments of Picture::deblock.
+//
+// SAO: a thread per four horizontally adjacent samples of a component.  The reference filters a whole CTU, copies the
+// disabled 8x8 blocks back and then undoes runs of samples on the CTU's top row / left column / last column / last row
+// according to which neighbouring CTUs are available; here that procedure is evaluated per sample (type off, block
+// disabled or sample in an undo run: the deblocked value is kept), so a sample is read and written once.
 //
 // Status: written after the round's GPU budget was spent; parity is established on the CPU side only (oracle pinned
 // against the reference templates, tests/test_oracle_pin_loopfilter.py); tests/test_gpu_zz_loopfilter.py is the device
@@ -260,6 +266,115 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// the undo runs of an edge-offset CTU (turing/LoopFilter.h:917-992): counts from the start of the top row / left column and
+// from the end of the last column / last row, and where those last ones lie
+struct SaoUndo
+{
+    int T, L, R, B, right, bottom;
+    __device__ __forceinline__ SaoUndo(const hvb_sao_ctu &ctu, int eo, int sh, int x0, int y0, int n) : T(0), L(0), R(0), B(0)
+    {
+        right = ctu.right >> sh;
+        bottom = ctu.bottom >> sh;
+        const bool availL = (ctu.left >> sh) < x0, availR = right > x0 + n, availT = (ctu.top >> sh) < y0, availB = bottom > y0 + n;
+        if (eo == 2)
+        {
+            if (!ctu.topLeft) ++T, ++L;
+            if (!ctu.bottomRight) ++R, ++B;
+        }
+        if (eo != 1)
+        {
+            if (!availL) L = n;
+            if (!availR) R = n;
+        }
+        if (eo != 0)
+        {
+            if (!availT) T = n;
+            if (!availB) B = n;
+        }
+        if (eo == 3)
+        {
+            if (ctu.topRight) --T, --R;
+            if (ctu.bottomLeft) --L, --B;
+        }
+        right = min(right, x0 + n);
+        bottom = min(bottom, y0 + n);
+    }
+    __device__ __forceinline__ bool undone(int x, int y, int lx, int ly, int n) const
+    {
+        return (ly == 0 && lx < T) || (lx == 0 && ly < L) || (x == right - 1 && ly >= n - R) || (y == bottom - 1 && lx >= n - B);
+    }
+};
+
+template <typename Sample>
+__global__ void __launch_bounds__(256)
+    saoKernel(const HvbPlane *__restrict__ planes, const HvbLoopInfo *__restrict__ info, const hvb_sao_task *__restrict__ tasks, int nTasks,
+              int bitDepth)
+{
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    const int maxv = (1 << bitDepth) - 1;
+    for (int ti = 0; ti < nTasks; ++ti)
+    {
+        const hvb_sao_task t = tasks[ti];
+        const HvbLoopInfo li = info[t.dst_pic];
+        const int first = max((int)t.ctuBegin, 0), ctus = min((int)t.ctuEnd, li.saoCount) - first;
+        if (ctus <= 0 || !li.sao || !li.blocks) continue;
+        for (int c = 0; c < 3; ++c)
+        {
+            if (!(c ? t.chromaFlag : t.lumaFlag)) continue;
+            const int sh = c ? 1 : 0, n = (1 << li.ctbLog2) >> sh, quads = n >> 2, perCtu = n * quads;
+            const HvbPlane &sp = planes[t.src_pic * 3 + c], &dp = planes[t.dst_pic * 3 + c];
+            const Sample *src = reinterpret_cast<const Sample *>(sp.base);
+            Sample *dst = reinterpret_cast<Sample *>(dp.base);
+            const int w = dp.width, h = dp.height; // of this component
+            for (int job = gtid; job < ctus * perCtu; job += gthreads)
+            {
+                const int ci = job / perCtu, r = job - ci * perCtu, ly = r / quads, lx = (r - ly * quads) << 2;
+                const int addr = first + ci, ry = addr / li.widthInCtbs, rx = addr - ry * li.widthInCtbs;
+                const int x0 = rx * n, y0 = ry * n, x = x0 + lx, y = y0 + ly;
+                if (x >= w || y >= h) continue;
+                const hvb_sao_ctu &ctu = li.sao[addr];
+                const int type = ctu.plane[c].typeIdx, eo = ctu.plane[c].classOrBand;
+                int v[4];
+                load4(src + (intptr_t)y * sp.stride + x, v);
+                const bool enabled = !(li.blocks[(intptr_t)((y << sh) >> 3) * li.blockStride + ((x << sh) >> 3)].data & 1);
+                if (type == 1 && enabled)
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                    {
+                        const int k = ((v[j] >> (bitDepth - 5)) - eo) & 31; // band index relative to sao_band_position
+                        if (k < 4) v[j] = hvbClip3(0, maxv, v[j] + ctu.plane[c].offset[k]);
+                    }
+                }
+                else if (type == 2 && enabled)
+                {
+                    const SaoUndo undo(ctu, eo, sh, x0, y0, n);
+                    const int hOff = eo == 1 ? 0 : (eo == 3 ? 1 : -1), vOff = eo == 0 ? 0 : -1;
+                    const intptr_t step = (intptr_t)vOff * sp.stride + hOff;
+                    const Sample *at = src + (intptr_t)y * sp.stride + x;
+                    int out[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                    {
+                        out[j] = v[j];
+                        if (x + j < w && !undo.undone(x + j, y, lx + j, ly, n))
+                        {
+                            const int a = at[j + step], b = at[j - step];
+                            const int idx = 2 + (v[j] > a) - (v[j] < a) + (v[j] > b) - (v[j] < b);
+                            // edgeIdx 0,1,2 -> 1,2,0 (H.265 8.7.3.2); category 0 (flat) gets no offset
+                            const int category = idx == 2 ? 0 : (idx < 2 ? idx + 1 : idx);
+                            if (category) out[j] = hvbClip3(0, maxv, v[j] + ctu.plane[c].offset[category - 1]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = out[j];
+                }
+                store4(dst + (intptr_t)y * dp.stride + x, v);
+            }
+        }
+    }
+}
+
 } // namespace
 
 extern "C" int hvb_deblock_info_upload(hvb_context *ctx, int pic, const hvb_deblock_block *blocks, int blockStride, int blockRows,
@@ -293,18 +408,63 @@ extern "C" int hvb_deblock_info_upload(hvb_context *ctx, int pic, const hvb_debl
     if (rc) return rc;
     rc = hvbUpload(ctx, dCtus, ctuBytes, ctus, ctuBytes, ctuBytes, 1, "deblock ctus");
     if (rc) return rc;
-    HvbLoopInfo li;
+    HvbLoopInfo &li = ctx->loopInfoHost[pic]; // the host mirror outlives the call; the SAO fields stay as they are
     li.blocks = reinterpret_cast<const hvb_deblock_block *>(dBlocks);
     li.ctus = reinterpret_cast<const hvb_deblock_ctu *>(dCtus);
     li.blockStride = blockStride;
     li.blockRows = blockRows;
     li.widthInCtbs = picWidthInCtbs;
     li.ctbLog2 = ctbLog2;
-    // a 32-byte kernel-argument-sized record: copied from a context-owned staging copy that outlives the call
-    ctx->loopInfoHost[pic] = li;
-    e = cudaMemcpyAsync(ctx->dLoopInfo + pic, &ctx->loopInfoHost[pic], sizeof(li), cudaMemcpyHostToDevice, ctx->stream);
+    e = cudaMemcpyAsync(ctx->dLoopInfo + pic, &li, sizeof(li), cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) return hvbCuda(ctx, e, "loop-filter table entry");
     return HVB_OK;
+}
+
+extern "C" int hvb_sao_info_upload(hvb_context *ctx, int pic, const hvb_sao_ctu *ctus, int n)
+{
+    HVB_CHECK_ARGS(ctx, pic >= 0 && pic < HVB_MAX_PICTURES && ctx->pictures[pic].live && ctus && n > 0);
+    if (!ctx->dLoopInfo || !ctx->loopInfoHost[pic].blocks)
+        return hvbFail(ctx, HVB_ERR_INVALID, "hvb_sao_info_upload before hvb_deblock_info_upload (block records and CTB geometry)");
+    cudaSetDevice(ctx->device);
+    HvbPicture &p = ctx->pictures[pic];
+    const size_t bytes = sizeof(hvb_sao_ctu) * (size_t)n;
+    if (p.saoBytes < bytes)
+    {
+        cudaStreamSynchronize(ctx->stream);
+        if (p.saoInfo) cudaFree(p.saoInfo);
+        p.saoInfo = nullptr;
+        p.saoBytes = 0;
+        cudaError_t e = cudaMalloc(&p.saoInfo, bytes);
+        if (e != cudaSuccess) return hvbCuda(ctx, e, "SAO records");
+        p.saoBytes = bytes;
+    }
+    int rc = hvbUpload(ctx, p.saoInfo, bytes, ctus, bytes, bytes, 1, "SAO records");
+    if (rc) return rc;
+    HvbLoopInfo &li = ctx->loopInfoHost[pic];
+    li.sao = static_cast<const hvb_sao_ctu *>(p.saoInfo);
+    li.saoCount = n;
+    cudaError_t e = cudaMemcpyAsync(ctx->dLoopInfo + pic, &li, sizeof(li), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return hvbCuda(ctx, e, "loop-filter table entry");
+    return HVB_OK;
+}
+
+extern "C" int hvb_sao_batch(hvb_context *ctx, const hvb_sao_task *tasks, int n, hvb_mem mem)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || tasks));
+    if (!n) return HVB_OK;
+    if (!ctx->dLoopInfo) return hvbFail(ctx, HVB_ERR_INVALID, "hvb_sao_batch before hvb_sao_info_upload");
+    cudaSetDevice(ctx->device);
+    HvbStaged st;
+    int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, nullptr, 0, mem, &st);
+    if (rc) return rc;
+    const auto *dT = static_cast<const hvb_sao_task *>(st.dTasks);
+    const int blocks = ctx->smCount * 8;
+    if (ctx->bps == 1)
+        saoKernel<uint8_t><<<blocks, 256, 0, ctx->stream>>>(ctx->dPlanes, ctx->dLoopInfo, dT, n, ctx->bitDepth);
+    else
+        saoKernel<uint16_t><<<blocks, 256, 0, ctx->stream>>>(ctx->dPlanes, ctx->dLoopInfo, dT, n, ctx->bitDepth);
+    HVB_LAUNCH_CHECK(ctx, "saoKernel");
+    return hvbStageOut(ctx, nullptr, 0, mem, st);
 }
 
 extern "C" int hvb_deblock_batch(hvb_context *ctx, const hvb_deblock_task *tasks, int n, hvb_mem mem)

@@ -62,6 +62,11 @@ deblock_block_t = np.dtype([("data", "i1"), ("packedBs", "u1")], align=True)
 deblock_ctu_t = np.dtype([("tc_offset_div2", "i1"), ("beta_offset_div2", "i1")], align=True)
 deblock_task_t = np.dtype([("pic", "<i2"), ("edgeType", "<i2"), ("xBegin", "<i2"), ("yBegin", "<i2"), ("xEnd", "<i2"),
                            ("yEnd", "<i2"), ("cbQpOffset", "<i2"), ("crQpOffset", "<i2")], align=True)
+sao_ctu_t = np.dtype([("left", "<i2"), ("top", "<i2"), ("right", "<i2"), ("bottom", "<i2"), ("topLeft", "u1"), ("topRight", "u1"),
+                      ("bottomLeft", "u1"), ("bottomRight", "u1"),
+                      ("plane", np.dtype([("typeIdx", "i1"), ("classOrBand", "i1"), ("offset", "<i2", 4)], align=True), 3)], align=True)
+sao_task_t = np.dtype([("src_pic", "<i2"), ("dst_pic", "<i2"), ("ctuBegin", "<i2"), ("ctuEnd", "<i2"), ("lumaFlag", "u1"),
+                       ("chromaFlag", "u1"), ("reserved", "<i2")], align=True)
 me_bi_task_t = np.dtype([("src_pic", "<i2"), ("ref_pic", "<i2"), ("x0", "<i2"), ("y0", "<i2"), ("w", "<i2"),
                          ("h", "<i2"), ("mvp", mv_t, 2), ("other_pic", "<i2"), ("reserved0", "<i2"),
                          ("rateMvpFlag", "<i8", 2), ("lambda", "<i4"), ("limitMin", mv_t), ("limitMax", mv_t),
@@ -131,8 +136,10 @@ def load_library() -> C.CDLL:
             getattr(lib, name).argtypes = [vp, vp, i32, vp, i32]
     if hasattr(lib, "hvb_deblock_info_upload"):
         lib.hvb_deblock_info_upload.argtypes = [vp, i32, vp, i32, i32, vp, i32, i32, i32]
+        lib.hvb_sao_info_upload.argtypes = [vp, i32, vp, i32]
     for name in ("hvb_pred_batch", "hvb_subtract_bi_batch", "hvb_intra_pred_batch", "hvb_transform_fwd_batch",
-                 "hvb_transform_inv_batch", "hvb_quantize_inverse_batch", "hvb_inverse_transform_add_batch", "hvb_deblock_batch"):
+                 "hvb_transform_inv_batch", "hvb_quantize_inverse_batch", "hvb_inverse_transform_add_batch", "hvb_deblock_batch",
+                 "hvb_sao_batch"):
         if hasattr(lib, name):
             getattr(lib, name).argtypes = [vp, vp, i32, i32]
     _lib = lib
@@ -332,6 +339,13 @@ class Context:
 
     def deblock(self, tasks, n=None, mem=HOST):
         self._no_out("hvb_deblock_batch", tasks, n, mem)
+
+    def sao_info_upload(self, pic: int, ctus: np.ndarray):
+        ctus = np.ascontiguousarray(ctus, dtype=sao_ctu_t)
+        self._check(self.lib.hvb_sao_info_upload(self.h, pic, _as_ptr(ctus), ctus.size), "hvb_sao_info_upload")
+
+    def sao(self, tasks, n=None, mem=HOST):
+        self._no_out("hvb_sao_batch", tasks, n, mem)
 
     def me_bi_search(self, tasks, n=None, out=None, mem=HOST):
         return self._with_out("hvb_me_bi_search_batch", tasks, n, out, me_bi_result_t, lambda k: (k,), mem)
