@@ -262,6 +262,11 @@ typedef struct
 void orc_sao(void *const dst[3], void *const src[3], const intptr_t strides[3], int bps, int bitDepthY, int bitDepthC, int picWidth,
              int picHeight, int ctbLog2, const uint8_t *blocks, int blockStride, const orc_sao_ctu *ctus, int lumaFlag, int chromaFlag);
 
+/* turing/EncSao.h:111-284: SAO statistics of the interior of a w x h block (the four edge classes' per-category counts and
+ * sums of original - reconstructed, the same per band); out = [class][E[5], count[5]], band E[32], band count[32]; returns
+ * startBand.  Pinned: tests/test_oracle_pin_loopfilter.py. */
+int orc_sao_stats(const void *org, intptr_t strideOrg, const void *rec, intptr_t strideRec, int w, int h, int shift, int bps, int64_t out[104]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -262,3 +262,44 @@ void orc_sao(void *const dst[3], void *const src[3], const intptr_t strides[3], 
             }
     }
 }
+
+/* ---- sample adaptive offset, encoder-side statistics ---------------------------------------------------------------------
+ *   EncSao::edge_offset_stats_class0..3     turing/EncSao.h:151-284
+ *   EncSao::band_offset_luma_stats          turing/EncSao.h:111-149 (the chroma variant :62-109 is this one on U and on V, added)
+ * For the interior of a block (the CTU clipped to the picture, first and last row and column left out) and each of the
+ * four edge classes: per category the number of samples and the sum of (original - reconstructed); the same per band of
+ * the reconstructed sample.  One pass over the block computes all five.  The reference's class-0 loop visits x = 1 of
+ * every row twice, the second time with signA = -signB, i.e. as category 0 (EncSao.h:167-181): reproduced.
+ * out: [class][E[5], count[5]] (40 values), band E[32], band count[32].  Returns startBand (:137-148). */
+int orc_sao_stats(const void *org, intptr_t strideOrg, const void *rec, intptr_t strideRec, int w, int h, int shift, int bps, int64_t out[104])
+{
+    static const int8_t hOff[4] = {-1, 0, -1, 1}, vOff[4] = {0, -1, -1, -1}, category[5] = {1, 2, 0, 3, 4};
+    const plane_t o = {(uint8_t *)org, strideOrg, bps}, r = {(uint8_t *)rec, strideRec, bps};
+    for (int i = 0; i < 104; ++i) out[i] = 0;
+    for (int y = 1; y < h - 1; ++y)
+        for (int x = 1; x < w - 1; ++x)
+        {
+            const intptr_t at = (intptr_t)y * strideRec + x;
+            const int v = get(&r, at), diff = get(&o, (intptr_t)y * strideOrg + x) - v;
+            for (int c = 0; c < 4; ++c)
+            {
+                const intptr_t step = (intptr_t)vOff[c] * strideRec + hOff[c];
+                const int cat = category[2 + sao_sign(v - get(&r, at + step)) + sao_sign(v - get(&r, at - step))];
+                out[c * 10 + cat] += diff;
+                out[c * 10 + 5 + cat] += 1;
+            }
+            if (x == 1) out[0] += diff, out[5] += 1; /* the class-0 double visit */
+            const int band = v >> (3 + shift);
+            out[40 + band] += diff;
+            out[72 + band] += 1;
+        }
+    /* the densest run of four bands; first maximum wins */
+    int start = 0;
+    int64_t best = 0;
+    for (int b = 0; b < 29; ++b)
+    {
+        const int64_t run = out[72 + b] + out[73 + b] + out[74 + b] + out[75 + b];
+        if (run > best) best = run, start = b;
+    }
+    return start + 1 < 2 ? 2 : start + 1;
+}

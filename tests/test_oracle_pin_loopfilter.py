@@ -211,3 +211,36 @@ def test_sao_matches_reference(reflib, oracle, bps, bit_depth):
             changed += int((want[c][views[c]] != src[c][views[c]]).sum())
             kept += int((want[c][views[c]] == src[c][views[c]]).sum())
     assert changed > 20000 and kept > 100000, (changed, kept)
+
+
+# ---- SAO statistics (encoder side) ---------------------------------------------------------------------------------------
+
+def stats_case(rng, bps, bit_depth, w, h):
+    """original and reconstructed block (reconstruction = original + coding noise), each inside a larger array"""
+    dtype = np.uint8 if bps == 1 else np.uint16
+    top = (1 << bit_depth) - 1
+    yy, xx = np.mgrid[0:h + 4, 0:w + 4]
+    org = np.clip(top / 2 + top / 3 * np.sin(xx / 5.0 + rng.random() * 6) * np.cos(yy / 4.0) + rng.integers(-4, 5, xx.shape) * (1 << (bit_depth - 8)), 0, top)
+    rec = np.clip(org + rng.integers(-6, 7, xx.shape) * (1 << (bit_depth - 8)), 0, top)
+    rec[rng.random(rec.shape) < 0.3] = rec[0, 0]  # flat runs: category 0 and ties occur
+    return org.astype(dtype), rec.astype(dtype)
+
+
+@pytest.mark.parametrize("bps,bit_depth", [(1, 8), (2, 10), (2, 9)])
+def test_sao_statistics_match_reference(reflib, oracle, bps, bit_depth):
+    if not hasattr(reflib, "ref_sao_stats"):
+        pytest.skip("libhavoc_ref.so predates ref_shim_saostats.cpp (make -C oracle ref)")
+    rng = np.random.default_rng(800 + bit_depth)
+    for lib_fn in (reflib.ref_sao_stats, oracle.lib.orc_sao_stats):
+        lib_fn.argtypes = [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    seen = np.zeros(104, np.int64)
+    for w, h in [(64, 64), (32, 32), (48, 64), (64, 16), (24, 8), (8, 8), (16, 40)] * 3:
+        org, rec = stats_case(rng, bps, bit_depth, w, h)
+        want, got = np.zeros(104, np.int64), np.zeros(104, np.int64)
+        at = lambda a: a.ctypes.data + (2 * a.shape[1] + 2) * a.itemsize  # noqa: E731  (the block starts at (2, 2))
+        start_ref = reflib.ref_sao_stats(at(org), org.shape[1], at(rec), rec.shape[1], w, h, bit_depth - 8, bps, want.ctypes.data)
+        start = oracle.lib.orc_sao_stats(at(org), org.shape[1], at(rec), rec.shape[1], w, h, bit_depth - 8, bps, got.ctypes.data)
+        assert np.array_equal(got, want), (w, h, np.nonzero(got != want)[0])
+        assert start == start_ref
+        seen += want != 0
+    assert (seen[:40].reshape(4, 2, 5)[:, 1] > 0).all()  # every category of every class was populated
