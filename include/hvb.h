@@ -443,6 +443,30 @@ typedef struct
 } hvb_sao_task; /* 12 bytes */
 int hvb_sao_batch(hvb_context *ctx, const hvb_sao_task *tasks, int n, hvb_mem mem);
 
+/* ---- SAO statistics, encoder side (first GPU verification pending) ---- */
+
+/* EncSao::edge_offset_stats_class0..3 and band_offset_luma_stats (turing/EncSao.h:111-284) over one block of one
+ * component -- the CTU clipped to the picture, as saoRdEstimateLuma / saoRdEstimateChroma cut it (:290-297, :535-539);
+ * the block's first and last row and column are left out, as there.  org_pic: the source picture, rec_pic: the
+ * reconstruction the statistics are taken on (deblocked, or not, by --sao-slow: :303-305). */
+typedef struct
+{
+    int16_t org_pic, rec_pic;
+    int16_t cIdx;
+    int16_t x0, y0, w, h; /* in samples of that component */
+    int16_t reserved;
+} hvb_sao_stats_task; /* 16 bytes */
+/* per edge class and category: sum of (original - reconstructed) and number of samples (category 0 of class 0 also
+ * carries the reference's second visit of column 1, EncSao.h:167-181); the same per band of 8 << (bitDepth - 8) levels.
+ * The chroma band statistics of the reference (:62-109) are the U and V results added; startBand (:137-148) and the
+ * offset / type decisions (:328-526) stay with the caller. */
+typedef struct
+{
+    int32_t edgeE[4][5], edgeCount[4][5];
+    int32_t bandE[32], bandCount[32];
+} hvb_sao_stats; /* 416 bytes */
+int hvb_sao_stats_batch(hvb_context *ctx, const hvb_sao_stats_task *tasks, int n, hvb_sao_stats *out, hvb_mem mem);
+
 #ifdef __cplusplus
 }
 #endif

@@ -99,3 +99,39 @@ def test_sao_matches_oracle(oracle, bps, bit_depth):
                 assert np.array_equal(got, want[c][views[c]]), (trial, c)
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("bps,bit_depth", [(1, 8), (2, 10)])
+def test_sao_statistics_match_oracle(oracle, bps, bit_depth):
+    """hvb_sao_stats_batch over every CTU and component of a picture against the oracle (pinned against EncSao's own functions)"""
+    import ctypes as C
+    rng = np.random.default_rng(1000 + bit_depth)
+    oracle.lib.orc_sao_stats.argtypes = [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    ctx = hvb.Context(0, bps, bit_depth)
+    try:
+        org_pic, rec_pic = ctx.picture_create(pin.W, pin.H, 16), ctx.picture_create(pin.W, pin.H, 16)
+        org3, rec3 = [], []
+        for c in range(3):
+            w, h = (pin.W, pin.H) if c == 0 else (pin.W // 2, pin.H // 2)
+            o, r = pin.stats_case(rng, bps, bit_depth, w - 4, h - 4)
+            org3.append(np.ascontiguousarray(o))
+            rec3.append(np.ascontiguousarray(r))
+        upload(ctx, org_pic, org3)
+        upload(ctx, rec_pic, rec3)
+        tasks, n = [], 1 << pin.CTB_LOG2
+        for c in range(3):
+            nc, w, h = (n, pin.W, pin.H) if c == 0 else (n // 2, pin.W // 2, pin.H // 2)
+            for y0 in range(0, h, nc):
+                for x0 in range(0, w, nc):
+                    tasks.append((org_pic, rec_pic, c, x0, y0, min(nc, w - x0), min(nc, h - y0), 0))
+        t = np.array(tasks, dtype=hvb.sao_stats_task_t)
+        out = ctx.sao_stats(t)
+        for i, task in enumerate(t):
+            o, r = org3[task["cIdx"]], rec3[task["cIdx"]]
+            want = np.zeros(104, np.int64)
+            at = lambda a: a.ctypes.data + (int(task["y0"]) * a.shape[1] + int(task["x0"])) * a.itemsize  # noqa: E731
+            oracle.lib.orc_sao_stats(at(o), o.shape[1], at(r), r.shape[1], int(task["w"]), int(task["h"]), bit_depth - 8, bps, want.ctypes.data)
+            got = np.concatenate([np.stack([out[i]["edgeE"], out[i]["edgeCount"]], axis=1).reshape(-1), out[i]["bandE"], out[i]["bandCount"]])
+            assert np.array_equal(got, want), (i, tuple(task))
+    finally:
+        ctx.close()

@@ -1,7 +1,8 @@
 """The device in-loop-filter kernels' own source (deblocking, SAO application), executed on the CPU, against the pinned oracle.
 
-csrc/hvb_loopfilter.cu's kernels use no warp-level primitive and walk their jobs in grid-stride loops, so with a grid of
-ONE thread their bodies are ordinary sequential programs.  This test cuts the kernels (the anonymous namespace of the .cu
+csrc/hvb_loopfilter.cu's kernels use no warp-level primitive and walk their jobs in grid-stride (or block-stride) loops, so
+with a grid of ONE thread their bodies are ordinary sequential programs (the statistics kernel's shared-memory atomics and
+block barriers degenerate to plain additions and no-ops).  This test cuts the kernels (the anonymous namespace of the .cu
 file, verbatim) out of the source, compiles it with g++ against the CUDA headers' host definitions (blockIdx / gridDim
 become constants of a 1-thread grid) and runs it on host memory: job decomposition, vector load / store packing, the
 decisions and the three filters are then checked bit-for-bit without a GPU.  What it cannot see is device-only behaviour
@@ -32,6 +33,8 @@ using std::max;
 using std::min;
 @STRUCTS@
 static inline int hvbClip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+static inline void __syncthreads() {}
+static inline int atomicAdd(int *p, int v) { const int old = *p; *p += v; return old; }
 static const uint3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0};
 static const dim3 blockDim(1), gridDim(1);
 '''
@@ -45,6 +48,11 @@ extern "C" void emu_sao(const HvbPlane *planes, const HvbLoopInfo *info, const h
 {
     if (bps == 1) saoKernel<uint8_t>(planes, info, tasks, n, bitDepth);
     else saoKernel<uint16_t>(planes, info, tasks, n, bitDepth);
+}
+extern "C" void emu_sao_stats(const HvbPlane *planes, const hvb_sao_stats_task *tasks, int n, hvb_sao_stats *out, int bitDepth, int bps)
+{
+    if (bps == 1) saoStatsKernel<uint8_t>(planes, tasks, n, out, bitDepth);
+    else saoStatsKernel<uint16_t>(planes, tasks, n, out, bitDepth);
 }
 extern "C" int emu_sizeof_plane() { return sizeof(HvbPlane); }
 extern "C" int emu_sizeof_loop_info() { return sizeof(HvbLoopInfo); }
@@ -73,7 +81,7 @@ def emu(tmp_path_factory):
         pytest.skip("CUDA headers not found")
     src = (ROOT / "turingcodec_b200" / "csrc" / "hvb_loopfilter.cu").read_text()
     kernel = src[src.index("namespace {"):src.index("} // namespace") + len("} // namespace")]
-    assert "deblockKernel" in kernel and "__shfl" not in kernel and "__syncthreads" not in kernel
+    assert "deblockKernel" in kernel and "__shfl" not in kernel and "__syncwarp" not in kernel
     internal = (ROOT / "turingcodec_b200" / "csrc" / "hvb_internal.cuh").read_text()
     structs = struct_text(internal, "HvbPlane") + "\n" + struct_text(internal, "HvbLoopInfo")
     d = tmp_path_factory.mktemp("emu_loopfilter")
@@ -175,3 +183,35 @@ def test_sao_kernel_source_on_cpu_matches_oracle(emu, oracle, bps, bit_depth):
         emu.emu_sao(table, info, C.c_void_p(tasks.ctypes.data), tasks.size, bit_depth, bps)
         for c in range(3):
             assert np.array_equal(host[3 + c][views[c]], want[c][views[c]]), (trial, c)
+
+
+@pytest.mark.parametrize("bps,bit_depth", [(1, 8), (2, 10), (2, 9)])
+def test_sao_statistics_kernel_source_on_cpu_matches_oracle(emu, oracle, bps, bit_depth):
+    """every CTU of a picture, three components: the statistics kernel's sums against the oracle's (and thereby EncSao's)"""
+    rng = np.random.default_rng(900 + bit_depth)
+    oracle.lib.orc_sao_stats.argtypes = [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    org3, rec3 = [], []
+    for c in range(3):
+        w, h = (pin.W, pin.H) if c == 0 else (pin.W // 2, pin.H // 2)
+        o, r = pin.stats_case(rng, bps, bit_depth, w - 4, h - 4)  # stats_case adds a margin of 2: exactly w x h
+        org3.append(aligned_copy(o))
+        rec3.append(aligned_copy(r))
+    table = (Plane * 6)(*[Plane(a.ctypes.data, a.strides[0] // a.itemsize, a.shape[1], a.shape[0], 0, 0) for a in org3 + rec3])
+    tasks = []
+    n = 1 << pin.CTB_LOG2
+    for c in range(3):
+        nc, w, h = (n, pin.W, pin.H) if c == 0 else (n // 2, pin.W // 2, pin.H // 2)
+        for y0 in range(0, h, nc):
+            for x0 in range(0, w, nc):
+                tasks.append((0, 1, c, x0, y0, min(nc, w - x0), min(nc, h - y0), 0))
+    t = np.array(tasks, dtype=hvb.sao_stats_task_t)
+    out = np.zeros(t.size, hvb.sao_stats_t)
+    emu.emu_sao_stats(table, C.c_void_p(t.ctypes.data), t.size, C.c_void_p(out.ctypes.data), bit_depth, bps)
+    for i, task in enumerate(t):
+        o, r = org3[task["cIdx"]], rec3[task["cIdx"]]
+        want = np.zeros(104, np.int64)
+        at = lambda a: a.ctypes.data + (int(task["y0"]) * (a.strides[0] // a.itemsize) + int(task["x0"])) * a.itemsize  # noqa: E731
+        oracle.lib.orc_sao_stats(at(o), o.strides[0] // o.itemsize, at(r), r.strides[0] // r.itemsize, int(task["w"]), int(task["h"]),
+                                 bit_depth - 8, bps, want.ctypes.data)
+        got = np.concatenate([np.stack([out[i]["edgeE"], out[i]["edgeCount"]], axis=1).reshape(-1), out[i]["bandE"], out[i]["bandCount"]])
+        assert np.array_equal(got, want), (i, tuple(task))

@@ -23,6 +23,11 @@
 // according to which neighbouring CTUs are available; here that procedure is evaluated per sample (type off, block
 // disabled or sample in an undo run: the deblocked value is kept), so a sample is read and written once.
 //
+// SAO statistics (the encoder's side: EncSao.h:111-284): a thread block per (block, component) task; every thread takes
+// interior samples of the block in a block-stride loop, classifies each once for the four edge classes and its band, and
+// adds (original - reconstructed) and 1 to shared-memory accumulators (integer atomics: the sums are order-independent,
+// hence bit-exact); 104 sums per task go out.  One read of each picture instead of the reference's five passes.
+//
 // Status: written after the round's GPU budget was spent; parity is established on the CPU side only (oracle pinned
 // against the reference templates, tests/test_oracle_pin_loopfilter.py); tests/test_gpu_zz_loopfilter.py is the device
 // parity test and has not yet run on a GPU.
@@ -375,6 +380,55 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ---- SAO statistics: one thread block per task -------------------------------------------------------------------------
+template <typename Sample>
+__global__ void __launch_bounds__(256)
+    saoStatsKernel(const HvbPlane *__restrict__ planes, const hvb_sao_stats_task *__restrict__ tasks, int n, hvb_sao_stats *__restrict__ out,
+                   int bitDepth)
+{
+    __shared__ int acc[104]; // hvb_sao_stats as a flat array: edgeE[4][5], edgeCount[4][5], bandE[32], bandCount[32]
+    for (int ti = blockIdx.x; ti < n; ti += gridDim.x)
+    {
+        const hvb_sao_stats_task t = tasks[ti];
+        for (int i = threadIdx.x; i < 104; i += blockDim.x) acc[i] = 0;
+        __syncthreads();
+        const HvbPlane &op = planes[t.org_pic * 3 + t.cIdx], &rp = planes[t.rec_pic * 3 + t.cIdx];
+        const Sample *org = reinterpret_cast<const Sample *>(op.base) + (intptr_t)t.y0 * op.stride + t.x0;
+        const Sample *rec = reinterpret_cast<const Sample *>(rp.base) + (intptr_t)t.y0 * rp.stride + t.x0;
+        const int iw = t.w - 2, ih = t.h - 2; // the interior: rows and columns 1 .. size - 2
+        for (int i = threadIdx.x; i < iw * ih; i += blockDim.x)
+        {
+            const int y = 1 + i / iw, x = 1 + i - (y - 1) * iw;
+            const Sample *at = rec + (intptr_t)y * rp.stride + x;
+            const int v = at[0], diff = (int)org[(intptr_t)y * op.stride + x] - v;
+            const intptr_t up = -(intptr_t)rp.stride;
+            // neighbour pairs of the classes: horizontal, vertical, the \ diagonal, the / diagonal (turing/sao.cpp:64-74)
+            const int a[4] = {at[-1], at[up], at[up - 1], at[up + 1]}, b[4] = {at[1], at[-up], at[-up + 1], at[-up - 1]};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+                const int idx = 2 + (v > a[c]) - (v < a[c]) + (v > b[c]) - (v < b[c]);
+                const int category = idx == 2 ? 0 : (idx < 2 ? idx + 1 : idx);
+                atomicAdd(&acc[c * 5 + category], diff);
+                atomicAdd(&acc[20 + c * 5 + category], 1);
+            }
+            if (x == 1)
+            {
+                // the reference's class-0 loop visits column 1 a second time, as category 0 (EncSao.h:167-181)
+                atomicAdd(&acc[0], diff);
+                atomicAdd(&acc[20], 1);
+            }
+            const int band = v >> (bitDepth - 5);
+            atomicAdd(&acc[40 + band], diff);
+            atomicAdd(&acc[72 + band], 1);
+        }
+        __syncthreads();
+        int *o = reinterpret_cast<int *>(out + ti);
+        for (int i = threadIdx.x; i < 104; i += blockDim.x) o[i] = acc[i];
+        __syncthreads();
+    }
+}
+
 } // namespace
 
 extern "C" int hvb_deblock_info_upload(hvb_context *ctx, int pic, const hvb_deblock_block *blocks, int blockStride, int blockRows,
@@ -484,4 +538,24 @@ extern "C" int hvb_deblock_batch(hvb_context *ctx, const hvb_deblock_task *tasks
         deblockKernel<uint16_t><<<blocks, 256, 0, ctx->stream>>>(ctx->dPlanes, ctx->dLoopInfo, dT, n, ctx->bitDepth);
     HVB_LAUNCH_CHECK(ctx, "deblockKernel");
     return hvbStageOut(ctx, nullptr, 0, mem, st);
+}
+
+extern "C" int hvb_sao_stats_batch(hvb_context *ctx, const hvb_sao_stats_task *tasks, int n, hvb_sao_stats *out, hvb_mem mem)
+{
+    HVB_CHECK_ARGS(ctx, n >= 0 && (n == 0 || (tasks && out)));
+    if (!n) return HVB_OK;
+    static_assert(sizeof(hvb_sao_stats) == 104 * sizeof(int32_t), "saoStatsKernel writes hvb_sao_stats as 104 ints");
+    cudaSetDevice(ctx->device);
+    HvbStaged st;
+    int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(*out) * n, mem, &st);
+    if (rc) return rc;
+    const auto *dT = static_cast<const hvb_sao_stats_task *>(st.dTasks);
+    auto *dO = static_cast<hvb_sao_stats *>(st.dOut);
+    const int blocks = min(n, ctx->smCount * 8);
+    if (ctx->bps == 1)
+        saoStatsKernel<uint8_t><<<blocks, 256, 0, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
+    else
+        saoStatsKernel<uint16_t><<<blocks, 256, 0, ctx->stream>>>(ctx->dPlanes, dT, n, dO, ctx->bitDepth);
+    HVB_LAUNCH_CHECK(ctx, "saoStatsKernel");
+    return hvbStageOut(ctx, out, sizeof(*out) * n, mem, st);
 }

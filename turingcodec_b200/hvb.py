@@ -67,6 +67,9 @@ sao_ctu_t = np.dtype([("left", "<i2"), ("top", "<i2"), ("right", "<i2"), ("botto
                       ("plane", np.dtype([("typeIdx", "i1"), ("classOrBand", "i1"), ("offset", "<i2", 4)], align=True), 3)], align=True)
 sao_task_t = np.dtype([("src_pic", "<i2"), ("dst_pic", "<i2"), ("ctuBegin", "<i2"), ("ctuEnd", "<i2"), ("lumaFlag", "u1"),
                        ("chromaFlag", "u1"), ("reserved", "<i2")], align=True)
+sao_stats_task_t = np.dtype([("org_pic", "<i2"), ("rec_pic", "<i2"), ("cIdx", "<i2"), ("x0", "<i2"), ("y0", "<i2"), ("w", "<i2"),
+                             ("h", "<i2"), ("reserved", "<i2")], align=True)
+sao_stats_t = np.dtype([("edgeE", "<i4", (4, 5)), ("edgeCount", "<i4", (4, 5)), ("bandE", "<i4", 32), ("bandCount", "<i4", 32)], align=True)
 me_bi_task_t = np.dtype([("src_pic", "<i2"), ("ref_pic", "<i2"), ("x0", "<i2"), ("y0", "<i2"), ("w", "<i2"),
                          ("h", "<i2"), ("mvp", mv_t, 2), ("other_pic", "<i2"), ("reserved0", "<i2"),
                          ("rateMvpFlag", "<i8", 2), ("lambda", "<i4"), ("limitMin", mv_t), ("limitMax", mv_t),
@@ -131,7 +134,7 @@ def load_library() -> C.CDLL:
     lib.hvb_rdoq_contexts_upload.argtypes = [vp, vp, i32, i32]
     for name in ("hvb_sad_batch", "hvb_ssd_batch", "hvb_satd_batch", "hvb_sad4_batch", "hvb_interp_satd_batch",
                  "hvb_intra_satd35_batch", "hvb_quantize_batch", "hvb_tu_chain_batch", "hvb_rdoq_batch",
-                 "hvb_me_search_batch", "hvb_me_bi_search_batch", "hvb_pu_cost_batch"):
+                 "hvb_me_search_batch", "hvb_me_bi_search_batch", "hvb_pu_cost_batch", "hvb_sao_stats_batch"):
         if hasattr(lib, name):
             getattr(lib, name).argtypes = [vp, vp, i32, vp, i32]
     if hasattr(lib, "hvb_deblock_info_upload"):
@@ -343,6 +346,9 @@ class Context:
     def sao_info_upload(self, pic: int, ctus: np.ndarray):
         ctus = np.ascontiguousarray(ctus, dtype=sao_ctu_t)
         self._check(self.lib.hvb_sao_info_upload(self.h, pic, _as_ptr(ctus), ctus.size), "hvb_sao_info_upload")
+
+    def sao_stats(self, tasks, n=None, out=None, mem=HOST):
+        return self._with_out("hvb_sao_stats_batch", tasks, n, out, sao_stats_t, lambda k: (k,), mem)
 
     def sao(self, tasks, n=None, mem=HOST):
         self._no_out("hvb_sao_batch", tasks, n, mem)
