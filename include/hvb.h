@@ -92,6 +92,9 @@ int hvb_picture_download_rect(hvb_context *ctx, int pic, int cIdx, void *host, i
                               int x0, int y0, int w, int h);
 /* replicate edge samples into the padding of all three planes (turing/Padding.h) */
 int hvb_picture_pad(hvb_context *ctx, int pic);
+/* device-to-device copy of all three planes incl. their padding (same geometry required): the copy of the deblocked
+ * picture that SAO filters from (turing/TaskSao.cpp:96-121) */
+int hvb_picture_copy(hvb_context *ctx, int dst_pic, int src_pic);
 /* raw device view of a plane: pointer to sample (0,0) and stride in samples (for zero-copy fills) */
 int hvb_picture_plane(hvb_context *ctx, int pic, int cIdx, void **dev_ptr, intptr_t *stride);
 

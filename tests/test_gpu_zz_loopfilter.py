@@ -83,9 +83,9 @@ def test_sao_matches_oracle(oracle, bps, bit_depth):
             want = [a.copy() for a in src]
             pin.sao_call(oracle.lib.orc_sao, False, want, src, bps, bit_depth, blocks, stride, ctus, *flags)
             visible = [np.ascontiguousarray(a[v]) for a, v in zip(src, views)]
-            for pic in (src_pic, dst_pic):
-                upload(ctx, pic, visible)
-                ctx.picture_pad(pic)  # the edge classes read one sample beyond the picture before the undo runs discard the result
+            upload(ctx, src_pic, visible)
+            ctx.picture_pad(src_pic)  # the edge classes read one sample beyond the picture before the undo runs discard the result
+            ctx.picture_copy(dst_pic, src_pic)  # as TaskSao: the picture and a copy of it, one filtered from the other
             b, _ = records(blocks, np.zeros((wc * hc, 2), np.int8))
             ctx.deblock_info_upload(dst_pic, b, np.zeros(wc * hc, hvb.deblock_ctu_t), wc, hc, pin.CTB_LOG2)
             ctx.sao_info_upload(dst_pic, np.frombuffer(bytes(ctus), dtype=hvb.sao_ctu_t).copy())

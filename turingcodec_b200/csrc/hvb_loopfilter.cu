@@ -559,3 +559,18 @@ extern "C" int hvb_sao_stats_batch(hvb_context *ctx, const hvb_sao_stats_task *t
     HVB_LAUNCH_CHECK(ctx, "saoStatsKernel");
     return hvbStageOut(ctx, out, sizeof(*out) * n, mem, st);
 }
+
+extern "C" int hvb_picture_copy(hvb_context *ctx, int dst_pic, int src_pic)
+{
+    HVB_CHECK_ARGS(ctx, dst_pic >= 0 && dst_pic < HVB_MAX_PICTURES && src_pic >= 0 && src_pic < HVB_MAX_PICTURES && dst_pic != src_pic);
+    const HvbPicture &d = ctx->pictures[dst_pic], &s = ctx->pictures[src_pic];
+    HVB_CHECK_ARGS(ctx, d.live && s.live && d.width == s.width && d.height == s.height && d.pad == s.pad);
+    cudaSetDevice(ctx->device);
+    for (int c = 0; c < 3; ++c)
+    {
+        if (d.allocBytes[c] != s.allocBytes[c]) return hvbFail(ctx, HVB_ERR_INVALID, "hvb_picture_copy: plane allocations differ");
+        cudaError_t e = cudaMemcpyAsync(d.alloc[c], s.alloc[c], s.allocBytes[c], cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) return hvbCuda(ctx, e, "hvb_picture_copy");
+    }
+    return HVB_OK;
+}

@@ -125,6 +125,8 @@ def load_library() -> C.CDLL:
     lib.hvb_picture_upload.argtypes = [vp, i32, i32, vp, C.c_ssize_t, i32, i32]
     lib.hvb_picture_download.argtypes = [vp, i32, i32, vp, C.c_ssize_t, i32, i32]
     lib.hvb_picture_pad.argtypes = [vp, i32]
+    if hasattr(lib, "hvb_picture_copy"):
+        lib.hvb_picture_copy.argtypes = [vp, i32, i32]
     lib.hvb_picture_upload_rect.argtypes = [vp, i32, i32, vp, C.c_ssize_t, i32, i32, i32, i32]
     lib.hvb_picture_download_rect.argtypes = [vp, i32, i32, vp, C.c_ssize_t, i32, i32, i32, i32]
     lib.hvb_picture_plane.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_ssize_t)]
@@ -228,6 +230,9 @@ class Context:
         self._check(self.lib.hvb_picture_download(self.h, pic, c_idx, _as_ptr(out), width, 0, height),
                     "hvb_picture_download")
         return out
+
+    def picture_copy(self, dst_pic: int, src_pic: int):
+        self._check(self.lib.hvb_picture_copy(self.h, dst_pic, src_pic), "hvb_picture_copy")
 
     def picture_pad(self, pic: int):
         self._check(self.lib.hvb_picture_pad(self.h, pic), "hvb_picture_pad")
