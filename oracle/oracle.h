@@ -267,6 +267,13 @@ void orc_sao(void *const dst[3], void *const src[3], const intptr_t strides[3], 
  * startBand.  Pinned: tests/test_oracle_pin_loopfilter.py. */
 int orc_sao_stats(const void *org, intptr_t strideOrg, const void *rec, intptr_t strideRec, int w, int h, int shift, int bps, int64_t out[104]);
 
+/* ---- coded-data feed ------------------------------------------------------------- */
+
+/* turing/CodedData.h:457-517 (storeResidual): the uint16 record of a (1 << log2n)^2 block of quantised levels (raster
+ * order) in the encoder's coded-data stream; returns its length in words, 0 for an all-zero block (nothing written).
+ * `out` needs 5 + 19 * (number of 4x4 sub-blocks) words at most.  Pinned: tests/test_oracle_pin_codeddata.py. */
+int orc_coded_residual(const int16_t *levels, int log2n, int scanIdx, uint16_t *out);
+
 #ifdef __cplusplus
 }
 #endif
