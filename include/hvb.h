@@ -470,6 +470,29 @@ typedef struct
 } hvb_sao_stats; /* 416 bytes */
 int hvb_sao_stats_batch(hvb_context *ctx, const hvb_sao_stats_task *tasks, int n, hvb_sao_stats *out, hvb_mem mem);
 
+/* ---- coded-data feed (first GPU verification pending) ---- */
+
+/* CodedData::storeResidual (turing/CodedData.h:457-517): the levels of a transform block (raster (1 << log2n)^2 int16 at
+ * coefficient-pool offset `levels`, e.g. where hvb_tu_chain_batch left them) serialised into the encoder's coded-data
+ * record -- the transform-skip word (0), the coded_sub_block flag word(s), then per significant 4x4 sub-block from the last
+ * in scan order: significance, greater-than-1 and sign masks (bit 15 - n for scan position n) and the magnitudes above 1.
+ * Records are packed into the pool region [recordsBase, recordsBase + capacityWords) (uint16 words; fetch it with
+ * hvb_coeff_download); out[i] = where block i's record starts and its length (0: all-zero block, nothing written;
+ * -1: the region was full), out[n] = {end of the used part, words that did not fit}.  The order of the records in the
+ * region is not defined (blocks reserve their room concurrently). */
+typedef struct
+{
+    int32_t levels;
+    int8_t log2n, scanIdx;
+    int16_t reserved;
+} hvb_coded_residual_task; /* 8 bytes */
+typedef struct
+{
+    int32_t offset, words;
+} hvb_coded_residual; /* 8 bytes */
+int hvb_coded_residual_batch(hvb_context *ctx, const hvb_coded_residual_task *tasks, int n, int32_t recordsBase, int32_t capacityWords,
+                             hvb_coded_residual *out /* [n + 1] */, hvb_mem mem);
+
 #ifdef __cplusplus
 }
 #endif

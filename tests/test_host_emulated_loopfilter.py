@@ -1,43 +1,17 @@
-"""The device in-loop-filter kernels' own source (deblocking, SAO application), executed on the CPU, against the pinned oracle.
-
-csrc/hvb_loopfilter.cu's kernels use no warp-level primitive and walk their jobs in grid-stride (or block-stride) loops, so
-with a grid of ONE thread their bodies are ordinary sequential programs (the statistics kernel's shared-memory atomics and
-block barriers degenerate to plain additions and no-ops).  This test cuts the kernels (the anonymous namespace of the .cu
-file, verbatim) out of the source, compiles it with g++ against the CUDA headers' host definitions (blockIdx / gridDim
-become constants of a 1-thread grid) and runs it on host memory: job decomposition, vector load / store packing, the
-decisions and the three filters are then checked bit-for-bit without a GPU.  What it cannot see is device-only behaviour
-(alignment faults, the launch itself) -- tests/test_gpu_zz_loopfilter.py covers that on a B200.  Nothing here is product
-code: the emulation library is built in a temporary directory."""
+"""The device in-loop-filter kernels' own source (deblocking, SAO application, SAO statistics), executed on the CPU
+(tests/host_emu.py: a 1-thread grid, g++ against the CUDA host headers), against the pinned oracle: job decomposition,
+vector load / store packing, decisions, filters, undo runs and the statistics sums are checked bit-for-bit without a GPU.
+tests/test_gpu_zz_loopfilter.py is the same comparison on a B200."""
 import ctypes as C
-import subprocess
-from pathlib import Path
 
 import numpy as np
 import pytest
 
+import host_emu
 import orc
 import test_oracle_pin_loopfilter as pin
 from turingcodec_b200 import hvb
 
-ROOT = Path(__file__).resolve().parent.parent
-CUDA_INC = Path("/usr/local/cuda/include")
-
-PRELUDE = r'''
-#include <cuda_runtime.h>
-#include <algorithm>
-#include <cstdint>
-#include <cstdlib>
-#include "hvb.h"
-#define __launch_bounds__(...)
-using std::max;
-using std::min;
-@STRUCTS@
-static inline int hvbClip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
-static inline void __syncthreads() {}
-static inline int atomicAdd(int *p, int v) { const int old = *p; *p += v; return old; }
-static const uint3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0};
-static const dim3 blockDim(1), gridDim(1);
-'''
 ENTRY = r'''
 extern "C" void emu_deblock(const HvbPlane *planes, const HvbLoopInfo *info, const hvb_deblock_task *tasks, int n, int bitDepth, int bps)
 {
@@ -69,26 +43,9 @@ class LoopInfo(C.Structure):
                 ("widthInCtbs", C.c_int32), ("ctbLog2", C.c_int32), ("saoCount", C.c_int32), ("reserved", C.c_int32)]
 
 
-def struct_text(header: str, name: str) -> str:
-    """the definition of `struct name { ... };` as csrc/hvb_internal.cuh has it, so that the emulation cannot drift from it"""
-    start = header.index(f"struct {name}\n{{")
-    return header[start:header.index("};", start) + 2]
-
-
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
-    if not (CUDA_INC / "cuda_runtime.h").exists():
-        pytest.skip("CUDA headers not found")
-    src = (ROOT / "turingcodec_b200" / "csrc" / "hvb_loopfilter.cu").read_text()
-    kernel = src[src.index("namespace {"):src.index("} // namespace") + len("} // namespace")]
-    assert "deblockKernel" in kernel and "__shfl" not in kernel and "__syncwarp" not in kernel
-    internal = (ROOT / "turingcodec_b200" / "csrc" / "hvb_internal.cuh").read_text()
-    structs = struct_text(internal, "HvbPlane") + "\n" + struct_text(internal, "HvbLoopInfo")
-    d = tmp_path_factory.mktemp("emu_loopfilter")
-    (d / "emu.cpp").write_text(PRELUDE.replace("@STRUCTS@", structs) + kernel + ENTRY)
-    subprocess.run(["g++", "-O1", "-fPIC", "-shared", "-w", "-std=c++17", f"-I{CUDA_INC}", f"-I{ROOT / 'include'}", str(d / "emu.cpp"),
-                    "-o", str(d / "emu.so")], check=True, capture_output=True)
-    lib = C.CDLL(str(d / "emu.so"))
+    lib = host_emu.build(tmp_path_factory.mktemp("emu_loopfilter"), "hvb_loopfilter.cu", ["HvbPlane", "HvbLoopInfo"], ENTRY)
     assert lib.emu_sizeof_plane() == C.sizeof(Plane) and lib.emu_sizeof_loop_info() == C.sizeof(LoopInfo)
     return lib
 
