@@ -493,6 +493,21 @@ typedef struct
 int hvb_coded_residual_batch(hvb_context *ctx, const hvb_coded_residual_task *tasks, int n, int32_t recordsBase, int32_t capacityWords,
                              hvb_coded_residual *out /* [n + 1] */, hvb_mem mem);
 
+/* ---- pre-analysis (first GPU verification pending) ---- */
+
+/* EstimateIntraComplexity::preAnalysis (turing/EstimateIntraComplexity.h:159-176) over a region of a source picture's
+ * luma plane: for each 8x8 block of the wBlocks x hBlocks blocks starting at (x0, y0) (multiples of 8), computeSatd8x8
+ * (:55-157), the sum of the absolute Hadamard coefficients of the samples without the DC term, (s + 2) >> 2 (16-bit
+ * samples: >> 2 more); out[task.out + by * wBlocks + bx].  A task must not overlap another's output.  The caller sums
+ * (m_satdSum, getSatdCtu). */
+typedef struct
+{
+    int16_t pic, reserved;
+    int16_t x0, y0, wBlocks, hBlocks;
+    int32_t out;
+} hvb_intra_complexity_task; /* 16 bytes */
+int hvb_intra_complexity_batch(hvb_context *ctx, const hvb_intra_complexity_task *tasks, int n, int32_t *out, int outCount, hvb_mem mem);
+
 #ifdef __cplusplus
 }
 #endif

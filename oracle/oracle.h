@@ -274,6 +274,14 @@ int orc_sao_stats(const void *org, intptr_t strideOrg, const void *rec, intptr_t
  * `out` needs 5 + 19 * (number of 4x4 sub-blocks) words at most.  Pinned: tests/test_oracle_pin_codeddata.py. */
 int orc_coded_residual(const int16_t *levels, int log2n, int scanIdx, uint16_t *out);
 
+/* ---- pre-analysis ------------------------------------------------------------------ */
+
+/* turing/EstimateIntraComplexity.h:55-157 (computeSatd8x8): AC Hadamard energy of an 8x8 block of source samples. */
+int orc_intra_complexity_8x8(const void *p, intptr_t stride, int bps);
+/* turing/EstimateIntraComplexity.h:159-176 (preAnalysis): the same for every whole 8x8 block of a plane, raster order;
+ * returns the sum.  Pinned: tests/test_oracle_pin_preanalysis.py. */
+int orc_intra_complexity(const void *plane, intptr_t stride, int width, int height, int bps, int32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,7 +40,8 @@ def test_struct_sizes_match_header(tmp_path):
                "hvb_deblock_block": hvb.deblock_block_t, "hvb_deblock_ctu": hvb.deblock_ctu_t, "hvb_deblock_task": hvb.deblock_task_t,
                "hvb_sao_ctu": hvb.sao_ctu_t, "hvb_sao_task": hvb.sao_task_t,
                "hvb_sao_stats_task": hvb.sao_stats_task_t, "hvb_sao_stats": hvb.sao_stats_t,
-               "hvb_coded_residual_task": hvb.coded_residual_task_t, "hvb_coded_residual": hvb.coded_residual_t}
+               "hvb_coded_residual_task": hvb.coded_residual_task_t, "hvb_coded_residual": hvb.coded_residual_t,
+               "hvb_intra_complexity_task": hvb.intra_complexity_task_t}
     src = tmp_path / "sizes.c"
     body = "\n".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in structs)
     src.write_text(f'#include <stdio.h>\n#include "hvb.h"\nint main(void){{{body} return 0;}}\n')

@@ -72,6 +72,8 @@ sao_stats_task_t = np.dtype([("org_pic", "<i2"), ("rec_pic", "<i2"), ("cIdx", "<
 sao_stats_t = np.dtype([("edgeE", "<i4", (4, 5)), ("edgeCount", "<i4", (4, 5)), ("bandE", "<i4", 32), ("bandCount", "<i4", 32)], align=True)
 coded_residual_task_t = np.dtype([("levels", "<i4"), ("log2n", "i1"), ("scanIdx", "i1"), ("reserved", "<i2")], align=True)
 coded_residual_t = np.dtype([("offset", "<i4"), ("words", "<i4")], align=True)
+intra_complexity_task_t = np.dtype([("pic", "<i2"), ("reserved", "<i2"), ("x0", "<i2"), ("y0", "<i2"), ("wBlocks", "<i2"),
+                                    ("hBlocks", "<i2"), ("out", "<i4")], align=True)
 me_bi_task_t = np.dtype([("src_pic", "<i2"), ("ref_pic", "<i2"), ("x0", "<i2"), ("y0", "<i2"), ("w", "<i2"),
                          ("h", "<i2"), ("mvp", mv_t, 2), ("other_pic", "<i2"), ("reserved0", "<i2"),
                          ("rateMvpFlag", "<i8", 2), ("lambda", "<i4"), ("limitMin", mv_t), ("limitMax", mv_t),
@@ -141,6 +143,8 @@ def load_library() -> C.CDLL:
                  "hvb_me_search_batch", "hvb_me_bi_search_batch", "hvb_pu_cost_batch", "hvb_sao_stats_batch"):
         if hasattr(lib, name):
             getattr(lib, name).argtypes = [vp, vp, i32, vp, i32]
+    if hasattr(lib, "hvb_intra_complexity_batch"):
+        lib.hvb_intra_complexity_batch.argtypes = [vp, vp, i32, vp, i32, i32]
     if hasattr(lib, "hvb_coded_residual_batch"):
         lib.hvb_coded_residual_batch.argtypes = [vp, vp, i32, i32, i32, vp, i32]
     if hasattr(lib, "hvb_deblock_info_upload"):
@@ -355,6 +359,14 @@ class Context:
     def sao_info_upload(self, pic: int, ctus: np.ndarray):
         ctus = np.ascontiguousarray(ctus, dtype=sao_ctu_t)
         self._check(self.lib.hvb_sao_info_upload(self.h, pic, _as_ptr(ctus), ctus.size), "hvb_sao_info_upload")
+
+    def intra_complexity(self, tasks, out_count: int) -> np.ndarray:
+        """-> int32 [out_count]: the 8x8 blocks' AC Hadamard energies, placed by each task's `out` offset (host tasks)"""
+        tasks = np.ascontiguousarray(tasks, dtype=intra_complexity_task_t)
+        out = np.zeros(out_count, np.int32)
+        self._check(self.lib.hvb_intra_complexity_batch(self.h, _as_ptr(tasks), tasks.size, _as_ptr(out), out_count, HOST),
+                    "hvb_intra_complexity_batch")
+        return out
 
     def coded_residual(self, tasks, records_base: int, capacity_words: int) -> np.ndarray:
         """-> coded_residual_t [n + 1] (host tasks): per block (offset, words), last entry (end of the used region, overflow)"""
