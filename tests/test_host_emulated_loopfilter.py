@@ -8,7 +8,6 @@ import numpy as np
 import pytest
 
 import host_emu
-import orc
 import test_oracle_pin_loopfilter as pin
 from turingcodec_b200 import hvb
 

@@ -15,6 +15,7 @@
 // (VABSDIFF4 / dp4a), then a 5-step shuffle tree.
 #include "hvb_internal.cuh"
 #include "hvb_satd.cuh"
+#include "hvb_unit.cuh"
 
 namespace {
 
@@ -194,6 +195,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 
 namespace {
 
+using hvb_unit::imma16832;
+
 // ---- 8-bit SATD of 8x8-tiled blocks on the integer tensor cores ---------------------------------------------------
 // sum |H d H^T| over a tile = sum |(H (x) H) vec(a) - (H (x) H) vec(b)|: eight tiles at a time are one
 // [H | -H] x [a ; b] product (IMMA m16n8k32, s8 x u8 -> s32, M = 64, K = 64 + 64), the B fragments loaded straight
@@ -216,13 +219,6 @@ struct HadamardFrag
             for (int r = 0; r < 4; ++r) x[m0][r] = (((r & 1) & t0) ^ ((r >> 1) & g2) ^ (m0 & t1)) ? pat ^ 0xfefefefeu : pat;
     }
 };
-
-__device__ __forceinline__ void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
-{
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
 
 // 8 bytes of a tile row: one 64-bit load when the row is 8-byte aligned, else three aligned words and two funnel shifts
 __device__ __forceinline__ uint2 loadRow8(const uint8_t *p)
