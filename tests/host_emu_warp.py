@@ -1,0 +1,242 @@
+"""Host emulation of WARP-LEVEL device kernels (test infrastructure, never product code).
+
+tests/host_emu.py runs kernels without warp primitives on a grid of one thread.  Kernels that shuffle, vote, synchronise
+warps or issue tensor-core products need their 32 lanes in lock step; here every CUDA thread of a block is a FIBER
+(ucontext) on one OS thread, scheduled round-robin, and a collective is a rendezvous of a warp's fibers:
+
+  __shfl_sync / __shfl_xor_sync / __any_sync / __ballot_sync / __syncwarp     exchange through a per-warp buffer
+  __syncthreads                                                                rendezvous of the block's fibers
+  mma.sync.m16n8k32.s8.u8 (the imma16832 wrapper of csrc/hvb_unit.cuh)         gathers the warp's A / B / C fragments and
+                                                                               forms the PTX-defined 16x8x32 product
+  atomicAdd, __ldg, __funnelshift_r, __byte_perm, __dp4a, __dp2a_lo/hi, ...    plain host code (one fiber runs at a time)
+
+build() assembles one translation unit: this prelude, the device helpers of csrc/hvb_internal.cuh, csrc/hvb_unit.cuh and
+the anonymous namespace of the kernel's .cu file -- all VERBATIM except that the two inline-PTX wrapper bodies (imma16832,
+dp4aUS) are replaced by the emulated ones and `__shared__` is mapped to block-wide storage.  Blocks run one after another;
+the launch geometry is the caller's.  Device-only behaviour (alignment faults, real scheduling) remains the GPU tests'."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+CSRC = ROOT / "turingcodec_b200" / "csrc"
+CUDA_INC = Path("/usr/local/cuda/include")
+
+PRELUDE = r'''
+#include <cuda_runtime.h>
+#include <ucontext.h>
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "hvb.h"
+#define __launch_bounds__(...)
+using std::max;
+using std::min;
+
+// ---- fibers -------------------------------------------------------------------------------------------------------------
+namespace emu {
+struct Fiber { ucontext_t ctx; std::vector<char> stack; bool done = false; };
+static std::vector<Fiber> fibers;
+static ucontext_t scheduler;
+static int current = 0, threads = 0;
+static void (*body)() = nullptr;
+struct WarpState { int arrived = 0; unsigned generation = 0; uint32_t buf[32]; uint64_t wide[32][10]; };
+static std::vector<WarpState> warps;
+static int blockArrived = 0; static unsigned blockGeneration = 0;
+alignas(16) static unsigned char sharedArena[256 * 1024];
+
+static void yield() { swapcontext(&fibers[current].ctx, &scheduler); }
+static void trampoline() { body(); fibers[current].done = true; swapcontext(&fibers[current].ctx, &scheduler); }
+static void warpRendezvous()
+{
+    WarpState &w = warps[current >> 5];
+    const unsigned gen = w.generation;
+    if (++w.arrived == 32) { w.arrived = 0; ++w.generation; }
+    else while (w.generation == gen) yield();
+}
+static void blockRendezvous()
+{
+    const unsigned gen = blockGeneration;
+    if (++blockArrived == threads) { blockArrived = 0; ++blockGeneration; }
+    else while (blockGeneration == gen) yield();
+}
+static uint32_t exchange(uint32_t v, int src)
+{
+    WarpState &w = warps[current >> 5];
+    w.buf[current & 31] = v;
+    warpRendezvous();
+    const uint32_t r = w.buf[src & 31];
+    warpRendezvous();
+    return r;
+}
+} // namespace emu
+
+static uint3 blockIdx = {0, 0, 0};
+static dim3 blockDim(1), gridDim(1);
+struct ThreadIdxProxy { struct X { operator unsigned() const { return (unsigned)emu::current; } } x; };
+static ThreadIdxProxy threadIdx;
+
+// run `kernel` (a closure over its arguments) for every block of the grid
+template <class F> static void emuLaunch(int grid, int block, F kernel)
+{
+    static F *closure; closure = &kernel;
+    emu::body = [] { (*closure)(); };
+    gridDim = dim3(grid); blockDim = dim3(block); emu::threads = block;
+    for (int b = 0; b < grid; ++b)
+    {
+        blockIdx.x = b;
+        emu::fibers.assign(block, emu::Fiber());
+        emu::warps.assign((block + 31) / 32, emu::WarpState());
+        emu::blockArrived = 0;
+        for (int t = 0; t < block; ++t)
+        {
+            emu::Fiber &f = emu::fibers[t];
+            f.stack.resize(256 * 1024);
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = f.stack.data();
+            f.ctx.uc_stack.ss_size = f.stack.size();
+            f.ctx.uc_link = &emu::scheduler;
+            makecontext(&f.ctx, emu::trampoline, 0);
+        }
+        for (bool live = true; live;)
+        {
+            live = false;
+            for (int t = 0; t < block; ++t)
+                if (!emu::fibers[t].done) { live = true; emu::current = t; swapcontext(&emu::scheduler, &emu::fibers[t].ctx); }
+        }
+    }
+}
+
+// ---- warp and block primitives ------------------------------------------------------------------------------------------
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warpRendezvous(); }
+static inline void __syncthreads() { emu::blockRendezvous(); }
+static inline int __shfl_sync(unsigned, int v, int src) { return (int)emu::exchange((uint32_t)v, src); }
+static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return emu::exchange(v, src); }
+static inline int __shfl_xor_sync(unsigned, int v, int m) { return (int)emu::exchange((uint32_t)v, (emu::current & 31) ^ m); }
+static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int m) { return emu::exchange(v, (emu::current & 31) ^ m); }
+static inline unsigned __ballot_sync(unsigned, int pred)
+{
+    emu::WarpState &w = emu::warps[emu::current >> 5];
+    w.buf[emu::current & 31] = pred != 0;
+    emu::warpRendezvous();
+    unsigned r = 0;
+    for (int i = 0; i < 32; ++i) r |= w.buf[i] << i;
+    emu::warpRendezvous();
+    return r;
+}
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
+static inline int atomicAdd(int *p, int v) { const int old = *p; *p += v; return old; }
+
+// ---- scalar intrinsics ----------------------------------------------------------------------------------------------------
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) { s &= 31; return s ? (lo >> s) | (hi << (32 - s)) : lo; }
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t sel)
+{
+    const uint64_t both = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((both >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+}
+static inline int __dp4a(int a, int b, int c) { for (int i = 0; i < 4; ++i) c += (int)(int8_t)(a >> (8 * i)) * (int)(int8_t)(b >> (8 * i)); return c; }
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) { for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xff) * ((b >> (8 * i)) & 0xff); return c; }
+static inline int __dp2a_lo(int a, int b, int c) { return c + (int)(int16_t)(a & 0xffff) * (int)(int8_t)(b & 0xff) + (int)(int16_t)(a >> 16) * (int)(int8_t)((b >> 8) & 0xff); }
+static inline int __dp2a_hi(int a, int b, int c) { return c + (int)(int16_t)(a & 0xffff) * (int)(int8_t)((b >> 16) & 0xff) + (int)(int16_t)(a >> 16) * (int)(int8_t)((b >> 24) & 0xff); }
+static inline unsigned __sad(int a, int b, unsigned c) { return c + (unsigned)std::abs(a - b); }
+static inline unsigned __vsadu4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; ++i) r += (unsigned)std::abs((int)((a >> (8 * i)) & 0xff) - (int)((b >> (8 * i)) & 0xff)); return r; }
+static inline unsigned __vabsdiffu4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; ++i) r |= (unsigned)std::abs((int)((a >> (8 * i)) & 0xff) - (int)((b >> (8 * i)) & 0xff)) << (8 * i); return r; }
+static inline int __vimin_s32_relu(int a, int b) { return std::max(std::min(a, b), 0); }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
+
+// ---- the two inline-PTX wrappers of csrc/hvb_unit.cuh, emulated ---------------------------------------------------------------
+namespace hvb_unit {
+// dp4a.u32.s32: unsigned bytes of a times signed bytes of b
+static inline int dp4aUS(uint32_t a, uint32_t b, int c) { for (int i = 0; i < 4; ++i) c += (int)((a >> (8 * i)) & 0xff) * (int)(int8_t)(b >> (8 * i)); return c; }
+// mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 (PTX ISA, "Matrix Fragments for mma.m16n8k32"): lane = 4 g + t holds
+//   A (16 x 32, s8, row):  a_r bytes j = A[g + 8 (r & 1)][4 t + 16 (r >> 1) + j]
+//   B (32 x 8,  u8, col):  b_r bytes j = B[4 t + 16 r + j][g]
+//   C / D (16 x 8, s32):   c_i        = C[g + 8 (i >> 1)][2 t + (i & 1)]
+static inline void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    emu::WarpState &w = emu::warps[emu::current >> 5];
+    const int lane = emu::current & 31, g = lane >> 2, t = lane & 3;
+    uint64_t *mine = w.wide[lane];
+    mine[0] = a0, mine[1] = a1, mine[2] = a2, mine[3] = a3, mine[4] = b0, mine[5] = b1;
+    emu::warpRendezvous();
+    for (int i = 0; i < 4; ++i)
+    {
+        const int row = g + 8 * (i >> 1), col = 2 * t + (i & 1);
+        int sum = c[i];
+        for (int k = 0; k < 32; ++k)
+        {
+            // A[row][k]: lane (row & 7, (k & 15) >> 2), register (row >> 3) + 2 (k >> 4), byte k & 3
+            const uint32_t areg = (uint32_t)w.wide[4 * (row & 7) + ((k & 15) >> 2)][(row >> 3) + 2 * (k >> 4)];
+            // B[k][col]: lane (col, (k & 15) >> 2), register k >> 4, byte k & 3
+            const uint32_t breg = (uint32_t)w.wide[4 * col + ((k & 15) >> 2)][4 + (k >> 4)];
+            sum += (int)(int8_t)(areg >> (8 * (k & 3))) * (int)((breg >> (8 * (k & 3))) & 0xff);
+        }
+        c[i] = sum;
+    }
+    emu::warpRendezvous();
+}
+} // namespace hvb_unit
+'''
+
+
+def _strip_function(text: str, signature_start: str) -> str:
+    """remove the definition that starts with `signature_start` (up to the closing brace of its body)"""
+    at = text.index(signature_start)
+    depth, i = 0, text.index("{", at)
+    while True:
+        depth += text[i] == "{"
+        depth -= text[i] == "}"
+        i += 1
+        if depth == 0:
+            break
+    return text[:at] + text[i:]
+
+
+def device_helpers() -> str:
+    """csrc/hvb_internal.cuh: the structs the kernels see and the section of device helpers"""
+    internal = (CSRC / "hvb_internal.cuh").read_text()
+    start = internal.index("struct HvbPlane\n{")
+    plane = internal[start:internal.index("};", start) + 2]
+    dev = internal[internal.index("#ifdef __CUDACC__") + len("#ifdef __CUDACC__"):internal.index("#endif // __CUDACC__")]
+    return plane + "\n" + dev
+
+
+def unit_header() -> str:
+    """csrc/hvb_unit.cuh without its includes and without the two PTX wrappers (emulated in the prelude)"""
+    text = (CSRC / "hvb_unit.cuh").read_text()
+    text = "\n".join(line for line in text.split("\n") if not line.startswith("#include") and not line.startswith("#pragma once"))
+    text = _strip_function(text, "__device__ __forceinline__ int dp4aUS(")
+    return _strip_function(text, "__device__ __forceinline__ void imma16832(")
+
+
+def build(tmp_dir: Path, cu_file: str, entry: str, strip: tuple = (), use_unit_header: bool = True) -> C.CDLL:
+    """strip: starts of the host-side definitions inside the kernel file's anonymous namespace (launch helpers with <<< >>>)"""
+    if not (CUDA_INC / "cuda_runtime.h").exists():
+        pytest.skip("CUDA headers not found")
+    src = (CSRC / cu_file).read_text()
+    kernels = src[src.index("namespace {"):src.index("} // namespace") + len("} // namespace")]
+    for signature in strip:
+        kernels = _strip_function(kernels, signature)
+    assert "<<<" not in kernels, "a host-side launch is left in the kernel text: add it to `strip`"
+    assert "asm volatile" not in kernels and "asm(" not in kernels, f"{cu_file} has inline PTX outside the emulated wrappers"
+    body = device_helpers() + ("\n" + unit_header() if use_unit_header else "") + "\n" + kernels
+    # dynamic shared memory is one block-wide arena; static __shared__ arrays become block-wide statics
+    body = re.sub(r"extern\s+__shared__\s+(__align__\(\d+\)\s+)?(\w[\w\s]*?)\s+(\w+)\[\];", r"\2 *const \3 = reinterpret_cast<\2 *>(emu::sharedArena);", body)
+    body = body.replace("__shared__", "static")
+    (tmp_dir / "emu_warp.cpp").write_text(PRELUDE + body + entry)
+    res = subprocess.run(["g++", "-O1", "-fPIC", "-shared", "-w", "-std=c++17", f"-I{CUDA_INC}", f"-I{ROOT / 'include'}",
+                          str(tmp_dir / "emu_warp.cpp"), "-o", str(tmp_dir / "emu_warp.so")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    return C.CDLL(str(tmp_dir / "emu_warp.so"))
