@@ -36,6 +36,9 @@ PRELUDE = r'''
 #include <vector>
 #include "hvb.h"
 #define __launch_bounds__(...)
+#ifndef __noinline__
+#define __noinline__
+#endif
 using std::max;
 using std::min;
 
@@ -46,19 +49,26 @@ static std::vector<Fiber> fibers;
 static ucontext_t scheduler;
 static int current = 0, threads = 0;
 static void (*body)() = nullptr;
-struct WarpState { int arrived = 0; unsigned generation = 0; uint32_t buf[32]; uint64_t wide[32][10]; };
+// a rendezvous is among the lanes of a mask: full warps, or the disjoint lane groups some kernels synchronise separately
+struct MaskState { unsigned mask = 0; int arrived = 0; unsigned generation = 0; };
+struct WarpState { MaskState masks[16]; uint32_t buf[32]; uint64_t wide[32][10]; };
 static std::vector<WarpState> warps;
 static int blockArrived = 0; static unsigned blockGeneration = 0;
 alignas(16) static unsigned char sharedArena[256 * 1024];
 
 static void yield() { swapcontext(&fibers[current].ctx, &scheduler); }
 static void trampoline() { body(); fibers[current].done = true; swapcontext(&fibers[current].ctx, &scheduler); }
-static void warpRendezvous()
+static void warpRendezvous(unsigned mask = 0xffffffffu)
 {
     WarpState &w = warps[current >> 5];
-    const unsigned gen = w.generation;
-    if (++w.arrived == 32) { w.arrived = 0; ++w.generation; }
-    else while (w.generation == gen) yield();
+    MaskState *m = nullptr;
+    for (MaskState &c : w.masks)
+        if (c.mask == mask || c.mask == 0) { m = &c; break; }
+    if (!m) { fprintf(stderr, "emu: more than 16 distinct lane masks in one warp\n"); abort(); }
+    m->mask = mask;
+    const unsigned gen = m->generation;
+    if (++m->arrived == __builtin_popcount(mask)) { m->arrived = 0; ++m->generation; }
+    else while (m->generation == gen) yield();
 }
 static void blockRendezvous()
 {
@@ -66,13 +76,13 @@ static void blockRendezvous()
     if (++blockArrived == threads) { blockArrived = 0; ++blockGeneration; }
     else while (blockGeneration == gen) yield();
 }
-static uint32_t exchange(uint32_t v, int src)
+static uint32_t exchange(unsigned mask, uint32_t v, int src)
 {
     WarpState &w = warps[current >> 5];
     w.buf[current & 31] = v;
-    warpRendezvous();
+    warpRendezvous(mask);
     const uint32_t r = w.buf[src & 31];
-    warpRendezvous();
+    warpRendezvous(mask);
     return r;
 }
 } // namespace emu
@@ -114,20 +124,21 @@ template <class F> static void emuLaunch(int grid, int block, F kernel)
 }
 
 // ---- warp and block primitives ------------------------------------------------------------------------------------------
-static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warpRendezvous(); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warpRendezvous(mask); }
 static inline void __syncthreads() { emu::blockRendezvous(); }
-static inline int __shfl_sync(unsigned, int v, int src) { return (int)emu::exchange((uint32_t)v, src); }
-static inline unsigned __shfl_sync(unsigned, unsigned v, int src) { return emu::exchange(v, src); }
-static inline int __shfl_xor_sync(unsigned, int v, int m) { return (int)emu::exchange((uint32_t)v, (emu::current & 31) ^ m); }
-static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int m) { return emu::exchange(v, (emu::current & 31) ^ m); }
-static inline unsigned __ballot_sync(unsigned, int pred)
+static inline int __shfl_sync(unsigned mask, int v, int src) { return (int)emu::exchange(mask, (uint32_t)v, src); }
+static inline unsigned __shfl_sync(unsigned mask, unsigned v, int src) { return emu::exchange(mask, v, src); }
+static inline int __shfl_xor_sync(unsigned mask, int v, int m) { return (int)emu::exchange(mask, (uint32_t)v, (emu::current & 31) ^ m); }
+static inline unsigned __shfl_xor_sync(unsigned mask, unsigned v, int m) { return emu::exchange(mask, v, (emu::current & 31) ^ m); }
+static inline unsigned __ballot_sync(unsigned mask, int pred)
 {
     emu::WarpState &w = emu::warps[emu::current >> 5];
     w.buf[emu::current & 31] = pred != 0;
-    emu::warpRendezvous();
+    emu::warpRendezvous(mask);
     unsigned r = 0;
-    for (int i = 0; i < 32; ++i) r |= w.buf[i] << i;
-    emu::warpRendezvous();
+    for (int i = 0; i < 32; ++i)
+        if (mask >> i & 1) r |= w.buf[i] << i;
+    emu::warpRendezvous(mask);
     return r;
 }
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
@@ -149,6 +160,7 @@ static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) { for (int i =
 static inline int __dp2a_lo(int a, int b, int c) { return c + (int)(int16_t)(a & 0xffff) * (int)(int8_t)(b & 0xff) + (int)(int16_t)(a >> 16) * (int)(int8_t)((b >> 8) & 0xff); }
 static inline int __dp2a_hi(int a, int b, int c) { return c + (int)(int16_t)(a & 0xffff) * (int)(int8_t)((b >> 16) & 0xff) + (int)(int16_t)(a >> 16) * (int)(int8_t)((b >> 24) & 0xff); }
 static inline unsigned __sad(int a, int b, unsigned c) { return c + (unsigned)std::abs(a - b); }
+static inline unsigned __vsadu2(unsigned a, unsigned b) { return (unsigned)std::abs((int)(a & 0xffff) - (int)(b & 0xffff)) + (unsigned)std::abs((int)(a >> 16) - (int)(b >> 16)); }
 static inline unsigned __vsadu4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; ++i) r += (unsigned)std::abs((int)((a >> (8 * i)) & 0xff) - (int)((b >> (8 * i)) & 0xff)); return r; }
 static inline unsigned __vabsdiffu4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; ++i) r |= (unsigned)std::abs((int)((a >> (8 * i)) & 0xff) - (int)((b >> (8 * i)) & 0xff)) << (8 * i); return r; }
 static inline int __vimin_s32_relu(int a, int b) { return std::max(std::min(a, b), 0); }
