@@ -168,15 +168,12 @@ static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 
-// ---- the two inline-PTX wrappers of csrc/hvb_unit.cuh, emulated ---------------------------------------------------------------
-namespace hvb_unit {
-// dp4a.u32.s32: unsigned bytes of a times signed bytes of b
-static inline int dp4aUS(uint32_t a, uint32_t b, int c) { for (int i = 0; i < 4; ++i) c += (int)((a >> (8 * i)) & 0xff) * (int)(int8_t)(b >> (8 * i)); return c; }
-// mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 (PTX ISA, "Matrix Fragments for mma.m16n8k32"): lane = 4 g + t holds
+// ---- inline-PTX wrappers, emulated ----------------------------------------------------------------------------------------
+// mma.sync.aligned.m16n8k32.row.col.s32.s8.{u8|s8}.s32 (PTX ISA, "Matrix Fragments for mma.m16n8k32"): lane = 4 g + t holds
 //   A (16 x 32, s8, row):  a_r bytes j = A[g + 8 (r & 1)][4 t + 16 (r >> 1) + j]
-//   B (32 x 8,  u8, col):  b_r bytes j = B[4 t + 16 r + j][g]
+//   B (32 x 8,  col):      b_r bytes j = B[4 t + 16 r + j][g]
 //   C / D (16 x 8, s32):   c_i        = C[g + 8 (i >> 1)][2 t + (i & 1)]
-static inline void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+static inline void emuMma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1, bool signedB)
 {
     emu::WarpState &w = emu::warps[emu::current >> 5];
     const int lane = emu::current & 31, g = lane >> 2, t = lane & 3;
@@ -193,11 +190,19 @@ static inline void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
             const uint32_t areg = (uint32_t)w.wide[4 * (row & 7) + ((k & 15) >> 2)][(row >> 3) + 2 * (k >> 4)];
             // B[k][col]: lane (col, (k & 15) >> 2), register k >> 4, byte k & 3
             const uint32_t breg = (uint32_t)w.wide[4 * col + ((k & 15) >> 2)][4 + (k >> 4)];
-            sum += (int)(int8_t)(areg >> (8 * (k & 3))) * (int)((breg >> (8 * (k & 3))) & 0xff);
+            const int bval = (int)((breg >> (8 * (k & 3))) & 0xff);
+            sum += (int)(int8_t)(areg >> (8 * (k & 3))) * (signedB ? (int)(int8_t)bval : bval);
         }
         c[i] = sum;
     }
     emu::warpRendezvous();
+}
+namespace hvb_unit {
+// dp4a.u32.s32: unsigned bytes of a times signed bytes of b
+static inline int dp4aUS(uint32_t a, uint32_t b, int c) { for (int i = 0; i < 4; ++i) c += (int)((a >> (8 * i)) & 0xff) * (int)(int8_t)(b >> (8 * i)); return c; }
+static inline void imma16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    emuMma16832(c, a0, a1, a2, a3, b0, b1, false);
 }
 } // namespace hvb_unit
 '''
@@ -233,17 +238,28 @@ def unit_header() -> str:
     return _strip_function(text, "__device__ __forceinline__ void imma16832(")
 
 
-def build(tmp_dir: Path, cu_file: str, entry: str, strip: tuple = (), use_unit_header: bool = True) -> C.CDLL:
-    """strip: starts of the host-side definitions inside the kernel file's anonymous namespace (launch helpers with <<< >>>)"""
+def build(tmp_dir: Path, cu_file: str, entry: str, strip: tuple = (), use_unit_header: bool = True, mma_wrappers: dict | None = None,
+          namespaces: int = 1) -> C.CDLL:
+    """strip: starts of the host-side definitions inside the kernel file's anonymous namespace (launch helpers with <<< >>>);
+    mma_wrappers: the file's own inline-PTX mma wrappers, name -> True when the B operand is signed (s8.s8), replaced by
+    the emulated product; namespaces: how many leading anonymous namespaces of the file hold the kernels"""
     if not (CUDA_INC / "cuda_runtime.h").exists():
         pytest.skip("CUDA headers not found")
     src = (CSRC / cu_file).read_text()
-    kernels = src[src.index("namespace {"):src.index("} // namespace") + len("} // namespace")]
+    end = 0
+    for _ in range(namespaces):
+        end = src.index("} // namespace", end) + len("} // namespace")
+    kernels = src[src.index("namespace {"):end]
     for signature in strip:
         kernels = _strip_function(kernels, signature)
+    injected = ""
+    for name, signed_b in (mma_wrappers or {}).items():
+        kernels = _strip_function(kernels, f"__device__ __forceinline__ void {name}(")
+        injected += (f"static inline void {name}(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)"
+                     f" {{ emuMma16832(c, a0, a1, a2, a3, b0, b1, {'true' if signed_b else 'false'}); }}\n")
     assert "<<<" not in kernels, "a host-side launch is left in the kernel text: add it to `strip`"
     assert "asm volatile" not in kernels and "asm(" not in kernels, f"{cu_file} has inline PTX outside the emulated wrappers"
-    body = device_helpers() + ("\n" + unit_header() if use_unit_header else "") + "\n" + kernels
+    body = device_helpers() + ("\n" + unit_header() if use_unit_header else "") + "\n" + injected + kernels
     # dynamic shared memory is one block-wide arena; static __shared__ arrays become block-wide statics
     body = re.sub(r"extern\s+__shared__\s+(__align__\(\d+\)\s+)?(\w[\w\s]*?)\s+(\w+)\[\];", r"\2 *const \3 = reinterpret_cast<\2 *>(emu::sharedArena);", body)
     body = body.replace("__shared__", "static")
