@@ -166,6 +166,12 @@ static inline unsigned __vabsdiffu4(unsigned a, unsigned b) { unsigned r = 0; fo
 static inline int __vimin_s32_relu(int a, int b) { return std::max(std::min(a, b), 0); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+static inline int __mul24(int a, int b) { return a * b; }
+static inline long long __mul64hi(long long a, long long b) { return (long long)(((__int128)a * b) >> 64); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 
 // ---- inline-PTX wrappers, emulated ----------------------------------------------------------------------------------------
@@ -238,8 +244,14 @@ def unit_header() -> str:
     return _strip_function(text, "__device__ __forceinline__ void imma16832(")
 
 
+def header_text(name: str) -> str:
+    """a csrc/*.cuh header without its include / pragma-once lines (its dependencies are already in the translation unit)"""
+    text = (CSRC / name).read_text()
+    return "\n".join(line for line in text.split("\n") if not line.startswith("#include") and not line.startswith("#pragma once"))
+
+
 def build(tmp_dir: Path, cu_file: str, entry: str, strip: tuple = (), use_unit_header: bool = True, mma_wrappers: dict | None = None,
-          namespaces: int = 1) -> C.CDLL:
+          namespaces: int = 1, extra_headers: tuple = ()) -> C.CDLL:
     """strip: starts of the host-side definitions inside the kernel file's anonymous namespace (launch helpers with <<< >>>);
     mma_wrappers: the file's own inline-PTX mma wrappers, name -> True when the B operand is signed (s8.s8), replaced by
     the emulated product; namespaces: how many leading anonymous namespaces of the file hold the kernels"""
@@ -259,7 +271,8 @@ def build(tmp_dir: Path, cu_file: str, entry: str, strip: tuple = (), use_unit_h
                      f" {{ emuMma16832(c, a0, a1, a2, a3, b0, b1, {'true' if signed_b else 'false'}); }}\n")
     assert "<<<" not in kernels, "a host-side launch is left in the kernel text: add it to `strip`"
     assert "asm volatile" not in kernels and "asm(" not in kernels, f"{cu_file} has inline PTX outside the emulated wrappers"
-    body = device_helpers() + ("\n" + unit_header() if use_unit_header else "") + "\n" + injected + kernels
+    body = (device_helpers() + ("\n" + unit_header() if use_unit_header else "") + "\n" + "\n".join(header_text(h) for h in extra_headers)
+            + "\n" + injected + kernels)
     # dynamic shared memory is one block-wide arena; static __shared__ arrays become block-wide statics
     body = re.sub(r"extern\s+__shared__\s+(__align__\(\d+\)\s+)?(\w[\w\s]*?)\s+(\w+)\[\];", r"\2 *const \3 = reinterpret_cast<\2 *>(emu::sharedArena);", body)
     body = body.replace("__shared__", "static")
