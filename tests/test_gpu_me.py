@@ -170,9 +170,8 @@ def fill_bi(t, o, src_pic, ref_pic, other_pic):
     t["smallWindow"], t["halfPel"], t["quarterPel"] = o.smallWindow, o.halfPel, o.quarterPel
 
 
-def test_me_bi_search_matches_oracle(scene, oracle):
-    rng = np.random.default_rng(77)
-    n = 300
+def make_bi_tasks(rng, scene, n):
+    """-> hvb_me_bi_task array and the matching orc.MeBiTask list (also used by tests/test_host_emulated_me.py)"""
     tasks = np.zeros(n, hvb.me_bi_task_t)
     otasks = []
     for i in range(n):
@@ -199,7 +198,11 @@ def test_me_bi_search_matches_oracle(scene, oracle):
         o.smallWindow, o.halfPel, o.quarterPel, o.bitDepth = i % 3 == 0, 1, i % 4 != 1, scene.bd
         fill_bi(tasks[i], o, scene.pics[0], scene.pics[1], scene.pics[2])
         otasks.append(o)
-    got = scene.ctx.me_bi_search(tasks)
+    return tasks, otasks
+
+
+def check_bi_results(oracle, scene, otasks, got):
+    """every field of every result against orc_me_bi_search; returns how many vectors the fractional rounds moved"""
     src, ref, other = (scene.host[k][0] for k in range(3))
     base = (PAD * src.shape[1] + PAD) * src.itemsize
     moved = 0
@@ -216,6 +219,14 @@ def test_me_bi_search_matches_oracle(scene, oracle):
         assert int(g["mvpFlag"]) == r.mvpFlag and int(g["cost"]) == r.cost, key
         assert int(g["nSad"]) == r.nSad, key
         moved += tuple(r.mv) != tuple(r.mvInteger)
+    return moved
+
+
+def test_me_bi_search_matches_oracle(scene, oracle):
+    rng = np.random.default_rng(77)
+    tasks, otasks = make_bi_tasks(rng, scene, 300)
+    got = scene.ctx.me_bi_search(tasks)
+    moved = check_bi_results(oracle, scene, otasks, got)
     assert moved > 30, moved
 
 

@@ -30,7 +30,19 @@ extern "C" void emu_me_large(const HvbPlane *planes, const hvb_me_task *tasks, i
     else emuLaunch(grid, kWarps * 32, [&] { meSearchKernel<uint16_t>(planes, tasks, n, out, bitDepth); });
 }
 '''
+ENTRY_BI = r'''
+extern "C" void emu_me_bi(const HvbPlane *planes, const hvb_me_bi_task *tasks, int n, hvb_me_bi_result *out, int bitDepth, int bps, int grid)
+{
+    if (bps == 1) emuLaunch(grid, kWarps * 32, [&] { meBiSearchKernel<uint8_t>(planes, tasks, n, out, bitDepth); });
+    else emuLaunch(grid, kWarps * 32, [&] { meBiSearchKernel<uint16_t>(planes, tasks, n, out, bitDepth); });
+}
+'''
 ENTRY_SUBPEL = r'''
+extern "C" void emu_me_bi_subpel(const HvbPlane *planes, const hvb_me_bi_task *tasks, int n, hvb_me_bi_result *out, int bitDepth, int bps, int grid)
+{
+    if (bps == 1) emuLaunch(grid, kWarps * 32, [&] { meSubpelKernel<uint8_t, true>(planes, tasks, n, out, bitDepth); });
+    else emuLaunch(grid, kWarps * 32, [&] { meSubpelKernel<uint16_t, true>(planes, tasks, n, out, bitDepth); });
+}
 extern "C" void emu_me_subpel(const HvbPlane *planes, const hvb_me_task *tasks, int n, hvb_me_result *out, int bitDepth, int bps, int grid)
 {
     if (bps == 1) emuLaunch(grid, kWarps * 32, [&] { meSubpelKernel<uint8_t, false>(planes, tasks, n, out, bitDepth); });
@@ -43,7 +55,7 @@ extern "C" void emu_me_subpel(const HvbPlane *planes, const hvb_me_task *tasks, 
 def kernels(tmp_path_factory):
     d = tmp_path_factory.mktemp("emu_me")
     libs = []
-    for name, entry in (("hvb_me_small.cu", ENTRY_SMALL), ("hvb_me.cu", ENTRY_LARGE), ("hvb_me_subpel.cu", ENTRY_SUBPEL)):
+    for name, entry in (("hvb_me_small.cu", ENTRY_SMALL), ("hvb_me.cu", ENTRY_LARGE + ENTRY_BI), ("hvb_me_subpel.cu", ENTRY_SUBPEL)):
         sub = d / name.replace(".", "_")
         sub.mkdir()
         libs.append(host_emu_warp.build(sub, name, entry))
@@ -62,16 +74,35 @@ def host_scene(bps, bit_depth):
     return SimpleNamespace(bps=bps, bd=bit_depth, pics=[0, 1, 2], host=host)
 
 
-@pytest.mark.parametrize("bps,bit_depth", [(1, 8), (2, 10)])
-def test_me_search_kernels_on_cpu_match_oracle(kernels, oracle, bps, bit_depth):
-    small, large, subpel = kernels
-    scene = host_scene(bps, bit_depth)
+def plane_table(scene):
     table = (Plane * 9)()
     for i, pic in enumerate(scene.host):
         for c, a in enumerate(pic):
             pad = PAD if c == 0 else PAD // 2
             table[3 * i + c] = Plane(a.ctypes.data + (pad * a.shape[1] + pad) * a.itemsize, a.shape[1], a.shape[1] - 2 * pad,
                                      a.shape[0] - 2 * pad, pad, 0)
+    return table
+
+
+@pytest.mark.parametrize("bps,bit_depth", [(1, 8), (2, 10)])
+def test_me_bi_search_kernels_on_cpu_match_oracle(kernels, oracle, bps, bit_depth):
+    """searchMotionBi: the integer grid (meBiSearchKernel), then both fractional rounds (meSubpelKernel<Sample, true>)"""
+    _, large, subpel = kernels
+    scene = host_scene(bps, bit_depth)
+    table = plane_table(scene)
+    tasks, otasks = gpu_me.make_bi_tasks(np.random.default_rng(77), scene, 69)
+    got = np.zeros(tasks.size, hvb.me_bi_result_t)
+    t_ptr, o_ptr = C.c_void_p(tasks.ctypes.data), C.c_void_p(got.ctypes.data)
+    large.emu_me_bi(table, t_ptr, tasks.size, o_ptr, bit_depth, bps, 2)
+    subpel.emu_me_bi_subpel(table, t_ptr, tasks.size, o_ptr, bit_depth, bps, 2)
+    assert gpu_me.check_bi_results(oracle, scene, otasks, got) > 5
+
+
+@pytest.mark.parametrize("bps,bit_depth", [(1, 8), (2, 10)])
+def test_me_search_kernels_on_cpu_match_oracle(kernels, oracle, bps, bit_depth):
+    small, large, subpel = kernels
+    scene = host_scene(bps, bit_depth)
+    table = plane_table(scene)
     rng = np.random.default_rng(51)
     n = 92
     tasks = np.zeros(n, hvb.me_task_t)
