@@ -145,6 +145,9 @@ static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pre
 static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 static inline int atomicAdd(int *p, int v) { const int old = *p; *p += v; return old; }
 
+// shared-memory addresses of the asynchronous-copy wrappers are offsets into the block's arena
+static inline size_t __cvta_generic_to_shared(const void *p) { return (size_t)(static_cast<const unsigned char *>(p) - emu::sharedArena); }
+
 // ---- scalar intrinsics ----------------------------------------------------------------------------------------------------
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) { s &= 31; return s ? (lo >> s) | (hi << (32 - s)) : lo; }
@@ -251,10 +254,11 @@ def header_text(name: str) -> str:
 
 
 def build(tmp_dir: Path, cu_file: str, entry: str, strip: tuple = (), use_unit_header: bool = True, mma_wrappers: dict | None = None,
-          namespaces: int = 1, extra_headers: tuple = ()) -> C.CDLL:
+          namespaces: int = 1, extra_headers: tuple = (), replace: dict | None = None) -> C.CDLL:
     """strip: starts of the host-side definitions inside the kernel file's anonymous namespace (launch helpers with <<< >>>);
     mma_wrappers: the file's own inline-PTX mma wrappers, name -> True when the B operand is signed (s8.s8), replaced by
-    the emulated product; namespaces: how many leading anonymous namespaces of the file hold the kernels"""
+    the emulated product; namespaces: how many leading anonymous namespaces of the file hold the kernels; replace: other
+    inline-PTX wrappers of the file, start of the definition -> emulated definition"""
     if not (CUDA_INC / "cuda_runtime.h").exists():
         pytest.skip("CUDA headers not found")
     src = (CSRC / cu_file).read_text()
@@ -265,6 +269,9 @@ def build(tmp_dir: Path, cu_file: str, entry: str, strip: tuple = (), use_unit_h
     for signature in strip:
         kernels = _strip_function(kernels, signature)
     injected = ""
+    for signature, replacement in (replace or {}).items():  # further inline-PTX wrappers: definition start -> emulated definition
+        kernels = _strip_function(kernels, signature)
+        injected += replacement + "\n"
     for name, signed_b in (mma_wrappers or {}).items():
         kernels = _strip_function(kernels, f"__device__ __forceinline__ void {name}(")
         injected += (f"static inline void {name}(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)"

@@ -1,0 +1,86 @@
+"""The batched metric kernels' own source (csrc/hvb_metrics.cu: SAD, SAD4, SSD, and the streaming SATD with its cp.async
+staging queue and tensor-core products), executed on the CPU by the warp-level emulator (tests/host_emu_warp.py; the three
+asynchronous-copy wrappers become synchronous copies into the block's shared arena), against the oracle: all PU sizes,
+candidates reaching into the padding at arbitrary alignment, luma and chroma, 8 and 10 bit -- tests/test_gpu_metrics.py's
+comparisons in the CPU-only suite."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import host_emu_warp
+import test_gpu_metrics as gm
+from test_host_emulated_loopfilter import Plane
+from turingcodec_b200 import hvb, synth
+
+ENTRY = r'''
+extern "C" void emu_metric(int which, const HvbPlane *planes, const hvb_metric_task *tasks, int n, int32_t *out, int bps, int grid)
+{
+    if (which == 0)
+    {
+        if (bps == 1) emuLaunch(grid, kWarpsPerBlock * 32, [&] { sadKernel<uint8_t>(planes, tasks, n, out); });
+        else emuLaunch(grid, kWarpsPerBlock * 32, [&] { sadKernel<uint16_t>(planes, tasks, n, out); });
+    }
+    else if (which == 1)
+    {
+        if (bps == 1) emuLaunch(grid, kWarpsPerBlock * 32, [&] { ssdKernel<uint8_t>(planes, tasks, n, reinterpret_cast<uint32_t *>(out)); });
+        else emuLaunch(grid, kWarpsPerBlock * 32, [&] { ssdKernel<uint16_t>(planes, tasks, n, reinterpret_cast<uint32_t *>(out)); });
+    }
+    else
+    {
+        // hvb_satd_batch: the tensor-core kernel for 8-bit blocks tiled 8x8, then the register-tile kernel for what it left
+        int leftover = 0;
+        if (bps == 1)
+        {
+            emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdMmaKernel<2>(planes, tasks, n, out, &leftover); });
+            emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdKernel<uint8_t>(planes, tasks, n, out, &leftover); });
+        }
+        else emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdKernel<uint16_t>(planes, tasks, n, out, nullptr); });
+    }
+}
+'''
+REPLACE = {
+    "__device__ __forceinline__ void cpAsync8(": "static inline void cpAsync8(uint32_t dst, const void *src) { memcpy(emu::sharedArena + dst, src, 8); }",
+    "__device__ __forceinline__ void cpAsyncCommit(": "static inline void cpAsyncCommit() {}",
+    "template <int PENDING>\n__device__ __forceinline__ void cpAsyncWait(": "template <int PENDING> static inline void cpAsyncWait() {}",
+}
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    return host_emu_warp.build(tmp_path_factory.mktemp("emu_metrics"), "hvb_metrics.cu", ENTRY, strip=("template <typename Task>\nint gridFor(",),
+                               extra_headers=("hvb_satd.cuh",), namespaces=2, replace=REPLACE)
+
+
+@pytest.mark.parametrize("bps,bit_depth", [(1, 8), (2, 10)])
+@pytest.mark.parametrize("chroma", [False, True])
+def test_metric_kernels_on_cpu_match_oracle(emu, oracle, bps, bit_depth, chroma):
+    dtype = np.uint8 if bps == 1 else np.uint16
+    frames = [[p.astype(dtype) for p in synth.frame(i, gm.W, gm.H, bit_depth)] for i in range(2)]
+    if bps == 2:
+        frames[1][0][::7, ::5] = 1023
+    host = [[np.ascontiguousarray(gm.padded(pl, gm.PAD if c == 0 else gm.PAD // 2)) for c, pl in enumerate(f)] for f in frames]
+    table = (Plane * 6)()
+    for i, pic in enumerate(host):
+        for c, a in enumerate(pic):
+            pad = gm.PAD if c == 0 else gm.PAD // 2
+            table[3 * i + c] = Plane(a.ctypes.data + (pad * a.shape[1] + pad) * a.itemsize, a.shape[1], a.shape[1] - 2 * pad,
+                                     a.shape[0] - 2 * pad, pad, 0)
+    rng = np.random.default_rng(5 + chroma)
+    t = gm.make_tasks(rng, 150, chroma)
+    t["b"]["x"][::5] = t["a"]["x"][::5]  # some co-located, aligned pairs: the 128-bit SAD / SSD path and the cp.async SATD path
+    for which, name in enumerate(("sad", "ssd", "satd")):
+        got = np.full(t.size, -1, np.int32)
+        emu.emu_metric(which, table, C.c_void_p(t.ctypes.data), t.size, C.c_void_p(got.ctypes.data), bps, 2)
+        for i in range(t.size):
+            c = int(t[i]["a"]["cIdx"])
+            a, oa, sa = gm.view(host, 0, c, t[i]["a"]["x"], t[i]["a"]["y"])
+            b, ob, sb = gm.view(host, 1, c, t[i]["b"]["x"], t[i]["b"]["y"])
+            w, h = int(t[i]["w"]), int(t[i]["h"])
+            if name == "sad":
+                want = oracle.sad(a, oa, sa, b, ob, sb, w, h)
+            elif name == "ssd":
+                want = oracle.ssd(a, oa, sa, b, ob, sb, w, h)
+            else:
+                want = oracle.measure_satd(a, oa, sa, b, ob, sb, w, h)
+            assert int(got[i]) & 0xffffffff == int(want) & 0xffffffff, (name, i, w, h, c)

@@ -274,6 +274,15 @@ __device__ __forceinline__ void cpAsync8(uint32_t dst, const void *src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cpAsyncCommit()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int PENDING>
+__device__ __forceinline__ void cpAsyncWait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+}
 
 // 8-bit blocks whose sides are multiples of 8 (the other blocks of the batch belong to satdKernel)
 template <int STAGES>
@@ -326,7 +335,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
                 satdCursorOpen(issue, planes, tasks, n, step, leftover);
             }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        cpAsyncCommit();
     };
 
     int qt[STAGES - 1], qb[STAGES - 1]; // the groups in flight, oldest first
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
     {
         int nt, nb;
         issueGroup(slot == 0 ? STAGES - 1 : slot - 1, nt, nb);
-        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+        cpAsyncWait<STAGES - 1>();
         const uint2 *src = mine + slot * 128;
         const uint2 r0 = src[0], r1 = src[32], r2 = src[64], r3 = src[96];
         const uint32_t bx[4] = {r0.x, r1.x, r2.x, r3.x}, by[4] = {r0.y, r1.y, r2.y, r3.y};
@@ -377,7 +386,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
         qb[STAGES - 2] = nb;
         slot = slot == STAGES - 1 ? 0 : slot + 1;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    cpAsyncWait<0>();
 }
 
 // one register-resident Hadamard tile per lane: 16-bit samples, and the 4x4 / 2x2 tiled blocks of 8-bit batches
