@@ -32,6 +32,7 @@ using namespace hvb_unit;
 
 constexpr int kWarps = 8;
 constexpr int kMaxW = 64; // columns of a strip: the luma PU width, or Cb | Cr side by side
+constexpr int kGrab = 4;  // PUs a warp takes from the cursor at a time
 
 // 4-tap chroma filters (havoc/pred_inter.cpp:52-69) packed as s8x4 words
 __device__ __constant__ uint32_t kChromaWords[8] = {0x00004000u, 0xfe0a3afeu, 0xfe1036fcu, 0xfc1c2efau,
@@ -361,12 +362,18 @@ __global__ void __launch_bounds__(kWarps * 32, 4)
     WarpSmem<Sample> &s = reinterpret_cast<WarpSmem<Sample> *>(smemPuCost)[warp];
     const HadamardA A(lane);
     const Depth D(sizeof(Sample) == 1 ? 8 : bitDepth);
+    // a warp takes kGrab consecutive PUs per visit to the cursor (the atomic and its broadcast were 10 % of the stall samples
+    // at one PU per visit, profiles/r01g_hot_lines.txt; consecutive PUs of a task list are of similar size)
+    int i = 0, end = 0;
     for (;;)
     {
-        int i = 0;
-        if (lane == 0) i = atomicAdd(cursor, 1);
-        i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= n) break;
+        if (i == end)
+        {
+            if (lane == 0) i = atomicAdd(cursor, kGrab);
+            i = __shfl_sync(0xffffffffu, i, 0);
+            if (i >= n) break;
+            end = min(i + kGrab, n);
+        }
         const hvb_pu_cost_task t = tasks[i];
         int bx0 = 0, bx1 = 0, by0 = 0, by1 = 0;
         if (t.ref_pic[0] >= 0)
@@ -403,6 +410,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4)
             out[3 * i + 1] = scb;
             out[3 * i + 2] = scr;
         }
+        ++i;
     }
 }
 
