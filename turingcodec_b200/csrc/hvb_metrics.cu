@@ -350,19 +350,24 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
         const uint2 *src = mine + slot * 128;
         const uint2 r0 = src[0], r1 = src[32], r2 = src[64], r3 = src[96];
         const uint32_t bx[4] = {r0.x, r1.x, r2.x, r3.x}, by[4] = {r0.y, r1.y, r2.y, r3.y};
+        // the four m-tiles' products advance together, k-step by k-step: four independent accumulator chains, so that an
+        // IMMA is followed by three that do not wait for it (the ncu capture of the mt-outer order showed `wait` on the
+        // dependent chains as the top stall, profiles/r01g_summary.txt)
+        int acc[4][4] = {};
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+            {
+                const uint32_t neg = ((((mt >> 1) & ks) ^ (ks >> 1)) & 1) ? 0xfefefefeu : 0u;
+                imma16832(acc[mt], A.x[mt & 1][0] ^ neg, A.x[mt & 1][1] ^ neg, A.x[mt & 1][2] ^ neg, A.x[mt & 1][3] ^ neg, bx[ks], by[ks]);
+            }
         int s0 = 0, s1 = 0;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
         {
-            int acc[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-            {
-                const uint32_t neg = ((((mt >> 1) & ks) ^ (ks >> 1)) & 1) ? 0xfefefefeu : 0u;
-                imma16832(acc, A.x[mt & 1][0] ^ neg, A.x[mt & 1][1] ^ neg, A.x[mt & 1][2] ^ neg, A.x[mt & 1][3] ^ neg, bx[ks], by[ks]);
-            }
-            s0 = __sad(acc[0], 0, __sad(acc[2], 0, (unsigned)s0));
-            s1 = __sad(acc[1], 0, __sad(acc[3], 0, (unsigned)s1));
+            s0 = __sad(acc[mt][0], 0, __sad(acc[mt][2], 0, (unsigned)s0));
+            s1 = __sad(acc[mt][1], 0, __sad(acc[mt][3], 0, (unsigned)s1));
         }
         // column 2t + (g & 1) of the group, summed over the 8 lanes that share t
         int sum = (g & 1) ? s1 : s0;
