@@ -182,7 +182,7 @@ def kernels_of(cu_file: str) -> C.CDLL:
         d = Path(_TMP.name) / cu_file.replace(".", "_")
         d.mkdir()
         spec = dict(ENTRIES[cu_file])
-        _LIBS[cu_file] = host_emu_warp.build(d, cu_file, spec.pop("entry"), **spec)
+        _LIBS[cu_file] = host_emu_warp.build(d, cu_file, spec.pop("entry"), check_alignment=True, **spec)
     return _LIBS[cu_file]
 
 
@@ -196,25 +196,34 @@ class EmuContext:
     def __init__(self, device: int = 0, bytes_per_sample: int = 1, bit_depth: int = 8):
         self.bps, self.bit_depth = bytes_per_sample, bit_depth
         self.sample_dtype = np.uint8 if bytes_per_sample == 1 else np.uint16
-        self.pictures: list = []  # [Y, Cb, Cr] padded arrays, or None
-        self.pads: list = []
+        self.pictures: list = []  # per picture: three plane records (see picture_create)
         self.sample_pool = np.zeros(0, self.sample_dtype)
         self.coeff_pool = np.zeros(0, np.int16)
         self.rdoq_ctx = np.zeros(0, hvb.rdoq_ctx_t)
         self.launch_count = 0
 
     # -- pictures ----------------------------------------------------------------------------
+    # laid out as hvb_picture_create does (csrc/hvb_context.cu): row pitch a multiple of 256 bytes, sample (0,0) of every
+    # row 256-byte aligned, `pad` valid samples on every side plus slack -- the kernels' vector accesses rely on it, and the
+    # emulation libraries are built with -fsanitize=alignment so that a misaligned one aborts here as it would fault there
     def picture_create(self, width: int, height: int, pad: int = 96) -> int:
-        planes = [np.zeros((height + 2 * pad, width + 2 * pad), self.sample_dtype)] + \
-                 [np.zeros((height // 2 + pad, width // 2 + pad), self.sample_dtype) for _ in range(2)]
+        planes = []
+        for c in range(3):
+            w, h, pd = (width, height, pad) if c == 0 else (width // 2, height // 2, pad // 2)
+            unit = 256 // self.bps
+            pad_left = -(-pd // unit) * unit
+            stride = -(-(pad_left + w + pd + 16) // unit) * unit
+            rows = h + 2 * pd + 2
+            raw = np.zeros(stride * rows * self.bps + 256, np.uint8)
+            off = (-raw.ctypes.data) % 256
+            full = raw[off:off + stride * rows * self.bps].view(self.sample_dtype).reshape(rows, stride)
+            planes.append(dict(full=full, ox=pad_left, oy=pd, w=w, h=h, pad=pd, keep=raw))
         self.pictures.append(planes)
-        self.pads.append(pad)
         return len(self.pictures) - 1
 
     def _visible(self, pic, c):
-        pad = self.pads[pic] if c == 0 else self.pads[pic] // 2
-        a = self.pictures[pic][c]
-        return a[pad:a.shape[0] - pad, pad:a.shape[1] - pad]
+        p = self.pictures[pic][c]
+        return p["full"][p["oy"]:p["oy"] + p["h"], p["ox"]:p["ox"] + p["w"]]
 
     def picture_upload(self, pic: int, c_idx: int, plane: np.ndarray, y0: int = 0, rows=None):
         rows = plane.shape[0] - y0 if rows is None else rows
@@ -225,9 +234,16 @@ class EmuContext:
 
     def picture_pad(self, pic: int):
         for c in range(3):
-            pad = self.pads[pic] if c == 0 else self.pads[pic] // 2
-            if pad:
-                self.pictures[pic][c][...] = np.pad(self._visible(pic, c), pad, mode="edge")
+            p = self.pictures[pic][c]
+            if p["pad"]:
+                full = p["full"]
+                full[...] = np.pad(self._visible(pic, c), ((p["oy"], full.shape[0] - p["oy"] - p["h"]), (p["ox"], full.shape[1] - p["ox"] - p["w"])),
+                                   mode="edge")
+
+    def padded(self, pic: int, c_idx: int) -> np.ndarray:
+        """a plain copy of the plane with exactly `pad` samples on every side (what np.pad(visible, pad, 'edge') gives after picture_pad)"""
+        p = self.pictures[pic][c_idx]
+        return np.ascontiguousarray(p["full"][p["oy"] - p["pad"]:p["oy"] + p["h"] + p["pad"], p["ox"] - p["pad"]:p["ox"] + p["w"] + p["pad"]])
 
     def upload_yuv(self, pic: int, y, u, v, pad: bool = True):
         for c, p in enumerate((y, u, v)):
@@ -238,18 +254,28 @@ class EmuContext:
     def _planes(self):
         table = (Plane * (3 * max(len(self.pictures), 1)))()
         for i, pic in enumerate(self.pictures):
-            for c, a in enumerate(pic):
-                pad = self.pads[i] if c == 0 else self.pads[i] // 2
-                table[3 * i + c] = Plane(a.ctypes.data + (pad * a.shape[1] + pad) * a.itemsize, a.shape[1], a.shape[1] - 2 * pad,
-                                         a.shape[0] - 2 * pad, pad, 0)
+            for c, p in enumerate(pic):
+                full = p["full"]
+                table[3 * i + c] = Plane(full.ctypes.data + (p["oy"] * full.shape[1] + p["ox"]) * full.itemsize, full.shape[1], p["w"], p["h"],
+                                         p["pad"], 0)
         return table
 
     # -- pools -------------------------------------------------------------------------------
     @staticmethod
-    def _store(pool, data, offset, dtype):
+    def _aligned(count, dtype):
+        """`count` zeroed elements starting on a 256-byte boundary, as cudaMalloc returns them"""
+        itemsize = np.dtype(dtype).itemsize
+        raw = np.zeros(count * itemsize + 256, np.uint8)
+        off = (-raw.ctypes.data) % 256
+        return raw[off:off + count * itemsize].view(dtype)
+
+    @classmethod
+    def _store(cls, pool, data, offset, dtype):
         data = np.ascontiguousarray(data, dtype=dtype).reshape(-1)
         if pool.size < offset + data.size:
-            pool = np.concatenate([pool, np.zeros(offset + data.size - pool.size, dtype)])
+            grown = cls._aligned(offset + data.size, dtype)
+            grown[:pool.size] = pool
+            pool = grown
         pool[offset:offset + data.size] = data
         return pool
 
@@ -265,12 +291,17 @@ class EmuContext:
     def rdoq_contexts_upload(self, snapshots, first: int = 0):
         snapshots = np.ascontiguousarray(snapshots, dtype=hvb.rdoq_ctx_t).reshape(-1)
         if self.rdoq_ctx.size < first + snapshots.size:
-            self.rdoq_ctx = np.concatenate([self.rdoq_ctx, np.zeros(first + snapshots.size - self.rdoq_ctx.size, hvb.rdoq_ctx_t)])
+            grown = self._aligned(first + snapshots.size, hvb.rdoq_ctx_t)
+            grown[:self.rdoq_ctx.size] = self.rdoq_ctx
+            self.rdoq_ctx = grown
         self.rdoq_ctx[first:first + snapshots.size] = snapshots
 
     # -- batched calls -----------------------------------------------------------------------
     def _tasks(self, tasks, dtype):
-        return np.ascontiguousarray(tasks, dtype=dtype).reshape(-1)
+        tasks = np.ascontiguousarray(tasks, dtype=dtype).reshape(-1)
+        staged = self._aligned(max(tasks.size, 1), dtype)  # the staging buffer of hvbStageIn is 256-byte aligned
+        staged[:tasks.size] = tasks
+        return staged[:tasks.size]
 
     def _metric(self, fn, tasks, dtype, out_dtype, per_task):
         t = self._tasks(tasks, dtype)
@@ -396,7 +427,7 @@ class EmuScene:
             pic = self.ctx.picture_create(width, height, pad)
             self.ctx.upload_yuv(pic, *f)
             self.pics.append(pic)
-            self.host.append([a.copy() for a in self.ctx.pictures[pic]])
+            self.host.append([self.ctx.padded(pic, c) for c in range(3)])
         self.scratch = [self.ctx.picture_create(width, height, pad) for _ in range(2)]
 
     def view(self, pic_index: int, c_idx: int, x: int, y: int):

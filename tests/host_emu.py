@@ -52,6 +52,9 @@ def build(tmp_dir: Path, cu_file: str, structs: list[str], entry: str) -> C.CDLL
     internal = (CSRC / "hvb_internal.cuh").read_text()
     text = PRELUDE.replace("@STRUCTS@", "\n".join(struct_text(internal, s) for s in structs)) + kernels + entry
     (tmp_dir / "emu.cpp").write_text(text)
-    subprocess.run(["g++", "-O1", "-fPIC", "-shared", "-w", "-std=c++17", f"-I{CUDA_INC}", f"-I{ROOT / 'include'}", str(tmp_dir / "emu.cpp"),
-                    "-o", str(tmp_dir / "emu.so")], check=True, capture_output=True)
+    # -fsanitize=alignment: a misaligned vector access, which x86 tolerates, aborts here as it would fault on the device (the
+    # tests give the kernels buffers aligned the way the device's are)
+    subprocess.run(["g++", "-O1", "-fPIC", "-shared", "-w", "-std=c++17", "-fsanitize=alignment", "-fno-sanitize-recover=alignment",
+                    "-static-libubsan", f"-I{CUDA_INC}", f"-I{ROOT / 'include'}", str(tmp_dir / "emu.cpp"), "-o", str(tmp_dir / "emu.so")],
+                   check=True, capture_output=True)
     return C.CDLL(str(tmp_dir / "emu.so"))

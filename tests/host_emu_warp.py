@@ -254,11 +254,13 @@ def header_text(name: str) -> str:
 
 
 def build(tmp_dir: Path, cu_file: str, entry: str, strip: tuple = (), use_unit_header: bool = True, mma_wrappers: dict | None = None,
-          namespaces: int = 1, extra_headers: tuple = (), replace: dict | None = None) -> C.CDLL:
+          namespaces: int = 1, extra_headers: tuple = (), replace: dict | None = None, check_alignment: bool = False) -> C.CDLL:
     """strip: starts of the host-side definitions inside the kernel file's anonymous namespace (launch helpers with <<< >>>);
     mma_wrappers: the file's own inline-PTX mma wrappers, name -> True when the B operand is signed (s8.s8), replaced by
     the emulated product; namespaces: how many leading anonymous namespaces of the file hold the kernels; replace: other
-    inline-PTX wrappers of the file, start of the definition -> emulated definition"""
+    inline-PTX wrappers of the file, start of the definition -> emulated definition; check_alignment: build with
+    -fsanitize=alignment (a misaligned vector access, which x86 would tolerate, aborts the test as it would fault on the
+    device) -- for callers whose buffers are aligned the way the device's are"""
     if not (CUDA_INC / "cuda_runtime.h").exists():
         pytest.skip("CUDA headers not found")
     src = (CSRC / cu_file).read_text()
@@ -284,7 +286,8 @@ def build(tmp_dir: Path, cu_file: str, entry: str, strip: tuple = (), use_unit_h
     body = re.sub(r"extern\s+__shared__\s+(__align__\(\d+\)\s+)?(\w[\w\s]*?)\s+(\w+)\[\];", r"\2 *const \3 = reinterpret_cast<\2 *>(emu::sharedArena);", body)
     body = body.replace("__shared__", "static")
     (tmp_dir / "emu_warp.cpp").write_text(PRELUDE + body + entry)
-    res = subprocess.run(["g++", "-O1", "-fPIC", "-shared", "-w", "-std=c++17", f"-I{CUDA_INC}", f"-I{ROOT / 'include'}",
+    sanitize = ["-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-static-libubsan"] if check_alignment else []
+    res = subprocess.run(["g++", "-O1", "-fPIC", "-shared", "-w", "-std=c++17", *sanitize, f"-I{CUDA_INC}", f"-I{ROOT / 'include'}",
                           str(tmp_dir / "emu_warp.cpp"), "-o", str(tmp_dir / "emu_warp.so")], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-3000:]
     return C.CDLL(str(tmp_dir / "emu_warp.so"))
