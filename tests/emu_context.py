@@ -169,6 +169,40 @@ extern "C" void emu_pu_cost(const HvbPlane *planes, const hvb_pu_cost_task *task
 '''),
 }
 
+ENTRIES["hvb_loopfilter.cu"] = dict(
+    use_unit_header=False, loop_info=True,
+    entry=r'''
+extern "C" void emu_deblock(const HvbPlane *planes, const HvbLoopInfo *info, const hvb_deblock_task *tasks, int n, int bitDepth, int bps, int grid)
+{ ''' + _both("emuLaunch(grid, 256, [&] { deblockKernel<Sample>(planes, info, tasks, n, bitDepth); });") + r''' }
+extern "C" void emu_sao(const HvbPlane *planes, const HvbLoopInfo *info, const hvb_sao_task *tasks, int n, int bitDepth, int bps, int grid)
+{ ''' + _both("emuLaunch(grid, 256, [&] { saoKernel<Sample>(planes, info, tasks, n, bitDepth); });") + r''' }
+extern "C" void emu_sao_stats(const HvbPlane *planes, const hvb_sao_stats_task *tasks, int n, hvb_sao_stats *out, int bitDepth, int bps, int grid)
+{ ''' + _both("emuLaunch(std::min(n, grid), 256, [&] { saoStatsKernel<Sample>(planes, tasks, n, out, bitDepth); });") + r''' }
+''')
+ENTRIES["hvb_codeddata.cu"] = dict(
+    use_unit_header=False,
+    entry=r'''
+extern "C" void emu_coded_residual(int16_t *pool, const hvb_coded_residual_task *tasks, int n, int recordsBase, int capacityWords,
+                                   hvb_coded_residual *out, int grid)
+{
+    int cursor = 0;
+    emuLaunch(grid, 128, [&] { codedResidualKernel(pool, reinterpret_cast<uint16_t *>(pool), tasks, n, recordsBase, capacityWords, out, &cursor); });
+    emuLaunch(1, 32, [&] { codedResidualTotalKernel(out, n, recordsBase, capacityWords, &cursor); });
+}
+''')
+ENTRIES["hvb_preanalysis.cu"] = dict(
+    use_unit_header=False,
+    entry=r'''
+extern "C" void emu_intra_complexity(const HvbPlane *planes, const hvb_intra_complexity_task *tasks, int n, int32_t *out, int bps, int grid)
+{ ''' + _both("emuLaunch(grid, 128, [&] { intraComplexityKernel<Sample>(planes, tasks, n, out); });") + r''' }
+''')
+
+
+class LoopInfo(C.Structure):
+    _fields_ = [("blocks", C.c_void_p), ("ctus", C.c_void_p), ("sao", C.c_void_p), ("blockStride", C.c_int32), ("blockRows", C.c_int32),
+                ("widthInCtbs", C.c_int32), ("ctbLog2", C.c_int32), ("saoCount", C.c_int32), ("reserved", C.c_int32)]
+
+
 _LIBS: dict = {}
 _TMP = None
 
@@ -182,6 +216,10 @@ def kernels_of(cu_file: str) -> C.CDLL:
         d = Path(_TMP.name) / cu_file.replace(".", "_")
         d.mkdir()
         spec = dict(ENTRIES[cu_file])
+        if spec.pop("loop_info", False):  # the kernels of this file also see HvbLoopInfo (csrc/hvb_internal.cuh)
+            internal = (host_emu_warp.CSRC / "hvb_internal.cuh").read_text()
+            start = internal.index("struct HvbLoopInfo\n{")
+            spec["prelude_structs"] = internal[start:internal.index("};", start) + 2]
         _LIBS[cu_file] = host_emu_warp.build(d, cu_file, spec.pop("entry"), check_alignment=True, **spec)
     return _LIBS[cu_file]
 
@@ -200,6 +238,7 @@ class EmuContext:
         self.sample_pool = np.zeros(0, self.sample_dtype)
         self.coeff_pool = np.zeros(0, np.int16)
         self.rdoq_ctx = np.zeros(0, hvb.rdoq_ctx_t)
+        self.loop_info: dict = {}
         self.launch_count = 0
 
     # -- pictures ----------------------------------------------------------------------------
@@ -402,6 +441,66 @@ class EmuContext:
         t = self._tasks(tasks, hvb.pu_cost_task_t)
         out = np.zeros((t.size, 3), np.int32)
         kernels_of("hvb_pu_cost.cu").emu_pu_cost(self._planes(), _ptr(t), t.size, _ptr(out), self.bit_depth, self.bps, GRID)
+        return out
+
+    # -- in-loop filters, coded data, pre-analysis ---------------------------------
+    def deblock_info_upload(self, pic, blocks, ctus, pic_width_in_ctbs, pic_height_in_ctbs, ctb_log2):
+        blocks = np.ascontiguousarray(blocks, dtype=hvb.deblock_block_t)
+        b = self._aligned(blocks.size, hvb.deblock_block_t)
+        b[:] = blocks.reshape(-1)
+        ctus = np.ascontiguousarray(ctus, dtype=hvb.deblock_ctu_t).reshape(-1)
+        c = self._aligned(ctus.size, hvb.deblock_ctu_t)
+        c[:] = ctus
+        info = self.loop_info.setdefault(pic, {})
+        info.update(blocks=b, ctus=c, blockStride=blocks.shape[1], blockRows=blocks.shape[0], widthInCtbs=pic_width_in_ctbs, ctbLog2=ctb_log2)
+
+    def sao_info_upload(self, pic, ctus):
+        assert pic in self.loop_info and "blocks" in self.loop_info[pic], "hvb_sao_info_upload before hvb_deblock_info_upload"
+        ctus = np.ascontiguousarray(ctus, dtype=hvb.sao_ctu_t).reshape(-1)
+        rec = self._aligned(ctus.size, hvb.sao_ctu_t)
+        rec[:] = ctus
+        self.loop_info[pic].update(sao=rec)
+
+    def _loop_table(self):
+        table = (LoopInfo * max(len(self.pictures), 1))()
+        for pic, info in self.loop_info.items():
+            sao = info.get("sao")
+            table[pic] = LoopInfo(info["blocks"].ctypes.data, info["ctus"].ctypes.data, sao.ctypes.data if sao is not None else None,
+                                  info["blockStride"], info["blockRows"], info["widthInCtbs"], info["ctbLog2"], sao.size if sao is not None else 0, 0)
+        return table
+
+    def deblock(self, tasks, **_):
+        t = self._tasks(tasks, hvb.deblock_task_t)
+        kernels_of("hvb_loopfilter.cu").emu_deblock(self._planes(), self._loop_table(), _ptr(t), t.size, self.bit_depth, self.bps, GRID)
+
+    def sao(self, tasks, **_):
+        t = self._tasks(tasks, hvb.sao_task_t)
+        kernels_of("hvb_loopfilter.cu").emu_sao(self._planes(), self._loop_table(), _ptr(t), t.size, self.bit_depth, self.bps, GRID)
+
+    def sao_stats(self, tasks, **_):
+        t = self._tasks(tasks, hvb.sao_stats_task_t)
+        out = np.zeros(t.size, hvb.sao_stats_t)
+        kernels_of("hvb_loopfilter.cu").emu_sao_stats(self._planes(), _ptr(t), t.size, _ptr(out), self.bit_depth, self.bps, GRID)
+        return out
+
+    def picture_copy(self, dst_pic, src_pic):
+        for c in range(3):
+            self.pictures[dst_pic][c]["full"][...] = self.pictures[src_pic][c]["full"]
+
+    def coded_residual(self, tasks, records_base, capacity_words):
+        t = self._tasks(tasks, hvb.coded_residual_task_t)
+        if self.coeff_pool.size < records_base + capacity_words:
+            grown = self._aligned(records_base + capacity_words, np.int16)
+            grown[:self.coeff_pool.size] = self.coeff_pool
+            self.coeff_pool = grown
+        out = np.zeros(t.size + 1, hvb.coded_residual_t)
+        kernels_of("hvb_codeddata.cu").emu_coded_residual(_ptr(self.coeff_pool), _ptr(t), t.size, records_base, capacity_words, _ptr(out), GRID)
+        return out
+
+    def intra_complexity(self, tasks, out_count):
+        t = self._tasks(tasks, hvb.intra_complexity_task_t)
+        out = np.zeros(out_count, np.int32)
+        kernels_of("hvb_preanalysis.cu").emu_intra_complexity(self._planes(), _ptr(t), t.size, _ptr(out), self.bps, GRID)
         return out
 
     def sync(self):

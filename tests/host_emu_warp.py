@@ -254,7 +254,7 @@ def header_text(name: str) -> str:
 
 
 def build(tmp_dir: Path, cu_file: str, entry: str, strip: tuple = (), use_unit_header: bool = True, mma_wrappers: dict | None = None,
-          namespaces: int = 1, extra_headers: tuple = (), replace: dict | None = None, check_alignment: bool = False) -> C.CDLL:
+          namespaces: int = 1, extra_headers: tuple = (), replace: dict | None = None, check_alignment: bool = False, prelude_structs: str = "") -> C.CDLL:
     """strip: starts of the host-side definitions inside the kernel file's anonymous namespace (launch helpers with <<< >>>);
     mma_wrappers: the file's own inline-PTX mma wrappers, name -> True when the B operand is signed (s8.s8), replaced by
     the emulated product; namespaces: how many leading anonymous namespaces of the file hold the kernels; replace: other
@@ -280,7 +280,7 @@ def build(tmp_dir: Path, cu_file: str, entry: str, strip: tuple = (), use_unit_h
                      f" {{ emuMma16832(c, a0, a1, a2, a3, b0, b1, {'true' if signed_b else 'false'}); }}\n")
     assert "<<<" not in kernels, "a host-side launch is left in the kernel text: add it to `strip`"
     assert "asm volatile" not in kernels and "asm(" not in kernels, f"{cu_file} has inline PTX outside the emulated wrappers"
-    body = (device_helpers() + ("\n" + unit_header() if use_unit_header else "") + "\n" + "\n".join(header_text(h) for h in extra_headers)
+    body = (device_helpers() + "\n" + prelude_structs + ("\n" + unit_header() if use_unit_header else "") + "\n" + "\n".join(header_text(h) for h in extra_headers)
             + "\n" + injected + kernels)
     # dynamic shared memory is one block-wide arena; static __shared__ arrays become block-wide statics
     body = re.sub(r"extern\s+__shared__\s+(__align__\(\d+\)\s+)?(\w[\w\s]*?)\s+(\w+)\[\];", r"\2 *const \3 = reinterpret_cast<\2 *>(emu::sharedArena);", body)
