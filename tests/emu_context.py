@@ -44,11 +44,12 @@ extern "C" void emu_ssd(const HvbPlane *planes, const hvb_metric_task *tasks, in
 { ''' + _both("emuLaunch(grid, kWarpsPerBlock * 32, [&] { ssdKernel<Sample>(planes, tasks, n, out); });") + r''' }
 extern "C" void emu_satd(const HvbPlane *planes, const hvb_metric_task *tasks, int n, int32_t *out, int bps, int grid)
 {
-    int leftover = 0;
+    int leftover[3] = {0, 0, 0}; // [0]: blocks for satdKernel, [2]: blocks for satdMmaSmallKernel
     if (bps == 1)
     {
-        emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdMmaKernel<2>(planes, tasks, n, out, &leftover); });
-        emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdKernel<uint8_t>(planes, tasks, n, out, &leftover); });
+        emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdMmaKernel<2>(planes, tasks, n, out, leftover); });
+        emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdMmaSmallKernel(planes, tasks, n, out, leftover); });
+        emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdKernel<uint8_t>(planes, tasks, n, out, leftover); });
     }
     else emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdKernel<uint16_t>(planes, tasks, n, out, nullptr); });
 }

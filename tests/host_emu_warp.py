@@ -130,6 +130,8 @@ static inline int __shfl_sync(unsigned mask, int v, int src) { return (int)emu::
 static inline unsigned __shfl_sync(unsigned mask, unsigned v, int src) { return emu::exchange(mask, v, src); }
 static inline int __shfl_xor_sync(unsigned mask, int v, int m) { return (int)emu::exchange(mask, (uint32_t)v, (emu::current & 31) ^ m); }
 static inline unsigned __shfl_xor_sync(unsigned mask, unsigned v, int m) { return emu::exchange(mask, v, (emu::current & 31) ^ m); }
+static inline int __shfl_up_sync(unsigned mask, int v, unsigned delta) { const int lane = emu::current & 31; const int r = (int)emu::exchange(mask, (uint32_t)v, lane >= (int)delta ? lane - (int)delta : lane); return r; }
+static inline int __shfl_down_sync(unsigned mask, int v, unsigned delta) { const int lane = emu::current & 31; return (int)emu::exchange(mask, (uint32_t)v, lane + (int)delta < 32 ? lane + (int)delta : lane); }
 static inline unsigned __ballot_sync(unsigned mask, int pred)
 {
     emu::WarpState &w = emu::warps[emu::current >> 5];

@@ -241,6 +241,8 @@ __device__ __forceinline__ uint2 loadRow8(const uint8_t *p)
 // 32x32 block is two groups).  Rows that are not 8-byte aligned take the register path (loadRow8) into the same slots.
 // Only the issuing side walks the task array; what the consuming side needs of a group in flight -- its task and its
 // place in the block -- travels in a register queue as deep as the pipeline.
+constexpr int kSmallTiles = 8; // blocks of up to this many 8x8 tiles share tile groups with their neighbours in the task list
+
 struct SatdCursor
 {
     int t, base, tiles, tilesX, sa, sb;
@@ -255,7 +257,9 @@ __device__ __forceinline__ void satdCursorOpen(SatdCursor &c, const HvbPlane *__
     while (c.t < n)
     {
         const hvb_metric_task task = tasks[c.t];
-        if (!((task.w | task.h) & 7))
+        if (!((task.w | task.h) & 7) && (task.w >> 3) * (task.h >> 3) <= kSmallTiles)
+            leftover[2] = 1; // a block for satdMmaSmallKernel
+        else if (!((task.w | task.h) & 7))
         {
             c.a = hvbBlockPtr<uint8_t>(planes, task.a, c.sa);
             c.b = hvbBlockPtr<uint8_t>(planes, task.b, c.sb);
@@ -265,7 +269,8 @@ __device__ __forceinline__ void satdCursorOpen(SatdCursor &c, const HvbPlane *__
             c.base = 0;
             return;
         }
-        *leftover = 1; // a block for satdKernel (every lane stores the same value)
+        else
+            leftover[0] = 1; // a block for satdKernel (every lane stores the same value)
         c.t += step;
     }
 }
@@ -394,6 +399,98 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
     cpAsyncWait<0>();
 }
 
+// ---- small blocks: tile groups filled across consecutive tasks --------------------------------------------------------
+// A block of one to eight tiles (8x8 .. 32x16 / 64x8) would leave most of a group's eight tile slots empty, and a warp per
+// block most of the machine idle (an 8x8 batch ran at 3 % of the HBM bandwidth that way).  Here a warp takes 32 consecutive
+// tasks, lays their tiles end to end (a prefix sum over the lanes) and walks that sequence eight tiles at a time, so a
+// group holds the tiles of up to eight blocks.  Per warp in shared memory: the 32 blocks' addresses, a tile -> block map
+// and the blocks' sums (integer atomics: order-independent).  Blocks of more than kSmallTiles tiles belong to the streaming
+// kernel above, which notes in leftover[2] whether this kernel has anything to do.
+struct SmallDesc
+{
+    const uint8_t *a, *b;
+    int sa, sb, tilesX, first; // first: position of the block's tile 0 in the warp's tile sequence
+};
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
+    satdMmaSmallKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out,
+                       const int *__restrict__ leftover)
+{
+    if (leftover[2] == 0) return;
+    __shared__ SmallDesc sDesc[kWarpsPerBlock][32];
+    __shared__ uint8_t sMap[kWarpsPerBlock][32 * kSmallTiles];
+    __shared__ int sSum[kWarpsPerBlock][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const HadamardFrag A(lane);
+    const int chunks = (n + 31) >> 5;
+    for (int chunk = blockIdx.x * kWarpsPerBlock + warp; chunk < chunks; chunk += gridDim.x * kWarpsPerBlock)
+    {
+        const int i = chunk * 32 + lane;
+        int tiles = 0;
+        SmallDesc d = {nullptr, nullptr, 0, 0, 1, 0};
+        if (i < n)
+        {
+            const hvb_metric_task task = tasks[i];
+            const int count = (task.w >> 3) * (task.h >> 3);
+            if (!((task.w | task.h) & 7) && count <= kSmallTiles)
+            {
+                tiles = count;
+                d.a = hvbBlockPtr<uint8_t>(planes, task.a, d.sa);
+                d.b = hvbBlockPtr<uint8_t>(planes, task.b, d.sb);
+                d.tilesX = task.w >> 3;
+            }
+        }
+        int incl = tiles;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue; // nothing of this kernel's in the chunk (the same for every lane)
+        d.first = incl - tiles;
+        sDesc[warp][lane] = d;
+        sSum[warp][lane] = 0;
+        for (int k = 0; k < tiles; ++k) sMap[warp][d.first + k] = (uint8_t)lane;
+        __syncwarp();
+        for (int base = 0; base < total; base += 8)
+        {
+            const int f = min(base + g, total - 1);
+            const SmallDesc &e = sDesc[warp][sMap[warp][f]];
+            const int tile = f - e.first, ty = tile / e.tilesX, tx = tile - ty * e.tilesX;
+            const uint8_t *S = e.a + (intptr_t)(ty * 8 + t) * e.sa + tx * 8, *P = e.b + (intptr_t)(ty * 8 + t) * e.sb + tx * 8;
+            const uint2 r0 = loadRow8(S), r1 = loadRow8(S + 4 * e.sa), r2 = loadRow8(P), r3 = loadRow8(P + 4 * e.sb);
+            const uint32_t bx[4] = {r0.x, r1.x, r2.x, r3.x}, by[4] = {r0.y, r1.y, r2.y, r3.y};
+            int acc[4][4] = {};
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+                {
+                    const uint32_t neg = ((((mt >> 1) & ks) ^ (ks >> 1)) & 1) ? 0xfefefefeu : 0u;
+                    imma16832(acc[mt], A.x[mt & 1][0] ^ neg, A.x[mt & 1][1] ^ neg, A.x[mt & 1][2] ^ neg, A.x[mt & 1][3] ^ neg, bx[ks], by[ks]);
+                }
+            int s0 = 0, s1 = 0;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+            {
+                s0 = __sad(acc[mt][0], 0, __sad(acc[mt][2], 0, (unsigned)s0));
+                s1 = __sad(acc[mt][1], 0, __sad(acc[mt][3], 0, (unsigned)s1));
+            }
+            int sum = (g & 1) ? s1 : s0;
+            sum += __shfl_xor_sync(0xffffffffu, (g & 1) ? s0 : s1, 4);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+            const int mine = base + 2 * t + g; // lane (g < 2, t) holds the tile at this position of the sequence
+            if (g < 2 && mine < total) atomicAdd(&sSum[warp][sMap[warp][mine]], (sum + 2) >> 2); // havoc/hadamard.cpp:319-323
+        }
+        __syncwarp();
+        if (tiles) out[i] = sSum[warp][lane];
+        __syncwarp(); // the tables are rewritten for the next chunk
+    }
+}
+
 // one register-resident Hadamard tile per lane: 16-bit samples, and the 4x4 / 2x2 tiled blocks of 8-bit batches
 template <typename Sample>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -491,8 +588,8 @@ extern "C" int hvb_satd_batch(hvb_context *ctx, const hvb_metric_task *tasks, in
     {
         const auto *dT = static_cast<const hvb_metric_task *>(st.dTasks);
         auto *dO = static_cast<int32_t *>(st.dOut);
-        leftover = ctx->workCursors + 2;
-        cudaMemsetAsync(leftover, 0, sizeof(int), ctx->stream);
+        leftover = ctx->workCursors + 2; // [0]: blocks for satdKernel, [2]: blocks for satdMmaSmallKernel
+        cudaMemsetAsync(leftover, 0, 3 * sizeof(int), ctx->stream);
         // two stages measured best (64.5 % of HBM peak at 64x64 against 64.1 % with three and 62.3 % with four: the
         // products, not the copies, bound the kernel, and a deeper queue costs registers and shared memory)
         constexpr int kStages = 2;
@@ -502,6 +599,9 @@ extern "C" int hvb_satd_batch(hvb_context *ctx, const hvb_metric_task *tasks, in
         const int blocks = min((n + kWarpsPerBlock - 1) / kWarpsPerBlock, ctx->smCount * max(perSm, 1));
         satdMmaKernel<kStages><<<blocks, kWarpsPerBlock * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, leftover);
         HVB_LAUNCH_CHECK(ctx, "satdMmaKernel");
+        const int smallBlocks = min((n + 32 * kWarpsPerBlock - 1) / (32 * kWarpsPerBlock), ctx->smCount * 4);
+        satdMmaSmallKernel<<<smallBlocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->dPlanes, dT, n, dO, leftover);
+        HVB_LAUNCH_CHECK(ctx, "satdMmaSmallKernel");
     }
     HVB_DISPATCH_SAMPLE(ctx, satdKernel, gridFor<hvb_metric_task>(ctx, n), ctx->dPlanes,
                         static_cast<const hvb_metric_task *>(st.dTasks), n, static_cast<int32_t *>(st.dOut), leftover);
