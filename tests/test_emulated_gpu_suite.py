@@ -104,3 +104,10 @@ def test_sad_ssd_satd(metrics_setup, oracle, chroma):
 def test_sad4(metrics_setup, oracle):
     import test_gpu_metrics as gm
     gm.test_sad4(metrics_setup, oracle)
+
+
+def test_me_search_is_independent_of_the_batch():
+    """prefixes of a shuffled, size-mixed batch reproduce the full batch's results (four searches per warp with refill from
+    the cursor, units of several PUs per warp pass): tests/test_gpu_batching.py's property, at 8 bit"""
+    import test_gpu_batching as batching
+    batching.test_me_search_is_independent_of_the_batch(EmuScene(1, 8))
