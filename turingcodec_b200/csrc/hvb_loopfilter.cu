@@ -28,9 +28,10 @@
 // adds (original - reconstructed) and 1 to shared-memory accumulators (integer atomics: the sums are order-independent,
 // hence bit-exact); 104 sums per task go out.  One read of each picture instead of the reference's five passes.
 //
-// Status: written after the round's GPU budget was spent; parity is established on the CPU side only (oracle pinned
-// against the reference templates, tests/test_oracle_pin_loopfilter.py); tests/test_gpu_zz_loopfilter.py is the device
-// parity test and has not yet run on a GPU.
+// Status: written after the round's GPU budget was spent.  The oracle is pinned against the reference templates
+// (tests/test_oracle_pin_loopfilter.py); these kernels' own source is bit-exact against it under host emulation
+// (tests/test_host_emulated_loopfilter.py, and tests/test_emulated_gpu_suite_widening.py with device-like alignment
+// checks); tests/test_gpu_zz_loopfilter.py is the device parity test and has not yet run on a GPU.
 #include "hvb_internal.cuh"
 
 namespace {
