@@ -222,7 +222,19 @@ def kernels_of(cu_file: str) -> C.CDLL:
             start = internal.index("struct HvbLoopInfo\n{")
             spec["prelude_structs"] = internal[start:internal.index("};", start) + 2]
         _LIBS[cu_file] = host_emu_warp.build(d, cu_file, spec.pop("entry"), check_alignment=True, **spec)
+        _LIBS[cu_file].emu_set_schedule(*_SCHEDULE)
     return _LIBS[cu_file]
+
+
+def set_schedule(mode: int, seed: int = 1):
+    """fiber visiting order of every emulation library built so far and from now on: 0 ascending, 1 descending, 2 random"""
+    global _SCHEDULE
+    _SCHEDULE = (mode, seed)
+    for lib in _LIBS.values():
+        lib.emu_set_schedule(mode, seed)
+
+
+_SCHEDULE = (0, 1)
 
 
 def _ptr(a):

@@ -54,6 +54,9 @@ struct MaskState { unsigned mask = 0; int arrived = 0; unsigned generation = 0; 
 struct WarpState { MaskState masks[16]; uint32_t buf[32]; uint64_t wide[32][10]; };
 static std::vector<WarpState> warps;
 static int blockArrived = 0; static unsigned blockGeneration = 0;
+// the order in which the scheduler visits the fibers: 0 ascending, 1 descending, 2 a fresh pseudo-random permutation per sweep.
+// Between two collectives a lane runs undisturbed, so a missing barrier shows as a result that depends on this order.
+static int scheduleMode = 0; static unsigned scheduleState = 1;
 alignas(16) static unsigned char sharedArena[256 * 1024];
 
 static void yield() { swapcontext(&fibers[current].ctx, &scheduler); }
@@ -114,14 +117,27 @@ template <class F> static void emuLaunch(int grid, int block, F kernel)
             f.ctx.uc_link = &emu::scheduler;
             makecontext(&f.ctx, emu::trampoline, 0);
         }
+        std::vector<int> order(block);
+        for (int t = 0; t < block; ++t) order[t] = emu::scheduleMode == 1 ? block - 1 - t : t;
         for (bool live = true; live;)
         {
             live = false;
-            for (int t = 0; t < block; ++t)
+            if (emu::scheduleMode == 2)
+                for (int t = block - 1; t > 0; --t)
+                {
+                    emu::scheduleState = emu::scheduleState * 1664525u + 1013904223u;
+                    std::swap(order[t], order[(emu::scheduleState >> 8) % (unsigned)(t + 1)]);
+                }
+            for (int k = 0; k < block; ++k)
+            {
+                const int t = order[k];
                 if (!emu::fibers[t].done) { live = true; emu::current = t; swapcontext(&emu::scheduler, &emu::fibers[t].ctx); }
+            }
         }
     }
 }
+
+extern "C" void emu_set_schedule(int mode, unsigned seed) { emu::scheduleMode = mode; emu::scheduleState = seed ? seed : 1u; }
 
 // ---- warp and block primitives ------------------------------------------------------------------------------------------
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warpRendezvous(mask); }
