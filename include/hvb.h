@@ -436,7 +436,8 @@ typedef struct
 int hvb_sao_info_upload(hvb_context *ctx, int pic, const hvb_sao_ctu *ctus, int n);
 /* LoopFilter::Picture::applySaoCTU (turing/LoopFilter.h:794-811 -> filterBlockSao :885-1017, sao_filter_edge / _band of
  * turing/sao.cpp) for the CTUs [ctuBegin, ctuEnd) of dst_pic in raster order: SAO of src_pic (a copy of the deblocked
- * picture, turing/TaskSao.cpp:96-121) into dst_pic, whose side information is used; visible samples only. */
+ * picture, turing/TaskSao.cpp:96-121) into dst_pic, whose side information is used; visible samples only.  src_pic and
+ * dst_pic must be different pictures (the edge classes read the unfiltered neighbours). */
 typedef struct
 {
     int16_t src_pic, dst_pic;
