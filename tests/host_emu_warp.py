@@ -44,8 +44,9 @@ using std::min;
 
 // ---- fibers -------------------------------------------------------------------------------------------------------------
 namespace emu {
-struct Fiber { ucontext_t ctx; std::vector<char> stack; bool done = false; };
+struct Fiber { ucontext_t ctx; bool done = false; };
 static std::vector<Fiber> fibers;
+static std::vector<std::vector<char>> stacks; // one per thread of a block, kept across blocks and launches
 static ucontext_t scheduler;
 static int current = 0, threads = 0;
 static void (*body)() = nullptr;
@@ -107,13 +108,14 @@ template <class F> static void emuLaunch(int grid, int block, F kernel)
         emu::fibers.assign(block, emu::Fiber());
         emu::warps.assign((block + 31) / 32, emu::WarpState());
         emu::blockArrived = 0;
+        if ((int)emu::stacks.size() < block) emu::stacks.resize(block);
         for (int t = 0; t < block; ++t)
         {
             emu::Fiber &f = emu::fibers[t];
-            f.stack.resize(256 * 1024);
+            if (emu::stacks[t].empty()) emu::stacks[t].resize(256 * 1024);
             getcontext(&f.ctx);
-            f.ctx.uc_stack.ss_sp = f.stack.data();
-            f.ctx.uc_stack.ss_size = f.stack.size();
+            f.ctx.uc_stack.ss_sp = emu::stacks[t].data();
+            f.ctx.uc_stack.ss_size = emu::stacks[t].size();
             f.ctx.uc_link = &emu::scheduler;
             makecontext(&f.ctx, emu::trampoline, 0);
         }
