@@ -116,6 +116,7 @@ def build(tmp_dir: Path, cu_files: tuple, stubs: str = "", max_grid: int = 2) ->
     res = subprocess.run(["g++", *flags, "-c", str(ROOT / "tests" / "fake_cuda" / "fake_cudart.cpp"), "-o", str(fake)], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-3000:]
     lib = tmp_dir / "libhvb_host.so"
-    res = subprocess.run(["g++", "-shared", "-o", str(lib), *objects, str(fake)], capture_output=True, text=True)
+    # -Bsymbolic: the library's calls bind to its own (fake) runtime even when the real libcudart is already in the process
+    res = subprocess.run(["g++", "-shared", "-Wl,-Bsymbolic", "-o", str(lib), *objects, str(fake)], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-3000:]
     return C.CDLL(str(lib))
