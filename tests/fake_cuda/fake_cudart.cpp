@@ -28,6 +28,16 @@ cudaError_t cudaDeviceGetAttribute(int *value, cudaDeviceAttr attr, int)
     return cudaSuccess;
 }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+// kernel attributes and occupancy: the launch code only sizes grids with them
+cudaError_t cudaFuncSetAttribute(const void *, cudaFuncAttribute, int) { return cudaSuccess; }
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *blocks, const void *, int, size_t) { *blocks = 4; return cudaSuccess; }
+cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int *blocks, const void *, int, size_t, unsigned) { *blocks = 4; return cudaSuccess; }
+// a __device__ variable is an ordinary variable here, and its "symbol" is its address
+cudaError_t cudaMemcpyToSymbol(const void *symbol, const void *src, size_t bytes, size_t offset, cudaMemcpyKind)
+{
+    memcpy(static_cast<char *>(const_cast<void *>(symbol)) + offset, src, bytes);
+    return cudaSuccess;
+}
 const char *cudaGetErrorString(cudaError_t) { return "emulated runtime: no error text"; }
 const char *cudaGetErrorName(cudaError_t) { return "cudaEmulated"; }
 

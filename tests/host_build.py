@@ -72,20 +72,53 @@ def rewrite_launches(text: str) -> str:
         args_start = text.index("(", cfg_end)
         args_end = _matching(text, args_start, "(", ")")
         assert text[args_end:].lstrip().startswith(";"), "a launch is expected to be a statement"
-        out += text[pos:m.start()] + f"emuLaunch({cfg[0]}, {cfg[1]}, [&] {{ {name}{text[args_start:args_end]}; }})"
+        launcher = "emuLaunchExact" if name.split("<")[0] in EXACT_GRID else "emuLaunch"
+        out += text[pos:m.start()] + f"{launcher}({cfg[0]}, {cfg[1]}, [&] {{ {name}{text[args_start:args_end]}; }})"
         pos = args_end
 
 
-def build(tmp_dir: Path, cu_files: tuple, stubs: str = "", max_grid: int = 2) -> C.CDLL:
-    """stubs: C++ definitions of the functions the named files call in files that are left out"""
+# kernels whose launches size the grid by the work (a thread or block per element, no stride loop): never capped
+EXACT_GRID = ("tuOrderKernel", "rdoqBitsKernel", "rdoqLastKernel", "codedResidualTotalKernel")
+
+# the inline-PTX wrappers of the individual files and their emulated replacements (as in tests/emu_context.py)
+FILE_PTX = {
+    "hvb_metrics.cu": dict(replace={
+        "__device__ __forceinline__ void cpAsync8(": "static inline void cpAsync8(uint32_t dst, const void *src) { memcpy(emu::sharedArena + dst, src, 8); }",
+        "__device__ __forceinline__ void cpAsyncCommit(": "static inline void cpAsyncCommit() {}",
+        "template <int PENDING>\n__device__ __forceinline__ void cpAsyncWait(": "template <int PENDING> static inline void cpAsyncWait() {}"}),
+    "hvb_intra.cu": dict(mma={"imma16832": False}),
+    "hvb_tu.cu": dict(mma={"immaS8U8": False, "immaS8S8": True}),
+}
+
+RUNTIME_TEMPLATES = ("#include <mutex>\n"
+                     "// kernels are plain functions here; cuda_runtime.h declares this overload for nvcc only\n"
+                     "template <class... A> static cudaError_t cudaFuncSetAttribute(void (*)(A...), cudaFuncAttribute, int) { return cudaSuccess; }\n")
+
+
+def build(tmp_dir: Path, cu_files: tuple, stubs: str = "", max_grid: int = 2, cpp_files: tuple = (), soname: str = "") -> C.CDLL:
+    """stubs: C++ definitions of the functions the named files call in files that are left out; cpp_files: plain C++ sources
+    of csrc/ to compile along (the havoc table shim); soname: give the library this soname (to stand in for libhvb.so)"""
     if not (host_emu_warp.CUDA_INC / "cuda_runtime.h").exists():
         pytest.skip("CUDA headers not found")
     internal = (CSRC / "hvb_internal.cuh").read_text()
     helpers = internal[internal.index("#ifdef __CUDACC__") + len("#ifdef __CUDACC__"):internal.index("#endif // __CUDACC__")]
     objects = []
-    flags = ["-O1", "-fPIC", "-w", "-std=c++17", f"-I{host_emu_warp.CUDA_INC}", f"-I{ROOT / 'include'}", f"-I{CSRC}"]
+    # hvb_unit.cuh without its two inline-PTX wrappers (the prelude emulates them) shadows the real header
+    (tmp_dir / "hvb_unit.cuh").write_text("#pragma once\n" + host_emu_warp.unit_header())
+    flags = ["-O1", "-fPIC", "-w", "-std=c++17", f"-I{tmp_dir}", f"-I{host_emu_warp.CUDA_INC}", f"-I{ROOT / 'include'}", f"-I{CSRC}"]
     for name in cu_files:
-        src = rewrite_launches((CSRC / name).read_text())
+        src = (CSRC / name).read_text()
+        ptx = FILE_PTX.get(name, {})
+        injected = ""
+        for signature, replacement in ptx.get("replace", {}).items():
+            src = host_emu_warp._strip_function(src, signature)
+            injected += replacement + "\n"
+        for wrapper, signed_b in ptx.get("mma", {}).items():
+            src = host_emu_warp._strip_function(src, f"__device__ __forceinline__ void {wrapper}(")
+            injected += (f"static inline void {wrapper}(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)"
+                         f" {{ emuMma16832(c, a0, a1, a2, a3, b0, b1, {'true' if signed_b else 'false'}); }}\n")
+        assert "asm volatile" not in src and "asm(" not in src, f"{name}: inline PTX outside the emulated wrappers"
+        src = rewrite_launches(src)
         assert "<<<" not in src
         # the file's own include of hvb_internal.cuh brings the host declarations; its device helpers are compiled only by
         # nvcc (#ifdef __CUDACC__), so they are appended behind that include together with the emulator's prelude
@@ -94,16 +127,25 @@ def build(tmp_dir: Path, cu_files: tuple, stubs: str = "", max_grid: int = 2) ->
         prelude = host_emu_warp.PRELUDE.replace('#include "hvb.h"', "").replace('extern "C" void emu_set_schedule(', "static void emu_set_schedule(")
         # the entry points size their grids for 148 SMs; the kernels built here walk their work in grid-stride loops, so a
         # grid of at most `max_grid` blocks computes the same and keeps the emulation fast
-        cap = "    gridDim = dim3(grid); blockDim = dim3(block);"
-        assert cap in prelude
-        prelude = prelude.replace(cap, f"    grid = std::min(grid, {max_grid});\n" + cap)
-        src = src.replace(include, include + "\n" + prelude + helpers, 1)
+        # launches are serialised per translation unit (the emulator's state is static), whichever host thread issues them
+        head = "template <class F> static void emuLaunch(int grid, int block, F kernel)\n{"
+        assert head in prelude
+        prelude = prelude.replace(head, "template <class F> static void emuLaunchExact(int grid, int block, F kernel)\n{\n"
+                                        "    static std::mutex serial; std::lock_guard<std::mutex> hold(serial);")
+        prelude += ("template <class F> static void emuLaunch(int grid, int block, F kernel) "
+                    f"{{ emuLaunchExact(std::min(grid, {max_grid}), block, kernel); }}\n")
+        src = src.replace(include, include + "\n" + RUNTIME_TEMPLATES + prelude + helpers + injected, 1)
         src = re.sub(r"extern\s+__shared__\s+(__align__\(\d+\)\s+)?(\w[\w\s]*?)\s+(\w+)\[\];", r"\2 *const \3 = reinterpret_cast<\2 *>(emu::sharedArena);", src)
         src = src.replace("__shared__", "static")
         cpp = tmp_dir / (name.replace(".", "_") + ".cpp")
         cpp.write_text(src)
         obj = cpp.with_suffix(".o")
         res = subprocess.run(["g++", *flags, "-c", str(cpp), "-o", str(obj)], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr[-3000:]
+        objects.append(str(obj))
+    for name in cpp_files:
+        obj = tmp_dir / (name.replace(".", "_") + ".o")
+        res = subprocess.run(["g++", *flags, "-c", str(CSRC / name), "-o", str(obj)], capture_output=True, text=True)
         assert res.returncode == 0, res.stderr[-3000:]
         objects.append(str(obj))
     if stubs:
@@ -115,8 +157,9 @@ def build(tmp_dir: Path, cu_files: tuple, stubs: str = "", max_grid: int = 2) ->
     fake = tmp_dir / "fake_cudart.o"
     res = subprocess.run(["g++", *flags, "-c", str(ROOT / "tests" / "fake_cuda" / "fake_cudart.cpp"), "-o", str(fake)], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-3000:]
-    lib = tmp_dir / "libhvb_host.so"
+    lib = tmp_dir / (soname or "libhvb_host.so")
     # -Bsymbolic: the library's calls bind to its own (fake) runtime even when the real libcudart is already in the process
-    res = subprocess.run(["g++", "-shared", "-Wl,-Bsymbolic", "-o", str(lib), *objects, str(fake)], capture_output=True, text=True)
+    res = subprocess.run(["g++", "-shared", "-Wl,-Bsymbolic", *(["-Wl,-soname=" + soname] if soname else []), "-o", str(lib), *objects, str(fake),
+                          "-pthread"], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-3000:]
     return C.CDLL(str(lib))

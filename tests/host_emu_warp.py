@@ -113,7 +113,10 @@ template <class F> static void emuLaunch(int grid, int block, F kernel)
         {
             emu::Fiber &f = emu::fibers[t];
             if (emu::stacks[t].empty()) emu::stacks[t].resize(256 * 1024);
-            getcontext(&f.ctx);
+            static ucontext_t proto;
+            static bool haveProto = false;
+            if (!haveProto) { getcontext(&proto); haveProto = true; } // one getcontext (a system call) for all fibers
+            f.ctx = proto;
             f.ctx.uc_stack.ss_sp = emu::stacks[t].data();
             f.ctx.uc_stack.ss_size = emu::stacks[t].size();
             f.ctx.uc_link = &emu::scheduler;
