@@ -2,7 +2,7 @@
 
 tests/host_emu.py runs kernels without warp primitives on a grid of one thread.  Kernels that shuffle, vote, synchronise
 warps or issue tensor-core products need their 32 lanes in lock step; here every CUDA thread of a block is a FIBER
-(ucontext) on one OS thread, scheduled round-robin, and a collective is a rendezvous of a warp's fibers:
+(its own stack; a register-push stack switch on x86-64, ucontext elsewhere) on one OS thread, scheduled round-robin, and a collective is a rendezvous of a warp's fibers:
 
   __shfl_sync / __shfl_xor_sync / __any_sync / __ballot_sync / __syncwarp     exchange through a per-warp buffer
   __syncthreads                                                                rendezvous of the block's fibers
@@ -44,10 +44,23 @@ using std::min;
 
 // ---- fibers -------------------------------------------------------------------------------------------------------------
 namespace emu {
+// A fiber switch is six register pushes and a stack-pointer exchange on x86-64 (swapcontext would add two system calls,
+// for the signal mask, to every rendezvous); elsewhere ucontext does it.
+#if defined(__x86_64__)
+__attribute__((naked, noinline)) static void switchStack(void **saveSp, void *loadSp)
+{
+    asm volatile("pushq %rbp\n pushq %rbx\n pushq %r12\n pushq %r13\n pushq %r14\n pushq %r15\n"
+                 "movq %rsp, (%rdi)\n movq %rsi, %rsp\n"
+                 "popq %r15\n popq %r14\n popq %r13\n popq %r12\n popq %rbx\n popq %rbp\n ret\n");
+}
+struct Fiber { void *sp = nullptr; bool done = false; };
+static void *schedulerSp = nullptr;
+#else
 struct Fiber { ucontext_t ctx; bool done = false; };
+static ucontext_t scheduler;
+#endif
 static std::vector<Fiber> fibers;
 static std::vector<std::vector<char>> stacks; // one per thread of a block, kept across blocks and launches
-static ucontext_t scheduler;
 static int current = 0, threads = 0;
 static void (*body)() = nullptr;
 // a rendezvous is among the lanes of a mask: full warps, or the disjoint lane groups some kernels synchronise separately
@@ -60,8 +73,32 @@ static int blockArrived = 0; static unsigned blockGeneration = 0;
 static int scheduleMode = 0; static unsigned scheduleState = 1;
 alignas(16) static unsigned char sharedArena[256 * 1024];
 
+#if defined(__x86_64__)
+static void yield() { switchStack(&fibers[current].sp, schedulerSp); }
+static void trampoline() { body(); fibers[current].done = true; switchStack(&fibers[current].sp, schedulerSp); __builtin_trap(); }
+static void resume(int t) { current = t; switchStack(&schedulerSp, fibers[t].sp); }
+static void prepare(Fiber &f, std::vector<char> &stack)
+{
+    // the first switch to the fiber pops six registers and returns into trampoline with the stack as after a call
+    uintptr_t top = (reinterpret_cast<uintptr_t>(stack.data()) + stack.size()) & ~uintptr_t(15);
+    void **sp = reinterpret_cast<void **>(top - 16);
+    *sp = reinterpret_cast<void *>(&trampoline);
+    for (int i = 0; i < 6; ++i) *--sp = nullptr;
+    f.sp = sp;
+}
+#else
 static void yield() { swapcontext(&fibers[current].ctx, &scheduler); }
 static void trampoline() { body(); fibers[current].done = true; swapcontext(&fibers[current].ctx, &scheduler); }
+static void resume(int t) { current = t; swapcontext(&scheduler, &fibers[t].ctx); }
+static void prepare(Fiber &f, std::vector<char> &stack)
+{
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = stack.data();
+    f.ctx.uc_stack.ss_size = stack.size();
+    f.ctx.uc_link = &scheduler;
+    makecontext(&f.ctx, trampoline, 0);
+}
+#endif
 static void warpRendezvous(unsigned mask = 0xffffffffu)
 {
     WarpState &w = warps[current >> 5];
@@ -113,14 +150,7 @@ template <class F> static void emuLaunch(int grid, int block, F kernel)
         {
             emu::Fiber &f = emu::fibers[t];
             if (emu::stacks[t].empty()) emu::stacks[t].resize(256 * 1024);
-            static ucontext_t proto;
-            static bool haveProto = false;
-            if (!haveProto) { getcontext(&proto); haveProto = true; } // one getcontext (a system call) for all fibers
-            f.ctx = proto;
-            f.ctx.uc_stack.ss_sp = emu::stacks[t].data();
-            f.ctx.uc_stack.ss_size = emu::stacks[t].size();
-            f.ctx.uc_link = &emu::scheduler;
-            makecontext(&f.ctx, emu::trampoline, 0);
+            emu::prepare(f, emu::stacks[t]);
         }
         std::vector<int> order(block);
         for (int t = 0; t < block; ++t) order[t] = emu::scheduleMode == 1 ? block - 1 - t : t;
@@ -136,7 +166,7 @@ template <class F> static void emuLaunch(int grid, int block, F kernel)
             for (int k = 0; k < block; ++k)
             {
                 const int t = order[k];
-                if (!emu::fibers[t].done) { live = true; emu::current = t; swapcontext(&emu::scheduler, &emu::fibers[t].ctx); }
+                if (!emu::fibers[t].done) { live = true; emu::resume(t); }
             }
         }
     }

@@ -23,16 +23,17 @@ def cpu_libhvb(tmp_path_factory):
     return d
 
 
-def test_reference_encoder_on_the_emulated_library_matches_reference(cpu_libhvb, tmp_path):
+@pytest.mark.parametrize("tag,width,height,frames,options", dropin.CASES, ids=[c[0] for c in dropin.CASES])
+def test_reference_encoder_on_the_emulated_library_matches_reference(cpu_libhvb, tmp_path, tag, width, height, frames, options):
+    """the option sets of tests/test_gpu_dropin.py (the reference's own signature test, turing/signature.cpp:228-237)"""
     if not (dropin.REF.exists() and dropin.B200.exists()):
         pytest.skip("oracle/_ref/turing_ref / turing_b200 not built (make -C oracle encoder, needs /root/reference)")
-    width, height, frames, options = 64, 64, 2, ["--speed", "fast"]  # an intra and an inter picture
     clip = tmp_path / "clip.yuv"
     dropin.write_clip(clip, width, height, frames)
 
     def encode(binary, tag, extra, lib_dir):
         bit, rec = tmp_path / f"{tag}.bit", tmp_path / f"{tag}.yuv"
-        cmd = [str(binary), "encode", "--input-res", f"{width}x{height}", "--frame-rate", "24", "--frames", str(frames), "--threads", "1",
+        cmd = [str(binary), "encode", "--input-res", f"{width}x{height}", "--frame-rate", "24", "--frames", str(frames), "--threads", "2",
                "-o", str(bit), "--dump-pictures", str(rec), *extra, *options, str(clip)]
         env = dict(os.environ)
         if lib_dir:
@@ -44,4 +45,4 @@ def test_reference_encoder_on_the_emulated_library_matches_reference(cpu_libhvb,
     want = encode(dropin.REF, "ref", ["--asm", "0"], None)
     got = encode(dropin.B200, "emulated", [], cpu_libhvb)
     assert want[2] > 100  # a real bitstream came out
-    assert got == want
+    assert got == want, tag
