@@ -263,8 +263,12 @@ typedef struct
     uint32_t ssd;     /* havoc_ssd(src, rec)  (Reconstruct.cpp:849-853) */
     uint32_t ssdPred; /* havoc_ssd(src, pred) (Reconstruct.cpp:856) */
     int32_t cbf;
-    int32_t reserved;
-} hvb_tu_result; /* 16 bytes */
+    int32_t status;      /* 0; -1: the task was rejected (levels outside the coefficient pool, log2n outside 2..5, or an RDOQ
+                            task whose rdoq_ctx was never uploaded) and nothing was computed for it */
+    uint32_t sadQuad[4]; /* sum |src - pred| over the block's quadrants, [2 * (y >= n/2) + (x >= n/2)]: what
+                            reconstructInter accumulates into Candidate::sadResidueQuad (Reconstruct.cpp:1268-1287, read by
+                            Aps::analyseResidueEnergy, turing/Aps.h:62-76); a caller whose CU spans several blocks adds them up */
+} hvb_tu_result; /* 32 bytes */
 int hvb_tu_chain_batch(hvb_context *ctx, const hvb_tu_task *tasks, int n, hvb_tu_result *out, hvb_mem mem);
 
 /* RDOQ inputs that are not pixels: a snapshot of the CABAC context states the reference's

@@ -56,7 +56,7 @@ typedef struct
     int32_t rdoq_ctx;
 } b_tu_task; /* 60 bytes */
 
-typedef struct { uint32_t ssd, ssdPred; int32_t cbf, reserved; } b_tu_result;
+typedef struct { uint32_t ssd, ssdPred; int32_t cbf, status; uint32_t sadQuad[4]; } b_tu_result;
 
 /* a picture plane on the host: pointer to sample (0,0), stride in samples */
 typedef struct { const void *base; intptr_t stride; } b_plane;
@@ -351,12 +351,15 @@ static void tu_body(void *a, int i)
         int16_t res[1024] __attribute__((aligned(32))), coeffs[1024] __attribute__((aligned(32)));
         int16_t deq[1024] __attribute__((aligned(32)));
         int16_t *levels = levelPool + t->levels;
+        uint32_t sadQuad[4] = {0, 0, 0, 0};
         for (int y = 0; y < nn; ++y)
             for (int x = 0; x < nn; ++x)
             {
                 int s = bps == 1 ? ((const uint8_t *)src)[y * sp->stride + x] : ((const uint16_t *)src)[y * sp->stride + x];
                 int p = bps == 1 ? ((const uint8_t *)pred)[y * pp->stride + x] : ((const uint16_t *)pred)[y * pp->stride + x];
                 res[y * nn + x] = (int16_t)(s - p);
+                /* Candidate::sadResidueQuad (turing/Reconstruct.cpp:1268-1287) */
+                sadQuad[2 * (y >> (t->log2n - 1)) + (x >> (t->log2n - 1))] += (uint32_t)abs(s - p);
             }
         if (prim.handle) prim.fwd(prim.handle, coeffs, res, nn, t->trType, t->log2n, bitDepth);
         else orc_transform_fwd(coeffs, res, nn, t->trType, t->log2n, bitDepth);
@@ -387,7 +390,8 @@ static void tu_body(void *a, int i)
             out[i].ssdPred = orc_ssd(src, sp->stride, pred, pp->stride, nn, nn, bps);
         }
         out[i].cbf = cbf != 0;
-        out[i].reserved = 0;
+        out[i].status = 0;
+        memcpy(out[i].sadQuad, sadQuad, sizeof sadQuad);
     }
 }
 

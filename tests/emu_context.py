@@ -113,9 +113,13 @@ extern "C" void emu_rdoq(int16_t *pool, int poolCount, const hvb_rdoq_ctx *rdoqC
     RdoqTables tables(rdoqCtx, nCtx);
     std::vector<HvbCoefRec> recs(poolCount);
     std::vector<HvbRdoqMid> mids(n);
+    const int chunks = (n + 1023) / 1024;
+    std::vector<int> compact(n), chunkBase(chunks + 1);
+    emuLaunch(chunks, 1024, [&] { scanLocalKernel(RdoqCount{tasks}, n, compact.data(), chunkBase.data()); });
+    emuLaunch(1, 1024, [&] { scanBlocksKernel(chunkBase.data(), chunks); });
     emuLaunch(grid, kWarps * 32, [&] { rdoqPrepassKernel(pool, rdoqCtx, tasks, n, mids.data(), cbf, bitDepth); });
     emuLaunch(std::min((n + 127) / 128, grid), 128, [&] { rdoqThreadKernel(pool, recs.data(), rdoqCtx, tasks, n, mids.data(), cbf, bitDepth,
-                                                                           tables.bits.data(), tables.last.data()); });
+                                                                           tables.bits.data(), tables.last.data(), compact.data(), chunkBase.data()); });
 }
 template <typename Sample>
 static void chain(const HvbPlane *planes, int16_t *pool, int poolCount, const hvb_rdoq_ctx *rdoqCtx, int nCtx, const hvb_tu_task *tasks, int n,
@@ -127,10 +131,15 @@ static void chain(const HvbPlane *planes, int16_t *pool, int poolCount, const hv
     std::vector<HvbRdoqMid> mids(n);
     std::vector<int> buckets(64 + n, 0);
     int *order = buckets.data() + 64;
-    emuLaunch(grid, kWarps * 32, [&] { tuFrontKernel<Sample>(planes, pool, coefTmp.data(), rdoqCtx, tasks, n, out, mids.data(), buckets.data(), bitDepth); });
+    const int chunks = (n + 1023) / 1024;
+    std::vector<int> compact(n), chunkBase(chunks + 1);
+    emuLaunch(chunks, 1024, [&] { scanLocalKernel(TuCount{tasks}, n, compact.data(), chunkBase.data()); });
+    emuLaunch(1, 1024, [&] { scanBlocksKernel(chunkBase.data(), chunks); });
+    emuLaunch(grid, kWarps * 32, [&] { tuFrontKernel<Sample>(planes, pool, coefTmp.data(), rdoqCtx, tasks, n, out, mids.data(), buckets.data(), bitDepth, compact.data(), chunkBase.data(), nCtx, (unsigned)poolCount); });
     emuLaunch((n + 255) / 256, 256, [&] { tuOrderKernel(mids.data(), n, buckets.data(), buckets.data() + kRdoqBuckets, order); });
     emuLaunch(std::min((n + 127) / 128, grid), 128, [&] { tuRdoqKernel(pool, coefTmp.data(), recs.data(), rdoqCtx, tasks, n, out, mids.data(),
-                                                                       buckets.data(), order, bitDepth, tables.bits.data(), tables.last.data()); });
+                                                                       buckets.data(), order, bitDepth, tables.bits.data(), tables.last.data(), compact.data(),
+                                                                       chunkBase.data()); });
     emuLaunch(grid, kWarps * 32, [&] { tuBackKernel<Sample>(planes, pool, tasks, n, out, bitDepth); });
 }
 extern "C" void emu_tu_chain(const HvbPlane *planes, int16_t *pool, int poolCount, const hvb_rdoq_ctx *rdoqCtx, int nCtx, const hvb_tu_task *tasks,

@@ -218,6 +218,7 @@ static inline int __dp2a_hi(int a, int b, int c) { return c + (int)(int16_t)(a &
 static inline unsigned __sad(int a, int b, unsigned c) { return c + (unsigned)std::abs(a - b); }
 static inline unsigned __vsadu2(unsigned a, unsigned b) { return (unsigned)std::abs((int)(a & 0xffff) - (int)(b & 0xffff)) + (unsigned)std::abs((int)(a >> 16) - (int)(b >> 16)); }
 static inline unsigned __vsadu4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; ++i) r += (unsigned)std::abs((int)((a >> (8 * i)) & 0xff) - (int)((b >> (8 * i)) & 0xff)); return r; }
+static inline unsigned __vabsdiffu2(unsigned a, unsigned b) { return (unsigned)std::abs((int)(a & 0xffff) - (int)(b & 0xffff)) | ((unsigned)std::abs((int)(a >> 16) - (int)(b >> 16)) << 16); }
 static inline unsigned __vabsdiffu4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; ++i) r |= (unsigned)std::abs((int)((a >> (8 * i)) & 0xff) - (int)((b >> (8 * i)) & 0xff)) << (8 * i); return r; }
 static inline int __vimin_s32_relu(int a, int b) { return std::max(std::min(a, b), 0); }
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }

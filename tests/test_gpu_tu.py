@@ -162,6 +162,13 @@ def oracle_tu_chain(oracle, scene, src, pred, tr, log2n, qp, c_idx, use_rdoq, ct
     return levels, rec, ssd, ssd_pred, int(cbf != 0), (qscale, qshift, qoffset, iqscale, iqshift)
 
 
+def sad_quadrants(src, pred):
+    """Candidate::sadResidueQuad of one block (Reconstruct.cpp:1268-1287): sum |src - pred| per quadrant, [2*yHalf + xHalf]"""
+    d = np.abs(src.astype(np.int64) - pred.astype(np.int64))
+    h = d.shape[0] // 2
+    return [int(d[:h, :h].sum()), int(d[:h, h:].sum()), int(d[h:, :h].sum()), int(d[h:, h:].sum())]
+
+
 @pytest.mark.parametrize("use_rdoq", [False, True])
 def test_tu_chain(scene, oracle, use_rdoq):
     rng = np.random.default_rng(44 + use_rdoq)
@@ -195,17 +202,18 @@ def test_tu_chain(scene, oracle, use_rdoq):
         t[i]["flags"] = (1 if use_rdoq else 0) | (is_intra << 1) | (sdh << 2)
         t[i]["qscale"], t[i]["qshift"], t[i]["qoffset"], t[i]["iqscale"], t[i]["iqshift"] = q
         t[i]["scanIdx"], t[i]["rdoq_ctx"] = scan_idx, k
-        want.append((levels, rec, ssd, ssd_pred, cbf, offset, n))
+        want.append((levels, rec, ssd, ssd_pred, cbf, offset, n, sad_quadrants(src, pred)))
         offset += n * n
     out = scene.ctx.tu_chain(t)
     got_levels = scene.ctx.coeff_download(offset)
     got_rec = scene.download(scene.scratch[1], 0)
     coded = 0
     for i, (cx, cy) in enumerate(cells):
-        levels, rec, ssd, ssd_pred, cbf, off, n = want[i]
+        levels, rec, ssd, ssd_pred, cbf, off, n, quad = want[i]
         assert np.array_equal(got_levels[off:off + n * n], levels), (i, n, use_rdoq)
         assert np.array_equal(got_rec[cy:cy + n, cx:cx + n], rec), (i, n)
         assert int(out[i]["ssd"]) == ssd and int(out[i]["ssdPred"]) == ssd_pred and int(out[i]["cbf"]) == cbf, (i, n)
+        assert out[i]["sadQuad"].tolist() == quad and int(out[i]["status"]) == 0, (i, n)
         coded += cbf
     assert coded > len(cells) // 4
 

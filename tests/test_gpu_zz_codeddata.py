@@ -1,17 +1,14 @@
 """GPU parity of hvb_coded_residual_batch against the oracle (pinned against the reference's
 CodedData::storeResidual by tests/test_oracle_pin_codeddata.py): a mixed batch through the coefficient pool.
 
-STATUS: written after round 1's GPU budget was spent; the kernel's own source is bit-exact under host emulation
-(tests/test_host_emulated_codeddata.py) but has not run on a GPU yet.  Sorted last and marked xfail(strict=False) so that an
-undiscovered bug cannot mask the verified suite; the marker is to be removed at the first GPU run of round 2."""
+First run on a B200 at the end of round 1 (driver run, GPUTEST_r01.json: bit-exact as written); a plain parity test since."""
 import numpy as np
 import pytest
 
 import test_host_emulated_codeddata as emu_test
 from turingcodec_b200 import hvb
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first GPU run of hvb_coded_residual_batch (written without GPU access)")]
+pytestmark = pytest.mark.gpu
 
 
 def test_coded_residual_matches_oracle(oracle):

@@ -3,18 +3,14 @@ oracle, which tests/test_oracle_pin_loopfilter.py pins against the reference's o
 whole-picture passes (all vertical edges, then all horizontal edges) and as the per-CTU regions of TaskDeblock::run in two
 batches; SAO from a copy of the picture into the picture, in two CTU ranges; 8 and 10 bit.
 
-STATUS: these kernels were written after round 1's GPU budget was spent and have not run on a GPU yet; their own source,
-executed on the CPU, is bit-exact against the oracle (tests/test_host_emulated_loopfilter.py).  The file sorts last
-and is marked xfail(strict=False) so that an undiscovered bug cannot mask the verified suite in front of it; the marker
-is to be removed at the first GPU run of round 2 (XPASS in the report means the kernel is bit-exact as written)."""
+First run on a B200 at the end of round 1 (driver run, GPUTEST_r01.json: bit-exact as written); a plain parity test since."""
 import numpy as np
 import pytest
 
 import test_oracle_pin_loopfilter as pin
 from turingcodec_b200 import hvb
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first GPU run of hvb_deblock_batch / hvb_sao_batch (written without GPU access)")]
+pytestmark = pytest.mark.gpu
 
 
 def upload(ctx, pic, planes):

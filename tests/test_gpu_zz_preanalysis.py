@@ -1,9 +1,7 @@
 """GPU parity of hvb_intra_complexity_batch against the oracle (pinned against the reference's
 EstimateIntraComplexity::computeSatd8x8 by tests/test_oracle_pin_preanalysis.py).
 
-STATUS: written after round 1's GPU budget was spent; the kernel's own source is bit-exact under host emulation
-(tests/test_host_emulated_preanalysis.py) but has not run on a GPU yet.  Sorted last and marked xfail(strict=False) so that
-an undiscovered bug cannot mask the verified suite; the marker is to be removed at the first GPU run of round 2."""
+First run on a B200 at the end of round 1 (driver run, GPUTEST_r01.json: bit-exact as written); a plain parity test since."""
 import numpy as np
 import pytest
 
@@ -11,8 +9,7 @@ import test_host_emulated_preanalysis as emu_test
 import test_oracle_pin_preanalysis as pin
 from turingcodec_b200 import hvb
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first GPU run of hvb_intra_complexity_batch (written without GPU access)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("bps,bit_depth", [(1, 8), (2, 10)])

@@ -36,11 +36,15 @@ static void chain(const HvbPlane *planes, int16_t *pool, int poolCount, const hv
     std::vector<HvbRdoqMid> mids(n);
     std::vector<int> buckets(64 + n, 0);
     int *order = buckets.data() + 64;
+    const int chunks = (n + 1023) / 1024;
+    std::vector<int> compact(n), chunkBase(chunks + 1);
+    emuLaunch(chunks, 1024, [&] { scanLocalKernel(TuCount{tasks}, n, compact.data(), chunkBase.data()); });
+    emuLaunch(1, 1024, [&] { scanBlocksKernel(chunkBase.data(), chunks); });
     const int gridW = std::min((n + kWarps - 1) / kWarps, 3), gridT = std::min((n + 127) / 128, 2);
-    emuLaunch(gridW, kWarps * 32, [&] { tuFrontKernel<Sample>(planes, pool, coefTmp.data(), rdoqCtx, tasks, n, out, mids.data(), buckets.data(), bitDepth); });
+    emuLaunch(gridW, kWarps * 32, [&] { tuFrontKernel<Sample>(planes, pool, coefTmp.data(), rdoqCtx, tasks, n, out, mids.data(), buckets.data(), bitDepth, compact.data(), chunkBase.data(), nCtx, (unsigned)poolCount); });
     emuLaunch((n + 255) / 256, 256, [&] { tuOrderKernel(mids.data(), n, buckets.data(), buckets.data() + kRdoqBuckets, order); });
     emuLaunch(gridT, 128, [&] { tuRdoqKernel(pool, coefTmp.data(), recs.data(), rdoqCtx, tasks, n, out, mids.data(), buckets.data(), order, bitDepth,
-                                             bits.data(), last.data()); });
+                                             bits.data(), last.data(), compact.data(), chunkBase.data()); });
     emuLaunch(gridW, kWarps * 32, [&] { tuBackKernel<Sample>(planes, pool, tasks, n, out, bitDepth); });
 }
 extern "C" void emu_tu_chain(const HvbPlane *planes, int16_t *pool, int poolCount, const hvb_rdoq_ctx *rdoqCtx, int nCtx, const hvb_tu_task *tasks,
@@ -96,7 +100,7 @@ def test_tu_chain_kernels_on_cpu_match_oracle(emu, oracle, bps, bit_depth, use_r
         t[i]["flags"] = (1 if use_rdoq else 0) | (is_intra << 1) | (sdh << 2)
         t[i]["qscale"], t[i]["qshift"], t[i]["qoffset"], t[i]["iqscale"], t[i]["iqshift"] = q
         t[i]["scanIdx"], t[i]["rdoq_ctx"] = scan_idx, k
-        want.append((levels, rec, ssd, ssd_pred, cbf, offset, n))
+        want.append((levels, rec, ssd, ssd_pred, cbf, offset, n, gpu_tu.sad_quadrants(src, pred)))
         offset += n * n
     pool = np.zeros(len(cells) * 1024, np.int16)
     out = np.zeros(len(cells), hvb.tu_result_t)
@@ -105,7 +109,8 @@ def test_tu_chain_kernels_on_cpu_match_oracle(emu, oracle, bps, bit_depth, use_r
     coded = 0
     got_rec = rec_pic[0][PAD:PAD + H, PAD:PAD + W]
     for i, (cx, cy) in enumerate(cells):
-        levels, rec, ssd, ssd_pred, cbf, off, n = want[i]
+        levels, rec, ssd, ssd_pred, cbf, off, n, quad = want[i]
+        assert out[i]["sadQuad"].tolist() == quad and int(out[i]["status"]) == 0, (i, n)
         assert np.array_equal(pool[off:off + n * n], levels), (i, n, use_rdoq)
         assert np.array_equal(got_rec[cy:cy + n, cx:cx + n], rec), (i, n)
         assert int(out[i]["ssd"]) == ssd and int(out[i]["ssdPred"]) == ssd_pred and int(out[i]["cbf"]) == cbf, (i, n)

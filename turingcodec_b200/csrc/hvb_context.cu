@@ -21,7 +21,7 @@ static_assert(sizeof(hvb_transform_task) == 16, "abi");
 static_assert(sizeof(hvb_quant_task) == 24, "abi");
 static_assert(sizeof(hvb_ita_task) == 24, "abi");
 static_assert(sizeof(hvb_tu_task) == 60, "abi");
-static_assert(sizeof(hvb_tu_result) == 16, "abi");
+static_assert(sizeof(hvb_tu_result) == 32, "abi");
 static_assert(sizeof(hvb_rdoq_ctx) == 136, "abi");
 static_assert(sizeof(hvb_rdoq_task) == 28, "abi");
 static_assert(sizeof(hvb_me_task) == 64, "abi");
@@ -73,7 +73,8 @@ extern "C" int hvb_create(int device, int bytes_per_sample, int bit_depth, hvb_c
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->dPlanes, sizeof(HvbPlane) * HVB_MAX_PICTURES * 3);
-    if (e == cudaSuccess) e = cudaMemset(ctx->dPlanes, 0, sizeof(HvbPlane) * HVB_MAX_PICTURES * 3);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->dPlanes, 0, sizeof(HvbPlane) * HVB_MAX_PICTURES * 3, ctx->ownStream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->ownStream);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->workCursors, 64 * sizeof(int));
     int sms = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -256,7 +257,11 @@ extern "C" int hvb_picture_destroy(hvb_context *ctx, int pic)
         p.lfInfo = p.saoInfo = nullptr;
         p.lfBytes = p.saoBytes = 0;
         ctx->loopInfoHost[pic] = HvbLoopInfo{};
-        if (ctx->dLoopInfo) cudaMemset(ctx->dLoopInfo + pic, 0, sizeof(HvbLoopInfo));
+        if (ctx->dLoopInfo)
+        {
+            cudaMemsetAsync(ctx->dLoopInfo + pic, 0, sizeof(HvbLoopInfo), ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+        }
     }
     p.live = false;
     ctx->planesDirty = true;
@@ -272,9 +277,11 @@ int hvbSyncPlanes(hvb_context *ctx)
         if (ctx->pictures[i].live)
             for (int c = 0; c < 3; ++c) host[i * 3 + c] = ctx->pictures[i].plane[c];
     // synchronous small copy: the table changes only when pictures are created or destroyed
+    // (on the context's stream -- ordered against its kernels -- and waited for: `host` is pageable and local)
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess)
-        e = cudaMemcpy(ctx->dPlanes, host.data(), host.size() * sizeof(HvbPlane), cudaMemcpyHostToDevice);
+        e = cudaMemcpyAsync(ctx->dPlanes, host.data(), host.size() * sizeof(HvbPlane), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return hvbCuda(ctx, e, "hvbSyncPlanes");
     ctx->planesDirty = false;
     return HVB_OK;
@@ -383,23 +390,45 @@ extern "C" int hvb_picture_pad(hvb_context *ctx, int pic)
 // Pools and staging
 // ---------------------------------------------------------------------------------------------
 
+// Pool growth.  Everything is issued on the context's stream (the stream is cudaStreamNonBlocking or a caller's
+// stream, so work on the legacy default stream would not be ordered against the kernels that follow) and the
+// host waits for it before the old allocation is released.  preserve = false (kernel workspace): the old
+// contents are neither copied nor is the new allocation cleared.
 template <typename T>
-static int growDevice(hvb_context *ctx, T **ptr, size_t *have, size_t want, size_t elemBytes, const char *what)
+static int growDevice(hvb_context *ctx, T **ptr, size_t *have, size_t want, size_t elemBytes, const char *what, bool preserve = true)
 {
     if (*have >= want) return HVB_OK;
     cudaSetDevice(ctx->device);
     size_t cap = *have ? *have : 1024;
     while (cap < want) cap *= 2;
     void *fresh = nullptr;
-    cudaError_t e = cudaMalloc(&fresh, cap * elemBytes);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream); // nothing in flight may still use the old allocation
+    if (e == cudaSuccess && ctx->copyIn) e = cudaStreamSynchronize(ctx->copyIn);
+    if (e == cudaSuccess && ctx->copyOut) e = cudaStreamSynchronize(ctx->copyOut);
     if (e != cudaSuccess) return hvbCuda(ctx, e, what);
-    cudaStreamSynchronize(ctx->stream);
-    if (*ptr)
+    if (!preserve && *ptr)
     {
-        cudaMemcpy(fresh, *ptr, *have * elemBytes, cudaMemcpyDeviceToDevice);
         cudaFree(*ptr);
+        *ptr = nullptr;
+        *have = 0;
     }
-    cudaMemset(static_cast<char *>(fresh) + *have * elemBytes, 0, (cap - *have) * elemBytes);
+    e = cudaMalloc(&fresh, cap * elemBytes);
+    if (e != cudaSuccess) return hvbCuda(ctx, e, what);
+    if (preserve)
+    {
+        if (*ptr) e = cudaMemcpyAsync(fresh, *ptr, *have * elemBytes, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaMemsetAsync(static_cast<char *>(fresh) + *have * elemBytes, 0, (cap - *have) * elemBytes, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (*ptr) cudaFree(*ptr);
+        if (e != cudaSuccess)
+        {
+            cudaFree(fresh);
+            *ptr = nullptr;
+            *have = 0;
+            return hvbCuda(ctx, e, what);
+        }
+    }
     *ptr = static_cast<T *>(fresh);
     *have = cap;
     return HVB_OK;
@@ -407,7 +436,7 @@ static int growDevice(hvb_context *ctx, T **ptr, size_t *have, size_t want, size
 
 int hvbEnsureScratch(hvb_context *ctx, size_t bytes)
 {
-    return growDevice(ctx, reinterpret_cast<char **>(&ctx->scratch), &ctx->scratchBytes, bytes, 1, "scratch");
+    return growDevice(ctx, reinterpret_cast<char **>(&ctx->scratch), &ctx->scratchBytes, bytes, 1, "scratch", false);
 }
 
 int hvbEnsureCoeffPool(hvb_context *ctx, size_t count)

@@ -9,10 +9,9 @@
 //
 // Mapping: one warp per candidate.  These kernels are pure streaming reductions (every sample is
 // read once per candidate), so the bound is memory: 2*w*h*B algorithmic bytes per candidate
-// (5*w*h*B for SAD4).  Source rows are 4-byte aligned by construction (PU x0 is a multiple of 4,
-// plane rows are 256-byte aligned); reference rows are arbitrarily aligned and are read as two
-// aligned words + funnel shift.  Byte lanes are reduced with the SIMD-in-word video instructions
-// (VABSDIFF4 / dp4a), then a 5-step shuffle tree.
+// (5*w*h*B for SAD4).  Blocks are arbitrarily aligned (motion-search candidates): every 16-byte chunk
+// of a row is one aligned 128-bit load, or two and a word funnel.  Byte / halfword lanes are reduced
+// with the SIMD-in-word video instructions (VABSDIFF4 / VABSDIFF2 / dp4a), then a 5-step shuffle tree.
 #include "hvb_internal.cuh"
 #include "hvb_satd.cuh"
 #include "hvb_unit.cuh"
@@ -21,45 +20,88 @@ namespace {
 
 constexpr int kWarpsPerBlock = 8;
 
-template <typename Sample>
-__device__ __forceinline__ int sadBlock(const Sample *a, int sa, const Sample *b, int sb, int w, int h, int lane)
+// 16 bytes at an arbitrary byte address: two aligned 128-bit loads and a word funnel.  The alignment is a property of
+// the block (one warp per candidate), so the branches are warp-uniform.  May touch up to 31 bytes past the last byte
+// wanted: picture rows carry that slack (hvb_picture_create).
+__device__ __forceinline__ uint4 load16(const uint8_t *p)
 {
-    int acc = 0;
-    if (sizeof(Sample) == 1 && !(w & 15) &&
-        !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | (uintptr_t)sa | (uintptr_t)sb) & 15))
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint4 *q = reinterpret_cast<const uint4 *>(a & ~uintptr_t(15));
+    const unsigned sh = (unsigned)(a & 15);
+    const uint4 lo = __ldg(q);
+    if (sh == 0) return lo;
+    const uint4 hi = __ldg(q + 1);
+    const unsigned b = (sh & 3) * 8;
+    uint32_t w0, w1, w2, w3, w4;
+    switch (sh >> 2)
     {
-        // streaming case (both blocks 16-byte aligned, e.g. co-located blocks): one 128-bit load per operand per lane
-        // per step -- this is the path the HBM roofline is quoted on (tools/stream_metrics.py)
-        const int cpr = w >> 4, total = cpr * h; // 16-byte chunks per row / in the block
-        const uint8_t *pa = reinterpret_cast<const uint8_t *>(a), *pb = reinterpret_cast<const uint8_t *>(b);
-        for (int i = lane; i < total; i += 32)
-        {
-            const int y = i / cpr, x = (i - y * cpr) << 4;
-            const uint4 va = __ldg(reinterpret_cast<const uint4 *>(pa + y * sa + x)), vb = __ldg(reinterpret_cast<const uint4 *>(pb + y * sb + x));
-            acc = __vsadu4(va.x, vb.x) + __vsadu4(va.y, vb.y) + __vsadu4(va.z, vb.z) + __vsadu4(va.w, vb.w) + acc;
-        }
+    case 0: w0 = lo.x, w1 = lo.y, w2 = lo.z, w3 = lo.w, w4 = hi.x; break;
+    case 1: w0 = lo.y, w1 = lo.z, w2 = lo.w, w3 = hi.x, w4 = hi.y; break;
+    case 2: w0 = lo.z, w1 = lo.w, w2 = hi.x, w3 = hi.y, w4 = hi.z; break;
+    default: w0 = lo.w, w1 = hi.x, w2 = hi.y, w3 = hi.z, w4 = hi.w; break;
     }
-    else if (sizeof(Sample) == 1 && !(w & 3))
+    return make_uint4(__funnelshift_r(w0, w1, b), __funnelshift_r(w1, w2, b), __funnelshift_r(w2, w3, b), __funnelshift_r(w3, w4, b));
+}
+
+// keep the first `valid` (1..16) bytes of a 16-byte chunk
+__device__ __forceinline__ uint4 maskChunk(uint4 v, int valid)
+{
+    if (valid >= 16) return v;
+    const auto m = [valid](int k) -> uint32_t {
+        const int b = valid - 4 * k;
+        return b >= 4 ? 0xffffffffu : (b <= 0 ? 0u : (1u << (8 * b)) - 1u);
+    };
+    return make_uint4(v.x & m(0), v.y & m(1), v.z & m(2), v.w & m(3));
+}
+
+template <typename Sample>
+__device__ __forceinline__ unsigned sadWords(uint4 a, uint4 b)
+{
+    if (sizeof(Sample) == 1) return __vsadu4(a.x, b.x) + __vsadu4(a.y, b.y) + __vsadu4(a.z, b.z) + __vsadu4(a.w, b.w);
+    return __vsadu2(a.x, b.x) + __vsadu2(a.y, b.y) + __vsadu2(a.z, b.z) + __vsadu2(a.w, b.w);
+}
+
+template <typename Sample>
+__device__ __forceinline__ unsigned ssdWords(uint4 a, uint4 b, unsigned acc)
+{
+    const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
     {
-        const int wq = w >> 2, total = wq * h;
-        for (int i = lane; i < total; i += 32)
+        if (sizeof(Sample) == 1)
         {
-            const int y = i / wq, x = (i - y * wq) << 2;
-            const uint32_t va = hvbLoad4u8(reinterpret_cast<const uint8_t *>(a) + y * sa + x);
-            const uint32_t vb = hvbLoad4u8(reinterpret_cast<const uint8_t *>(b) + y * sb + x);
-            acc = __vsadu4(va, vb) + acc;
+            const uint32_t d = __vabsdiffu4(wa[k], wb[k]);
+            acc = __dp4a(d, d, acc);
         }
-    }
-    else
-    {
-        const int total = w * h;
-        for (int i = lane; i < total; i += 32)
+        else
         {
-            const int y = i / w, x = i - y * w;
-            acc += abs((int)a[y * sa + x] - (int)b[y * sb + x]);
+            const uint32_t d = __vabsdiffu2(wa[k], wb[k]);
+            const uint32_t l = d & 0xffffu, h = d >> 16;
+            acc += l * l + h * h;
         }
     }
     return acc;
+}
+
+// Streaming form shared by SAD, SAD4 and SSD: a block is h rows of ceil(w * B / 16) 16-byte chunks, the chunks go
+// round the lanes, every operand chunk is one or two 128-bit loads whatever the block's alignment (co-located blocks,
+// motion-search candidates, 8- and 16-bit samples alike); the excess bytes of a row's last chunk are masked in both
+// operands, so they contribute |0 - 0|.
+template <typename Sample>
+__device__ __forceinline__ int sadBlock(const Sample *a, int sa, const Sample *b, int sb, int w, int h, int lane)
+{
+    const int B = (int)sizeof(Sample), wb = w * B, cpr = (wb + 15) >> 4, total = cpr * h;
+    const uint8_t *pa = reinterpret_cast<const uint8_t *>(a), *pb = reinterpret_cast<const uint8_t *>(b);
+    unsigned acc = 0;
+#pragma unroll 2
+    for (int i = lane; i < total; i += 32)
+    {
+        const int y = i / cpr, x = (i - y * cpr) << 4;
+        const uint4 va = maskChunk(load16(pa + (intptr_t)y * sa * B + x), wb - x);
+        const uint4 vb = maskChunk(load16(pb + (intptr_t)y * sb * B + x), wb - x);
+        acc += sadWords<Sample>(va, vb);
+    }
+    return (int)acc;
 }
 
 template <typename Sample>
@@ -86,47 +128,35 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 {
     const int lane = threadIdx.x & 31;
     const int warpsTotal = gridDim.x * kWarpsPerBlock;
+    const int B = (int)sizeof(Sample);
     for (int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n; t += warpsTotal)
     {
         const hvb_sad4_task task = tasks[t];
         int ss;
-        const Sample *src = hvbBlockPtr<Sample>(planes, task.src, ss);
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(hvbBlockPtr<Sample>(planes, task.src, ss));
         const HvbPlane &rp = planes[task.ref_pic * 3 + task.ref_cIdx];
-        const Sample *rbase = reinterpret_cast<const Sample *>(rp.base);
+        const uint8_t *rbase = reinterpret_cast<const uint8_t *>(rp.base);
         const int sr = rp.stride;
-        const int w = task.w, h = task.h;
-        int acc[4] = {0, 0, 0, 0};
-        const Sample *ref[4];
+        const int wb = task.w * B, h = task.h, cpr = (wb + 15) >> 4, total = cpr * h;
+        unsigned acc[4] = {0, 0, 0, 0};
+        const uint8_t *ref[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ref[k] = rbase + (intptr_t)task.ry[k] * sr + task.rx[k];
-
-        if (sizeof(Sample) == 1 && !(w & 3))
+        for (int k = 0; k < 4; ++k) ref[k] = rbase + ((intptr_t)task.ry[k] * sr + task.rx[k]) * B;
+        // the source chunk is loaded once and compared with the four references (havoc/sad.cpp:513-542)
+        for (int i = lane; i < total; i += 32)
         {
-            const int wq = w >> 2, total = wq * h;
-            for (int i = lane; i < total; i += 32)
-            {
-                const int y = i / wq, x = (i - y * wq) << 2;
-                const uint32_t vs = hvbLoad4u8(reinterpret_cast<const uint8_t *>(src) + y * ss + x);
+            const int y = i / cpr, x = (i - y * cpr) << 4;
+            const uint4 vs = maskChunk(load16(src + (intptr_t)y * ss * B + x), wb - x);
+            uint4 vr[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    acc[k] = __vsadu4(vs, hvbLoad4u8(reinterpret_cast<const uint8_t *>(ref[k]) + y * sr + x)) + acc[k];
-            }
-        }
-        else
-        {
-            const int total = w * h;
-            for (int i = lane; i < total; i += 32)
-            {
-                const int y = i / w, x = i - y * w;
-                const int s = src[y * ss + x];
+            for (int k = 0; k < 4; ++k) vr[k] = load16(ref[k] + (intptr_t)y * sr * B + x);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) acc[k] += abs(s - (int)ref[k][y * sr + x]);
-            }
+            for (int k = 0; k < 4; ++k) acc[k] += sadWords<Sample>(vs, maskChunk(vr[k], wb - x));
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
         {
-            int v = hvbWarpSum(acc[k]);
+            int v = hvbWarpSum((int)acc[k]);
             if (sizeof(Sample) == 2) v >>= 2;
             if (lane == 0) out[t * 4 + k] = v;
         }
@@ -139,51 +169,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 {
     const int lane = threadIdx.x & 31;
     const int warpsTotal = gridDim.x * kWarpsPerBlock;
+    const int B = (int)sizeof(Sample);
     for (int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n; t += warpsTotal)
     {
         const hvb_metric_task task = tasks[t];
         int sa, sb;
-        const Sample *a = hvbBlockPtr<Sample>(planes, task.a, sa);
-        const Sample *b = hvbBlockPtr<Sample>(planes, task.b, sb);
-        const int w = task.w, h = task.h;
-        unsigned acc = 0;
-        if (sizeof(Sample) == 1 && !(w & 15) &&
-            !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | (uintptr_t)sa | (uintptr_t)sb) & 15))
+        const uint8_t *pa = reinterpret_cast<const uint8_t *>(hvbBlockPtr<Sample>(planes, task.a, sa));
+        const uint8_t *pb = reinterpret_cast<const uint8_t *>(hvbBlockPtr<Sample>(planes, task.b, sb));
+        const int wb = task.w * B, h = task.h, cpr = (wb + 15) >> 4, total = cpr * h;
+        unsigned acc = 0; // modulo 2^32, like the reference's uint32_t accumulator (havoc/ssd.cpp:28-43)
+#pragma unroll 2
+        for (int i = lane; i < total; i += 32)
         {
-            const int cpr = w >> 4, total = cpr * h;
-            const uint8_t *pa = reinterpret_cast<const uint8_t *>(a), *pb = reinterpret_cast<const uint8_t *>(b);
-            for (int i = lane; i < total; i += 32)
-            {
-                const int y = i / cpr, x = (i - y * cpr) << 4;
-                const uint4 va = __ldg(reinterpret_cast<const uint4 *>(pa + y * sa + x)), vb = __ldg(reinterpret_cast<const uint4 *>(pb + y * sb + x));
-                uint32_t d;
-                d = __vabsdiffu4(va.x, vb.x); acc = __dp4a(d, d, acc);
-                d = __vabsdiffu4(va.y, vb.y); acc = __dp4a(d, d, acc);
-                d = __vabsdiffu4(va.z, vb.z); acc = __dp4a(d, d, acc);
-                d = __vabsdiffu4(va.w, vb.w); acc = __dp4a(d, d, acc);
-            }
-        }
-        else if (sizeof(Sample) == 1 && !(w & 3))
-        {
-            const int wq = w >> 2, total = wq * h;
-            for (int i = lane; i < total; i += 32)
-            {
-                const int y = i / wq, x = (i - y * wq) << 2;
-                const uint32_t va = hvbLoad4u8(reinterpret_cast<const uint8_t *>(a) + y * sa + x);
-                const uint32_t vb = hvbLoad4u8(reinterpret_cast<const uint8_t *>(b) + y * sb + x);
-                const uint32_t d = __vabsdiffu4(va, vb);
-                acc = __dp4a(d, d, acc);
-            }
-        }
-        else
-        {
-            const int total = w * h;
-            for (int i = lane; i < total; i += 32)
-            {
-                const int y = i / w, x = i - y * w;
-                const int d = (int)a[y * sa + x] - (int)b[y * sb + x];
-                acc += (unsigned)(d * d);
-            }
+            const int y = i / cpr, x = (i - y * cpr) << 4;
+            const uint4 va = maskChunk(load16(pa + (intptr_t)y * sa * B + x), wb - x);
+            const uint4 vb = maskChunk(load16(pb + (intptr_t)y * sb * B + x), wb - x);
+            acc = ssdWords<Sample>(va, vb, acc);
         }
         acc = hvbWarpSumU(acc);
         if (sizeof(Sample) == 2) acc >>= 4;

@@ -12,9 +12,12 @@
 // (C = M X M^T); integer sums are associative and nothing overflows int32, so the products are
 // evaluated directly: one warp per transform block, lanes across the output frequency (forward) or
 // output sample (inverse) index so that the matrix row is read conflict-free from shared memory and
-// the block operand is a broadcast.  The fused pipeline keeps residual, coefficients and levels in
-// the warp's shared-memory slice: per TU it reads src and pred (2 n^2 B), writes rec (n^2 B), the
-// levels (2 n^2) and 16 bytes of results; nothing intermediate touches HBM.
+// the block operand is a broadcast.  The fused pipeline keeps residual and coefficients in the warp's
+// shared-memory slice: per TU it reads src and pred (2 n^2 B), writes rec (n^2 B), the levels (2 n^2) and
+// 16 bytes of results.  RDOQ blocks additionally pass through a workspace between the front stage and
+// the serial stage: the unquantised coefficients (2 B each) and one 32-byte record per coefficient, laid
+// out by a per-batch compaction (scanLocalKernel / scanBlocksKernel below), so the workspace is sized by
+// the RDOQ blocks of the batch, not by the capacity of the coefficient pool.
 #include "hvb_internal.cuh"
 #include "hvb_rdoq.cuh"
 
@@ -379,6 +382,93 @@ __device__ __forceinline__ int rdoqBucket(int lastSp)
     return 2 * e + (e ? (v >> (e - 1)) & 1 : 0);
 }
 
+// Compaction of the RDOQ workspace: exclusive prefix sum of the element counts of a batch's RDOQ blocks.
+// compact[t] is the offset inside t's 1024-task chunk, chunkBase[t >> 10] the chunk's base (after scanBlocksKernel).
+struct TuCount
+{
+    const hvb_tu_task *tasks;
+    __device__ int operator()(int t) const { return (tasks[t].flags & 1) ? 1 << (2 * tasks[t].log2n) : 0; }
+};
+struct RdoqCount
+{
+    const hvb_rdoq_task *tasks;
+    __device__ int operator()(int t) const { return 1 << (2 * tasks[t].log2n); }
+};
+
+template <class Count>
+__global__ void __launch_bounds__(1024) scanLocalKernel(Count count, int n, int *__restrict__ compact, int *__restrict__ chunkBase)
+{
+    __shared__ int sWarp[32];
+    const int t = blockIdx.x * 1024 + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v = t < n ? count(t) : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) sWarp[warp] = incl;
+    __syncthreads();
+    if (warp == 0)
+    {
+        int w = sWarp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
+        }
+        sWarp[lane] = w; // inclusive over the warps
+    }
+    __syncthreads();
+    const int base = warp ? sWarp[warp - 1] : 0;
+    if (t < n) compact[t] = base + incl - v;
+    if (threadIdx.x == 1023) chunkBase[blockIdx.x] = base + incl;
+}
+
+// exclusive scan of the chunk totals, in place (one block; chunks beyond 1024 are walked with a running total)
+__global__ void __launch_bounds__(1024) scanBlocksKernel(int *__restrict__ chunkBase, int chunks)
+{
+    __shared__ int sWarp[32];
+    __shared__ int sRun;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) sRun = 0;
+    __syncthreads();
+    for (int first = 0; first < chunks; first += 1024)
+    {
+        const int i = first + threadIdx.x;
+        const int v = i < chunks ? chunkBase[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) sWarp[warp] = incl;
+        __syncthreads();
+        if (warp == 0)
+        {
+            int w = sWarp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const int u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            sWarp[lane] = w;
+        }
+        __syncthreads();
+        const int run = sRun;
+        const int base = warp ? sWarp[warp - 1] : 0;
+        if (i < chunks) chunkBase[i] = run + base + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) sRun = run + base + incl;
+        __syncthreads();
+    }
+}
+
 // counts[kRdoqBuckets] filled by the front stage; cursors[kRdoqBuckets] zero on entry.  Ranks are taken inside the
 // block first (shared-memory atomics), then one global atomic per bucket and block reserves the block's range.
 __global__ void __launch_bounds__(256)
@@ -410,7 +500,8 @@ template <typename Sample>
 __global__ void __launch_bounds__(kWarps * 32)
     tuFrontKernel(const HvbPlane *__restrict__ planes, int16_t *__restrict__ pool, int16_t *__restrict__ coefTmp,
                   const hvb_rdoq_ctx *__restrict__ rdoqCtx, const hvb_tu_task *__restrict__ tasks, int n, hvb_tu_result *__restrict__ out,
-                  HvbRdoqMid *__restrict__ mids, int *__restrict__ bucketCounts, int bitDepth)
+                  HvbRdoqMid *__restrict__ mids, int *__restrict__ bucketCounts, int bitDepth, const int *__restrict__ compact,
+                  const int *__restrict__ chunkBase, int rdoqCtxCount, unsigned poolCount)
 {
     __shared__ Matrices M;
     __shared__ __align__(16) int16_t sA[kWarps][kBlk];
@@ -424,18 +515,53 @@ __global__ void __launch_bounds__(kWarps * 32)
         const hvb_tu_task task = tasks[t];
         const int log2n = task.log2n, nn = 1 << log2n, count = nn * nn;
         const bool dst = task.trType != 0;
+        // a task that points outside the pool or at a context snapshot that was never uploaded is not run:
+        // its result carries status = -1 and the later stages skip it
+        if (log2n < 2 || log2n > 5 || task.levels < 0 || (unsigned)task.levels + (unsigned)count > poolCount ||
+            ((task.flags & 1) && (unsigned)task.rdoq_ctx >= (unsigned)rdoqCtxCount))
+        {
+            if (lane == 0)
+            {
+                HvbRdoqMid bad;
+                bad.lastSp = -2;
+                bad.reserved = -1;
+                bad.totalDist0 = bad.tailDist0 = 0;
+                mids[t] = bad;
+                hvb_tu_result r;
+                r.ssd = r.ssdPred = 0;
+                r.cbf = 0;
+                r.status = -1;
+                r.sadQuad[0] = r.sadQuad[1] = r.sadQuad[2] = r.sadQuad[3] = 0;
+                out[t] = r;
+            }
+            continue;
+        }
         int ss, sp;
         const Sample *src = hvbBlockPtr<Sample>(planes, task.src, ss);
         const Sample *pred = hvbBlockPtr<Sample>(planes, task.pred, sp);
 
         // residual (Reconstruct.cpp:1275-1287) and SSD of the prediction (:856)
-        unsigned ssdPred = 0;
+        // and the per-quadrant sum of absolute differences (:1268-1287).  4x4 blocks have 2x2 quadrants: with
+        // count = 16 a lane holds at most one sample; larger blocks give a lane samples of one column half only
+        // (x = i & (nn - 1) and 32 is a multiple of nn or the other way round), split by row.
+        unsigned ssdPred = 0, sadTop = 0, sadBottom = 0;
         for (int i = lane; i < count; i += 32)
         {
             const int y = i >> log2n, x = i & (nn - 1);
             const int d = (int)src[y * ss + x] - (int)pred[y * sp + x];
             sA[warp][i] = (int16_t)d;
             ssdPred += (unsigned)(d * d);
+            if (y >> (log2n - 1)) sadBottom += (unsigned)abs(d);
+            else sadTop += (unsigned)abs(d);
+        }
+        unsigned sadQuad[4];
+        {
+            // a lane's column half is fixed: lane & (nn - 1) when nn <= 32 (the only sizes there are)
+            const bool right = ((lane & (nn - 1)) >> (log2n - 1)) != 0;
+            sadQuad[0] = hvbWarpSumU(right ? 0u : sadTop);
+            sadQuad[1] = hvbWarpSumU(right ? sadTop : 0u);
+            sadQuad[2] = hvbWarpSumU(right ? 0u : sadBottom);
+            sadQuad[3] = hvbWarpSumU(right ? sadBottom : 0u);
         }
         __syncwarp();
         forwardTransform(M, sA[warp], sB[warp], log2n, dst, bitDepth, lane); // sA = coefficients
@@ -447,7 +573,8 @@ __global__ void __launch_bounds__(kWarps * 32)
         int cbf = 0;
         if (task.flags & 1)
         {
-            for (int i = lane; i < count; i += 32) coefTmp[task.levels + i] = sA[warp][i];
+            int16_t *tmp = coefTmp + chunkBase[t >> 10] + compact[t];
+            for (int i = lane; i < count; i += 32) tmp[i] = sA[warp][i];
             mid = hvbRdoqPrepass(pool + task.levels, sA[warp], rdoqCtx + task.rdoq_ctx, task.qscale, task.qshift, task.iqscale, log2n,
                                  task.cIdx, task.scanIdx, bitDepth, lane);
         }
@@ -475,7 +602,11 @@ __global__ void __launch_bounds__(kWarps * 32)
             r.ssd = 0;
             r.ssdPred = ssdPred;
             r.cbf = cbf;
-            r.reserved = 0;
+            r.status = 0;
+            r.sadQuad[0] = sadQuad[0];
+            r.sadQuad[1] = sadQuad[1];
+            r.sadQuad[2] = sadQuad[2];
+            r.sadQuad[3] = sadQuad[3];
             out[t] = r;
         }
         __syncwarp();
@@ -486,7 +617,8 @@ __global__ void __launch_bounds__(128)
     tuRdoqKernel(int16_t *__restrict__ pool, const int16_t *__restrict__ coefTmp, HvbCoefRec *__restrict__ recs,
                  const hvb_rdoq_ctx *__restrict__ rdoqCtx, const hvb_tu_task *__restrict__ tasks, int n, hvb_tu_result *__restrict__ out,
                  const HvbRdoqMid *__restrict__ mids, const int *__restrict__ bucketCounts, const int *__restrict__ order, int bitDepth,
-                 const int2 *__restrict__ rdoqBits, const int *__restrict__ rdoqLast)
+                 const int2 *__restrict__ rdoqBits, const int *__restrict__ rdoqLast, const int *__restrict__ compact,
+                 const int *__restrict__ chunkBase)
 {
     // blocks that are plain-quantised, or whose levels all round to zero (cbf already 0), are not in the ordering
     int total = 0;
@@ -496,9 +628,10 @@ __global__ void __launch_bounds__(128)
         const int t = order[idx];
         const HvbRdoqMid mid = mids[t];
         const hvb_tu_task task = tasks[t];
-        const int c = hvbRdoqThread(pool + task.levels, coefTmp + task.levels, rdoqCtx + task.rdoq_ctx, mid, task.qscale, task.qshift,
+        const int ws = chunkBase[t >> 10] + compact[t];
+        const int c = hvbRdoqThread(pool + task.levels, coefTmp + ws, rdoqCtx + task.rdoq_ctx, mid, task.qscale, task.qshift,
                                     task.iqscale, task.log2n, task.cIdx, task.scanIdx, (task.flags & 2) != 0, (task.flags & 4) != 0, bitDepth,
-                                    recs + task.levels, rdoqBits + (size_t)task.rdoq_ctx * sizeof(hvb_rdoq_ctx),
+                                    recs + ws, rdoqBits + (size_t)task.rdoq_ctx * sizeof(hvb_rdoq_ctx),
                                     rdoqLast + (size_t)task.rdoq_ctx * hvb_rdoq::kLastTabPerCtx);
         out[t].cbf = c != 0;
     }
@@ -523,6 +656,7 @@ __global__ void __launch_bounds__(kWarps * 32)
         const int log2n = task.log2n, nn = 1 << log2n, count = nn * nn;
         const bool dst = task.trType != 0;
         const int cbf = out[t].cbf;
+        if (out[t].status == -1) continue; // rejected by the front stage
         int ss, sp, sr;
         const Sample *src = hvbBlockPtr<Sample>(planes, task.src, ss);
         const Sample *pred = hvbBlockPtr<Sample>(planes, task.pred, sp);
@@ -579,7 +713,8 @@ __global__ void __launch_bounds__(kWarps * 32)
 __global__ void __launch_bounds__(128)
     rdoqThreadKernel(int16_t *__restrict__ pool, HvbCoefRec *__restrict__ recs, const hvb_rdoq_ctx *__restrict__ rdoqCtx,
                      const hvb_rdoq_task *__restrict__ tasks, int n, const HvbRdoqMid *__restrict__ mids, int32_t *__restrict__ cbf,
-                     int bitDepth, const int2 *__restrict__ rdoqBits, const int *__restrict__ rdoqLast)
+                     int bitDepth, const int2 *__restrict__ rdoqBits, const int *__restrict__ rdoqLast, const int *__restrict__ compact,
+                     const int *__restrict__ chunkBase)
 {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
     {
@@ -588,7 +723,7 @@ __global__ void __launch_bounds__(128)
         const hvb_rdoq_task task = tasks[t];
         const int c = hvbRdoqThread(pool + task.dst, pool + task.src, rdoqCtx + task.rdoq_ctx, mid, task.qscale, task.qshift, task.iqscale,
                                     task.log2n, task.cIdx, task.scanIdx, (task.flags & 2) != 0, (task.flags & 4) != 0, bitDepth,
-                                    recs + task.dst, rdoqBits + (size_t)task.rdoq_ctx * sizeof(hvb_rdoq_ctx),
+                                    recs + chunkBase[t >> 10] + compact[t], rdoqBits + (size_t)task.rdoq_ctx * sizeof(hvb_rdoq_ctx),
                                     rdoqLast + (size_t)task.rdoq_ctx * hvb_rdoq::kLastTabPerCtx);
         cbf[t] = c != 0;
     }
@@ -642,7 +777,9 @@ int initRdoqTables(hvb_context *ctx)
     return HVB_OK;
 }
 
-// scratch layout of the pipeline: [coefTmp: count int16][recs: count HvbCoefRec][mids: n HvbRdoqMid]
+// scratch layout of the pipeline: [coefTmp: elems int16][recs: elems HvbCoefRec][mids: n HvbRdoqMid][buckets][order: n]
+// [compact: n][chunkBase: n/1024 + 1], elems = the RDOQ blocks' elements of this batch (an upper bound when the tasks
+// live on the device: the host cannot add them up without a round trip)
 struct ChainScratch
 {
     int16_t *coefTmp;
@@ -650,14 +787,18 @@ struct ChainScratch
     HvbRdoqMid *mids;
     int *buckets; // [2][kRdoqBuckets]: counts, cursors
     int *order;   // [n]
+    int *compact; // [n]
+    int *chunkBase;
+    int chunks;
 };
 
-int chainScratch(hvb_context *ctx, size_t count, size_t n, bool needCoefTmp, ChainScratch *cs)
+int chainScratch(hvb_context *ctx, size_t elems, size_t n, bool needCoefTmp, ChainScratch *cs)
 {
-    const size_t coefBytes = needCoefTmp ? ((count * sizeof(int16_t) + 255) & ~size_t(255)) : 0;
-    const size_t recBytes = (count * sizeof(HvbCoefRec) + 255) & ~size_t(255);
+    const size_t coefBytes = needCoefTmp ? ((elems * sizeof(int16_t) + 255) & ~size_t(255)) : 0;
+    const size_t recBytes = (elems * sizeof(HvbCoefRec) + 255) & ~size_t(255);
     const size_t midBytes = (n * sizeof(HvbRdoqMid) + 255) & ~size_t(255);
-    int rc = hvbEnsureScratch(ctx, coefBytes + recBytes + midBytes + 256 + n * sizeof(int));
+    const size_t chunks = (n + 1023) / 1024;
+    int rc = hvbEnsureScratch(ctx, coefBytes + recBytes + midBytes + 256 + (2 * n + chunks + 1) * sizeof(int));
     if (rc) return rc;
     char *base = static_cast<char *>(ctx->scratch);
     cs->coefTmp = reinterpret_cast<int16_t *>(base);
@@ -665,7 +806,25 @@ int chainScratch(hvb_context *ctx, size_t count, size_t n, bool needCoefTmp, Cha
     cs->mids = reinterpret_cast<HvbRdoqMid *>(base + coefBytes + recBytes);
     cs->buckets = reinterpret_cast<int *>(base + coefBytes + recBytes + midBytes);
     cs->order = cs->buckets + 64;
+    cs->compact = cs->order + n;
+    cs->chunkBase = cs->compact + n;
+    cs->chunks = (int)chunks;
     return HVB_OK;
+}
+
+// elements the RDOQ workspace must hold for a batch
+template <class Task, class F>
+size_t workspaceElems(hvb_context *ctx, const Task *tasks, int n, hvb_mem mem, F count)
+{
+    size_t bound = (size_t)n * 1024;
+    if (mem == HVB_HOST)
+    {
+        bound = 0;
+        for (int i = 0; i < n; ++i) bound += count(tasks[i]);
+    }
+    else if (bound > ctx->coeffPoolCount)
+        bound = ctx->coeffPoolCount; // distinct blocks of one pool cannot add up to more
+    return bound;
 }
 
 int gridWarps(hvb_context *ctx, int n, int warps, int perSm)
@@ -754,7 +913,11 @@ extern "C" int hvb_tu_chain_batch(hvb_context *ctx, const hvb_tu_task *tasks, in
     int rc = initRdoqTables(ctx);
     if (rc) return rc;
     ChainScratch cs;
-    rc = chainScratch(ctx, ctx->coeffPoolCount, (size_t)n, true, &cs);
+    const size_t elems = workspaceElems(ctx, tasks, n, mem, [](const hvb_tu_task &t) {
+        return (t.flags & 1) && t.log2n >= 2 && t.log2n <= 5 ? size_t(1) << (2 * t.log2n) : size_t(0);
+    });
+    if (elems && !ctx->rdoqCtx) return hvbFail(ctx, HVB_ERR_INVALID, "hvb_tu_chain_batch: RDOQ tasks before hvb_rdoq_contexts_upload");
+    rc = chainScratch(ctx, elems, (size_t)n, true, &cs);
     if (rc) return rc;
     HvbStaged st;
     rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(hvb_tu_result) * n, mem, &st);
@@ -765,17 +928,22 @@ extern "C" int hvb_tu_chain_batch(hvb_context *ctx, const hvb_tu_task *tasks, in
     int gridT = (n + 127) / 128;
     if (gridT > ctx->smCount * 16) gridT = ctx->smCount * 16;
     cudaMemsetAsync(cs.buckets, 0, 2 * kRdoqBuckets * sizeof(int), ctx->stream);
+    scanLocalKernel<<<cs.chunks, 1024, 0, ctx->stream>>>(TuCount{dT}, n, cs.compact, cs.chunkBase);
+    HVB_LAUNCH_CHECK(ctx, "scanLocalKernel");
+    scanBlocksKernel<<<1, 1024, 0, ctx->stream>>>(cs.chunkBase, cs.chunks);
+    HVB_LAUNCH_CHECK(ctx, "scanBlocksKernel");
+    const unsigned poolCount = (unsigned)(ctx->coeffPoolCount > 0x7fffffffu ? 0x7fffffffu : ctx->coeffPoolCount);
     if (ctx->bps == 1)
         tuFrontKernel<uint8_t><<<gridW, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, cs.coefTmp, ctx->rdoqCtx, dT, n, dO, cs.mids,
-                                                                       cs.buckets, ctx->bitDepth);
+                                                                       cs.buckets, ctx->bitDepth, cs.compact, cs.chunkBase, ctx->rdoqCtx ? ctx->rdoqCtxCount : 0, poolCount);
     else
         tuFrontKernel<uint16_t><<<gridW, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, cs.coefTmp, ctx->rdoqCtx, dT, n, dO, cs.mids,
-                                                                        cs.buckets, ctx->bitDepth);
+                                                                        cs.buckets, ctx->bitDepth, cs.compact, cs.chunkBase, ctx->rdoqCtx ? ctx->rdoqCtxCount : 0, poolCount);
     HVB_LAUNCH_CHECK(ctx, "tuFrontKernel");
     tuOrderKernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(cs.mids, n, cs.buckets, cs.buckets + kRdoqBuckets, cs.order);
     HVB_LAUNCH_CHECK(ctx, "tuOrderKernel");
     tuRdoqKernel<<<gridT, 128, 0, ctx->stream>>>(ctx->coeffPool, cs.coefTmp, cs.recs, ctx->rdoqCtx, dT, n, dO, cs.mids, cs.buckets, cs.order,
-                                                 ctx->bitDepth, ctx->rdoqBits, ctx->rdoqLast);
+                                                 ctx->bitDepth, ctx->rdoqBits, ctx->rdoqLast, cs.compact, cs.chunkBase);
     HVB_LAUNCH_CHECK(ctx, "tuRdoqKernel");
     if (ctx->bps == 1)
         tuBackKernel<uint8_t><<<gridW, kWarps * 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, dT, n, dO, ctx->bitDepth);
@@ -793,18 +961,25 @@ extern "C" int hvb_rdoq_batch(hvb_context *ctx, const hvb_rdoq_task *tasks, int 
     int rc = initRdoqTables(ctx);
     if (rc) return rc;
     ChainScratch cs;
-    rc = chainScratch(ctx, ctx->coeffPoolCount, (size_t)n, false, &cs);
+    const size_t elems = workspaceElems(ctx, tasks, n, mem, [](const hvb_rdoq_task &t) {
+        return t.log2n >= 2 && t.log2n <= 5 ? size_t(1) << (2 * t.log2n) : size_t(0);
+    });
+    rc = chainScratch(ctx, elems, (size_t)n, false, &cs);
     if (rc) return rc;
     HvbStaged st;
     rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, cbf, sizeof(int32_t) * n, mem, &st);
     if (rc) return rc;
     const auto *dT = static_cast<const hvb_rdoq_task *>(st.dTasks);
     auto *dC = static_cast<int32_t *>(st.dOut);
+    scanLocalKernel<<<cs.chunks, 1024, 0, ctx->stream>>>(RdoqCount{dT}, n, cs.compact, cs.chunkBase);
+    HVB_LAUNCH_CHECK(ctx, "scanLocalKernel");
+    scanBlocksKernel<<<1, 1024, 0, ctx->stream>>>(cs.chunkBase, cs.chunks);
+    HVB_LAUNCH_CHECK(ctx, "scanBlocksKernel");
     int gridT = (n + 127) / 128;
     if (gridT > ctx->smCount * 16) gridT = ctx->smCount * 16;
     rdoqPrepassKernel<<<gridWarps(ctx, n, kWarps, 8), kWarps * 32, 0, ctx->stream>>>(ctx->coeffPool, ctx->rdoqCtx, dT, n, cs.mids, dC, ctx->bitDepth);
     HVB_LAUNCH_CHECK(ctx, "rdoqPrepassKernel");
-    rdoqThreadKernel<<<gridT, 128, 0, ctx->stream>>>(ctx->coeffPool, cs.recs, ctx->rdoqCtx, dT, n, cs.mids, dC, ctx->bitDepth, ctx->rdoqBits, ctx->rdoqLast);
+    rdoqThreadKernel<<<gridT, 128, 0, ctx->stream>>>(ctx->coeffPool, cs.recs, ctx->rdoqCtx, dT, n, cs.mids, dC, ctx->bitDepth, ctx->rdoqBits, ctx->rdoqLast, cs.compact, cs.chunkBase);
     HVB_LAUNCH_CHECK(ctx, "rdoqThreadKernel");
     return hvbStageOut(ctx, cbf, sizeof(int32_t) * n, mem, st);
 }

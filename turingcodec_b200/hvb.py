@@ -43,7 +43,7 @@ tu_task_t = np.dtype([("src", block_t), ("pred", block_t), ("rec", block_t), ("l
                       ("trType", "i1"), ("cIdx", "i1"), ("flags", "i1"), ("qscale", "<i4"), ("qshift", "<i4"),
                       ("qoffset", "<i4"), ("iqscale", "<i4"), ("iqshift", "<i4"), ("scanIdx", "i1"),
                       ("reserved", "i1", 3), ("rdoq_ctx", "<i4")])
-tu_result_t = np.dtype([("ssd", "<u4"), ("ssdPred", "<u4"), ("cbf", "<i4"), ("reserved", "<i4")])
+tu_result_t = np.dtype([("ssd", "<u4"), ("ssdPred", "<u4"), ("cbf", "<i4"), ("status", "<i4"), ("sadQuad", "<u4", (4,))])
 rdoq_ctx_t = np.dtype([("sig_coeff_flag", "u1", 44), ("greater1_flag", "u1", 24), ("greater2_flag", "u1", 6),
                        ("coded_sub_block_flag", "u1", 4), ("last_x_prefix", "u1", 18), ("last_y_prefix", "u1", 18),
                        ("cbf_luma", "u1", 2), ("cbf_cbcr", "u1", 5), ("rqt_root_cbf", "u1", 1),
@@ -89,7 +89,7 @@ _SIZES = {
     "block": (block_t, 8), "metric": (metric_task_t, 24), "sad4": (sad4_task_t, 32), "pred": (pred_task_t, 32),
     "subtract_bi": (subtract_bi_task_t, 32), "interp_satd": (interp_satd_task_t, 20), "intra": (intra_task_t, 16),
     "intra_sweep": (intra_sweep_task_t, 24), "transform": (transform_task_t, 16), "quant": (quant_task_t, 24),
-    "ita": (ita_task_t, 24), "tu": (tu_task_t, 60), "tu_result": (tu_result_t, 16), "rdoq_ctx": (rdoq_ctx_t, 136),
+    "ita": (ita_task_t, 24), "tu": (tu_task_t, 60), "tu_result": (tu_result_t, 32), "rdoq_ctx": (rdoq_ctx_t, 136),
     "rdoq": (rdoq_task_t, 28), "me": (me_task_t, 64), "me_result": (me_result_t, 56),
     "pu_cost": (pu_cost_task_t, 24), "me_bi": (me_bi_task_t, 64), "me_bi_result": (me_bi_result_t, 32),
 }
