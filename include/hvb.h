@@ -68,6 +68,13 @@ int hvb_sync(hvb_context *ctx);
  * pictures / pool regions that no batch in flight reads (double-buffer).  Results and source buffers belong to the
  * library until hvb_sync() returns.  Calls with pageable buffers keep the blocking behaviour. */
 int hvb_set_pipelined(hvb_context *ctx, int on);
+/* Page-locked host memory that the device can address directly (cudaHostAlloc, portable + mapped): an encoder's task /
+ * result arena.  With unified addressing the returned pointer is valid on both sides, so arrays in it may be passed
+ * with HVB_HOST (copied from / to without staging) or with HVB_DEVICE (the kernels read the tasks and write the results
+ * across the bus themselves: no copy is enqueued at all -- the cheapest form for the small, latency-bound batches of a
+ * submission queue; results are valid after hvb_sync). */
+int hvb_host_alloc(hvb_context *ctx, size_t bytes, void **out);
+int hvb_host_free(hvb_context *ctx, void *ptr);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t hvb_launch_count(hvb_context *ctx);
 /* 1 when the device is present and kernels for it are in this binary */
@@ -85,7 +92,8 @@ int hvb_picture_upload(hvb_context *ctx, int pic, int cIdx, const void *host, in
 int hvb_picture_download(hvb_context *ctx, int pic, int cIdx, void *host, intptr_t stride,
                          int y0, int rows);
 /* rectangle variants (x0,y0,w,h in samples of that plane; the rectangle may lie in the padding):
- * what the per-block table shim and the encoder's per-CTU reconstruction commit (turing/Write.h:828-830) use */
+ * what the per-block table shim and the encoder's per-CTU reconstruction commit (turing/Write.h:828-830) use.
+ * In pipelined mode an upload from page-locked memory is only enqueued (as hvb_picture_upload). */
 int hvb_picture_upload_rect(hvb_context *ctx, int pic, int cIdx, const void *host, intptr_t stride,
                             int x0, int y0, int w, int h);
 int hvb_picture_download_rect(hvb_context *ctx, int pic, int cIdx, void *host, intptr_t stride,
@@ -95,6 +103,10 @@ int hvb_picture_pad(hvb_context *ctx, int pic);
 /* device-to-device copy of all three planes incl. their padding (same geometry required): the copy of the deblocked
  * picture that SAO filters from (turing/TaskSao.cpp:96-121) */
 int hvb_picture_copy(hvb_context *ctx, int dst_pic, int src_pic);
+/* A one-plane picture (cIdx 0, no padding) over caller memory from hvb_host_alloc: the kernels read and write it across
+ * the bus, nothing is copied.  For blocks a caller supplies or wants back per task (a CU's prediction and reconstruction,
+ * hvbenc_tu_chain) when a copy per block would cost more than the bytes.  hvb_picture_destroy releases the id only. */
+int hvb_picture_wrap(hvb_context *ctx, void *host, intptr_t stride, int width, int height, int *pic);
 /* raw device view of a plane: pointer to sample (0,0) and stride in samples (for zero-copy fills) */
 int hvb_picture_plane(hvb_context *ctx, int pic, int cIdx, void **dev_ptr, intptr_t *stride);
 

@@ -1,0 +1,33 @@
+// integration/turing_hooks_state.h -- what turing_hooks.hpp (compiled into the reference encoder's translation units) and
+// turing_hooks.cpp (the process-wide state) share; free of reference types.
+#ifndef INCLUDED_turing_hooks_state_h
+#define INCLUDED_turing_hooks_state_h
+
+#include "hvb_encoder.h"
+#include <cstring>
+
+namespace hvbhooks {
+
+bool on();                                                        // HVB_BATCHED=0 in the environment switches the hooks off
+hvbenc *session(int bytesPerSample, int bitDepth, int width, int height); // created on first use
+int pictureId(const void *key, bool fresh);
+void fatal(const char *what, int rc);
+unsigned enabledMask();                                           // HVB_HOOKS: bit 0 me, 1 bi, 2 pu cost, 3 intra, 4 tu
+
+struct Memo // per-thread results of tasks issued ahead of the reference's control flow
+{
+    static const int kMe = 4, kPu = 16;
+    hvb_me_task meTask[kMe];
+    hvb_me_result meResult[kMe];
+    int nMe;
+    hvb_pu_cost_task puTask[kPu];
+    int32_t puResult[kPu][3];
+    int nPu;
+    void clear() { nMe = nPu = 0; }
+};
+Memo &memo();
+
+
+} // namespace hvbhooks
+
+#endif

@@ -45,6 +45,8 @@ cudaError_t cudaMalloc(void **p, size_t bytes) { return posix_memalign(p, 256, b
 cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 cudaError_t cudaMallocHost(void **p, size_t bytes) { return posix_memalign(p, 256, bytes ? bytes : 1) ? cudaErrorMemoryAllocation : cudaSuccess; }
 cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+cudaError_t cudaHostAlloc(void **p, size_t bytes, unsigned) { return posix_memalign(p, 256, bytes ? bytes : 1) ? cudaErrorMemoryAllocation : cudaSuccess; }
+cudaError_t cudaHostGetDevicePointer(void **dev, void *host, unsigned) { *dev = host; return cudaSuccess; }
 cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *attr, const void *)
 {
     memset(attr, 0, sizeof(*attr));

@@ -184,6 +184,21 @@ int hvbUpload(hvb_context *ctx, void *dev, size_t devPitch, const void *host, si
 
 extern "C" int64_t hvb_launch_count(hvb_context *ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int hvb_host_alloc(hvb_context *ctx, size_t bytes, void **out)
+{
+    HVB_CHECK_ARGS(ctx, out && bytes > 0);
+    cudaSetDevice(ctx->device);
+    *out = nullptr;
+    return hvbCuda(ctx, cudaHostAlloc(out, bytes, cudaHostAllocPortable | cudaHostAllocMapped), "hvb_host_alloc");
+}
+
+extern "C" int hvb_host_free(hvb_context *ctx, void *ptr)
+{
+    HVB_CHECK_ARGS(ctx, ptr);
+    cudaSetDevice(ctx->device);
+    return hvbCuda(ctx, cudaFreeHost(ptr), "hvb_host_free");
+}
+
 // ---------------------------------------------------------------------------------------------
 // Pictures
 // ---------------------------------------------------------------------------------------------
@@ -238,6 +253,34 @@ extern "C" int hvb_picture_create(hvb_context *ctx, int width, int height, int p
     return HVB_OK;
 }
 
+extern "C" int hvb_picture_wrap(hvb_context *ctx, void *host, intptr_t stride, int width, int height, int *pic)
+{
+    HVB_CHECK_ARGS(ctx, pic && host && width > 0 && height > 0 && stride >= width);
+    int id = -1;
+    for (int i = 0; i < HVB_MAX_PICTURES; ++i)
+        if (!ctx->pictures[i].live)
+        {
+            id = i;
+            break;
+        }
+    if (id < 0) return hvbFail(ctx, HVB_ERR_NOMEM, "picture table full");
+    cudaSetDevice(ctx->device);
+    void *dev = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&dev, host, 0);
+    if (e != cudaSuccess) return hvbCuda(ctx, e, "hvb_picture_wrap: not memory from hvb_host_alloc");
+    HvbPicture &p = ctx->pictures[id];
+    p = HvbPicture{};
+    p.width = width;
+    p.height = height;
+    p.pad = 0;
+    for (int c = 0; c < 3; ++c) p.plane[c] = HvbPlane{nullptr, 0, 0, 0, 0, 0};
+    p.plane[0] = HvbPlane{dev, (int32_t)stride, width, height, 0, 0};
+    p.live = true;
+    ctx->planesDirty = true;
+    *pic = id;
+    return HVB_OK;
+}
+
 extern "C" int hvb_picture_destroy(hvb_context *ctx, int pic)
 {
     HVB_CHECK_ARGS(ctx, pic >= 0 && pic < HVB_MAX_PICTURES && ctx->pictures[pic].live);
@@ -246,7 +289,7 @@ extern "C" int hvb_picture_destroy(hvb_context *ctx, int pic)
     HvbPicture &p = ctx->pictures[pic];
     for (int c = 0; c < 3; ++c)
     {
-        cudaFree(p.alloc[c]);
+        if (p.alloc[c]) cudaFree(p.alloc[c]); // a wrapped picture owns nothing
         p.alloc[c] = nullptr;
     }
     if (p.lfInfo || p.saoInfo)
@@ -326,8 +369,8 @@ static int rectCopy(hvb_context *ctx, int pic, int cIdx, void *host, intptr_t st
     char *dev = static_cast<char *>(pl.base) + ((intptr_t)y0 * pl.stride + x0) * ctx->bps;
     cudaError_t e;
     if (upload)
-        e = cudaMemcpy2DAsync(dev, (size_t)pl.stride * ctx->bps, host, (size_t)stride * ctx->bps, (size_t)w * ctx->bps, h,
-                              cudaMemcpyHostToDevice, ctx->stream);
+        return hvbUpload(ctx, dev, (size_t)pl.stride * ctx->bps, host, (size_t)stride * ctx->bps, (size_t)w * ctx->bps, h,
+                         "hvb_picture_upload_rect");
     else
         e = cudaMemcpy2DAsync(host, (size_t)stride * ctx->bps, dev, (size_t)pl.stride * ctx->bps, (size_t)w * ctx->bps, h,
                               cudaMemcpyDeviceToHost, ctx->stream);

@@ -916,7 +916,7 @@ extern "C" int hvb_tu_chain_batch(hvb_context *ctx, const hvb_tu_task *tasks, in
     const size_t elems = workspaceElems(ctx, tasks, n, mem, [](const hvb_tu_task &t) {
         return (t.flags & 1) && t.log2n >= 2 && t.log2n <= 5 ? size_t(1) << (2 * t.log2n) : size_t(0);
     });
-    if (elems && !ctx->rdoqCtx) return hvbFail(ctx, HVB_ERR_INVALID, "hvb_tu_chain_batch: RDOQ tasks before hvb_rdoq_contexts_upload");
+    if (mem == HVB_HOST && elems && !ctx->rdoqCtx) return hvbFail(ctx, HVB_ERR_INVALID, "hvb_tu_chain_batch: RDOQ tasks before hvb_rdoq_contexts_upload");
     rc = chainScratch(ctx, elems, (size_t)n, true, &cs);
     if (rc) return rc;
     HvbStaged st;
