@@ -15,6 +15,14 @@ BEFORE, AFTER, REPLACE = "before", "after", "replace"
 
 PATCHES = {
     "Search.hpp": [
+        ("#include \"Aps.h\"\n", AFTER,
+         "namespace hvbhooks { template <class H> bool intraSweep(H &h, IntraPartition const &intraPartition, int32_t *distortion); }\n"),
+        # the 35-mode loop: the candidate bookkeeping of an iteration stays, its prediction + SATD comes from the device
+        ("        for (int n = 0; n < 35; ++n)\n        {\n            candidate.resetPieces();\n", BEFORE,
+         "        int32_t hvbDistortion[35];\n"
+         "        const bool hvbSwept = hvbhooks::intraSweep(h, intraPartition, hvbDistortion);\n"),
+        ("                distortion = predictIntraLuma(transform_tree(e.x0 + i, e.y0 + j, e.x0, e.y0, e.log2CbSize - e.split, e.split, e.blkIdx), h);\n", REPLACE,
+         "                distortion = hvbSwept ? hvbDistortion[n] : predictIntraLuma(transform_tree(e.x0 + i, e.y0 + j, e.x0, e.y0, e.log2CbSize - e.split, e.split, e.blkIdx), h);\n"),
         # the hooks need LimitFullPelMv / StateMeFullPel (declared above searchMotionBi); searchMotionUni sits above them
         ("template <class H> static void searchMotionUni(H &h, int refList)\n{\n", BEFORE,
          "namespace hvbhooks { template <class H> bool searchMotionUni(H &h, int refList); }\n"),
@@ -27,6 +35,27 @@ PATCHES = {
         # measurePuCost: the prediction + SATD block
         ("    int32_t satd[3];\n    {\n        StateReconstructedPicture<Sample> *stateReconstructedPicture = h;\n", REPLACE,
          "    int32_t satd[3];\n    if (!hvbhooks::puCost(h, pu, puData, satd))\n    {\n        StateReconstructedPicture<Sample> *stateReconstructedPicture = h;\n"),
+    ],
+    "Reconstruct.cpp": [
+        ("#include \"Rdoq.h\"\n", AFTER, "#define HVBHOOKS_RECONSTRUCT\n#include \"turing_hooks.hpp\"\n"),
+        # the root of an inter CU's transform tree: all its blocks in one submission
+        ("        stateCodedData->transformTree.word0().split_transform_flag = h[split_transform_flag()];\n\n        Syntax<transform_tree>::go(tt, h);\n", BEFORE,
+         "        if (tt.trafoDepth == 0) hvbhooks::prefetchInterCu(h, tt, !!h[split_transform_flag()]);\n"),
+        # ReconstructInterBlock::go: transform .. SSD of one block from the device
+        ("        bool bUseTSkip = false;\n\n        static int nn = 0;\n", AFTER,
+         "        const hvbhooks::TuBlock *hvbTu = (!checkTSkip && candidate->noresidual == 0) ? hvbhooks::interBlock(h, rc) : nullptr;\n"),
+        ("        if (candidate->noresidual == 0)\n        {\n            int constexpr bitDepth = 2 * sizeof(Sample) + 6;\n", REPLACE,
+         "        if (candidate->noresidual == 0 && !hvbTu)\n        {\n            int constexpr bitDepth = 2 * sizeof(Sample) + 6;\n"),
+        ("        bool cbf;\n        if (candidate->noresidual == 0)\n        {\n            if (stateEncode->rdoq)\n", REPLACE,
+         "        bool cbf;\n        if (hvbTu)\n        {\n            cbf = hvbTu->cbf != 0;\n"
+         "            memcpy(quantizedCoefficients.p, hvbTu->levels, sizeof(int16_t) * n);\n        }\n"
+         "        else if (candidate->noresidual == 0)\n        {\n            if (stateEncode->rdoq)\n"),
+        ("        if (candidate->noresidual == 0)\n        {\n            // add to prediction\n", REPLACE,
+         "        if (candidate->noresidual == 0 && !hvbTu)\n        {\n            // add to prediction\n"),
+        ("backupSSDNoTSkip = stateEncodeSubstream->ssd[rc.cIdx] + ssd(sourceSamples.p, sourceSamples.stride, recSamples.p, recSamples.stride, nTbS, nTbS);", REPLACE,
+         "backupSSDNoTSkip = stateEncodeSubstream->ssd[rc.cIdx] + (hvbTu ? hvbTu->ssd : ssd(sourceSamples.p, sourceSamples.stride, recSamples.p, recSamples.stride, nTbS, nTbS));"),
+        ("stateEncodeSubstream->ssdPrediction[rc.cIdx] += ssd(sourceSamples.p, sourceSamples.stride, predSamples.p, predSamples.stride, nTbS, nTbS);", REPLACE,
+         "stateEncodeSubstream->ssdPrediction[rc.cIdx] += (hvbTu ? hvbTu->ssdPred : ssd(sourceSamples.p, sourceSamples.stride, predSamples.p, predSamples.stride, nTbS, nTbS));"),
     ],
     "Search.cpp": [],
     "SearchLzcnt.cpp": [],

@@ -73,6 +73,12 @@ int pictureId(const void *key, bool fresh)
     return pic;
 }
 
+TuMemo &tuMemo()
+{
+    static thread_local TuMemo m = {};
+    return m;
+}
+
 Memo &memo()
 {
     static thread_local Memo m = {};

@@ -221,7 +221,204 @@ template <class H> bool puCost(H &h, const prediction_unit &pu, const PuData &pu
     return true;
 }
 
+
+// the 35-mode SATD sweep of searchIntraPartition (turing/Search.hpp:113-142 -> predictIntraLuma, turing/Reconstruct.cpp:630-712)
+// for a partition of 4x4 .. 32x32: the reference samples have been substituted by the caller (:54-61); the filtered
+// array is derived on the device (turing/IntraReferenceSamples.h:373-419).  Leaves what the loop's last iteration leaves
+// in the substream state (predictIntraLuma resets ssd and sets satd, Reconstruct.cpp:1140-1158).
+template <class H> bool intraSweep(H &h, IntraPartition const &intraPartition, int32_t distortion[35])
+{
+    if (!usable(h) || !(enabledMask() & 8)) return false;
+    typedef typename SampleOf<H>::Type Sample;
+    StateEncodeSubstream<Sample> *stateEncodeSubstream = h;
+    const int log2n = intraPartition.log2CbSize - intraPartition.split;
+    if (log2n < 2 || log2n > 5) return false;
+    hvb_intra_sweep_task t;
+    memset(&t, 0, sizeof(t));
+    t.src.pic = (int16_t)inputPicture(h);
+    t.src.cIdx = 0;
+    t.src.x = (int16_t)xPositionOf(intraPartition);
+    t.src.y = (int16_t)yPositionOf(intraPartition);
+    t.log2n = (int8_t)log2n;
+    t.cIdx = 0;
+    t.strong_intra_smoothing = (int8_t)h[strong_intra_smoothing_enabled_flag()];
+    auto &unfiltered = stateEncodeSubstream->unfiltered[0];
+    const int rc = hvbenc_intra_sweep(sessionOf(h), &t, &unfiltered(-1, (2 << log2n) - 1), distortion);
+    if (rc) fatal("hvbenc_intra_sweep", rc);
+    StateEncodeSubstreamBase *base = h;
+    base->satd = distortion[34];
+    base->ssd[0] = base->ssd[1] = base->ssd[2] = 0;
+    return true;
+}
+
 #endif // HVBHOOKS_SEARCH
+
+#ifdef HVBHOOKS_RECONSTRUCT
+
+// ---- transform blocks of an inter CU (turing/Reconstruct.cpp:733-857) ------------------------------------------------
+
+inline void snapshotContexts(Contexts &contexts, double lambda, hvb_rdoq_ctx &s)
+{
+    memset(&s, 0, sizeof(s));
+    for (int i = 0; i < 44; ++i) s.sig_coeff_flag[i] = contexts.get<sig_coeff_flag>(i).state;
+    for (int i = 0; i < 24; ++i) s.greater1_flag[i] = contexts.get<coeff_abs_level_greater1_flag>(i).state;
+    for (int i = 0; i < 6; ++i) s.greater2_flag[i] = contexts.get<coeff_abs_level_greater2_flag>(i).state;
+    for (int i = 0; i < 4; ++i) s.coded_sub_block_flag[i] = contexts.get<coded_sub_block_flag>(i).state;
+    for (int i = 0; i < 18; ++i) s.last_x_prefix[i] = contexts.get<last_sig_coeff_x_prefix>(i).state;
+    for (int i = 0; i < 18; ++i) s.last_y_prefix[i] = contexts.get<last_sig_coeff_y_prefix>(i).state;
+    for (int i = 0; i < 2; ++i) s.cbf_luma[i] = contexts.get<cbf_luma>(i).state;
+    for (int i = 0; i < 4; ++i) s.cbf_cbcr[i] = contexts.get<cbf_cX>(i).state;
+    s.rqt_root_cbf[0] = contexts.get<rqt_root_cbf>(0).state;
+    s.lambda = lambda;
+}
+
+// the task of one inter transform block, parameters as ReconstructInterBlock::go derives them (:778-790)
+template <class H> void fillInterTuTask(H &h, int x0, int y0, int cIdx, int log2n, hvb_tu_task &t)
+{
+    StateEncode *stateEncode = h;
+    memset(&t, 0, sizeof(t));
+    t.src.pic = (int16_t)inputPicture(h);
+    t.src.cIdx = (int16_t)cIdx;
+    t.src.x = (int16_t)(x0 >> (cIdx ? 1 : 0));
+    t.src.y = (int16_t)(y0 >> (cIdx ? 1 : 0));
+    t.log2n = (int8_t)log2n;
+    t.trType = 0;
+    t.cIdx = (int8_t)cIdx;
+    const int bitDepth = cIdx ? h[BitDepthC()] : h[BitDepthY()];
+    int const qpScaled = static_cast<QpState *>(h)->getQp(cIdx);
+    int const shiftQuantise = 29 - bitDepth + qpScaled / 6 - log2n;
+    int const offsetQuantise = 85 << (shiftQuantise - 9);
+    t.qscale = static_cast<QpState *>(h)->getQuantiseScale(cIdx);
+    t.qshift = shiftQuantise;
+    t.qoffset = offsetQuantise >> (shiftQuantise - 16);
+    t.iqscale = static_cast<QpState *>(h)->getScale(cIdx);
+    t.iqshift = log2n - 1 + bitDepth - 8;
+    t.flags = (int8_t)((stateEncode->rdoq ? 1 : 0) | (h[sign_data_hiding_enabled_flag()] ? 4 : 0));
+}
+
+// Issue the given blocks of the current CU in one submission; results into the memo.
+template <class H> void issueInterBlocks(H &h, const int (*blocks)[4] /* x0, y0, cIdx, log2n */, int count)
+{
+    typedef typename SampleOf<H>::Type Sample;
+    StateEncodeSubstream<Sample> *stateEncodeSubstream = h;
+    Candidate<Sample> *candidate = h;
+    coding_quadtree const *cqt = h;
+    StateEncode *stateEncode = h;
+    TuMemo &m = tuMemo();
+    hvb_tu_task tasks[TuMemo::kBlocks];
+    hvb_tu_result results[TuMemo::kBlocks];
+    const void *pred[TuMemo::kBlocks];
+    void *rec[TuMemo::kBlocks];
+    intptr_t predStride[TuMemo::kBlocks], recStride[TuMemo::kBlocks];
+    int16_t *levels[TuMemo::kBlocks];
+    int n = 0;
+    for (int i = 0; i < count && m.n + n < TuMemo::kBlocks; ++i)
+    {
+        const int x0 = blocks[i][0], y0 = blocks[i][1], cIdx = blocks[i][2], log2n = blocks[i][3];
+        fillInterTuTask(h, x0, y0, cIdx, log2n, tasks[n]);
+        // scanIdx of an inter block is 0 (H.265 7.4.9.11: mode dependent scans are intra only)
+        tasks[n].scanIdx = 0;
+        auto predPiece = candidate->stateReconstructionCache->components[cIdx].get(stateEncodeSubstream->interPieces[cIdx][0]);
+        auto predSamples = predPiece.offset((x0 - cqt->x0) >> (cIdx ? 1 : 0), (y0 - cqt->y0) >> (cIdx ? 1 : 0));
+        auto recPiece = candidate->stateReconstructionCache->components[cIdx].get(stateEncodeSubstream->interPieces[cIdx][1 + candidate->rqtdepth]);
+        auto recSamples = recPiece.offset((x0 - cqt->x0) >> (cIdx ? 1 : 0), (y0 - cqt->y0) >> (cIdx ? 1 : 0));
+        pred[n] = predSamples.p, predStride[n] = predSamples.stride;
+        rec[n] = recSamples.p, recStride[n] = recSamples.stride;
+        TuBlock &b = m.block[m.n + n];
+        b.x0 = x0, b.y0 = y0, b.cIdx = cIdx, b.log2n = log2n;
+        levels[n] = b.levels;
+        ++n;
+    }
+    if (!n) return;
+    hvb_rdoq_ctx snapshot;
+    if (stateEncode->rdoq) snapshotContexts(*static_cast<Contexts *>(h), static_cast<StateEncodePicture *>(h)->lambda, snapshot);
+    const int rc = hvbenc_tu_chain(sessionOf(h), tasks, n, stateEncode->rdoq ? &snapshot : nullptr, pred, predStride, rec, recStride, levels, results);
+    if (rc) fatal("hvbenc_tu_chain", rc);
+    for (int i = 0; i < n; ++i)
+    {
+        TuBlock &b = m.block[m.n + i];
+        b.ssd = results[i].ssd, b.ssdPred = results[i].ssdPred, b.cbf = results[i].cbf;
+    }
+    m.n += n;
+}
+
+// One block of ReconstructInterBlock::go: the reconstruction has been written to the block's piece of the cache
+// (interPieces[cIdx][1 + rqtdepth]); returns levels, SSDs and cbf.  Blocks issued ahead by prefetchInterCu are found
+// in the memo; anything else costs its own round trip.
+template <class H> const TuBlock *interBlock(H &h, residual_coding const &rc)
+{
+    if (!usable(h) || !(enabledMask() & 16)) return nullptr;
+    TuMemo &m = tuMemo();
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        for (int i = 0; i < m.n; ++i)
+        {
+            TuBlock &b = m.block[i];
+            if (b.x0 == rc.x0 && b.y0 == rc.y0 && b.cIdx == rc.cIdx && b.log2n == rc.log2TrafoSize) return &b;
+        }
+        if (pass) break;
+        if (m.n == TuMemo::kBlocks) m.n = 0;
+        const int one[1][4] = {{rc.x0, rc.y0, rc.cIdx, rc.log2TrafoSize}};
+        issueInterBlocks(h, one, 1);
+    }
+    return nullptr;
+}
+
+// reconstructInter (turing/Reconstruct.cpp:1237-...), before the tree walk: forget the previous CU's blocks
+inline void beginInterCu() { tuMemo().n = 0; }
+
+
+// ReconstructInter<transform_tree>::go at the root of a CU's transform tree (turing/Reconstruct.cpp:58-96), split flag
+// known: every block the walk is about to visit goes to the device in one submission.  The children of a split root
+// are assumed not to split again (true unless max_transform_hierarchy_depth_inter > 1); a block that is not found in
+// the memo later costs its own round trip, nothing else.
+template <class H> void prefetchInterCu(H &h, transform_tree const &tt, bool split)
+{
+    beginInterCu();
+    if (!usable(h) || !(enabledMask() & 16)) return;
+    typedef typename SampleOf<H>::Type Sample;
+    Candidate<Sample> *candidate = h;
+    if (candidate->noresidual) return;
+    int blocks[TuMemo::kBlocks][4];
+    int n = 0;
+    const int log2n = tt.log2TrafoSize;
+    auto add = [&](int x0, int y0, int cIdx, int log2) {
+        if (log2 == 2 && h[transform_skip_enabled_flag()]) return; // transform skip is decided on the host (:860-1030)
+        blocks[n][0] = x0, blocks[n][1] = y0, blocks[n][2] = cIdx, blocks[n][3] = log2;
+        ++n;
+    };
+    if (!split)
+    {
+        if (log2n > 5) return;
+        add(tt.x0, tt.y0, 0, log2n);
+        add(tt.x0, tt.y0, 1, log2n - 1);
+        add(tt.x0, tt.y0, 2, log2n - 1);
+    }
+    else
+    {
+        const int child = log2n - 1;
+        if (child > 5 || child < 2) return;
+        for (int blkIdx = 0; blkIdx < 4; ++blkIdx)
+        {
+            const int x = tt.x0 + ((blkIdx & 1) << child), y = tt.y0 + ((blkIdx >> 1) << child);
+            add(x, y, 0, child);
+            if (child > 2)
+            {
+                add(x, y, 1, child - 1);
+                add(x, y, 2, child - 1);
+            }
+        }
+        if (child == 2)
+        {
+            // 4x4 luma blocks: the 4x4 chroma blocks of the parent are coded with its last child (H.265 7.3.8.10)
+            add(tt.x0, tt.y0, 1, 2);
+            add(tt.x0, tt.y0, 2, 2);
+        }
+    }
+    issueInterBlocks(h, blocks, n);
+}
+
+#endif // HVBHOOKS_RECONSTRUCT
 
 // ---- pictures ------------------------------------------------------------------------------------------------------
 

@@ -27,6 +27,23 @@ struct Memo // per-thread results of tasks issued ahead of the reference's contr
 };
 Memo &memo();
 
+struct TuBlock // what the device returns for one transform block
+{
+    int x0, y0, cIdx, log2n;
+    uint32_t ssd, ssdPred;
+    int cbf;
+    int16_t levels[32 * 32];
+};
+
+struct TuMemo // per-thread: the blocks of the CU being reconstructed, issued together ahead of the tree walk
+{
+    static const int kBlocks = 24;
+    TuBlock block[kBlocks];
+    int n;
+};
+TuMemo &tuMemo();
+
+
 
 } // namespace hvbhooks
 
