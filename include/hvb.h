@@ -60,6 +60,10 @@ const char *hvb_last_error(hvb_context *ctx);
 /* use an existing cudaStream_t (passed as void*) for all subsequent work; NULL = own stream */
 int hvb_set_stream(hvb_context *ctx, void *cuda_stream);
 int hvb_sync(hvb_context *ctx);
+/* 1 when everything enqueued on the context so far has completed, 0 when work is still in flight, < 0 on error; never
+ * blocks and may be called from any thread (a completion thread that serves several contexts without parking a core
+ * per context inside the driver's wait). */
+int hvb_poll(hvb_context *ctx);
 /* Pipelined host mode.  Off (default): every HVB_HOST call returns after its results have landed.  On: a batch call
  * whose task and result arrays are page-locked (cudaHostAlloc / cudaHostRegister -- an encoder's arena) only enqueues
  * work -- tasks go up on a copy-in stream, the kernels run on the context's stream, the results come back on a copy-out
@@ -107,6 +111,10 @@ int hvb_picture_copy(hvb_context *ctx, int dst_pic, int src_pic);
  * the bus, nothing is copied.  For blocks a caller supplies or wants back per task (a CU's prediction and reconstruction,
  * hvbenc_tu_chain) when a copy per block would cost more than the bytes.  hvb_picture_destroy releases the id only. */
 int hvb_picture_wrap(hvb_context *ctx, void *host, intptr_t stride, int width, int height, int *pic);
+/* Make picture `owner_pic` of context `owner` visible in `ctx` under the id *pic: the same device memory, not a copy (both
+ * contexts must be on the same device).  The importing context never frees it; the owner must outlive the import.  For
+ * several contexts (one per dispatcher thread, each with its own stream) working on one set of pictures. */
+int hvb_picture_import(hvb_context *ctx, hvb_context *owner, int owner_pic, int *pic);
 /* raw device view of a plane: pointer to sample (0,0) and stride in samples (for zero-copy fills) */
 int hvb_picture_plane(hvb_context *ctx, int pic, int cIdx, void **dev_ptr, intptr_t *stride);
 
@@ -219,6 +227,7 @@ int hvb_intra_satd35_batch(hvb_context *ctx, const hvb_intra_sweep_task *tasks, 
 /* raw coefficient-domain primitives over a device-resident int16 pool (hvb_coeff_upload /
  * hvb_coeff_download); offsets are in int16 elements, blocks are n x n contiguous. */
 int hvb_coeff_upload(hvb_context *ctx, const int16_t *data, size_t count, size_t offset);
+/* (pipelined mode, page-locked destination: the copy is only enqueued; the data is valid after hvb_sync / hvb_poll) */
 int hvb_coeff_download(hvb_context *ctx, int16_t *data, size_t count, size_t offset);
 
 typedef struct

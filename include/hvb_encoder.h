@@ -39,6 +39,15 @@ int hvbenc_picture(hvbenc *enc, const void *key, int fresh, int *pic);
 /* copy a rectangle of plane cIdx (x0, y0, w, h in samples of that plane, may extend into the padding) from host memory;
  * `host` points at the rectangle's first sample, stride in samples */
 int hvbenc_upload_rect(hvbenc *enc, int pic, int cIdx, const void *host, intptr_t stride, int x0, int y0, int w, int h);
+/* several rectangles of one picture in one hand-over (a finished CTU: its luma and both chroma blocks) */
+typedef struct
+{
+    int cIdx;
+    const void *host;
+    intptr_t stride;
+    int x0, y0, w, h;
+} hvbenc_rect;
+int hvbenc_upload_rects(hvbenc *enc, int pic, const hvbenc_rect *rects, int n);
 
 /* one blocking call each; the session batches across callers */
 int hvbenc_me(hvbenc *enc, const hvb_me_task *task, hvb_me_result *out);

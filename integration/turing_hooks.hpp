@@ -451,6 +451,7 @@ template <class Sample, class H> void uploadReconstructedCtu(H &h, Picture<Sampl
     int x0 = rx << h[CtbLog2SizeY()], y0 = ry << h[CtbLog2SizeY()];
     int width = std::min(h[CtbSizeY()], h[pic_width_in_luma_samples()] - x0);
     int height = std::min(h[CtbSizeY()], h[pic_height_in_luma_samples()] - y0);
+    hvbenc_rect rects[3];
     for (int c = 0; c < 3; ++c)
     {
         const int sh = c ? 1 : 0, pd = pad >> sh;
@@ -460,9 +461,10 @@ template <class Sample, class H> void uploadReconstructedCtu(H &h, Picture<Sampl
         if (top) y -= pd, hh += pd;
         if (bottom) hh += pd;
         auto &plane = picture[c];
-        const int rc = hvbenc_upload_rect(enc, pic, c, &plane(x, y), plane.stride, x, y, w, hh);
-        if (rc) fatal("hvbenc_upload_rect(reconstruction)", rc);
+        rects[c] = hvbenc_rect{c, &plane(x, y), plane.stride, x, y, w, hh};
     }
+    const int rc = hvbenc_upload_rects(enc, pic, rects, 3);
+    if (rc) fatal("hvbenc_upload_rects(reconstruction)", rc);
 }
 
 } // namespace hvbhooks

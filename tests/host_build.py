@@ -130,8 +130,11 @@ def build(tmp_dir: Path, cu_files: tuple, stubs: str = "", max_grid: int = 2, cp
         # launches are serialised per translation unit (the emulator's state is static), whichever host thread issues them
         head = "template <class F> static void emuLaunch(int grid, int block, F kernel)\n{"
         assert head in prelude
-        prelude = prelude.replace(head, "template <class F> static void emuLaunchExact(int grid, int block, F kernel)\n{\n"
-                                        "    static std::mutex serial; std::lock_guard<std::mutex> hold(serial);")
+        # (one mutex per translation unit, not per instantiation of the launcher: two host threads launching DIFFERENT
+        # kernels of one file share the emulator's static state just the same)
+        prelude = prelude.replace(head, "static std::mutex &emuSerial() { static std::mutex m; return m; }\n"
+                                        "template <class F> static void emuLaunchExact(int grid, int block, F kernel)\n{\n"
+                                        "    std::lock_guard<std::mutex> hold(emuSerial());")
         prelude += ("template <class F> static void emuLaunch(int grid, int block, F kernel) "
                     f"{{ emuLaunchExact(std::min(grid, {max_grid}), block, kernel); }}\n")
         src = src.replace(include, include + "\n" + RUNTIME_TEMPLATES + prelude + helpers + injected, 1)

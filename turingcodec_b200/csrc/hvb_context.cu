@@ -144,6 +144,20 @@ extern "C" int hvb_sync(hvb_context *ctx)
     return hvbCuda(ctx, e, "hvb_sync");
 }
 
+extern "C" int hvb_poll(hvb_context *ctx)
+{
+    if (!ctx) return HVB_ERR_INVALID;
+    const cudaStream_t streams[3] = {ctx->stream, ctx->copyIn, ctx->copyOut};
+    for (cudaStream_t s : streams)
+    {
+        if (!s) continue;
+        const cudaError_t e = cudaStreamQuery(s);
+        if (e == cudaErrorNotReady) return 0;
+        if (e != cudaSuccess) return HVB_ERR_CUDA; // (lastError is the owning thread's to write)
+    }
+    return 1;
+}
+
 extern "C" int hvb_set_pipelined(hvb_context *ctx, int on)
 {
     if (!ctx) return HVB_ERR_INVALID;
@@ -276,6 +290,28 @@ extern "C" int hvb_picture_wrap(hvb_context *ctx, void *host, intptr_t stride, i
     for (int c = 0; c < 3; ++c) p.plane[c] = HvbPlane{nullptr, 0, 0, 0, 0, 0};
     p.plane[0] = HvbPlane{dev, (int32_t)stride, width, height, 0, 0};
     p.live = true;
+    ctx->planesDirty = true;
+    *pic = id;
+    return HVB_OK;
+}
+
+extern "C" int hvb_picture_import(hvb_context *ctx, hvb_context *owner, int owner_pic, int *pic)
+{
+    HVB_CHECK_ARGS(ctx, pic && owner && owner != ctx && owner->device == ctx->device && owner->bps == ctx->bps && owner_pic >= 0 &&
+                            owner_pic < HVB_MAX_PICTURES && owner->pictures[owner_pic].live);
+    int id = -1;
+    for (int i = 0; i < HVB_MAX_PICTURES; ++i)
+        if (!ctx->pictures[i].live)
+        {
+            id = i;
+            break;
+        }
+    if (id < 0) return hvbFail(ctx, HVB_ERR_NOMEM, "picture table full");
+    HvbPicture &p = ctx->pictures[id];
+    p = owner->pictures[owner_pic];
+    for (int c = 0; c < 3; ++c) p.alloc[c] = nullptr; // borrowed: hvb_picture_destroy / hvb_destroy free nothing
+    p.lfInfo = p.saoInfo = nullptr;
+    p.lfBytes = p.saoBytes = 0;
     ctx->planesDirty = true;
     *pic = id;
     return HVB_OK;
@@ -517,7 +553,7 @@ extern "C" int hvb_coeff_download(hvb_context *ctx, int16_t *data, size_t count,
 {
     HVB_CHECK_ARGS(ctx, (data || !count) && offset + count <= ctx->coeffPoolCount);
     cudaError_t e = cudaMemcpyAsync(data, ctx->coeffPool + offset, count * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && !(ctx->pipelined && hvbIsPinned(data))) e = cudaStreamSynchronize(ctx->stream);
     return hvbCuda(ctx, e, "hvb_coeff_download");
 }
 
@@ -536,6 +572,7 @@ extern "C" int hvb_rdoq_contexts_upload(hvb_context *ctx, const hvb_rdoq_ctx *sn
     if (e != cudaSuccess) return hvbCuda(ctx, e, "hvb_rdoq_contexts_upload");
     rc = hvbLaunchRdoqBits(ctx, first, count); // {bits(0), bits(1)} per state byte: what the RDOQ walk actually reads
     if (rc) return rc;
+    if (ctx->pipelined && hvbIsPinned(snapshots)) return HVB_OK; // the source stays the library's until hvb_sync
     return hvbCuda(ctx, cudaStreamSynchronize(ctx->stream), "hvb_rdoq_contexts_upload");
 }
 

@@ -6,10 +6,14 @@
 // at the same time (up to PicHeightInCtbs x concurrent-frames of them, turing/TaskEncodeSubstream.cpp:55-136) are gathered
 // into one batch per kind.  The session is built on the public hvb.h ABI only.
 //
-// Threading: workers append to the buffer being filled (double-buffered, page-locked, device-addressable) under one
-// mutex and sleep on their own condition variable; the dispatcher thread flips the buffers, issues every kind's batch on
-// the context's stream, waits for the stream once, hands the results out and wakes the workers.  The hvb_context is
-// touched by the dispatcher thread only.
+// Threading: a session runs several ENGINES, each an hvb_context with its own stream, its own page-locked buffers and its
+// own dispatcher thread; the pictures live in engine 0's context and are imported into the others (same ids everywhere).
+// A worker hands its request to the engine with the least work in flight: while the system is lightly loaded a request
+// starts at once on an idle engine (the kernels of different engines overlap on the device), under load every engine
+// batches what arrives while its previous batch is on the device.  Inside an engine workers append to the buffer being
+// filled (double-buffered, device-addressable) under the engine's mutex and sleep on their own condition variable; the
+// dispatcher flips the buffers, issues every kind's batch on the stream, waits for the stream once, hands the results
+// out and wakes the workers.  An hvb_context is touched by its dispatcher thread only.
 #include "../../include/hvb_encoder.h"
 
 #include <algorithm>
@@ -17,6 +21,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -110,18 +115,24 @@ struct TuExtra // per transform block: where the caller wants reconstruction and
 
 constexpr int kTuCell = 32;          // staging cell of a transform block: 32 x 32 samples
 constexpr int kTuCellsPerRow = 16;   // wrapped staging pictures are 512 samples wide
-constexpr int kTuCapacity = 2048;    // transform blocks per batch
-constexpr int kRdoqSnapshots = 512;  // context snapshots per batch
-constexpr size_t kUploadBytes = 24u << 20;
-constexpr size_t kPoolSamples = 1u << 20; // intra neighbours per batch
+constexpr int kTuCapacity = 1024;    // transform blocks per batch
+constexpr int kRdoqSnapshots = 256;  // context snapshots per batch
+constexpr size_t kUploadBytes = 8u << 20;
+constexpr size_t kPoolSamples = 1u << 18; // intra neighbours per batch
 
 } // namespace
 
-struct hvbenc
+struct Engine
 {
     hvb_context *ctx = nullptr;
     int bps = 1, bitDepth = 8, width = 0, height = 0;
     std::string lastError;
+    std::atomic<int> inflight{0}; // requests handed to this engine and not yet answered
+    struct hvbenc *session = nullptr;
+    // completion of the batch on the device, signalled by the session's poller thread
+    std::mutex doneM;
+    std::condition_variable doneCv;
+    int pollResult = 0; // 0: in flight, 1: complete, < 0: error
 
     std::mutex m;
     std::condition_variable workCv, spaceCv;
@@ -155,6 +166,16 @@ struct hvbenc
     int nSnapshots[2] = {0, 0};
     int16_t *levelsHost = nullptr; // page-locked, kTuCapacity * 1024
 
+    double deviceSeconds = 0;
+    int64_t dispatches = 0;
+};
+
+struct hvbenc
+{
+    std::vector<Engine *> engines;
+    int bps = 1;
+    std::string lastError;
+    std::mutex poolMutex;
     // picture pool
     struct Slot
     {
@@ -166,20 +187,40 @@ struct hvbenc
     std::unordered_map<const void *, int> byKey;
     uint64_t useClock = 0;
 
-    double deviceSeconds = 0;
-    int64_t dispatches = 0;
+    // One completion thread for all engines: it polls the contexts that have a batch in flight (hvb_poll) and wakes the
+    // engine whose batch has finished, so that no dispatcher parks a core inside the driver's stream wait.
+    std::thread poller;
+    std::mutex pollM;
+    std::condition_variable pollCv;
+    std::vector<Engine *> watching;
+    bool pollStop = false;
+
+    // per kind: requests and the time from hand-over to wake-up (ns), for the statistics
+    std::atomic<int64_t> waitNs[6], waitCount[6];
+
+    Engine *pick()
+    {
+        Engine *best = engines[0];
+        int load = best->inflight.load(std::memory_order_relaxed);
+        for (size_t i = 1; i < engines.size() && load > 0; ++i)
+        {
+            const int l = engines[i]->inflight.load(std::memory_order_relaxed);
+            if (l < load) best = engines[i], load = l;
+        }
+        return best;
+    }
 };
 
 namespace {
 
-int fail(hvbenc *enc, int rc, const char *what)
+int fail(Engine *enc, int rc, const char *what)
 {
     if (enc) enc->lastError = std::string(what) + ": " + (enc->ctx ? hvb_last_error(enc->ctx) : "");
     return rc;
 }
 
 // Issue everything in buffer b.  Order on the stream: uploads, then the searches, costs, sweeps and transform blocks.
-int runBatch(hvbenc *enc, int b)
+int runBatch(Engine *enc, int b)
 {
     hvb_context *ctx = enc->ctx;
     int rc = 0;
@@ -208,9 +249,26 @@ int runBatch(hvbenc *enc, int b)
         if (rc) return rc;
         levelCount = (size_t)enc->tu.n[b] * 1024;
     }
-    // one wait for the whole batch; the levels come back with it
+    // the levels come back with the batch (enqueued: the destination is page-locked)
     if (levelCount) rc = hvb_coeff_download(ctx, enc->levelsHost, levelCount, 0);
-    else rc = hvb_sync(ctx);
+    if (rc) return rc;
+    // one wait for the whole batch, on the session's completion thread
+    {
+        hvbenc *session = enc->session;
+        {
+            std::lock_guard<std::mutex> g(enc->doneM);
+            enc->pollResult = 0;
+        }
+        {
+            std::lock_guard<std::mutex> g(session->pollM);
+            session->watching.push_back(enc);
+        }
+        session->pollCv.notify_one();
+        std::unique_lock<std::mutex> lock(enc->doneM);
+        enc->doneCv.wait(lock, [&] { return enc->pollResult != 0; });
+        if (enc->pollResult < 0) return hvb_sync(ctx); // collects the error text
+    }
+    rc = hvb_sync(ctx); // everything has completed: returns at once, and resets the context's staging slots
     if (rc) return rc;
     // reconstruction cells and levels back to the callers' buffers
     for (size_t i = 0; i < enc->tuExtra[b].size(); ++i)
@@ -227,7 +285,7 @@ int runBatch(hvbenc *enc, int b)
     return 0;
 }
 
-void dispatch(hvbenc *enc)
+void dispatch(Engine *enc)
 {
     std::vector<Waiter *> wake;
     for (;;)
@@ -247,6 +305,8 @@ void dispatch(hvbenc *enc)
         enc->deviceSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         ++enc->dispatches;
         wake.clear();
+        const int answered = (int)(enc->me.requests[b].size() + enc->bi.requests[b].size() + enc->pu.requests[b].size() +
+                                   enc->intra.requests[b].size() + enc->tu.requests[b].size() + enc->uploadWaiters[b].size());
         enc->me.deliver(b, rc, wake);
         enc->bi.deliver(b, rc, wake);
         enc->pu.deliver(b, rc, wake);
@@ -269,6 +329,7 @@ void dispatch(hvbenc *enc)
         // a worker may have several requests in one batch (never the case today); wake each once
         std::sort(wake.begin(), wake.end());
         wake.erase(std::unique(wake.begin(), wake.end()), wake.end());
+        enc->inflight.fetch_sub(answered, std::memory_order_relaxed);
         for (Waiter *w : wake)
         {
             {
@@ -277,6 +338,36 @@ void dispatch(hvbenc *enc)
             }
             w->cv.notify_one();
         }
+    }
+}
+
+void pollLoop(hvbenc *session)
+{
+    std::vector<Engine *> snapshot;
+    for (;;)
+    {
+        {
+            std::unique_lock<std::mutex> lock(session->pollM);
+            session->pollCv.wait(lock, [&] { return !session->watching.empty() || session->pollStop; });
+            if (session->pollStop && session->watching.empty()) return;
+            snapshot = session->watching;
+        }
+        for (Engine *e : snapshot)
+        {
+            const int r = hvb_poll(e->ctx);
+            if (!r) continue;
+            {
+                std::lock_guard<std::mutex> g(session->pollM);
+                auto &w = session->watching;
+                w.erase(std::remove(w.begin(), w.end(), e), w.end());
+            }
+            {
+                std::lock_guard<std::mutex> g(e->doneM);
+                e->pollResult = r;
+            }
+            e->doneCv.notify_one();
+        }
+        std::this_thread::yield();
     }
 }
 
@@ -289,11 +380,12 @@ int waitFor(Waiter &w)
 
 // append `count` tasks of a lane; `extra(b, first)` runs under the lock once the room is there
 template <class LaneT, class Task, class Extra>
-int submit(hvbenc *enc, LaneT &lane, const Task *tasks, int count, void *dst, Extra extra)
+int submit(Engine *enc, LaneT &lane, const Task *tasks, int count, void *dst, Extra extra)
 {
     if (!enc || !tasks || count <= 0 || count > lane.capacity) return HVB_ERR_INVALID;
     Waiter &w = myWaiter();
     w.done = false;
+    enc->inflight.fetch_add(1, std::memory_order_relaxed);
     {
         std::unique_lock<std::mutex> lock(enc->m);
         enc->spaceCv.wait(lock, [&] { return lane.n[enc->fill] + count <= lane.capacity && extra(enc->fill, -1); });
@@ -310,35 +402,43 @@ int submit(hvbenc *enc, LaneT &lane, const Task *tasks, int count, void *dst, Ex
 
 } // namespace
 
-extern "C" int hvbenc_create(int device, int bytes_per_sample, int bit_depth, int width, int height, int pool_pictures, hvbenc **out)
+namespace {
+
+int createEngine(int device, int bytes_per_sample, int bit_depth, int width, int height, Engine **out)
 {
-    if (!out || pool_pictures < 2 || pool_pictures > 200) return HVB_ERR_INVALID;
-    *out = nullptr;
     hvb_context *ctx = nullptr;
     int rc = hvb_create(device, bytes_per_sample, bit_depth, &ctx);
     if (rc) return rc;
-    hvbenc *enc = new hvbenc;
+    Engine *enc = new Engine;
     enc->ctx = ctx;
     enc->bps = bytes_per_sample;
     enc->bitDepth = bit_depth;
     enc->width = width;
     enc->height = height;
-    rc = hvb_set_pipelined(ctx, 1); // uploads from the page-locked staging buffers are enqueued, not waited for
-    if (!rc) rc = enc->me.init(ctx, 4096);
-    if (!rc) rc = enc->bi.init(ctx, 4096);
-    if (!rc) rc = enc->pu.init(ctx, 8192);
-    if (!rc) rc = enc->intra.init(ctx, 4096);
+    *out = enc;
+    return hvb_set_pipelined(ctx, 1); // uploads from the page-locked staging buffers are enqueued, not waited for
+}
+
+// buffers and staging pictures of an engine; the session's pictures are already in its context (ids 0 .. pool - 1)
+int equipEngine(Engine *enc)
+{
+    hvb_context *ctx = enc->ctx;
+    int rc = enc->me.init(ctx, 1024);
+    if (!rc) rc = enc->bi.init(ctx, 1024);
+    if (!rc) rc = enc->pu.init(ctx, 2048);
+    if (!rc) rc = enc->intra.init(ctx, 1024);
     if (!rc) rc = enc->tu.init(ctx, kTuCapacity);
-    const size_t cellBytes = (size_t)kTuCell * kTuCellsPerRow * bytes_per_sample * kTuCell * (kTuCapacity / kTuCellsPerRow);
+    const int rows = kTuCell * (kTuCapacity / kTuCellsPerRow);
+    const size_t cellBytes = (size_t)kTuCell * kTuCellsPerRow * enc->bps * rows;
     for (int b = 0; b < 2 && !rc; ++b)
     {
         rc = hvb_host_alloc(ctx, kUploadBytes, reinterpret_cast<void **>(&enc->uploadStage[b]));
-        if (!rc) rc = hvb_host_alloc(ctx, kPoolSamples * bytes_per_sample, reinterpret_cast<void **>(&enc->poolStage[b]));
+        if (!rc) rc = hvb_host_alloc(ctx, kPoolSamples * enc->bps, reinterpret_cast<void **>(&enc->poolStage[b]));
         if (!rc) rc = hvb_host_alloc(ctx, cellBytes, reinterpret_cast<void **>(&enc->tuPredHost[b]));
         if (!rc) rc = hvb_host_alloc(ctx, cellBytes, reinterpret_cast<void **>(&enc->tuRecHost[b]));
         if (!rc) rc = hvb_host_alloc(ctx, sizeof(hvb_rdoq_ctx) * kRdoqSnapshots, reinterpret_cast<void **>(&enc->snapshots[b]));
-        if (!rc) rc = hvb_picture_wrap(ctx, enc->tuPredHost[b], kTuCell * kTuCellsPerRow, kTuCell * kTuCellsPerRow, kTuCell * (kTuCapacity / kTuCellsPerRow), &enc->tuPredPic[b]);
-        if (!rc) rc = hvb_picture_wrap(ctx, enc->tuRecHost[b], kTuCell * kTuCellsPerRow, kTuCell * kTuCellsPerRow, kTuCell * (kTuCapacity / kTuCellsPerRow), &enc->tuRecPic[b]);
+        if (!rc) rc = hvb_picture_wrap(ctx, enc->tuPredHost[b], kTuCell * kTuCellsPerRow, kTuCell * kTuCellsPerRow, rows, &enc->tuPredPic[b]);
+        if (!rc) rc = hvb_picture_wrap(ctx, enc->tuRecHost[b], kTuCell * kTuCellsPerRow, kTuCell * kTuCellsPerRow, rows, &enc->tuRecPic[b]);
     }
     if (!rc) rc = hvb_host_alloc(ctx, sizeof(int16_t) * 1024 * kTuCapacity, reinterpret_cast<void **>(&enc->levelsHost));
     if (!rc)
@@ -347,24 +447,12 @@ extern "C" int hvbenc_create(int device, int bytes_per_sample, int bit_depth, in
         std::vector<int16_t> zero(1024, 0);
         rc = hvb_coeff_upload(ctx, zero.data(), 1024, (size_t)1024 * (kTuCapacity - 1));
     }
-    enc->slots.resize(pool_pictures);
-    for (int i = 0; i < pool_pictures && !rc; ++i) rc = hvb_picture_create(ctx, width, height, 96, &enc->slots[i].pic);
     if (!rc) rc = hvb_sync(ctx);
-    if (rc)
-    {
-        fprintf(stderr, "hvbenc_create: %s\n", hvb_last_error(ctx));
-        hvb_destroy(ctx);
-        delete enc;
-        return rc;
-    }
-    enc->dispatcher = std::thread(dispatch, enc);
-    *out = enc;
-    return HVB_OK;
+    return rc;
 }
 
-extern "C" void hvbenc_destroy(hvbenc *enc)
+void destroyEngine(Engine *enc)
 {
-    if (!enc) return;
     {
         std::lock_guard<std::mutex> g(enc->m);
         enc->stop = true;
@@ -386,16 +474,99 @@ extern "C" void hvbenc_destroy(hvbenc *enc)
         if (enc->snapshots[b]) hvb_host_free(enc->ctx, enc->snapshots[b]);
     }
     if (enc->levelsHost) hvb_host_free(enc->ctx, enc->levelsHost);
-    hvb_destroy(enc->ctx);
+}
+
+struct Clock
+{
+    hvbenc *enc;
+    int kind;
+    std::chrono::steady_clock::time_point t0;
+    Clock(hvbenc *e, int k) : enc(e), kind(k), t0(std::chrono::steady_clock::now()) {}
+    ~Clock()
+    {
+        enc->waitNs[kind] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        enc->waitCount[kind] += 1;
+    }
+};
+
+} // namespace
+
+extern "C" int hvbenc_create(int device, int bytes_per_sample, int bit_depth, int width, int height, int pool_pictures, hvbenc **out)
+{
+    if (!out || pool_pictures < 2 || pool_pictures > 900) return HVB_ERR_INVALID;
+    *out = nullptr;
+    int nEngines = 8;
+    if (const char *v = getenv("HVB_ENGINES")) nEngines = std::max(1, std::min(32, atoi(v)));
+    hvbenc *enc = new hvbenc;
+    enc->bps = bytes_per_sample;
+    for (int k = 0; k < 6; ++k) enc->waitNs[k] = 0, enc->waitCount[k] = 0;
+    int rc = 0;
+    for (int e = 0; e < nEngines && !rc; ++e)
+    {
+        Engine *engine = nullptr;
+        rc = createEngine(device, bytes_per_sample, bit_depth, width, height, &engine);
+        if (engine) enc->engines.push_back(engine);
+    }
+    // the pictures: owned by engine 0, imported by the others in the same order, so an id means the same picture everywhere
+    enc->slots.resize(pool_pictures);
+    for (int i = 0; i < pool_pictures && !rc; ++i)
+    {
+        rc = hvb_picture_create(enc->engines[0]->ctx, width, height, 96, &enc->slots[i].pic);
+        for (size_t e = 1; e < enc->engines.size() && !rc; ++e)
+        {
+            int id = -1;
+            rc = hvb_picture_import(enc->engines[e]->ctx, enc->engines[0]->ctx, enc->slots[i].pic, &id);
+            if (!rc && id != enc->slots[i].pic) rc = HVB_ERR_INVALID;
+        }
+    }
+    for (size_t e = 0; e < enc->engines.size() && !rc; ++e) rc = equipEngine(enc->engines[e]);
+    if (rc)
+    {
+        fprintf(stderr, "hvbenc_create failed (%d): %s\n", rc, enc->engines.empty() ? "no engine" : hvb_last_error(enc->engines.back()->ctx));
+        hvbenc_destroy(enc);
+        return rc;
+    }
+    enc->poller = std::thread(pollLoop, enc);
+    for (Engine *engine : enc->engines)
+    {
+        engine->session = enc;
+        engine->dispatcher = std::thread(dispatch, engine);
+    }
+    *out = enc;
+    return HVB_OK;
+}
+
+extern "C" void hvbenc_destroy(hvbenc *enc)
+{
+    if (!enc) return;
+    for (Engine *engine : enc->engines) destroyEngine(engine);
+    {
+        std::lock_guard<std::mutex> g(enc->pollM);
+        enc->pollStop = true;
+    }
+    enc->pollCv.notify_all();
+    if (enc->poller.joinable()) enc->poller.join();
+    // importing contexts first, the owner of the pictures last
+    for (size_t e = enc->engines.size(); e-- > 0;)
+    {
+        hvb_destroy(enc->engines[e]->ctx);
+        delete enc->engines[e];
+    }
     delete enc;
 }
 
-extern "C" const char *hvbenc_last_error(hvbenc *enc) { return enc ? enc->lastError.c_str() : "null session"; }
+extern "C" const char *hvbenc_last_error(hvbenc *enc)
+{
+    if (!enc) return "null session";
+    for (Engine *engine : enc->engines)
+        if (!engine->lastError.empty()) return engine->lastError.c_str();
+    return enc->lastError.c_str();
+}
 
 extern "C" int hvbenc_picture(hvbenc *enc, const void *key, int fresh, int *pic)
 {
     if (!enc || !key || !pic) return HVB_ERR_INVALID;
-    std::lock_guard<std::mutex> g(enc->m);
+    std::lock_guard<std::mutex> g(enc->poolMutex);
     auto it = enc->byKey.find(key);
     int slot;
     if (it != enc->byKey.end())
@@ -416,57 +587,95 @@ extern "C" int hvbenc_picture(hvbenc *enc, const void *key, int fresh, int *pic)
     return HVB_OK;
 }
 
-extern "C" int hvbenc_upload_rect(hvbenc *enc, int pic, int cIdx, const void *host, intptr_t stride, int x0, int y0, int w, int h)
+extern "C" int hvbenc_upload_rects(hvbenc *session, int pic, const hvbenc_rect *rects, int n)
 {
-    if (!enc || !host || w <= 0 || h <= 0 || stride < w) return HVB_ERR_INVALID;
-    const size_t rowBytes = (size_t)w * enc->bps, bytes = (rowBytes * h + 63) & ~size_t(63);
-    if (bytes > kUploadBytes)
+    if (!session || !rects || n <= 0) return HVB_ERR_INVALID;
+    size_t total = 0;
+    for (int i = 0; i < n; ++i)
     {
-        // larger than the staging buffer: split by rows
-        const int rows = std::max(1, (int)(kUploadBytes / 2 / rowBytes));
-        for (int y = 0; y < h; y += rows)
+        if (!rects[i].host || rects[i].w <= 0 || rects[i].h <= 0 || rects[i].stride < rects[i].w) return HVB_ERR_INVALID;
+        total += ((size_t)rects[i].w * session->bps * rects[i].h + 63) & ~size_t(63);
+    }
+    if (total > kUploadBytes / 2)
+    {
+        // more than the staging buffer affords in one piece: rectangle by rectangle, split by rows
+        for (int i = 0; i < n; ++i)
         {
-            const int rc = hvbenc_upload_rect(enc, pic, cIdx, static_cast<const char *>(host) + (size_t)y * stride * enc->bps, stride, x0, y0 + y, w,
-                                              std::min(rows, h - y));
-            if (rc) return rc;
+            const hvbenc_rect &r = rects[i];
+            const size_t rowBytes = (size_t)r.w * session->bps;
+            const int rows = std::max(1, (int)(kUploadBytes / 4 / rowBytes));
+            for (int y = 0; y < r.h; y += rows)
+            {
+                hvbenc_rect part = r;
+                part.host = static_cast<const char *>(r.host) + (size_t)y * r.stride * session->bps;
+                part.y0 = r.y0 + y;
+                part.h = std::min(rows, r.h - y);
+                const int rc = hvbenc_upload_rects(session, pic, &part, 1);
+                if (rc) return rc;
+            }
         }
         return HVB_OK;
     }
+    Clock clock(session, 0);
+    Engine *enc = session->pick();
     Waiter &wt = myWaiter();
     wt.done = false;
+    enc->inflight.fetch_add(1, std::memory_order_relaxed);
     {
         std::unique_lock<std::mutex> lock(enc->m);
-        enc->spaceCv.wait(lock, [&] { return enc->uploadUsed[enc->fill] + bytes <= kUploadBytes; });
+        enc->spaceCv.wait(lock, [&] { return enc->uploadUsed[enc->fill] + total <= kUploadBytes; });
         const int b = enc->fill;
-        char *dst = enc->uploadStage[b] + enc->uploadUsed[b];
-        for (int y = 0; y < h; ++y) memcpy(dst + y * rowBytes, static_cast<const char *>(host) + (size_t)y * stride * enc->bps, rowBytes);
-        enc->uploads[b].push_back(UploadTask{pic, cIdx, x0, y0, w, h, enc->uploadUsed[b]});
+        for (int i = 0; i < n; ++i)
+        {
+            const hvbenc_rect &r = rects[i];
+            const size_t rowBytes = (size_t)r.w * enc->bps;
+            char *dst = enc->uploadStage[b] + enc->uploadUsed[b];
+            for (int y = 0; y < r.h; ++y) memcpy(dst + y * rowBytes, static_cast<const char *>(r.host) + (size_t)y * r.stride * enc->bps, rowBytes);
+            enc->uploads[b].push_back(UploadTask{pic, r.cIdx, r.x0, r.y0, r.w, r.h, enc->uploadUsed[b]});
+            enc->uploadUsed[b] += (rowBytes * r.h + 63) & ~size_t(63);
+        }
         enc->uploadWaiters[b].push_back(&wt);
-        enc->uploadUsed[b] += bytes;
         ++enc->pending;
     }
     enc->workCv.notify_one();
     return waitFor(wt);
 }
 
-extern "C" int hvbenc_me(hvbenc *enc, const hvb_me_task *task, hvb_me_result *out)
+extern "C" int hvbenc_upload_rect(hvbenc *session, int pic, int cIdx, const void *host, intptr_t stride, int x0, int y0, int w, int h)
 {
+    const hvbenc_rect r = {cIdx, host, stride, x0, y0, w, h};
+    return hvbenc_upload_rects(session, pic, &r, 1);
+}
+
+extern "C" int hvbenc_me(hvbenc *session, const hvb_me_task *task, hvb_me_result *out)
+{
+    if (!session) return HVB_ERR_INVALID;
+    Clock clock(session, 1);
+    Engine *enc = session->pick();
     return submit(enc, enc->me, task, 1, out, [](int, int) { return true; });
 }
 
-extern "C" int hvbenc_me_bi(hvbenc *enc, const hvb_me_bi_task *task, hvb_me_bi_result *out)
+extern "C" int hvbenc_me_bi(hvbenc *session, const hvb_me_bi_task *task, hvb_me_bi_result *out)
 {
+    if (!session) return HVB_ERR_INVALID;
+    Clock clock(session, 2);
+    Engine *enc = session->pick();
     return submit(enc, enc->bi, task, 1, out, [](int, int) { return true; });
 }
 
-extern "C" int hvbenc_pu_cost(hvbenc *enc, const hvb_pu_cost_task *tasks, int n, int32_t *out)
+extern "C" int hvbenc_pu_cost(hvbenc *session, const hvb_pu_cost_task *tasks, int n, int32_t *out)
 {
+    if (!session) return HVB_ERR_INVALID;
+    Clock clock(session, 3);
+    Engine *enc = session->pick();
     return submit(enc, enc->pu, tasks, n, out, [](int, int) { return true; });
 }
 
-extern "C" int hvbenc_intra_sweep(hvbenc *enc, const hvb_intra_sweep_task *task, const void *neighbours, int32_t *out)
+extern "C" int hvbenc_intra_sweep(hvbenc *session, const hvb_intra_sweep_task *task, const void *neighbours, int32_t *out)
 {
-    if (!enc || !task || !neighbours || task->log2n < 2 || task->log2n > 5) return HVB_ERR_INVALID;
+    if (!session || !task || !neighbours || task->log2n < 2 || task->log2n > 5) return HVB_ERR_INVALID;
+    Clock clock(session, 4);
+    Engine *enc = session->pick();
     const size_t count = (size_t)(4 << task->log2n) + 1, room = (count + 15) & ~size_t(15);
     return submit(enc, enc->intra, task, 1, out, [&](int b, int first) {
         if (first < 0) return enc->poolUsed[b] + room <= kPoolSamples;
@@ -480,10 +689,12 @@ extern "C" int hvbenc_intra_sweep(hvbenc *enc, const hvb_intra_sweep_task *task,
     });
 }
 
-extern "C" int hvbenc_tu_chain(hvbenc *enc, hvb_tu_task *tasks, int n, const hvb_rdoq_ctx *snapshot, const void *const *pred, const intptr_t *pred_stride,
-                               void *const *rec, const intptr_t *rec_stride, int16_t *const *levels, hvb_tu_result *out)
+extern "C" int hvbenc_tu_chain(hvbenc *session, hvb_tu_task *tasks, int n, const hvb_rdoq_ctx *snapshot, const void *const *pred,
+                               const intptr_t *pred_stride, void *const *rec, const intptr_t *rec_stride, int16_t *const *levels, hvb_tu_result *out)
 {
-    if (!enc || !tasks || n <= 0 || !pred || !pred_stride || !rec || !rec_stride || !levels || !out) return HVB_ERR_INVALID;
+    if (!session || !tasks || n <= 0 || !pred || !pred_stride || !rec || !rec_stride || !levels || !out) return HVB_ERR_INVALID;
+    Clock clock(session, 5);
+    Engine *enc = session->pick();
     return submit(enc, enc->tu, tasks, n, out, [&](int b, int first) {
         if (first < 0) return !snapshot || enc->nSnapshots[b] < kRdoqSnapshots;
         int snap = 0;
@@ -511,18 +722,35 @@ extern "C" int hvbenc_tu_chain(hvbenc *enc, hvb_tu_task *tasks, int n, const hvb
     });
 }
 
-extern "C" int hvbenc_stats(hvbenc *enc, char *buf, size_t bytes)
+extern "C" int hvbenc_stats(hvbenc *session, char *buf, size_t bytes)
 {
-    if (!enc || !buf || !bytes) return HVB_ERR_INVALID;
-    std::lock_guard<std::mutex> g(enc->m);
-    snprintf(buf, bytes,
-             "{\"dispatches\": %lld, \"device_wait_s\": %.3f, \"kernel_launches\": %lld, "
-             "\"me\": {\"tasks\": %lld, \"batches\": %lld}, \"me_bi\": {\"tasks\": %lld, \"batches\": %lld}, "
-             "\"pu_cost\": {\"tasks\": %lld, \"batches\": %lld}, \"intra_sweep\": {\"tasks\": %lld, \"batches\": %lld}, "
-             "\"tu_chain\": {\"tasks\": %lld, \"batches\": %lld}, \"uploads\": {\"rects\": %lld, \"bytes\": %lld}}",
-             (long long)enc->dispatches, enc->deviceSeconds, (long long)hvb_launch_count(enc->ctx), (long long)enc->me.totalTasks,
-             (long long)enc->me.totalBatches, (long long)enc->bi.totalTasks, (long long)enc->bi.totalBatches, (long long)enc->pu.totalTasks,
-             (long long)enc->pu.totalBatches, (long long)enc->intra.totalTasks, (long long)enc->intra.totalBatches,
-             (long long)enc->tu.totalTasks, (long long)enc->tu.totalBatches, (long long)enc->totalUploads, (long long)enc->totalUploadBytes);
+    if (!session || !buf || !bytes) return HVB_ERR_INVALID;
+    long long dispatches = 0, launches = 0, tasks[5] = {0, 0, 0, 0, 0}, batches[5] = {0, 0, 0, 0, 0}, rects = 0, rectBytes = 0;
+    double busy = 0;
+    for (Engine *enc : session->engines)
+    {
+        std::lock_guard<std::mutex> g(enc->m);
+        dispatches += enc->dispatches;
+        busy += enc->deviceSeconds;
+        launches += hvb_launch_count(enc->ctx);
+        const long long t[5] = {enc->me.totalTasks, enc->bi.totalTasks, enc->pu.totalTasks, enc->intra.totalTasks, enc->tu.totalTasks};
+        const long long bt[5] = {enc->me.totalBatches, enc->bi.totalBatches, enc->pu.totalBatches, enc->intra.totalBatches, enc->tu.totalBatches};
+        for (int k = 0; k < 5; ++k) tasks[k] += t[k], batches[k] += bt[k];
+        rects += enc->totalUploads;
+        rectBytes += enc->totalUploadBytes;
+    }
+    const char *names[5] = {"me", "me_bi", "pu_cost", "intra_sweep", "tu_chain"};
+    int at = snprintf(buf, bytes, "{\"engines\": %d, \"dispatches\": %lld, \"engine_busy_s\": %.3f, \"kernel_launches\": %lld, ", (int)session->engines.size(),
+                      dispatches, busy, launches);
+    for (int k = 0; k < 5 && at < (int)bytes; ++k)
+    {
+        const long long c = session->waitCount[k + 1];
+        at += snprintf(buf + at, bytes - at, "\"%s\": {\"tasks\": %lld, \"batches\": %lld, \"requests\": %lld, \"mean_wait_us\": %.1f}, ", names[k], tasks[k],
+                       batches[k], c, c ? session->waitNs[k + 1] / 1000.0 / c : 0.0);
+    }
+    const long long uc = session->waitCount[0];
+    if (at < (int)bytes)
+        snprintf(buf + at, bytes - at, "\"uploads\": {\"rects\": %lld, \"bytes\": %lld, \"mean_wait_us\": %.1f}}", rects, rectBytes,
+                 uc ? session->waitNs[0] / 1000.0 / uc : 0.0);
     return HVB_OK;
 }

@@ -22,7 +22,7 @@ struct HvbPlane
     int32_t reserved;
 };
 
-static const int HVB_MAX_PICTURES = 256;
+static const int HVB_MAX_PICTURES = 1024;
 
 struct HvbPicture
 {

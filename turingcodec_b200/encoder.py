@@ -22,6 +22,7 @@ from . import synth
 ROOT = Path(__file__).resolve().parent.parent
 REFERENCE = ROOT / "oracle" / "_ref" / "turing_ref"
 BATCHED = ROOT / "integration" / "_build" / "turing_b200_batched"
+SEGMENTS = ROOT / "integration" / "_build" / "turing_b200_segments"
 LIB_DIR = ROOT / "turingcodec_b200" / "csrc"
 
 # The configuration bit-identity is defined on.  With SAO on, `--speed medium` is not a deterministic function of its input
@@ -65,9 +66,12 @@ def encode(binary: Path, clip: Path, width: int, height: int, frames: int, optio
            dump_reconstruction: bool = True, env: dict | None = None, timeout: float = 3600, frame_rate: int = 30) -> dict:
     """one `turing encode` run; returns wall seconds, fps, md5s and (batched build) the submission queue's counters"""
     bit, rec = out_dir / f"{tag}.bit", out_dir / f"{tag}.yuv"
-    cmd = [str(binary), "encode", "--input-res", f"{width}x{height}", "--frame-rate", str(frame_rate), "--frames", str(frames), "-o", str(bit)]
-    if dump_reconstruction:
+    cmd = [str(binary)] + ([] if binary.name == SEGMENTS.name else ["encode"])
+    cmd += ["--input-res", f"{width}x{height}", "--frame-rate", str(frame_rate), "--frames", str(frames), "-o", str(bit)]
+    if dump_reconstruction and binary.name != SEGMENTS.name:  # (each instance of the segment driver would write the same file)
         cmd += ["--dump-pictures", str(rec)]
+    else:
+        dump_reconstruction = False
     if threads is not None:
         cmd += ["--threads", str(threads)]
     cmd += [*options, str(clip)]
@@ -82,6 +86,7 @@ def encode(binary: Path, clip: Path, width: int, height: int, frames: int, optio
         raise RuntimeError(f"{binary.name} failed ({res.returncode}): {res.stdout[-1500:]}\n{res.stderr[-3000:]}")
     out = {"binary": binary.name, "wall_s": wall, "fps": frames / wall, "frames": frames, "bitstream_bytes": bit.stat().st_size,
            "bitstream_md5": md5_file(bit), "cmd": " ".join(cmd[1:-1])}
+    bit.unlink()
     if dump_reconstruction:
         out["reconstruction_md5"] = md5_file(rec)
         rec.unlink()
