@@ -1,25 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- frame-pass throughput of the B200-native Turing-codec pixel hot path.
+"""bench.py -- 4K encode frames per second of the batched B200 build of the Turing encoder, next to the reference on the host.
 
-One step = one pass of the hot path over one 3840x2160 8-bit frame at the reference's `--speed medium`
-settings (turingcodec_b200/workload.py): a uni-directional motion search (integer pattern search +
-1/2- and 1/4-pel refinement) for every PU of the CU quadtree, a 35-mode intra SATD sweep for every
-partition, and the TU pipeline (DCT -> RDOQ+SDH -> dequant -> IDCT+add -> SSD) for two candidates of
-every CU in luma and both chroma planes.  Eight kernel launches per step (small-PU and large-PU integer search,
-sub-pel refinement, intra sweep, TU front / order / RDOQ / back).
+Metric and configuration are BASELINE.json's: 3840x2160 YUV420 8-bit, `--speed medium`, synthetic frames.
+What runs is the reference encoder with its hot loops -- motion search (integer + sub-pel, uni and bi), PU cost, the
+35-mode intra sweep and the transform / RDOQ / reconstruction blocks -- on libhvb.so's sm_100a kernels through the
+submission queue of include/hvb_encoder.h (integration/), IDR-segment-parallel (integration/segments_main.cpp); its
+bitstream is byte-identical to `turing_ref encode --asm 0` with the same options, which the run checks and reports
+(`bitstream_md5_equals_asm0`).  Identity configuration: `--speed medium --no-sao` (with SAO the reference itself is not
+reproducible from run to run, profiles/r02a_asm0_asm1_experiment.txt).
 
-  value   frames/s with pictures, task and result arrays resident in HBM (CUDA events, max over ranks)
-  e2e     frames/s through the host-facing C-ABI (hvb_* with HVB_HOST, pipelined mode): per step the source
-          and reference pictures are uploaded from pinned host memory, the task arrays go host->device and
-          every result array comes back device->host inside the timed region
-  roofline  for the dominant kernel: algorithmic bytes per launch (SURVEY.md 8(d) formulas) / its
-          average duration, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
-  cpu_baseline  the same workload on the host cores through the reference's own havoc tables
-          (oracle/_ref, AVX2/xbyak JIT) when they were built, else the oracle's C port, on a bounded sample
+  step    one IDR segment of --segment-frames (8) pictures; every rank encodes K segments in the timed region (weak scaling)
+  value   frames/s from the encoder's own clock: first picture submitted to last bitstream byte, device session set up
+          and the source clip in the page cache before the clock starts (max over ranks)
+  e2e     frames/s of the whole `turing_b200_segments` process by wall clock: start-up, CUDA context and session, reading the
+          YUV file, every host->device byte (source pictures, finished CTUs of reference pictures, tasks, predictions) and
+          device->host byte (results, reconstructions, levels) inside the timed region
+  roofline  the kernel group that took most device time during the timed encode (CUDA events per batch, HVB_PROFILE):
+          algorithmic bytes / device time against the measured HBM copy bandwidth -- the batches of a host-driven encoder
+          are a few tasks deep, so this is far from the roofline; `hot_path_pass` gives the same kernels at saturating
+          batch sizes (one whole frame's candidates per launch: round 1's frame pass, verified against the oracle at 4K)
+          and `stream` the streaming SAD / SAD4 / SSD / SATD kernels against the HBM roofline
+  cpu_baseline  `turing_ref encode --asm 1` (AVX2/xbyak JIT, all host threads) on a bounded clip of the same content and options
 
-`--impl reference` times the CPU arm alone (rank 0 only under torchrun).
-NOTE this is the pixel hot path of SURVEY.md section 8, not a complete encoder: entropy coding and the
-mode-decision bookkeeping stay on the host in the reference and are out of scope.
+`--impl reference` times the unmodified reference encoder alone (rank 0 only under torchrun).
 """
 from __future__ import annotations
 
@@ -38,7 +41,8 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "4K YUV420 8-bit hot-path frame passes per second (medium preset: ME + intra sweep + TU/RDOQ for one frame)"
+METRIC = "4K YUV420 8-bit encode fps (medium)"
+PASS_METRIC = "hot-path frame passes per second (ME + intra sweep + TU/RDOQ for every candidate of one frame, inputs resident)"
 UNIT = "frames/s"
 N_PICS = 9  # source, reference, second prediction source, six reconstruction targets
 
@@ -46,8 +50,18 @@ N_PICS = 9  # source, reference, second prediction source, six reconstruction ta
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=20)
-    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--steps", type=int, default=12, help="IDR segments encoded in the timed region (per rank)")
+    p.add_argument("--warmup", type=int, default=3, help="segments encoded before it")
+    p.add_argument("--segment-frames", type=int, default=8)
+    p.add_argument("--parallel-segments", type=int, default=0, help="segments in flight per rank (0: chosen from the host's cores)")
+    p.add_argument("--threads", type=int, default=0, help="pool threads per encoder instance (0: chosen from the host's cores)")
+    p.add_argument("--concurrent-frames", type=int, default=8)
+    p.add_argument("--engines", type=int, default=0, help="dispatcher engines of the submission queue (0: default)")
+    p.add_argument("--clip-frames", type=int, default=32, help="distinct frames in the synthetic clip (segments wrap around it)")
+    p.add_argument("--no-identity", action="store_true", help="skip the md5 comparison with turing_ref --asm 0")
+    p.add_argument("--no-pass", action="store_true", help="skip the hot_path_pass block")
+    p.add_argument("--no-stream", action="store_true", help="skip the stream block")
+    p.add_argument("--pass-steps", type=int, default=10)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--width", type=int, default=3840)
     p.add_argument("--height", type=int, default=2160)
@@ -56,6 +70,7 @@ def parse():
     p.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     p.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--workdir", default="")
     return p.parse_args()
 
 
@@ -409,30 +424,197 @@ def reference_encoder_fps(width, height, frames=6):
                 "cmd": "turing_ref encode --speed medium (AVX2/xbyak JIT, threads auto, concurrent-frames 4)"}
 
 
+# ------------------------------------------------------------------------------------------------
+# the encoders
+# ------------------------------------------------------------------------------------------------
+def host_plan(args, world):
+    """threads / instances for this host: the workers of the batched build block on the device, so they are oversubscribed"""
+    cores = os.cpu_count() or 16
+    per_rank = max(4, cores // max(1, world))
+    parallel = args.parallel_segments or max(2, min(8, per_rank // 3))
+    threads = args.threads or max(16, min(64, 6 * per_rank // parallel))
+    return cores, parallel, threads
+
+
+def encoder_options(args):
+    from turingcodec_b200 import encoder
+    return [*encoder.MEDIUM, "--concurrent-frames", str(args.concurrent_frames), "--segment", str(args.segment_frames), "--verbosity", "0"]
+
+
+def workdir(args):
+    base = Path(args.workdir) if args.workdir else Path("/dev/shm" if Path("/dev/shm").exists() else "/tmp") / f"hvb_bench_{os.environ.get('MASTER_PORT', os.getpid())}"
+    base.mkdir(parents=True, exist_ok=True)
+    return base
+
+
+def run_segments(args, clip, frames, out_dir, tag, parallel, threads, rank=0, device=0, profile=True, ranks=1):
+    """one run of integration/_build/turing_b200_segments; returns (wall seconds, encoder-clock seconds, queue stats, md5)"""
+    import re
+    from turingcodec_b200 import encoder
+    bit = out_dir / f"{tag}.bit"
+    cmd = [str(encoder.SEGMENTS), "--parallel-segments", str(parallel), "--clip-frames", str(args.clip_frames)]
+    if ranks > 1:
+        cmd += ["--segment-rank", str(rank), "--segment-ranks", str(ranks)]
+    cmd += ["--input-res", f"{args.width}x{args.height}",
+           "--frame-rate", "30", "--frames", str(frames), "--threads", str(threads), "-o", str(bit)]
+    if args.bit_depth != 8:
+        cmd += ["--bit-depth", str(args.bit_depth)]
+    cmd += [*encoder_options(args), str(clip)]
+    env = dict(os.environ, HVB_STATS="1", HVB_DEVICE=str(device), HVB_PROFILE="1" if profile else "0")
+    env["LD_LIBRARY_PATH"] = str(encoder.LIB_DIR) + ":" + env.get("LD_LIBRARY_PATH", "")
+    if args.engines:
+        env["HVB_ENGINES"] = str(args.engines)
+    t0 = time.perf_counter()
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    wall = time.perf_counter() - t0
+    if res.returncode != 0:
+        raise RuntimeError(f"turing_b200_segments failed ({res.returncode}): {res.stdout[-800:]}\n{res.stderr[-2500:]}")
+    m = re.search(r"segments wall: ([\d.]+) s", res.stderr)
+    inner = float(m.group(1)) if m else wall
+    m = re.search(r"hvbenc stats: (\{.*\})", res.stderr)
+    stats = json.loads(m.group(1)) if m else {}
+    md5, size = None, 0
+    if ranks == 1:
+        md5 = encoder.md5_file(bit)
+        size = bit.stat().st_size
+        bit.unlink()
+    return wall, inner, stats, md5, size, " ".join(cmd[1:-1])
+
+
+KIND_KERNELS = {"me": "meSearchSmallKernel+meSearchKernel+meSubpelKernel", "me_bi": "meBiSearchKernel+meSubpelKernel<BI>", "pu_cost": "puCostKernel",
+                "intra_sweep": "intraSweepKernel8", "tu_chain": "tuFrontKernel+tuOrderKernel+tuRdoqKernel+tuBackKernel"}
+
+
+def encode_roofline(stats):
+    """the kernel group with the most device time in the timed encode: algorithmic bytes / device time vs the HBM copy peak"""
+    kinds = [k for k in KIND_KERNELS if stats.get(k, {}).get("device_ms", 0) > 0]
+    if not kinds:
+        return None
+    peak, peak_src = peaks()
+    top = max(kinds, key=lambda k: stats[k]["device_ms"])
+    s = stats[top]
+    launches = max(1, s["batches"])
+    achieved = s["algorithmic_bytes"] / (s["device_ms"] * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": KIND_KERNELS[top], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": s["algorithmic_bytes"] / launches,
+            "ms_per_launch": s["device_ms"] / launches, "tasks_per_launch": s["tasks"] / launches,
+            "all_kernels": {KIND_KERNELS[k]: {"device_ms": stats[k]["device_ms"], "launches": stats[k]["batches"], "tasks": stats[k]["tasks"],
+                                              "algorithmic_GBps": stats[k]["algorithmic_bytes"] / max(stats[k]["device_ms"], 1e-9) / 1e6,
+                                              "mean_round_trip_us": stats[k]["mean_wait_us"]} for k in kinds},
+            "note": "a host-driven encoder hands the device a few tasks at a time (tasks_per_launch): the kernels are latency-bound here by "
+                    "construction; hot_path_pass has the same kernels at a whole frame per launch, stream the SAD/SATD kernels against HBM"}
+
+
+def reference_encode(args, clip, frames, out_dir, tag, asm, threads=None):
+    from turingcodec_b200 import encoder
+    opts = ["--asm", str(asm), *encoder_options(args)]
+    if args.bit_depth != 8:
+        opts += ["--bit-depth", str(args.bit_depth)]
+    return encoder.encode(encoder.REFERENCE, clip, args.width, args.height, frames, opts, out_dir, tag, threads=threads, dump_reconstruction=False)
+
+
 def run_reference(args, rank):
+    """--impl reference: the unmodified reference encoder (AVX2/xbyak JIT, all host threads) on the same content and options"""
     if rank != 0:
         return
-    arm = CpuArm(args)
-    steps = []
-    for _ in range(max(1, args.warmup if args.warmup < 2 else 1)):
-        arm.run_fraction(1 / 512)
-    budget = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps)))
-    res = None
+    from turingcodec_b200 import encoder
+    if not encoder.REFERENCE.exists():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/turing_ref not built (make -C oracle encoder needs /root/reference)"}))
+        return
+    out = workdir(args)
+    seg = args.segment_frames
+    clip_frames = args.clip_frames
+    clip = out / f"clip_{args.width}x{args.height}_{clip_frames}.yuv"
+    if not clip.exists():
+        encoder.write_clip(clip, args.width, args.height, clip_frames, args.bit_depth)
     t0 = time.time()
-    for _ in range(args.steps):
-        res = arm.measure(budget)
-        steps.append(res["value"])
-    fps = float(np.mean(steps))
+    # bounded: the reference cannot wrap around its input, so a step is a segment of the clip; K steps are timed in runs of
+    # at most clip_frames pictures
+    for _ in range(min(args.warmup, 1)):
+        reference_encode(args, clip, min(seg, clip_frames), out, "refwarm", 1)
+    frames_left, wall, inner, runs = args.steps * seg, 0.0, 0.0, 0
+    last = None
+    while frames_left > 0:
+        n = min(frames_left, clip_frames)
+        last = reference_encode(args, clip, n, out, "ref", 1)
+        wall += last["wall_s"]
+        inner += last.get("encoder_wall_s", last["wall_s"])
+        frames_left -= n
+        runs += 1
+    frames = args.steps * seg
+    fps = frames / inner
+    cores = os.cpu_count()
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"{args.width}x{args.height} YUV420 8-bit, medium preset, one hot-path frame pass per step",
-                       "units_per_step": arm.fp.units, "l2": "n/a (CPU arm)"},
-            "cpu_baseline": {**res, "value": fps},
-            "reference_encoder": reference_encoder_fps(args.width, args.height),
-            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "ms_per_step": 1000.0 * inner / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8" if args.bit_depth == 8 else "u16", "data": "synthetic", "impl": "reference",
+            "config": workload_config(args, 1, None, None),
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "reference",
+                             "sample": f"turing_ref encode --asm 1 ({last['cmd']}), {frames} frames in {runs} run(s) of <= {clip_frames} frames, "
+                                       f"{inner:.1f} s by the encoder's clock on {cores} host threads"},
+            "e2e": {"value": frames / wall, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
     print(json.dumps(line))
+
+
+def workload_config(args, world, parallel, threads):
+    cfg = {"workload": f"{args.width}x{args.height} YUV420 {args.bit_depth}-bit, turing encode --speed medium --no-sao --segment {args.segment_frames} "
+                       f"--concurrent-frames {args.concurrent_frames} (BASELINE.json configs[2]; identity configuration, see bench.py docstring), "
+                       f"one step = one IDR segment of {args.segment_frames} frames, synthetic clip of {args.clip_frames} frames",
+           "frames_per_step": args.segment_frames,
+           "l2": "n/a for the encode (working set: 16+ pictures of 12.4 MB per instance, far above L2); hot_path_pass: per-step working set ~370 MB > 126 MB L2"}
+    if parallel:
+        cfg["parallelism"] = f"{world} GPU(s) x {parallel} segments in flight x {threads} pool threads; segments sharded over ranks, no collective"
+    return cfg
+
+
+def hot_path_pass(args, local, steps):
+    """round 1's measurement, kept as the kernels' own benchmark: one launch per kind over every candidate of a 4K frame, inputs
+    resident; checked here against the oracle's frame pass on the same inputs (the CPU arm's port) when it is built"""
+    import torch
+    from turingcodec_b200 import hvb, workload
+    arm = GpuArm(args, local)
+    for _ in range(3):
+        arm.step_resident()
+    torch.cuda.synchronize(local)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    for k in range(steps):
+        arm.step_resident(ev[k])
+    torch.cuda.synchronize(local)
+    total_ms = ev[0][0].elapsed_time(ev[-1][3])
+    kern = {"me": 0.0, "intra": 0.0, "tu": 0.0}
+    for k in range(steps):
+        kern["me"] += ev[k][0].elapsed_time(ev[k][1]) / steps
+        kern["intra"] += ev[k][1].elapsed_time(ev[k][2]) / steps
+        kern["tu"] += ev[k][2].elapsed_time(ev[k][3]) / steps
+    fp = arm.fp
+    me_out = arm.o_me.cpu().numpy().view(hvb.me_result_t)
+    n_sad_samples = int((me_out["nSad"].astype(np.int64) * fp.me["w"].astype(np.int64) * fp.me["h"].astype(np.int64)).sum())
+    ab = workload.algorithmic_bytes(fp, 0, arm.bps)
+    alg = {"me": ab["me_fixed"] + n_sad_samples * arm.bps, "intra": ab["intra"], "tu": ab["tu"]}
+    peak, peak_src = peaks()
+    names = {"me": "meSearchSmallKernel+meSearchKernel+meSubpelKernel", "intra": "intraSweepKernel8", "tu": "tuFrontKernel+tuRdoqKernel+tuBackKernel"}
+    out = {"metric": PASS_METRIC, "value": 1000.0 * steps / total_ms, "unit": "passes/s", "steps": steps, "units_per_step": fp.units,
+           "kernels": {names[k]: {"ms": kern[k], "algorithmic_GBps": alg[k] / (kern[k] * 1e-3) / 1e9, "frac_of_hbm_peak": alg[k] / (kern[k] * 1e-3) / 1e9 / peak}
+                       for k in kern},
+           "peak_GBps": peak, "peak_source": peak_src, "ncu": ncu_evidence()}
+    # parity at the benchmarked scale: the whole 4K pass against the oracle's port on the host
+    verified = None
+    try:
+        cpu = CpuArm(args, frames=arm.frames)
+        cpu.oracle.lib.orc_bench_use_port()
+        _, _, (o_me, o_intra, o_tu, *_rest) = cpu.run_fraction(1.0)
+        g_me = me_out
+        g_intra = arm.o_intra.cpu().numpy().reshape(-1, 35)
+        g_tu = arm.o_tu.cpu().numpy().view(hvb.tu_result_t)
+        levels = arm.ctx.coeff_download(fp.coeff_count)
+        verified = bool(all(np.array_equal(g_me[n], o_me[n]) for n in ("mv", "mvd", "mvInteger", "mvpFlag", "cost", "subpelCost", "nSad", "flags"))
+                        and np.array_equal(g_intra, o_intra) and all(np.array_equal(g_tu[n], o_tu[n]) for n in ("ssd", "ssdPred", "cbf", "sadQuad"))
+                        and np.array_equal(levels, cpu.levels))
+    except (OSError, ImportError, AttributeError) as e:
+        out["verify_error"] = str(e)[:200]
+    out["verified_vs_oracle"] = verified
+    arm.ctx.close()
+    return out
 
 
 def main():
@@ -446,107 +628,97 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from turingcodec_b200 import build
+    from turingcodec_b200 import build, encoder
     if not build.LIB.exists():
         build.build()
+    if not encoder.SEGMENTS.exists():
+        raise SystemExit("integration/_build/turing_b200_segments is not built (python -c 'import __graft_entry__ as g; g.build()' where /root/reference exists); "
+                         "there is no fallback")
+    torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    arm = GpuArm(args, local)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(local)
 
-    # ---- resident throughput -------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        arm.step_resident()
-    barrier()
-    launches0 = arm.ctx.launch_count
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    with ClockSampler(local) as clocks:
-        barrier()
-        for k in range(args.steps):
-            arm.step_resident(ev[k])
-        barrier()
-    launches = arm.ctx.launch_count - launches0
-    total_ms = ev[0][0].elapsed_time(ev[-1][3])
-    kern = {"me": 0.0, "intra": 0.0, "tu": 0.0}
-    for k in range(args.steps):
-        kern["me"] += ev[k][0].elapsed_time(ev[k][1])
-        kern["intra"] += ev[k][1].elapsed_time(ev[k][2])
-        kern["tu"] += ev[k][2].elapsed_time(ev[k][3])
-    kern = {k: v / args.steps for k, v in kern.items()}
-    t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = world * 1000.0 / ms_per_step  # every rank processes its own frame per step (weak scaling)
-
-    # ---- roofline of the dominant kernel ---------------------------------------------------------
-    from turingcodec_b200 import hvb, workload
-    me_out = arm.o_me.cpu().numpy().view(hvb.me_result_t)
-    fp = arm.fp
-    n_sad_samples = int((me_out["nSad"].astype(np.int64) * fp.me["w"].astype(np.int64) * fp.me["h"].astype(np.int64)).sum())
-    ab = workload.algorithmic_bytes(fp, 0, arm.bps)
-    alg = {"me": ab["me_fixed"] + n_sad_samples * arm.bps, "intra": ab["intra"], "tu": ab["tu"]}
-    dominant = max(kern, key=kern.get)
-    peak, peak_src = peaks()
-    achieved = alg[dominant] / (kern[dominant] * 1e-3) / 1e9
-    kernel_names = {"me": "meSearchSmallKernel+meSearchKernel+meSubpelKernel", "intra": "intraSweepKernel8", "tu": "tuFrontKernel+tuRdoqKernel+tuBackKernel"}
-    roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic_from_profile(kernel_names[dominant]), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[dominant], "ms_per_launch": kern[dominant],
-                "all_kernels": {kernel_names[k]: {"ms": kern[k], "algorithmic_GBps": alg[k] / (kern[k] * 1e-3) / 1e9} for k in kern},
-                "ncu": ncu_evidence(),
-                "note": "pictures (25 MB) stay L2-resident across the 100-300 candidates of a search, so algorithmic "
-                        "bytes exceed DRAM traffic by design; see DESIGN.md"}
-
-    # ---- end to end through the host-facing ABI ---------------------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        arm.ctx.set_stream(None)
-        arm.ctx.set_pipelined(True)  # page-locked task / result arrays: copies overlap the kernels, results valid after sync()
-        arm.step_e2e(0)
-        arm.step_e2e(1)
-        arm.ctx.sync()
-        barrier()
-        n_e2e = max(1, min(args.steps, 5))
-        t0 = time.perf_counter()
-        for k in range(n_e2e):
-            arm.step_e2e(k)
-        arm.ctx.sync()
-        wall = time.perf_counter() - t0
-        # the host-facing path delivers what the resident path computed
-        for name in ("mv", "mvd", "cost", "subpelCost", "nSad"):
-            assert np.array_equal(arm.h_me[name], me_out[name]), f"e2e motion-search results differ from the resident run in {name}"
-        t = torch.tensor([wall], dtype=torch.float64, device=f"cuda:{local}")
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        h2d, d2h = arm.e2e_bytes()
-        e2e = {"value": world * n_e2e / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": n_e2e, "timing": "host wall clock from the first hvb_* call of the first step to hvb_sync() after the last; "
-               "pipelined host mode (hvb_set_pipelined): every step uploads both pictures, the neighbour pool and the three task "
-               "arrays from page-locked host memory and receives the three result arrays back; uploads are double-buffered "
-               "(two picture pairs / pool regions alternate) so step k+1's copies overlap step k's kernels"}
-        arm.ctx.set_pipelined(False)
+        return float(t.item())
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = CpuArm(args, fp=None, frames=arm.frames).measure(args.cpu_seconds)
+    cores, parallel, threads = host_plan(args, world)
+    out = workdir(args)
+    seg = args.segment_frames
+    clip = out / f"clip_{args.width}x{args.height}_{args.clip_frames}.yuv"
+    if rank == 0 and not clip.exists():
+        encoder.write_clip(clip, args.width, args.height, args.clip_frames, args.bit_depth)
+    barrier()
+    rank_dir = out / f"rank{rank}"
+    rank_dir.mkdir(exist_ok=True)
 
+    # ---- warm-up: W segments (page cache, driver, clocks) -----------------------------------------
+    if args.warmup > 0:
+        run_segments(args, clip, args.warmup * seg, rank_dir, "warm", parallel, threads, rank, local, profile=False)
+    barrier()
+    # ---- timed region: K segments per rank: one job of world * K segments, rank r takes segments r, r + world, ... ------
+    frames = args.steps * seg
+    job_dir = out / "job"
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u8" if args.bit_depth == 8 else "u16", "data": "synthetic",
-                "config": {"workload": f"{args.width}x{args.height} YUV420 {args.bit_depth}-bit, medium preset, one hot-path frame pass per step "
-                                       + ("(configs[2] of BASELINE.json)" if args.bit_depth == 8 else "(16-bit sample path of configs[3])"),
-                           "units_per_step": fp.units,
-                           "l2": "per-step working set (tasks+results+levels+pictures) ~370 MB > 126 MB L2; no explicit flush",
-                           "parallelism": f"frames sharded over {world} GPU(s), no collective"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks.summary()}
+        job_dir.mkdir(exist_ok=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        wall, inner, stats, _md5, _size, cmd = run_segments(args, clip, world * frames, job_dir if world > 1 else rank_dir, "timed", parallel, threads,
+                                                            rank, local, ranks=world)
+        barrier()
+    if world > 1 and rank == 0:
+        parts = [job_dir / f"timed.bit.seg{k}" for k in range(world * args.steps)]
+        from turingcodec_b200 import sharding
+        sharding.concat_segments(parts, job_dir / "timed.bit")
+        for part in parts:
+            part.unlink()
+    wall, inner = max_over_ranks(wall), max_over_ranks(inner)
+    value = world * frames / inner
+    e2e = {"value": world * frames / wall, "unit": UNIT, "h2d_bytes_per_step": stats.get("h2d_bytes", 0) / args.steps,
+           "d2h_bytes_per_step": stats.get("d2h_bytes", 0) / args.steps, "steps": args.steps,
+           "timing": "wall clock around the turing_b200_segments process of each rank (max over ranks): process start, CUDA context and session, "
+                     "YUV read, encode, bitstream write; h2d = source pictures + finished CTUs of reference pictures + tasks + predictions, "
+                     "d2h = results + reconstructions + levels (counted by the submission queue)"}
+
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1000.0 * inner / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8" if args.bit_depth == 8 else "u16", "data": "synthetic",
+                "config": workload_config(args, world, parallel, threads), "host_cores": cores, "cmd": cmd,
+                "roofline": encode_roofline(stats), "queue": stats, "e2e": None if args.no_e2e else e2e,
+                "gpu_launches": int(stats.get("kernel_launches", 0)), "clocks": clocks.summary()}
+    # ---- identity: one more run on a clip the reference can encode in one go, against --asm 0 --------------------------------------------
+    if rank == 0 and world == 1 and not args.no_identity and encoder.REFERENCE.exists():
+        n = min(args.clip_frames, 2 * seg + 1)
+        _, _, _, md5, size, _ = run_segments(args, clip, n, rank_dir, "ident", parallel, threads, rank, local, profile=False)
+        ref0 = reference_encode(args, clip, n, rank_dir, "ref0", 0)
+        line["bitstream_md5_equals_asm0"] = bool(md5 == ref0["bitstream_md5"])
+        line["identity"] = {"frames": n, "bitstream_bytes": size, "md5": md5, "reference_asm0_md5": ref0["bitstream_md5"],
+                            "reference_asm0_fps": ref0["fps"], "cmd": ref0["cmd"]}
+    # ---- the reference on the host cores (reported baseline) -----------------------------------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu and encoder.REFERENCE.exists():
+        n = min(args.clip_frames, 3 * seg)
+        ref1 = reference_encode(args, clip, n, rank_dir, "ref1", 1)
+        line["cpu_baseline"] = {"value": n / ref1.get("encoder_wall_s", ref1["wall_s"]), "unit": UNIT, "cores": cores, "kind": "reference",
+                                "sample": f"turing_ref encode --asm 1 on the first {n} frames of the same clip, same options, all host threads "
+                                          f"({ref1.get('encoder_wall_s', ref1['wall_s']):.1f} s by the encoder's clock)"}
+    # ---- the kernels at saturating batch sizes ---------------------------------------------------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_pass:
+        line["hot_path_pass"] = hot_path_pass(args, local, args.pass_steps)
+    if rank == 0 and world == 1 and not args.no_stream:
+        sys.path.insert(0, str(ROOT / "tools"))
+        import stream_metrics
+        st = stream_metrics.measure(local, blocks=(64, 32), reps=3)
+        line["stream"] = st
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -64,6 +64,10 @@ int hvb_sync(hvb_context *ctx);
  * blocks and may be called from any thread (a completion thread that serves several contexts without parking a core
  * per context inside the driver's wait). */
 int hvb_poll(hvb_context *ctx);
+/* Device-side stopwatch: hvb_mark records a timestamp on the context's stream (slot 0..15, events created on first use);
+ * hvb_elapsed_ms gives the device time between two recorded slots once the work between them has completed. */
+int hvb_mark(hvb_context *ctx, int slot);
+int hvb_elapsed_ms(hvb_context *ctx, int from, int to, float *ms);
 /* Pipelined host mode.  Off (default): every HVB_HOST call returns after its results have landed.  On: a batch call
  * whose task and result arrays are page-locked (cudaHostAlloc / cudaHostRegister -- an encoder's arena) only enqueues
  * work -- tasks go up on a copy-in stream, the kernels run on the context's stream, the results come back on a copy-out

@@ -26,6 +26,9 @@
 #include <thread>
 #include <vector>
 
+#include "turing_hooks_state.h"
+#include <chrono>
+
 int encode(int argc, const char *const argv[]); // turing/encode.cpp:577
 
 namespace {
@@ -71,8 +74,8 @@ void appendSegment(std::ofstream &out, const std::vector<char> &b, bool first)
 
 int main(int argc, const char *argv[])
 {
-    int parallel = 4, rank = 0, ranks = 1;
-    long frames = -1, segment = -1, seek = 0;
+    int parallel = 4, rank = 0, ranks = 1, width = 0, height = 0, bitDepth = 8, internalBitDepth = 0;
+    long frames = -1, segment = -1, seek = 0, clipFrames = 0;
     std::string output;
     std::vector<std::string> pass; // options handed to every instance unchanged
     for (int i = 1; i < argc; ++i)
@@ -86,7 +89,19 @@ int main(int argc, const char *argv[])
         else if (a == "--seek") seek = atol(value().c_str());
         else if (a == "--segment") segment = atol(value().c_str());
         else if (a == "-o" || a == "--output-file") output = value();
-        else pass.push_back(a);
+        else if (a == "--clip-frames") clipFrames = atol(value().c_str()); // benchmarking: the input holds this many frames, segments wrap around
+        else
+        {
+            pass.push_back(a);
+            if ((a == "--input-res" || a == "--bit-depth" || a == "--internal-bit-depth") && i + 1 < argc)
+            {
+                const std::string v = argv[++i];
+                pass.push_back(v);
+                if (a == "--input-res") sscanf(v.c_str(), "%dx%d", &width, &height);
+                else if (a == "--bit-depth") bitDepth = atoi(v.c_str());
+                else internalBitDepth = atoi(v.c_str());
+            }
+        }
     }
     if (frames <= 0 || segment <= 0 || output.empty() || parallel < 1 || ranks < 1 || rank < 0 || rank >= ranks)
     {
@@ -96,6 +111,13 @@ int main(int argc, const char *argv[])
     }
     // device pictures: every instance keeps its DPB and a source + reconstruction per picture in flight
     setenv("HVB_POOL_PICTURES", std::to_string(std::min(900, 48 * parallel + 16)).c_str(), 0);
+    // the device session before the clock starts (CUDA context, page-locked buffers, the picture pool: a one-off)
+    if (width > 0 && height > 0 && hvbhooks::on())
+    {
+        const int depth = internalBitDepth ? internalBitDepth : bitDepth;
+        hvbhooks::session(depth > 8 ? 2 : 1, depth, width, height);
+    }
+    const auto t0 = std::chrono::steady_clock::now();
     const long nSegments = (frames + segment - 1) / segment;
     std::vector<long> mine;
     for (long k = rank; k < nSegments; k += ranks) mine.push_back(k);
@@ -108,8 +130,10 @@ int main(int argc, const char *argv[])
             if (at >= mine.size()) return;
             const long k = mine[at];
             const long first = k * segment, count = std::min(segment, frames - first);
+            long from = seek + first;
+            if (clipFrames > 0) from = (from / segment) % std::max(1L, clipFrames / segment) * segment;
             std::vector<std::string> args = {"turing encode", "--segment", std::to_string(segment), "--frames", std::to_string(count), "--seek",
-                                             std::to_string(seek + first), "-o", output + ".seg" + std::to_string(k)};
+                                             std::to_string(from), "-o", output + ".seg" + std::to_string(k)};
             args.insert(args.end(), pass.begin(), pass.end());
             std::vector<const char *> av;
             for (auto &s : args) av.push_back(s.c_str());
@@ -120,6 +144,10 @@ int main(int argc, const char *argv[])
     for (int t = 0; t < std::min<long>(parallel, (long)mine.size()); ++t) threads.emplace_back(worker);
     for (auto &t : threads) t.join();
     if (failed) return 1;
+    long encoded = 0;
+    for (long k : mine) encoded += std::min(segment, frames - k * segment);
+    fprintf(stderr, "segments wall: %.6f s for %ld frames in %zu segments (session set-up excluded)\n",
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), encoded, mine.size());
     if (ranks == 1)
     {
         std::ofstream out(output, std::ios::binary);

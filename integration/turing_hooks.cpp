@@ -24,7 +24,7 @@ void shutdown()
     if (!gSession) return;
     if (envInt("HVB_STATS", 0))
     {
-        char buf[2048];
+        char buf[4096];
         if (!hvbenc_stats(gSession, buf, sizeof(buf))) fprintf(stderr, "hvbenc stats: %s\n", buf);
     }
     hvbenc_destroy(gSession);

@@ -71,6 +71,8 @@ cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = reinterpret_cast<cudaEvent_t>(malloc(1)); return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = reinterpret_cast<cudaEvent_t>(malloc(1)); return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }

@@ -63,3 +63,45 @@ def test_sharding_properties():
         for n in (0, 1, 7, 8, 33):
             seen = sorted(s for r in range(world) for s in sharding.segments_for_rank(n, r, world))
             assert seen == list(range(n))
+
+
+# ---- the real thing on the CPU: two ranks encode alternate IDR segments, rank 0 reassembles the reference's stream ----------
+
+def _encode_worker(rank, world, port, clip, width, height, frames, seg, work):
+    import subprocess
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from turingcodec_b200 import encoder, sharding
+    for k, rng in zip(sharding.segments_for_rank((frames + seg - 1) // seg, rank, world), sharding.frames_for_rank(frames, seg, rank, world)):
+        # what integration/segments_main.cpp hands each encoder instance, with the reference encoder standing in on the CPU
+        cmd = [str(encoder.REFERENCE), "encode", "--input-res", f"{width}x{height}", "--frame-rate", "30", "--speed", "fast", "--threads", "2",
+               "--segment", str(seg), "--seek", str(rng.start), "--frames", str(len(rng)), "-o", f"{work}/out.seg{k}", clip]
+        subprocess.run(cmd, check=True, capture_output=True)
+    dist.barrier()
+    if rank == 0:
+        n = (frames + seg - 1) // seg
+        sharding.concat_segments([f"{work}/out.seg{k}" for k in range(n)], f"{work}/out.bit")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_reassemble_the_reference_segment_stream(tmp_path):
+    import subprocess
+
+    import pytest
+    from turingcodec_b200 import encoder
+    if not encoder.REFERENCE.exists():
+        pytest.skip("oracle/_ref/turing_ref not built")
+    width, height, frames, seg = 64, 64, 11, 4
+    clip = encoder.write_clip(tmp_path / "clip.yuv", width, height, frames)
+    subprocess.run([str(encoder.REFERENCE), "encode", "--input-res", f"{width}x{height}", "--frame-rate", "30", "--speed", "fast", "--threads", "2",
+                    "--segment", str(seg), "--frames", str(frames), "-o", str(tmp_path / "whole.bit"), str(clip)], check=True, capture_output=True)
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_encode_worker, args=(r, 2, port, str(clip), width, height, frames, seg, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert (tmp_path / "out.bit").read_bytes() == (tmp_path / "whole.bit").read_bytes()

@@ -109,6 +109,8 @@ extern "C" void hvb_destroy(hvb_context *ctx)
         if (slot.dev) cudaFree(slot.dev);
         if (slot.done) cudaEventDestroy(slot.done);
     }
+    for (cudaEvent_t &m : ctx->marks)
+        if (m) cudaEventDestroy(m);
     if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
     if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
     if (ctx->evIn) cudaEventDestroy(ctx->evIn);
@@ -142,6 +144,22 @@ extern "C" int hvb_sync(hvb_context *ctx)
     if (e == cudaSuccess && ctx->copyOut) e = cudaStreamSynchronize(ctx->copyOut);
     for (auto &slot : ctx->slots) slot.busy = false;
     return hvbCuda(ctx, e, "hvb_sync");
+}
+
+extern "C" int hvb_mark(hvb_context *ctx, int slot)
+{
+    HVB_CHECK_ARGS(ctx, slot >= 0 && slot < 16);
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaSuccess;
+    if (!ctx->marks[slot]) e = cudaEventCreate(&ctx->marks[slot]);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->marks[slot], ctx->stream);
+    return hvbCuda(ctx, e, "hvb_mark");
+}
+
+extern "C" int hvb_elapsed_ms(hvb_context *ctx, int from, int to, float *ms)
+{
+    HVB_CHECK_ARGS(ctx, ms && from >= 0 && from < 16 && to >= 0 && to < 16 && ctx->marks[from] && ctx->marks[to]);
+    return hvbCuda(ctx, cudaEventElapsedTime(ms, ctx->marks[from], ctx->marks[to]), "hvb_elapsed_ms");
 }
 
 extern "C" int hvb_poll(hvb_context *ctx)

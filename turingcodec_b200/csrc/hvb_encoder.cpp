@@ -168,6 +168,11 @@ struct Engine
 
     double deviceSeconds = 0;
     int64_t dispatches = 0;
+    // statistics: device time per kind (HVB_PROFILE), the kernels' algorithmic bytes, bytes crossing the bus
+    bool profile = false;
+    double kindMs[6] = {0, 0, 0, 0, 0, 0}; // uploads, me, bi, pu, intra, tu
+    double algBytes[6] = {0, 0, 0, 0, 0, 0};
+    double toDevice = 0, fromDevice = 0;
 };
 
 struct hvbenc
@@ -224,23 +229,30 @@ int runBatch(Engine *enc, int b)
 {
     hvb_context *ctx = enc->ctx;
     int rc = 0;
+    const bool prof = enc->profile;
+    if (prof) hvb_mark(ctx, 0);
     for (const UploadTask &u : enc->uploads[b])
     {
         rc = hvb_picture_upload_rect(ctx, u.pic, u.cIdx, enc->uploadStage[b] + u.offset, u.w, u.x0, u.y0, u.w, u.h);
         if (rc) return rc;
     }
+    if (prof) hvb_mark(ctx, 1);
     if (enc->me.n[b]) rc = hvb_me_search_batch(ctx, enc->me.tasks[b], enc->me.n[b], enc->me.results[b], HVB_DEVICE);
     if (rc) return rc;
+    if (prof) hvb_mark(ctx, 2);
     if (enc->bi.n[b]) rc = hvb_me_bi_search_batch(ctx, enc->bi.tasks[b], enc->bi.n[b], enc->bi.results[b], HVB_DEVICE);
     if (rc) return rc;
+    if (prof) hvb_mark(ctx, 3);
     if (enc->pu.n[b]) rc = hvb_pu_cost_batch(ctx, enc->pu.tasks[b], enc->pu.n[b], enc->pu.results[b], HVB_DEVICE);
     if (rc) return rc;
+    if (prof) hvb_mark(ctx, 4);
     if (enc->intra.n[b])
     {
         rc = hvb_pool_upload(ctx, enc->poolStage[b], enc->poolUsed[b], 0);
         if (!rc) rc = hvb_intra_satd35_batch(ctx, enc->intra.tasks[b], enc->intra.n[b], enc->intra.results[b], HVB_DEVICE);
         if (rc) return rc;
     }
+    if (prof) hvb_mark(ctx, 5);
     size_t levelCount = 0;
     if (enc->tu.n[b])
     {
@@ -252,6 +264,7 @@ int runBatch(Engine *enc, int b)
     // the levels come back with the batch (enqueued: the destination is page-locked)
     if (levelCount) rc = hvb_coeff_download(ctx, enc->levelsHost, levelCount, 0);
     if (rc) return rc;
+    if (prof) hvb_mark(ctx, 6);
     // one wait for the whole batch, on the session's completion thread
     {
         hvbenc *session = enc->session;
@@ -270,6 +283,52 @@ int runBatch(Engine *enc, int b)
     }
     rc = hvb_sync(ctx); // everything has completed: returns at once, and resets the context's staging slots
     if (rc) return rc;
+    if (prof)
+        for (int k = 0; k < 6; ++k)
+        {
+            float ms = 0;
+            if (!hvb_elapsed_ms(ctx, k, k + 1, &ms)) enc->kindMs[k] += ms;
+        }
+    // statistics: what the kernels of this batch had to touch and what crossed the bus
+    {
+        const double B = enc->bps;
+        for (const UploadTask &u : enc->uploads[b]) enc->toDevice += (double)u.w * u.h * B;
+        for (int i = 0; i < enc->me.n[b]; ++i)
+        {
+            const hvb_me_task &t = enc->me.tasks[b][i];
+            const double wh = (double)t.w * t.h, sup = (double)(t.w + 7) * (t.h + 7) + wh;
+            enc->algBytes[1] += wh * B + enc->me.results[b][i].nSad * wh * B + (t.halfPel ? (t.quarterPel ? 17 : 9) * sup * B : 0);
+        }
+        for (int i = 0; i < enc->bi.n[b]; ++i)
+        {
+            const hvb_me_bi_task &t = enc->bi.tasks[b][i];
+            const double wh = (double)t.w * t.h, sup = (double)(t.w + 7) * (t.h + 7) + wh;
+            enc->algBytes[2] += wh * B + (t.smallWindow ? 9 : 121) * wh * B + (t.halfPel ? (t.quarterPel ? 18 : 9) : 0) * sup * B;
+        }
+        for (int i = 0; i < enc->pu.n[b]; ++i)
+        {
+            const hvb_pu_cost_task &t = enc->pu.tasks[b][i];
+            const double sup = (double)(t.w + 7) * (t.h + 7) + (double)t.w * t.h;
+            enc->algBytes[3] += 1.5 * sup * B * ((t.ref_pic[0] >= 0) + (t.ref_pic[1] >= 0));
+        }
+        for (int i = 0; i < enc->intra.n[b]; ++i)
+        {
+            const double n = 1 << enc->intra.tasks[b][i].log2n;
+            enc->algBytes[4] += (4 * n + 1) * B + n * n * B + 140;
+        }
+        for (int i = 0; i < enc->tu.n[b]; ++i)
+        {
+            const double nn = (double)(1 << (2 * enc->tu.tasks[b][i].log2n));
+            enc->algBytes[5] += 3 * nn * B + 2 * nn + 32;
+            enc->toDevice += nn * B;
+            enc->fromDevice += nn * B + 2 * nn;
+        }
+        enc->toDevice += enc->me.n[b] * sizeof(hvb_me_task) + enc->bi.n[b] * sizeof(hvb_me_bi_task) + enc->pu.n[b] * sizeof(hvb_pu_cost_task) +
+                         enc->intra.n[b] * sizeof(hvb_intra_sweep_task) + enc->tu.n[b] * sizeof(hvb_tu_task) + enc->poolUsed[b] * B +
+                         enc->nSnapshots[b] * sizeof(hvb_rdoq_ctx);
+        enc->fromDevice += enc->me.n[b] * sizeof(hvb_me_result) + enc->bi.n[b] * sizeof(hvb_me_bi_result) + enc->pu.n[b] * 12.0 +
+                           enc->intra.n[b] * 140.0 + enc->tu.n[b] * sizeof(hvb_tu_result);
+    }
     // reconstruction cells and levels back to the callers' buffers
     for (size_t i = 0; i < enc->tuExtra[b].size(); ++i)
     {
@@ -415,6 +474,7 @@ int createEngine(int device, int bytes_per_sample, int bit_depth, int width, int
     enc->bitDepth = bit_depth;
     enc->width = width;
     enc->height = height;
+    if (const char *v = getenv("HVB_PROFILE")) enc->profile = atoi(v) != 0;
     *out = enc;
     return hvb_set_pipelined(ctx, 1); // uploads from the page-locked staging buffers are enqueued, not waited for
 }
@@ -726,10 +786,13 @@ extern "C" int hvbenc_stats(hvbenc *session, char *buf, size_t bytes)
 {
     if (!session || !buf || !bytes) return HVB_ERR_INVALID;
     long long dispatches = 0, launches = 0, tasks[5] = {0, 0, 0, 0, 0}, batches[5] = {0, 0, 0, 0, 0}, rects = 0, rectBytes = 0;
-    double busy = 0;
+    double busy = 0, kindMs[6] = {0, 0, 0, 0, 0, 0}, alg[6] = {0, 0, 0, 0, 0, 0}, toDevice = 0, fromDevice = 0;
     for (Engine *enc : session->engines)
     {
         std::lock_guard<std::mutex> g(enc->m);
+        for (int k = 0; k < 6; ++k) kindMs[k] += enc->kindMs[k], alg[k] += enc->algBytes[k];
+        toDevice += enc->toDevice;
+        fromDevice += enc->fromDevice;
         dispatches += enc->dispatches;
         busy += enc->deviceSeconds;
         launches += hvb_launch_count(enc->ctx);
@@ -745,12 +808,16 @@ extern "C" int hvbenc_stats(hvbenc *session, char *buf, size_t bytes)
     for (int k = 0; k < 5 && at < (int)bytes; ++k)
     {
         const long long c = session->waitCount[k + 1];
-        at += snprintf(buf + at, bytes - at, "\"%s\": {\"tasks\": %lld, \"batches\": %lld, \"requests\": %lld, \"mean_wait_us\": %.1f}, ", names[k], tasks[k],
-                       batches[k], c, c ? session->waitNs[k + 1] / 1000.0 / c : 0.0);
+        at += snprintf(buf + at, bytes - at,
+                       "\"%s\": {\"tasks\": %lld, \"batches\": %lld, \"requests\": %lld, \"mean_wait_us\": %.1f, \"device_ms\": %.3f, "
+                       "\"algorithmic_bytes\": %.0f}, ",
+                       names[k], tasks[k], batches[k], c, c ? session->waitNs[k + 1] / 1000.0 / c : 0.0, kindMs[k + 1], alg[k + 1]);
     }
     const long long uc = session->waitCount[0];
     if (at < (int)bytes)
-        snprintf(buf + at, bytes - at, "\"uploads\": {\"rects\": %lld, \"bytes\": %lld, \"mean_wait_us\": %.1f}}", rects, rectBytes,
-                 uc ? session->waitNs[0] / 1000.0 / uc : 0.0);
+        snprintf(buf + at, bytes - at,
+                 "\"uploads\": {\"rects\": %lld, \"bytes\": %lld, \"mean_wait_us\": %.1f, \"device_ms\": %.3f}, "
+                 "\"h2d_bytes\": %.0f, \"d2h_bytes\": %.0f}",
+                 rects, rectBytes, uc ? session->waitNs[0] / 1000.0 / uc : 0.0, kindMs[0], toDevice, fromDevice);
     return HVB_OK;
 }

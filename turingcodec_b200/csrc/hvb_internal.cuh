@@ -55,6 +55,7 @@ struct hvb_context
     cudaStream_t stream = nullptr;
     cudaStream_t ownStream = nullptr;
     int64_t launches = 0;
+    cudaEvent_t marks[16] = {}; // hvb_mark
     std::string lastError;
 
     HvbPicture pictures[HVB_MAX_PICTURES];
