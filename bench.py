@@ -9,7 +9,9 @@ bitstream is byte-identical to `turing_ref encode --asm 0` with the same options
 (`bitstream_md5_equals_asm0`).  Identity configuration: `--speed medium --no-sao` (with SAO the reference itself is not
 reproducible from run to run, profiles/r02a_asm0_asm1_experiment.txt).
 
-  step    one IDR segment of --segment-frames (8) pictures; every rank encodes K segments in the timed region (weak scaling)
+  step    one IDR segment of --segment-frames (8) pictures; the timed region is ONE job of K segments, sharded over the ranks
+          (rank r encodes segments r, r + N, ...: strong scaling -- the host's cores, which run the reference's decision code
+          for every rank, are a fixed resource of the box)
   value   frames/s from the encoder's own clock: first picture submitted to last bitstream byte, device session set up
           and the source clip in the page cache before the clock starts (max over ranks)
   e2e     frames/s of the whole `turing_b200_segments` process by wall clock: start-up, CUDA context and session, reading the
@@ -44,6 +46,8 @@ sys.path.insert(0, str(ROOT))
 METRIC = "4K YUV420 8-bit encode fps (medium)"
 PASS_METRIC = "hot-path frame passes per second (ME + intra sweep + TU/RDOQ for every candidate of one frame, inputs resident)"
 UNIT = "frames/s"
+# the unmodified reference encoder (test infrastructure, built by oracle/Makefile): the CPU arm and the identity check
+REFERENCE_ENCODER = ROOT / "oracle" / "_ref" / "turing_ref"
 N_PICS = 9  # source, reference, second prediction source, six reconstruction targets
 
 
@@ -510,7 +514,7 @@ def reference_encode(args, clip, frames, out_dir, tag, asm, threads=None):
     opts = ["--asm", str(asm), *encoder_options(args)]
     if args.bit_depth != 8:
         opts += ["--bit-depth", str(args.bit_depth)]
-    return encoder.encode(encoder.REFERENCE, clip, args.width, args.height, frames, opts, out_dir, tag, threads=threads, dump_reconstruction=False)
+    return encoder.encode(REFERENCE_ENCODER, clip, args.width, args.height, frames, opts, out_dir, tag, threads=threads, dump_reconstruction=False)
 
 
 def run_reference(args, rank):
@@ -518,7 +522,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     from turingcodec_b200 import encoder
-    if not encoder.REFERENCE.exists():
+    if not REFERENCE_ENCODER.exists():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/turing_ref not built (make -C oracle encoder needs /root/reference)"}))
         return
     out = workdir(args)
@@ -545,7 +549,7 @@ def run_reference(args, rank):
     fps = frames / inner
     cores = os.cpu_count()
     line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1000.0 * inner / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1000.0 * inner / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8" if args.bit_depth == 8 else "u16", "data": "synthetic", "impl": "reference",
             "config": workload_config(args, 1, None, None),
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "reference",
@@ -562,8 +566,6 @@ def workload_config(args, world, parallel, threads):
                        f"one step = one IDR segment of {args.segment_frames} frames, synthetic clip of {args.clip_frames} frames",
            "frames_per_step": args.segment_frames,
            "l2": "n/a for the encode (working set: 16+ pictures of 12.4 MB per instance, far above L2); hot_path_pass: per-step working set ~370 MB > 126 MB L2"}
-    if parallel:
-        cfg["parallelism"] = f"{world} GPU(s) x {parallel} segments in flight x {threads} pool threads; segments sharded over ranks, no collective"
     return cfg
 
 
@@ -663,26 +665,27 @@ def main():
     if args.warmup > 0:
         run_segments(args, clip, args.warmup * seg, rank_dir, "warm", parallel, threads, rank, local, profile=False)
     barrier()
-    # ---- timed region: K segments per rank: one job of world * K segments, rank r takes segments r, r + world, ... ------
+    # ---- timed region: one job of K segments, rank r takes segments r, r + world, ... (strong scaling) ------------------
     frames = args.steps * seg
     job_dir = out / "job"
     if rank == 0:
         job_dir.mkdir(exist_ok=True)
     with ClockSampler(local) as clocks:
         barrier()
-        wall, inner, stats, _md5, _size, cmd = run_segments(args, clip, world * frames, job_dir if world > 1 else rank_dir, "timed", parallel, threads,
+        wall, inner, stats, _md5, _size, cmd = run_segments(args, clip, frames, job_dir if world > 1 else rank_dir, "timed", parallel, threads,
                                                             rank, local, ranks=world)
         barrier()
     if world > 1 and rank == 0:
-        parts = [job_dir / f"timed.bit.seg{k}" for k in range(world * args.steps)]
+        parts = [job_dir / f"timed.bit.seg{k}" for k in range(args.steps)]
         from turingcodec_b200 import sharding
         sharding.concat_segments(parts, job_dir / "timed.bit")
         for part in parts:
             part.unlink()
     wall, inner = max_over_ranks(wall), max_over_ranks(inner)
-    value = world * frames / inner
-    e2e = {"value": world * frames / wall, "unit": UNIT, "h2d_bytes_per_step": stats.get("h2d_bytes", 0) / args.steps,
-           "d2h_bytes_per_step": stats.get("d2h_bytes", 0) / args.steps, "steps": args.steps,
+    value = frames / inner
+    my_steps = max(1, len(range(rank, args.steps, world)))
+    e2e = {"value": frames / wall, "unit": UNIT, "h2d_bytes_per_step": stats.get("h2d_bytes", 0) / my_steps,
+           "d2h_bytes_per_step": stats.get("d2h_bytes", 0) / my_steps, "steps": args.steps,
            "timing": "wall clock around the turing_b200_segments process of each rank (max over ranks): process start, CUDA context and session, "
                      "YUV read, encode, bitstream write; h2d = source pictures + finished CTUs of reference pictures + tasks + predictions, "
                      "d2h = results + reconstructions + levels (counted by the submission queue)"}
@@ -690,13 +693,14 @@ def main():
     line = None
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1000.0 * inner / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": 1000.0 * inner / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "u8" if args.bit_depth == 8 else "u16", "data": "synthetic",
                 "config": workload_config(args, world, parallel, threads), "host_cores": cores, "cmd": cmd,
+                "parallelism": f"{world} GPU(s), per rank up to {parallel} segments in flight x {threads} pool threads; segments sharded over ranks, no collective",
                 "roofline": encode_roofline(stats), "queue": stats, "e2e": None if args.no_e2e else e2e,
                 "gpu_launches": int(stats.get("kernel_launches", 0)), "clocks": clocks.summary()}
     # ---- identity: one more run on a clip the reference can encode in one go, against --asm 0 --------------------------------------------
-    if rank == 0 and world == 1 and not args.no_identity and encoder.REFERENCE.exists():
+    if rank == 0 and world == 1 and not args.no_identity and REFERENCE_ENCODER.exists():
         n = min(args.clip_frames, 2 * seg + 1)
         _, _, _, md5, size, _ = run_segments(args, clip, n, rank_dir, "ident", parallel, threads, rank, local, profile=False)
         ref0 = reference_encode(args, clip, n, rank_dir, "ref0", 0)
@@ -704,7 +708,7 @@ def main():
         line["identity"] = {"frames": n, "bitstream_bytes": size, "md5": md5, "reference_asm0_md5": ref0["bitstream_md5"],
                             "reference_asm0_fps": ref0["fps"], "cmd": ref0["cmd"]}
     # ---- the reference on the host cores (reported baseline) -----------------------------------------------------------------------------
-    if rank == 0 and world == 1 and not args.no_cpu and encoder.REFERENCE.exists():
+    if rank == 0 and world == 1 and not args.no_cpu and REFERENCE_ENCODER.exists():
         n = min(args.clip_frames, 3 * seg)
         ref1 = reference_encode(args, clip, n, rank_dir, "ref1", 1)
         line["cpu_baseline"] = {"value": n / ref1.get("encoder_wall_s", ref1["wall_s"]), "unit": UNIT, "cores": cores, "kind": "reference",

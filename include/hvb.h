@@ -83,6 +83,10 @@ int hvb_set_pipelined(hvb_context *ctx, int on);
  * submission queue; results are valid after hvb_sync). */
 int hvb_host_alloc(hvb_context *ctx, size_t bytes, void **out);
 int hvb_host_free(hvb_context *ctx, void *ptr);
+/* hvb_sad_batch / hvb_sad4_batch with the blocks staged into shared memory by the Tensor Memory Accelerator
+ * (cp.async.bulk.tensor over per-plane tensor maps) instead of the load/store path; same results.  Default: off, or the
+ * value of HVB_TMA in the environment.  Pictures must own device memory (not hvb_picture_wrap). */
+int hvb_set_tma(hvb_context *ctx, int on);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t hvb_launch_count(hvb_context *ctx);
 /* 1 when the device is present and kernels for it are in this binary */

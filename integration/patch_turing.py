@@ -32,6 +32,12 @@ PATCHES = {
          "#define HVBHOOKS_SEARCH\n#include \"turing_hooks.hpp\"\n"),
         ("template <class H> static void searchMotionBi(H &h, int refList)\n{\n", AFTER,
          "    if (hvbhooks::searchMotionBi(h, refList)) return;\n"),
+        # Search<prediction_unit>::go2: results issued ahead for one PU must not outlive it (picture ids are recycled)
+        ("            bool debug = false;//pu == prediction_unit(116, 0, 12, 16) && h[PicOrderCntVal()] == 8;\n", AFTER,
+         "            hvbhooks::memo().clear();\n"),
+        # searchMergeModes: all candidates' predictions + SATDs in one hand-over, ahead of the loop
+        ("            populateMergeCandidates(h, pu);\n            for (int i = 0; i < h[MaxNumMergeCand()]; ++i)\n", REPLACE,
+         "            populateMergeCandidates(h, pu);\n            hvbhooks::prefetchMergeCosts(h, pu);\n            for (int i = 0; i < h[MaxNumMergeCand()]; ++i)\n"),
         # measurePuCost: the prediction + SATD block
         ("    int32_t satd[3];\n    {\n        StateReconstructedPicture<Sample> *stateReconstructedPicture = h;\n", REPLACE,
          "    int32_t satd[3];\n    if (!hvbhooks::puCost(h, pu, puData, satd))\n    {\n        StateReconstructedPicture<Sample> *stateReconstructedPicture = h;\n"),

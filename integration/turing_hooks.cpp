@@ -44,6 +44,12 @@ unsigned enabledMask()
     return value;
 }
 
+int intraMinLog2()
+{
+    static const int value = envInt("HVB_INTRA_MIN_LOG2", 2);
+    return value;
+}
+
 void fatal(const char *what, int rc)
 {
     // there is no CPU fallback behind a failed device call: a wrong bitstream is worse than none

@@ -222,6 +222,32 @@ template <class H> bool puCost(H &h, const prediction_unit &pu, const PuData &pu
 }
 
 
+// searchMergeModes (turing/Search.hpp:1761-1768) measures the candidates one after the other; their predictions and SATDs
+// do not depend on each other, so all of them go to the device in one hand-over, ahead of the loop; the loop's
+// measurePuCost calls find their distortion in the memo.
+template <class H> void prefetchMergeCosts(H &h, const prediction_unit &pu)
+{
+    if (!usable(h) || !(enabledMask() & 4) || h[weightedPredFlag()]) return;
+    Mvp::Predictors *predictors = h;
+    Memo &m = memo();
+    m.nPu = 0;
+    hvb_pu_cost_task tasks[Memo::kPu];
+    int n = 0;
+    for (int i = 0; i < h[MaxNumMergeCand()] && n < Memo::kPu; ++i)
+    {
+        hvb_pu_cost_task t;
+        if (!fillPuCostTask(h, pu, predictors->merge[i], t)) continue;
+        bool seen = false; // candidates may coincide
+        for (int k = 0; k < n; ++k) seen |= !memcmp(&tasks[k], &t, sizeof(t));
+        if (!seen) tasks[n++] = t;
+    }
+    if (n < 2) return; // a single candidate gains nothing from going early
+    const int rc = hvbenc_pu_cost(sessionOf(h), tasks, n, &m.puResult[0][0]);
+    if (rc) fatal("hvbenc_pu_cost(merge candidates)", rc);
+    memcpy(m.puTask, tasks, sizeof(hvb_pu_cost_task) * n);
+    m.nPu = n;
+}
+
 // the 35-mode SATD sweep of searchIntraPartition (turing/Search.hpp:113-142 -> predictIntraLuma, turing/Reconstruct.cpp:630-712)
 // for a partition of 4x4 .. 32x32: the reference samples have been substituted by the caller (:54-61); the filtered
 // array is derived on the device (turing/IntraReferenceSamples.h:373-419).  Leaves what the loop's last iteration leaves
@@ -232,7 +258,7 @@ template <class H> bool intraSweep(H &h, IntraPartition const &intraPartition, i
     typedef typename SampleOf<H>::Type Sample;
     StateEncodeSubstream<Sample> *stateEncodeSubstream = h;
     const int log2n = intraPartition.log2CbSize - intraPartition.split;
-    if (log2n < 2 || log2n > 5) return false;
+    if (log2n < intraMinLog2() || log2n > 5) return false;
     hvb_intra_sweep_task t;
     memset(&t, 0, sizeof(t));
     t.src.pic = (int16_t)inputPicture(h);

@@ -12,6 +12,7 @@ bool on();                                                        // HVB_BATCHED
 hvbenc *session(int bytesPerSample, int bitDepth, int width, int height); // created on first use
 int pictureId(const void *key, bool fresh);
 void fatal(const char *what, int rc);
+int intraMinLog2();                                              // HVB_INTRA_MIN_LOG2 (default 2): smallest partition whose sweep goes to the device
 unsigned enabledMask();                                           // HVB_HOOKS: bit 0 me, 1 bi, 2 pu cost, 3 intra, 4 tu
 
 struct Memo // per-thread results of tasks issued ahead of the reference's control flow

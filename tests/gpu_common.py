@@ -41,3 +41,8 @@ class Scene:
 
 def block(t, name, pic, c_idx, x, y):
     t[name]["pic"], t[name]["cIdx"], t[name]["x"], t[name]["y"] = pic, c_idx, x, y
+
+
+# the unmodified reference encoder built by oracle/Makefile `encoder` (test infrastructure)
+from pathlib import Path as _Path
+REFERENCE_ENCODER = _Path(__file__).resolve().parent.parent / "oracle" / "_ref" / "turing_ref"

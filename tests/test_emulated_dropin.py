@@ -18,7 +18,7 @@ import test_gpu_dropin as dropin
 @pytest.fixture(scope="module")
 def cpu_libhvb(tmp_path_factory):
     d = tmp_path_factory.mktemp("libhvb_cpu")
-    files = tuple(sorted(p.name for p in host_build.CSRC.glob("*.cu")))
+    files = tuple(sorted(p.name for p in host_build.CSRC.glob("*.cu") if not p.name.endswith("_tma.cu")))  # (TMA has no host emulation)
     host_build.build(d, files, cpp_files=("havoc_b200.cpp",), soname="libhvb.so")
     return d
 

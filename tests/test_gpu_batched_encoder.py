@@ -29,11 +29,12 @@ CASES = [
 
 @pytest.mark.parametrize("tag,width,height,frames,bit_depth,options", CASES, ids=[c[0] for c in CASES])
 def test_batched_encoder_matches_reference_asm0(tmp_path, tag, width, height, frames, bit_depth, options):
+    import gpu_common
     from turingcodec_b200 import encoder
-    if not (encoder.REFERENCE.exists() and encoder.BATCHED.exists()):
+    if not (gpu_common.REFERENCE_ENCODER.exists() and encoder.BATCHED.exists()):
         pytest.skip("turing_ref / turing_b200_batched not built (make -C oracle encoder && make -C integration; needs /root/reference)")
     clip = encoder.write_clip(tmp_path / "clip.yuv", width, height, frames, bit_depth)
-    want = encoder.encode(encoder.REFERENCE, clip, width, height, frames, ["--asm", "0", *options], tmp_path, "ref", frame_rate=24)
+    want = encoder.encode(gpu_common.REFERENCE_ENCODER, clip, width, height, frames, ["--asm", "0", *options], tmp_path, "ref", frame_rate=24)
     got = encoder.encode(encoder.BATCHED, clip, width, height, frames, options, tmp_path, "batched", threads=48, frame_rate=24)
     assert want["bitstream_bytes"] > 100
     assert (got["bitstream_md5"], got["reconstruction_md5"]) == (want["bitstream_md5"], want["reconstruction_md5"]), (tag, got, want)

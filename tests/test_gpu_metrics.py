@@ -116,6 +116,38 @@ def test_sad4(setup, oracle):
         assert list(got[i]) == oracle.sad4(a, oa, sa, b, offs, b.shape[1], w, h), (i, w, h)
 
 
+def test_sad_and_sad4_staged_by_tma(setup):
+    """hvb_set_tma: the same batches with the blocks staged by cp.async.bulk.tensor (csrc/hvb_metrics_tma.cu) -- every PU
+    size, luma and chroma, vectors into the padding, both sample widths -- equal the load/store kernels' results, which the
+    tests above check against the oracle."""
+    ctx, pics, host, bps = setup
+    rng = np.random.default_rng(15)
+    n = 400
+    t4 = np.zeros(n, hvb.sad4_task_t)
+    for i in range(n):
+        w, h = PU_SIZES[i % len(PU_SIZES)]
+        t4[i]["w"], t4[i]["h"] = w, h
+        t4[i]["src"]["pic"] = 0
+        t4[i]["src"]["x"] = rng.integers(0, (W - w) // 4 + 1) * 4
+        t4[i]["src"]["y"] = rng.integers(0, H - h + 1)
+        t4[i]["ref_pic"] = 1
+        t4[i]["rx"] = rng.integers(-PAD + 1, W + PAD - w - 1, 4)
+        t4[i]["ry"] = rng.integers(-PAD + 1, H + PAD - h - 1, 4)
+    singles = [make_tasks(rng, 600), make_tasks(rng, 300, True)]
+    singles[0]["b"]["x"][:40] = -PAD + 1  # into the padding
+    want4, want = ctx.sad4(t4), [ctx.sad(t) for t in singles]
+    ctx.set_tma(True)
+    try:
+        before = ctx.launch_count
+        got4, got = ctx.sad4(t4), [ctx.sad(t) for t in singles]
+        assert ctx.launch_count == before + 3
+    finally:
+        ctx.set_tma(False)
+    assert np.array_equal(got4, want4)
+    for g, w_ in zip(got, want):
+        assert np.array_equal(g, w_)
+
+
 def test_device_memory_path_and_launch_count(setup, oracle):
     """HVB_DEVICE: tasks and results live in torch tensors; the call only enqueues work."""
     import torch

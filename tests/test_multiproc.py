@@ -71,10 +71,12 @@ def _encode_worker(rank, world, port, clip, width, height, frames, seg, work):
     import subprocess
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from turingcodec_b200 import encoder, sharding
+    sys.path.insert(0, str(ROOT / "tests"))
+    import gpu_common
+    from turingcodec_b200 import sharding
     for k, rng in zip(sharding.segments_for_rank((frames + seg - 1) // seg, rank, world), sharding.frames_for_rank(frames, seg, rank, world)):
         # what integration/segments_main.cpp hands each encoder instance, with the reference encoder standing in on the CPU
-        cmd = [str(encoder.REFERENCE), "encode", "--input-res", f"{width}x{height}", "--frame-rate", "30", "--speed", "fast", "--threads", "2",
+        cmd = [str(gpu_common.REFERENCE_ENCODER), "encode", "--input-res", f"{width}x{height}", "--frame-rate", "30", "--speed", "fast", "--threads", "2",
                "--segment", str(seg), "--seek", str(rng.start), "--frames", str(len(rng)), "-o", f"{work}/out.seg{k}", clip]
         subprocess.run(cmd, check=True, capture_output=True)
     dist.barrier()
@@ -89,12 +91,14 @@ def test_two_ranks_reassemble_the_reference_segment_stream(tmp_path):
     import subprocess
 
     import pytest
+
+    import gpu_common
     from turingcodec_b200 import encoder
-    if not encoder.REFERENCE.exists():
+    if not gpu_common.REFERENCE_ENCODER.exists():
         pytest.skip("oracle/_ref/turing_ref not built")
     width, height, frames, seg = 64, 64, 11, 4
     clip = encoder.write_clip(tmp_path / "clip.yuv", width, height, frames)
-    subprocess.run([str(encoder.REFERENCE), "encode", "--input-res", f"{width}x{height}", "--frame-rate", "30", "--speed", "fast", "--threads", "2",
+    subprocess.run([str(gpu_common.REFERENCE_ENCODER), "encode", "--input-res", f"{width}x{height}", "--frame-rate", "30", "--speed", "fast", "--threads", "2",
                     "--segment", str(seg), "--frames", str(frames), "-o", str(tmp_path / "whole.bit"), str(clip)], check=True, capture_output=True)
     ctx = mp.get_context("spawn")
     port = _free_port()

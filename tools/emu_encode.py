@@ -17,7 +17,7 @@ LIBDIR = ROOT / "gpurun_out" / "emu_lib"
 def build_lib():
     import host_build
     LIBDIR.mkdir(parents=True, exist_ok=True)
-    files = tuple(sorted(p.name for p in host_build.CSRC.glob("*.cu")))
+    files = tuple(sorted(p.name for p in host_build.CSRC.glob("*.cu") if not p.name.endswith("_tma.cu")))  # (TMA has no host emulation)
     host_build.build(LIBDIR, files, cpp_files=("havoc_b200.cpp", "hvb_encoder.cpp"), soname="libhvb.so")
 
 

@@ -10,6 +10,8 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from turingcodec_b200 import encoder  # noqa: E402
 
+REFERENCE_ENCODER = ROOT / "oracle" / "_ref" / "turing_ref"
+
 p = argparse.ArgumentParser()
 p.add_argument("res")
 p.add_argument("frames", type=int)
@@ -28,10 +30,10 @@ with tempfile.TemporaryDirectory(dir="/dev/shm" if Path("/dev/shm").exists() els
     clip = encoder.write_clip(tmp / "clip.yuv", w, h, a.frames, a.bit_depth)
     runs = {}
     if not a.no_asm1:
-        runs["ref_asm1"] = encoder.encode(encoder.REFERENCE, clip, w, h, a.frames, ["--asm", "1", *opts], tmp, "ref1")
+        runs["ref_asm1"] = encoder.encode(REFERENCE_ENCODER, clip, w, h, a.frames, ["--asm", "1", *opts], tmp, "ref1")
         print(json.dumps({"run": "ref_asm1", **runs["ref_asm1"]}), flush=True)
     if not a.no_asm0:
-        runs["ref_asm0"] = encoder.encode(encoder.REFERENCE, clip, w, h, a.frames, ["--asm", "0", *opts], tmp, "ref0")
+        runs["ref_asm0"] = encoder.encode(REFERENCE_ENCODER, clip, w, h, a.frames, ["--asm", "0", *opts], tmp, "ref0")
         print(json.dumps({"run": "ref_asm0", **runs["ref_asm0"]}), flush=True)
     env = dict(kv.split("=", 1) for kv in a.env.split(",") if kv)
     for t in [t for t in a.threads.split(",") if t and not a.segments]:

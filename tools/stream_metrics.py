@@ -23,7 +23,7 @@ def peak_gbs():
 
 
 def measure(device=0, blocks=(64, 32, 16, 8), bps_list=(1, 2), layouts=("colocated", "unaligned"), reps=5, side=16384,
-            target_candidates=1 << 20, kinds=("sad", "sad4", "ssd", "satd"), log=None):
+            target_candidates=1 << 20, kinds=("sad", "sad4", "ssd", "satd"), log=None, tma=False):
     import torch
     from turingcodec_b200 import hvb
     peak, peak_src = peak_gbs()
@@ -32,6 +32,7 @@ def measure(device=0, blocks=(64, 32, 16, 8), bps_list=(1, 2), layouts=("colocat
         ctx = hvb.Context(device, bps, 8 if bps == 1 else 10)
         stream = torch.cuda.Stream(device)
         ctx.set_stream(stream.cuda_stream)
+        ctx.set_tma(tma)  # SAD / SAD4 staged by cp.async.bulk.tensor (csrc/hvb_metrics_tma.cu)
         # five luma-only-sized pictures (source + four references); content is irrelevant to bandwidth
         pics = [ctx.picture_create(side, side, 0) for _ in range(5)]
         rng = np.random.default_rng(0)
@@ -84,7 +85,7 @@ def measure(device=0, blocks=(64, 32, 16, 8), bps_list=(1, 2), layouts=("colocat
                     torch.cuda.synchronize(device)
                     ms = e0.elapsed_time(e1) / reps
                     gbs = per * cnt / ms / 1e6
-                    r = {"kernel": kind, "block": n, "bytes_per_sample": bps, "layout": layout, "candidates": int(cnt), "ms": round(ms, 4),
+                    r = {"kernel": kind + ("(tma)" if tma and kind in ("sad", "sad4") else ""), "block": n, "bytes_per_sample": bps, "layout": layout, "candidates": int(cnt), "ms": round(ms, 4),
                          "GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
                     results.append(r)
                     if log:
@@ -104,8 +105,9 @@ if __name__ == "__main__":
     p.add_argument("--kinds", default="sad,sad4,ssd,satd")
     p.add_argument("--reps", type=int, default=5)
     p.add_argument("--json", default=None)
+    p.add_argument("--tma", action="store_true")
     a = p.parse_args()
     res = measure(0, [int(v) for v in a.block.split(",")], [int(v) for v in a.bps.split(",")], a.layouts.split(","), a.reps,
-                  kinds=a.kinds.split(","), log=lambda r: print(json.dumps(r), flush=True))
+                  kinds=a.kinds.split(","), log=lambda r: print(json.dumps(r), flush=True), tma=a.tma)
     if a.json:
         Path(a.json).write_text(json.dumps(res, indent=1) + "\n")

@@ -6,6 +6,7 @@
 // (turing/StatePictures.h:154-156, Padding.h) living in HBM.
 #include "hvb_internal.cuh"
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -84,6 +85,7 @@ extern "C" int hvb_create(int device, int bytes_per_sample, int bit_depth, hvb_c
         return HVB_ERR_CUDA;
     }
     ctx->smCount = sms;
+    ctx->useTma = hvbEnvTma();
     ctx->stream = ctx->ownStream;
     *out = ctx;
     return HVB_OK;
@@ -102,6 +104,7 @@ extern "C" void hvb_destroy(hvb_context *ctx)
         if (p.saoInfo) cudaFree(p.saoInfo);
     }
     if (ctx->dPlanes) cudaFree(ctx->dPlanes);
+    if (ctx->dTensorMaps) cudaFree(ctx->dTensorMaps);
     if (ctx->dLoopInfo) cudaFree(ctx->dLoopInfo);
     if (ctx->workCursors) cudaFree(ctx->workCursors);
     for (auto &slot : ctx->slots)
@@ -162,6 +165,13 @@ extern "C" int hvb_elapsed_ms(hvb_context *ctx, int from, int to, float *ms)
     return hvbCuda(ctx, cudaEventElapsedTime(ms, ctx->marks[from], ctx->marks[to]), "hvb_elapsed_ms");
 }
 
+extern "C" int hvb_set_tma(hvb_context *ctx, int on)
+{
+    if (!ctx) return HVB_ERR_INVALID;
+    ctx->useTma = on != 0;
+    return HVB_OK;
+}
+
 extern "C" int hvb_poll(hvb_context *ctx)
 {
     if (!ctx) return HVB_ERR_INVALID;
@@ -212,6 +222,15 @@ int hvbUpload(hvb_context *ctx, void *dev, size_t devPitch, const void *host, si
     cudaError_t e = cudaMemcpy2DAsync(dev, devPitch, host, hostPitch, widthBytes, rows, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // the host buffer may be pageable
     return hvbCuda(ctx, e, what);
+}
+
+bool hvbEnvTma()
+{
+    static const bool value = [] {
+        const char *v = getenv("HVB_TMA");
+        return v && *v && *v != '0';
+    }();
+    return value;
 }
 
 extern "C" int64_t hvb_launch_count(hvb_context *ctx) { return ctx ? ctx->launches : 0; }
@@ -277,10 +296,13 @@ extern "C" int hvb_picture_create(hvb_context *ctx, int width, int height, int p
         p.plane[c].width = w;
         p.plane[c].height = h;
         p.plane[c].pad = pd;
-        p.plane[c].reserved = 0;
+        p.plane[c].reserved = (int32_t)padLeft; // sample (-pd) of a row starts padLeft - pd samples into it; (padLeft + x) indexes the row
+        p.tmaBase[c] = p.alloc[c];
+        p.tmaRows[c] = (int)rows;
     }
     p.live = true;
     ctx->planesDirty = true;
+    ctx->tensorMapsDirty = true;
     *pic = id;
     return HVB_OK;
 }
@@ -331,6 +353,7 @@ extern "C" int hvb_picture_import(hvb_context *ctx, hvb_context *owner, int owne
     p.lfInfo = p.saoInfo = nullptr;
     p.lfBytes = p.saoBytes = 0;
     ctx->planesDirty = true;
+    ctx->tensorMapsDirty = true;
     *pic = id;
     return HVB_OK;
 }

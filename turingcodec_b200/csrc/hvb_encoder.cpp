@@ -194,6 +194,7 @@ struct hvbenc
 
     // One completion thread for all engines: it polls the contexts that have a batch in flight (hvb_poll) and wakes the
     // engine whose batch has finished, so that no dispatcher parks a core inside the driver's stream wait.
+    bool usePoller = true;
     std::thread poller;
     std::mutex pollM;
     std::condition_variable pollCv;
@@ -265,7 +266,13 @@ int runBatch(Engine *enc, int b)
     if (levelCount) rc = hvb_coeff_download(ctx, enc->levelsHost, levelCount, 0);
     if (rc) return rc;
     if (prof) hvb_mark(ctx, 6);
-    // one wait for the whole batch, on the session's completion thread
+    // one wait for the whole batch: on the session's completion thread, or (HVB_POLLER=0) inside the driver
+    if (!enc->session->usePoller)
+    {
+        rc = hvb_sync(ctx);
+        if (rc) return rc;
+    }
+    else
     {
         hvbenc *session = enc->session;
         {
@@ -586,6 +593,7 @@ extern "C" int hvbenc_create(int device, int bytes_per_sample, int bit_depth, in
         hvbenc_destroy(enc);
         return rc;
     }
+    if (const char *v = getenv("HVB_POLLER")) enc->usePoller = atoi(v) != 0;
     enc->poller = std::thread(pollLoop, enc);
     for (Engine *engine : enc->engines)
     {

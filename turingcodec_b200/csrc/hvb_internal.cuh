@@ -19,7 +19,7 @@ struct HvbPlane
     int32_t stride; // in samples
     int32_t width, height;
     int32_t pad;
-    int32_t reserved;
+    int32_t reserved; // column of sample 0 in an allocated row: sample (x, y) sits at column reserved + x of row pad + y (tensor-map coordinates)
 };
 
 static const int HVB_MAX_PICTURES = 1024;
@@ -31,6 +31,8 @@ struct HvbPicture
     void *alloc[3] = {nullptr, nullptr, nullptr};
     size_t allocBytes[3] = {0, 0, 0};
     HvbPlane plane[3];
+    void *tmaBase[3] = {nullptr, nullptr, nullptr}; // start of each plane's device allocation and its rows (tensor maps span the
+    int tmaRows[3] = {0, 0, 0};                     // whole allocation, padding included); kept by imports, null for wrapped pictures
     void *lfInfo = nullptr; // deblocking side information (hvb_deblock_info_upload): block records, then CTU records
     size_t lfBytes = 0;
     void *saoInfo = nullptr; // SAO records per CTU (hvb_sao_info_upload)
@@ -61,6 +63,9 @@ struct hvb_context
     HvbPicture pictures[HVB_MAX_PICTURES];
     HvbPlane *dPlanes = nullptr; // [HVB_MAX_PICTURES*3] mirrored on device
     bool planesDirty = true;
+    void *dTensorMaps = nullptr; // [HVB_MAX_PICTURES * 3 * 3] CUtensorMap (hvb_metrics_tma.cu), built on first use
+    bool tensorMapsDirty = true;
+    bool useTma = false; // hvb_set_tma
     HvbLoopInfo *dLoopInfo = nullptr; // [HVB_MAX_PICTURES] on the device, allocated by the first hvb_deblock_info_upload
     HvbLoopInfo loopInfoHost[HVB_MAX_PICTURES] = {};
     int *workCursors = nullptr; // [64] device-side task cursors of the persistent kernels (zeroed on the stream before each use)
@@ -103,6 +108,8 @@ struct hvb_context
 int hvbFail(hvb_context *ctx, int status, const char *what);
 int hvbCuda(hvb_context *ctx, cudaError_t e, const char *what);
 int hvbSyncPlanes(hvb_context *ctx);
+int hvbLaunchSadTma(hvb_context *ctx, const void *dTasks, int n, int32_t *dOut, int nref); // hvb_metrics_tma.cu
+bool hvbEnvTma();                                                                          // HVB_TMA=1 in the environment: default of hvb_set_tma
 int hvbEnsureScratch(hvb_context *ctx, size_t bytes);
 int hvbEnsureCoeffPool(hvb_context *ctx, size_t count);
 int hvbEnsureSamplePool(hvb_context *ctx, size_t count);

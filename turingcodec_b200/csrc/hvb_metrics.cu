@@ -542,6 +542,14 @@ extern "C" int hvb_sad_batch(hvb_context *ctx, const hvb_metric_task *tasks, int
     HvbStaged st;
     int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(int32_t) * n, mem, &st);
     if (rc) return rc;
+#ifdef __CUDACC__
+    if (ctx->useTma) // blocks staged by the TMA (hvb_metrics_tma.cu); an experiment until it wins everywhere: HVB_TMA=1
+    {
+        rc = hvbLaunchSadTma(ctx, st.dTasks, n, static_cast<int32_t *>(st.dOut), 1);
+        if (rc) return rc;
+        return hvbStageOut(ctx, out, sizeof(int32_t) * n, mem, st);
+    }
+#endif
     HVB_DISPATCH_SAMPLE(ctx, sadKernel, gridFor<hvb_metric_task>(ctx, n), ctx->dPlanes,
                         static_cast<const hvb_metric_task *>(st.dTasks), n, static_cast<int32_t *>(st.dOut));
     HVB_LAUNCH_CHECK(ctx, "sadKernel");
@@ -556,6 +564,14 @@ extern "C" int hvb_sad4_batch(hvb_context *ctx, const hvb_sad4_task *tasks, int 
     HvbStaged st;
     int rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(int32_t) * 4 * n, mem, &st);
     if (rc) return rc;
+#ifdef __CUDACC__
+    if (ctx->useTma)
+    {
+        rc = hvbLaunchSadTma(ctx, st.dTasks, n, static_cast<int32_t *>(st.dOut), 4);
+        if (rc) return rc;
+        return hvbStageOut(ctx, out, sizeof(int32_t) * 4 * n, mem, st);
+    }
+#endif
     HVB_DISPATCH_SAMPLE(ctx, sad4Kernel, gridFor<hvb_sad4_task>(ctx, n), ctx->dPlanes,
                         static_cast<const hvb_sad4_task *>(st.dTasks), n, static_cast<int32_t *>(st.dOut));
     HVB_LAUNCH_CHECK(ctx, "sad4Kernel");

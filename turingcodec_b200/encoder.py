@@ -1,7 +1,8 @@
-"""Driving the encoders: the reference (oracle/_ref/turing_ref, built unmodified by oracle/Makefile) and the batched B200
-build of it (integration/_build/turing_b200_batched: the same encoder with its hot loops on libhvb.so, integration/).
+"""Driving the batched B200 build of the reference encoder (integration/_build/turing_b200_batched: the reference's encoder
+with its hot loops on libhvb.so, and turing_b200_segments, its IDR-segment-parallel driver; integration/) -- and, for the
+callers that compare with it, any other `turing` binary handed in (tests and bench.py pass the unmodified reference build).
 
-Both take the reference's own command line (turing/encode.cpp:61-234); this module writes the synthetic clips of SURVEY.md
+All take the reference's own command line (turing/encode.cpp:61-234); this module writes the synthetic clips of SURVEY.md
 section 8(d), runs `turing encode`, and reports what the reference's golden-hash test reports (turing/signature.cpp:103-190):
 md5 of the bitstream and of the reconstruction -- plus wall-clock frames per second and the submission queue's counters.
 Used by bench.py, tests/test_gpu_batched_encoder.py and tools/."""
@@ -20,7 +21,6 @@ import numpy as np
 from . import synth
 
 ROOT = Path(__file__).resolve().parent.parent
-REFERENCE = ROOT / "oracle" / "_ref" / "turing_ref"
 BATCHED = ROOT / "integration" / "_build" / "turing_b200_batched"
 SEGMENTS = ROOT / "integration" / "_build" / "turing_b200_segments"
 LIB_DIR = ROOT / "turingcodec_b200" / "csrc"

@@ -210,6 +210,9 @@ class Context:
     def sync(self):
         self._check(self.lib.hvb_sync(self.h), "hvb_sync")
 
+    def set_tma(self, on: bool):
+        self._check(self.lib.hvb_set_tma(self.h, 1 if on else 0), "hvb_set_tma")
+
     def set_pipelined(self, on: bool):
         """HOST calls on page-locked arrays only enqueue (copies overlap the kernels); results are valid after sync()."""
         self._check(self.lib.hvb_set_pipelined(self.h, int(bool(on))), "hvb_set_pipelined")
