@@ -527,7 +527,7 @@ typedef struct
 int hvb_coded_residual_batch(hvb_context *ctx, const hvb_coded_residual_task *tasks, int n, int32_t recordsBase, int32_t capacityWords,
                              hvb_coded_residual *out /* [n + 1] */, hvb_mem mem);
 
-/* ---- pre-analysis (first GPU verification pending) ---- */
+/* ---- pre-analysis ---- */
 
 /* EstimateIntraComplexity::preAnalysis (turing/EstimateIntraComplexity.h:159-176) over a region of a source picture's
  * luma plane: for each 8x8 block of the wBlocks x hBlocks blocks starting at (x0, y0) (multiples of 8), computeSatd8x8
@@ -541,6 +541,43 @@ typedef struct
     int32_t out;
 } hvb_intra_complexity_task; /* 16 bytes */
 int hvb_intra_complexity_batch(hvb_context *ctx, const hvb_intra_complexity_task *tasks, int n, int32_t *out, int outCount, hvb_mem mem);
+
+/* AdaptiveQuantisation::preAnalysis (turing/AdaptiveQuantisation.h:172-246), one layer per task: the luma plane of a source
+ * picture is cut into `unit` x `unit` squares (unit = maxCuSize >> depth, a power of two, 4..64; the last row / column of
+ * units is clipped to the picture), each unit into four quadrants at (w >> 1, h >> 1), and for each quadrant
+ * variance = sumSquare / N - (sum / N)^2 in INTEGER quotients with N = (w * h) >> 2 -- with the reference's two quirks kept:
+ * quadrant 0's "sum of squares" is the square of its last sample only (:197) and quadrant 1's is its plain sum (:208).
+ * out[task.out + row * unitsPerRow + col] = the minimum of the four (an integer; the reference holds it in a double);
+ * the unit's activity is 1.0 + that (:239), the layer's average activity the truncated mean of the activities (:244-245),
+ * which the caller forms (integer-valued doubles: any order gives the same sum).  getAqOffset (:147-169) stays with the caller. */
+typedef struct
+{
+    int16_t pic, unit;
+    int32_t out;
+} hvb_aq_layer_task; /* 8 bytes */
+int hvb_aq_activity_batch(hvb_context *ctx, const hvb_aq_layer_task *tasks, int n, int64_t *out, int outCount, hvb_mem mem);
+
+/* ShotChangeDetection::processSeq's per-picture pixel pass (turing/SCDetection.h:237-262, :299-304, :402-407): the 64-bin
+ * histogram of the luma plane, sample -> (unsigned char)(sample >> 2) for 16-bit samples (:244, :284), then >> SHIFT_DOWN (2).
+ * out[64 * i + bin] for picture pics[i].  Black / white / fade tests and the histogram differences stay with the caller. */
+int hvb_scd_histogram_batch(hvb_context *ctx, const int16_t *pics, int n, int32_t *out /* [64 n] */, hvb_mem mem);
+
+/* ShotChangeDetection::getLikelihood's block statistics (turing/SCDetection.h:71-147): the picture's luma plane, reduced to
+ * 8 bits as above and taken as the reference's packed width x height byte vector, is cut into blocks of (width >> 3) x
+ * (height >> 3); for the blocks at j = margin * bh, (margin + 1) * bh, .. < height - margin * bh (rows) and likewise i over
+ * the columns, avg = sum / (bh * bw) and var = (sum over the block in raster order of (elem - avg)^2) / (bh * bw), IEEE
+ * doubles, each operation rounded once, additions in the reference's order.  The reference addresses element (h, w) of a
+ * block as block + h * HEIGHT + w (:87, :103 -- the picture's height where the row pitch was meant); that addressing is
+ * kept, so a "block" is a sheared set of samples, and a picture for which it would leave the plane is refused
+ * (HVB_ERR_INVALID; the reference reads past its vector there).  margin 1: the previous picture's 6 x 6 grid, margin 2:
+ * the current picture's 4 x 4.  out[task.out + 2 k] = avg, out[task.out + 2 k + 1] = var of block k (raster
+ * order).  calc_likelihood and the 3 x 3 neighbourhood minimum (:40-47, :149-176) stay with the caller. */
+typedef struct
+{
+    int16_t pic, margin;
+    int32_t out; /* index of the task's first double in `out` */
+} hvb_scd_stats_task; /* 8 bytes */
+int hvb_scd_block_stats_batch(hvb_context *ctx, const hvb_scd_stats_task *tasks, int n, double *out, int outCount, hvb_mem mem);
 
 #ifdef __cplusplus
 }

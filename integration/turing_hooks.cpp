@@ -50,6 +50,24 @@ int intraMinLog2()
     return value;
 }
 
+int meMinArea()
+{
+    static const int value = envInt("HVB_ME_MIN_AREA", 0);
+    return value;
+}
+
+int puMinArea()
+{
+    static const int value = envInt("HVB_PU_MIN_AREA", 0);
+    return value;
+}
+
+int tuMinLog2()
+{
+    static const int value = envInt("HVB_TU_MIN_LOG2", 0);
+    return value;
+}
+
 void fatal(const char *what, int rc)
 {
     // there is no CPU fallback behind a failed device call: a wrong bitstream is worse than none

@@ -117,6 +117,10 @@ inline bool meLookup(const hvb_me_task &t, hvb_me_result &r)
 template <class H> bool searchMotionUni(H &h, int refList)
 {
     if (!usable(h) || !(enabledMask() & 1)) return false;
+    {
+        prediction_unit const *pu = h;
+        if (pu->nPbW * pu->nPbH < meMinArea()) return false;
+    }
     StateCodedData *stateCodedData = h;
     auto *substream = &h[Concrete<StateSubstream>()];
     hvb_me_task t;
@@ -144,6 +148,7 @@ template <class H> bool searchMotionBi(H &h, int refList)
     Speed *speed = h;
     StateCodedData *stateCodedData = h;
     prediction_unit const *pu = h;
+    if (pu->nPbW * pu->nPbH < meMinArea()) return false;
     Mvp::Predictors *predictors = h;
     PuData puData;
     setPuDataMvpPredFlags(puData, h, true, true);
@@ -213,6 +218,7 @@ inline bool puLookup(const hvb_pu_cost_task &t, int32_t satd[3])
 template <class H> bool puCost(H &h, const prediction_unit &pu, const PuData &puData, int32_t satd[3])
 {
     if (!usable(h) || !(enabledMask() & 4) || h[weightedPredFlag()]) return false;
+    if (pu.nPbW * pu.nPbH < puMinArea()) return false;
     hvb_pu_cost_task t;
     if (!fillPuCostTask(h, pu, puData, t)) return false;
     if (puLookup(t, satd)) return true;
@@ -228,6 +234,7 @@ template <class H> bool puCost(H &h, const prediction_unit &pu, const PuData &pu
 template <class H> void prefetchMergeCosts(H &h, const prediction_unit &pu)
 {
     if (!usable(h) || !(enabledMask() & 4) || h[weightedPredFlag()]) return;
+    if (pu.nPbW * pu.nPbH < puMinArea()) return;
     Mvp::Predictors *predictors = h;
     Memo &m = memo();
     m.nPu = 0;
@@ -375,6 +382,7 @@ template <class H> const TuBlock *interBlock(H &h, residual_coding const &rc)
 {
     if (!usable(h) || !(enabledMask() & 16)) return nullptr;
     TuMemo &m = tuMemo();
+    if (!m.active) return nullptr;
     for (int pass = 0; pass < 2; ++pass)
     {
         for (int i = 0; i < m.n; ++i)
@@ -391,7 +399,7 @@ template <class H> const TuBlock *interBlock(H &h, residual_coding const &rc)
 }
 
 // reconstructInter (turing/Reconstruct.cpp:1237-...), before the tree walk: forget the previous CU's blocks
-inline void beginInterCu() { tuMemo().n = 0; }
+inline void beginInterCu() { tuMemo().n = 0, tuMemo().active = false; }
 
 
 // ReconstructInter<transform_tree>::go at the root of a CU's transform tree (turing/Reconstruct.cpp:58-96), split flag
@@ -405,6 +413,8 @@ template <class H> void prefetchInterCu(H &h, transform_tree const &tt, bool spl
     typedef typename SampleOf<H>::Type Sample;
     Candidate<Sample> *candidate = h;
     if (candidate->noresidual) return;
+    if (tt.log2TrafoSize < tuMinLog2()) return;
+    tuMemo().active = true;
     int blocks[TuMemo::kBlocks][4];
     int n = 0;
     const int log2n = tt.log2TrafoSize;

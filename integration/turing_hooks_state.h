@@ -14,6 +14,11 @@ int pictureId(const void *key, bool fresh);
 void fatal(const char *what, int rc);
 int intraMinLog2();                                              // HVB_INTRA_MIN_LOG2 (default 2): smallest partition whose sweep goes to the device
 unsigned enabledMask();                                           // HVB_HOOKS: bit 0 me, 1 bi, 2 pu cost, 3 intra, 4 tu
+// Size thresholds: a block below them stays with the reference's own body (its CPU havoc tables), because a hand-over costs
+// more host time than the block's arithmetic does there; results are bit-exact either way, so the bitstream cannot tell.
+int meMinArea();                                                 // HVB_ME_MIN_AREA: smallest PU (w*h) whose uni / bi search goes to the device
+int puMinArea();                                                 // HVB_PU_MIN_AREA: smallest PU (w*h) whose prediction + SATD goes to the device
+int tuMinLog2();                                                 // HVB_TU_MIN_LOG2: smallest inter CU (log2 of the transform tree's root) whose blocks go to the device
 
 struct Memo // per-thread results of tasks issued ahead of the reference's control flow
 {
@@ -41,6 +46,7 @@ struct TuMemo // per-thread: the blocks of the CU being reconstructed, issued to
     static const int kBlocks = 24;
     TuBlock block[kBlocks];
     int n;
+    bool active; // the CU being reconstructed has its blocks on the device
 };
 TuMemo &tuMemo();
 

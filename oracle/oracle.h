@@ -281,6 +281,13 @@ int orc_intra_complexity_8x8(const void *p, intptr_t stride, int bps);
 /* turing/EstimateIntraComplexity.h:159-176 (preAnalysis): the same for every whole 8x8 block of a plane, raster order;
  * returns the sum.  Pinned: tests/test_oracle_pin_preanalysis.py. */
 int orc_intra_complexity(const void *plane, intptr_t stride, int width, int height, int bps, int32_t *out);
+/* turing/AdaptiveQuantisation.h:172-246 (preAnalysis), one layer: per unit the smallest quadrant variance (activity - 1);
+ * returns the layer's truncated average activity. */
+int orc_aq_layer(const void *plane, intptr_t stride, int width, int height, int bps, int unit, int64_t *out);
+/* turing/SCDetection.h:237-262: 64-bin luma histogram; :71-147: block statistics of getLikelihood; :40-47,:149-178: the ratio. */
+void orc_scd_histogram(const void *plane, intptr_t stride, int width, int height, int bps, int32_t *hist);
+int orc_scd_block_stats(const void *plane, intptr_t stride, int width, int height, int bps, int margin, double *out);
+double orc_scd_likelihood(const double *prev, const double *cur);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,7 @@ using std::min;
 static inline int hvbClip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 static inline void __syncthreads() {}
 static inline int atomicAdd(int *p, int v) { const int old = *p; *p += v; return old; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long old = *p; *p += v; return old; }
 static const uint3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0};
 static const dim3 blockDim(1), gridDim(1);
 '''

@@ -197,6 +197,7 @@ static inline unsigned __ballot_sync(unsigned mask, int pred)
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 static inline int atomicAdd(int *p, int v) { const int old = *p; *p += v; return old; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long old = *p; *p += v; return old; }
 
 // shared-memory addresses of the asynchronous-copy wrappers are offsets into the block's arena
 static inline size_t __cvta_generic_to_shared(const void *p) { return (size_t)(static_cast<const unsigned char *>(p) - emu::sharedArena); }

@@ -63,6 +63,13 @@ def test_intra_complexity(library, oracle, bps, bit_depth):
     pa.test_intra_complexity_matches_oracle(oracle, bps, bit_depth)
 
 
+@pytest.mark.parametrize("bps,bit_depth", [(1, 8), (2, 10)])
+def test_aq_activity_and_scd(library, oracle, bps, bit_depth):
+    import test_gpu_zz_preanalysis as pa
+    pa.test_aq_activity_and_scd_match_oracle(oracle, bps, bit_depth)
+    pa.test_scd_block_stats_refuses_what_the_reference_overreads(oracle)
+
+
 def test_call_order_errors(library):
     """the entry points refuse, with a message, what cannot work: SAO records before the deblocking records, batches before uploads"""
     import numpy as np

@@ -60,3 +60,87 @@ def test_intra_complexity_kernel_source_on_cpu_matches_oracle(emu, oracle, bps, 
         got = np.full(count, -1, np.int32)
         emu.emu_intra_complexity(table, C.c_void_p(tasks.ctypes.data), tasks.size, C.c_void_p(got.ctypes.data), bps)
         assert np.array_equal(got, expected(oracle, pic, tasks, count, bps))
+
+
+# ---- adaptive-quantisation activity and shot-change detection ------------------------------------------------------------
+
+ENTRY_AQ_SCD = r'''
+extern "C" void emu_aq_activity(const HvbPlane *planes, const hvb_aq_layer_task *tasks, int n, long long *out, int bps)
+{
+    if (bps == 1) aqActivityKernel<uint8_t>(planes, tasks, n, out);
+    else aqActivityKernel<uint16_t>(planes, tasks, n, out);
+}
+extern "C" void emu_scd_histogram(const HvbPlane *planes, const int16_t *pics, int n, int *out, int bps)
+{
+    if (bps == 1) scdHistogramKernel<uint8_t>(planes, pics, n, out);
+    else scdHistogramKernel<uint16_t>(planes, pics, n, out);
+}
+extern "C" void emu_scd_block_stats(const HvbPlane *planes, const hvb_scd_stats_task *tasks, int n, double *out, int bps)
+{
+    if (bps == 1) scdBlockStatsKernel<uint8_t>(planes, tasks, n, out);
+    else scdBlockStatsKernel<uint16_t>(planes, tasks, n, out);
+}
+'''
+
+
+@pytest.fixture(scope="module")
+def emu2(tmp_path_factory):
+    return host_emu.build(tmp_path_factory.mktemp("emu_preanalysis2"), "hvb_preanalysis.cu", ["HvbPlane"], ENTRY_AQ_SCD)
+
+
+def aq_tasks(pic, w, h):
+    """the four layers of a 64-sample CTU (turing/AdaptiveQuantisation.h:139-142), each with its own output range"""
+    tasks, at = [], 0
+    for depth in range(4):
+        unit = 64 >> depth
+        tasks.append((pic, unit, at))
+        at += -(-w // unit) * -(-h // unit)
+    return np.array(tasks, dtype=hvb.aq_layer_task_t), at
+
+
+def aq_expected(oracle, picture, tasks, count):
+    lib = pin.oracle_aq(oracle)
+    want = np.zeros(count, np.int64)
+    for t in tasks:
+        got, _ = pin.aq_layer(lib, picture, int(t["unit"]))
+        want[t["out"]:t["out"] + got.size] = got
+    return want
+
+
+def scd_expected(oracle, picture, margin):
+    lib = pin.oracle_aq(oracle)
+    h, w = picture.shape
+    out = np.zeros(2 * 64, np.float64)
+    n = lib.orc_scd_block_stats(picture.ctypes.data, w, w, h, picture.itemsize, margin, out.ctypes.data)
+    return out[:2 * n]
+
+
+def scd_histogram_expected(oracle, picture):
+    lib = pin.oracle_aq(oracle)
+    h, w = picture.shape
+    out = np.zeros(64, np.int32)
+    lib.orc_scd_histogram(picture.ctypes.data, w, w, h, picture.itemsize, out.ctypes.data)
+    return out
+
+
+@pytest.mark.parametrize("bps,bit_depth", [(1, 8), (2, 10)])
+def test_aq_and_scd_kernel_source_on_cpu_matches_oracle(emu2, oracle, bps, bit_depth):
+    rng = np.random.default_rng(180 + bit_depth)
+    for w, h in [(136, 112), (90, 70), (128, 72)]:
+        for pic in pin.pictures(rng, bps, bit_depth, w, h):
+            luma = aligned_copy(pic)
+            table = (Plane * 3)(Plane(luma.ctypes.data, luma.strides[0] // luma.itemsize, w, h, 0, 0))
+            tasks, count = aq_tasks(0, w, h)
+            got = np.full(count, -7, np.int64)
+            emu2.emu_aq_activity(table, C.c_void_p(tasks.ctypes.data), tasks.size, C.c_void_p(got.ctypes.data), bps)
+            assert np.array_equal(got, aq_expected(oracle, pic, tasks, count)), (w, h)
+            hist = np.zeros(64, np.int32)
+            pics = np.zeros(1, np.int16)
+            emu2.emu_scd_histogram(table, C.c_void_p(pics.ctypes.data), 1, C.c_void_p(hist.ctypes.data), bps)
+            assert np.array_equal(hist, scd_histogram_expected(oracle, pic))
+            if (w, h) != (128, 72):
+                continue
+            stats_tasks = np.array([(0, 1, 0), (0, 2, 72)], dtype=hvb.scd_stats_task_t)
+            stats = np.zeros(72 + 32, np.float64)
+            emu2.emu_scd_block_stats(table, C.c_void_p(stats_tasks.ctypes.data), 2, C.c_void_p(stats.ctypes.data), bps)
+            assert np.array_equal(stats[:72], scd_expected(oracle, pic, 1)) and np.array_equal(stats[72:], scd_expected(oracle, pic, 2))

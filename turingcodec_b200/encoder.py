@@ -97,4 +97,8 @@ def encode(binary: Path, clip: Path, width: int, height: int, frames: int, optio
     m = re.search(r"([\d.]+)s wall", res.stdout)
     if m:
         out["encoder_wall_s"] = float(m.group(1))
+    # the same footer's host time (boost cpu_timer: "Ns wall, Ns user + Ns system"): user + system over wall = host cores kept busy
+    m = re.search(r"([\d.]+)s user \+ ([\d.]+)s system", res.stdout)
+    if m:
+        out["host_user_s"], out["host_system_s"] = float(m.group(1)), float(m.group(2))
     return out

@@ -74,6 +74,8 @@ coded_residual_task_t = np.dtype([("levels", "<i4"), ("log2n", "i1"), ("scanIdx"
 coded_residual_t = np.dtype([("offset", "<i4"), ("words", "<i4")], align=True)
 intra_complexity_task_t = np.dtype([("pic", "<i2"), ("reserved", "<i2"), ("x0", "<i2"), ("y0", "<i2"), ("wBlocks", "<i2"),
                                     ("hBlocks", "<i2"), ("out", "<i4")], align=True)
+aq_layer_task_t = np.dtype([("pic", "<i2"), ("unit", "<i2"), ("out", "<i4")], align=True)
+scd_stats_task_t = np.dtype([("pic", "<i2"), ("margin", "<i2"), ("out", "<i4")], align=True)
 me_bi_task_t = np.dtype([("src_pic", "<i2"), ("ref_pic", "<i2"), ("x0", "<i2"), ("y0", "<i2"), ("w", "<i2"),
                          ("h", "<i2"), ("mvp", mv_t, 2), ("other_pic", "<i2"), ("reserved0", "<i2"),
                          ("rateMvpFlag", "<i8", 2), ("lambda", "<i4"), ("limitMin", mv_t), ("limitMax", mv_t),
@@ -145,6 +147,10 @@ def load_library() -> C.CDLL:
             getattr(lib, name).argtypes = [vp, vp, i32, vp, i32]
     if hasattr(lib, "hvb_intra_complexity_batch"):
         lib.hvb_intra_complexity_batch.argtypes = [vp, vp, i32, vp, i32, i32]
+    if hasattr(lib, "hvb_aq_activity_batch"):
+        lib.hvb_aq_activity_batch.argtypes = [vp, vp, i32, vp, i32, i32]
+        lib.hvb_scd_histogram_batch.argtypes = [vp, vp, i32, vp, i32]
+        lib.hvb_scd_block_stats_batch.argtypes = [vp, vp, i32, vp, i32, i32]
     if hasattr(lib, "hvb_coded_residual_batch"):
         lib.hvb_coded_residual_batch.argtypes = [vp, vp, i32, i32, i32, vp, i32]
     if hasattr(lib, "hvb_deblock_info_upload"):
@@ -369,6 +375,28 @@ class Context:
         out = np.zeros(out_count, np.int32)
         self._check(self.lib.hvb_intra_complexity_batch(self.h, _as_ptr(tasks), tasks.size, _as_ptr(out), out_count, HOST),
                     "hvb_intra_complexity_batch")
+        return out
+
+    def aq_activity(self, tasks, out_count: int) -> np.ndarray:
+        """-> int64 [out_count]: per unit of each layer task the smallest quadrant variance (AdaptiveQuantisation's activity - 1)"""
+        tasks = np.ascontiguousarray(tasks, dtype=aq_layer_task_t)
+        out = np.zeros(out_count, np.int64)
+        self._check(self.lib.hvb_aq_activity_batch(self.h, _as_ptr(tasks), tasks.size, _as_ptr(out), out_count, HOST), "hvb_aq_activity_batch")
+        return out
+
+    def scd_histogram(self, pics) -> np.ndarray:
+        """-> int32 [n, 64]: ShotChangeDetection's luma histogram of each picture"""
+        pics = np.ascontiguousarray(pics, dtype=np.int16)
+        out = np.zeros((pics.size, 64), np.int32)
+        self._check(self.lib.hvb_scd_histogram_batch(self.h, _as_ptr(pics), pics.size, _as_ptr(out), HOST), "hvb_scd_histogram_batch")
+        return out
+
+    def scd_block_stats(self, tasks, out_count: int) -> np.ndarray:
+        """-> float64 [out_count]: (avg, var) pairs of getLikelihood's block grids, placed by each task's `out`"""
+        tasks = np.ascontiguousarray(tasks, dtype=scd_stats_task_t)
+        out = np.zeros(out_count, np.float64)
+        self._check(self.lib.hvb_scd_block_stats_batch(self.h, _as_ptr(tasks), tasks.size, _as_ptr(out), out_count, HOST),
+                    "hvb_scd_block_stats_batch")
         return out
 
     def coded_residual(self, tasks, records_base: int, capacity_words: int) -> np.ndarray:
