@@ -32,6 +32,8 @@ ENTRIES = {
         strip=("template <typename Task>\nint gridFor(",), extra_headers=("hvb_satd.cuh",), namespaces=2,
         replace={
             "__device__ __forceinline__ void cpAsync8(": "static inline void cpAsync8(uint32_t dst, const void *src) { memcpy(emu::sharedArena + dst, src, 8); }",
+        "__device__ __forceinline__ void cpAsync4(": "static inline void cpAsync4(uint32_t dst, const void *src) { memcpy(emu::sharedArena + dst, src, 4); }",
+        "__device__ __forceinline__ void cpAsync16(": "static inline void cpAsync16(uint32_t dst, const void *src) { memcpy(emu::sharedArena + dst, src, 16); }",
             "__device__ __forceinline__ void cpAsyncCommit(": "static inline void cpAsyncCommit() {}",
             "template <int PENDING>\n__device__ __forceinline__ void cpAsyncWait(": "template <int PENDING> static inline void cpAsyncWait() {}",
         },
@@ -51,7 +53,11 @@ extern "C" void emu_satd(const HvbPlane *planes, const hvb_metric_task *tasks, i
         emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdMmaSmallKernel(planes, tasks, n, out, leftover); });
         emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdKernel<uint8_t>(planes, tasks, n, out, leftover); });
     }
-    else emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdKernel<uint16_t>(planes, tasks, n, out, nullptr); });
+    else
+        {
+            emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdMma16Kernel<2>(planes, tasks, n, out, leftover); });
+            emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdKernel<uint16_t>(planes, tasks, n, out, leftover); });
+        }
 }
 '''),
     "hvb_pred.cu": dict(

@@ -84,6 +84,8 @@ EXACT_GRID = ("tuOrderKernel", "rdoqBitsKernel", "rdoqLastKernel", "codedResidua
 FILE_PTX = {
     "hvb_metrics.cu": dict(replace={
         "__device__ __forceinline__ void cpAsync8(": "static inline void cpAsync8(uint32_t dst, const void *src) { memcpy(emu::sharedArena + dst, src, 8); }",
+        "__device__ __forceinline__ void cpAsync4(": "static inline void cpAsync4(uint32_t dst, const void *src) { memcpy(emu::sharedArena + dst, src, 4); }",
+        "__device__ __forceinline__ void cpAsync16(": "static inline void cpAsync16(uint32_t dst, const void *src) { memcpy(emu::sharedArena + dst, src, 16); }",
         "__device__ __forceinline__ void cpAsyncCommit(": "static inline void cpAsyncCommit() {}",
         "template <int PENDING>\n__device__ __forceinline__ void cpAsyncWait(": "template <int PENDING> static inline void cpAsyncWait() {}"}),
     "hvb_intra.cu": dict(mma={"imma16832": False}),

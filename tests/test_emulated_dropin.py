@@ -46,3 +46,17 @@ def test_reference_encoder_on_the_emulated_library_matches_reference(cpu_libhvb,
     got = encode(dropin.B200, "emulated", [], cpu_libhvb)
     assert want[2] > 100  # a real bitstream came out
     assert got == want, tag
+
+
+@pytest.mark.parametrize("tag,width,height,frames,options", dropin.DECODE_CASES[:2], ids=[c[0] for c in dropin.DECODE_CASES[:2]])
+def test_reference_decoder_on_the_emulated_library_matches_reference(cpu_libhvb, tmp_path, tag, width, height, frames, options):
+    """decoder reuse without a GPU: the reference decoder's reconstruction through the table shim and
+    the kernels' source, against the reference decoder on its own C path"""
+    if not (dropin.REF.exists() and dropin.B200.exists()):
+        pytest.skip("oracle/_ref/turing_ref / turing_b200 not built (make -C oracle encoder, needs /root/reference)")
+    clip = tmp_path / "clip.yuv"
+    dropin.write_clip(clip, width, height, frames)
+    dropin.encode(dropin.REF, clip, tmp_path, "ref", width, height, frames, ["--asm", "0", *options])
+    want = dropin.decode(dropin.REF, tmp_path / "ref.bit", tmp_path / "dec_ref.yuv")
+    got = dropin.decode(dropin.B200, tmp_path / "ref.bit", tmp_path / "dec_emulated.yuv", lib_dir=cpu_libhvb)
+    assert got == want, tag

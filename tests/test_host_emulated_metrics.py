@@ -36,12 +36,18 @@ extern "C" void emu_metric(int which, const HvbPlane *planes, const hvb_metric_t
             emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdMmaSmallKernel(planes, tasks, n, out, leftover); });
             emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdKernel<uint8_t>(planes, tasks, n, out, leftover); });
         }
-        else emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdKernel<uint16_t>(planes, tasks, n, out, nullptr); });
+        else
+        {
+            emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdMma16Kernel<2>(planes, tasks, n, out, leftover); });
+            emuLaunch(grid, kWarpsPerBlock * 32, [&] { satdKernel<uint16_t>(planes, tasks, n, out, leftover); });
+        }
     }
 }
 '''
 REPLACE = {
     "__device__ __forceinline__ void cpAsync8(": "static inline void cpAsync8(uint32_t dst, const void *src) { memcpy(emu::sharedArena + dst, src, 8); }",
+        "__device__ __forceinline__ void cpAsync4(": "static inline void cpAsync4(uint32_t dst, const void *src) { memcpy(emu::sharedArena + dst, src, 4); }",
+        "__device__ __forceinline__ void cpAsync16(": "static inline void cpAsync16(uint32_t dst, const void *src) { memcpy(emu::sharedArena + dst, src, 16); }",
     "__device__ __forceinline__ void cpAsyncCommit(": "static inline void cpAsyncCommit() {}",
     "template <int PENDING>\n__device__ __forceinline__ void cpAsyncWait(": "template <int PENDING> static inline void cpAsyncWait() {}",
 }

@@ -22,7 +22,7 @@ def peak_gbs():
     return (float(json.loads(path.read_text())["hbm_gbs"]), "measured") if path.exists() else (6650.0, "fallback")
 
 
-def measure(device=0, blocks=(64, 32, 16, 8), bps_list=(1, 2), layouts=("colocated", "unaligned"), reps=5, side=16384,
+def measure(device=0, blocks=(64, 32, 16, 8), bps_list=(1, 2), layouts=("colocated", "unaligned"), reps=5, side=32704,
             target_candidates=1 << 20, kinds=("sad", "sad4", "ssd", "satd"), log=None, tma=False):
     import torch
     from turingcodec_b200 import hvb
@@ -36,11 +36,14 @@ def measure(device=0, blocks=(64, 32, 16, 8), bps_list=(1, 2), layouts=("colocat
         # five luma-only-sized pictures (source + four references); content is irrelevant to bandwidth
         pics = [ctx.picture_create(side, side, 0) for _ in range(5)]
         rng = np.random.default_rng(0)
+        # (task coordinates are int16: 32704 = 511 * 64 is the largest side; a 64x64 batch is then 261,000 candidates, 2.1 GB)
         row = rng.integers(0, 256 if bps == 1 else 1024, (256, side)).astype(np.uint8 if bps == 1 else np.uint16)
-        plane = np.tile(row, (side // 256, 1))
-        for pic in pics:
-            ctx.picture_upload(pic, 0, plane)
-        del plane
+        reps_y = -(-side // 256)
+        for pic in pics:  # uploaded in bands of 256 rows: no host copy of the whole plane
+            for band in range(reps_y):
+                rows_here = min(256, side - band * 256)
+                rc = ctx.lib.hvb_picture_upload_rect(ctx.h, pic, 0, hvb._as_ptr(row), side, 0, band * 256, side, rows_here)
+                assert rc == 0, rc
         for n in blocks:
             for layout in layouts:
                 pitch = n if layout == "colocated" else n + 16
@@ -92,7 +95,7 @@ def measure(device=0, blocks=(64, 32, 16, 8), bps_list=(1, 2), layouts=("colocat
                         log(r)
                 del d_m, d_s4, d_out
         ctx.close()
-    return {"peak_GBps": peak, "peak_source": peak_src, "working_set_MB": 2 * side * side / 1e6,
+    return {"peak_GBps": peak, "peak_source": peak_src, "working_set_MB": 2 * side * side / 1e6, "side": side,
             "how": "CUDA events on the launching stream, %d back-to-back launches after 2 warm-ups; blocks disjoint, every sample read from HBM once; "
                    "algorithmic bytes = (2 (SAD4: 5) w h B + task + result bytes) x candidates" % reps, "rows": results}
 
@@ -106,8 +109,9 @@ if __name__ == "__main__":
     p.add_argument("--reps", type=int, default=5)
     p.add_argument("--json", default=None)
     p.add_argument("--tma", action="store_true")
+    p.add_argument("--side", type=int, default=32704)
     a = p.parse_args()
-    res = measure(0, [int(v) for v in a.block.split(",")], [int(v) for v in a.bps.split(",")], a.layouts.split(","), a.reps,
+    res = measure(0, [int(v) for v in a.block.split(",")], [int(v) for v in a.bps.split(",")], a.layouts.split(","), a.reps, side=a.side,
                   kinds=a.kinds.split(","), log=lambda r: print(json.dumps(r), flush=True), tma=a.tma)
     if a.json:
         Path(a.json).write_text(json.dumps(res, indent=1) + "\n")

@@ -280,6 +280,10 @@ __device__ __forceinline__ void cpAsync8(uint32_t dst, const void *src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cpAsync4(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cpAsyncCommit()
 {
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -296,21 +300,31 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
     satdMmaKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out,
                   int *__restrict__ leftover)
 {
-    extern __shared__ __align__(16) uint2 satdStage[]; // [warp][stage][part 0..3][lane]
+    // per warp and stage: [part 0..3][lane] 8-byte row slots (1 KB), then [part 2..3][lane] the third word of a prediction row
+    // that is not 8-byte aligned (256 B)
+    extern __shared__ __align__(16) uint2 satdStage[];
+    constexpr int kStageWords = 128 + 32; // in uint2
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int step = gridDim.x * kWarpsPerBlock;
     const HadamardFrag A(lane);
-    uint2 *mine = satdStage + warp * STAGES * 128 + lane;
+    uint2 *mine = satdStage + warp * STAGES * kStageWords + lane;
     const uint32_t mineAddr = (uint32_t)__cvta_generic_to_shared(mine);
+    const uint32_t *mineThird = reinterpret_cast<const uint32_t *>(satdStage + warp * STAGES * kStageWords + 128) + lane;
+    const uint32_t thirdAddr = (uint32_t)__cvta_generic_to_shared(mineThird);
 
     SatdCursor issue;
     issue.t = blockIdx.x * kWarpsPerBlock + warp;
     satdCursorOpen(issue, planes, tasks, n, step, leftover);
 
-    // requests one group into `slot`; (qt, qb) = its task (>= n: none left) and the tiles its block has left, this group included
-    auto issueGroup = [&](int slot, int &qt, int &qb) {
+    // requests one group into `slot`; (qt, qb) = its task (>= n: none left) and the tiles its block has left, this group
+    // included; qs = the bit shift that realigns this lane's prediction rows when they are read back.
+    // The source block of a search sits on a PU boundary, the prediction anywhere: an 8-byte aligned row is one 8-byte
+    // asynchronous copy; any other prediction row is copied as the three aligned words that contain it (still asynchronous:
+    // nothing waits at issue) and funnel-shifted into place by the consuming side.
+    auto issueGroup = [&](int slot, int &qt, int &qb, unsigned &qs) {
         qt = issue.t;
         qb = 0;
+        qs = 0;
         if (issue.t < n)
         {
             qb = issue.tiles - issue.base;
@@ -318,21 +332,37 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
             const int ty = issue.tilesX == 1 ? tile : issue.tiles < 65536 ? (int)__umulhi((unsigned)tile, issue.recip) : tile / issue.tilesX;
             const int tx = tile - ty * issue.tilesX;
             const uint8_t *S = issue.a + (intptr_t)(ty * 8 + t) * issue.sa + tx * 8, *P = issue.b + (intptr_t)(ty * 8 + t) * issue.sb + tx * 8;
-            if (!((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(P) | (uintptr_t)issue.sa | (uintptr_t)issue.sb) & 7))
+            const uint32_t dst = mineAddr + slot * (kStageWords * 8);
+            if (!((reinterpret_cast<uintptr_t>(S) | (uintptr_t)issue.sa) & 7))
             {
-                const uint32_t dst = mineAddr + slot * 1024;
                 cpAsync8(dst, S);
                 cpAsync8(dst + 256, S + 4 * issue.sa);
+            }
+            else
+            {
+                uint2 *d = mine + slot * kStageWords;
+                d[0] = loadRow8(S);
+                d[32] = loadRow8(S + 4 * issue.sa);
+            }
+            if (!((reinterpret_cast<uintptr_t>(P) | (uintptr_t)issue.sb) & 7))
+            {
                 cpAsync8(dst + 512, P);
                 cpAsync8(dst + 768, P + 4 * issue.sb);
             }
             else
             {
-                uint2 *dst = mine + slot * 128;
-                dst[0] = loadRow8(S);
-                dst[32] = loadRow8(S + 4 * issue.sa);
-                dst[64] = loadRow8(P);
-                dst[96] = loadRow8(P + 4 * issue.sb);
+                // (a stride that is no multiple of 4 cannot occur: plane pitches are multiples of 256 bytes)
+                const uintptr_t a = reinterpret_cast<uintptr_t>(P);
+                const uint8_t *q = reinterpret_cast<const uint8_t *>(a & ~uintptr_t(3));
+                qs = (unsigned)(a & 3) * 8;
+                const uint32_t third = thirdAddr + slot * (kStageWords * 8);
+                cpAsync4(dst + 512, q);
+                cpAsync4(dst + 516, q + 4);
+                cpAsync4(third, q + 8);
+                q += 4 * (intptr_t)issue.sb;
+                cpAsync4(dst + 768, q);
+                cpAsync4(dst + 772, q + 4);
+                cpAsync4(third + 128, q + 8);
             }
             issue.base += 8;
             if (issue.base >= issue.tiles)
@@ -345,16 +375,27 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
     };
 
     int qt[STAGES - 1], qb[STAGES - 1]; // the groups in flight, oldest first
+    unsigned qs[STAGES - 1];
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) issueGroup(s, qt[s], qb[s]);
+    for (int s = 0; s < STAGES - 1; ++s) issueGroup(s, qt[s], qb[s], qs[s]);
     int slot = 0, total = 0;
     while (qt[0] < n)
     {
         int nt, nb;
-        issueGroup(slot == 0 ? STAGES - 1 : slot - 1, nt, nb);
+        unsigned ns;
+        issueGroup(slot == 0 ? STAGES - 1 : slot - 1, nt, nb, ns);
         cpAsyncWait<STAGES - 1>();
-        const uint2 *src = mine + slot * 128;
-        const uint2 r0 = src[0], r1 = src[32], r2 = src[64], r3 = src[96];
+        const uint2 *src = mine + slot * kStageWords;
+        const uint2 r0 = src[0], r1 = src[32];
+        uint2 r2 = src[64], r3 = src[96];
+        if (qs[0])
+        {
+            // prediction rows that arrived as three aligned words: bytes (shift / 8) .. (shift / 8) + 7 of them
+            const uint32_t *third = mineThird + slot * (kStageWords * 2);
+            const uint32_t w2 = third[0], w3 = third[32];
+            r2 = make_uint2(__funnelshift_r(r2.x, r2.y, qs[0]), __funnelshift_r(r2.y, w2, qs[0]));
+            r3 = make_uint2(__funnelshift_r(r3.x, r3.y, qs[0]), __funnelshift_r(r3.y, w3, qs[0]));
+        }
         const uint32_t bx[4] = {r0.x, r1.x, r2.x, r3.x}, by[4] = {r0.y, r1.y, r2.y, r3.y};
         // the four m-tiles' products advance together, k-step by k-step: four independent accumulator chains, so that an
         // IMMA is followed by three that do not wait for it (the ncu capture of the mt-outer order showed `wait` on the
@@ -392,9 +433,222 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
         {
             qt[s] = qt[s + 1];
             qb[s] = qb[s + 1];
+            qs[s] = qs[s + 1];
         }
         qt[STAGES - 2] = nt;
         qb[STAGES - 2] = nb;
+        qs[STAGES - 2] = ns;
+        slot = slot == STAGES - 1 ? 0 : slot + 1;
+    }
+    cpAsyncWait<0>();
+}
+
+// ---- 16-bit samples: the same stream, the products on the samples' byte planes ---------------------------------------
+// A tile row is 16 bytes.  Lane (g, t) requests rows t and t + 4 of tile g of both pictures: one 16-byte asynchronous copy
+// where the row is 16-byte aligned (the source block of a search always is), otherwise the five aligned words that contain
+// it, realigned by the consuming side.  The rows are split into their low-byte and high-byte planes (two byte permutes per
+// 8 bytes); the high plane's products run first, the accumulators are scaled by 256 and the low plane's products continue
+// in the same registers: sum_k H[m][k] (256 hi_k + lo_k), exact in 32 bits, so the absolute value is taken of the
+// reference's coefficient.  Blocks of up to kSmallTiles tiles stay with satdKernel (two per warp).
+__device__ __forceinline__ void cpAsync16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void satdCursorOpen16(SatdCursor &c, const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks,
+                                                 int n, int step, int *__restrict__ leftover)
+{
+    while (c.t < n)
+    {
+        const hvb_metric_task task = tasks[c.t];
+        if (!((task.w | task.h) & 7) && (task.w >> 3) * (task.h >> 3) > kSmallTiles)
+        {
+            int sa, sb;
+            c.a = reinterpret_cast<const uint8_t *>(hvbBlockPtr<uint16_t>(planes, task.a, sa));
+            c.b = reinterpret_cast<const uint8_t *>(hvbBlockPtr<uint16_t>(planes, task.b, sb));
+            c.sa = 2 * sa, c.sb = 2 * sb; // in bytes
+            c.tilesX = task.w >> 3;
+            c.recip = c.tilesX > 1 ? 0xffffffffu / (unsigned)c.tilesX + 1u : 0u;
+            c.tiles = c.tilesX * (task.h >> 3);
+            c.base = 0;
+            return;
+        }
+        leftover[0] = 1; // a block for satdKernel (every lane stores the same value)
+        c.t += step;
+    }
+}
+
+// 16 bytes of a 16-bit tile row at any 2-byte aligned address, synchronously (source rows off the 16-byte grid: not the
+// case for the blocks of a search)
+__device__ __forceinline__ uint4 loadRow16(const uint8_t *p)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    if ((a & 15) == 0) return __ldg(reinterpret_cast<const uint4 *>(p));
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+    const unsigned sh = (unsigned)(a & 3) * 8;
+    const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3);
+    if (sh == 0) return make_uint4(w0, w1, w2, w3);
+    const uint32_t w4 = __ldg(q + 4);
+    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
+    satdMma16Kernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out,
+                    int *__restrict__ leftover)
+{
+    // per warp and stage: [part 0..3][lane] 16-byte row slots (2 KB), then [part 2..3][lane] the fifth word of a prediction
+    // row that is not 16-byte aligned (256 B)
+    extern __shared__ __align__(16) uint4 satdStage16[];
+    constexpr int kStageQuads = 128 + 16; // in uint4
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int step = gridDim.x * kWarpsPerBlock;
+    const HadamardFrag A(lane);
+    uint4 *mine = satdStage16 + warp * STAGES * kStageQuads + lane;
+    const uint32_t mineAddr = (uint32_t)__cvta_generic_to_shared(mine);
+    const uint32_t *mineFifth = reinterpret_cast<const uint32_t *>(satdStage16 + warp * STAGES * kStageQuads + 128) + lane;
+    const uint32_t fifthAddr = (uint32_t)__cvta_generic_to_shared(mineFifth);
+
+    SatdCursor issue;
+    issue.t = blockIdx.x * kWarpsPerBlock + warp;
+    satdCursorOpen16(issue, planes, tasks, n, step, leftover);
+
+    auto issueGroup = [&](int slot, int &qt, int &qb, unsigned &qs) {
+        qt = issue.t;
+        qb = 0;
+        qs = 0;
+        if (issue.t < n)
+        {
+            qb = issue.tiles - issue.base;
+            const int tile = min(issue.base + g, issue.tiles - 1);
+            const int ty = issue.tilesX == 1 ? tile : issue.tiles < 65536 ? (int)__umulhi((unsigned)tile, issue.recip) : tile / issue.tilesX;
+            const int tx = tile - ty * issue.tilesX;
+            const uint8_t *S = issue.a + (intptr_t)(ty * 8 + t) * issue.sa + tx * 16, *P = issue.b + (intptr_t)(ty * 8 + t) * issue.sb + tx * 16;
+            const uint32_t dst = mineAddr + slot * (kStageQuads * 16);
+            if (!((reinterpret_cast<uintptr_t>(S) | (uintptr_t)issue.sa) & 15))
+            {
+                cpAsync16(dst, S);
+                cpAsync16(dst + 512, S + 4 * issue.sa);
+            }
+            else
+            {
+                uint4 *d = mine + slot * kStageQuads;
+                d[0] = loadRow16(S);
+                d[32] = loadRow16(S + 4 * issue.sa);
+            }
+            if (!((reinterpret_cast<uintptr_t>(P) | (uintptr_t)issue.sb) & 15))
+            {
+                cpAsync16(dst + 1024, P);
+                cpAsync16(dst + 1536, P + 4 * issue.sb);
+            }
+            else
+            {
+                const uintptr_t a = reinterpret_cast<uintptr_t>(P);
+                const uint8_t *q = reinterpret_cast<const uint8_t *>(a & ~uintptr_t(3));
+                qs = (unsigned)(a & 3) * 8; // 0 or 16
+                const uint32_t fifth = fifthAddr + slot * (kStageQuads * 16);
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                {
+                    const uint32_t d = dst + 1024 + 512 * r;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) cpAsync4(d + 4 * i, q + 4 * i);
+                    cpAsync4(fifth + 128 * r, q + 16);
+                    q += 4 * (intptr_t)issue.sb;
+                }
+            }
+            issue.base += 8;
+            if (issue.base >= issue.tiles)
+            {
+                issue.t += step;
+                satdCursorOpen16(issue, planes, tasks, n, step, leftover);
+            }
+        }
+        cpAsyncCommit();
+    };
+
+    int qt[STAGES - 1], qb[STAGES - 1];
+    unsigned qs[STAGES - 1];
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issueGroup(s, qt[s], qb[s], qs[s]);
+    int slot = 0, total = 0;
+    while (qt[0] < n)
+    {
+        int nt, nb;
+        unsigned ns;
+        issueGroup(slot == 0 ? STAGES - 1 : slot - 1, nt, nb, ns);
+        cpAsyncWait<STAGES - 1>();
+        const uint4 *src = mine + slot * kStageQuads;
+        uint4 r[4] = {src[0], src[32], src[64], src[96]};
+        if (qs[0])
+        {
+            const uint32_t *fifth = mineFifth + slot * (kStageQuads * 4);
+            const uint32_t w4[2] = {fifth[0], fifth[32]};
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+            {
+                uint4 &v = r[2 + i];
+                v = make_uint4(__funnelshift_r(v.x, v.y, qs[0]), __funnelshift_r(v.y, v.z, qs[0]), __funnelshift_r(v.z, v.w, qs[0]),
+                               __funnelshift_r(v.w, w4[i], qs[0]));
+            }
+        }
+        int acc[4][4] = {};
+#pragma unroll
+        for (int plane = 1; plane >= 0; --plane)
+        {
+            // byte plane of the four rows: the samples' high bytes first, then (accumulators scaled by 256) their low bytes
+            const unsigned sel = plane ? 0x7531u : 0x6420u;
+            uint32_t bx[4], by[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                bx[i] = __byte_perm(r[i].x, r[i].y, sel);
+                by[i] = __byte_perm(r[i].z, r[i].w, sel);
+            }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+                {
+                    const uint32_t neg = ((((mt >> 1) & ks) ^ (ks >> 1)) & 1) ? 0xfefefefeu : 0u;
+                    imma16832(acc[mt], A.x[mt & 1][0] ^ neg, A.x[mt & 1][1] ^ neg, A.x[mt & 1][2] ^ neg, A.x[mt & 1][3] ^ neg, bx[ks], by[ks]);
+                }
+            if (plane)
+            {
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[mt][i] *= 256;
+            }
+        }
+        int s0 = 0, s1 = 0;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+        {
+            s0 = __sad(acc[mt][0], 0, __sad(acc[mt][2], 0, (unsigned)s0));
+            s1 = __sad(acc[mt][1], 0, __sad(acc[mt][3], 0, (unsigned)s1));
+        }
+        int sum = (g & 1) ? s1 : s0;
+        sum += __shfl_xor_sync(0xffffffffu, (g & 1) ? s0 : s1, 4);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+        if (g < 2 && 2 * t + g < qb[0]) total += ((sum + 2) >> 2) >> 2; // havoc/hadamard.cpp:319-323, 16-bit samples: >> 2 per tile
+        if (qb[0] <= 8)
+        {
+            total = hvbWarpSum(total);
+            if (lane == 0) out[qt[0]] = total;
+            total = 0;
+        }
+#pragma unroll
+        for (int s = 0; s + 1 < STAGES - 1; ++s)
+        {
+            qt[s] = qt[s + 1];
+            qb[s] = qb[s + 1];
+            qs[s] = qs[s + 1];
+        }
+        qt[STAGES - 2] = nt;
+        qb[STAGES - 2] = nb;
+        qs[STAGES - 2] = ns;
         slot = slot == STAGES - 1 ? 0 : slot + 1;
     }
     cpAsyncWait<0>();
@@ -502,16 +756,35 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     if (leftover && *leftover == 0) return;
     const int lane = threadIdx.x & 31;
     const int warpsTotal = gridDim.x * kWarpsPerBlock;
-    for (int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n; t += warpsTotal)
+    // a warp takes two consecutive tasks at a time: a half-warp each when both blocks have at most 16 tiles (a 32x32 block of
+    // 8x8 tiles would leave half the lanes idle), otherwise the whole warp one block after the other
+    for (int t2 = 2 * (blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)); t2 < n; t2 += 2 * warpsTotal)
     {
-        const hvb_metric_task task = tasks[t];
-        if (sizeof(Sample) == 1 && ((task.w | task.h) & 7) == 0) continue; // satdMmaKernel
-        int sa, sb;
-        const Sample *a = hvbBlockPtr<Sample>(planes, task.a, sa);
-        const Sample *b = hvbBlockPtr<Sample>(planes, task.b, sb);
-        int acc = hvbMeasureSatdLanes<Sample, Sample>(a, sa, b, sb, task.w, task.h, lane, 32, sizeof(Sample) == 2 ? 2 : 0);
-        acc = hvbWarpSum(acc);
-        if (lane == 0) out[t] = acc;
+        const bool pair = t2 + 1 < n;
+        const hvb_metric_task task0 = tasks[t2], task1 = pair ? tasks[t2 + 1] : task0;
+        const bool split = pair && hvbSatdTiles(task0.w, task0.h) <= 16 && hvbSatdTiles(task1.w, task1.h) <= 16;
+        for (int k = 0; k < (split || !pair ? 1 : 2); ++k)
+        {
+            const int half = lane >> 4;
+            const int index = split ? t2 + half : t2 + k;
+            const hvb_metric_task task = (split ? half : k) ? task1 : task0;
+            // blocks tiled 8x8 belong to the tensor-core kernels: all of them with 8-bit samples (satdMmaKernel, satdMmaSmallKernel),
+            // those of more than kSmallTiles tiles with 16-bit samples (satdMma16Kernel)
+            const bool skip = ((task.w | task.h) & 7) == 0 && (sizeof(Sample) == 1 || (task.w >> 3) * (task.h >> 3) > kSmallTiles);
+            int acc = 0;
+            if (!skip)
+            {
+                int sa, sb;
+                const Sample *a = hvbBlockPtr<Sample>(planes, task.a, sa);
+                const Sample *b = hvbBlockPtr<Sample>(planes, task.b, sb);
+                acc = hvbMeasureSatdLanes<Sample, Sample>(a, sa, b, sb, task.w, task.h, split ? (lane & 15) : lane, split ? 16 : 32,
+                                                          sizeof(Sample) == 2 ? 2 : 0);
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (!split) acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            if ((lane & (split ? 15 : 31)) == 0 && !skip) out[index] = acc;
+        }
     }
 }
 
@@ -610,7 +883,7 @@ extern "C" int hvb_satd_batch(hvb_context *ctx, const hvb_metric_task *tasks, in
         // two stages measured best (64.5 % of HBM peak at 64x64 against 64.1 % with three and 62.3 % with four: the
         // products, not the copies, bound the kernel, and a deeper queue costs registers and shared memory)
         constexpr int kStages = 2;
-        const int smem = kWarpsPerBlock * kStages * 1024;
+        const int smem = kWarpsPerBlock * kStages * 1280; // per warp and stage: 1 KB of row slots + 256 B of third words
         int perSm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, satdMmaKernel<kStages>, kWarpsPerBlock * 32, smem);
         const int blocks = min((n + kWarpsPerBlock - 1) / kWarpsPerBlock, ctx->smCount * max(perSm, 1));
@@ -619,6 +892,21 @@ extern "C" int hvb_satd_batch(hvb_context *ctx, const hvb_metric_task *tasks, in
         const int smallBlocks = min((n + 32 * kWarpsPerBlock - 1) / (32 * kWarpsPerBlock), ctx->smCount * 4);
         satdMmaSmallKernel<<<smallBlocks, kWarpsPerBlock * 32, 0, ctx->stream>>>(ctx->dPlanes, dT, n, dO, leftover);
         HVB_LAUNCH_CHECK(ctx, "satdMmaSmallKernel");
+    }
+    else
+    {
+        const auto *dT = static_cast<const hvb_metric_task *>(st.dTasks);
+        auto *dO = static_cast<int32_t *>(st.dOut);
+        leftover = ctx->workCursors + 2;
+        cudaMemsetAsync(leftover, 0, 3 * sizeof(int), ctx->stream);
+        constexpr int kStages = 2;
+        const int smem = kWarpsPerBlock * kStages * 2304; // per warp and stage: 2 KB of row slots + 256 B of fifth words
+        cudaFuncSetAttribute(satdMma16Kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        int perSm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, satdMma16Kernel<kStages>, kWarpsPerBlock * 32, smem);
+        const int blocks = min((n + kWarpsPerBlock - 1) / kWarpsPerBlock, ctx->smCount * max(perSm, 1));
+        satdMma16Kernel<kStages><<<blocks, kWarpsPerBlock * 32, smem, ctx->stream>>>(ctx->dPlanes, dT, n, dO, leftover);
+        HVB_LAUNCH_CHECK(ctx, "satdMma16Kernel");
     }
     HVB_DISPATCH_SAMPLE(ctx, satdKernel, gridFor<hvb_metric_task>(ctx, n), ctx->dPlanes,
                         static_cast<const hvb_metric_task *>(st.dTasks), n, static_cast<int32_t *>(st.dOut), leftover);

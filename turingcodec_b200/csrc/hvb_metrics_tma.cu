@@ -7,6 +7,11 @@
 // takes the block's coordinates as they are: `cp.async.bulk.tensor.2d` drops a box of the picture plane into shared
 // memory, aligned, signalling an mbarrier with the bytes it delivered; the lanes then read aligned 128-bit chunks.
 //
+// The TMA takes box coordinates whose innermost byte offset is a multiple of 16 only (measured on the B200: any other
+// coordinate faults the kernel with "illegal instruction"), so a task with an operand off that grid -- the usual
+// motion-search candidate -- is computed by the warp straight from global memory instead; the staged path serves
+// co-located and 16-byte aligned operands, which is where it was measured against the load/store kernels.
+//
 // Tensor maps: one per plane and box shape, over the plane's whole allocation (padding included, so a vector into the
 // padding is an ordinary coordinate), element type UINT8 for both sample widths (a 16-bit plane is a byte plane twice as
 // wide).  Every box is 1 KB: 16 B x 64 rows, 32 B x 32 rows or 64 B x 16 rows, chosen per task by the block's width in
@@ -94,6 +99,17 @@ __device__ __forceinline__ void shapeOf(int wb, int &shape, int &boxW, int &boxH
     halves = wb > 64 ? 2 : 1;
 }
 
+// every operand of the item starts on a 16-byte boundary of its plane's allocation
+template <int NREF, int B>
+__device__ __forceinline__ bool boxAligned(const HvbPlane *__restrict__ planes, const Item &item)
+{
+    unsigned bits = (unsigned)((planes[item.srcPlane].reserved + item.srcX) * B);
+    const int reserved = planes[item.refPlane].reserved;
+#pragma unroll
+    for (int k = 0; k < NREF; ++k) bits |= (unsigned)((reserved + item.refX[k]) * B);
+    return (bits & 15u) == 0;
+}
+
 template <typename Sample, int NREF, int STAGES>
 __global__ void __launch_bounds__(kWarps * 32)
     sadTmaKernel(const HvbPlane *__restrict__ planes, const CUtensorMap *__restrict__ maps, const void *__restrict__ tasks, int n, int32_t *__restrict__ out)
@@ -119,8 +135,13 @@ __global__ void __launch_bounds__(kWarps * 32)
     for (int k = 0; k < NREF; ++k) acc[k] = 0;
 
     auto issueOne = [&]() {
-        if (it >= n) return false;
-        const Item item = loadItem<NREF>(tasks, it);
+        Item item;
+        for (;; it += warpsTotal) // tasks with an operand off the 16-byte grid are not staged
+        {
+            if (it >= n) return false;
+            item = loadItem<NREF>(tasks, it);
+            if (boxAligned<NREF, B>(planes, item)) break;
+        }
         int shape, boxW, boxH, halves;
         shapeOf(item.w * B, shape, boxW, boxH, halves);
         const int stage = issued % STAGES;
@@ -154,8 +175,32 @@ __global__ void __launch_bounds__(kWarps * 32)
     for (int s = 0; s < STAGES - 1; ++s) issueOne();
     while (ct < n)
     {
-        issueOne(); // keeps STAGES - 1 items in flight while this one is consumed (the stage it targets was freed last turn)
         const Item item = loadItem<NREF>(tasks, ct);
+        if (!boxAligned<NREF, B>(planes, item))
+        {
+            // straight from global memory, a lane per sample
+            const HvbPlane sp = planes[item.srcPlane], rp = planes[item.refPlane];
+            const Sample *src = reinterpret_cast<const Sample *>(sp.base) + (intptr_t)item.srcY * sp.stride + item.srcX;
+            for (int i = lane; i < item.w * item.h; i += 32)
+            {
+                const int y = i / item.w, x = i - y * item.w;
+                const int a = src[(intptr_t)y * sp.stride + x];
+#pragma unroll
+                for (int k = 0; k < NREF; ++k)
+                    acc[k] += (unsigned)abs(a - (int)(reinterpret_cast<const Sample *>(rp.base) + (intptr_t)(item.refY[k] + y) * rp.stride + item.refX[k])[x]);
+            }
+#pragma unroll
+            for (int k = 0; k < NREF; ++k)
+            {
+                int v = hvbWarpSum((int)acc[k]);
+                if (B == 2) v >>= 2;
+                if (lane == 0) out[ct * NREF + k] = v;
+                acc[k] = 0;
+            }
+            ct += warpsTotal;
+            continue;
+        }
+        issueOne(); // keeps STAGES - 1 items in flight while this one is consumed (the stage it targets was freed last turn)
         int shape, boxW, boxH, halves;
         const int wb = item.w * B;
         shapeOf(wb, shape, boxW, boxH, halves);

@@ -29,6 +29,33 @@ __device__ __forceinline__ int hvbSatdTile(const SampleA *a, int sa, const Sampl
             }
         }
     }
+    else if (N == 8 && sizeof(SampleA) == 2 && sizeof(SampleB) == 2 &&
+             !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | (uintptr_t)(2 * sa) | (uintptr_t)(2 * sb)) & 3))
+    {
+        // 16-bit rows on a 4-byte boundary: four 32-bit loads per row per operand (one 128-bit load when the row is 16-byte
+        // aligned) instead of eight 16-bit loads
+#pragma unroll
+        for (int y = 0; y < N; ++y)
+        {
+            const uint32_t *pa = reinterpret_cast<const uint32_t *>(a + y * sa), *pb = reinterpret_cast<const uint32_t *>(b + y * sb);
+            uint4 va, vb;
+            if (!(reinterpret_cast<uintptr_t>(pa) & 15))
+                va = __ldg(reinterpret_cast<const uint4 *>(pa));
+            else
+                va = make_uint4(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pa + 3));
+            if (!(reinterpret_cast<uintptr_t>(pb) & 15))
+                vb = __ldg(reinterpret_cast<const uint4 *>(pb));
+            else
+                vb = make_uint4(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), __ldg(pb + 3));
+            const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+            {
+                m[y][2 * x] = (int)(wa[x] & 0xffff) - (int)(wb[x] & 0xffff);
+                m[y][2 * x + 1] = (int)(wa[x] >> 16) - (int)(wb[x] >> 16);
+            }
+        }
+    }
     else
     {
 #pragma unroll
@@ -72,6 +99,13 @@ __device__ __forceinline__ int hvbSatdTile(const SampleA *a, int sa, const Sampl
         for (int x = 0; x < N; ++x) acc += abs(m[y][x]);
     // havoc/hadamard.cpp:93-96: normalise, then the 16-bit sample paths shift right by 2 per tile
     return (acc >> (LOG2N - 1)) >> postShift;
+}
+
+// the number of Hadamard tiles measureSatd cuts a w x h block into (turing/Measure.h:96-135)
+__device__ __forceinline__ int hvbSatdTiles(int w, int h)
+{
+    const int log2 = ((w | h) & 3) ? 1 : (((w | h) & 7) ? 2 : 3);
+    return (w >> log2) * (h >> log2);
 }
 
 template <typename SampleA, typename SampleB>
