@@ -44,7 +44,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = "4K YUV420 8-bit encode fps (medium)"
-PASS_METRIC = "hot-path frame passes per second (ME + intra sweep + TU/RDOQ for every candidate of one frame, inputs resident)"
+PASS_METRIC = "hot-path frame passes per second (uni + bi motion search, PU costs, intra sweep, TU/RDOQ for every candidate of one frame, inputs resident)"
 UNIT = "frames/s"
 # the unmodified reference encoder (test infrastructure, built by oracle/Makefile): the CPU arm and the identity check
 REFERENCE_ENCODER = ROOT / "oracle" / "_ref" / "turing_ref"
@@ -226,6 +226,34 @@ class GpuArm:
             self.sets.append(dict(pics=pics_b, pool_offset=int(fp.neighbours.size), me=pin(me_b), intra=pin(intra_b), tu=pin(tu_b)))
         self.kernel_ms = {"me": 0.0, "intra": 0.0, "tu": 0.0}
         torch.cuda.synchronize(device)
+        # The bi-prediction refinement and the PU costs of the same PUs (turing/Search.hpp:1796-1827, :1656-1706): seeded with
+        # the vectors the uni-directional search has just found, as Search<prediction_unit>::go2 seeds them; PUs of 8x4 / 4x8
+        # are uni-predicted only (:1886).  One searchMotionBi and one uni + one bi measurePuCost per PU.
+        self.ctx.me_search(self.d_me.data_ptr(), fp.me.size, self.o_me.data_ptr(), hvb.DEVICE)
+        torch.cuda.synchronize(device)
+        found = self.o_me.cpu().numpy().view(hvb.me_result_t)
+        me = fp.me
+        both = (me["w"].astype(np.int32) + me["h"]) != 12
+        bi = np.zeros(int(both.sum()), hvb.me_bi_task_t)
+        for name in ("src_pic", "ref_pic", "x0", "y0", "w", "h", "mvp", "rateMvpFlag", "limitMin", "limitMax"):
+            bi[name] = me[name][both]
+        bi["other_pic"] = self.pics[2]
+        bi["lambda"] = me["lambda"][both] // 2
+        bi["mvStart"], bi["mvOther"] = found["mv"][both], found["mv"][both]
+        bi["smallWindow"], bi["halfPel"], bi["quarterPel"] = 0, 1, 1
+        pu = np.zeros(me.size + bi.size, hvb.pu_cost_task_t)
+        pu["src_pic"], pu["dst_pic"] = self.pics[0], -1
+        for name in ("x0", "y0", "w", "h"):
+            pu[name][:me.size], pu[name][me.size:] = me[name], bi[name]
+        pu["ref_pic"][:, 0], pu["ref_pic"][:me.size, 1], pu["ref_pic"][me.size:, 1] = self.pics[1], -1, self.pics[2]
+        pu["mvx"][:me.size, 0], pu["mvy"][:me.size, 0] = found["mv"]["x"], found["mv"]["y"]
+        for k in range(2):
+            pu["mvx"][me.size:, k], pu["mvy"][me.size:, k] = bi["mvStart"]["x"], bi["mvStart"]["y"]
+        self.bi, self.pu = bi, pu
+        self.d_bi, self.d_pu = to_dev(bi), to_dev(pu)
+        self.o_bi = torch.zeros(bi.size * hvb.me_bi_result_t.itemsize, dtype=torch.uint8, device=dev)
+        self.o_pu = torch.zeros(pu.size * 3, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(device)
 
     # resident step: three launches
     def step_resident(self, events=None):
@@ -241,6 +269,12 @@ class GpuArm:
         self.ctx.tu_chain(self.d_tu.data_ptr(), fp.tu.size, self.o_tu.data_ptr(), hvb.DEVICE)
         if events is not None:
             events[3].record(self.stream)
+        self.ctx.me_bi_search(self.d_bi.data_ptr(), self.bi.size, self.o_bi.data_ptr(), hvb.DEVICE)
+        if events is not None:
+            events[4].record(self.stream)
+        self.ctx.pu_cost(self.d_pu.data_ptr(), self.pu.size, self.o_pu.data_ptr(), hvb.DEVICE)
+        if events is not None:
+            events[5].record(self.stream)
 
     # host-facing step: upload pictures + neighbours, host task arrays in, host result arrays out
     def step_e2e(self, k: int = 0):
@@ -578,24 +612,32 @@ def hot_path_pass(args, local, steps):
     for _ in range(3):
         arm.step_resident()
     torch.cuda.synchronize(local)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(steps)]
     for k in range(steps):
         arm.step_resident(ev[k])
     torch.cuda.synchronize(local)
-    total_ms = ev[0][0].elapsed_time(ev[-1][3])
-    kern = {"me": 0.0, "intra": 0.0, "tu": 0.0}
+    total_ms = ev[0][0].elapsed_time(ev[-1][5])
+    kern = {"me": 0.0, "intra": 0.0, "tu": 0.0, "bi": 0.0, "pu": 0.0}
     for k in range(steps):
-        kern["me"] += ev[k][0].elapsed_time(ev[k][1]) / steps
-        kern["intra"] += ev[k][1].elapsed_time(ev[k][2]) / steps
-        kern["tu"] += ev[k][2].elapsed_time(ev[k][3]) / steps
+        for i, name in enumerate(("me", "intra", "tu", "bi", "pu")):
+            kern[name] += ev[k][i].elapsed_time(ev[k][i + 1]) / steps
     fp = arm.fp
     me_out = arm.o_me.cpu().numpy().view(hvb.me_result_t)
     n_sad_samples = int((me_out["nSad"].astype(np.int64) * fp.me["w"].astype(np.int64) * fp.me["h"].astype(np.int64)).sum())
     ab = workload.algorithmic_bytes(fp, 0, arm.bps)
-    alg = {"me": ab["me_fixed"] + n_sad_samples * arm.bps, "intra": ab["intra"], "tu": ab["tu"]}
+    # SURVEY.md 8d / DESIGN.md section 4: bi search  whB + 121 whB + 18 ((w+7)(h+7) + wh) B per PU; PU cost  3/2 ((w+7)(h+7) + wh) B per list
+    B = arm.bps
+    wh_bi = arm.bi["w"].astype(np.int64) * arm.bi["h"]
+    sup_bi = (arm.bi["w"].astype(np.int64) + 7) * (arm.bi["h"].astype(np.int64) + 7) + wh_bi
+    sup_pu = (arm.pu["w"].astype(np.int64) + 7) * (arm.pu["h"].astype(np.int64) + 7) + arm.pu["w"].astype(np.int64) * arm.pu["h"]
+    lists = (arm.pu["ref_pic"] >= 0).sum(axis=1)
+    alg = {"me": ab["me_fixed"] + n_sad_samples * arm.bps, "intra": ab["intra"], "tu": ab["tu"],
+           "bi": int((122 * wh_bi + 18 * sup_bi).sum()) * B, "pu": int((3 * sup_pu * lists).sum()) * B // 2}
     peak, peak_src = peaks()
-    names = {"me": "meSearchSmallKernel+meSearchKernel+meSubpelKernel", "intra": "intraSweepKernel8", "tu": "tuFrontKernel+tuRdoqKernel+tuBackKernel"}
-    out = {"metric": PASS_METRIC, "value": 1000.0 * steps / total_ms, "unit": "passes/s", "steps": steps, "units_per_step": fp.units,
+    names = {"me": "meSearchSmallKernel+meSearchKernel+meSubpelKernel", "intra": "intraSweepKernel8", "tu": "tuFrontKernel+tuRdoqKernel+tuBackKernel",
+             "bi": "meBiSearchKernel+meSubpelKernel<BI>", "pu": "puCostKernel"}
+    units = dict(fp.units, bi_searches=int(arm.bi.size), pu_costs=int(arm.pu.size))
+    out = {"metric": PASS_METRIC, "value": 1000.0 * steps / total_ms, "unit": "passes/s", "steps": steps, "units_per_step": units,
            "kernels": {names[k]: {"ms": kern[k], "algorithmic_GBps": alg[k] / (kern[k] * 1e-3) / 1e9, "frac_of_hbm_peak": alg[k] / (kern[k] * 1e-3) / 1e9 / peak}
                        for k in kern},
            "peak_GBps": peak, "peak_source": peak_src, "ncu": ncu_evidence()}

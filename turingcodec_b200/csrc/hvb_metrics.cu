@@ -83,6 +83,40 @@ __device__ __forceinline__ unsigned ssdWords(uint4 a, uint4 b, unsigned acc)
     return acc;
 }
 
+// Both operands on the 16-byte grid (co-located blocks, or a candidate that happens to be aligned) and rows of 1, 2, 4 or 8
+// whole chunks: the warp's 32 lanes cover 32 / cpr rows per turn, a lane keeps its column, and four turns' loads (eight
+// 128-bit loads per lane) are requested before the first is consumed -- two loads in flight per lane do not cover the
+// HBM latency at full bandwidth.  Returns false when the block does not qualify.
+template <typename F>
+__device__ __forceinline__ bool alignedChunks(const uint8_t *pa, intptr_t pitchA, const uint8_t *pb, intptr_t pitchB, int wb, int h, int lane, F consume)
+{
+    const int cpr = wb >> 4;
+    if (((reinterpret_cast<uintptr_t>(pa) | reinterpret_cast<uintptr_t>(pb) | (uintptr_t)pitchA | (uintptr_t)pitchB | (uintptr_t)wb) & 15) ||
+        (cpr != 1 && cpr != 2 && cpr != 4 && cpr != 8))
+        return false;
+    const int shift = __ffs(cpr) - 1, rowsPerTurn = 32 >> shift;
+    const int x = (lane & (cpr - 1)) << 4;
+    const uint8_t *qa = pa + (intptr_t)(lane >> shift) * pitchA + x, *qb = pb + (intptr_t)(lane >> shift) * pitchB + x;
+    const intptr_t stepA = rowsPerTurn * pitchA, stepB = rowsPerTurn * pitchB;
+    for (int y = lane >> shift; y < h; y += 4 * rowsPerTurn)
+    {
+        uint4 va[4], vb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (y + k * rowsPerTurn < h)
+            {
+                va[k] = __ldg(reinterpret_cast<const uint4 *>(qa + k * stepA));
+                vb[k] = __ldg(reinterpret_cast<const uint4 *>(qb + k * stepB));
+            }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (y + k * rowsPerTurn < h) consume(va[k], vb[k]);
+        qa += 4 * stepA;
+        qb += 4 * stepB;
+    }
+    return true;
+}
+
 // Streaming form shared by SAD, SAD4 and SSD: a block is h rows of ceil(w * B / 16) 16-byte chunks, the chunks go
 // round the lanes, every operand chunk is one or two 128-bit loads whatever the block's alignment (co-located blocks,
 // motion-search candidates, 8- and 16-bit samples alike); the excess bytes of a row's last chunk are masked in both
@@ -93,6 +127,8 @@ __device__ __forceinline__ int sadBlock(const Sample *a, int sa, const Sample *b
     const int B = (int)sizeof(Sample), wb = w * B, cpr = (wb + 15) >> 4, total = cpr * h;
     const uint8_t *pa = reinterpret_cast<const uint8_t *>(a), *pb = reinterpret_cast<const uint8_t *>(b);
     unsigned acc = 0;
+    if (alignedChunks(pa, (intptr_t)sa * B, pb, (intptr_t)sb * B, wb, h, lane, [&](const uint4 &va, const uint4 &vb) { acc += sadWords<Sample>(va, vb); }))
+        return (int)acc;
 #pragma unroll 2
     for (int i = lane; i < total; i += 32)
     {
@@ -178,13 +214,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
         const uint8_t *pb = reinterpret_cast<const uint8_t *>(hvbBlockPtr<Sample>(planes, task.b, sb));
         const int wb = task.w * B, h = task.h, cpr = (wb + 15) >> 4, total = cpr * h;
         unsigned acc = 0; // modulo 2^32, like the reference's uint32_t accumulator (havoc/ssd.cpp:28-43)
-#pragma unroll 2
-        for (int i = lane; i < total; i += 32)
+        if (!alignedChunks(pa, (intptr_t)sa * B, pb, (intptr_t)sb * B, wb, h, lane, [&](const uint4 &va, const uint4 &vb) { acc = ssdWords<Sample>(va, vb, acc); }))
         {
-            const int y = i / cpr, x = (i - y * cpr) << 4;
-            const uint4 va = maskChunk(load16(pa + (intptr_t)y * sa * B + x), wb - x);
-            const uint4 vb = maskChunk(load16(pb + (intptr_t)y * sb * B + x), wb - x);
-            acc = ssdWords<Sample>(va, vb, acc);
+#pragma unroll 2
+            for (int i = lane; i < total; i += 32)
+            {
+                const int y = i / cpr, x = (i - y * cpr) << 4;
+                const uint4 va = maskChunk(load16(pa + (intptr_t)y * sa * B + x), wb - x);
+                const uint4 vb = maskChunk(load16(pb + (intptr_t)y * sb * B + x), wb - x);
+                acc = ssdWords<Sample>(va, vb, acc);
+            }
         }
         acc = hvbWarpSumU(acc);
         if (sizeof(Sample) == 2) acc >>= 4;
@@ -220,6 +259,13 @@ struct HadamardFrag
             for (int r = 0; r < 4; ++r) x[m0][r] = (((r & 1) & t0) ^ ((r >> 1) & g2) ^ (m0 & t1)) ? pat ^ 0xfefefefeu : pat;
     }
 };
+
+// the k-steps of m-tile mt in the order the streaming kernels run them: phase 0 = the two whose products enter negated
+// (((mt >> 1) & ks) ^ (ks >> 1) odd: ks in {2, 3} for mt < 2, {1, 2} otherwise), phase 1 = the other two
+__device__ __forceinline__ constexpr int satdStep(int mt, int phase, int j)
+{
+    return mt < 2 ? (phase == 0 ? 2 + j : j) : (phase == 0 ? 1 + j : 3 * j);
+}
 
 // 8 bytes of a tile row: one 64-bit load when the row is 8-byte aligned, else three aligned words and two funnel shifts
 __device__ __forceinline__ uint2 loadRow8(const uint8_t *p)
@@ -400,15 +446,30 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
         // the four m-tiles' products advance together, k-step by k-step: four independent accumulator chains, so that an
         // IMMA is followed by three that do not wait for it (the ncu capture of the mt-outer order showed `wait` on the
         // dependent chains as the top stall, profiles/r01g_summary.txt)
+        // The A registers of (m-tile mt, k-step ks) are x[mt & 1], negated when ((mt >> 1) & ks) ^ (ks >> 1) is odd.  Instead
+        // of negating four registers per product, the two k-steps of an m-tile whose products enter negated run first, the
+        // accumulators change sign once, and the other two k-steps follow: H x = -(sum over the negated steps) + (the rest).
+        // The four m-tiles advance together, so an IMMA is followed by three that do not wait for it.
         int acc[4][4] = {};
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
+        for (int phase = 0; phase < 2; ++phase)
+        {
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+                {
+                    const int ks = satdStep(mt, phase, j);
+                    imma16832(acc[mt], A.x[mt & 1][0], A.x[mt & 1][1], A.x[mt & 1][2], A.x[mt & 1][3], bx[ks], by[ks]);
+                }
+            if (phase == 0)
             {
-                const uint32_t neg = ((((mt >> 1) & ks) ^ (ks >> 1)) & 1) ? 0xfefefefeu : 0u;
-                imma16832(acc[mt], A.x[mt & 1][0] ^ neg, A.x[mt & 1][1] ^ neg, A.x[mt & 1][2] ^ neg, A.x[mt & 1][3] ^ neg, bx[ks], by[ks]);
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[mt][i] = -acc[mt][i];
             }
+        }
         int s0 = 0, s1 = 0;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
@@ -592,33 +653,40 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
                                __funnelshift_r(v.w, w4[i], qs[0]));
             }
         }
+        // Byte planes of the four rows (high bytes, low bytes), and the order of the products: with N / P the k-steps of an
+        // m-tile that enter negated / as they are (satdStep), the accumulators go through
+        //   N_hi, change sign, P_hi              = P_hi - N_hi
+        //   times -256, N_lo, change sign        = 256 (P_hi - N_hi) - N_lo
+        //   P_lo                                 = sum_k H[m][k] (256 hi_k + lo_k), exact in 32 bits
+        // so no A register is ever negated.
+        uint32_t bxh[4], byh[4], bxl[4], byl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            bxh[i] = __byte_perm(r[i].x, r[i].y, 0x7531u);
+            byh[i] = __byte_perm(r[i].z, r[i].w, 0x7531u);
+            bxl[i] = __byte_perm(r[i].x, r[i].y, 0x6420u);
+            byl[i] = __byte_perm(r[i].z, r[i].w, 0x6420u);
+        }
         int acc[4][4] = {};
 #pragma unroll
-        for (int plane = 1; plane >= 0; --plane)
+        for (int step = 0; step < 4; ++step) // N_hi, P_hi, N_lo, P_lo
         {
-            // byte plane of the four rows: the samples' high bytes first, then (accumulators scaled by 256) their low bytes
-            const unsigned sel = plane ? 0x7531u : 0x6420u;
-            uint32_t bx[4], by[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-            {
-                bx[i] = __byte_perm(r[i].x, r[i].y, sel);
-                by[i] = __byte_perm(r[i].z, r[i].w, sel);
-            }
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
+            for (int j = 0; j < 2; ++j)
 #pragma unroll
                 for (int mt = 0; mt < 4; ++mt)
                 {
-                    const uint32_t neg = ((((mt >> 1) & ks) ^ (ks >> 1)) & 1) ? 0xfefefefeu : 0u;
-                    imma16832(acc[mt], A.x[mt & 1][0] ^ neg, A.x[mt & 1][1] ^ neg, A.x[mt & 1][2] ^ neg, A.x[mt & 1][3] ^ neg, bx[ks], by[ks]);
+                    const int ks = satdStep(mt, step & 1, j);
+                    imma16832(acc[mt], A.x[mt & 1][0], A.x[mt & 1][1], A.x[mt & 1][2], A.x[mt & 1][3], step < 2 ? bxh[ks] : bxl[ks],
+                              step < 2 ? byh[ks] : byl[ks]);
                 }
-            if (plane)
+            if (step < 3)
             {
 #pragma unroll
                 for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[mt][i] *= 256;
+                    for (int i = 0; i < 4; ++i) acc[mt][i] = step == 1 ? acc[mt][i] * -256 : -acc[mt][i];
             }
         }
         int s0 = 0, s1 = 0;

@@ -19,8 +19,8 @@ __device__ __forceinline__ int hvbSatdTile(const SampleA *a, int sa, const Sampl
 #pragma unroll
         for (int y = 0; y < N; ++y)
         {
-            const uint2 va = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(a) + y * sa));
-            const uint2 vb = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(b) + y * sb));
+            const uint2 va = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(a) + y * sa);
+            const uint2 vb = *reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(b) + y * sb);
 #pragma unroll
             for (int x = 0; x < 4; ++x)
             {
@@ -38,15 +38,16 @@ __device__ __forceinline__ int hvbSatdTile(const SampleA *a, int sa, const Sampl
         for (int y = 0; y < N; ++y)
         {
             const uint32_t *pa = reinterpret_cast<const uint32_t *>(a + y * sa), *pb = reinterpret_cast<const uint32_t *>(b + y * sb);
+            // (plain loads: the prediction operand of the fused interpolation + SATD kernel lives in shared memory)
             uint4 va, vb;
             if (!(reinterpret_cast<uintptr_t>(pa) & 15))
-                va = __ldg(reinterpret_cast<const uint4 *>(pa));
+                va = *reinterpret_cast<const uint4 *>(pa);
             else
-                va = make_uint4(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pa + 3));
+                va = make_uint4(pa[0], pa[1], pa[2], pa[3]);
             if (!(reinterpret_cast<uintptr_t>(pb) & 15))
-                vb = __ldg(reinterpret_cast<const uint4 *>(pb));
+                vb = *reinterpret_cast<const uint4 *>(pb);
             else
-                vb = make_uint4(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), __ldg(pb + 3));
+                vb = make_uint4(pb[0], pb[1], pb[2], pb[3]);
             const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
             for (int x = 0; x < 4; ++x)
