@@ -23,14 +23,9 @@ constexpr int kWarpsPerBlock = 8;
 // 16 bytes at an arbitrary byte address: two aligned 128-bit loads and a word funnel.  The alignment is a property of
 // the block (one warp per candidate), so the branches are warp-uniform.  May touch up to 31 bytes past the last byte
 // wanted: picture rows carry that slack (hvb_picture_create).
-__device__ __forceinline__ uint4 load16(const uint8_t *p)
+// bytes sh .. sh + 15 (sh = 1..15) of the 32 bytes (lo, hi)
+__device__ __forceinline__ uint4 funnel16(const uint4 &lo, const uint4 &hi, unsigned sh)
 {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint4 *q = reinterpret_cast<const uint4 *>(a & ~uintptr_t(15));
-    const unsigned sh = (unsigned)(a & 15);
-    const uint4 lo = __ldg(q);
-    if (sh == 0) return lo;
-    const uint4 hi = __ldg(q + 1);
     const unsigned b = (sh & 3) * 8;
     uint32_t w0, w1, w2, w3, w4;
     switch (sh >> 2)
@@ -41,6 +36,16 @@ __device__ __forceinline__ uint4 load16(const uint8_t *p)
     default: w0 = lo.w, w1 = hi.x, w2 = hi.y, w3 = hi.z, w4 = hi.w; break;
     }
     return make_uint4(__funnelshift_r(w0, w1, b), __funnelshift_r(w1, w2, b), __funnelshift_r(w2, w3, b), __funnelshift_r(w3, w4, b));
+}
+
+__device__ __forceinline__ uint4 load16(const uint8_t *p)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint4 *q = reinterpret_cast<const uint4 *>(a & ~uintptr_t(15));
+    const unsigned sh = (unsigned)(a & 15);
+    const uint4 lo = __ldg(q);
+    if (sh == 0) return lo;
+    return funnel16(lo, __ldg(q + 1), sh);
 }
 
 // keep the first `valid` (1..16) bytes of a 16-byte chunk
@@ -83,36 +88,73 @@ __device__ __forceinline__ unsigned ssdWords(uint4 a, uint4 b, unsigned acc)
     return acc;
 }
 
-// Both operands on the 16-byte grid (co-located blocks, or a candidate that happens to be aligned) and rows of 1, 2, 4 or 8
-// whole chunks: the warp's 32 lanes cover 32 / cpr rows per turn, a lane keeps its column, and four turns' loads (eight
-// 128-bit loads per lane) are requested before the first is consumed -- two loads in flight per lane do not cover the
-// HBM latency at full bandwidth.  Returns false when the block does not qualify.
+// Streaming walk of a block pair as 16-byte chunks, `consume(chunk of a, chunk of b)` per chunk.  Rows of 1, 2, 4 or 8 whole
+// chunks (every PU width of 16 bytes and more except the 24- and 48-byte AMP widths) with the first operand on the 16-byte
+// grid -- a source block always is -- take one of two lean loops in which the warp's 32 lanes cover 32 / cpr rows per turn,
+// a lane keeps its column, and the loads of several turns are requested before the first is consumed (two loads in
+// flight per lane do not cover the HBM latency at full bandwidth, and address arithmetic between the loads costs more than
+// the loads):
+//   second operand on the grid too (co-located blocks)        three turns in flight, six 128-bit loads per lane;
+//   second operand anywhere (a motion-search candidate)       a chunk is the five aligned words that contain it and four
+//                                                             funnel shifts; two turns in flight.
+// Everything else (partial chunks, AMP widths, a source off the grid) returns false and takes the caller's general loop.
 template <typename F>
 __device__ __forceinline__ bool alignedChunks(const uint8_t *pa, intptr_t pitchA, const uint8_t *pb, intptr_t pitchB, int wb, int h, int lane, F consume)
 {
     const int cpr = wb >> 4;
-    if (((reinterpret_cast<uintptr_t>(pa) | reinterpret_cast<uintptr_t>(pb) | (uintptr_t)pitchA | (uintptr_t)pitchB | (uintptr_t)wb) & 15) ||
-        (cpr != 1 && cpr != 2 && cpr != 4 && cpr != 8))
+    if (((reinterpret_cast<uintptr_t>(pa) | (uintptr_t)pitchA | (uintptr_t)pitchB | (uintptr_t)wb) & 15) || (cpr != 1 && cpr != 2 && cpr != 4 && cpr != 8))
         return false;
     const int shift = __ffs(cpr) - 1, rowsPerTurn = 32 >> shift;
-    const int x = (lane & (cpr - 1)) << 4;
-    const uint8_t *qa = pa + (intptr_t)(lane >> shift) * pitchA + x, *qb = pb + (intptr_t)(lane >> shift) * pitchB + x;
+    const int x = (lane & (cpr - 1)) << 4, y0 = lane >> shift;
+    const uint8_t *qa = pa + (intptr_t)y0 * pitchA + x, *qb = pb + (intptr_t)y0 * pitchB + x;
     const intptr_t stepA = rowsPerTurn * pitchA, stepB = rowsPerTurn * pitchB;
-    for (int y = lane >> shift; y < h; y += 4 * rowsPerTurn)
+    const unsigned off = (unsigned)(reinterpret_cast<uintptr_t>(pb) & 15);
+    if (off)
     {
-        uint4 va[4], vb[4];
+        // the five aligned words that contain the chunk, funnel-shifted by the byte part of the offset: no word selection
+        // (a switch over the word part costs the compiler four live variants of every chunk)
+        const unsigned bits = (off & 3) * 8;
+        qb -= off & 3;
+#pragma unroll 1
+        for (int y = y0; y < h; y += 2 * rowsPerTurn)
+        {
+            uint4 va[2];
+            uint32_t w[2][5];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < 2; ++k)
+                if (y + k * rowsPerTurn < h)
+                {
+                    va[k] = __ldg(reinterpret_cast<const uint4 *>(qa + k * stepA));
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(qb + k * stepB);
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) w[k][i] = __ldg(q + i);
+                }
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if (y + k * rowsPerTurn < h)
+                    consume(va[k], make_uint4(__funnelshift_r(w[k][0], w[k][1], bits), __funnelshift_r(w[k][1], w[k][2], bits),
+                                              __funnelshift_r(w[k][2], w[k][3], bits), __funnelshift_r(w[k][3], w[k][4], bits)));
+            qa += 2 * stepA;
+            qb += 2 * stepB;
+        }
+        return true;
+    }
+#pragma unroll 1
+    for (int y = y0; y < h; y += 3 * rowsPerTurn)
+    {
+        uint4 va[3], vb[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
             if (y + k * rowsPerTurn < h)
             {
                 va[k] = __ldg(reinterpret_cast<const uint4 *>(qa + k * stepA));
                 vb[k] = __ldg(reinterpret_cast<const uint4 *>(qb + k * stepB));
             }
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 3; ++k)
             if (y + k * rowsPerTurn < h) consume(va[k], vb[k]);
-        qa += 4 * stepA;
-        qb += 4 * stepB;
+        qa += 3 * stepA;
+        qb += 3 * stepB;
     }
     return true;
 }
@@ -129,7 +171,7 @@ __device__ __forceinline__ int sadBlock(const Sample *a, int sa, const Sample *b
     unsigned acc = 0;
     if (alignedChunks(pa, (intptr_t)sa * B, pb, (intptr_t)sb * B, wb, h, lane, [&](const uint4 &va, const uint4 &vb) { acc += sadWords<Sample>(va, vb); }))
         return (int)acc;
-#pragma unroll 2
+#pragma unroll 1
     for (int i = lane; i < total; i += 32)
     {
         const int y = i / cpr, x = (i - y * cpr) << 4;
@@ -141,20 +183,29 @@ __device__ __forceinline__ int sadBlock(const Sample *a, int sa, const Sample *b
 }
 
 template <typename Sample>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
     sadKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out)
 {
     const int lane = threadIdx.x & 31;
     const int warpsTotal = gridDim.x * kWarpsPerBlock;
-    for (int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n; t += warpsTotal)
+    int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (t >= n) return;
+    hvb_metric_task task = tasks[t];
+    for (;;)
     {
-        const hvb_metric_task task = tasks[t];
+        // the next block's task is requested while this block streams: one memory latency per block instead of two
+        const int tn = t + warpsTotal;
+        hvb_metric_task next = task;
+        if (tn < n) next = tasks[tn];
         int sa, sb;
         const Sample *a = hvbBlockPtr<Sample>(planes, task.a, sa);
         const Sample *b = hvbBlockPtr<Sample>(planes, task.b, sb);
         int acc = hvbWarpSum(sadBlock<Sample>(a, sa, b, sb, task.w, task.h, lane));
         if (sizeof(Sample) == 2) acc >>= 2;
         if (lane == 0) out[t] = acc;
+        if (tn >= n) break;
+        task = next;
+        t = tn;
     }
 }
 
@@ -200,15 +251,20 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 }
 
 template <typename Sample>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
     ssdKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, uint32_t *__restrict__ out)
 {
     const int lane = threadIdx.x & 31;
     const int warpsTotal = gridDim.x * kWarpsPerBlock;
     const int B = (int)sizeof(Sample);
-    for (int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n; t += warpsTotal)
+    int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (t >= n) return;
+    hvb_metric_task task = tasks[t];
+    for (;;)
     {
-        const hvb_metric_task task = tasks[t];
+        const int tn = t + warpsTotal; // (the next block's task is requested while this block streams)
+        hvb_metric_task next = task;
+        if (tn < n) next = tasks[tn];
         int sa, sb;
         const uint8_t *pa = reinterpret_cast<const uint8_t *>(hvbBlockPtr<Sample>(planes, task.a, sa));
         const uint8_t *pb = reinterpret_cast<const uint8_t *>(hvbBlockPtr<Sample>(planes, task.b, sb));
@@ -216,7 +272,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
         unsigned acc = 0; // modulo 2^32, like the reference's uint32_t accumulator (havoc/ssd.cpp:28-43)
         if (!alignedChunks(pa, (intptr_t)sa * B, pb, (intptr_t)sb * B, wb, h, lane, [&](const uint4 &va, const uint4 &vb) { acc = ssdWords<Sample>(va, vb, acc); }))
         {
-#pragma unroll 2
+#pragma unroll 1
             for (int i = lane; i < total; i += 32)
             {
                 const int y = i / cpr, x = (i - y * cpr) << 4;
@@ -228,6 +284,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
         acc = hvbWarpSumU(acc);
         if (sizeof(Sample) == 2) acc >>= 4;
         if (lane == 0) out[t] = acc;
+        if (tn >= n) break;
+        task = next;
+        t = tn;
     }
 }
 
@@ -295,7 +354,19 @@ struct SatdCursor
     int t, base, tiles, tilesX, sa, sb;
     unsigned recip; // ceil(2^32 / tilesX): umulhi(tile, recip) = tile / tilesX for tile < 2^16, tilesX > 1
     const uint8_t *a, *b;
+    // blocks 1, 2, 4 or 8 tiles wide made of whole groups: a group is 8 / tilesX tile rows, so a lane's rows of the next group
+    // are its rows of this one plus a constant -- no tile arithmetic after a block's first group
+    bool fast;
+    int dS, dP;          // bytes from a group to the next
+    const uint8_t *S, *P; // this lane's row t of its tile in the NEXT group to be requested (valid once base > 0)
 };
+
+__device__ __forceinline__ void satdCursorFast(SatdCursor &c)
+{
+    c.fast = c.tilesX <= 8 && !(c.tilesX & (c.tilesX - 1)) && !(c.tiles & 7);
+    c.dS = (64 / c.tilesX) * c.sa;
+    c.dP = (64 / c.tilesX) * c.sb;
+}
 
 // position the cursor on the first task at or after c.t (stepping by `step`) that this kernel owns
 __device__ __forceinline__ void satdCursorOpen(SatdCursor &c, const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks,
@@ -314,6 +385,7 @@ __device__ __forceinline__ void satdCursorOpen(SatdCursor &c, const HvbPlane *__
             c.recip = c.tilesX > 1 ? 0xffffffffu / (unsigned)c.tilesX + 1u : 0u;
             c.tiles = c.tilesX * (task.h >> 3);
             c.base = 0;
+            satdCursorFast(c);
             return;
         }
         else
@@ -374,10 +446,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
         if (issue.t < n)
         {
             qb = issue.tiles - issue.base;
-            const int tile = min(issue.base + g, issue.tiles - 1);
-            const int ty = issue.tilesX == 1 ? tile : issue.tiles < 65536 ? (int)__umulhi((unsigned)tile, issue.recip) : tile / issue.tilesX;
-            const int tx = tile - ty * issue.tilesX;
-            const uint8_t *S = issue.a + (intptr_t)(ty * 8 + t) * issue.sa + tx * 8, *P = issue.b + (intptr_t)(ty * 8 + t) * issue.sb + tx * 8;
+            const uint8_t *S, *P;
+            if (issue.fast && issue.base > 0)
+                S = issue.S, P = issue.P;
+            else
+            {
+                const int tile = min(issue.base + g, issue.tiles - 1);
+                const int ty = issue.tilesX == 1 ? tile : issue.tiles < 65536 ? (int)__umulhi((unsigned)tile, issue.recip) : tile / issue.tilesX;
+                const int tx = tile - ty * issue.tilesX;
+                S = issue.a + (intptr_t)(ty * 8 + t) * issue.sa + tx * 8;
+                P = issue.b + (intptr_t)(ty * 8 + t) * issue.sb + tx * 8;
+            }
+            issue.S = S + issue.dS;
+            issue.P = P + issue.dP;
             const uint32_t dst = mineAddr + slot * (kStageWords * 8);
             if (!((reinterpret_cast<uintptr_t>(S) | (uintptr_t)issue.sa) & 7))
             {
@@ -447,35 +528,30 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
         // IMMA is followed by three that do not wait for it (the ncu capture of the mt-outer order showed `wait` on the
         // dependent chains as the top stall, profiles/r01g_summary.txt)
         // The A registers of (m-tile mt, k-step ks) are x[mt & 1], negated when ((mt >> 1) & ks) ^ (ks >> 1) is odd.  Instead
-        // of negating four registers per product, the two k-steps of an m-tile whose products enter negated run first, the
-        // accumulators change sign once, and the other two k-steps follow: H x = -(sum over the negated steps) + (the rest).
-        // The four m-tiles advance together, so an IMMA is followed by three that do not wait for it.
-        int acc[4][4] = {};
+        // of negating four registers per product, the k-steps whose products enter negated accumulate in one register set and
+        // the others in a second one, and the coefficient's absolute value |P - N| is one absolute-difference-and-add.  Two
+        // m-tiles at a time: four independent accumulator chains (an IMMA is followed by three that do not wait for it) in
+        // the sixteen registers one set of all four m-tiles would take.
+        int s0 = 0, s1 = 0;
 #pragma unroll
-        for (int phase = 0; phase < 2; ++phase)
+        for (int pair = 0; pair < 2; ++pair)
         {
+            int accN[2][4] = {}, accP[2][4] = {};
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt)
+                for (int m = 0; m < 2; ++m)
                 {
-                    const int ks = satdStep(mt, phase, j);
-                    imma16832(acc[mt], A.x[mt & 1][0], A.x[mt & 1][1], A.x[mt & 1][2], A.x[mt & 1][3], bx[ks], by[ks]);
+                    const int mt = 2 * pair + m, kn = satdStep(mt, 0, j), kp = satdStep(mt, 1, j);
+                    imma16832(accN[m], A.x[m][0], A.x[m][1], A.x[m][2], A.x[m][3], bx[kn], by[kn]);
+                    imma16832(accP[m], A.x[m][0], A.x[m][1], A.x[m][2], A.x[m][3], bx[kp], by[kp]);
                 }
-            if (phase == 0)
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
             {
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[mt][i] = -acc[mt][i];
+                s0 = __sad(accP[m][0], accN[m][0], __sad(accP[m][2], accN[m][2], (unsigned)s0));
+                s1 = __sad(accP[m][1], accN[m][1], __sad(accP[m][3], accN[m][3], (unsigned)s1));
             }
-        }
-        int s0 = 0, s1 = 0;
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
-        {
-            s0 = __sad(acc[mt][0], 0, __sad(acc[mt][2], 0, (unsigned)s0));
-            s1 = __sad(acc[mt][1], 0, __sad(acc[mt][3], 0, (unsigned)s1));
         }
         // column 2t + (g & 1) of the group, summed over the 8 lanes that share t
         int sum = (g & 1) ? s1 : s0;
@@ -532,6 +608,7 @@ __device__ __forceinline__ void satdCursorOpen16(SatdCursor &c, const HvbPlane *
             c.recip = c.tilesX > 1 ? 0xffffffffu / (unsigned)c.tilesX + 1u : 0u;
             c.tiles = c.tilesX * (task.h >> 3);
             c.base = 0;
+            satdCursorFast(c);
             return;
         }
         leftover[0] = 1; // a block for satdKernel (every lane stores the same value)
@@ -581,10 +658,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
         if (issue.t < n)
         {
             qb = issue.tiles - issue.base;
-            const int tile = min(issue.base + g, issue.tiles - 1);
-            const int ty = issue.tilesX == 1 ? tile : issue.tiles < 65536 ? (int)__umulhi((unsigned)tile, issue.recip) : tile / issue.tilesX;
-            const int tx = tile - ty * issue.tilesX;
-            const uint8_t *S = issue.a + (intptr_t)(ty * 8 + t) * issue.sa + tx * 16, *P = issue.b + (intptr_t)(ty * 8 + t) * issue.sb + tx * 16;
+            const uint8_t *S, *P;
+            if (issue.fast && issue.base > 0)
+                S = issue.S, P = issue.P;
+            else
+            {
+                const int tile = min(issue.base + g, issue.tiles - 1);
+                const int ty = issue.tilesX == 1 ? tile : issue.tiles < 65536 ? (int)__umulhi((unsigned)tile, issue.recip) : tile / issue.tilesX;
+                const int tx = tile - ty * issue.tilesX;
+                S = issue.a + (intptr_t)(ty * 8 + t) * issue.sa + tx * 16;
+                P = issue.b + (intptr_t)(ty * 8 + t) * issue.sb + tx * 16;
+            }
+            issue.S = S + issue.dS;
+            issue.P = P + issue.dP;
             const uint32_t dst = mineAddr + slot * (kStageQuads * 16);
             if (!((reinterpret_cast<uintptr_t>(S) | (uintptr_t)issue.sa) & 15))
             {
