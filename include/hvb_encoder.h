@@ -66,6 +66,19 @@ int hvbenc_intra_sweep(hvbenc *enc, const hvb_intra_sweep_task *task, const void
 int hvbenc_tu_chain(hvbenc *enc, hvb_tu_task *tasks, int n, const hvb_rdoq_ctx *snapshot, const void *const *pred, const intptr_t *pred_stride,
                     void *const *rec, const intptr_t *rec_stride, int16_t *const *levels, hvb_tu_result *out);
 
+/* Cooperative callers.  A thread that multiplexes many callers as fibers (integration/fiber_pool.cpp: the encoder's pool
+ * threads, one per core, each running hundreds of CTU-row tasks) registers how a caller gives the thread up: in place of
+ * the sleep, a waiting call invokes park(arg, done) until *done != 0 (park switches to the scheduler, which resumes the fiber
+ * once *done is set); a session thread calls notify(arg) right after setting *done, so that a scheduler that went to sleep
+ * with nothing runnable can be woken.  Per calling thread; NULL (or park == NULL) restores the blocking wait. */
+typedef struct
+{
+    void (*park)(void *arg, const volatile int *done);
+    void (*notify)(void *arg);
+    void *arg;
+} hvbenc_thread_hooks;
+void hvbenc_set_thread_hooks(const hvbenc_thread_hooks *hooks);
+
 /* counters since creation: tasks and batches per kind, device time.  Written as one JSON object into buf. */
 int hvbenc_stats(hvbenc *enc, char *buf, size_t bytes);
 

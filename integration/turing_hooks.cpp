@@ -97,16 +97,33 @@ int pictureId(const void *key, bool fresh)
     return pic;
 }
 
+namespace {
+thread_local CallerState *tlCaller = nullptr;
+
+CallerState &caller()
+{
+    if (!tlCaller)
+    {
+        static thread_local CallerState *own = new CallerState(); // zero-initialised; lives as long as the thread may run hooks
+        tlCaller = own;
+    }
+    return *tlCaller;
+}
+} // namespace
+
+void setCallerState(CallerState *state)
+{
+    tlCaller = state;
+}
+
 TuMemo &tuMemo()
 {
-    static thread_local TuMemo m = {};
-    return m;
+    return caller().tu;
 }
 
 Memo &memo()
 {
-    static thread_local Memo m = {};
-    return m;
+    return caller().memo;
 }
 
 } // namespace hvbhooks

@@ -50,6 +50,21 @@ struct TuMemo // per-thread: the blocks of the CU being reconstructed, issued to
 };
 TuMemo &tuMemo();
 
+// The memos belong to a CALLER (one CTU row being encoded), not to a thread: integration/fiber_pool.cpp runs many rows per
+// pool thread and switches the caller's state with the fiber.  A thread that runs its tasks directly uses its own.
+struct CallerState
+{
+    Memo memo;
+    TuMemo tu;
+    void clear()
+    {
+        memo.clear();
+        tu.n = 0;
+        tu.active = false;
+    }
+};
+void setCallerState(CallerState *state); // nullptr: back to the calling thread's own
+
 
 
 } // namespace hvbhooks

@@ -31,18 +31,43 @@
 
 namespace {
 
+// A caller waiting for its answer.  Blocking callers (a thread per caller) sleep on the condition variable of their thread's
+// waiter; cooperative callers (hvbenc_set_thread_hooks: fibers multiplexed on a scheduler thread) have a waiter on their own
+// stack, park through the thread's hook and are announced to the scheduler by `notify` -- no futex on either side.
 struct Waiter
 {
     std::mutex m;
     std::condition_variable cv;
-    bool done = false;
+    std::atomic<int> done{0};
     int rc = 0;
+    void (*notify)(void *) = nullptr;
+    void *notifyArg = nullptr;
 };
 
 Waiter &myWaiter()
 {
     static thread_local Waiter w;
     return w;
+}
+
+thread_local hvbenc_thread_hooks tlHooks = {nullptr, nullptr, nullptr};
+
+// the answer is there: last access to a cooperative waiter is the store (it lives on a stack that may unwind right after)
+void complete(Waiter *w)
+{
+    if (w->notify)
+    {
+        void (*const fn)(void *) = w->notify;
+        void *const arg = w->notifyArg;
+        w->done.store(1, std::memory_order_release);
+        fn(arg);
+        return;
+    }
+    {
+        std::lock_guard<std::mutex> g(w->m);
+        w->done.store(1, std::memory_order_release);
+    }
+    w->cv.notify_one();
 }
 
 struct Request
@@ -396,14 +421,7 @@ void dispatch(Engine *enc)
         std::sort(wake.begin(), wake.end());
         wake.erase(std::unique(wake.begin(), wake.end()), wake.end());
         enc->inflight.fetch_sub(answered, std::memory_order_relaxed);
-        for (Waiter *w : wake)
-        {
-            {
-                std::lock_guard<std::mutex> g(w->m);
-                w->done = true;
-            }
-            w->cv.notify_one();
-        }
+        for (Waiter *w : wake) complete(w);
     }
 }
 
@@ -439,9 +457,25 @@ void pollLoop(hvbenc *session)
 
 int waitFor(Waiter &w)
 {
+    if (w.notify)
+    {
+        // cooperative: the scheduler runs other callers on this thread until the answer is there
+        while (!w.done.load(std::memory_order_acquire)) tlHooks.park(tlHooks.arg, reinterpret_cast<const volatile int *>(&w.done));
+        return w.rc;
+    }
     std::unique_lock<std::mutex> lock(w.m);
-    w.cv.wait(lock, [&] { return w.done; });
+    w.cv.wait(lock, [&] { return w.done.load(std::memory_order_acquire) != 0; });
     return w.rc;
+}
+
+// the waiter of this call: the thread's own, or (cooperative callers) `local` on the caller's stack
+Waiter &armWaiter(Waiter &local)
+{
+    Waiter &w = tlHooks.park ? local : myWaiter();
+    w.done.store(0, std::memory_order_relaxed);
+    w.notify = tlHooks.park ? tlHooks.notify : nullptr;
+    w.notifyArg = tlHooks.arg;
+    return w;
 }
 
 // append `count` tasks of a lane; `extra(b, first)` runs under the lock once the room is there
@@ -449,8 +483,8 @@ template <class LaneT, class Task, class Extra>
 int submit(Engine *enc, LaneT &lane, const Task *tasks, int count, void *dst, Extra extra)
 {
     if (!enc || !tasks || count <= 0 || count > lane.capacity) return HVB_ERR_INVALID;
-    Waiter &w = myWaiter();
-    w.done = false;
+    Waiter local;
+    Waiter &w = armWaiter(local);
     enc->inflight.fetch_add(1, std::memory_order_relaxed);
     {
         std::unique_lock<std::mutex> lock(enc->m);
@@ -686,8 +720,8 @@ extern "C" int hvbenc_upload_rects(hvbenc *session, int pic, const hvbenc_rect *
     }
     Clock clock(session, 0);
     Engine *enc = session->pick();
-    Waiter &wt = myWaiter();
-    wt.done = false;
+    Waiter local;
+    Waiter &wt = armWaiter(local);
     enc->inflight.fetch_add(1, std::memory_order_relaxed);
     {
         std::unique_lock<std::mutex> lock(enc->m);
@@ -788,6 +822,11 @@ extern "C" int hvbenc_tu_chain(hvbenc *session, hvb_tu_task *tasks, int n, const
         }
         return true;
     });
+}
+
+extern "C" void hvbenc_set_thread_hooks(const hvbenc_thread_hooks *hooks)
+{
+    tlHooks = hooks ? *hooks : hvbenc_thread_hooks{nullptr, nullptr, nullptr};
 }
 
 extern "C" int hvbenc_stats(hvbenc *session, char *buf, size_t bytes)
