@@ -44,6 +44,26 @@ PATCHES = {
     ],
     "Reconstruct.cpp": [
         ("#include \"Rdoq.h\"\n", AFTER, "#define HVBHOOKS_RECONSTRUCT\n#include \"turing_hooks.hpp\"\n"),
+        # ReconstructIntraBlock::go: residual .. SSD of one intra transform block from the device (prediction stays here)
+        ("        // input picture\n        auto &pictureInput = static_cast<PictureWrap<Sample> &>(*static_cast<StateEncodePicture *>(h)->docket->picture);\n"
+         "        auto sourceSamples = pictureInput(rc.x0, rc.y0, rc.cIdx);\n\n        ALIGN(32, int16_t, resSamplesRawBuffer[32 * 32]);\n", AFTER,
+         "        ALIGN(32, int16_t, hvbIntraLevels[32 * 32]);\n        hvbhooks::IntraTu hvbIntra;\n"
+         "        const bool hvbIntraDone = hvbhooks::intraBlock(h, rc, recSamples.p, (intptr_t)recSamples.stride, nTbS == 4 && rc.cIdx == 0, hvbIntraLevels, hvbIntra);\n"),
+        ("        // subtract prediction from input\n        // review: SIMD optimisations, perhaps integrate into forward transform\n        for (int y = 0; y < nTbS; ++y)\n", REPLACE,
+         "        // subtract prediction from input\n        // review: SIMD optimisations, perhaps integrate into forward transform\n        if (!hvbIntraDone) for (int y = 0; y < nTbS; ++y)\n"),
+        ("        {\n            // forward transform\n            int constexpr bitDepth = 2 * sizeof(Sample) + 6;\n            havoc::table_transform<bitDepth> *table = h;\n", REPLACE,
+         "        if (!hvbIntraDone)\n        {\n            // forward transform\n            int constexpr bitDepth = 2 * sizeof(Sample) + 6;\n            havoc::table_transform<bitDepth> *table = h;\n"),
+        ("        bool cbf;\n\n        {\n            // review: precompute most of this\n", REPLACE,
+         "        bool cbf;\n\n        if (hvbIntraDone)\n        {\n            cbf = hvbIntra.cbf != 0;\n"
+         "            memcpy(quantizedCoefficients.p, hvbIntraLevels, sizeof(int16_t) << (2 * rc.log2TrafoSize));\n        }\n        else\n        {\n            // review: precompute most of this\n"),
+        ("        {\n            havoc::table_inverse_transform_add<Sample> *table = h;\n            auto *inverseTransformAdd = *havoc::get_inverse_transform_add(table, trType, rc.log2TrafoSize);\n\n"
+         "            // inverse transform and add to predicted samples\n", REPLACE,
+         "        if (!hvbIntraDone)\n        {\n            havoc::table_inverse_transform_add<Sample> *table = h;\n            auto *inverseTransformAdd = *havoc::get_inverse_transform_add(table, trType, rc.log2TrafoSize);\n\n"
+         "            // inverse transform and add to predicted samples\n"),
+        ("            backupSSDNoTSkip = stateEncodeSubstream->ssd[rc.cIdx] + ssdFunction(sourceSamples.p, sourceSamples.stride, recSamples.p, recSamples.stride, nTbS, nTbS);\n"
+         "            if (!(checkTSkip && cbf))\n", REPLACE,
+         "            backupSSDNoTSkip = stateEncodeSubstream->ssd[rc.cIdx] + (hvbIntraDone ? hvbIntra.ssd : ssdFunction(sourceSamples.p, sourceSamples.stride, recSamples.p, recSamples.stride, nTbS, nTbS));\n"
+         "            if (!(checkTSkip && cbf))\n"),
         # the root of an inter CU's transform tree: all its blocks in one submission
         ("        stateCodedData->transformTree.word0().split_transform_flag = h[split_transform_flag()];\n\n        Syntax<transform_tree>::go(tt, h);\n", BEFORE,
          "        if (tt.trafoDepth == 0) hvbhooks::prefetchInterCu(h, tt, !!h[split_transform_flag()]);\n"),

@@ -27,6 +27,9 @@ void shutdown()
         char buf[4096];
         if (!hvbenc_stats(gSession, buf, sizeof(buf))) fprintf(stderr, "hvbenc stats: %s\n", buf);
     }
+    // The process is about to end: releasing gigabytes of device pictures and page-locked buffers one by one costs seconds the
+    // driver's own teardown does not (HVB_FAST_EXIT=0 keeps the orderly release, e.g. under a leak checker).
+    if (envInt("HVB_FAST_EXIT", 1)) return;
     hvbenc_destroy(gSession);
     gSession = nullptr;
 }
@@ -40,13 +43,19 @@ bool on()
 
 unsigned enabledMask()
 {
-    static const unsigned value = (unsigned)envInt("HVB_HOOKS", 0x1f);
+    static const unsigned value = (unsigned)envInt("HVB_HOOKS", 0x3f);
     return value;
 }
 
 int intraMinLog2()
 {
     static const int value = envInt("HVB_INTRA_MIN_LOG2", 2);
+    return value;
+}
+
+int intraTuMinLog2()
+{
+    static const int value = envInt("HVB_INTRA_TU_MIN_LOG2", 4);
     return value;
 }
 

@@ -454,6 +454,56 @@ template <class H> void prefetchInterCu(H &h, transform_tree const &tt, bool spl
     issueInterBlocks(h, blocks, n);
 }
 
+// ---- a transform block of an intra candidate (ReconstructIntraBlock::go, turing/Reconstruct.cpp:249-356) ---------------------
+// The prediction has been written to the block's piece of the reconstruction cache by the reference's own code (it needs
+// the neighbours the previous block of the same candidate reconstructed); residual, forward transform, RDOQ + sign hiding or
+// plain quantisation, dequantisation, inverse transform + add (in place, as the reference does) and the SSD come back from
+// the device.  Profile of the reference on the bench's job: this chain -- its scalar RDOQ above all -- is the largest single
+// consumer of host time (profiles/r02f_host_profile.txt), and a block of 16x16 or more costs the host more than a hand-over.
+struct IntraTu
+{
+    uint32_t ssd;
+    int cbf;
+};
+
+template <class H, class Sample>
+bool intraBlock(H &h, residual_coding const &rc, Sample *samples, intptr_t stride, int trType, int16_t *levels, IntraTu &out)
+{
+    if (!usable(h) || !(enabledMask() & 32)) return false;
+    if (rc.log2TrafoSize < intraTuMinLog2() || rc.log2TrafoSize > 5) return false;
+    if (rc.log2TrafoSize == 2 && h[transform_skip_enabled_flag()]) return false; // transform skip is decided on the host (:384-...)
+    StateEncode *stateEncode = h;
+    QpState *qpState = h;
+    auto const &entry = qpState->lookup(rc.cIdx);
+    const int bitDepth = rc.cIdx ? h[BitDepthC()] : h[BitDepthY()];
+    hvb_tu_task t;
+    memset(&t, 0, sizeof(t));
+    t.src.pic = (int16_t)inputPicture(h);
+    t.src.cIdx = (int16_t)rc.cIdx;
+    t.src.x = (int16_t)(rc.x0 >> (rc.cIdx ? 1 : 0));
+    t.src.y = (int16_t)(rc.y0 >> (rc.cIdx ? 1 : 0));
+    t.log2n = (int8_t)rc.log2TrafoSize;
+    t.trType = (int8_t)trType;
+    t.cIdx = (int8_t)rc.cIdx;
+    t.flags = (int8_t)((stateEncode->rdoq ? 1 : 0) | 2 | (h[sign_data_hiding_enabled_flag()] ? 4 : 0));
+    t.qscale = entry.quantiseScale;
+    t.qshift = entry.quantizeShift - rc.log2TrafoSize;
+    t.qoffset = entry.offsetQuantiseShifted;
+    t.iqscale = entry.scale;
+    t.iqshift = rc.log2TrafoSize - 1 + bitDepth - 8;
+    t.scanIdx = (int8_t)h[scanIdx()];
+    hvb_rdoq_ctx snapshot;
+    if (stateEncode->rdoq) snapshotContexts(*static_cast<Contexts *>(h), static_cast<StateEncodePicture *>(h)->lambda, snapshot);
+    const void *pred = samples;
+    void *rec = samples;
+    hvb_tu_result result;
+    const int rcode = hvbenc_tu_chain(sessionOf(h), &t, 1, stateEncode->rdoq ? &snapshot : nullptr, &pred, &stride, &rec, &stride, &levels, &result);
+    if (rcode) fatal("hvbenc_tu_chain(intra)", rcode);
+    out.ssd = result.ssd;
+    out.cbf = result.cbf;
+    return true;
+}
+
 #endif // HVBHOOKS_RECONSTRUCT
 
 // ---- pictures ------------------------------------------------------------------------------------------------------

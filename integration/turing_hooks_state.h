@@ -13,7 +13,8 @@ hvbenc *session(int bytesPerSample, int bitDepth, int width, int height); // cre
 int pictureId(const void *key, bool fresh);
 void fatal(const char *what, int rc);
 int intraMinLog2();                                              // HVB_INTRA_MIN_LOG2 (default 2): smallest partition whose sweep goes to the device
-unsigned enabledMask();                                           // HVB_HOOKS: bit 0 me, 1 bi, 2 pu cost, 3 intra, 4 tu
+unsigned enabledMask();                                           // HVB_HOOKS: bit 0 me, 1 bi, 2 pu cost, 3 intra sweep, 4 inter tu, 5 intra tu
+int intraTuMinLog2();                                            // HVB_INTRA_TU_MIN_LOG2 (default 4): smallest intra transform block whose chain goes to the device
 // Size thresholds: a block below them stays with the reference's own body (its CPU havoc tables), because a hand-over costs
 // more host time than the block's arithmetic does there; results are bit-exact either way, so the bitstream cannot tell.
 int meMinArea();                                                 // HVB_ME_MIN_AREA: smallest PU (w*h) whose uni / bi search goes to the device

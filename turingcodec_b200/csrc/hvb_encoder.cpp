@@ -28,6 +28,10 @@
 #include <thread>
 #include <unordered_map>
 #include <vector>
+#include <time.h>
+#ifdef __linux__
+#include <sys/prctl.h>
+#endif
 
 namespace {
 
@@ -225,15 +229,52 @@ struct hvbenc
     std::condition_variable pollCv;
     std::vector<Engine *> watching;
     bool pollStop = false;
+    int pollSleepUs = 20; // HVB_POLL_SLEEP_US; 0: spin
 
     // per kind: requests and the time from hand-over to wake-up (ns), for the statistics
     std::atomic<int64_t> waitNs[6], waitCount[6];
 
-    Engine *pick()
+    // Engines by kind (0 uploads, 1 me, 2 bi, 3 pu cost, 4 intra sweep, 5 transform blocks).  A batch is issued on one
+    // stream in a fixed order, so a sweep (tens of microseconds on the device) that shares a batch with a motion search waits
+    // for the search; with enough engines (HVB_ENGINES >= 12) every kind gets its own group of engines -- first[k] .. first[k+1]
+    // -- in proportion to its share of the device time of a 4K medium encode (HVB_ENGINE_SHARES overrides), and kernels of
+    // different kinds overlap on the device.  With fewer engines every engine serves every kind.
+    int first[7] = {0, 0, 0, 0, 0, 0, 0};
+    bool partitioned = false;
+
+    void partition()
     {
-        Engine *best = engines[0];
+        const int n = (int)engines.size();
+        double share[6] = {2, 6, 7, 3, 5, 9};
+        if (const char *v = getenv("HVB_ENGINE_SHARES")) sscanf(v, "%lf,%lf,%lf,%lf,%lf,%lf", &share[0], &share[1], &share[2], &share[3], &share[4], &share[5]);
+        partitioned = n >= 12;
+        if (const char *v = getenv("HVB_ENGINE_PARTITION")) partitioned = atoi(v) != 0 && n >= 6;
+        if (!partitioned) return;
+        double total = 0, acc = 0;
+        for (double v : share) total += v;
+        int count[6], used = 0;
+        for (int k = 0; k < 6; ++k) count[k] = 1, ++used;
+        // largest remainder over what is left after one engine each
+        double want[6];
+        for (int k = 0; k < 6; ++k) want[k] = share[k] / total * n - 1;
+        while (used < n)
+        {
+            int best = 0;
+            for (int k = 1; k < 6; ++k)
+                if (want[k] - (count[k] - 1) > want[best] - (count[best] - 1)) best = k;
+            ++count[best], ++used;
+        }
+        (void)acc;
+        for (int k = 0; k < 6; ++k) first[k + 1] = first[k] + count[k];
+    }
+
+    Engine *pick(int kind)
+    {
+        size_t lo = 0, hi = engines.size();
+        if (partitioned) lo = (size_t)first[kind], hi = (size_t)first[kind + 1];
+        Engine *best = engines[lo];
         int load = best->inflight.load(std::memory_order_relaxed);
-        for (size_t i = 1; i < engines.size() && load > 0; ++i)
+        for (size_t i = lo + 1; i < hi && load > 0; ++i)
         {
             const int l = engines[i]->inflight.load(std::memory_order_relaxed);
             if (l < load) best = engines[i], load = l;
@@ -427,6 +468,9 @@ void dispatch(Engine *enc)
 
 void pollLoop(hvbenc *session)
 {
+#ifdef __linux__
+    prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0); // 1 us: the default 50 us slack would triple the sleep below
+#endif
     std::vector<Engine *> snapshot;
     for (;;)
     {
@@ -436,10 +480,12 @@ void pollLoop(hvbenc *session)
             if (session->pollStop && session->watching.empty()) return;
             snapshot = session->watching;
         }
+        bool any = false;
         for (Engine *e : snapshot)
         {
             const int r = hvb_poll(e->ctx);
             if (!r) continue;
+            any = true;
             {
                 std::lock_guard<std::mutex> g(session->pollM);
                 auto &w = session->watching;
@@ -451,7 +497,15 @@ void pollLoop(hvbenc *session)
             }
             e->doneCv.notify_one();
         }
-        std::this_thread::yield();
+        // nothing finished in this sweep: give the core away for a moment (a batch is on the device for 50 .. 500 us; the
+        // encoder's own threads need the core more than the sweep needs the last 20 us of latency)
+        if (any || session->pollSleepUs <= 0)
+            std::this_thread::yield();
+        else
+        {
+            timespec ts = {0, session->pollSleepUs * 1000L};
+            nanosleep(&ts, nullptr);
+        }
     }
 }
 
@@ -596,18 +650,24 @@ extern "C" int hvbenc_create(int device, int bytes_per_sample, int bit_depth, in
 {
     if (!out || pool_pictures < 2 || pool_pictures > 900) return HVB_ERR_INVALID;
     *out = nullptr;
+    // every engine has its own stream; the driver maps streams onto this many hardware queues (default 8), and streams that
+    // share a queue serialise.  Only effective before the process's first CUDA call, and never overrides the user's value.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int nEngines = 8;
-    if (const char *v = getenv("HVB_ENGINES")) nEngines = std::max(1, std::min(32, atoi(v)));
+    if (const char *v = getenv("HVB_ENGINES")) nEngines = std::max(1, std::min(64, atoi(v)));
     hvbenc *enc = new hvbenc;
     enc->bps = bytes_per_sample;
     for (int k = 0; k < 6; ++k) enc->waitNs[k] = 0, enc->waitCount[k] = 0;
     int rc = 0;
+    const auto tStart = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - tStart).count(); };
     for (int e = 0; e < nEngines && !rc; ++e)
     {
         Engine *engine = nullptr;
         rc = createEngine(device, bytes_per_sample, bit_depth, width, height, &engine);
         if (engine) enc->engines.push_back(engine);
     }
+    const double tEngines = since();
     // the pictures: owned by engine 0, imported by the others in the same order, so an id means the same picture everywhere
     enc->slots.resize(pool_pictures);
     for (int i = 0; i < pool_pictures && !rc; ++i)
@@ -620,14 +680,20 @@ extern "C" int hvbenc_create(int device, int bytes_per_sample, int bit_depth, in
             if (!rc && id != enc->slots[i].pic) rc = HVB_ERR_INVALID;
         }
     }
+    const double tPictures = since();
     for (size_t e = 0; e < enc->engines.size() && !rc; ++e) rc = equipEngine(enc->engines[e]);
+    if (getenv("HVB_STATS") && atoi(getenv("HVB_STATS")))
+        fprintf(stderr, "hvbenc set-up: %d contexts %.3f s, %d pictures %.3f s, page-locked buffers %.3f s\n", nEngines, tEngines, pool_pictures,
+                tPictures - tEngines, since() - tPictures);
     if (rc)
     {
         fprintf(stderr, "hvbenc_create failed (%d): %s\n", rc, enc->engines.empty() ? "no engine" : hvb_last_error(enc->engines.back()->ctx));
         hvbenc_destroy(enc);
         return rc;
     }
+    enc->partition();
     if (const char *v = getenv("HVB_POLLER")) enc->usePoller = atoi(v) != 0;
+    if (const char *v = getenv("HVB_POLL_SLEEP_US")) enc->pollSleepUs = atoi(v);
     enc->poller = std::thread(pollLoop, enc);
     for (Engine *engine : enc->engines)
     {
@@ -719,7 +785,7 @@ extern "C" int hvbenc_upload_rects(hvbenc *session, int pic, const hvbenc_rect *
         return HVB_OK;
     }
     Clock clock(session, 0);
-    Engine *enc = session->pick();
+    Engine *enc = session->pick(0);
     Waiter local;
     Waiter &wt = armWaiter(local);
     enc->inflight.fetch_add(1, std::memory_order_relaxed);
@@ -753,7 +819,7 @@ extern "C" int hvbenc_me(hvbenc *session, const hvb_me_task *task, hvb_me_result
 {
     if (!session) return HVB_ERR_INVALID;
     Clock clock(session, 1);
-    Engine *enc = session->pick();
+    Engine *enc = session->pick(1);
     return submit(enc, enc->me, task, 1, out, [](int, int) { return true; });
 }
 
@@ -761,7 +827,7 @@ extern "C" int hvbenc_me_bi(hvbenc *session, const hvb_me_bi_task *task, hvb_me_
 {
     if (!session) return HVB_ERR_INVALID;
     Clock clock(session, 2);
-    Engine *enc = session->pick();
+    Engine *enc = session->pick(2);
     return submit(enc, enc->bi, task, 1, out, [](int, int) { return true; });
 }
 
@@ -769,7 +835,7 @@ extern "C" int hvbenc_pu_cost(hvbenc *session, const hvb_pu_cost_task *tasks, in
 {
     if (!session) return HVB_ERR_INVALID;
     Clock clock(session, 3);
-    Engine *enc = session->pick();
+    Engine *enc = session->pick(3);
     return submit(enc, enc->pu, tasks, n, out, [](int, int) { return true; });
 }
 
@@ -777,7 +843,7 @@ extern "C" int hvbenc_intra_sweep(hvbenc *session, const hvb_intra_sweep_task *t
 {
     if (!session || !task || !neighbours || task->log2n < 2 || task->log2n > 5) return HVB_ERR_INVALID;
     Clock clock(session, 4);
-    Engine *enc = session->pick();
+    Engine *enc = session->pick(4);
     const size_t count = (size_t)(4 << task->log2n) + 1, room = (count + 15) & ~size_t(15);
     return submit(enc, enc->intra, task, 1, out, [&](int b, int first) {
         if (first < 0) return enc->poolUsed[b] + room <= kPoolSamples;
@@ -796,7 +862,7 @@ extern "C" int hvbenc_tu_chain(hvbenc *session, hvb_tu_task *tasks, int n, const
 {
     if (!session || !tasks || n <= 0 || !pred || !pred_stride || !rec || !rec_stride || !levels || !out) return HVB_ERR_INVALID;
     Clock clock(session, 5);
-    Engine *enc = session->pick();
+    Engine *enc = session->pick(5);
     return submit(enc, enc->tu, tasks, n, out, [&](int b, int first) {
         if (first < 0) return !snapshot || enc->nSnapshots[b] < kRdoqSnapshots;
         int snap = 0;

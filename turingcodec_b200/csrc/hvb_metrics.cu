@@ -88,8 +88,9 @@ __device__ __forceinline__ unsigned ssdWords(uint4 a, uint4 b, unsigned acc)
     return acc;
 }
 
-// Streaming walk of a block pair as 16-byte chunks, `consume(chunk of a, chunk of b)` per chunk.  Rows of 1, 2, 4 or 8 whole
-// chunks (every PU width of 16 bytes and more except the 24- and 48-byte AMP widths) with the first operand on the 16-byte
+// Streaming walk of a block pair as 16-byte chunks, `consume(chunk of a, chunk of b)` per chunk.  Rows of 4 or 8 whole
+// chunks (64- and 128-byte rows; narrower blocks measured slower here than in the general loop -- B200 call 11: 32x32 8-bit
+// 51 % / 31 % of the HBM peak co-located / as a search candidate against 60 % / 49 %) with the first operand on the 16-byte
 // grid -- a source block always is -- take one of two lean loops in which the warp's 32 lanes cover 32 / cpr rows per turn,
 // a lane keeps its column, and the loads of several turns are requested before the first is consumed (two loads in
 // flight per lane do not cover the HBM latency at full bandwidth, and address arithmetic between the loads costs more than
@@ -102,7 +103,7 @@ template <typename F>
 __device__ __forceinline__ bool alignedChunks(const uint8_t *pa, intptr_t pitchA, const uint8_t *pb, intptr_t pitchB, int wb, int h, int lane, F consume)
 {
     const int cpr = wb >> 4;
-    if (((reinterpret_cast<uintptr_t>(pa) | (uintptr_t)pitchA | (uintptr_t)pitchB | (uintptr_t)wb) & 15) || (cpr != 1 && cpr != 2 && cpr != 4 && cpr != 8))
+    if (((reinterpret_cast<uintptr_t>(pa) | (uintptr_t)pitchA | (uintptr_t)pitchB | (uintptr_t)wb) & 15) || (cpr != 4 && cpr != 8))
         return false;
     const int shift = __ffs(cpr) - 1, rowsPerTurn = 32 >> shift;
     const int x = (lane & (cpr - 1)) << 4, y0 = lane >> shift;
@@ -171,7 +172,7 @@ __device__ __forceinline__ int sadBlock(const Sample *a, int sa, const Sample *b
     unsigned acc = 0;
     if (alignedChunks(pa, (intptr_t)sa * B, pb, (intptr_t)sb * B, wb, h, lane, [&](const uint4 &va, const uint4 &vb) { acc += sadWords<Sample>(va, vb); }))
         return (int)acc;
-#pragma unroll 1
+#pragma unroll 2
     for (int i = lane; i < total; i += 32)
     {
         const int y = i / cpr, x = (i - y * cpr) << 4;
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
         unsigned acc = 0; // modulo 2^32, like the reference's uint32_t accumulator (havoc/ssd.cpp:28-43)
         if (!alignedChunks(pa, (intptr_t)sa * B, pb, (intptr_t)sb * B, wb, h, lane, [&](const uint4 &va, const uint4 &vb) { acc = ssdWords<Sample>(va, vb, acc); }))
         {
-#pragma unroll 1
+#pragma unroll 2
             for (int i = lane; i < total; i += 32)
             {
                 const int y = i / cpr, x = (i - y * cpr) << 4;
