@@ -64,6 +64,10 @@ int hvb_sync(hvb_context *ctx);
  * blocks and may be called from any thread (a completion thread that serves several contexts without parking a core
  * per context inside the driver's wait). */
 int hvb_poll(hvb_context *ctx);
+/* Completion without driver calls: after everything enqueued on the context so far has completed (its effects visible to the
+ * host), `value` is stored to *flag, which must lie in memory from hvb_host_alloc.  A completion thread that watches many
+ * contexts reads flags instead of querying streams (each query takes the driver's lock, which the launching threads need). */
+int hvb_signal(hvb_context *ctx, int32_t *flag, int32_t value);
 /* Device-side stopwatch: hvb_mark records a timestamp on the context's stream (slot 0..15, events created on first use);
  * hvb_elapsed_ms gives the device time between two recorded slots once the work between them has completed. */
 int hvb_mark(hvb_context *ctx, int slot);
@@ -87,6 +91,10 @@ int hvb_host_free(hvb_context *ctx, void *ptr);
  * (cp.async.bulk.tensor over per-plane tensor maps) instead of the load/store path; same results.  Default: off, or the
  * value of HVB_TMA in the environment.  Pictures must own device memory (not hvb_picture_wrap). */
 int hvb_set_tma(hvb_context *ctx, int on);
+/* hvb_tu_chain_batch has two forms with identical results: staged kernels sized for whole frames, and one launch with a warp per
+ * block for callers that wait for a few blocks (the batched encoder).  Batches of at most `blocks` blocks take the second
+ * (default 256, HVB_TU_FUSED_MAX in the environment; 0: always the staged form). */
+int hvb_set_tu_fused_max(hvb_context *ctx, int blocks);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t hvb_launch_count(hvb_context *ctx);
 /* 1 when the device is present and kernels for it are in this binary */

@@ -148,6 +148,20 @@ static void chain(const HvbPlane *planes, int16_t *pool, int poolCount, const hv
                                                                        chunkBase.data()); });
     emuLaunch(grid, kWarps * 32, [&] { tuBackKernel<Sample>(planes, pool, tasks, n, out, bitDepth); });
 }
+template <typename Sample>
+static void fusedChain(const HvbPlane *planes, int16_t *pool, int poolCount, const hvb_rdoq_ctx *rdoqCtx, int nCtx, const hvb_tu_task *tasks, int n,
+                       hvb_tu_result *out, int bitDepth, int grid)
+{
+    RdoqTables tables(rdoqCtx, nCtx);
+    emuLaunch(std::min(n, grid), 32, [&] { tuFusedKernel<Sample>(planes, pool, rdoqCtx, tasks, n, out, bitDepth, nCtx, (unsigned)poolCount,
+                                                                  tables.bits.data(), tables.last.data()); });
+}
+extern "C" void emu_tu_chain_fused(const HvbPlane *planes, int16_t *pool, int poolCount, const hvb_rdoq_ctx *rdoqCtx, int nCtx, const hvb_tu_task *tasks,
+                                   int n, hvb_tu_result *out, int bitDepth, int bps, int grid)
+{
+    if (bps == 1) fusedChain<uint8_t>(planes, pool, poolCount, rdoqCtx, nCtx, tasks, n, out, bitDepth, grid);
+    else fusedChain<uint16_t>(planes, pool, poolCount, rdoqCtx, nCtx, tasks, n, out, bitDepth, grid);
+}
 extern "C" void emu_tu_chain(const HvbPlane *planes, int16_t *pool, int poolCount, const hvb_rdoq_ctx *rdoqCtx, int nCtx, const hvb_tu_task *tasks,
                              int n, hvb_tu_result *out, int bitDepth, int bps, int grid)
 {
@@ -441,11 +455,16 @@ class EmuContext:
                                          _ptr(cbf), self.bit_depth, GRID)
         return cbf
 
+    def set_tu_fused_max(self, blocks: int):
+        self.tu_fused_max = int(blocks)
+
     def tu_chain(self, tasks, **_):
         t = self._tasks(tasks, hvb.tu_task_t)
         out = np.zeros(t.size, hvb.tu_result_t)
-        kernels_of("hvb_tu.cu").emu_tu_chain(self._planes(), _ptr(self.coeff_pool), self.coeff_pool.size, _ptr(self.rdoq_ctx), self.rdoq_ctx.size,
-                                             _ptr(t), t.size, _ptr(out), self.bit_depth, self.bps, GRID)
+        lib = kernels_of("hvb_tu.cu")
+        entry = lib.emu_tu_chain_fused if t.size <= getattr(self, "tu_fused_max", 256) else lib.emu_tu_chain  # as hvb_tu_chain_batch chooses
+        entry(self._planes(), _ptr(self.coeff_pool), self.coeff_pool.size, _ptr(self.rdoq_ctx), self.rdoq_ctx.size,
+              _ptr(t), t.size, _ptr(out), self.bit_depth, self.bps, GRID)
         return out
 
     def me_search(self, tasks, **_):

@@ -29,6 +29,7 @@ using std::min;
 @STRUCTS@
 static inline int hvbClip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 static inline void __syncthreads() {}
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); } // one fiber runs at a time; the host side reads after the launch returns
 static inline int atomicAdd(int *p, int v) { const int old = *p; *p += v; return old; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long old = *p; *p += v; return old; }
 static const uint3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0};

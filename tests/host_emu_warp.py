@@ -177,6 +177,7 @@ extern "C" void emu_set_schedule(int mode, unsigned seed) { emu::scheduleMode = 
 // ---- warp and block primitives ------------------------------------------------------------------------------------------
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warpRendezvous(mask); }
 static inline void __syncthreads() { emu::blockRendezvous(); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); } // one fiber runs at a time; the host side reads after the launch returns
 static inline int __shfl_sync(unsigned mask, int v, int src) { return (int)emu::exchange(mask, (uint32_t)v, src); }
 static inline unsigned __shfl_sync(unsigned mask, unsigned v, int src) { return emu::exchange(mask, v, src); }
 static inline int __shfl_xor_sync(unsigned mask, int v, int m) { return (int)emu::exchange(mask, (uint32_t)v, (emu::current & 31) ^ m); }

@@ -53,9 +53,10 @@ def test_intra_satd35_sweep(scene, oracle, derive_filtered):
     pred_intra.test_intra_satd35_sweep(scene, oracle, derive_filtered)
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["staged", "fused"])
 @pytest.mark.parametrize("use_rdoq", [False, True])
-def test_tu_chain(scene, oracle, use_rdoq):
-    tu.test_tu_chain(scene, oracle, use_rdoq)
+def test_tu_chain(scene, oracle, use_rdoq, fused):
+    tu.test_tu_chain(scene, oracle, use_rdoq, fused)
 
 
 def test_pu_cost_matches_oracle_and_reference(scene, oracle):

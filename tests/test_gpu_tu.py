@@ -169,8 +169,11 @@ def sad_quadrants(src, pred):
     return [int(d[:h, :h].sum()), int(d[:h, h:].sum()), int(d[h:, :h].sum()), int(d[h:, h:].sum())]
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["staged", "fused"])
 @pytest.mark.parametrize("use_rdoq", [False, True])
-def test_tu_chain(scene, oracle, use_rdoq):
+def test_tu_chain(scene, oracle, use_rdoq, fused):
+    """both forms of hvb_tu_chain_batch: the staged kernels (whole frames) and the one-launch form (a warp per block, small batches)"""
+    scene.ctx.set_tu_fused_max(1 << 20 if fused else 0)
     rng = np.random.default_rng(44 + use_rdoq)
     cells = [(cx, cy) for cy in range(0, H - 31, 32) for cx in range(0, W - 31, 32)]
     n_ctx = 6

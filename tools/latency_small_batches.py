@@ -60,11 +60,13 @@ intra = fp.intra
 for log2n in (5, 4, 3):
     sweep("intra_sweep", f"{1 << log2n}x{1 << log2n}", ctx.intra_satd35, intra[intra["log2n"] == log2n], 140)
 tu = fp.tu
-for log2n in (5, 4, 3):
-    sel = tu[(tu["log2n"] == log2n) & (tu["cIdx"] == 0)]
-    sweep("tu_chain", f"{1 << log2n}x{1 << log2n} luma rdoq+sdh", ctx.tu_chain, sel, hvb.tu_result_t.itemsize)
-    plain = sel.copy()
-    plain["flags"] &= -2
-    sweep("tu_chain", f"{1 << log2n}x{1 << log2n} luma plain", ctx.tu_chain, plain, hvb.tu_result_t.itemsize)
+for form, fused_max in (("staged", 0), ("fused", 1 << 20)):
+    ctx.set_tu_fused_max(fused_max)
+    for log2n in (5, 4, 3):
+        sel = tu[(tu["log2n"] == log2n) & (tu["cIdx"] == 0)]
+        sweep("tu_chain", f"{form} {1 << log2n}x{1 << log2n} rdoq+sdh", ctx.tu_chain, sel, hvb.tu_result_t.itemsize)
+        plain = sel.copy()
+        plain["flags"] &= -2
+        sweep("tu_chain", f"{form} {1 << log2n}x{1 << log2n} plain", ctx.tu_chain, plain, hvb.tu_result_t.itemsize)
 if "--json" in sys.argv:
     Path(sys.argv[sys.argv.index("--json") + 1]).write_text(json.dumps(rows))

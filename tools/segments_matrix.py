@@ -23,7 +23,7 @@ for spec in sys.argv[2:]:
     tag, parallel, threads, envs = (spec.split(":") + [""])[:4]
     env = dict(os.environ, HVB_STATS="1", HVB_PROFILE="0")
     env["LD_LIBRARY_PATH"] = str(encoder.LIB_DIR) + ":" + env.get("LD_LIBRARY_PATH", "")
-    env.update(dict(kv.split("=", 1) for kv in envs.split(",") if kv))
+    env.update(dict(kv.split("=", 1) for kv in re.split(r",(?=[A-Z_0-9]+=)", envs) if kv))
     bit = tmp / "out.bit"
     cmd = [str(encoder.SEGMENTS), "--parallel-segments", parallel, "--clip-frames", str(CLIP), "--input-res", f"{W}x{H}", "--frame-rate", "30",
            "--frames", str(FRAMES), "--threads", threads, "-o", str(bit), *encoder.MEDIUM, "--concurrent-frames", "8", "--segment", str(SEG),

@@ -5,6 +5,9 @@
 // (turing/encode.cpp:363-451 copies planes into PictureWrap) and padded reconstructed pictures
 // (turing/StatePictures.h:154-156, Padding.h) living in HBM.
 #include "hvb_internal.cuh"
+#include <mutex>
+#include <utility>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -86,6 +89,7 @@ extern "C" int hvb_create(int device, int bytes_per_sample, int bit_depth, hvb_c
     }
     ctx->smCount = sms;
     ctx->useTma = hvbEnvTma();
+    if (const char *v = getenv("HVB_TU_FUSED_MAX")) ctx->tuFusedMax = atoi(v) < 0 ? 0 : atoi(v);
     ctx->stream = ctx->ownStream;
     *out = ctx;
     return HVB_OK;
@@ -172,6 +176,23 @@ extern "C" int hvb_set_tma(hvb_context *ctx, int on)
     return HVB_OK;
 }
 
+namespace {
+__global__ void signalKernel(volatile int32_t *flag, int32_t value)
+{
+    __threadfence_system(); // everything the stream did before is visible to the host before the flag is
+    *flag = value;
+}
+} // namespace
+
+extern "C" int hvb_signal(hvb_context *ctx, int32_t *flag, int32_t value)
+{
+    HVB_CHECK_ARGS(ctx, flag);
+    cudaSetDevice(ctx->device);
+    signalKernel<<<1, 1, 0, ctx->stream>>>(flag, value);
+    HVB_LAUNCH_CHECK(ctx, "signalKernel");
+    return HVB_OK;
+}
+
 extern "C" int hvb_poll(hvb_context *ctx)
 {
     if (!ctx) return HVB_ERR_INVALID;
@@ -184,6 +205,13 @@ extern "C" int hvb_poll(hvb_context *ctx)
         if (e != cudaSuccess) return HVB_ERR_CUDA; // (lastError is the owning thread's to write)
     }
     return 1;
+}
+
+extern "C" int hvb_set_tu_fused_max(hvb_context *ctx, int blocks)
+{
+    HVB_CHECK_ARGS(ctx, blocks >= 0);
+    ctx->tuFusedMax = blocks;
+    return HVB_OK;
 }
 
 extern "C" int hvb_set_pipelined(hvb_context *ctx, int on)
@@ -235,18 +263,40 @@ bool hvbEnvTma()
 
 extern "C" int64_t hvb_launch_count(hvb_context *ctx) { return ctx ? ctx->launches : 0; }
 
+// Page-locked ranges handed out by hvb_host_alloc: hvbIsPinned answers for them without asking the driver (every driver
+// call takes the context's lock, and a session with dozens of engines lives on that lock's throughput).
+namespace {
+std::mutex gPinnedMutex;
+std::vector<std::pair<uintptr_t, size_t>> gPinned;
+} // namespace
+
 extern "C" int hvb_host_alloc(hvb_context *ctx, size_t bytes, void **out)
 {
     HVB_CHECK_ARGS(ctx, out && bytes > 0);
     cudaSetDevice(ctx->device);
     *out = nullptr;
-    return hvbCuda(ctx, cudaHostAlloc(out, bytes, cudaHostAllocPortable | cudaHostAllocMapped), "hvb_host_alloc");
+    const int rc = hvbCuda(ctx, cudaHostAlloc(out, bytes, cudaHostAllocPortable | cudaHostAllocMapped), "hvb_host_alloc");
+    if (!rc)
+    {
+        std::lock_guard<std::mutex> g(gPinnedMutex);
+        gPinned.emplace_back(reinterpret_cast<uintptr_t>(*out), bytes);
+    }
+    return rc;
 }
 
 extern "C" int hvb_host_free(hvb_context *ctx, void *ptr)
 {
     HVB_CHECK_ARGS(ctx, ptr);
     cudaSetDevice(ctx->device);
+    {
+        std::lock_guard<std::mutex> g(gPinnedMutex);
+        for (size_t i = 0; i < gPinned.size(); ++i)
+            if (gPinned[i].first == reinterpret_cast<uintptr_t>(ptr))
+            {
+                gPinned.erase(gPinned.begin() + i);
+                break;
+            }
+    }
     return hvbCuda(ctx, cudaFreeHost(ptr), "hvb_host_free");
 }
 
@@ -619,6 +669,13 @@ extern "C" int hvb_rdoq_contexts_upload(hvb_context *ctx, const hvb_rdoq_ctx *sn
 
 bool hvbIsPinned(const void *p)
 {
+    if (p)
+    {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        std::lock_guard<std::mutex> g(gPinnedMutex);
+        for (const auto &r : gPinned)
+            if (a >= r.first && a - r.first < r.second) return true;
+    }
     cudaPointerAttributes attr;
     if (!p || cudaPointerGetAttributes(&attr, p) != cudaSuccess)
     {

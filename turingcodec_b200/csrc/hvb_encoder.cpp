@@ -162,6 +162,10 @@ struct Engine
     std::mutex doneM;
     std::condition_variable doneCv;
     int pollResult = 0; // 0: in flight, 1: complete, < 0: error
+    // the batch's last stream operation stores `sequence` here (page-locked): the completion thread reads memory, not the driver
+    int32_t *doneFlag = nullptr;
+    int32_t sequence = 0;
+    std::chrono::steady_clock::time_point issuedAt;
 
     std::mutex m;
     std::condition_variable workCv, spaceCv;
@@ -341,6 +345,12 @@ int runBatch(Engine *enc, int b)
     else
     {
         hvbenc *session = enc->session;
+        if (enc->doneFlag)
+        {
+            rc = hvb_signal(ctx, enc->doneFlag, ++enc->sequence);
+            if (rc) return rc;
+            enc->issuedAt = std::chrono::steady_clock::now();
+        }
         {
             std::lock_guard<std::mutex> g(enc->doneM);
             enc->pollResult = 0;
@@ -354,8 +364,13 @@ int runBatch(Engine *enc, int b)
         enc->doneCv.wait(lock, [&] { return enc->pollResult != 0; });
         if (enc->pollResult < 0) return hvb_sync(ctx); // collects the error text
     }
-    rc = hvb_sync(ctx); // everything has completed: returns at once, and resets the context's staging slots
-    if (rc) return rc;
+    // everything has completed.  hvb_sync returns at once and surfaces a sticky error; with the flag scheme the batch's completion
+    // is already known, so the three stream queries behind it are only spent now and then
+    if (!enc->doneFlag || !enc->session->usePoller || (enc->dispatches & 63) == 0)
+    {
+        rc = hvb_sync(ctx);
+        if (rc) return rc;
+    }
     if (prof)
         for (int k = 0; k < 6; ++k)
         {
@@ -483,7 +498,20 @@ void pollLoop(hvbenc *session)
         bool any = false;
         for (Engine *e : snapshot)
         {
-            const int r = hvb_poll(e->ctx);
+            int r;
+            if (e->doneFlag)
+            {
+                r = *const_cast<volatile int32_t *>(e->doneFlag) == e->sequence ? 1 : 0;
+                // a batch that has not come back after a long time: ask the driver (a fault never stores the flag)
+                if (!r && std::chrono::steady_clock::now() - e->issuedAt > std::chrono::milliseconds(200))
+                {
+                    r = hvb_poll(e->ctx);
+                    if (!r) e->issuedAt = std::chrono::steady_clock::now();
+                }
+                if (r > 0) std::atomic_thread_fence(std::memory_order_acquire);
+            }
+            else
+                r = hvb_poll(e->ctx);
             if (!r) continue;
             any = true;
             {
@@ -596,6 +624,12 @@ int equipEngine(Engine *enc)
         if (!rc) rc = hvb_picture_wrap(ctx, enc->tuRecHost[b], kTuCell * kTuCellsPerRow, kTuCell * kTuCellsPerRow, rows, &enc->tuRecPic[b]);
     }
     if (!rc) rc = hvb_host_alloc(ctx, sizeof(int16_t) * 1024 * kTuCapacity, reinterpret_cast<void **>(&enc->levelsHost));
+    const char *flagEnv = getenv("HVB_DONE_FLAG");
+    if (!rc && !(flagEnv && atoi(flagEnv) == 0))
+    {
+        rc = hvb_host_alloc(ctx, 64, reinterpret_cast<void **>(&enc->doneFlag));
+        if (!rc) *enc->doneFlag = 0;
+    }
     if (!rc)
     {
         // size the level pool once: block i of a batch owns elements [1024 i, 1024 (i + 1))
@@ -629,6 +663,7 @@ void destroyEngine(Engine *enc)
         if (enc->snapshots[b]) hvb_host_free(enc->ctx, enc->snapshots[b]);
     }
     if (enc->levelsHost) hvb_host_free(enc->ctx, enc->levelsHost);
+    if (enc->doneFlag) hvb_host_free(enc->ctx, enc->doneFlag);
 }
 
 struct Clock

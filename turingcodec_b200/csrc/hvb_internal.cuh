@@ -66,6 +66,7 @@ struct hvb_context
     void *dTensorMaps = nullptr; // [HVB_MAX_PICTURES * 3 * 3] CUtensorMap (hvb_metrics_tma.cu), built on first use
     bool tensorMapsDirty = true;
     bool useTma = false; // hvb_set_tma
+    int tuFusedMax = 256; // hvb_set_tu_fused_max: batches of at most this many transform blocks take the one-launch form of hvb_tu_chain_batch
     HvbLoopInfo *dLoopInfo = nullptr; // [HVB_MAX_PICTURES] on the device, allocated by the first hvb_deblock_info_upload
     HvbLoopInfo loopInfoHost[HVB_MAX_PICTURES] = {};
     int *workCursors = nullptr; // [64] device-side task cursors of the persistent kernels (zeroed on the stream before each use)

@@ -690,6 +690,190 @@ __global__ void __launch_bounds__(kWarps * 32)
     }
 }
 
+// ---- the latency form of the chain: one launch, a warp per block ---------------------------------------------------------
+// The three-stage form above is built for whole frames: blocks are sorted by the length of their serial walk, 32 walks
+// share a warp, the stages hand over through global scratch.  A caller that waits for a handful of blocks (the batched
+// encoder: a CU's transform tree, one intra candidate) pays seven launches and the device's latency on every global
+// record for that.  Here a block stays with ONE warp from the prediction to the reconstruction: source and prediction
+// tiles are fetched once, with every row requested before the first is used (the prediction may sit in page-locked host
+// memory: one trip across the bus instead of one per row), the coefficients, the levels and the walk's 32-byte records
+// live in shared memory, lane 0 runs the same hvbRdoqThread, and the back stage continues from the levels in place.
+// Same device functions, same arithmetic: results are identical to the staged form's (tests run both).
+template <typename Sample>
+__device__ __forceinline__ void loadTile(Sample *tile, const Sample *g, int stride, int log2n, int lane)
+{
+    const int nn = 1 << log2n, rowBytes = nn * (int)sizeof(Sample);
+    if (((reinterpret_cast<uintptr_t>(g) | (uintptr_t)(stride * (int)sizeof(Sample))) & 3) == 0)
+    {
+        // words: every load of a batch of eight is requested before the first is stored
+        const int wpr = rowBytes >> 2, words = wpr << log2n;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(tile);
+        const char *base = reinterpret_cast<const char *>(g);
+        const intptr_t pitch = (intptr_t)stride * (int)sizeof(Sample);
+        for (int first = 0; first < words; first += 256)
+        {
+            uint32_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+            {
+                const int i = first + j * 32 + lane;
+                if (i < words) v[j] = *reinterpret_cast<const uint32_t *>(base + (intptr_t)(i / wpr) * pitch + (i % wpr) * 4);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+            {
+                const int i = first + j * 32 + lane;
+                if (i < words) dst[i] = v[j];
+            }
+        }
+        return;
+    }
+    const int count = nn * nn;
+    for (int first = 0; first < count; first += 256)
+    {
+        Sample v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+        {
+            const int i = first + j * 32 + lane;
+            if (i < count) v[j] = g[(i >> log2n) * stride + (i & (nn - 1))];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+        {
+            const int i = first + j * 32 + lane;
+            if (i < count) tile[i] = v[j];
+        }
+    }
+}
+
+template <typename Sample>
+__global__ void __launch_bounds__(32)
+    tuFusedKernel(const HvbPlane *__restrict__ planes, int16_t *__restrict__ pool, const hvb_rdoq_ctx *__restrict__ rdoqCtx,
+                  const hvb_tu_task *__restrict__ tasks, int n, hvb_tu_result *__restrict__ out, int bitDepth, int rdoqCtxCount, unsigned poolCount,
+                  const int2 *__restrict__ rdoqBits, const int *__restrict__ rdoqLast)
+{
+    __shared__ Matrices M;
+    __shared__ __align__(16) int16_t sA[kBlk];
+    __shared__ __align__(16) int16_t sB[kBlk];
+    __shared__ __align__(16) int16_t sLev[kBlk];
+    __shared__ __align__(16) Sample sSrc[kBlk];
+    __shared__ __align__(16) Sample sPred[kBlk];
+    __shared__ __align__(16) HvbCoefRec sRec[kBlk];
+    initMatrices(M);
+    __syncthreads();
+    const int lane = threadIdx.x;
+    const int maxv = (1 << bitDepth) - 1;
+    for (int t = blockIdx.x; t < n; t += gridDim.x)
+    {
+        const hvb_tu_task task = tasks[t];
+        const int log2n = task.log2n, nn = 1 << log2n, count = nn * nn;
+        const bool dst = task.trType != 0;
+        hvb_tu_result r;
+        r.ssd = r.ssdPred = 0;
+        r.cbf = 0;
+        r.status = 0;
+        r.sadQuad[0] = r.sadQuad[1] = r.sadQuad[2] = r.sadQuad[3] = 0;
+        if (log2n < 2 || log2n > 5 || task.levels < 0 || (unsigned)task.levels + (unsigned)count > poolCount ||
+            ((task.flags & 1) && (unsigned)task.rdoq_ctx >= (unsigned)rdoqCtxCount))
+        {
+            r.status = -1; // as the staged form: rejected, nothing computed
+            if (lane == 0) out[t] = r;
+            continue;
+        }
+        int ss, sp, sr;
+        const Sample *src = hvbBlockPtr<Sample>(planes, task.src, ss);
+        const Sample *pred = hvbBlockPtr<Sample>(planes, task.pred, sp);
+        Sample *rec = hvbBlockPtrW<Sample>(planes, task.rec, sr);
+        loadTile<Sample>(sPred, pred, sp, log2n, lane);
+        loadTile<Sample>(sSrc, src, ss, log2n, lane);
+        __syncwarp();
+
+        // front: residual, SSD of the prediction, per-quadrant sums of absolute differences (as tuFrontKernel)
+        unsigned ssdPred = 0, sadTop = 0, sadBottom = 0;
+        for (int i = lane; i < count; i += 32)
+        {
+            const int y = i >> log2n;
+            const int d = (int)sSrc[i] - (int)sPred[i];
+            sA[i] = (int16_t)d;
+            ssdPred += (unsigned)(d * d);
+            if (y >> (log2n - 1)) sadBottom += (unsigned)abs(d);
+            else sadTop += (unsigned)abs(d);
+        }
+        {
+            const bool right = ((lane & (nn - 1)) >> (log2n - 1)) != 0;
+            r.sadQuad[0] = hvbWarpSumU(right ? 0u : sadTop);
+            r.sadQuad[1] = hvbWarpSumU(right ? sadTop : 0u);
+            r.sadQuad[2] = hvbWarpSumU(right ? 0u : sadBottom);
+            r.sadQuad[3] = hvbWarpSumU(right ? sadBottom : 0u);
+        }
+        __syncwarp();
+        forwardTransform(M, sA, sB, log2n, dst, bitDepth, lane); // sA = coefficients
+        __syncwarp();
+        ssdPred = hvbWarpSumU(ssdPred);
+        if (sizeof(Sample) == 2) ssdPred >>= 4;
+        r.ssdPred = ssdPred;
+
+        int cbf = 0;
+        if (task.flags & 1)
+        {
+            const HvbRdoqMid mid = hvbRdoqPrepass(sLev, sA, rdoqCtx + task.rdoq_ctx, task.qscale, task.qshift, task.iqscale, log2n, task.cIdx,
+                                                  task.scanIdx, bitDepth, lane);
+            __syncwarp();
+            int c = 0;
+            if (lane == 0 && mid.lastSp >= 0)
+                c = hvbRdoqThread(sLev, sA, rdoqCtx + task.rdoq_ctx, mid, task.qscale, task.qshift, task.iqscale, log2n, task.cIdx, task.scanIdx,
+                                  (task.flags & 2) != 0, (task.flags & 4) != 0, bitDepth, sRec,
+                                  rdoqBits + (size_t)task.rdoq_ctx * sizeof(hvb_rdoq_ctx), rdoqLast + (size_t)task.rdoq_ctx * hvb_rdoq::kLastTabPerCtx);
+            __syncwarp();
+            cbf = __shfl_sync(0xffffffffu, c, 0) != 0;
+        }
+        else
+        {
+            const int off = task.qoffset << (task.qshift - 16);
+            int any = 0;
+            for (int i = lane; i < count; i += 32)
+            {
+                const int q = quantOne(sA[i], task.qscale, task.qshift, off);
+                any |= q;
+                sLev[i] = (int16_t)q;
+            }
+            cbf = __any_sync(0xffffffffu, any != 0);
+        }
+        __syncwarp();
+        for (int i = lane; i < count; i += 32) pool[task.levels + i] = sLev[i];
+        r.cbf = cbf;
+
+        // back: dequantise, inverse transform, add, clip, SSD (as tuBackKernel)
+        if (cbf)
+        {
+            const bool tr = inverseWantsTransposed(log2n) && !dst;
+            for (int i = lane; i < count; i += 32)
+            {
+                const int v = dequantOne(sLev[i], task.iqscale, task.iqshift);
+                sA[tr ? ((i & (nn - 1)) << log2n) + (i >> log2n) : i] = (int16_t)v;
+            }
+            __syncwarp();
+            inverseTransform(M, sA, sB, log2n, dst, bitDepth, lane);
+            __syncwarp();
+        }
+        unsigned ssd = 0;
+        for (int i = lane; i < count; i += 32)
+        {
+            const int y = i >> log2n, x = i & (nn - 1);
+            const int v = cbf ? hvbClip3(0, maxv, (int)sPred[i] + sA[i]) : (int)sPred[i];
+            rec[y * sr + x] = (Sample)v;
+            const int d = (int)sSrc[i] - v;
+            ssd += (unsigned)(d * d);
+        }
+        ssd = hvbWarpSumU(ssd);
+        if (sizeof(Sample) == 2) ssd >>= 4;
+        r.ssd = ssd;
+        if (lane == 0) out[t] = r;
+        __syncwarp();
+    }
+}
+
 // Rdoq::runQuantisation alone, on pool coefficients: cooperative pre-pass, then one thread per block
 __global__ void __launch_bounds__(kWarps * 32)
     rdoqPrepassKernel(int16_t *__restrict__ pool, const hvb_rdoq_ctx *__restrict__ rdoqCtx, const hvb_rdoq_task *__restrict__ tasks, int n,
@@ -912,6 +1096,26 @@ extern "C" int hvb_tu_chain_batch(hvb_context *ctx, const hvb_tu_task *tasks, in
     cudaSetDevice(ctx->device);
     int rc = initRdoqTables(ctx);
     if (rc) return rc;
+    if (n <= ctx->tuFusedMax)
+    {
+        // the latency form: one launch, no scratch (a batch of RDOQ blocks without uploaded snapshots is rejected block by block)
+        HvbStaged st;
+        rc = hvbStageIn(ctx, tasks, sizeof(*tasks) * n, out, sizeof(hvb_tu_result) * n, mem, &st);
+        if (rc) return rc;
+        const auto *dT = static_cast<const hvb_tu_task *>(st.dTasks);
+        auto *dO = static_cast<hvb_tu_result *>(st.dOut);
+        const unsigned poolCount = (unsigned)(ctx->coeffPoolCount > 0x7fffffffu ? 0x7fffffffu : ctx->coeffPoolCount);
+        const int grid = n < ctx->smCount * 4 ? n : ctx->smCount * 4;
+        const int ctxCount = ctx->rdoqCtx ? ctx->rdoqCtxCount : 0;
+        if (ctx->bps == 1)
+            tuFusedKernel<uint8_t><<<grid, 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, ctx->rdoqCtx, dT, n, dO, ctx->bitDepth, ctxCount, poolCount,
+                                                                 ctx->rdoqBits, ctx->rdoqLast);
+        else
+            tuFusedKernel<uint16_t><<<grid, 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, ctx->rdoqCtx, dT, n, dO, ctx->bitDepth, ctxCount, poolCount,
+                                                                  ctx->rdoqBits, ctx->rdoqLast);
+        HVB_LAUNCH_CHECK(ctx, "tuFusedKernel");
+        return hvbStageOut(ctx, out, sizeof(hvb_tu_result) * n, mem, st);
+    }
     ChainScratch cs;
     const size_t elems = workspaceElems(ctx, tasks, n, mem, [](const hvb_tu_task &t) {
         return (t.flags & 1) && t.log2n >= 2 && t.log2n <= 5 ? size_t(1) << (2 * t.log2n) : size_t(0);

@@ -219,6 +219,10 @@ class Context:
     def set_tma(self, on: bool):
         self._check(self.lib.hvb_set_tma(self.h, 1 if on else 0), "hvb_set_tma")
 
+    def set_tu_fused_max(self, blocks: int):
+        """batches of at most `blocks` transform blocks take the one-launch form of tu_chain (0: always the staged kernels)"""
+        self._check(self.lib.hvb_set_tu_fused_max(self.h, int(blocks)), "hvb_set_tu_fused_max")
+
     def set_pipelined(self, on: bool):
         """HOST calls on page-locked arrays only enqueue (copies overlap the kernels); results are valid after sync()."""
         self._check(self.lib.hvb_set_pipelined(self.h, int(bool(on))), "hvb_set_pipelined")
