@@ -41,7 +41,38 @@ __attribute__((naked, noinline)) void switchStack(void **saveSp, void *loadSp)
                  "popq %r15\n popq %r14\n popq %r13\n popq %r12\n popq %rbx\n popq %rbp\n ret\n");
 }
 
-std::atomic<uint64_t> gNudges{0};
+// nudge() counters, one per pool (ThreadPool.h is the reference's: no room for a member).  A worker rescans the backlog only
+// when its pool was nudged or one of its own tasks returned; a hand-over -- tens of thousands per picture -- must not cost
+// a walk over the backlog under the pool mutex.
+struct PoolCounter
+{
+    std::atomic<ThreadPool *> pool{nullptr};
+    std::atomic<uint64_t> nudges{0};
+};
+constexpr int kMaxPools = 256;
+PoolCounter gCounters[kMaxPools];
+thread_local bool tlQuietNudge = false; // notify(): wake sleepers without announcing a change of the backlog
+
+std::atomic<uint64_t> &counterOf(ThreadPool *pool)
+{
+    for (int i = 0; i < kMaxPools; ++i)
+    {
+        ThreadPool *seen = gCounters[i].pool.load(std::memory_order_acquire);
+        if (seen == pool) return gCounters[i].nudges;
+        if (!seen)
+        {
+            ThreadPool *expected = nullptr;
+            if (gCounters[i].pool.compare_exchange_strong(expected, pool) || expected == pool) return gCounters[i].nudges;
+        }
+    }
+    return gCounters[kMaxPools - 1].nudges; // more pools than slots: they share a counter (spurious rescans only)
+}
+
+void releaseCounter(ThreadPool *pool)
+{
+    for (int i = 0; i < kMaxPools; ++i)
+        if (gCounters[i].pool.load(std::memory_order_acquire) == pool) gCounters[i].pool.store(nullptr, std::memory_order_release);
+}
 
 struct Fiber
 {
@@ -130,10 +161,12 @@ void notify(void *arg)
     w->ready.store(1, std::memory_order_seq_cst);
     if (w->sleeping.load(std::memory_order_seq_cst))
     {
-        // the worker checks `ready` and goes to sleep under the pool mutex: passing through it closes the window
-        w->pool->lock();
-        w->pool->unlock();
+        // No pass through the pool mutex here (tasks and scanning workers hold it for long stretches, and this runs on the
+        // dispatcher's time): a wake-up that falls between the worker's last look at `ready` and its wait is lost, which the
+        // wait's short time-out bounds.
+        tlQuietNudge = true;
         w->pool->nudge();
+        tlQuietNudge = false;
     }
 }
 
@@ -154,6 +187,7 @@ ThreadPool::~ThreadPool()
     }
     this->nudge();
     for (auto &thread : this->threads) thread.join();
+    releaseCounter(this);
 }
 
 void ThreadPool::add(Task &task)
@@ -206,8 +240,10 @@ void ThreadPool::worker()
     tlWorker = &w;
     const hvbenc_thread_hooks hooks = {park, notify, &w};
     hvbenc_set_thread_hooks(&hooks);
-    const auto spinFor = std::chrono::microseconds(envInt("HVB_FIBER_SPIN_US", 30));
+    const auto spinFor = std::chrono::microseconds(envInt("HVB_FIBER_SPIN_US", 0));
+    std::atomic<uint64_t> &nudgeCounter = counterOf(this);
 
+    bool rescan = true;
     // run fiber f until it parks or its task returns
     auto resume = [&](Fiber *f) {
         f->waitingFor = nullptr;
@@ -222,6 +258,7 @@ void ThreadPool::worker()
             return;
         }
         --w.live;
+        rescan = true; // a task of this worker returned: the reference's loop would look at the backlog now
         if (f->blockedResult)
         {
             std::unique_lock<std::mutex> lock(this->poolMutex);
@@ -231,7 +268,7 @@ void ThreadPool::worker()
         w.spare.push_back(f);
     };
 
-    bool exiting = false, rescan = true;
+    bool exiting = false;
     uint64_t seenNudges = ~uint64_t(0);
     for (;;)
     {
@@ -246,7 +283,7 @@ void ThreadPool::worker()
                 std::atomic_thread_fence(std::memory_order_acquire);
                 w.parked.erase(w.parked.begin() + i);
                 resume(f);
-                progressed = rescan = true;
+                progressed = true;
             }
             else
                 ++i;
@@ -264,7 +301,7 @@ void ThreadPool::worker()
             }
             else
             {
-                const uint64_t nudges = gNudges.load(std::memory_order_acquire);
+                const uint64_t nudges = nudgeCounter.load(std::memory_order_acquire);
                 if (rescan || nudges != seenNudges)
                 {
                     std::unique_lock<std::mutex> lock(this->poolMutex);
@@ -305,8 +342,8 @@ void ThreadPool::worker()
                     f->finished = false;
                     f->state.clear();
                     ++w.live;
+                    rescan = true; // more tasks may be runnable: keep taking them while there is room
                     resume(f);
-                    rescan = true;
                 }
             }
         }
@@ -318,7 +355,7 @@ void ThreadPool::worker()
         bool found = false;
         while (!found && std::chrono::steady_clock::now() - t0 < spinFor)
         {
-            if (w.ready.load(std::memory_order_relaxed) || gNudges.load(std::memory_order_relaxed) != seenNudges) found = true;
+            if (w.ready.load(std::memory_order_relaxed) || nudgeCounter.load(std::memory_order_relaxed) != seenNudges) found = true;
             else
                 __builtin_ia32_pause();
         }
@@ -326,8 +363,8 @@ void ThreadPool::worker()
         {
             std::unique_lock<std::mutex> lock(this->poolMutex);
             w.sleeping.store(1, std::memory_order_seq_cst);
-            if (!w.ready.load(std::memory_order_seq_cst) && gNudges.load(std::memory_order_acquire) == seenNudges)
-                this->taskAvailable.wait_for(lock, std::chrono::milliseconds(2));
+            if (!w.ready.load(std::memory_order_seq_cst) && nudgeCounter.load(std::memory_order_acquire) == seenNudges)
+                this->taskAvailable.wait_for(lock, std::chrono::microseconds(250));
             w.sleeping.store(0, std::memory_order_seq_cst);
         }
     }
@@ -354,7 +391,7 @@ std::mutex &ThreadPool::mutex()
 
 void ThreadPool::nudge()
 {
-    gNudges.fetch_add(1, std::memory_order_release);
+    if (!tlQuietNudge) counterOf(this).fetch_add(1, std::memory_order_release);
     this->taskAvailable.notify_all();
 }
 

@@ -24,7 +24,7 @@ void shutdown()
     if (!gSession) return;
     if (envInt("HVB_STATS", 0))
     {
-        char buf[4096];
+        char buf[8192];
         if (!hvbenc_stats(gSession, buf, sizeof(buf))) fprintf(stderr, "hvbenc stats: %s\n", buf);
     }
     // The process is about to end: releasing gigabytes of device pictures and page-locked buffers one by one costs seconds the

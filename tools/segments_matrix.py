@@ -43,6 +43,8 @@ for spec in sys.argv[2:]:
         row["md5"] = encoder.md5_file(bit)
         row["dispatches"], row["busy_s"] = q.get("dispatches"), q.get("engine_busy_s")
         row["kinds"] = {k: (q[k]["requests"], q[k]["batches"], round(q[k]["mean_wait_us"])) for k in ("me", "me_bi", "pu_cost", "intra_sweep", "tu_chain") if k in q}
+        row["phases_us"] = {k: (round(q[k].get("mean_queue_us", 0)), round(q[k].get("mean_batch_us", 0)), round(q[k].get("mean_wake_us", 0)))
+                            for k in ("me", "me_bi", "pu_cost", "intra_sweep", "tu_chain") if k in q and q[k]["requests"]}
         row["cpu_s"] = ru.children_user + ru.children_system
     else:
         row["err"] = res.stderr[-600:]

@@ -75,6 +75,14 @@ extern "C" int hvb_create(int device, int bytes_per_sample, int bit_depth, hvb_c
     ctx->bitDepth = bit_depth;
 
     cudaError_t e = cudaSetDevice(device);
+    if (const char *v = getenv("HVB_BLOCKING_SYNC"))
+        if (atoi(v))
+        {
+            // a thread that waits for a stream sleeps until the device's interrupt instead of spinning in the driver: what a
+            // session with dozens of dispatcher threads on a few cores wants (hvb_encoder.cpp, HVB_POLLER=0)
+            cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);
+            cudaGetLastError();
+        }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->dPlanes, sizeof(HvbPlane) * HVB_MAX_PICTURES * 3);
     if (e == cudaSuccess) e = cudaMemsetAsync(ctx->dPlanes, 0, sizeof(HvbPlane) * HVB_MAX_PICTURES * 3, ctx->ownStream);

@@ -46,7 +46,13 @@ struct Waiter
     int rc = 0;
     void (*notify)(void *) = nullptr;
     void *notifyArg = nullptr;
+    int64_t tSubmit = 0, tFlip = 0, tDone = 0; // ns: handed over, its batch taken by the dispatcher, answered
 };
+
+inline int64_t nowNs()
+{
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 Waiter &myWaiter()
 {
@@ -56,15 +62,21 @@ Waiter &myWaiter()
 
 thread_local hvbenc_thread_hooks tlHooks = {nullptr, nullptr, nullptr};
 
-// the answer is there: last access to a cooperative waiter is the store (it lives on a stack that may unwind right after)
-void complete(Waiter *w)
+// the answer is there: last access to a cooperative waiter is the store (it lives on a stack that may unwind right after).
+// Cooperative waiters of one scheduler are announced once per batch: `told` collects the schedulers already notified.
+void complete(Waiter *w, std::vector<void *> &told)
 {
+    w->tDone = nowNs();
     if (w->notify)
     {
         void (*const fn)(void *) = w->notify;
         void *const arg = w->notifyArg;
         w->done.store(1, std::memory_order_release);
-        fn(arg);
+        if (std::find(told.begin(), told.end(), arg) == told.end())
+        {
+            told.push_back(arg);
+            fn(arg);
+        }
         return;
     }
     {
@@ -237,6 +249,9 @@ struct hvbenc
 
     // per kind: requests and the time from hand-over to wake-up (ns), for the statistics
     std::atomic<int64_t> waitNs[6], waitCount[6];
+    // where a hand-over's time goes: [0] until the dispatcher takes its batch, [1] the batch (issue, device, completion seen),
+    // [2] from the answer to the caller running again
+    std::atomic<int64_t> phaseNs[6][3];
 
     // Engines by kind (0 uploads, 1 me, 2 bi, 3 pu cost, 4 intra sweep, 5 transform blocks).  A batch is issued on one
     // stream in a fixed order, so a sweep (tens of microseconds on the device) that shares a batch with a motion search waits
@@ -435,6 +450,7 @@ int runBatch(Engine *enc, int b)
 void dispatch(Engine *enc)
 {
     std::vector<Waiter *> wake;
+    std::vector<void *> told;
     for (;;)
     {
         int b;
@@ -447,6 +463,15 @@ void dispatch(Engine *enc)
             enc->pending = 0;
         }
         enc->spaceCv.notify_all();
+        {
+            const int64_t flip = nowNs();
+            for (const Request &r : enc->me.requests[b]) r.waiter->tFlip = flip;
+            for (const Request &r : enc->bi.requests[b]) r.waiter->tFlip = flip;
+            for (const Request &r : enc->pu.requests[b]) r.waiter->tFlip = flip;
+            for (const Request &r : enc->intra.requests[b]) r.waiter->tFlip = flip;
+            for (const Request &r : enc->tu.requests[b]) r.waiter->tFlip = flip;
+            for (Waiter *w : enc->uploadWaiters[b]) w->tFlip = flip;
+        }
         const auto t0 = std::chrono::steady_clock::now();
         const int rc = runBatch(enc, b);
         enc->deviceSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -477,7 +502,8 @@ void dispatch(Engine *enc)
         std::sort(wake.begin(), wake.end());
         wake.erase(std::unique(wake.begin(), wake.end()), wake.end());
         enc->inflight.fetch_sub(answered, std::memory_order_relaxed);
-        for (Waiter *w : wake) complete(w);
+        told.clear();
+        for (Waiter *w : wake) complete(w, told);
     }
 }
 
@@ -561,12 +587,21 @@ Waiter &armWaiter(Waiter &local)
 }
 
 // append `count` tasks of a lane; `extra(b, first)` runs under the lock once the room is there
+void notePhases(hvbenc *session, int kind, const Waiter &w)
+{
+    const int64_t resumed = nowNs();
+    session->phaseNs[kind][0] += w.tFlip - w.tSubmit;
+    session->phaseNs[kind][1] += w.tDone - w.tFlip;
+    session->phaseNs[kind][2] += resumed - w.tDone;
+}
+
 template <class LaneT, class Task, class Extra>
-int submit(Engine *enc, LaneT &lane, const Task *tasks, int count, void *dst, Extra extra)
+int submit(Engine *enc, int kind, LaneT &lane, const Task *tasks, int count, void *dst, Extra extra)
 {
     if (!enc || !tasks || count <= 0 || count > lane.capacity) return HVB_ERR_INVALID;
     Waiter local;
     Waiter &w = armWaiter(local);
+    w.tSubmit = nowNs();
     enc->inflight.fetch_add(1, std::memory_order_relaxed);
     {
         std::unique_lock<std::mutex> lock(enc->m);
@@ -579,7 +614,9 @@ int submit(Engine *enc, LaneT &lane, const Task *tasks, int count, void *dst, Ex
         ++enc->pending;
     }
     enc->workCv.notify_one();
-    return waitFor(w);
+    const int rc = waitFor(w);
+    notePhases(enc->session, kind, w);
+    return rc;
 }
 
 } // namespace
@@ -692,7 +729,11 @@ extern "C" int hvbenc_create(int device, int bytes_per_sample, int bit_depth, in
     if (const char *v = getenv("HVB_ENGINES")) nEngines = std::max(1, std::min(64, atoi(v)));
     hvbenc *enc = new hvbenc;
     enc->bps = bytes_per_sample;
-    for (int k = 0; k < 6; ++k) enc->waitNs[k] = 0, enc->waitCount[k] = 0;
+    for (int k = 0; k < 6; ++k)
+    {
+        enc->waitNs[k] = 0, enc->waitCount[k] = 0;
+        for (int j = 0; j < 3; ++j) enc->phaseNs[k][j] = 0;
+    }
     int rc = 0;
     const auto tStart = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - tStart).count(); };
@@ -823,6 +864,7 @@ extern "C" int hvbenc_upload_rects(hvbenc *session, int pic, const hvbenc_rect *
     Engine *enc = session->pick(0);
     Waiter local;
     Waiter &wt = armWaiter(local);
+    wt.tSubmit = nowNs();
     enc->inflight.fetch_add(1, std::memory_order_relaxed);
     {
         std::unique_lock<std::mutex> lock(enc->m);
@@ -841,7 +883,9 @@ extern "C" int hvbenc_upload_rects(hvbenc *session, int pic, const hvbenc_rect *
         ++enc->pending;
     }
     enc->workCv.notify_one();
-    return waitFor(wt);
+    const int rcWait = waitFor(wt);
+    notePhases(session, 0, wt);
+    return rcWait;
 }
 
 extern "C" int hvbenc_upload_rect(hvbenc *session, int pic, int cIdx, const void *host, intptr_t stride, int x0, int y0, int w, int h)
@@ -855,7 +899,7 @@ extern "C" int hvbenc_me(hvbenc *session, const hvb_me_task *task, hvb_me_result
     if (!session) return HVB_ERR_INVALID;
     Clock clock(session, 1);
     Engine *enc = session->pick(1);
-    return submit(enc, enc->me, task, 1, out, [](int, int) { return true; });
+    return submit(enc, 1, enc->me, task, 1, out, [](int, int) { return true; });
 }
 
 extern "C" int hvbenc_me_bi(hvbenc *session, const hvb_me_bi_task *task, hvb_me_bi_result *out)
@@ -863,7 +907,7 @@ extern "C" int hvbenc_me_bi(hvbenc *session, const hvb_me_bi_task *task, hvb_me_
     if (!session) return HVB_ERR_INVALID;
     Clock clock(session, 2);
     Engine *enc = session->pick(2);
-    return submit(enc, enc->bi, task, 1, out, [](int, int) { return true; });
+    return submit(enc, 2, enc->bi, task, 1, out, [](int, int) { return true; });
 }
 
 extern "C" int hvbenc_pu_cost(hvbenc *session, const hvb_pu_cost_task *tasks, int n, int32_t *out)
@@ -871,7 +915,7 @@ extern "C" int hvbenc_pu_cost(hvbenc *session, const hvb_pu_cost_task *tasks, in
     if (!session) return HVB_ERR_INVALID;
     Clock clock(session, 3);
     Engine *enc = session->pick(3);
-    return submit(enc, enc->pu, tasks, n, out, [](int, int) { return true; });
+    return submit(enc, 3, enc->pu, tasks, n, out, [](int, int) { return true; });
 }
 
 extern "C" int hvbenc_intra_sweep(hvbenc *session, const hvb_intra_sweep_task *task, const void *neighbours, int32_t *out)
@@ -880,7 +924,7 @@ extern "C" int hvbenc_intra_sweep(hvbenc *session, const hvb_intra_sweep_task *t
     Clock clock(session, 4);
     Engine *enc = session->pick(4);
     const size_t count = (size_t)(4 << task->log2n) + 1, room = (count + 15) & ~size_t(15);
-    return submit(enc, enc->intra, task, 1, out, [&](int b, int first) {
+    return submit(enc, 4, enc->intra, task, 1, out, [&](int b, int first) {
         if (first < 0) return enc->poolUsed[b] + room <= kPoolSamples;
         const size_t at = enc->poolUsed[b];
         memcpy(enc->poolStage[b] + at * enc->bps, neighbours, count * enc->bps);
@@ -898,7 +942,7 @@ extern "C" int hvbenc_tu_chain(hvbenc *session, hvb_tu_task *tasks, int n, const
     if (!session || !tasks || n <= 0 || !pred || !pred_stride || !rec || !rec_stride || !levels || !out) return HVB_ERR_INVALID;
     Clock clock(session, 5);
     Engine *enc = session->pick(5);
-    return submit(enc, enc->tu, tasks, n, out, [&](int b, int first) {
+    return submit(enc, 5, enc->tu, tasks, n, out, [&](int b, int first) {
         if (first < 0) return !snapshot || enc->nSnapshots[b] < kRdoqSnapshots;
         int snap = 0;
         if (snapshot)
@@ -958,8 +1002,10 @@ extern "C" int hvbenc_stats(hvbenc *session, char *buf, size_t bytes)
         const long long c = session->waitCount[k + 1];
         at += snprintf(buf + at, bytes - at,
                        "\"%s\": {\"tasks\": %lld, \"batches\": %lld, \"requests\": %lld, \"mean_wait_us\": %.1f, \"device_ms\": %.3f, "
-                       "\"algorithmic_bytes\": %.0f}, ",
-                       names[k], tasks[k], batches[k], c, c ? session->waitNs[k + 1] / 1000.0 / c : 0.0, kindMs[k + 1], alg[k + 1]);
+                       "\"algorithmic_bytes\": %.0f, \"mean_queue_us\": %.1f, \"mean_batch_us\": %.1f, \"mean_wake_us\": %.1f}, ",
+                       names[k], tasks[k], batches[k], c, c ? session->waitNs[k + 1] / 1000.0 / c : 0.0, kindMs[k + 1], alg[k + 1],
+                       c ? session->phaseNs[k + 1][0] / 1000.0 / c : 0.0, c ? session->phaseNs[k + 1][1] / 1000.0 / c : 0.0,
+                       c ? session->phaseNs[k + 1][2] / 1000.0 / c : 0.0);
     }
     const long long uc = session->waitCount[0];
     if (at < (int)bytes)
