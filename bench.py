@@ -465,12 +465,20 @@ def reference_encoder_fps(width, height, frames=6):
 # ------------------------------------------------------------------------------------------------
 # the encoders
 # ------------------------------------------------------------------------------------------------
+# The submission queue and the hooks as the bench runs them (measured on the 16-core B200 box, profiles/r02f_*): the encoder's pool threads are
+# fiber schedulers (integration/fiber_pool.cpp), so an instance needs two threads, not dozens; many instances (segments) in flight supply the
+# hand-overs that fill the batches; engines are grouped by kind.  HVB_HOOKS / thresholds: which blocks are worth a hand-over -- the transform
+# blocks (inter CUs and intra candidates, 16x16 and larger: DCT + RDOQ + reconstruction), which are 56 % of the reference's host time
+# (profiles/r02f_host_profile.txt); the motion search and the sweeps of small blocks cost the host less than the hand-over.
+QUEUE_ENV = {"HVB_ENGINES": "32", "HVB_FIBERS": "128", "HVB_HOOKS": "48", "HVB_INTRA_TU_MIN_LOG2": "4", "HVB_TU_MIN_LOG2": "4"}
+
+
 def host_plan(args, world):
-    """threads / instances for this host: the workers of the batched build block on the device, so they are oversubscribed"""
+    """instances / pool threads for this host: a pool thread is a fiber scheduler that carries many CTU rows, so threads ~ cores, not rows"""
     cores = os.cpu_count() or 16
     per_rank = max(4, cores // max(1, world))
-    parallel = args.parallel_segments or max(2, min(8, per_rank // 3))
-    threads = args.threads or max(16, min(64, 6 * per_rank // parallel))
+    parallel = args.parallel_segments or max(2, min(12, (3 * per_rank) // 4, args.steps))
+    threads = args.threads or max(1, min(8, (3 * per_rank) // (2 * parallel)))
     return cores, parallel, threads
 
 
@@ -485,7 +493,7 @@ def workdir(args):
     return base
 
 
-def run_segments(args, clip, frames, out_dir, tag, parallel, threads, rank=0, device=0, profile=True, ranks=1):
+def run_segments(args, clip, frames, out_dir, tag, parallel, threads, rank=0, device=0, profile=False, ranks=1, extra_env=None):
     """one run of integration/_build/turing_b200_segments; returns (wall seconds, encoder-clock seconds, queue stats, md5)"""
     import re
     from turingcodec_b200 import encoder
@@ -500,8 +508,12 @@ def run_segments(args, clip, frames, out_dir, tag, parallel, threads, rank=0, de
     cmd += [*encoder_options(args), str(clip)]
     env = dict(os.environ, HVB_STATS="1", HVB_DEVICE=str(device), HVB_PROFILE="1" if profile else "0")
     env["LD_LIBRARY_PATH"] = str(encoder.LIB_DIR) + ":" + env.get("LD_LIBRARY_PATH", "")
+    for name, value in QUEUE_ENV.items():
+        env.setdefault(name, value)  # (the caller's environment wins: tools/ sweeps these)
     if args.engines:
         env["HVB_ENGINES"] = str(args.engines)
+    if extra_env:
+        env.update(extra_env)
     t0 = time.perf_counter()
     res = subprocess.run(cmd, capture_output=True, text=True, env=env)
     wall = time.perf_counter() - t0

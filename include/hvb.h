@@ -308,6 +308,7 @@ typedef struct
 } hvb_tu_result; /* 32 bytes */
 int hvb_tu_chain_batch(hvb_context *ctx, const hvb_tu_task *tasks, int n, hvb_tu_result *out, hvb_mem mem);
 
+
 /* RDOQ inputs that are not pixels: a snapshot of the CABAC context states the reference's
  * Rdoq reads through estimateBits (turing/Rdoq.cpp:26-31) plus lambda.  One snapshot serves many
  * TUs (the reference snapshots per CU).  Layout: see hvb_rdoq_ctx below. */
@@ -326,6 +327,13 @@ typedef struct
     double lambda; /* as passed to Rdoq::Rdoq (turing/Rdoq.h:170) */
 } hvb_rdoq_ctx; /* 136 bytes */
 int hvb_rdoq_contexts_upload(hvb_context *ctx, const hvb_rdoq_ctx *snapshots, int count, int first);
+/* A caller that waits for every batch (the submission queue of hvb_encoder.h) can spare the copies around the one-launch form of
+ * hvb_tu_chain_batch: levels are written to, and context snapshots read from, the caller's own page-locked arrays (hvb_host_alloc)
+ * across the bus.  `levels`: the pool hvb_tu_task.levels indexes; `snapshots`: the array hvb_tu_task.rdoq_ctx indexes -- both must
+ * stay untouched while a batch is in flight.  NULL / 0 returns to the context's device arrays.  While either is set, batches larger
+ * than hvb_set_tu_fused_max are refused. */
+int hvb_coeff_pool_wrap(hvb_context *ctx, int16_t *levels, size_t count);
+int hvb_rdoq_contexts_wrap(hvb_context *ctx, const hvb_rdoq_ctx *snapshots, int count);
 
 /* Rdoq::runQuantisation alone (turing/Rdoq.cpp:35-450) on pool coefficients */
 typedef struct

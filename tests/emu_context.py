@@ -152,9 +152,7 @@ template <typename Sample>
 static void fusedChain(const HvbPlane *planes, int16_t *pool, int poolCount, const hvb_rdoq_ctx *rdoqCtx, int nCtx, const hvb_tu_task *tasks, int n,
                        hvb_tu_result *out, int bitDepth, int grid)
 {
-    RdoqTables tables(rdoqCtx, nCtx);
-    emuLaunch(std::min(n, grid), 32, [&] { tuFusedKernel<Sample>(planes, pool, rdoqCtx, tasks, n, out, bitDepth, nCtx, (unsigned)poolCount,
-                                                                  tables.bits.data(), tables.last.data()); });
+    emuLaunch(std::min(n, grid), 32, [&] { tuFusedKernel<Sample>(planes, pool, rdoqCtx, tasks, n, out, bitDepth, nCtx, (unsigned)poolCount); });
 }
 extern "C" void emu_tu_chain_fused(const HvbPlane *planes, int16_t *pool, int poolCount, const hvb_rdoq_ctx *rdoqCtx, int nCtx, const hvb_tu_task *tasks,
                                    int n, hvb_tu_result *out, int bitDepth, int bps, int grid)

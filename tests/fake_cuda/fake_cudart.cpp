@@ -28,6 +28,7 @@ cudaError_t cudaDeviceGetAttribute(int *value, cudaDeviceAttr attr, int)
     return cudaSuccess;
 }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+cudaError_t cudaSetDeviceFlags(unsigned int) { return cudaSuccess; }
 // kernel attributes and occupancy: the launch code only sizes grids with them
 cudaError_t cudaFuncSetAttribute(const void *, cudaFuncAttribute, int) { return cudaSuccess; }
 cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *blocks, const void *, int, size_t) { *blocks = 4; return cudaSuccess; }

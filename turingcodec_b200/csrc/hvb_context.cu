@@ -656,6 +656,22 @@ extern "C" int hvb_coeff_download(hvb_context *ctx, int16_t *data, size_t count,
     return hvbCuda(ctx, e, "hvb_coeff_download");
 }
 
+extern "C" int hvb_coeff_pool_wrap(hvb_context *ctx, int16_t *levels, size_t count)
+{
+    HVB_CHECK_ARGS(ctx, (levels && count > 0 && hvbIsPinned(levels)) || (!levels && !count));
+    ctx->coeffWrap = levels;
+    ctx->coeffWrapCount = count;
+    return HVB_OK;
+}
+
+extern "C" int hvb_rdoq_contexts_wrap(hvb_context *ctx, const hvb_rdoq_ctx *snapshots, int count)
+{
+    HVB_CHECK_ARGS(ctx, (snapshots && count > 0 && hvbIsPinned(snapshots)) || (!snapshots && !count));
+    ctx->rdoqWrap = snapshots;
+    ctx->rdoqWrapCount = count;
+    return HVB_OK;
+}
+
 extern "C" int hvb_rdoq_contexts_upload(hvb_context *ctx, const hvb_rdoq_ctx *snapshots, int count, int first)
 {
     HVB_CHECK_ARGS(ctx, snapshots && count > 0 && first >= 0);

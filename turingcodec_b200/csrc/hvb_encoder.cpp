@@ -339,17 +339,14 @@ int runBatch(Engine *enc, int b)
         if (rc) return rc;
     }
     if (prof) hvb_mark(ctx, 5);
-    size_t levelCount = 0;
     if (enc->tu.n[b])
     {
-        if (enc->nSnapshots[b]) rc = hvb_rdoq_contexts_upload(ctx, enc->snapshots[b], enc->nSnapshots[b], 0);
+        // one launch: the kernel reads this batch's snapshots and writes its levels in the page-locked arrays themselves
+        // (the level pool was wrapped once, equipEngine); no upload, no table kernels, no download
+        rc = hvb_rdoq_contexts_wrap(ctx, enc->snapshots[b], kRdoqSnapshots);
         if (!rc) rc = hvb_tu_chain_batch(ctx, enc->tu.tasks[b], enc->tu.n[b], enc->tu.results[b], HVB_DEVICE);
         if (rc) return rc;
-        levelCount = (size_t)enc->tu.n[b] * 1024;
     }
-    // the levels come back with the batch (enqueued: the destination is page-locked)
-    if (levelCount) rc = hvb_coeff_download(ctx, enc->levelsHost, levelCount, 0);
-    if (rc) return rc;
     if (prof) hvb_mark(ctx, 6);
     // one wait for the whole batch: on the session's completion thread, or (HVB_POLLER=0) inside the driver
     if (!enc->session->usePoller)
@@ -669,9 +666,12 @@ int equipEngine(Engine *enc)
     }
     if (!rc)
     {
-        // size the level pool once: block i of a batch owns elements [1024 i, 1024 (i + 1))
+        // block i of a batch owns elements [1024 i, 1024 (i + 1)) of the level pool, which is the page-locked array the results
+        // are read from; every batch of the queue takes the one-launch form of the chain
         std::vector<int16_t> zero(1024, 0);
-        rc = hvb_coeff_upload(ctx, zero.data(), 1024, (size_t)1024 * (kTuCapacity - 1));
+        rc = hvb_coeff_upload(ctx, zero.data(), 1024, 0); // (hvb_tu_chain_batch wants a device pool to exist)
+        if (!rc) rc = hvb_coeff_pool_wrap(ctx, enc->levelsHost, (size_t)1024 * kTuCapacity);
+        if (!rc) rc = hvb_set_tu_fused_max(ctx, kTuCapacity);
     }
     if (!rc) rc = hvb_sync(ctx);
     return rc;

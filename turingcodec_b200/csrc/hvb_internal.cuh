@@ -97,6 +97,11 @@ struct hvb_context
     size_t coeffPoolCount = 0;
     hvb_rdoq_ctx *rdoqCtx = nullptr;
     int rdoqCtxCount = 0;
+    // the caller's page-locked arrays in place of the two above (hvb_coeff_pool_wrap, hvb_rdoq_contexts_wrap): one-launch TU chain only
+    int16_t *coeffWrap = nullptr;
+    size_t coeffWrapCount = 0;
+    const hvb_rdoq_ctx *rdoqWrap = nullptr;
+    int rdoqWrapCount = 0;
     int2 *rdoqBits = nullptr; // [rdoqCtxCount * sizeof(hvb_rdoq_ctx)] bit costs of both bins per context state byte
     size_t rdoqBitsCount = 0;
     int *rdoqLast = nullptr; // [rdoqCtxCount * 160] last-position prefix rates per snapshot (hvb_rdoq.cuh lastPrefixRate)

@@ -157,7 +157,7 @@ struct Engine
 // the bit cost of coding `bin` with the context whose state byte is `state` (a member of *e.cx)
 __device__ __forceinline__ int bitsOf(const Engine &e, int bin, const uint8_t &state)
 {
-    const int2 v = __ldg(e.bits + (&state - reinterpret_cast<const uint8_t *>(e.cx)));
+    const int2 v = e.bits[&state - reinterpret_cast<const uint8_t *>(e.cx)]; // (plain loads: the table may be in shared memory, tuFusedKernel)
     return bin ? v.y : v.x;
 }
 
@@ -169,7 +169,7 @@ struct CoefBits
 };
 __device__ __forceinline__ int2 bitsBoth(const Engine &e, const uint8_t &state)
 {
-    return __ldg(e.bits + (&state - reinterpret_cast<const uint8_t *>(e.cx)));
+    return e.bits[&state - reinterpret_cast<const uint8_t *>(e.cx)];
 }
 
 __device__ __forceinline__ int baseLevel(int g1Cnt, int g2Cnt) { return g1Cnt < 8 ? 2 + (g2Cnt < 1) : 1; }
@@ -368,7 +368,7 @@ __device__ inline int lastPrefixRate(const hvb_rdoq_ctx &cx, bool isY, int len, 
 
 __device__ __forceinline__ long long lastPosCost(const Engine &e, int xC, int yC)
 {
-    return e.lam(__ldg(e.lastTab + lastLen(xC)) + __ldg(e.lastTab + 10 + lastLen(yC)));
+    return e.lam(e.lastTab[lastLen(xC)] + e.lastTab[10 + lastLen(yC)]);
 }
 
 // neighbours right / below of coefficient group (xS, yS) in the 64-bit csbf mask (Rdoq.cpp:601-617, :675-697)

@@ -750,8 +750,7 @@ __device__ __forceinline__ void loadTile(Sample *tile, const Sample *g, int stri
 template <typename Sample>
 __global__ void __launch_bounds__(32)
     tuFusedKernel(const HvbPlane *__restrict__ planes, int16_t *__restrict__ pool, const hvb_rdoq_ctx *__restrict__ rdoqCtx,
-                  const hvb_tu_task *__restrict__ tasks, int n, hvb_tu_result *__restrict__ out, int bitDepth, int rdoqCtxCount, unsigned poolCount,
-                  const int2 *__restrict__ rdoqBits, const int *__restrict__ rdoqLast)
+                  const hvb_tu_task *__restrict__ tasks, int n, hvb_tu_result *__restrict__ out, int bitDepth, int rdoqCtxCount, unsigned poolCount)
 {
     __shared__ Matrices M;
     __shared__ __align__(16) int16_t sA[kBlk];
@@ -760,6 +759,11 @@ __global__ void __launch_bounds__(32)
     __shared__ __align__(16) Sample sSrc[kBlk];
     __shared__ __align__(16) Sample sPred[kBlk];
     __shared__ __align__(16) HvbCoefRec sRec[kBlk];
+    // the block's context snapshot and what the walk reads of it, derived here (rdoqBitsKernel / rdoqLastKernel do the same for
+    // the staged form when snapshots are uploaded): the snapshots may sit in page-locked host memory (hvb_rdoq_contexts_wrap)
+    __shared__ __align__(16) hvb_rdoq_ctx sCtx;
+    __shared__ int2 sBits[sizeof(hvb_rdoq_ctx)];
+    __shared__ int sLast[hvb_rdoq::kLastTabPerCtx];
     initMatrices(M);
     __syncthreads();
     const int lane = threadIdx.x;
@@ -817,14 +821,28 @@ __global__ void __launch_bounds__(32)
         int cbf = 0;
         if (task.flags & 1)
         {
-            const HvbRdoqMid mid = hvbRdoqPrepass(sLev, sA, rdoqCtx + task.rdoq_ctx, task.qscale, task.qshift, task.iqscale, log2n, task.cIdx,
+            {
+                static_assert(sizeof(hvb_rdoq_ctx) % 4 == 0, "snapshot copied as words");
+                const uint32_t *g = reinterpret_cast<const uint32_t *>(rdoqCtx + task.rdoq_ctx);
+                for (int i = lane; i < (int)(sizeof(hvb_rdoq_ctx) / 4); i += 32) reinterpret_cast<uint32_t *>(&sCtx)[i] = g[i];
+                __syncwarp();
+                for (int i = lane; i < (int)sizeof(hvb_rdoq_ctx); i += 32)
+                {
+                    const uint8_t state = reinterpret_cast<const uint8_t *>(&sCtx)[i];
+                    sBits[i] = make_int2(hvb_rdoq::kEntropyBits[state >> 1], hvb_rdoq::kEntropyBits[(state >> 1) ^ 1]);
+                }
+                // the 20 last-position prefix rates of this block's plane class and size, where hvbRdoqThread looks for them
+                const int chroma = task.cIdx ? 1 : 0;
+                if (lane < 20) sLast[(chroma * 4 + (log2n - 2)) * 20 + lane] = hvb_rdoq::lastPrefixRate(sCtx, lane >= 10, lane % 10, chroma, log2n);
+                __syncwarp();
+            }
+            const HvbRdoqMid mid = hvbRdoqPrepass(sLev, sA, &sCtx, task.qscale, task.qshift, task.iqscale, log2n, task.cIdx,
                                                   task.scanIdx, bitDepth, lane);
             __syncwarp();
             int c = 0;
             if (lane == 0 && mid.lastSp >= 0)
-                c = hvbRdoqThread(sLev, sA, rdoqCtx + task.rdoq_ctx, mid, task.qscale, task.qshift, task.iqscale, log2n, task.cIdx, task.scanIdx,
-                                  (task.flags & 2) != 0, (task.flags & 4) != 0, bitDepth, sRec,
-                                  rdoqBits + (size_t)task.rdoq_ctx * sizeof(hvb_rdoq_ctx), rdoqLast + (size_t)task.rdoq_ctx * hvb_rdoq::kLastTabPerCtx);
+                c = hvbRdoqThread(sLev, sA, &sCtx, mid, task.qscale, task.qshift, task.iqscale, log2n, task.cIdx, task.scanIdx,
+                                  (task.flags & 2) != 0, (task.flags & 4) != 0, bitDepth, sRec, sBits, sLast);
             __syncwarp();
             cbf = __shfl_sync(0xffffffffu, c, 0) != 0;
         }
@@ -1104,18 +1122,23 @@ extern "C" int hvb_tu_chain_batch(hvb_context *ctx, const hvb_tu_task *tasks, in
         if (rc) return rc;
         const auto *dT = static_cast<const hvb_tu_task *>(st.dTasks);
         auto *dO = static_cast<hvb_tu_result *>(st.dOut);
-        const unsigned poolCount = (unsigned)(ctx->coeffPoolCount > 0x7fffffffu ? 0x7fffffffu : ctx->coeffPoolCount);
+        // levels and snapshots: the context's own device arrays, or the caller's page-locked ones (hvb_coeff_pool_wrap,
+        // hvb_rdoq_contexts_wrap: the kernel addresses them across the bus, no copy is enqueued)
+        int16_t *levelPool = ctx->coeffWrap ? ctx->coeffWrap : ctx->coeffPool;
+        const size_t levelCount = ctx->coeffWrap ? ctx->coeffWrapCount : ctx->coeffPoolCount;
+        const unsigned poolCount = (unsigned)(levelCount > 0x7fffffffu ? 0x7fffffffu : levelCount);
         const int grid = n < ctx->smCount * 4 ? n : ctx->smCount * 4;
-        const int ctxCount = ctx->rdoqCtx ? ctx->rdoqCtxCount : 0;
+        const hvb_rdoq_ctx *snapshots = ctx->rdoqWrap ? ctx->rdoqWrap : ctx->rdoqCtx;
+        const int ctxCount = ctx->rdoqWrap ? ctx->rdoqWrapCount : (ctx->rdoqCtx ? ctx->rdoqCtxCount : 0);
         if (ctx->bps == 1)
-            tuFusedKernel<uint8_t><<<grid, 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, ctx->rdoqCtx, dT, n, dO, ctx->bitDepth, ctxCount, poolCount,
-                                                                 ctx->rdoqBits, ctx->rdoqLast);
+            tuFusedKernel<uint8_t><<<grid, 32, 0, ctx->stream>>>(ctx->dPlanes, levelPool, snapshots, dT, n, dO, ctx->bitDepth, ctxCount, poolCount);
         else
-            tuFusedKernel<uint16_t><<<grid, 32, 0, ctx->stream>>>(ctx->dPlanes, ctx->coeffPool, ctx->rdoqCtx, dT, n, dO, ctx->bitDepth, ctxCount, poolCount,
-                                                                  ctx->rdoqBits, ctx->rdoqLast);
+            tuFusedKernel<uint16_t><<<grid, 32, 0, ctx->stream>>>(ctx->dPlanes, levelPool, snapshots, dT, n, dO, ctx->bitDepth, ctxCount, poolCount);
         HVB_LAUNCH_CHECK(ctx, "tuFusedKernel");
         return hvbStageOut(ctx, out, sizeof(hvb_tu_result) * n, mem, st);
     }
+    if (ctx->coeffWrap || ctx->rdoqWrap)
+        return hvbFail(ctx, HVB_ERR_INVALID, "hvb_tu_chain_batch: wrapped level / snapshot arrays serve the one-launch form only (raise hvb_set_tu_fused_max)");
     ChainScratch cs;
     const size_t elems = workspaceElems(ctx, tasks, n, mem, [](const hvb_tu_task &t) {
         return (t.flags & 1) && t.log2n >= 2 && t.log2n <= 5 ? size_t(1) << (2 * t.log2n) : size_t(0);
