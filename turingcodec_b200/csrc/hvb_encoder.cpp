@@ -182,7 +182,9 @@ struct Engine
     std::mutex m;
     std::condition_variable workCv, spaceCv;
     int fill = 0;         // buffer the workers append to
-    int pending = 0;      // requests in the buffer being filled
+    std::atomic<int> pending{0}; // requests in the buffer being filled (written under m; the service threads peek at it)
+    int flying = -1;      // service mode: the buffer whose batch is on the device
+    std::chrono::steady_clock::time_point flyingSince;
     bool stop = false;
     std::thread dispatcher;
 
@@ -246,6 +248,11 @@ struct hvbenc
     std::vector<Engine *> watching;
     bool pollStop = false;
     int pollSleepUs = 20; // HVB_POLL_SLEEP_US; 0: spin
+    // Service mode (HVB_SERVICE_THREADS > 0, the default): no dispatcher thread per engine and no completion thread.  A few
+    // service threads sweep the engines: a batch whose flag has arrived is answered and, in the same visit, the requests that
+    // gathered meanwhile are issued.  Between a batch's completion and its callers' wake-up there is no thread hand-over left.
+    std::vector<std::thread> services;
+    std::atomic<bool> serviceStop{false};
 
     // per kind: requests and the time from hand-over to wake-up (ns), for the statistics
     std::atomic<int64_t> waitNs[6], waitCount[6];
@@ -311,7 +318,8 @@ int fail(Engine *enc, int rc, const char *what)
 }
 
 // Issue everything in buffer b.  Order on the stream: uploads, then the searches, costs, sweeps and transform blocks.
-int runBatch(Engine *enc, int b)
+// everything of buffer b onto the engine's stream; does not wait
+int issueBatch(Engine *enc, int b)
 {
     hvb_context *ctx = enc->ctx;
     int rc = 0;
@@ -348,34 +356,15 @@ int runBatch(Engine *enc, int b)
         if (rc) return rc;
     }
     if (prof) hvb_mark(ctx, 6);
-    // one wait for the whole batch: on the session's completion thread, or (HVB_POLLER=0) inside the driver
-    if (!enc->session->usePoller)
-    {
-        rc = hvb_sync(ctx);
-        if (rc) return rc;
-    }
-    else
-    {
-        hvbenc *session = enc->session;
-        if (enc->doneFlag)
-        {
-            rc = hvb_signal(ctx, enc->doneFlag, ++enc->sequence);
-            if (rc) return rc;
-            enc->issuedAt = std::chrono::steady_clock::now();
-        }
-        {
-            std::lock_guard<std::mutex> g(enc->doneM);
-            enc->pollResult = 0;
-        }
-        {
-            std::lock_guard<std::mutex> g(session->pollM);
-            session->watching.push_back(enc);
-        }
-        session->pollCv.notify_one();
-        std::unique_lock<std::mutex> lock(enc->doneM);
-        enc->doneCv.wait(lock, [&] { return enc->pollResult != 0; });
-        if (enc->pollResult < 0) return hvb_sync(ctx); // collects the error text
-    }
+    return 0;
+}
+
+// the batch in buffer b has completed on the device: statistics, reconstructions and levels back to the callers' buffers
+int collectBatch(Engine *enc, int b)
+{
+    hvb_context *ctx = enc->ctx;
+    int rc = 0;
+    const bool prof = enc->profile;
     // everything has completed.  hvb_sync returns at once and surfaces a sticky error; with the flag scheme the batch's completion
     // is already known, so the three stream queries behind it are only spent now and then
     if (!enc->doneFlag || !enc->session->usePoller || (enc->dispatches & 63) == 0)
@@ -444,6 +433,55 @@ int runBatch(Engine *enc, int b)
     return 0;
 }
 
+int runBatch(Engine *enc, int b)
+{
+    hvb_context *ctx = enc->ctx;
+    int rc = issueBatch(enc, b);
+    if (rc) return rc;
+    // one wait for the whole batch: on the session's completion thread, or (HVB_POLLER=0) inside the driver
+    if (!enc->session->usePoller)
+    {
+        rc = hvb_sync(ctx);
+        if (rc) return rc;
+    }
+    else
+    {
+        hvbenc *session = enc->session;
+        if (enc->doneFlag)
+        {
+            rc = hvb_signal(ctx, enc->doneFlag, ++enc->sequence);
+            if (rc) return rc;
+            enc->issuedAt = std::chrono::steady_clock::now();
+        }
+        {
+            std::lock_guard<std::mutex> g(enc->doneM);
+            enc->pollResult = 0;
+        }
+        {
+            std::lock_guard<std::mutex> g(session->pollM);
+            session->watching.push_back(enc);
+        }
+        session->pollCv.notify_one();
+        std::unique_lock<std::mutex> lock(enc->doneM);
+        enc->doneCv.wait(lock, [&] { return enc->pollResult != 0; });
+        if (enc->pollResult < 0) return hvb_sync(ctx); // collects the error text
+    }
+    return collectBatch(enc, b);
+}
+
+void answerBatch(Engine *enc, int b, int rc, std::vector<Waiter *> &wake, std::vector<void *> &told);
+
+void stampFlip(Engine *enc, int b)
+{
+    const int64_t flip = nowNs();
+    for (const Request &r : enc->me.requests[b]) r.waiter->tFlip = flip;
+    for (const Request &r : enc->bi.requests[b]) r.waiter->tFlip = flip;
+    for (const Request &r : enc->pu.requests[b]) r.waiter->tFlip = flip;
+    for (const Request &r : enc->intra.requests[b]) r.waiter->tFlip = flip;
+    for (const Request &r : enc->tu.requests[b]) r.waiter->tFlip = flip;
+    for (Waiter *w : enc->uploadWaiters[b]) w->tFlip = flip;
+}
+
 void dispatch(Engine *enc)
 {
     std::vector<Waiter *> wake;
@@ -460,18 +498,18 @@ void dispatch(Engine *enc)
             enc->pending = 0;
         }
         enc->spaceCv.notify_all();
-        {
-            const int64_t flip = nowNs();
-            for (const Request &r : enc->me.requests[b]) r.waiter->tFlip = flip;
-            for (const Request &r : enc->bi.requests[b]) r.waiter->tFlip = flip;
-            for (const Request &r : enc->pu.requests[b]) r.waiter->tFlip = flip;
-            for (const Request &r : enc->intra.requests[b]) r.waiter->tFlip = flip;
-            for (const Request &r : enc->tu.requests[b]) r.waiter->tFlip = flip;
-            for (Waiter *w : enc->uploadWaiters[b]) w->tFlip = flip;
-        }
+        stampFlip(enc, b);
         const auto t0 = std::chrono::steady_clock::now();
         const int rc = runBatch(enc, b);
         enc->deviceSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        answerBatch(enc, b, rc, wake, told);
+    }
+}
+
+// results of buffer b to the callers, buffers reset, callers announced
+void answerBatch(Engine *enc, int b, int rc, std::vector<Waiter *> &wake, std::vector<void *> &told)
+{
+    {
         ++enc->dispatches;
         wake.clear();
         const int answered = (int)(enc->me.requests[b].size() + enc->bi.requests[b].size() + enc->pu.requests[b].size() +
@@ -501,6 +539,71 @@ void dispatch(Engine *enc)
         enc->inflight.fetch_sub(answered, std::memory_order_relaxed);
         told.clear();
         for (Waiter *w : wake) complete(w, told);
+    }
+}
+
+void serviceLoop(hvbenc *session, int index, int count)
+{
+#ifdef __linux__
+    prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);
+#endif
+    std::vector<Waiter *> wake;
+    std::vector<void *> told;
+    std::vector<Engine *> mine;
+    for (size_t e = index; e < session->engines.size(); e += count) mine.push_back(session->engines[e]);
+    while (!session->serviceStop.load(std::memory_order_acquire))
+    {
+        bool any = false;
+        for (Engine *enc : mine)
+        {
+            if (enc->flying >= 0)
+            {
+                bool done = *const_cast<volatile int32_t *>(enc->doneFlag) == enc->sequence;
+                int rc = 0;
+                if (!done && std::chrono::steady_clock::now() - enc->issuedAt > std::chrono::milliseconds(200))
+                {
+                    // a batch that does not come back: ask the driver (a fault never stores the flag)
+                    const int r = hvb_poll(enc->ctx);
+                    if (r < 0) rc = hvb_sync(enc->ctx), done = true;
+                    else if (r > 0) done = true;
+                    else enc->issuedAt = std::chrono::steady_clock::now();
+                }
+                if (!done) continue;
+                std::atomic_thread_fence(std::memory_order_acquire);
+                const int b = enc->flying;
+                if (!rc) rc = collectBatch(enc, b);
+                enc->deviceSeconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - enc->flyingSince).count();
+                enc->flying = -1;
+                answerBatch(enc, b, rc, wake, told);
+                any = true;
+            }
+            if (enc->flying < 0 && enc->pending.load(std::memory_order_acquire) > 0)
+            {
+                int b;
+                {
+                    std::lock_guard<std::mutex> lock(enc->m);
+                    b = enc->fill;
+                    enc->fill ^= 1;
+                    enc->pending = 0;
+                }
+                enc->spaceCv.notify_all();
+                stampFlip(enc, b);
+                enc->flyingSince = std::chrono::steady_clock::now();
+                int rc = issueBatch(enc, b);
+                if (!rc) rc = hvb_signal(enc->ctx, enc->doneFlag, ++enc->sequence);
+                enc->issuedAt = std::chrono::steady_clock::now();
+                if (rc)
+                    answerBatch(enc, b, rc, wake, told);
+                else
+                    enc->flying = b;
+                any = true;
+            }
+        }
+        if (!any)
+        {
+            timespec ts = {0, (session->pollSleepUs > 0 ? session->pollSleepUs : 1) * 500L};
+            nanosleep(&ts, nullptr);
+        }
     }
 }
 
@@ -770,11 +873,22 @@ extern "C" int hvbenc_create(int device, int bytes_per_sample, int bit_depth, in
     enc->partition();
     if (const char *v = getenv("HVB_POLLER")) enc->usePoller = atoi(v) != 0;
     if (const char *v = getenv("HVB_POLL_SLEEP_US")) enc->pollSleepUs = atoi(v);
-    enc->poller = std::thread(pollLoop, enc);
+    int nServices = 4;
+    if (const char *v = getenv("HVB_SERVICE_THREADS")) nServices = std::max(0, std::min(16, atoi(v)));
     for (Engine *engine : enc->engines)
     {
         engine->session = enc;
-        engine->dispatcher = std::thread(dispatch, engine);
+        if (!engine->doneFlag) nServices = 0; // (HVB_DONE_FLAG=0: the flag is what the service threads watch)
+    }
+    if (nServices > 0)
+    {
+        nServices = std::min(nServices, (int)enc->engines.size());
+        for (int k = 0; k < nServices; ++k) enc->services.emplace_back(serviceLoop, enc, k, nServices);
+    }
+    else
+    {
+        enc->poller = std::thread(pollLoop, enc);
+        for (Engine *engine : enc->engines) engine->dispatcher = std::thread(dispatch, engine);
     }
     *out = enc;
     return HVB_OK;
@@ -783,6 +897,19 @@ extern "C" int hvbenc_create(int device, int bytes_per_sample, int bit_depth, in
 extern "C" void hvbenc_destroy(hvbenc *enc)
 {
     if (!enc) return;
+    if (!enc->services.empty())
+    {
+        // let the batches in flight come back and the gathered requests go out, then stop sweeping
+        for (int spin = 0; spin < 20000; ++spin)
+        {
+            bool busy = false;
+            for (Engine *engine : enc->engines) busy |= engine->inflight.load() > 0;
+            if (!busy) break;
+            std::this_thread::sleep_for(std::chrono::microseconds(100));
+        }
+        enc->serviceStop.store(true, std::memory_order_release);
+        for (std::thread &t : enc->services) t.join();
+    }
     for (Engine *engine : enc->engines) destroyEngine(engine);
     {
         std::lock_guard<std::mutex> g(enc->pollM);
