@@ -465,12 +465,15 @@ def reference_encoder_fps(width, height, frames=6):
 # ------------------------------------------------------------------------------------------------
 # the encoders
 # ------------------------------------------------------------------------------------------------
-# The submission queue and the hooks as the bench runs them (measured on the 16-core B200 box, profiles/r02f_*): the encoder's pool threads are
-# fiber schedulers (integration/fiber_pool.cpp), so an instance needs two threads, not dozens; many instances (segments) in flight supply the
-# hand-overs that fill the batches; engines are grouped by kind.  HVB_HOOKS / thresholds: which blocks are worth a hand-over -- the transform
-# blocks (inter CUs and intra candidates, 16x16 and larger: DCT + RDOQ + reconstruction), which are 56 % of the reference's host time
-# (profiles/r02f_host_profile.txt); the motion search and the sweeps of small blocks cost the host less than the hand-over.
-QUEUE_ENV = {"HVB_ENGINES": "32", "HVB_FIBERS": "128", "HVB_HOOKS": "48", "HVB_INTRA_TU_MIN_LOG2": "4", "HVB_TU_MIN_LOG2": "4"}
+# The submission queue and the hooks as the bench runs them, chosen by end-to-end frames per second on the 16-core B200 box
+# (profiles/r02f_segments_matrix_c*.jsonl): the encoder's pool threads are fiber schedulers (integration/fiber_pool.cpp), so an instance needs
+# three threads, not dozens, and twelve instances (segments) are in flight; engines are grouped by kind.  HVB_HOOKS / thresholds: which blocks
+# leave the host -- the 32x32 transform blocks of intra candidates and the transform trees of 64x64 inter CUs (DCT + RDOQ + reconstruction;
+# the transform blocks are 56 % of the reference's host time, profiles/r02f_host_profile.txt).  Wider settings (16x16 blocks, the motion
+# search, the sweeps: tools/segments_matrix.py) are bit-identical too and slower end to end: a hand-over's latency is on the row's critical
+# path and the serial RDOQ walk of one block is slower on a device thread than on a host core.
+QUEUE_ENV = {"HVB_ENGINES": "12", "HVB_ENGINE_SHARES": "1,1,1,1,1,7", "HVB_FIBERS": "128", "HVB_HOOKS": "48", "HVB_INTRA_TU_MIN_LOG2": "5",
+             "HVB_TU_MIN_LOG2": "6"}
 
 
 def host_plan(args, world):
@@ -478,7 +481,7 @@ def host_plan(args, world):
     cores = os.cpu_count() or 16
     per_rank = max(4, cores // max(1, world))
     parallel = args.parallel_segments or max(2, min(12, (3 * per_rank) // 4, args.steps))
-    threads = args.threads or max(1, min(8, (3 * per_rank) // (2 * parallel)))
+    threads = args.threads or max(2, min(8, (9 * per_rank) // (4 * parallel)))
     return cores, parallel, threads
 
 
@@ -727,7 +730,7 @@ def main():
     with ClockSampler(local) as clocks:
         barrier()
         wall, inner, stats, _md5, _size, cmd = run_segments(args, clip, frames, job_dir if world > 1 else rank_dir, "timed", parallel, threads,
-                                                            rank, local, ranks=world)
+                                                            rank, local, profile=True, ranks=world)
         barrier()
     if world > 1 and rank == 0:
         parts = [job_dir / f"timed.bit.seg{k}" for k in range(args.steps)]
@@ -761,6 +764,13 @@ def main():
         line["bitstream_md5_equals_asm0"] = bool(md5 == ref0["bitstream_md5"])
         line["identity"] = {"frames": n, "bitstream_bytes": size, "md5": md5, "reference_asm0_md5": ref0["bitstream_md5"],
                             "reference_asm0_fps": ref0["fps"], "cmd": ref0["cmd"]}
+    # ---- the same driver with every hook off (the reference's JIT path in 12 instances): what the segment parallelism alone is worth -----
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n = min(frames, 4 * seg)
+        w0, i0, _s, _m, _z, _c = run_segments(args, clip, n, rank_dir, "hostonly", parallel, threads, rank, local, extra_env={"HVB_BATCHED": "0"})
+        line["host_only_same_driver"] = {"value": n / i0, "e2e": n / w0, "unit": UNIT, "frames": n,
+                                         "note": "turing_b200_segments with HVB_BATCHED=0: no device work at all, the reference's AVX2 path in "
+                                                 f"{parallel} instances x {threads} threads -- the share of `value` that is the driver's, not the device's"}
     # ---- the reference on the host cores (reported baseline) -----------------------------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu and REFERENCE_ENCODER.exists():
         n = min(args.clip_frames, 3 * seg)

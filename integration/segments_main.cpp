@@ -110,7 +110,10 @@ int main(int argc, const char *argv[])
         return 2;
     }
     // device pictures: every instance keeps its DPB and a source + reconstruction per picture in flight
-    setenv("HVB_POOL_PICTURES", std::to_string(std::min(900, 48 * parallel + 16)).c_str(), 0);
+    // (with the search hooks off only source pictures go up: the pictures an instance has in flight, HVB_HOOKS bits 0-2)
+    const char *hooks = getenv("HVB_HOOKS");
+    const bool references = !hooks || (atoi(hooks) & 7);
+    setenv("HVB_POOL_PICTURES", std::to_string(std::min(900, (references ? 48 : 20) * parallel + 16)).c_str(), 0);
     // the device session before the clock starts (CUDA context, page-locked buffers, the picture pool: a one-off)
     if (width > 0 && height > 0 && hvbhooks::on())
     {

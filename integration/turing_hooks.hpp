@@ -529,6 +529,7 @@ template <class Sample, class H> void uploadInput(H &h, PictureWrapper &wrapper)
 template <class Sample, class H> void uploadReconstructedCtu(H &h, Picture<Sample> &picture, int rx, int ry)
 {
     if (!on()) return;
+    if (!(enabledMask() & 7)) return; // no search / PU-cost hook: nothing on the device reads a reference picture
     if (isSubLayerNonReferencePicture(h[nal_unit_type()])) return;
     hvbenc *enc = sessionOf(h);
     const int pic = pictureId(&picture, false);
