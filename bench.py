@@ -472,7 +472,7 @@ def reference_encoder_fps(width, height, frames=6):
 # the transform blocks are 56 % of the reference's host time, profiles/r02f_host_profile.txt).  Wider settings (16x16 blocks, the motion
 # search, the sweeps: tools/segments_matrix.py) are bit-identical too and slower end to end: a hand-over's latency is on the row's critical
 # path and the serial RDOQ walk of one block is slower on a device thread than on a host core.
-QUEUE_ENV = {"HVB_ENGINES": "12", "HVB_ENGINE_SHARES": "1,1,1,1,1,7", "HVB_FIBERS": "128", "HVB_HOOKS": "48", "HVB_INTRA_TU_MIN_LOG2": "5",
+QUEUE_ENV = {"HVB_ENGINES": "20", "HVB_ENGINE_SHARES": "1,1,1,1,1,15", "HVB_FIBERS": "128", "HVB_HOOKS": "48", "HVB_INTRA_TU_MIN_LOG2": "5",
              "HVB_TU_MIN_LOG2": "6"}
 
 
