@@ -39,11 +39,11 @@ ENTRIES = {
         },
         entry=r'''
 extern "C" void emu_sad(const HvbPlane *planes, const hvb_metric_task *tasks, int n, int32_t *out, int bps, int grid)
-{ ''' + _both("emuLaunch(grid, kWarpsPerBlock * 32, [&] { sadKernel<Sample>(planes, tasks, n, out); }); emuLaunch(grid, kWarpsPerBlock * 32, [&] { sadSmallKernel<Sample>(planes, tasks, n, out); });") + r''' }
+{ ''' + _both("emuLaunch(grid, kWarpsPerBlock * 32, [&] { sadKernel<Sample>(planes, tasks, n, out); });") + r''' }
 extern "C" void emu_sad4(const HvbPlane *planes, const hvb_sad4_task *tasks, int n, int32_t *out, int bps, int grid)
 { ''' + _both("emuLaunch(grid, kWarpsPerBlock * 32, [&] { sad4Kernel<Sample>(planes, tasks, n, out); });") + r''' }
 extern "C" void emu_ssd(const HvbPlane *planes, const hvb_metric_task *tasks, int n, uint32_t *out, int bps, int grid)
-{ ''' + _both("emuLaunch(grid, kWarpsPerBlock * 32, [&] { ssdKernel<Sample>(planes, tasks, n, out); }); emuLaunch(grid, kWarpsPerBlock * 32, [&] { ssdSmallKernel<Sample>(planes, tasks, n, out); });") + r''' }
+{ ''' + _both("emuLaunch(grid, kWarpsPerBlock * 32, [&] { ssdKernel<Sample>(planes, tasks, n, out); });") + r''' }
 extern "C" void emu_satd(const HvbPlane *planes, const hvb_metric_task *tasks, int n, int32_t *out, int bps, int grid)
 {
     int leftover[3] = {0, 0, 0}; // [0]: blocks for satdKernel, [2]: blocks for satdMmaSmallKernel

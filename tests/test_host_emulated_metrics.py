@@ -18,13 +18,13 @@ extern "C" void emu_metric(int which, const HvbPlane *planes, const hvb_metric_t
 {
     if (which == 0)
     {
-        if (bps == 1) { emuLaunch(grid, kWarpsPerBlock * 32, [&] { sadKernel<uint8_t>(planes, tasks, n, out); }); emuLaunch(grid, kWarpsPerBlock * 32, [&] { sadSmallKernel<uint8_t>(planes, tasks, n, out); }); }
-        else { emuLaunch(grid, kWarpsPerBlock * 32, [&] { sadKernel<uint16_t>(planes, tasks, n, out); }); emuLaunch(grid, kWarpsPerBlock * 32, [&] { sadSmallKernel<uint16_t>(planes, tasks, n, out); }); }
+        if (bps == 1) emuLaunch(grid, kWarpsPerBlock * 32, [&] { sadKernel<uint8_t>(planes, tasks, n, out); });
+        else emuLaunch(grid, kWarpsPerBlock * 32, [&] { sadKernel<uint16_t>(planes, tasks, n, out); });
     }
     else if (which == 1)
     {
-        if (bps == 1) { emuLaunch(grid, kWarpsPerBlock * 32, [&] { ssdKernel<uint8_t>(planes, tasks, n, reinterpret_cast<uint32_t *>(out)); }); emuLaunch(grid, kWarpsPerBlock * 32, [&] { ssdSmallKernel<uint8_t>(planes, tasks, n, reinterpret_cast<uint32_t *>(out)); }); }
-        else { emuLaunch(grid, kWarpsPerBlock * 32, [&] { ssdKernel<uint16_t>(planes, tasks, n, reinterpret_cast<uint32_t *>(out)); }); emuLaunch(grid, kWarpsPerBlock * 32, [&] { ssdSmallKernel<uint16_t>(planes, tasks, n, reinterpret_cast<uint32_t *>(out)); }); }
+        if (bps == 1) emuLaunch(grid, kWarpsPerBlock * 32, [&] { ssdKernel<uint8_t>(planes, tasks, n, reinterpret_cast<uint32_t *>(out)); });
+        else emuLaunch(grid, kWarpsPerBlock * 32, [&] { ssdKernel<uint16_t>(planes, tasks, n, reinterpret_cast<uint32_t *>(out)); });
     }
     else
     {

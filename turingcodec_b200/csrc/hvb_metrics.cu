@@ -99,13 +99,6 @@ __device__ __forceinline__ unsigned ssdWords(uint4 a, uint4 b, unsigned acc)
 //   second operand anywhere (a motion-search candidate)       a chunk is the five aligned words that contain it and four
 //                                                             funnel shifts; two turns in flight.
 // Everything else (partial chunks, AMP widths, a source off the grid) returns false and takes the caller's general loop.
-// does a block pair take the lean loops of alignedChunks?  (sadKernel / ssdKernel own these blocks, sadSmallKernel / ssdSmallKernel the rest)
-__device__ __forceinline__ bool leanBlock(const uint8_t *pa, intptr_t pitchA, intptr_t pitchB, int wb)
-{
-    const int cpr = wb >> 4;
-    return !((reinterpret_cast<uintptr_t>(pa) | (uintptr_t)pitchA | (uintptr_t)pitchB | (uintptr_t)wb) & 15) && (cpr == 4 || cpr == 8);
-}
-
 template <typename F>
 __device__ __forceinline__ bool alignedChunks(const uint8_t *pa, intptr_t pitchA, const uint8_t *pb, intptr_t pitchB, int wb, int h, int lane, F consume)
 {
@@ -171,18 +164,31 @@ __device__ __forceinline__ bool alignedChunks(const uint8_t *pa, intptr_t pitchA
 // round the lanes, every operand chunk is one or two 128-bit loads whatever the block's alignment (co-located blocks,
 // motion-search candidates, 8- and 16-bit samples alike); the excess bytes of a row's last chunk are masked in both
 // operands, so they contribute |0 - 0|.
-// Two kernels per batch, each owning the blocks its loop is good at (a batch is usually of one kind, so one of the launches only
-// walks the task array).  Wide rows on the 16-byte grid stream through the lean loops above, whose deep per-lane pipelines cost
-// registers (three CTAs per SM); everything else -- 32x32 and smaller 8-bit blocks above all, 2 KB or less per operand -- wants warps,
-// not depth: the plain loop at full occupancy (B200, 32x32 8-bit co-located / as a search candidate: 60 % / 49 % of the HBM peak
-// in the plain kernel, 42 % / 37 % when it shared the lean kernel's register budget).
+template <typename Sample>
+__device__ __forceinline__ int sadBlock(const Sample *a, int sa, const Sample *b, int sb, int w, int h, int lane)
+{
+    const int B = (int)sizeof(Sample), wb = w * B, cpr = (wb + 15) >> 4, total = cpr * h;
+    const uint8_t *pa = reinterpret_cast<const uint8_t *>(a), *pb = reinterpret_cast<const uint8_t *>(b);
+    unsigned acc = 0;
+    if (alignedChunks(pa, (intptr_t)sa * B, pb, (intptr_t)sb * B, wb, h, lane, [&](const uint4 &va, const uint4 &vb) { acc += sadWords<Sample>(va, vb); }))
+        return (int)acc;
+#pragma unroll 2
+    for (int i = lane; i < total; i += 32)
+    {
+        const int y = i / cpr, x = (i - y * cpr) << 4;
+        const uint4 va = maskChunk(load16(pa + (intptr_t)y * sa * B + x), wb - x);
+        const uint4 vb = maskChunk(load16(pb + (intptr_t)y * sb * B + x), wb - x);
+        acc += sadWords<Sample>(va, vb);
+    }
+    return (int)acc;
+}
+
 template <typename Sample>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
     sadKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out)
 {
     const int lane = threadIdx.x & 31;
     const int warpsTotal = gridDim.x * kWarpsPerBlock;
-    const int B = (int)sizeof(Sample);
     int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (t >= n) return;
     hvb_metric_task task = tasks[t];
@@ -193,50 +199,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
         hvb_metric_task next = task;
         if (tn < n) next = tasks[tn];
         int sa, sb;
-        const uint8_t *pa = reinterpret_cast<const uint8_t *>(hvbBlockPtr<Sample>(planes, task.a, sa));
-        const uint8_t *pb = reinterpret_cast<const uint8_t *>(hvbBlockPtr<Sample>(planes, task.b, sb));
-        if (leanBlock(pa, (intptr_t)sa * B, (intptr_t)sb * B, task.w * B))
-        {
-            unsigned sum = 0;
-            alignedChunks(pa, (intptr_t)sa * B, pb, (intptr_t)sb * B, task.w * B, task.h, lane,
-                          [&](const uint4 &va, const uint4 &vb) { sum += sadWords<Sample>(va, vb); });
-            int acc = hvbWarpSum((int)sum);
-            if (sizeof(Sample) == 2) acc >>= 2;
-            if (lane == 0) out[t] = acc;
-        }
+        const Sample *a = hvbBlockPtr<Sample>(planes, task.a, sa);
+        const Sample *b = hvbBlockPtr<Sample>(planes, task.b, sb);
+        int acc = hvbWarpSum(sadBlock<Sample>(a, sa, b, sb, task.w, task.h, lane));
+        if (sizeof(Sample) == 2) acc >>= 2;
+        if (lane == 0) out[t] = acc;
         if (tn >= n) break;
         task = next;
         t = tn;
-    }
-}
-
-template <typename Sample>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-    sadSmallKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, int32_t *__restrict__ out)
-{
-    const int lane = threadIdx.x & 31;
-    const int warpsTotal = gridDim.x * kWarpsPerBlock;
-    const int B = (int)sizeof(Sample);
-    for (int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n; t += warpsTotal)
-    {
-        const hvb_metric_task task = tasks[t];
-        int sa, sb;
-        const uint8_t *pa = reinterpret_cast<const uint8_t *>(hvbBlockPtr<Sample>(planes, task.a, sa));
-        const uint8_t *pb = reinterpret_cast<const uint8_t *>(hvbBlockPtr<Sample>(planes, task.b, sb));
-        const int wb = task.w * B, cpr = (wb + 15) >> 4, total = cpr * task.h;
-        if (leanBlock(pa, (intptr_t)sa * B, (intptr_t)sb * B, wb)) continue; // sadKernel's
-        unsigned sum = 0;
-#pragma unroll 2
-        for (int i = lane; i < total; i += 32)
-        {
-            const int y = i / cpr, x = (i - y * cpr) << 4;
-            const uint4 va = maskChunk(load16(pa + (intptr_t)y * sa * B + x), wb - x);
-            const uint4 vb = maskChunk(load16(pb + (intptr_t)y * sb * B + x), wb - x);
-            sum += sadWords<Sample>(va, vb);
-        }
-        int acc = hvbWarpSum((int)sum);
-        if (sizeof(Sample) == 2) acc >>= 2;
-        if (lane == 0) out[t] = acc;
     }
 }
 
@@ -299,48 +269,25 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
         int sa, sb;
         const uint8_t *pa = reinterpret_cast<const uint8_t *>(hvbBlockPtr<Sample>(planes, task.a, sa));
         const uint8_t *pb = reinterpret_cast<const uint8_t *>(hvbBlockPtr<Sample>(planes, task.b, sb));
-        if (leanBlock(pa, (intptr_t)sa * B, (intptr_t)sb * B, task.w * B))
+        const int wb = task.w * B, h = task.h, cpr = (wb + 15) >> 4, total = cpr * h;
+        unsigned acc = 0; // modulo 2^32, like the reference's uint32_t accumulator (havoc/ssd.cpp:28-43)
+        if (!alignedChunks(pa, (intptr_t)sa * B, pb, (intptr_t)sb * B, wb, h, lane, [&](const uint4 &va, const uint4 &vb) { acc = ssdWords<Sample>(va, vb, acc); }))
         {
-            unsigned acc = 0; // modulo 2^32, like the reference's uint32_t accumulator (havoc/ssd.cpp:28-43)
-            alignedChunks(pa, (intptr_t)sa * B, pb, (intptr_t)sb * B, task.w * B, task.h, lane,
-                          [&](const uint4 &va, const uint4 &vb) { acc = ssdWords<Sample>(va, vb, acc); });
-            acc = hvbWarpSumU(acc);
-            if (sizeof(Sample) == 2) acc >>= 4;
-            if (lane == 0) out[t] = acc;
-        }
-        if (tn >= n) break;
-        task = next;
-        t = tn;
-    }
-}
-
-template <typename Sample>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-    ssdSmallKernel(const HvbPlane *__restrict__ planes, const hvb_metric_task *__restrict__ tasks, int n, uint32_t *__restrict__ out)
-{
-    const int lane = threadIdx.x & 31;
-    const int warpsTotal = gridDim.x * kWarpsPerBlock;
-    const int B = (int)sizeof(Sample);
-    for (int t = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); t < n; t += warpsTotal)
-    {
-        const hvb_metric_task task = tasks[t];
-        int sa, sb;
-        const uint8_t *pa = reinterpret_cast<const uint8_t *>(hvbBlockPtr<Sample>(planes, task.a, sa));
-        const uint8_t *pb = reinterpret_cast<const uint8_t *>(hvbBlockPtr<Sample>(planes, task.b, sb));
-        const int wb = task.w * B, cpr = (wb + 15) >> 4, total = cpr * task.h;
-        if (leanBlock(pa, (intptr_t)sa * B, (intptr_t)sb * B, wb)) continue; // ssdKernel's
-        unsigned acc = 0;
 #pragma unroll 2
-        for (int i = lane; i < total; i += 32)
-        {
-            const int y = i / cpr, x = (i - y * cpr) << 4;
-            const uint4 va = maskChunk(load16(pa + (intptr_t)y * sa * B + x), wb - x);
-            const uint4 vb = maskChunk(load16(pb + (intptr_t)y * sb * B + x), wb - x);
-            acc = ssdWords<Sample>(va, vb, acc);
+            for (int i = lane; i < total; i += 32)
+            {
+                const int y = i / cpr, x = (i - y * cpr) << 4;
+                const uint4 va = maskChunk(load16(pa + (intptr_t)y * sa * B + x), wb - x);
+                const uint4 vb = maskChunk(load16(pb + (intptr_t)y * sb * B + x), wb - x);
+                acc = ssdWords<Sample>(va, vb, acc);
+            }
         }
         acc = hvbWarpSumU(acc);
         if (sizeof(Sample) == 2) acc >>= 4;
         if (lane == 0) out[t] = acc;
+        if (tn >= n) break;
+        task = next;
+        t = tn;
     }
 }
 
@@ -1034,9 +981,6 @@ extern "C" int hvb_sad_batch(hvb_context *ctx, const hvb_metric_task *tasks, int
     HVB_DISPATCH_SAMPLE(ctx, sadKernel, gridFor<hvb_metric_task>(ctx, n), ctx->dPlanes,
                         static_cast<const hvb_metric_task *>(st.dTasks), n, static_cast<int32_t *>(st.dOut));
     HVB_LAUNCH_CHECK(ctx, "sadKernel");
-    HVB_DISPATCH_SAMPLE(ctx, sadSmallKernel, gridFor<hvb_metric_task>(ctx, n), ctx->dPlanes,
-                        static_cast<const hvb_metric_task *>(st.dTasks), n, static_cast<int32_t *>(st.dOut));
-    HVB_LAUNCH_CHECK(ctx, "sadSmallKernel");
     return hvbStageOut(ctx, out, sizeof(int32_t) * n, mem, st);
 }
 
@@ -1073,9 +1017,6 @@ extern "C" int hvb_ssd_batch(hvb_context *ctx, const hvb_metric_task *tasks, int
     HVB_DISPATCH_SAMPLE(ctx, ssdKernel, gridFor<hvb_metric_task>(ctx, n), ctx->dPlanes,
                         static_cast<const hvb_metric_task *>(st.dTasks), n, static_cast<uint32_t *>(st.dOut));
     HVB_LAUNCH_CHECK(ctx, "ssdKernel");
-    HVB_DISPATCH_SAMPLE(ctx, ssdSmallKernel, gridFor<hvb_metric_task>(ctx, n), ctx->dPlanes,
-                        static_cast<const hvb_metric_task *>(st.dTasks), n, static_cast<uint32_t *>(st.dOut));
-    HVB_LAUNCH_CHECK(ctx, "ssdSmallKernel");
     return hvbStageOut(ctx, out, sizeof(uint32_t) * n, mem, st);
 }
 
