@@ -24,7 +24,7 @@ cudaError_t cudaGetDeviceProperties_v2(cudaDeviceProp *prop, int)
 }
 cudaError_t cudaDeviceGetAttribute(int *value, cudaDeviceAttr attr, int)
 {
-    *value = attr == cudaDevAttrMultiProcessorCount ? 148 : 0;
+    *value = attr == cudaDevAttrMultiProcessorCount ? 148 : attr == cudaDevAttrComputeCapabilityMajor ? 10 : 0;
     return cudaSuccess;
 }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }

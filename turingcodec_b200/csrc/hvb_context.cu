@@ -52,11 +52,19 @@ int hvbCuda(hvb_context *ctx, cudaError_t e, const char *what)
 
 extern "C" int hvb_device_ok(int device)
 {
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return 0;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 0;
-    return prop.major == 10 ? 1 : 0; // kernels are compiled for sm_100a only
+    // asked once per device: cudaGetDeviceProperties takes tens of milliseconds, and a session creates dozens of contexts
+    static std::mutex m;
+    static int known[64]; // 0: not asked, 1: usable, 2: not
+    if (device < 0) return 0;
+    std::lock_guard<std::mutex> g(m);
+    if (device < 64 && known[device]) return known[device] == 1;
+    int count = 0, major = 0;
+    int ok = 0;
+    if (cudaGetDeviceCount(&count) == cudaSuccess && device < count &&
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) == cudaSuccess)
+        ok = major == 10; // kernels are compiled for sm_100a only
+    if (device < 64) known[device] = ok ? 1 : 2;
+    return ok;
 }
 
 extern "C" int hvb_create(int device, int bytes_per_sample, int bit_depth, hvb_context **out)
