@@ -49,6 +49,29 @@ def test_batched_encoder_on_the_emulated_library_matches_reference(cpu_libhvb, t
     assert '"me": {"tasks": 0' not in res.stderr and "hvbenc stats" in res.stderr  # the queue did the work
 
 
+MODES = {
+    "thread_per_row": dict(HVB_FIBERS="0"),                                  # the reference's pool loop: a hand-over sleeps on a condition variable
+    "service_threads": dict(HVB_SERVICE_THREADS="2"),                        # no dispatcher / completion threads: two threads sweep the engines
+    "stream_queries": dict(HVB_DONE_FLAG="0"),                               # completion by hvb_poll instead of the flag the stream writes
+    "engines_by_kind": dict(HVB_ENGINES="12", HVB_ENGINE_SHARES="1,1,1,1,1,7"),
+    "transform_blocks_only": dict(HVB_HOOKS="48", HVB_INTRA_TU_MIN_LOG2="2", HVB_TU_MIN_LOG2="3"),  # bench.py's hooks, every block size
+}
+
+
+@pytest.mark.parametrize("mode", sorted(MODES))
+def test_queue_modes_give_the_same_bitstream(cpu_libhvb, tmp_path, mode):
+    """every way the submission queue and the pool can be run (fiber schedulers are the default of the other tests) writes the reference's stream"""
+    width, height, frames = 128, 64, 2
+    clip = encoder.write_clip(tmp_path / "clip.yuv", width, height, frames)
+    common = ["--input-res", f"{width}x{height}", "--frame-rate", "24", "--frames", frames, *encoder.MEDIUM]
+    run([gpu_common.REFERENCE_ENCODER, "encode", "--asm", "0", "-o", tmp_path / "ref.bit", *common, clip])
+    env = dict(HVB_ENGINES="3", HVB_STATS="1")
+    env.update(MODES[mode])
+    res = run([encoder.BATCHED, "encode", "--threads", "3", "-o", tmp_path / "b.bit", *common, clip], cpu_libhvb, **env)
+    assert (tmp_path / "b.bit").read_bytes() == (tmp_path / "ref.bit").read_bytes(), mode
+    assert "hvbenc stats" in res.stderr and '"tu_chain": {"tasks": 0' not in res.stderr
+
+
 def test_segment_parallel_driver_on_the_emulated_library_matches_reference_segment_run(cpu_libhvb, tmp_path):
     width, height, frames, seg = 64, 64, 7, 3
     clip = encoder.write_clip(tmp_path / "clip.yuv", width, height, frames)
