@@ -105,6 +105,10 @@ int hvb_device_ok(int device);
 /* luma width x height; chroma planes are (w/2) x (h/2).  pad = luma padding in samples on every
  * side (chroma gets pad/2); the reference uses 96 (StatePictures.h:154-156).  */
 int hvb_picture_create(hvb_context *ctx, int width, int height, int pad, int *pic);
+/* One device allocation for the planes of the next `count` pictures of this geometry (hvb_picture_create carves from it while it
+ * lasts; such a picture's memory returns with hvb_destroy, not hvb_picture_destroy): a session that creates hundreds of pictures
+ * spares as many trips through the allocator.  Once per context. */
+int hvb_picture_reserve(hvb_context *ctx, int width, int height, int pad, int count);
 int hvb_picture_destroy(hvb_context *ctx, int pic);
 /* copy rows [y0, y0+rows) of plane cIdx from host (stride in samples) */
 int hvb_picture_upload(hvb_context *ctx, int pic, int cIdx, const void *host, intptr_t stride,

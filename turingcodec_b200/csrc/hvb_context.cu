@@ -123,6 +123,7 @@ extern "C" void hvb_destroy(hvb_context *ctx)
         if (p.lfInfo) cudaFree(p.lfInfo);
         if (p.saoInfo) cudaFree(p.saoInfo);
     }
+    if (ctx->slab) cudaFree(ctx->slab);
     if (ctx->dPlanes) cudaFree(ctx->dPlanes);
     if (ctx->dTensorMaps) cudaFree(ctx->dTensorMaps);
     if (ctx->dLoopInfo) cudaFree(ctx->dLoopInfo);
@@ -345,7 +346,18 @@ extern "C" int hvb_picture_create(hvb_context *ctx, int width, int height, int p
         const size_t strideSamples = (padLeft + w + pd + 16 + (256 / ctx->bps - 1)) / (256 / ctx->bps) * (256 / ctx->bps);
         const size_t rows = (size_t)h + 2 * pd + 2; // +2 slack rows: vector loads may run a few bytes past a block
         const size_t bytes = strideSamples * rows * ctx->bps;
-        cudaError_t e = cudaMalloc(&p.alloc[c], bytes);
+        // from the context's reserve when there is one (hvb_picture_reserve: one allocation for a whole pool of pictures; the
+        // plane is then not the picture's to free), else its own allocation
+        void *mem = nullptr;
+        const size_t need = (bytes + 255) & ~size_t(255);
+        if (ctx->slab && ctx->slabUsed + need <= ctx->slabBytes)
+        {
+            mem = static_cast<char *>(ctx->slab) + ctx->slabUsed;
+            ctx->slabUsed += need;
+            p.alloc[c] = nullptr;
+        }
+        cudaError_t e = mem ? cudaSuccess : cudaMalloc(&p.alloc[c], bytes);
+        if (!mem) mem = p.alloc[c];
         if (e != cudaSuccess)
         {
             for (int k = 0; k < c; ++k)
@@ -355,15 +367,15 @@ extern "C" int hvb_picture_create(hvb_context *ctx, int width, int height, int p
             }
             return hvbCuda(ctx, e, "hvb_picture_create");
         }
-        cudaMemsetAsync(p.alloc[c], 0, bytes, ctx->stream);
+        if (p.alloc[c]) cudaMemsetAsync(mem, 0, bytes, ctx->stream); // (the reserve was cleared when it was made)
         p.allocBytes[c] = bytes;
-        p.plane[c].base = static_cast<char *>(p.alloc[c]) + ((size_t)pd * strideSamples + padLeft) * ctx->bps;
+        p.plane[c].base = static_cast<char *>(mem) + ((size_t)pd * strideSamples + padLeft) * ctx->bps;
         p.plane[c].stride = (int32_t)strideSamples;
         p.plane[c].width = w;
         p.plane[c].height = h;
         p.plane[c].pad = pd;
         p.plane[c].reserved = (int32_t)padLeft; // sample (-pd) of a row starts padLeft - pd samples into it; (padLeft + x) indexes the row
-        p.tmaBase[c] = p.alloc[c];
+        p.tmaBase[c] = mem;
         p.tmaRows[c] = (int)rows;
     }
     p.live = true;
@@ -371,6 +383,32 @@ extern "C" int hvb_picture_create(hvb_context *ctx, int width, int height, int p
     ctx->tensorMapsDirty = true;
     *pic = id;
     return HVB_OK;
+}
+
+extern "C" int hvb_picture_reserve(hvb_context *ctx, int width, int height, int pad, int count)
+{
+    HVB_CHECK_ARGS(ctx, width > 0 && height > 0 && pad >= 0 && !(width & 1) && !(height & 1) && !(pad & 1) && count > 0 && !ctx->slab);
+    cudaSetDevice(ctx->device);
+    size_t perPicture = 0;
+    for (int c = 0; c < 3; ++c)
+    {
+        // (the geometry of hvb_picture_create)
+        const int w = c ? width / 2 : width, h = c ? height / 2 : height, pd = c ? pad / 2 : pad;
+        const size_t padLeft = ((size_t)pd * ctx->bps + 255) / 256 * 256 / ctx->bps;
+        const size_t strideSamples = (padLeft + w + pd + 16 + (256 / ctx->bps - 1)) / (256 / ctx->bps) * (256 / ctx->bps);
+        const size_t rows = (size_t)h + 2 * pd + 2;
+        perPicture += (strideSamples * rows * ctx->bps + 255) & ~size_t(255);
+    }
+    const size_t bytes = perPicture * (size_t)count;
+    cudaError_t e = cudaMalloc(&ctx->slab, bytes);
+    if (e != cudaSuccess)
+    {
+        ctx->slab = nullptr;
+        return hvbCuda(ctx, e, "hvb_picture_reserve");
+    }
+    ctx->slabBytes = bytes;
+    ctx->slabUsed = 0;
+    return hvbCuda(ctx, cudaMemsetAsync(ctx->slab, 0, bytes, ctx->stream), "hvb_picture_reserve");
 }
 
 extern "C" int hvb_picture_wrap(hvb_context *ctx, void *host, intptr_t stride, int width, int height, int *pic)

@@ -93,6 +93,36 @@ struct Request
     int first, count;
 };
 
+// One page-locked allocation per engine, carved: pinning memory is slow, and an engine needs some thirty buffers.
+struct Arena
+{
+    hvb_context *ctx = nullptr;
+    char *base = nullptr;
+    size_t size = 0, used = 0;
+    static size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+    int reserve(hvb_context *c, size_t bytes)
+    {
+        ctx = c;
+        size = bytes;
+        used = 0;
+        return hvb_host_alloc(c, bytes, reinterpret_cast<void **>(&base));
+    }
+    template <class T> int take(T **out, size_t bytes)
+    {
+        *out = nullptr;
+        if (!bytes) return 0;
+        if (!base || used + padded(bytes) > size) return HVB_ERR_NOMEM;
+        *out = reinterpret_cast<T *>(base + used);
+        used += padded(bytes);
+        return 0;
+    }
+    void release()
+    {
+        if (base) hvb_host_free(ctx, base);
+        base = nullptr;
+    }
+};
+
 // one kind of task: two page-locked task / result arrays, the one being filled and the one on the device
 template <class Task, class Result, int ResultsPerTask = 1>
 struct Lane
@@ -104,25 +134,18 @@ struct Lane
     int n[2] = {0, 0};
     int64_t totalTasks = 0, totalBatches = 0;
 
-    int init(hvb_context *ctx, int cap)
+    static size_t bytes(int cap) { return 2 * (Arena::padded(sizeof(Task) * cap) + Arena::padded(sizeof(Result) * ResultsPerTask * cap)); }
+    int init(Arena &arena, int cap)
     {
         capacity = cap;
         for (int b = 0; b < 2; ++b)
         {
-            int rc = hvb_host_alloc(ctx, sizeof(Task) * cap, reinterpret_cast<void **>(&tasks[b]));
+            int rc = arena.take(&tasks[b], sizeof(Task) * cap);
             if (rc) return rc;
-            rc = hvb_host_alloc(ctx, sizeof(Result) * ResultsPerTask * cap, reinterpret_cast<void **>(&results[b]));
+            rc = arena.take(&results[b], sizeof(Result) * ResultsPerTask * cap);
             if (rc) return rc;
         }
         return 0;
-    }
-    void release(hvb_context *ctx)
-    {
-        for (int b = 0; b < 2; ++b)
-        {
-            if (tasks[b]) hvb_host_free(ctx, tasks[b]);
-            if (results[b]) hvb_host_free(ctx, results[b]);
-        }
     }
     // results of buffer b back to the callers; the waiters are collected for one wake-up pass
     void deliver(int b, int rc, std::vector<Waiter *> &wake)
@@ -212,6 +235,8 @@ struct Engine
     hvb_rdoq_ctx *snapshots[2] = {nullptr, nullptr};
     int nSnapshots[2] = {0, 0};
     int16_t *levelsHost = nullptr; // page-locked, kTuCapacity * 1024
+    Arena arena;                   // every page-locked buffer of the engine
+    bool serves[6] = {true, true, true, true, true, true}; // kinds this engine can be handed (engines by kind: its own group's only)
 
     double deviceSeconds = 0;
     int64_t dispatches = 0;
@@ -743,31 +768,41 @@ int createEngine(int device, int bytes_per_sample, int bit_depth, int width, int
 int equipEngine(Engine *enc)
 {
     hvb_context *ctx = enc->ctx;
-    int rc = enc->me.init(ctx, 1024);
-    if (!rc) rc = enc->bi.init(ctx, 1024);
-    if (!rc) rc = enc->pu.init(ctx, 2048);
-    if (!rc) rc = enc->intra.init(ctx, 1024);
-    if (!rc) rc = enc->tu.init(ctx, kTuCapacity);
     const int rows = kTuCell * (kTuCapacity / kTuCellsPerRow);
     const size_t cellBytes = (size_t)kTuCell * kTuCellsPerRow * enc->bps * rows;
+    // buffers of kinds the engine is never handed (engines by kind) are not allocated: uploads need 16 MB of staging, transform
+    // blocks 6 MB of cells and levels
+    const size_t uploadBytes = enc->serves[0] ? kUploadBytes : 0, poolBytes = enc->serves[4] ? kPoolSamples * enc->bps : 0;
+    const size_t tuCells = enc->serves[5] ? cellBytes : 0, levelBytes = enc->serves[5] ? sizeof(int16_t) * 1024 * kTuCapacity : 0;
+    const size_t snapshotBytes = enc->serves[5] ? sizeof(hvb_rdoq_ctx) * kRdoqSnapshots : 0;
+    const size_t total = decltype(enc->me)::bytes(1024) + decltype(enc->bi)::bytes(1024) + decltype(enc->pu)::bytes(2048) +
+                         decltype(enc->intra)::bytes(1024) + decltype(enc->tu)::bytes(kTuCapacity) +
+                         2 * (Arena::padded(uploadBytes) + Arena::padded(poolBytes) + 2 * Arena::padded(tuCells) + Arena::padded(snapshotBytes)) +
+                         Arena::padded(levelBytes) + 256;
+    int rc = enc->arena.reserve(ctx, total);
+    if (!rc) rc = enc->me.init(enc->arena, 1024);
+    if (!rc) rc = enc->bi.init(enc->arena, 1024);
+    if (!rc) rc = enc->pu.init(enc->arena, 2048);
+    if (!rc) rc = enc->intra.init(enc->arena, 1024);
+    if (!rc) rc = enc->tu.init(enc->arena, kTuCapacity);
     for (int b = 0; b < 2 && !rc; ++b)
     {
-        rc = hvb_host_alloc(ctx, kUploadBytes, reinterpret_cast<void **>(&enc->uploadStage[b]));
-        if (!rc) rc = hvb_host_alloc(ctx, kPoolSamples * enc->bps, reinterpret_cast<void **>(&enc->poolStage[b]));
-        if (!rc) rc = hvb_host_alloc(ctx, cellBytes, reinterpret_cast<void **>(&enc->tuPredHost[b]));
-        if (!rc) rc = hvb_host_alloc(ctx, cellBytes, reinterpret_cast<void **>(&enc->tuRecHost[b]));
-        if (!rc) rc = hvb_host_alloc(ctx, sizeof(hvb_rdoq_ctx) * kRdoqSnapshots, reinterpret_cast<void **>(&enc->snapshots[b]));
-        if (!rc) rc = hvb_picture_wrap(ctx, enc->tuPredHost[b], kTuCell * kTuCellsPerRow, kTuCell * kTuCellsPerRow, rows, &enc->tuPredPic[b]);
-        if (!rc) rc = hvb_picture_wrap(ctx, enc->tuRecHost[b], kTuCell * kTuCellsPerRow, kTuCell * kTuCellsPerRow, rows, &enc->tuRecPic[b]);
+        rc = enc->arena.take(&enc->uploadStage[b], uploadBytes);
+        if (!rc) rc = enc->arena.take(&enc->poolStage[b], poolBytes);
+        if (!rc) rc = enc->arena.take(&enc->tuPredHost[b], tuCells);
+        if (!rc) rc = enc->arena.take(&enc->tuRecHost[b], tuCells);
+        if (!rc) rc = enc->arena.take(&enc->snapshots[b], snapshotBytes);
+        if (!rc && tuCells) rc = hvb_picture_wrap(ctx, enc->tuPredHost[b], kTuCell * kTuCellsPerRow, kTuCell * kTuCellsPerRow, rows, &enc->tuPredPic[b]);
+        if (!rc && tuCells) rc = hvb_picture_wrap(ctx, enc->tuRecHost[b], kTuCell * kTuCellsPerRow, kTuCell * kTuCellsPerRow, rows, &enc->tuRecPic[b]);
     }
-    if (!rc) rc = hvb_host_alloc(ctx, sizeof(int16_t) * 1024 * kTuCapacity, reinterpret_cast<void **>(&enc->levelsHost));
+    if (!rc) rc = enc->arena.take(&enc->levelsHost, levelBytes);
     const char *flagEnv = getenv("HVB_DONE_FLAG");
     if (!rc && !(flagEnv && atoi(flagEnv) == 0))
     {
-        rc = hvb_host_alloc(ctx, 64, reinterpret_cast<void **>(&enc->doneFlag));
+        rc = enc->arena.take(&enc->doneFlag, 64);
         if (!rc) *enc->doneFlag = 0;
     }
-    if (!rc)
+    if (!rc && levelBytes)
     {
         // block i of a batch owns elements [1024 i, 1024 (i + 1)) of the level pool, which is the page-locked array the results
         // are read from; every batch of the queue takes the one-launch form of the chain
@@ -789,21 +824,7 @@ void destroyEngine(Engine *enc)
     enc->workCv.notify_all();
     if (enc->dispatcher.joinable()) enc->dispatcher.join();
     hvb_sync(enc->ctx);
-    enc->me.release(enc->ctx);
-    enc->bi.release(enc->ctx);
-    enc->pu.release(enc->ctx);
-    enc->intra.release(enc->ctx);
-    enc->tu.release(enc->ctx);
-    for (int b = 0; b < 2; ++b)
-    {
-        if (enc->uploadStage[b]) hvb_host_free(enc->ctx, enc->uploadStage[b]);
-        if (enc->poolStage[b]) hvb_host_free(enc->ctx, enc->poolStage[b]);
-        if (enc->tuPredHost[b]) hvb_host_free(enc->ctx, enc->tuPredHost[b]);
-        if (enc->tuRecHost[b]) hvb_host_free(enc->ctx, enc->tuRecHost[b]);
-        if (enc->snapshots[b]) hvb_host_free(enc->ctx, enc->snapshots[b]);
-    }
-    if (enc->levelsHost) hvb_host_free(enc->ctx, enc->levelsHost);
-    if (enc->doneFlag) hvb_host_free(enc->ctx, enc->doneFlag);
+    enc->arena.release();
 }
 
 struct Clock
@@ -849,6 +870,7 @@ extern "C" int hvbenc_create(int device, int bytes_per_sample, int bit_depth, in
     const double tEngines = since();
     // the pictures: owned by engine 0, imported by the others in the same order, so an id means the same picture everywhere
     enc->slots.resize(pool_pictures);
+    if (!rc) rc = hvb_picture_reserve(enc->engines[0]->ctx, width, height, 96, pool_pictures);
     for (int i = 0; i < pool_pictures && !rc; ++i)
     {
         rc = hvb_picture_create(enc->engines[0]->ctx, width, height, 96, &enc->slots[i].pic);
@@ -860,6 +882,10 @@ extern "C" int hvbenc_create(int device, int bytes_per_sample, int bit_depth, in
         }
     }
     const double tPictures = since();
+    enc->partition();
+    if (enc->partitioned)
+        for (size_t e = 0; e < enc->engines.size(); ++e)
+            for (int k = 0; k < 6; ++k) enc->engines[e]->serves[k] = (int)e >= enc->first[k] && (int)e < enc->first[k + 1];
     for (size_t e = 0; e < enc->engines.size() && !rc; ++e) rc = equipEngine(enc->engines[e]);
     if (getenv("HVB_STATS") && atoi(getenv("HVB_STATS")))
         fprintf(stderr, "hvbenc set-up: %d contexts %.3f s, %d pictures %.3f s, page-locked buffers %.3f s\n", nEngines, tEngines, pool_pictures,
@@ -870,7 +896,6 @@ extern "C" int hvbenc_create(int device, int bytes_per_sample, int bit_depth, in
         hvbenc_destroy(enc);
         return rc;
     }
-    enc->partition();
     if (const char *v = getenv("HVB_POLLER")) enc->usePoller = atoi(v) != 0;
     if (const char *v = getenv("HVB_POLL_SLEEP_US")) enc->pollSleepUs = atoi(v);
     int nServices = 0; // measured (B200 call 20): a dispatcher thread per engine answers sooner than four threads sweeping eight engines each

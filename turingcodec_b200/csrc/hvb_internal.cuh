@@ -93,6 +93,8 @@ struct hvb_context
     // pools
     void *samplePool = nullptr; // neighbour samples (bps each)
     size_t samplePoolCount = 0;
+    void *slab = nullptr; // hvb_picture_reserve: one allocation the following hvb_picture_create calls carve their planes from
+    size_t slabBytes = 0, slabUsed = 0;
     int16_t *coeffPool = nullptr;
     size_t coeffPoolCount = 0;
     hvb_rdoq_ctx *rdoqCtx = nullptr;
