@@ -558,6 +558,29 @@ def encode_roofline(stats):
                     "construction; hot_path_pass has the same kernels at a whole frame per launch, stream the SAD/SATD kernels against HBM"}
 
 
+def issue_ruler():
+    """The other ruler for a latency-bound kernel: issue slots of the one warp a block's RDOQ walk runs on, from the
+    committed ncu capture of tuFusedKernel -- the kernel behind every transform-block hand-over of the encode (profiles/r02f_tufused_ncu.csv)."""
+    import csv
+    path = ROOT / "profiles" / "r02f_tufused_ncu.csv"
+    if not path.exists():
+        return None
+    rows = list(csv.reader(open(path)))
+    hdr, first = rows[0], rows[2]
+    def val(name):
+        return float(first[hdr.index(name)]) if name in hdr else None
+    issue = val("smsp__issue_active.avg.pct_of_peak_sustained_active")
+    return {"bound": "issue slots of a single warp per scheduler (one block's serial RDOQ walk; 16 dense 32x32 blocks, one warp each)",
+            "kernel": "tuFusedKernel", "achieved": issue / 100.0, "peak": 1.0, "unit": "instructions/cycle/scheduler", "frac": issue / 100.0,
+            "us": val("gpu__time_duration.sum"), "threads_per_instruction": val("smsp__thread_inst_executed_per_inst_executed.ratio"),
+            "stall_cycles_per_issue": {"wait": val("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"),
+                                       "long_scoreboard": val("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"),
+                                       "short_scoreboard": val("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio")},
+            "dram_kbytes": val("dram__bytes_read.sum"), "source": "profiles/r02f_tufused_ncu.csv (ncu --set full --clock-control none, GPU call 23)",
+            "reading": "the walk is a chain of dependent instructions on one thread: a quarter of the issue slots of its scheduler, stalls are "
+                       "fixed-latency waits, DRAM traffic 140 KB -- neither HBM nor issue width bounds it, the dependency chain does"}
+
+
 def reference_encode(args, clip, frames, out_dir, tag, asm, threads=None):
     from turingcodec_b200 import encoder
     opts = ["--asm", str(asm), *encoder_options(args)]
@@ -754,7 +777,7 @@ def main():
                 "dtype": "u8" if args.bit_depth == 8 else "u16", "data": "synthetic",
                 "config": workload_config(args, world, parallel, threads), "host_cores": cores, "cmd": cmd,
                 "parallelism": f"{world} GPU(s), per rank up to {parallel} segments in flight x {threads} pool threads; segments sharded over ranks, no collective",
-                "roofline": encode_roofline(stats), "queue": stats, "e2e": None if args.no_e2e else e2e,
+                "roofline": encode_roofline(stats), "issue_ruler": issue_ruler(), "queue": stats, "e2e": None if args.no_e2e else e2e,
                 "gpu_launches": int(stats.get("kernel_launches", 0)), "clocks": clocks.summary()}
     # ---- identity: one more run on a clip the reference can encode in one go, against --asm 0 --------------------------------------------
     if rank == 0 and world == 1 and not args.no_identity and REFERENCE_ENCODER.exists():
