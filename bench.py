@@ -789,7 +789,7 @@ def main():
                             "reference_asm0_fps": ref0["fps"], "cmd": ref0["cmd"]}
     # ---- the same driver with every hook off (the reference's JIT path in 12 instances): what the segment parallelism alone is worth -----
     if rank == 0 and world == 1 and not args.no_cpu:
-        n = min(frames, 4 * seg)
+        n = frames  # the same job: fewer segments would leave instances idle and flatter the device
         w0, i0, _s, _m, _z, _c = run_segments(args, clip, n, rank_dir, "hostonly", parallel, threads, rank, local, extra_env={"HVB_BATCHED": "0"})
         line["host_only_same_driver"] = {"value": n / i0, "e2e": n / w0, "unit": UNIT, "frames": n,
                                          "note": "turing_b200_segments with HVB_BATCHED=0: no device work at all, the reference's AVX2 path in "
