@@ -229,6 +229,10 @@ typedef struct
 int orc_rdoq(int16_t *dst, const int16_t *src, const orc_rdoq_ctx *ctx, int quantiserScale,
              int quantiserShift, int invQuantScale, int log2n, int cIdx, int scanIdx, int isIntra,
              int sdh, int bitDepth);
+/* the same function with stage 1 computed group by group for every (carry, right, below) and selected afterwards: must equal
+ * orc_rdoq bit for bit -- the decomposition a warp-parallel RDOQ walk rests on (oracle_rdoq.c, DESIGN.md roadmap 0(a)) */
+int orc_rdoq_grouped(int16_t *dst, const int16_t *src, const orc_rdoq_ctx *ctx, int quantiserScale, int quantiserShift, int inverseScale,
+                     int log2TrafoSize, int cIdx, int scanIdx, int isIntra, int sdh, int bitDepth);
 
 /* turing/ScanOrder.h: x (comp 0) / y (comp 1) of scan position `pos` in a (1<<log2)^2 block */
 int orc_scan_order(int log2, int scanIdx, int pos, int comp);

@@ -295,6 +295,82 @@ static void sign_data_hiding(const engine *e, int totalCg, int16_t *dst, const i
 
 static int32_t fixed16(double d) { return (int32_t)(d * 65536 + 0.5); } /* FixedPoint<int32,16>::set(double) */
 
+/* stage 2 (last significant position), signs, sign-data hiding: everything after the level decisions of stage 1 */
+static int rdoq_finish(engine *e, int16_t *dst, const int16_t *src, const orc_rdoq_ctx *ctx, const int *scan, const int *rateUp,
+                       const int *rateDown, const int *sigDelta, const int *deltaU, int log2, int cIdx, int scanIdx, int isIntra, int sdh,
+                       int lastSp, int lastCg, cost_t totalDist0, cost_t rdCostTu)
+{
+    const int n = 1 << (2 * log2), totalCg = n >> 4, log2Cg = log2 - 2;
+    int cbf = 0;
+    if (lastSp >= 0)
+    {
+        /* ---- stage 2: last significant position (Rdoq.cpp:313-397) ---- */
+        cost_t best;
+        int lastIdx = 0;
+        if (!isIntra && cIdx == 0)
+        {
+            best = totalDist0 + lam(e, bits(0, ctx->rqt_root_cbf[0]));
+            rdCostTu += lam(e, bits(1, ctx->rqt_root_cbf[0]));
+        }
+        else
+        {
+            /* getCbfCtxIdx(isLuma, rqtDepth 0): luma 1, chroma 0 (Rdoq.cpp:687-697) */
+            const uint8_t st = cIdx == 0 ? ctx->cbf_luma[1] : ctx->cbf_cbcr[0];
+            best = totalDist0 + lam(e, bits(0, st));
+            rdCostTu += lam(e, bits(1, st));
+        }
+        int found = 0;
+        for (int cg = lastCg; cg >= 0 && !found; --cg)
+        {
+            const int cgX = orc_scan_order(log2Cg, scanIdx, cg, 0), cgY = orc_scan_order(log2Cg, scanIdx, cg, 1);
+            const int cgPos = cgY * (1 << log2Cg) + cgX;
+            rdCostTu -= e->rateCostCgSig[cg];
+            if (!e->csbf[cgPos]) continue;
+            for (int k = 15; k >= 0; --k)
+            {
+                const int sp = cg * 16 + k;
+                if (sp > lastSp) continue;
+                const int pos = scan[sp];
+                if (dst[pos])
+                {
+                    const int x = pos & ((1 << log2) - 1), y = pos >> log2;
+                    const cost_t lastCost = scanIdx == 2 ? last_pos_cost(e, y, x, cIdx, log2) : last_pos_cost(e, x, y, cIdx, log2);
+                    const cost_t total = rdCostTu + lastCost - e->rateCostSig[sp];
+                    if (total < best)
+                    {
+                        lastIdx = sp + 1;
+                        best = total;
+                    }
+                    if (dst[pos] > 1)
+                    {
+                        found = 1;
+                        break;
+                    }
+                    rdCostTu -= e->rdCostCoeff[sp];
+                    rdCostTu += e->distCoeff0[sp];
+                }
+                else
+                    rdCostTu -= e->rateCostSig[sp];
+            }
+        }
+
+        /* signs back, uncoded tail to zero (Rdoq.cpp:414-431) */
+        int absSum = 0;
+        for (int sp = 0; sp < lastIdx; ++sp)
+        {
+            const int pos = scan[sp], level = dst[pos];
+            absSum += level;
+            dst[pos] = (int16_t)(src[pos] < 0 ? -level : level);
+            cbf |= level;
+        }
+        for (int sp = lastIdx; sp <= lastSp; ++sp) dst[scan[sp]] = 0;
+
+        if (sdh && absSum >= 2) sign_data_hiding(e, totalCg, dst, src, scan, rateUp, rateDown, sigDelta, deltaU);
+    }
+
+    return cbf;
+}
+
 int orc_rdoq(int16_t *dst, const int16_t *src, const orc_rdoq_ctx *ctx, int qScale, int qShift, int iqScale,
              int log2, int cIdx, int scanIdx, int isIntra, int sdh, int bitDepth)
 {
@@ -461,73 +537,215 @@ int orc_rdoq(int16_t *dst, const int16_t *src, const orc_rdoq_ctx *ctx, int qSca
         }
     }
 
-    int cbf = 0;
-    if (lastSp >= 0)
+    const int cbf = rdoq_finish(e, dst, src, ctx, scan, rateUp, rateDown, sigDelta, deltaU, log2, cIdx, scanIdx, isIntra, sdh, lastSp, lastCg,
+                                totalDist0, rdCostTu);
+
+    free(scan);
+    free(deltaU);
+    free(sigDelta);
+    free(rateDown);
+    free(rateUp);
+    free(e);
+    return cbf;
+}
+
+/* ---- the same function with stage 1 restructured by coefficient group ---------------------------------------------------
+ * Claim under test (DESIGN.md 1b / roadmap 0(a)): the level decisions of a 4x4 group depend on the rest of the block only through
+ * (1) one bit carried from the previous group in scan order -- whether it ended with a level above 1 (g1Idx == 0 at its last
+ * coefficient, which raises the next group's context set by one) -- and (2) the coded flags of its right and below neighbours
+ * (the significance-context pattern and the coded_sub_block_flag context).  The Rice parameter and the greater-1 / greater-2
+ * counters restart at every group; the running cost only enters comparisons whose two sides contain it alike; all sums are
+ * integers.  So every group can be walked for the 2 x 4 combinations of (carry, neighbour pattern) WITHOUT knowing the others, and
+ * a cheap pass in scan order picks each group's variant and commits it.  orc_rdoq_grouped does exactly that and must equal
+ * orc_rdoq bit for bit (tests/test_oracle_rdoq.py); a device kernel can then spread the walks over the lanes of a warp. */
+typedef struct
+{
+    int16_t level[16];
+    cost_t rdCostCoeff[16], rateCostSig[16];
+    int deltaU[16], sigDelta[16], rateUp[16], rateDown[16];
+    cost_t rdDelta, rateCostCgSig;
+    int coded, carryOut;
+} group_out;
+
+static void group_walk(const engine *base, const int16_t *src, const int *scan, int qScale, int qShift, int log2, int cIdx, int scanIdx,
+                       int cg, int lastSp, int lastCg, int carry, int right, int below, group_out *o)
+{
+    engine *e = (engine *)malloc(sizeof(engine)); /* private copy: adjust_level writes per-position members */
+    memcpy(e, base, sizeof(engine));
+    const orc_rdoq_ctx *ctx = e->cx;
+    const int g1Off = cIdx > 0 ? 16 : 0, g2Off = cIdx > 0 ? 4 : 0;
+    const int prev = right + (below << 1);
+    int ctxSet = ((cg == 0 || cIdx != 0) ? 0 : 2) + carry, g1Idx = 1, g1Cnt = 0, g2Cnt = 0, rice = 0;
+    int nzBeforePos0 = 0, coded = 0;
+    cost_t cgDist0 = 0, cgRateSig = 0, cgRateSigPos0 = 0, cgRdCoeff = 0, rd = 0;
+    memset(o, 0, sizeof(*o));
+    for (int k = 15; k >= 0; --k)
     {
-        /* ---- stage 2: last significant position (Rdoq.cpp:313-397) ---- */
-        cost_t best;
-        int lastIdx = 0;
-        if (!isIntra && cIdx == 0)
+        const int sp = cg * 16 + k, pos = scan[sp];
+        if (sp > lastSp) continue; /* the tail of the last group: accounted for before stage 1 */
+        const int x = pos & ((1 << log2) - 1), y = pos >> log2;
+        const int a = abs(src[pos]);
+        const int scaled = a * qScale;
+        const int q = (scaled + (1 << (qShift - 1))) >> qShift;
+        const int g1Ctx = 4 * ctxSet + g1Idx + g1Off, g2Ctx = ctxSet + g2Off;
+        const int sc = sig_ctx(prev, scanIdx, x, y, log2, cIdx);
+        const int level = adjust_level(e, sp, a, q, sc, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt, sp == lastSp);
+        o->deltaU[k] = (scaled - (level << qShift)) >> (qShift - 8);
+        if (sp != lastSp) o->sigDelta[k] = bits(1, ctx->sig_coeff_flag[sc]) - bits(0, ctx->sig_coeff_flag[sc]);
+        if (level > 0)
         {
-            best = totalDist0 + lam(e, bits(0, ctx->rqt_root_cbf[0]));
-            rdCostTu += lam(e, bits(1, ctx->rqt_root_cbf[0]));
+            const int now = level_rate(e, level, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt);
+            o->rateUp[k] = level_rate(e, level + 1, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt) - now;
+            o->rateDown[k] = level_rate(e, level - 1, g1Ctx, g2Ctx, rice, g1Cnt, g2Cnt) - now;
         }
         else
+            o->rateUp[k] = bits(0, ctx->greater1_flag[g1Ctx]);
+        o->level[k] = (int16_t)level;
+        rd += e->rdCostCoeff[sp];
+        if (level >= base_level(g1Cnt, g2Cnt) && level > 3 * (1 << rice)) rice = rice + 1 > 4 ? 4 : rice + 1;
+        if (level >= 1) g1Cnt++;
+        if (level > 1)
         {
-            /* getCbfCtxIdx(isLuma, rqtDepth 0): luma 1, chroma 0 (Rdoq.cpp:687-697) */
-            const uint8_t st = cIdx == 0 ? ctx->cbf_luma[1] : ctx->cbf_cbcr[0];
-            best = totalDist0 + lam(e, bits(0, st));
-            rdCostTu += lam(e, bits(1, st));
+            g1Idx = 0;
+            g2Cnt++;
         }
-        int found = 0;
-        for (int cg = lastCg; cg >= 0 && !found; --cg)
+        else if (g1Idx < 3 && g1Idx > 0 && level)
+            g1Idx++;
+        if (k == 0) o->carryOut = g1Idx == 0; /* what the reset at a group's last coefficient hands to the next group */
+        cgRateSig += e->rateCostSig[sp];
+        if (k == 0) cgRateSigPos0 = e->rateCostSig[sp];
+        if (level)
         {
-            const int cgX = orc_scan_order(log2Cg, scanIdx, cg, 0), cgY = orc_scan_order(log2Cg, scanIdx, cg, 1);
-            const int cgPos = cgY * (1 << log2Cg) + cgX;
-            rdCostTu -= e->rateCostCgSig[cg];
-            if (!e->csbf[cgPos]) continue;
-            for (int k = 15; k >= 0; --k)
+            coded = 1;
+            cgRdCoeff += e->rdCostCoeff[sp] - e->rateCostSig[sp];
+            cgDist0 += e->distCoeff0[sp];
+            if (k != 0) nzBeforePos0++;
+        }
+    }
+    /* coefficient-group zeroing (Rdoq.cpp:200-304): both sides of its comparison carry the running cost, so it is local */
+    if (cg)
+    {
+        int c = right + below;
+        if (c > 1) c = 1;
+        if (cIdx) c += 2;
+        const cost_t zero = lam(e, bits(0, ctx->coded_sub_block_flag[c]));
+        if (!coded)
+        {
+            rd += zero - cgRateSig;
+            o->rateCostCgSig = zero;
+        }
+        else if (cg < lastCg)
+        {
+            if (nzBeforePos0 == 0)
             {
-                const int sp = cg * 16 + k;
-                if (sp > lastSp) continue;
-                const int pos = scan[sp];
-                if (dst[pos])
-                {
-                    const int x = pos & ((1 << log2) - 1), y = pos >> log2;
-                    const cost_t lastCost = scanIdx == 2 ? last_pos_cost(e, y, x, cIdx, log2) : last_pos_cost(e, x, y, cIdx, log2);
-                    const cost_t total = rdCostTu + lastCost - e->rateCostSig[sp];
-                    if (total < best)
+                rd -= cgRateSigPos0;
+                cgRateSig -= cgRateSigPos0;
+            }
+            const cost_t one = lam(e, bits(1, ctx->coded_sub_block_flag[c]));
+            const cost_t allZero = rd + zero + cgDist0 - cgRdCoeff - cgRateSig;
+            rd += one;
+            o->rateCostCgSig = one;
+            if (allZero < rd)
+            {
+                coded = 0;
+                rd = allZero;
+                o->rateCostCgSig = zero;
+                for (int k = 0; k < 16; ++k)
+                    if (o->level[k])
                     {
-                        lastIdx = sp + 1;
-                        best = total;
+                        const int sp = cg * 16 + k;
+                        o->level[k] = 0;
+                        e->rdCostCoeff[sp] = e->distCoeff0[sp];
+                        e->rateCostSig[sp] = 0;
                     }
-                    if (dst[pos] > 1)
-                    {
-                        found = 1;
-                        break;
-                    }
-                    rdCostTu -= e->rdCostCoeff[sp];
-                    rdCostTu += e->distCoeff0[sp];
-                }
-                else
-                    rdCostTu -= e->rateCostSig[sp];
             }
         }
-
-        /* signs back, uncoded tail to zero (Rdoq.cpp:414-431) */
-        int absSum = 0;
-        for (int sp = 0; sp < lastIdx; ++sp)
-        {
-            const int pos = scan[sp], level = dst[pos];
-            absSum += level;
-            dst[pos] = (int16_t)(src[pos] < 0 ? -level : level);
-            cbf |= level;
-        }
-        for (int sp = lastIdx; sp <= lastSp; ++sp) dst[scan[sp]] = 0;
-
-        if (sdh && absSum >= 2) sign_data_hiding(e, totalCg, dst, src, scan, rateUp, rateDown, sigDelta, deltaU);
     }
+    else
+        coded = 1; /* the DC group is always treated as coded */
+    for (int k = 0; k < 16; ++k)
+    {
+        o->rdCostCoeff[k] = e->rdCostCoeff[cg * 16 + k];
+        o->rateCostSig[k] = e->rateCostSig[cg * 16 + k];
+    }
+    o->rdDelta = rd;
+    o->coded = coded;
+    free(e);
+}
 
+int orc_rdoq_grouped(int16_t *dst, const int16_t *src, const orc_rdoq_ctx *ctx, int qScale, int qShift, int iqScale,
+                     int log2, int cIdx, int scanIdx, int isIntra, int sdh, int bitDepth)
+{
+    const int n = 1 << (2 * log2), totalCg = n >> 4, log2Cg = log2 - 2;
+    engine *e = (engine *)calloc(1, sizeof(engine));
+    int *rateUp = (int *)calloc(n, sizeof(int)), *rateDown = (int *)calloc(n, sizeof(int));
+    int *sigDelta = (int *)calloc(n, sizeof(int)), *deltaU = (int *)calloc(n, sizeof(int));
+    int *scan = (int *)malloc(n * sizeof(int));
+    e->cx = ctx;
+    e->lambda = fixed16(ctx->lambda);
+    e->shdFactor = (int)(iqScale * iqScale / ctx->lambda / 16 + 0.5);
+    {
+        const int transformShift = 15 - bitDepth - log2;
+        const int distShift = 15 - 2 * transformShift - 2 * (bitDepth - 8);
+        e->distScale = fixed16((double)(1 << distShift));
+        e->iqScale = iqScale;
+        e->iqShift = 20 - 14 - transformShift;
+        e->iqOffset = 1 << (e->iqShift - 1);
+    }
+    for (int cg = 0, i = 0; cg < totalCg; ++cg)
+        for (int k = 0; k < 16; ++k)
+        {
+            const int x = (orc_scan_order(log2Cg, scanIdx, cg, 0) << 2) + orc_scan_order(2, scanIdx, k, 0);
+            const int y = (orc_scan_order(log2Cg, scanIdx, cg, 1) << 2) + orc_scan_order(2, scanIdx, k, 1);
+            scan[i++] = (y << log2) + x;
+        }
+    /* before stage 1: rounding levels, the first coded position of the reverse scan, the "all zero" distortion sums */
+    cost_t totalDist0 = 0, rdCostTu = 0;
+    int lastSp = -1;
+    for (int sp = n - 1; sp >= 0; --sp)
+    {
+        const int pos = scan[sp], a = abs(src[pos]);
+        const int q = (a * qScale + (1 << (qShift - 1))) >> qShift;
+        e->distCoeff0[sp] = dist(e, a);
+        totalDist0 += e->distCoeff0[sp];
+        dst[pos] = 0;
+        if (q > 0 && lastSp < 0) lastSp = sp;
+        if (lastSp < 0) rdCostTu += e->distCoeff0[sp];
+    }
+    const int lastCg = lastSp >= 0 ? lastSp >> 4 : -1;
+    /* every group, every (carry, right, below): independent of each other -- this is what a warp would do in parallel */
+    group_out *var = (group_out *)malloc(sizeof(group_out) * 8 * (size_t)(lastCg + 1 > 0 ? lastCg + 1 : 1));
+    for (int cg = 0; cg <= lastCg; ++cg)
+        for (int v = 0; v < 8; ++v)
+            group_walk(e, src, scan, qScale, qShift, log2, cIdx, scanIdx, cg, lastSp, lastCg, v & 1, (v >> 1) & 1, (v >> 2) & 1, &var[cg * 8 + v]);
+    /* in scan order: pick each group's variant by what the groups before it left behind, and commit it */
+    int carry = 0;
+    const int wcg = 1 << log2Cg;
+    for (int cg = lastCg; cg >= 0; --cg)
+    {
+        const int cgX = orc_scan_order(log2Cg, scanIdx, cg, 0), cgY = orc_scan_order(log2Cg, scanIdx, cg, 1);
+        const int right = cgX < wcg - 1 ? e->csbf[cgY * wcg + cgX + 1] : 0, below = cgY < wcg - 1 ? e->csbf[(cgY + 1) * wcg + cgX] : 0;
+        const group_out *o = &var[cg * 8 + (carry | right << 1 | below << 2)];
+        for (int k = 0; k < 16; ++k)
+        {
+            const int sp = cg * 16 + k, pos = scan[sp];
+            if (sp > lastSp) continue;
+            dst[pos] = o->level[k];
+            e->rdCostCoeff[sp] = o->rdCostCoeff[k];
+            e->rateCostSig[sp] = o->rateCostSig[k];
+            deltaU[pos] = o->deltaU[k];
+            sigDelta[pos] = o->sigDelta[k];
+            rateUp[pos] = o->rateUp[k];
+            rateDown[pos] = o->rateDown[k];
+        }
+        rdCostTu += o->rdDelta;
+        e->rateCostCgSig[cg] = o->rateCostCgSig;
+        e->csbf[cgY * wcg + cgX] = o->coded;
+        carry = o->carryOut;
+    }
+    free(var);
+    const int cbf = rdoq_finish(e, dst, src, ctx, scan, rateUp, rateDown, sigDelta, deltaU, log2, cIdx, scanIdx, isIntra, sdh, lastSp, lastCg,
+                                totalDist0, rdCostTu);
     free(scan);
     free(deltaU);
     free(sigDelta);

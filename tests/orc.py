@@ -271,6 +271,11 @@ def oracle_rdoq(oracle: "Oracle", *a):
     return _rdoq(oracle.lib.orc_rdoq, *a)
 
 
+def oracle_rdoq_grouped(oracle: "Oracle", *a):
+    """orc_rdoq with stage 1 decomposed by coefficient group (every (carry, right, below) variant, then a selection pass)"""
+    return _rdoq(oracle.lib.orc_rdoq_grouped, *a)
+
+
 def ref_rdoq(ref: "Ref", *a):
     return _rdoq(ref.lib.ref_rdoq, *a)
 

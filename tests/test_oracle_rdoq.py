@@ -47,6 +47,36 @@ def test_rdoq_matches_reference(oracle, ref_c, bit_depth):
     assert hidden > 5                  # ...and blocks where sign-data hiding changed a level
 
 
+@pytest.mark.parametrize("bit_depth", [8, 10])
+def test_rdoq_decomposes_by_coefficient_group(oracle, bit_depth):
+    """The decomposition a warp-parallel RDOQ walk rests on (DESIGN.md roadmap 0(a)): a 4x4 group's level decisions depend on the rest of
+    the block only through one carried bit and its right / below neighbours' coded flags, so all groups can be walked for the eight
+    combinations independently and selected afterwards.  orc_rdoq_grouped does that and must equal the pinned serial oracle bit for bit."""
+    rng = np.random.default_rng(77 + bit_depth)
+    coded = dense = carried = 0
+    for trial in range(500):
+        log2n = int(rng.integers(2, 6))
+        c_idx = int(rng.integers(0, 3)) if log2n < 5 else 0
+        scan_idx = int(rng.integers(0, 3)) if log2n <= 3 else 0
+        qp = int(rng.integers(8, 40))
+        lam = 0.57 * 2 ** ((qp - 12) / 3.0) * float(rng.uniform(0.5, 2.0))
+        is_intra, sdh = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+        amp = float(rng.choice([2, 6, 20, 60, 200])) * (1 << (bit_depth - 8))
+        src = coefficient_block(oracle, rng, log2n, bit_depth, amp)
+        ctx = orc.random_rdoq_ctx(rng, lam)
+        qscale, qshift, iqscale, _ = orc.quant_params(qp, log2n, bit_depth)
+        a, b = np.zeros_like(src), np.zeros_like(src)
+        args = (src, ctx, qscale, qshift, iqscale, log2n, c_idx, scan_idx, is_intra, sdh, bit_depth)
+        ca = orc.oracle_rdoq(oracle, a, *args)
+        cb = orc.oracle_rdoq_grouped(oracle, b, *args)
+        assert np.array_equal(a, b), (trial, log2n, c_idx, scan_idx, qp, is_intra, sdh)
+        assert ca == cb
+        coded += int(a.any())
+        dense += int(np.count_nonzero(a) > a.size // 4)
+        carried += int((np.abs(a) > 1).sum() > 8)  # many levels above 1: the carried bit is set again and again
+    assert coded > 250 and dense > 40 and carried > 60
+
+
 def test_scan_orders(oracle):
     # turing/ScanOrder.h:32-101: up-right diagonal, horizontal, vertical
     L = oracle.lib
