@@ -80,3 +80,47 @@ def test_call_order_errors(library):
     with pytest.raises(hvb.HvbError):
         ctx.sao_info_upload(pic, np.zeros(1, hvb.sao_ctu_t))
     ctx.close()
+
+
+def test_queue_fast_path_entry_points(library):
+    """hvb_picture_reserve, hvb_host_alloc / hvb_signal, hvb_coeff_pool_wrap / hvb_rdoq_contexts_wrap on the CPU build: what the
+    submission queue's set-up and completion rest on (hvb_encoder.cpp)"""
+    import ctypes as C
+
+    import numpy as np
+    ctx = hvb.Context(0, 1, 8)
+    # a pool of pictures from one allocation: they behave like any picture; destroying one frees nothing and breaks nothing
+    ctx.picture_reserve(64, 32, 16, 3)
+    with pytest.raises(hvb.HvbError):
+        ctx.picture_reserve(64, 32, 16, 3)  # once per context
+    pics = [ctx.picture_create(64, 32, 16) for _ in range(4)]  # the fourth no longer fits the reserve: its own allocation
+    rng = np.random.default_rng(3)
+    for i, pic in enumerate(pics):
+        planes = [rng.integers(0, 256, (32, 64), dtype=np.uint8), rng.integers(0, 256, (16, 32), dtype=np.uint8), rng.integers(0, 256, (16, 32), dtype=np.uint8)]
+        ctx.upload_yuv(pic, *planes)
+        for c in range(3):
+            assert np.array_equal(ctx.picture_download(pic, c, planes[c].shape[1], planes[c].shape[0]), planes[c]), (i, c)
+    ctx.picture_destroy(pics[1])
+    ctx.picture_destroy(pics[3])
+    again = ctx.picture_create(64, 32, 16)
+    ctx.upload_yuv(again, *planes)
+    assert np.array_equal(ctx.picture_download(again, 0, 64, 32), planes[0])
+    # completion flag: stored after the work enqueued before it
+    flag = ctx.host_alloc(64)
+    word = C.c_int32.from_address(flag)
+    word.value = 0
+    ctx.signal(flag, 41)
+    ctx.sync()
+    assert word.value == 41 and ctx.poll() == 1
+    # page-locked arrays in place of the context's device arrays: only memory from host_alloc is taken
+    pool = ctx.host_alloc(2 * 1024 * 4)
+    ctx.coeff_pool_wrap(pool, 1024 * 4)
+    ctx.coeff_pool_wrap(None)
+    ordinary = np.zeros(1024, np.int16)
+    with pytest.raises(hvb.HvbError):
+        ctx.coeff_pool_wrap(ordinary.ctypes.data, ordinary.size)
+    with pytest.raises(hvb.HvbError):
+        ctx.rdoq_contexts_wrap(ordinary.ctypes.data, 4)
+    ctx.host_free(pool)
+    ctx.host_free(flag)
+    ctx.close()

@@ -161,6 +161,13 @@ def load_library() -> C.CDLL:
                  "hvb_sao_batch"):
         if hasattr(lib, name):
             getattr(lib, name).argtypes = [vp, vp, i32, i32]
+    # entry points of the submission queue's fast paths (hvb_encoder.cpp): completion flags, page-locked arrays the kernels address
+    # themselves, one device allocation for a pool of pictures
+    for name, types in (("hvb_host_alloc", [vp, C.c_size_t, C.POINTER(vp)]), ("hvb_host_free", [vp, vp]), ("hvb_signal", [vp, vp, i32]),
+                        ("hvb_poll", [vp]), ("hvb_picture_reserve", [vp, i32, i32, i32, i32]), ("hvb_coeff_pool_wrap", [vp, vp, C.c_size_t]),
+                        ("hvb_rdoq_contexts_wrap", [vp, vp, i32]), ("hvb_set_tu_fused_max", [vp, i32])):
+        if hasattr(lib, name):
+            getattr(lib, name).argtypes = types
     _lib = lib
     return lib
 
@@ -218,6 +225,32 @@ class Context:
 
     def set_tma(self, on: bool):
         self._check(self.lib.hvb_set_tma(self.h, 1 if on else 0), "hvb_set_tma")
+
+    def host_alloc(self, nbytes: int) -> int:
+        """page-locked, device-addressable host memory (address as int); free with host_free"""
+        p = C.c_void_p()
+        self._check(self.lib.hvb_host_alloc(self.h, nbytes, C.byref(p)), "hvb_host_alloc")
+        return p.value
+
+    def host_free(self, address: int):
+        self._check(self.lib.hvb_host_free(self.h, C.c_void_p(address)), "hvb_host_free")
+
+    def signal(self, flag_address: int, value: int):
+        """after everything enqueued so far has completed, `value` is stored to the int32 at flag_address (memory from host_alloc)"""
+        self._check(self.lib.hvb_signal(self.h, C.c_void_p(flag_address), int(value)), "hvb_signal")
+
+    def poll(self) -> int:
+        return self.lib.hvb_poll(self.h)
+
+    def picture_reserve(self, width: int, height: int, pad: int, count: int):
+        """one device allocation for the planes of the next `count` pictures of this geometry"""
+        self._check(self.lib.hvb_picture_reserve(self.h, width, height, pad, count), "hvb_picture_reserve")
+
+    def coeff_pool_wrap(self, address: int | None, count: int = 0):
+        self._check(self.lib.hvb_coeff_pool_wrap(self.h, C.c_void_p(address or 0), count), "hvb_coeff_pool_wrap")
+
+    def rdoq_contexts_wrap(self, address: int | None, count: int = 0):
+        self._check(self.lib.hvb_rdoq_contexts_wrap(self.h, C.c_void_p(address or 0), count), "hvb_rdoq_contexts_wrap")
 
     def set_tu_fused_max(self, blocks: int):
         """batches of at most `blocks` transform blocks take the one-launch form of tu_chain (0: always the staged kernels)"""
